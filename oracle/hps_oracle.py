@@ -1,0 +1,321 @@
+"""NumPy FP64 restatement of the reference's HPS hot path (CPU oracle).
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs
+may import it; the ``jaxhps_b200`` package never does (its CUDA path fails loudly when
+the extension is missing — there is no CPU fallback).
+
+What it restates (all paths relative to /root/reference/src/jaxhps):
+
+* leaf operator assembly and the DtN / ItI local solve:
+  ``local_solve/_uniform_2D_DtN.py:105-280``, ``local_solve/_uniform_3D_DtN.py:13-145``,
+  ``local_solve/_uniform_2D_ItI.py:120-193``;
+* the oct / quad Schur-complement merges with explicit inverses and dense B, C, D:
+  ``merge/_uniform_3D_DtN.py:12-541``, ``merge/_schur_complement.py:78-237,293-774``,
+  ``merge/_uniform_2D_DtN.py:13-475``, ``merge/_uniform_2D_ItI.py:19-405``;
+* the downward pass: ``down_pass/_uniform_3D_DtN.py:8-251``,
+  ``down_pass/_uniform_2D_DtN.py:7-194``, ``down_pass/_uniform_2D_ItI.py:8-197``.
+
+Third-party arithmetic: the reference's ``jnp.linalg.inv`` / ``@`` live in jax/jaxlib
+(unpinned ``jax>=0.4``, absent from this image); here they are ``numpy.linalg.inv`` and
+``@`` (LAPACK getrf+getri / OpenBLAS).
+
+Pinning: JAX cannot be installed here, so the reference is executed through the NumPy
+``jax`` shim in ``tests/golden/jaxshim`` (the reference's own Python — index maps, block
+assembly, stage loops — with NumPy arithmetic).  ``tests/golden/make_golden.py`` freezes
+those outputs as fixtures and ``tests/test_oracle_golden.py`` checks this file against
+them; the 2D analytic known-answer cases of the reference test-suite
+(``tests/test_accuracy/cases.py``) are restated in ``tests/test_oracle_analytic.py``.
+
+The tree topology below is derived from the children's geometric positions rather than
+written as the reference's literal index lists, so that it is an independent check of the
+hand-written tables the CUDA path uses.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+# =====================================================================================
+# Leaf level
+# =====================================================================================
+
+_COEFF_ORDER_3D = ("D_xx", "D_xy", "D_yy", "D_xz", "D_yz", "D_zz", "D_x", "D_y", "D_z", "I")
+_COEFF_ORDER_2D = ("D_xx", "D_xy", "D_yy", "D_x", "D_y", "I")
+
+
+def gather_coeffs(pde_problem, order: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
+    """Stack the non-None coefficient arrays in the fixed order and say which were given
+    (``_gather_coeffs_3D`` `_uniform_3D_DtN.py:109-145`; ``_gather_coeffs_2D``
+    `_uniform_2D_DtN.py:105-133`)."""
+    arrs = [getattr(pde_problem, f"{name}_coefficients", None) for name in order]
+    which = np.array([a is not None for a in arrs])
+    return np.array([np.asarray(a) for a in arrs if a is not None]), which
+
+
+def assemble_diff_operator(coeffs: np.ndarray, which: np.ndarray, diff_ops: Sequence[np.ndarray]) -> np.ndarray:
+    """``A = sum_k diag(c_k) D_k`` over the coefficients that were given; dtype follows the
+    coefficients (`_uniform_2D_DtN.py:182-218`)."""
+    out = np.zeros(diff_ops[0].shape, dtype=coeffs.dtype)
+    counter = 0
+    for k, present in enumerate(which):
+        if present:
+            out = out + diff_ops[k] * coeffs[counter][:, None]
+            counter += 1
+    return out
+
+
+def get_DtN(source: np.ndarray, A: np.ndarray, Q: np.ndarray, P: np.ndarray):
+    """One leaf: explicit interior inverse, then Y, T, v, h (`_uniform_2D_DtN.py:228-273`)."""
+    nb = P.shape[0]
+    A_ii_inv = np.linalg.inv(A[nb:, nb:])
+    A_ie = A[nb:, :nb]
+    L2 = np.zeros((A.shape[0], nb), dtype=A.dtype)
+    L2[:nb] = np.eye(nb)
+    L2[nb:] = -1 * A_ii_inv @ A_ie
+    Y = L2 @ P
+    T = Q @ Y
+    v = np.zeros((A.shape[0], source.shape[-1]), dtype=A.dtype)
+    v[nb:] = A_ii_inv @ source[nb:]
+    h = Q @ v
+    return Y, T, v, h
+
+
+def get_ItI(source: np.ndarray, A: np.ndarray, P: np.ndarray, QH: np.ndarray, G: np.ndarray):
+    """One leaf, impedance formulation: ``B = [G; A_interior_rows]`` inverted whole
+    (`_uniform_2D_ItI.py:120-186`).  Returns (R, Y, h, v) like the reference's ``get_ItI``."""
+    nb = P.shape[0]
+    B = np.concatenate([G, A[nb:].astype(np.complex128)], axis=0)
+    B_inv = np.linalg.inv(B)
+    Y = B_inv[:, :nb] @ P
+    Phi = B_inv[:, nb:]
+    v = Phi @ source[nb:]
+    h = QH @ v
+    R = QH @ Y
+    return R, Y, h, v
+
+
+def _leaf_operators(pde_problem, order):
+    eye = np.eye(pde_problem.D_x.shape[0])
+    return [eye if name == "I" else getattr(pde_problem, name) for name in order]
+
+
+def local_solve_stage_uniform_3D_DtN(pde_problem):
+    """(Y, T, v, h) for every leaf (`local_solve/_uniform_3D_DtN.py:13-106`)."""
+    return _local_solve_DtN(pde_problem, _COEFF_ORDER_3D)
+
+
+def local_solve_stage_uniform_2D_DtN(pde_problem):
+    """(Y, T, v, h) for every leaf (`local_solve/_uniform_2D_DtN.py:9-102`)."""
+    return _local_solve_DtN(pde_problem, _COEFF_ORDER_2D)
+
+
+def _local_solve_DtN(pde_problem, order):
+    coeffs, which = gather_coeffs(pde_problem, order)
+    ops = _leaf_operators(pde_problem, order)
+    src = np.asarray(pde_problem.source)
+    multi = src.ndim == 3
+    if not multi:
+        src = src[..., None]
+    Ys, Ts, vs, hs = [], [], [], []
+    for leaf in range(src.shape[0]):
+        A = assemble_diff_operator(coeffs[:, leaf], which, ops)
+        Y, T, v, h = get_DtN(src[leaf], A, pde_problem.Q, pde_problem.P)
+        Ys.append(Y), Ts.append(T), vs.append(v), hs.append(h)
+    Y, T, v, h = (np.stack(x) for x in (Ys, Ts, vs, hs))
+    if not multi:
+        v, h = v[..., 0], h[..., 0]
+    return Y, T, v, h
+
+
+def local_solve_stage_uniform_2D_ItI(pde_problem):
+    """(Y, R, v, h), complex128 (`local_solve/_uniform_2D_ItI.py:10-117`)."""
+    coeffs, which = gather_coeffs(pde_problem, _COEFF_ORDER_2D)
+    ops = _leaf_operators(pde_problem, _COEFF_ORDER_2D)
+    src = np.asarray(pde_problem.source)
+    multi = src.ndim == 3
+    if not multi:
+        src = src[..., None]
+    Rs, Ys, hs, vs = [], [], [], []
+    for leaf in range(src.shape[0]):
+        A = assemble_diff_operator(coeffs[:, leaf], which, ops)
+        R, Y, h, v = get_ItI(src[leaf], A, pde_problem.P, pde_problem.QH, pde_problem.G)
+        Rs.append(R), Ys.append(Y), hs.append(h), vs.append(v)
+    R, Y, h, v = (np.stack(x) for x in (Rs, Ys, hs, vs))
+    if not multi:
+        v, h = v[..., 0], h[..., 0]
+    return Y, R, v, h
+
+
+# =====================================================================================
+# Schur complement core (`merge/_schur_complement.py:117-147, 182-237`)
+# =====================================================================================
+
+
+def assemble_merge_outputs(A_lst, B, C, D_inv, h_ext, h_int):
+    """``S=-D^-1 C``, ``T=A (+) B S``, ``g~=-D^-1 h_int``, ``h=h_ext+B g~``."""
+    S = -1 * D_inv @ C
+    T = B @ S
+    at = 0
+    for A in A_lst:
+        n = A.shape[0]
+        T[at : at + n, at : at + n] += A
+        at += n
+    g_tilde = -1 * D_inv @ h_int
+    h_out = h_ext + B @ g_tilde
+    return T, S, h_out, g_tilde
+
+
+# =====================================================================================
+# 3D oct merge.  Children a..h sit at (ix,iy,iz); faces 0..5 = x-,x+,y-,y+,z-,z+.
+# =====================================================================================
+
+_OCT_POS = [(0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1), (0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0)]
+# interface order of the interior unknowns: 9:a|b 10:b|c 11:c|d 12:d|a 13:e|f 14:f|g
+# 15:g|h 16:h|e 17:a|e 18:b|f 19:c|g 20:d|h (`merge/_uniform_3D_DtN.py:238-380`)
+_OCT_INTERFACES = [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7)]
+
+
+def _oct_face_roles():
+    """roles[child][face] = ("ext", None) or ("int", interface slot 0..11)."""
+    roles = []
+    for c, pos in enumerate(_OCT_POS):
+        r = []
+        for face in range(6):
+            axis, side = divmod(face, 2)
+            if pos[axis] == side:
+                r.append(("ext", None))
+            else:
+                nb_pos = list(pos)
+                nb_pos[axis] = side
+                nb = _OCT_POS.index(tuple(nb_pos))
+                slot = [i for i, pr in enumerate(_OCT_INTERFACES) if set(pr) == {c, nb}][0]
+                r.append(("int", slot))
+        roles.append(r)
+    return roles
+
+
+def _oct_parent_face_children():
+    """For each parent face, the four children touching it in quad-recursion order
+    SW,SE,NE,NW of the face's two free coordinates (`merge/_uniform_3D_DtN.py:507-541`)."""
+    out = []
+    for face in range(6):
+        axis, side = divmod(face, 2)
+        free = [a for a in range(3) if a != axis]
+        order = []
+        for u, v in ((0, 0), (1, 0), (1, 1), (0, 1)):
+            pos = [0, 0, 0]
+            pos[axis] = side
+            pos[free[0]], pos[free[1]] = u, v
+            order.append(_OCT_POS.index(tuple(pos)))
+        out.append(order)
+    return out
+
+
+_OCT_ROLES = _oct_face_roles()
+_OCT_FACE_CHILDREN = _oct_parent_face_children()
+
+
+def uniform_oct_merge_DtN(T_children: np.ndarray, h_children: np.ndarray):
+    """One oct merge as the reference performs it: dense B (24m x 12m), C, D assembled from
+    the children's face blocks, explicit ``inv(D)``, then the region->face permutation
+    (`merge/_uniform_3D_DtN.py:127-187`, `_schur_complement.py:293-774`).
+
+    T_children (8, 6m, 6m); h_children (8, 6m[, n_src]).  Returns (S, T, h_out, g_tilde)."""
+    m = T_children.shape[-1] // 6
+    tail = h_children.shape[2:]
+    B = np.zeros((24 * m, 12 * m))
+    C = np.zeros((12 * m, 24 * m))
+    D = np.zeros((12 * m, 12 * m))
+    h_int = np.zeros((12 * m,) + tail)
+    h_ext = np.zeros((24 * m,) + tail)
+    A_lst = []
+    fs = lambda f: slice(f * m, (f + 1) * m)  # noqa: E731
+    for c in range(8):
+        T, h = T_children[c], h_children[c]
+        ext_faces = [f for f in range(6) if _OCT_ROLES[c][f][0] == "ext"]
+        int_faces = [f for f in range(6) if _OCT_ROLES[c][f][0] == "int"]
+        ext_slot = {f: 3 * c + i for i, f in enumerate(ext_faces)}
+        int_slot = {f: _OCT_ROLES[c][f][1] for f in int_faces}
+        ext_idx = np.concatenate([np.arange(f * m, (f + 1) * m) for f in ext_faces])
+        A_lst.append(T[np.ix_(ext_idx, ext_idx)])
+        for f in ext_faces:
+            h_ext[fs(ext_slot[f])] = h[fs(f)]
+            for g in int_faces:
+                B[fs(ext_slot[f]), fs(int_slot[g])] = T[fs(f), fs(g)]
+                C[fs(int_slot[g]), fs(ext_slot[f])] = T[fs(g), fs(f)]
+        for f in int_faces:
+            h_int[fs(int_slot[f])] += h[fs(f)]
+            for g in int_faces:
+                D[fs(int_slot[f]), fs(int_slot[g])] += T[fs(f), fs(g)]
+    D_inv = np.linalg.inv(D)
+    T, S, h_out, g_tilde = assemble_merge_outputs(A_lst, B, C, D_inv, h_ext, h_int)
+    r = oct_region_to_face_permutation(m)
+    return S[:, r], T[np.ix_(r, r)], h_out[r], g_tilde
+
+
+def oct_region_to_face_permutation(m: int) -> np.ndarray:
+    """Index vector turning [child a ext faces, ..., child h ext faces] into
+    [face 0 panels, ..., face 5 panels] (`merge/_uniform_3D_DtN.py:443-541`)."""
+    out = []
+    for face in range(6):
+        for c in _OCT_FACE_CHILDREN[face]:
+            ext_faces = [f for f in range(6) if _OCT_ROLES[c][f][0] == "ext"]
+            slot = 3 * c + ext_faces.index(face)
+            out.append(np.arange(slot * m, (slot + 1) * m))
+    return np.concatenate(out)
+
+
+def merge_stage_uniform_3D_DtN(T_arr: np.ndarray, h_arr: np.ndarray, l: int, return_T: bool = False):
+    """Level loop (`merge/_uniform_3D_DtN.py:12-124`).  ``S_lst``/``g_tilde_lst`` run from
+    the level above the leaves to the root; the root entries carry no batch axis."""
+    S_lst: List[np.ndarray] = []
+    g_lst: List[np.ndarray] = []
+    for _ in range(l - 1, 0, -1):
+        n = T_arr.shape[0] // 8
+        outs = [uniform_oct_merge_DtN(T_arr[8 * i : 8 * i + 8], h_arr[8 * i : 8 * i + 8]) for i in range(n)]
+        S_lst.append(np.stack([o[0] for o in outs]))
+        T_arr = np.stack([o[1] for o in outs])
+        h_arr = np.stack([o[2] for o in outs])
+        g_lst.append(np.stack([o[3] for o in outs]))
+    S, T, h, g = uniform_oct_merge_DtN(T_arr[:8], h_arr[:8])
+    S_lst.append(S)
+    g_lst.append(g)
+    if return_T:
+        return S_lst, g_lst, T
+    return S_lst, g_lst
+
+
+def propagate_down_oct_DtN(S: np.ndarray, g_ext: np.ndarray, g_tilde: np.ndarray) -> np.ndarray:
+    """(8, 6m[, n_src]) child boundary data from the parent's (`down_pass/_uniform_3D_DtN.py:116-246`)."""
+    m = g_ext.shape[0] // 24
+    g_int = S @ g_ext + g_tilde
+    kids = []
+    for c in range(8):
+        parts = []
+        for face in range(6):
+            kind, slot = _OCT_ROLES[c][face]
+            if kind == "int":
+                parts.append(g_int[slot * m : (slot + 1) * m])
+            else:
+                panel = _OCT_FACE_CHILDREN[face].index(c)
+                at = face * 4 * m + panel * m
+                parts.append(g_ext[at : at + m])
+        kids.append(np.concatenate(parts))
+    return np.stack(kids)
+
+
+def down_pass_uniform_3D_DtN(boundary_data, S_lst, g_tilde_lst, Y_arr, v_arr):
+    """Top-down sweep then ``u = Y g + v`` on every leaf (`down_pass/_uniform_3D_DtN.py:8-113`)."""
+    S_lst = list(S_lst)
+    g_tilde_lst = list(g_tilde_lst)
+    S_lst[-1] = S_lst[-1][None]
+    g_tilde_lst[-1] = g_tilde_lst[-1][None]
+    bdry = np.asarray(boundary_data)[None]
+    for level in range(len(S_lst) - 1, -1, -1):
+        kids = [propagate_down_oct_DtN(S_lst[level][i], bdry[i], g_tilde_lst[level][i]) for i in range(bdry.shape[0])]
+        bdry = np.concatenate(kids, axis=0)
+    if bdry.ndim == 3:
+        return np.einsum("ijk,ikl->ijl", Y_arr, bdry) + v_arr
+    return np.einsum("ijk,ik->ij", Y_arr, bdry) + v_arr
