@@ -1,0 +1,113 @@
+/*
+ * hps_b200.h — C ABI of libhps_b200.so: the B200 (sm_100a) implementation of the HPS
+ * build+solve hot path of meliao/jaxhps.
+ *
+ * The reference has no FFI of its own (it is pure Python on JAX); the seam this library
+ * plugs into is the set of *stage functions* selected by `build_solver` / `solve`
+ * (reference: src/jaxhps/_build_solver.py:102-114, src/jaxhps/_solve.py:77-83).  Each
+ * entry point below replaces the device-side body of one of them; the Python shims in
+ * jaxhps_b200/ keep the reference's signatures and call these through ctypes, and a
+ * jax.ffi handler would wrap the same symbols one-to-one.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless said otherwise;
+ *   - all matrices are row-major (C-contiguous), FP64;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it and
+ *     performs no host synchronisation;
+ *   - the library never allocates device memory: callers pass workspaces whose size comes
+ *     from the matching *_workspace query;
+ *   - return value: 0 = ok, <0 = argument error (-k: k-th argument), >0 = cudaError_t;
+ *     hps_last_error_string() describes the last failure on the calling thread;
+ *   - `info` (device int[batch]) follows LAPACK: 0 = ok, k>0 = exact zero pivot met at
+ *     column k of that matrix.  It is written on the stream; the caller reads it back.
+ */
+#ifndef HPS_B200_H
+#define HPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- diagnostics ---------------------------------------------------------------- */
+int hps_version(void);
+const char* hps_last_error_string(void);
+
+/* ---- dense building blocks (exported for tests, benches and the jax.ffi shim) ------
+ * C[b] = alpha * A[b] (MxK) * B[b] (KxN) + beta * C[b], b < batch, element strides sX.
+ * FP64 tensor-core (DMMA) kernel.  Replaces the XLA dot_general calls on the path
+ * (e.g. merge/_schur_complement.py:222-235, local_solve/_uniform_2D_DtN.py:264-271). */
+int hps_dgemm_strided_batched(void* stream, int M, int N, int K, double alpha,
+                              const double* A, int64_t lda, int64_t sA,
+                              const double* B, int64_t ldb, int64_t sB, double beta,
+                              double* C, int64_t ldc, int64_t sC, int batch);
+
+/* Batched LU with partial pivoting of A[b] (n x n) followed by the in-place solve
+ * rhs_k[b] := A[b]^-1 rhs_k[b] for up to 4 right-hand-side matrices (n x ncols[k]).
+ * A is overwritten (U in the upper triangle).  Replaces the `jnp.linalg.inv` + matmul
+ * pairs of the reference (local_solve/_uniform_2D_DtN.py:257-259,
+ * merge/_schur_complement.py:146,222,234). */
+int hps_lu_solve_workspace(int batch, int n, size_t* bytes);
+int hps_lu_solve(void* stream, int batch, int n, double* A, int64_t lda, int64_t sA,
+                 int n_rhs, double* const* rhs, const int64_t* ld_rhs, const int64_t* s_rhs,
+                 const int* ncols, void* ws, size_t ws_bytes, int* info);
+
+/* ---- local_solve_stage (reference: local_solve/_uniform_3D_DtN.py:13-106,
+ *      local_solve/_uniform_2D_DtN.py:9-102 + get_DtN :228-273) -------------------------
+ * dim = 2 or 3.  n_c = p^dim, n_i = (p-2)^dim, n_b = n_c - n_i, n_g = 2*dim*q^(dim-1).
+ * which[k] != 0 says coefficient k of the fixed order
+ *   3D: [xx,xy,yy,xz,yz,zz,x,y,z,I]   2D: [xx,xy,yy,x,y,I]
+ * is present; coeffs holds the present ones, [n_coef][n_leaves][n_c] in leaf ordering.
+ * D1: [p][p] 1-D Chebyshev differentiation matrix already divided by the half side
+ * length; P [n_b][n_g]; Q [n_g][n_c]; src [n_leaves][n_c][n_src].
+ * Outputs: Y [n_leaves][n_c][n_g], T [n_leaves][n_g][n_g], v [n_leaves][n_c][n_src],
+ * h [n_leaves][n_g][n_src]. */
+int hps_local_solve_dtn_workspace(int dim, int n_leaves, int p, int q, int n_src, size_t* bytes);
+int hps_local_solve_dtn(void* stream, int dim, int n_leaves, int p, int q, int n_src,
+                        const uint8_t* which /* host */, const double* coeffs,
+                        const double* D1, const double* P, const double* Q, const double* src,
+                        double* Y, double* T, double* v, double* h,
+                        void* ws, size_t ws_bytes, int* info);
+
+/* ---- merge_stage, one tree level per call (reference: merge/_uniform_3D_DtN.py:127-234,
+ *      merge/_schur_complement.py:293-774,117-147,182-237) -----------------------------
+ * T_in [8*n_merges][6m][6m], h_in [8*n_merges][6m][n_src]; children in a..h order.
+ * S [n_merges][12m][24m], g_tilde [n_merges][12m][n_src],
+ * T_out [n_merges][24m][24m] and h_out [n_merges][24m][n_src] (face-ordered, i.e. already
+ * permuted by the reference's get_rearrange_indices).  want_T = 0 skips T_out/h_out. */
+int hps_merge_oct_dtn_level_workspace(int n_merges, int m, int n_src, size_t* bytes);
+int hps_merge_oct_dtn_level(void* stream, int n_merges, int m, int n_src,
+                            const double* T_in, const double* h_in,
+                            double* S, double* g_tilde, double* T_out, double* h_out,
+                            int want_T, void* ws, size_t ws_bytes, int* info);
+
+/* 2D quad merge, DtN (reference: merge/_uniform_2D_DtN.py:206-348).
+ * T_in [4*n_merges][4m][4m] (children SW,SE,NE,NW; sides S,E,N,W), S [n][4m][8m],
+ * T_out [n][8m][8m]. */
+int hps_merge_quad_dtn_level_workspace(int n_merges, int m, int n_src, size_t* bytes);
+int hps_merge_quad_dtn_level(void* stream, int n_merges, int m, int n_src,
+                             const double* T_in, const double* h_in,
+                             double* S, double* g_tilde, double* T_out, double* h_out,
+                             int want_T, void* ws, size_t ws_bytes, int* info);
+
+/* ---- down_pass (reference: down_pass/_uniform_3D_DtN.py:116-246,
+ *      down_pass/_uniform_2D_DtN.py:125-189) -------------------------------------------
+ * One level: g_int = S g_ext + g_tilde, then the children's boundary vectors.
+ * g_ext [n_nodes][24m][n_src] -> g_children [n_nodes][8][6m][n_src] (3D)
+ * g_ext [n_nodes][8m][n_src]  -> g_children [n_nodes][4][4m][n_src] (2D).
+ * ws: n_nodes * n_int * n_src doubles. */
+int hps_down_oct_level(void* stream, int n_nodes, int m, int n_src, const double* S,
+                       const double* g_ext, const double* g_tilde, double* g_children, void* ws);
+int hps_down_quad_level(void* stream, int n_nodes, int m, int n_src, const double* S,
+                        const double* g_ext, const double* g_tilde, double* g_children, void* ws);
+
+/* Leaf evaluation u = Y g + v (reference: down_pass/_uniform_3D_DtN.py:104-111). */
+int hps_leaf_apply(void* stream, int n_leaves, int n_c, int n_g, int n_src,
+                   const double* Y, const double* g, const double* v, double* u);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPS_B200_H */

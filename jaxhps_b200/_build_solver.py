@@ -1,0 +1,44 @@
+"""``build_solver``: dispatch + result stashing, mirroring `src/jaxhps/_build_solver.py:38-171`.
+
+The reference loops over leaf chunks on the host because its assembled operators do not
+fit on an 80 GB device; here the chunking lives inside the local-solve stage (bounded scratch),
+so the driver is a straight line."""
+from __future__ import annotations
+
+from ._pdeproblem import PDEProblem
+from .local_solve import local_solve_stage_uniform_2D_DtN, local_solve_stage_uniform_3D_DtN
+from .merge import merge_stage_uniform_2D_DtN, merge_stage_uniform_3D_DtN
+
+
+def build_solver(pde_problem: PDEProblem, return_top_T: bool = False, compute_device=None, host_device=None):
+    """Run the local solves and all merges; store ``Y, v, S_lst, g_tilde_lst`` on the problem.
+
+    ``compute_device``: CUDA device (default: current).  ``host_device``: where the stored
+    operators live — ``None``/"cpu" copies them to host NumPy arrays like the reference's
+    default; a CUDA device keeps them resident (recommended: ``solve`` then moves nothing).
+    Returns the top-level Poincaré–Steklov matrix when ``return_top_T`` is set."""
+    if pde_problem.source is None:
+        raise NotImplementedError(
+            "building without a source (up-pass formulation, reference `_build_solver.py:261-331`) "
+            "is not part of the hot path built so far"
+        )
+    if not pde_problem.domain.bool_uniform:
+        raise NotImplementedError("adaptive discretisations are outside the hot path built so far")
+    if pde_problem.use_ItI:
+        raise NotImplementedError("2D ItI merges run on the oracle only so far; the CUDA path covers DtN")
+    if pde_problem.domain.bool_2D:
+        Y, T, v, h = local_solve_stage_uniform_2D_DtN(pde_problem, device=compute_device, host_device=compute_device)
+        merge_fn = merge_stage_uniform_2D_DtN
+    else:
+        Y, T, v, h = local_solve_stage_uniform_3D_DtN(pde_problem, device=compute_device, host_device=compute_device)
+        merge_fn = merge_stage_uniform_3D_DtN
+    from . import _lib
+
+    pde_problem.Y = _lib.to_result(Y, host_device)
+    pde_problem.v = _lib.to_result(v, host_device)
+    out = merge_fn(T, h, l=pde_problem.domain.L, device=compute_device, host_device=host_device, return_T=return_top_T)
+    pde_problem.S_lst = out[0]
+    pde_problem.g_tilde_lst = out[1]
+    if return_top_T:
+        return out[2]
+    return None

@@ -1,0 +1,154 @@
+"""ctypes binding of ``libhps_b200.so`` (C ABI in ``include/hps_b200.h``).
+
+PyTorch is used only as the device-memory / stream provider: tensors are allocated with
+``torch.empty(..., device="cuda")`` and handed to the library as raw pointers together with
+the current CUDA stream.  There is NO CPU fallback: if the shared library is missing or no
+CUDA device is present, every stage function raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhps_b200.so")
+_lib: Optional[ctypes.CDLL] = None
+
+_i = ctypes.c_int
+_l = ctypes.c_int64
+_d = ctypes.c_double
+_p = ctypes.c_void_p
+_sz = ctypes.c_size_t
+
+_SIGNATURES = {
+    "hps_version": (_i, []),
+    "hps_last_error_string": (ctypes.c_char_p, []),
+    "hps_dgemm_strided_batched": (_i, [_p, _i, _i, _i, _d, _p, _l, _l, _p, _l, _l, _d, _p, _l, _l, _i]),
+    "hps_lu_solve_workspace": (_i, [_i, _i, ctypes.POINTER(_sz)]),
+    "hps_lu_solve": (_i, [_p, _i, _i, _p, _l, _l, _i, ctypes.POINTER(_p), ctypes.POINTER(_l),
+                          ctypes.POINTER(_l), ctypes.POINTER(_i), _p, _sz, _p]),
+    "hps_local_solve_dtn_workspace": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(_sz)]),
+    "hps_local_solve_dtn": (_i, [_p, _i, _i, _i, _i, _i, ctypes.c_char_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "hps_merge_oct_dtn_level_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),
+    "hps_merge_oct_dtn_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "hps_merge_quad_dtn_level_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),
+    "hps_merge_quad_dtn_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "hps_down_oct_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "hps_down_quad_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "hps_leaf_apply": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class HpsLibraryError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Fails loudly; never falls back to a CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise HpsLibraryError(
+                f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  jaxhps_b200 has no CPU fallback."
+            )
+        lib = ctypes.CDLL(_LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().hps_last_error_string().decode(errors="replace")
+        raise HpsLibraryError(f"{what} failed with code {rc}: {msg}")
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise HpsLibraryError(
+            "jaxhps_b200 runs its hot path as CUDA kernels only; no CUDA device is visible "
+            "(there is no CPU fallback — use the oracle under oracle/ for CPU checks)."
+        )
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise HpsLibraryError(f"compute device must be a CUDA device, got {dev}")
+    return dev
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def is_host(host_device) -> bool:
+    """``host_device`` follows the reference's meaning: where results are returned.  ``None`` or
+    ``"cpu"`` -> NumPy arrays on the host; a CUDA device -> results stay resident as torch tensors."""
+    if host_device is None:
+        return True
+    return torch.device(host_device).type == "cpu"
+
+
+def to_device(x, dev: torch.device, dtype=torch.float64) -> torch.Tensor:
+    """NumPy / torch (any device) -> contiguous tensor on ``dev``; host arrays go through pinned memory."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if t.device != dev:
+        if t.device.type == "cpu" and t.numel() > 1 << 16:
+            t = t.contiguous().pin_memory()
+        t = t.to(dev, non_blocking=True)
+    return t.contiguous()
+
+
+def to_result(t: torch.Tensor, host_device):
+    """Device tensor -> what the caller asked for (NumPy on the host, or the tensor itself)."""
+    if is_host(host_device):
+        return t.cpu().numpy()
+    dev = torch.device(host_device)
+    return t if t.device == dev else t.to(dev)
+
+
+class Workspace:
+    """Grow-only device scratch buffer handed to the library (which never allocates)."""
+
+    def __init__(self):
+        self._buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int, dev: torch.device) -> torch.Tensor:
+        if self._buf is None or self._buf.numel() < nbytes or self._buf.device != dev:
+            self._buf = None
+            self._buf = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        return self._buf
+
+    def release(self):
+        self._buf = None
+
+
+WORKSPACE = Workspace()
+
+
+def check_info(info: torch.Tensor, what: str) -> None:
+    """LAPACK-style singularity report (one host sync; the stages call it once per level)."""
+    bad = torch.nonzero(info)
+    if bad.numel():
+        k = int(bad[0, 0])
+        raise np.linalg.LinAlgError(f"{what}: exact zero pivot in matrix {k} at column {int(info[k])}")

@@ -1,0 +1,32 @@
+"""``solve``: mirror of `src/jaxhps/_solve.py:18-93` for uniform DtN problems."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._pdeproblem import PDEProblem
+from .down_pass import down_pass_uniform_2D_DtN, down_pass_uniform_3D_DtN
+
+
+def solve(pde_problem: PDEProblem, boundary_data, source=None, compute_device=None, host_device=None):
+    """Downward pass with the operators stored by :func:`build_solver`.  Returns the solution on
+    the HPS grid, shape ``(n_leaves, p^d[, n_src])``."""
+    if source is not None:
+        if not pde_problem.domain.bool_2D or not pde_problem.domain.bool_uniform:
+            raise ValueError(
+                "Source can only be specified for 2D uniform ItI problems. For other problems, the source must "
+                "be specified at the time the solver is built."
+            )
+        raise NotImplementedError("solve-time sources (up pass) are not part of the hot path built so far")
+    if not pde_problem.domain.bool_uniform:
+        raise NotImplementedError("adaptive discretisations are outside the hot path built so far")
+    if isinstance(boundary_data, list):
+        if all(isinstance(b, torch.Tensor) for b in boundary_data):
+            boundary_data = torch.cat(boundary_data)
+        else:
+            boundary_data = np.concatenate([np.asarray(b) for b in boundary_data])
+    if pde_problem.use_ItI:
+        raise NotImplementedError("2D ItI down pass runs on the oracle only so far")
+    down = down_pass_uniform_2D_DtN if pde_problem.domain.bool_2D else down_pass_uniform_3D_DtN
+    return down(boundary_data, pde_problem.S_lst, pde_problem.g_tilde_lst, pde_problem.Y, pde_problem.v,
+                device=compute_device, host_device=host_device)

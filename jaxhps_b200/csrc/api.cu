@@ -1,0 +1,107 @@
+// extern "C" surface of libhps_b200.so (declared in include/hps_b200.h).
+#include "../../include/hps_b200.h"
+
+#include "common.cuh"
+
+namespace hps {
+std::string& last_error() {
+  static thread_local std::string s;
+  return s;
+}
+int fail_arg(int which, const char* what) {
+  last_error() = std::string("argument error: ") + what;
+  return -which;
+}
+int fail_cuda(cudaError_t e, const char* where) {
+  last_error() = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + where;
+  return static_cast<int>(e);
+}
+}  // namespace hps
+
+using namespace hps;
+
+extern "C" {
+
+int hps_version(void) { return 100; }
+const char* hps_last_error_string(void) { return last_error().c_str(); }
+
+int hps_dgemm_strided_batched(void* stream, int M, int N, int K, double alpha, const double* A, int64_t lda,
+                              int64_t sA, const double* B, int64_t ldb, int64_t sB, double beta, double* C,
+                              int64_t ldc, int64_t sC, int batch) {
+  if (M < 0 || N < 0 || K < 0) return fail_arg(2, "negative dimension");
+  return dgemm(static_cast<cudaStream_t>(stream), M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+}
+
+int hps_lu_solve_workspace(int batch, int n, size_t* bytes) {
+  if (!bytes) return fail_arg(3, "null output pointer");
+  *bytes = lu_workspace_bytes(batch, n);
+  return 0;
+}
+
+int hps_lu_solve(void* stream, int batch, int n, double* A, int64_t lda, int64_t sA, int n_rhs, double* const* rhs,
+                 const int64_t* ld_rhs, const int64_t* s_rhs, const int* ncols, void* ws, size_t ws_bytes,
+                 int* info) {
+  if (n_rhs < 0 || n_rhs > 4) return fail_arg(7, "n_rhs must be in [0, 4]");
+  RhsDesc d[4];
+  for (int k = 0; k < n_rhs; ++k) d[k] = RhsDesc{rhs[k], ld_rhs[k], s_rhs[k], ncols[k]};
+  return lu_solve(static_cast<cudaStream_t>(stream), batch, n, A, lda, sA, n_rhs, d, ws, ws_bytes, info);
+}
+
+int hps_local_solve_dtn_workspace(int dim, int n_leaves, int p, int q, int n_src, size_t* bytes) {
+  (void)q; (void)n_src;
+  if (!bytes) return fail_arg(6, "null output pointer");
+  if (dim != 2 && dim != 3) return fail_arg(1, "dim must be 2 or 3");
+  *bytes = local_solve_workspace_bytes(dim, n_leaves, p);
+  return 0;
+}
+
+int hps_local_solve_dtn(void* stream, int dim, int n_leaves, int p, int q, int n_src, const uint8_t* which,
+                        const double* coeffs, const double* D1, const double* P, const double* Q,
+                        const double* src, double* Y, double* T, double* v, double* h, void* ws, size_t ws_bytes,
+                        int* info) {
+  return local_solve_dtn(static_cast<cudaStream_t>(stream), dim, n_leaves, p, q, n_src, which, coeffs, D1, P, Q, src,
+                         Y, T, v, h, ws, ws_bytes, info);
+}
+
+int hps_merge_oct_dtn_level_workspace(int n_merges, int m, int n_src, size_t* bytes) {
+  (void)n_src;
+  if (!bytes) return fail_arg(4, "null output pointer");
+  *bytes = merge_oct_ws_bytes(n_merges, m);
+  return 0;
+}
+int hps_merge_oct_dtn_level(void* stream, int n_merges, int m, int n_src, const double* T_in, const double* h_in,
+                            double* S, double* g_tilde, double* T_out, double* h_out, int want_T, void* ws,
+                            size_t ws_bytes, int* info) {
+  return merge_oct_level(static_cast<cudaStream_t>(stream), n_merges, m, n_src, T_in, h_in, S, g_tilde, T_out, h_out,
+                         want_T, ws, ws_bytes, info);
+}
+int hps_merge_quad_dtn_level_workspace(int n_merges, int m, int n_src, size_t* bytes) {
+  (void)n_src;
+  if (!bytes) return fail_arg(4, "null output pointer");
+  *bytes = merge_quad_ws_bytes(n_merges, m);
+  return 0;
+}
+int hps_merge_quad_dtn_level(void* stream, int n_merges, int m, int n_src, const double* T_in, const double* h_in,
+                             double* S, double* g_tilde, double* T_out, double* h_out, int want_T, void* ws,
+                             size_t ws_bytes, int* info) {
+  return merge_quad_level(static_cast<cudaStream_t>(stream), n_merges, m, n_src, T_in, h_in, S, g_tilde, T_out, h_out,
+                          want_T, ws, ws_bytes, info);
+}
+
+int hps_down_oct_level(void* stream, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
+                       const double* g_tilde, double* g_children, void* ws) {
+  return down_oct_level(static_cast<cudaStream_t>(stream), n_nodes, m, n_src, S, g_ext, g_tilde, g_children, ws);
+}
+int hps_down_quad_level(void* stream, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
+                        const double* g_tilde, double* g_children, void* ws) {
+  return down_quad_level(static_cast<cudaStream_t>(stream), n_nodes, m, n_src, S, g_ext, g_tilde, g_children, ws);
+}
+
+int hps_leaf_apply(void* stream, int n_leaves, int n_c, int n_g, int n_src, const double* Y, const double* g,
+                   const double* v, double* u) {
+  if (n_leaves <= 0 || n_c <= 0 || n_g <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
+  return dgemm_affine(static_cast<cudaStream_t>(stream), n_c, n_src, n_g, Y, n_g, (int64_t)n_c * n_g, g, n_src,
+                      (int64_t)n_g * n_src, v, n_src, (int64_t)n_c * n_src, u, n_src, (int64_t)n_c * n_src, n_leaves);
+}
+
+}  // extern "C"

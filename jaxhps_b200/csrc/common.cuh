@@ -1,0 +1,94 @@
+// Shared helpers for libhps_b200 (sm_100a).  Internal header.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace hps {
+
+// thread-local last error text, surfaced through hps_last_error_string()
+std::string& last_error();
+int fail_arg(int which, const char* what);
+int fail_cuda(cudaError_t e, const char* where);
+
+#define HPS_CUDA(call)                                            \
+  do {                                                            \
+    cudaError_t _e = (call);                                      \
+    if (_e != cudaSuccess) return ::hps::fail_cuda(_e, #call);    \
+  } while (0)
+
+#define HPS_LAUNCH_CHECK(name)                                    \
+  do {                                                            \
+    cudaError_t _e = cudaGetLastError();                          \
+    if (_e != cudaSuccess) return ::hps::fail_cuda(_e, name);     \
+  } while (0)
+
+#define HPS_TRY(expr)          \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != 0) return _rc;  \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// bump allocator over a caller-provided workspace
+struct Arena {
+  char* base;
+  size_t cap;
+  size_t off = 0;
+  Arena(void* p, size_t n) : base(static_cast<char*>(p)), cap(n) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T), 256);
+    if (off + bytes > cap) return nullptr;
+    T* r = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return r;
+  }
+};
+
+// ---- internal dense primitives (gemm.cu / lu.cu) ---------------------------------
+int dgemm(cudaStream_t st, int M, int N, int K, double alpha, const double* A, int64_t lda,
+          int64_t sA, const double* B, int64_t ldb, int64_t sB, double beta, double* C,
+          int64_t ldc, int64_t sC, int batch);
+
+// C = alpha*A*B + beta*Cin for narrow N (< 16): bandwidth kernel, one warp per row of A.
+int dgemm_skinny(cudaStream_t st, int M, int N, int K, double alpha, const double* A,
+                 int64_t lda, int64_t sA, const double* B, int64_t ldb, int64_t sB, double beta,
+                 const double* Cin, int64_t ldcin, int64_t sCin, double* C, int64_t ldc,
+                 int64_t sC, int batch);
+
+// C = A*B + Cin, C and Cin distinct (picks the narrow or the DMMA kernel by N)
+int dgemm_affine(cudaStream_t st, int M, int N, int K, const double* A, int64_t lda, int64_t sA, const double* B,
+                 int64_t ldb, int64_t sB, const double* Cin, int64_t ldcin, int64_t sCin, double* C, int64_t ldc,
+                 int64_t sC, int batch);
+
+struct RhsDesc {
+  double* ptr;
+  int64_t ld;
+  int64_t stride;
+  int ncols;
+};
+size_t lu_workspace_bytes(int batch, int n);
+int lu_solve(cudaStream_t st, int batch, int n, double* A, int64_t lda, int64_t sA, int n_rhs,
+             const RhsDesc* rhs, void* ws, size_t ws_bytes, int* info);
+
+// ---- stages (leaf.cu / merge.cu) --------------------------------------------------------
+size_t local_solve_workspace_bytes(int dim, int n_leaves, int p);
+int local_solve_dtn(cudaStream_t st, int dim, int n_leaves, int p, int q, int n_src, const uint8_t* which,
+                    const double* coeffs, const double* D1, const double* P, const double* Q, const double* src,
+                    double* Y, double* T, double* v, double* h, void* ws, size_t ws_bytes, int* info);
+size_t merge_oct_ws_bytes(int n_merges, int m);
+size_t merge_quad_ws_bytes(int n_merges, int m);
+int merge_oct_level(cudaStream_t st, int n_merges, int m, int n_src, const double* T_in, const double* h_in, double* S,
+                    double* gt, double* T_out, double* h_out, int want_T, void* ws, size_t ws_bytes, int* info);
+int merge_quad_level(cudaStream_t st, int n_merges, int m, int n_src, const double* T_in, const double* h_in,
+                     double* S, double* gt, double* T_out, double* h_out, int want_T, void* ws, size_t ws_bytes,
+                     int* info);
+int down_oct_level(cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
+                   const double* gt, double* g_children, void* ws);
+int down_quad_level(cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
+                    const double* gt, double* g_children, void* ws);
+
+}  // namespace hps

@@ -1,0 +1,213 @@
+// local_solve_stage on the device (reference: local_solve/_uniform_3D_DtN.py:13-106,
+// local_solve/_uniform_2D_DtN.py:9-102,182-273).
+//
+// Per leaf:  A = sum_k diag(c_k) D_k  restricted to the interior rows, built directly from the
+// scaled 1-D Chebyshev matrix (the p^d x p^d Kronecker operators are never materialised);
+//   [Y_int | v_int] = A_ii^-1 [ -A_ie P | f_i ]   (batched LU with partial pivoting, lu.cu)
+//   Y = [P ; Y_int],  v = [0 ; v_int],  T = Q Y,  h = Q v.
+// The solve runs in place inside the caller's Y and v buffers.
+#include "common.cuh"
+
+namespace hps {
+
+namespace {
+
+constexpr int MAX_P = 32;
+
+struct LeafGeom {
+  int dim, p, n_c, n_i, n_b;
+};
+
+// natural (i,j[,k]) coordinates of leaf-ordered point `idx`
+// 3D ordering: [x- face | x+ face | y- rest | y+ rest | z- rest | z+ rest | interior], natural
+//   index = i*p*p + j*p + k (reference: _grid_creation_3D.py:421-458)
+__device__ __forceinline__ void decode3(int idx, int p, int& i, int& j, int& k) {
+  const int p2 = p * p, q = p - 2;
+  if (idx < p2) { i = 0; j = idx / p; k = idx - j * p; return; }
+  idx -= p2;
+  if (idx < p2) { i = p - 1; j = idx / p; k = idx - j * p; return; }
+  idx -= p2;
+  if (idx < q * p) { j = 0; i = 1 + idx / p; k = idx % p; return; }
+  idx -= q * p;
+  if (idx < q * p) { j = p - 1; i = 1 + idx / p; k = idx % p; return; }
+  idx -= q * p;
+  if (idx < q * q) { k = 0; i = 1 + idx / q; j = 1 + idx % q; return; }
+  idx -= q * q;
+  if (idx < q * q) { k = p - 1; i = 1 + idx / q; j = 1 + idx % q; return; }
+  idx -= q * q;
+  i = 1 + idx / (q * q);
+  const int rem = idx % (q * q);
+  j = 1 + rem / q;
+  k = 1 + rem % q;
+}
+
+// 2D ordering: 4(p-1) boundary points counter-clockwise from the SW corner (S,E,N,W), then
+// the interior; natural index = i*p + j with j counting DOWN in y (j = p-1 is y_min)
+// (reference: _grid_creation_2D.py:204-233, :62)
+__device__ __forceinline__ void decode2(int idx, int p, int& i, int& j) {
+  const int m = p - 1;
+  if (idx < p) { i = idx; j = m; return; }                    // south, W -> E (both corners)
+  if (idx < 2 * p - 1) { i = m; j = m - 1 - (idx - p); return; }      // east, S -> N
+  if (idx < 3 * p - 3) { i = m - 1 - (idx - (2 * p - 1)); j = 0; return; }  // north, E -> W
+  if (idx == 3 * p - 3) { i = 0; j = 0; return; }               // NW corner
+  if (idx < 4 * m) { i = 0; j = 1 + (idx - (3 * p - 2)); return; }      // west, N -> S
+  idx -= 4 * m;
+  const int q = p - 2;
+  i = 1 + idx / q;
+  j = 1 + idx % q;
+}
+
+struct AssembleArgs {
+  LeafGeom geo;
+  int n_leaves, n_coef;
+  int slot[10];            // slot[k] = position of coefficient k inside coeffs, or -1
+  const double* coeffs;    // [n_coef][n_leaves][n_c]
+  const double* D1;        // [p][p]
+  double* Aii;             // [n_leaves][n_i][n_i]
+  double* Aie;             // [n_leaves][n_i][n_b]
+};
+
+// one thread per (interior row a, column b) entry; blockIdx.y = leaf
+template <int DIM>
+__global__ void __launch_bounds__(256) assemble_kernel(AssembleArgs g) {
+  __shared__ double D[MAX_P * MAX_P];
+  __shared__ double D2[MAX_P * MAX_P];
+  const int p = g.geo.p, n_c = g.geo.n_c, n_i = g.geo.n_i, n_b = g.geo.n_b;
+  for (int t = threadIdx.x; t < p * p; t += blockDim.x) D[t] = g.D1[t];
+  __syncthreads();
+  for (int t = threadIdx.x; t < p * p; t += blockDim.x) {
+    const int r = t / p, c = t - r * p;
+    double s = 0.0;
+    for (int u = 0; u < p; ++u) s = fma(D[r * p + u], D[u * p + c], s);
+    D2[t] = s;
+  }
+  __syncthreads();
+  const int leaf = blockIdx.y;
+  const int64_t total = (int64_t)n_i * n_c;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int a = (int)(e / n_c), b = (int)(e - (int64_t)a * n_c);
+    const int row = n_b + a;
+    auto coef = [&](int k) -> double {
+      const int s = g.slot[k];
+      return s < 0 ? 0.0 : g.coeffs[((int64_t)s * g.n_leaves + leaf) * n_c + row];
+    };
+    double val = 0.0;
+    if (DIM == 3) {
+      int i, j, k, i2, j2, k2;
+      decode3(row, p, i, j, k);
+      decode3(b, p, i2, j2, k2);
+      const bool di = i == i2, dj = j == j2, dk = k == k2;
+      // order of the reference's stack: xx, xy, yy, xz, yz, zz, x, y, z, I
+      if (dj && dk) val = fma(coef(0), D2[i * p + i2], val);
+      if (dk) val = fma(coef(1), D[i * p + i2] * D[j * p + j2], val);
+      if (di && dk) val = fma(coef(2), D2[j * p + j2], val);
+      if (dj) val = fma(coef(3), D[i * p + i2] * D[k * p + k2], val);
+      if (di) val = fma(coef(4), D[j * p + j2] * D[k * p + k2], val);
+      if (di && dj) val = fma(coef(5), D2[k * p + k2], val);
+      if (dj && dk) val = fma(coef(6), D[i * p + i2], val);
+      if (di && dk) val = fma(coef(7), D[j * p + j2], val);
+      if (di && dj) val = fma(coef(8), D[k * p + k2], val);
+      if (di && dj && dk) val += coef(9);
+    } else {
+      int i, j, i2, j2;
+      decode2(row, p, i, j);
+      decode2(b, p, i2, j2);
+      const bool di = i == i2, dj = j == j2;
+      // D_x = kron(D, I); D_y = -kron(I, D) because y is stored descending; order xx, xy, yy, x, y, I
+      if (dj) val = fma(coef(0), D2[i * p + i2], val);
+      val = fma(coef(1), -(D[i * p + i2] * D[j * p + j2]), val);
+      if (di) val = fma(coef(2), D2[j * p + j2], val);
+      if (dj) val = fma(coef(3), D[i * p + i2], val);
+      if (di) val = fma(coef(4), -D[j * p + j2], val);
+      if (di && dj) val += coef(5);
+    }
+    if (b < n_b) g.Aie[((int64_t)leaf * n_i + a) * n_b + b] = val;
+    else g.Aii[((int64_t)leaf * n_i + a) * n_i + (b - n_b)] = val;
+  }
+}
+
+// Y[:n_b] = P, v[:n_b] = 0, v[n_b:] = f[n_b:]
+__global__ void leaf_init_kernel(int n_c, int n_b, int n_g, int n_src, const double* __restrict__ P,
+                                 const double* __restrict__ src, double* __restrict__ Y, double* __restrict__ v) {
+  const int leaf = blockIdx.y;
+  const int64_t nY = (int64_t)n_b * n_g, nV = (int64_t)n_c * n_src;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nY + nV; e += (int64_t)gridDim.x * blockDim.x) {
+    if (e < nY) {
+      Y[(int64_t)leaf * n_c * n_g + e] = P[e];
+    } else {
+      const int64_t t = e - nY;
+      const int64_t r = t / n_src;
+      v[(int64_t)leaf * nV + t] = (r < n_b) ? 0.0 : src[(int64_t)leaf * nV + t];
+    }
+  }
+}
+
+int ipow(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
+
+LeafGeom geom(int dim, int p) {
+  LeafGeom g;
+  g.dim = dim; g.p = p;
+  g.n_c = ipow(p, dim);
+  g.n_i = ipow(p - 2, dim);
+  g.n_b = g.n_c - g.n_i;
+  return g;
+}
+
+}  // namespace
+
+size_t local_solve_workspace_bytes(int dim, int n_leaves, int p) {
+  const LeafGeom g = geom(dim, p);
+  return align_up((size_t)n_leaves * g.n_i * g.n_i * sizeof(double), 256) +
+         align_up((size_t)n_leaves * g.n_i * g.n_b * sizeof(double), 256) + lu_workspace_bytes(n_leaves, g.n_i) + 1024;
+}
+
+int local_solve_dtn(cudaStream_t st, int dim, int n_leaves, int p, int q, int n_src, const uint8_t* which,
+                    const double* coeffs, const double* D1, const double* P, const double* Q, const double* src,
+                    double* Y, double* T, double* v, double* h, void* ws, size_t ws_bytes, int* info) {
+  if (dim != 2 && dim != 3) return fail_arg(2, "dim must be 2 or 3");
+  if (p < 3 || p > MAX_P) return fail_arg(4, "p out of range [3, 32]");
+  if (n_leaves <= 0 || n_src <= 0 || q <= 0) return fail_arg(3, "non-positive size");
+  if (n_leaves > 65535) return fail_arg(3, "n_leaves per call is limited to 65535; chunk the leaves");
+  const LeafGeom geo = geom(dim, p);
+  const int n_g = 2 * dim * ipow(q, dim - 1);
+  const int n_which = dim == 3 ? 10 : 6;
+
+  Arena ar(ws, ws_bytes);
+  double* Aii = ar.take<double>((size_t)n_leaves * geo.n_i * geo.n_i);
+  double* Aie = ar.take<double>((size_t)n_leaves * geo.n_i * geo.n_b);
+  if (!Aii || !Aie) return fail_arg(17, "local_solve: workspace too small");
+  void* lu_ws = ar.base + ar.off;
+  const size_t lu_ws_bytes = ar.cap - ar.off;
+
+  AssembleArgs aa;
+  aa.geo = geo; aa.n_leaves = n_leaves; aa.coeffs = coeffs; aa.D1 = D1; aa.Aii = Aii; aa.Aie = Aie;
+  int n_coef = 0;
+  for (int k = 0; k < 10; ++k) aa.slot[k] = (k < n_which && which[k]) ? n_coef++ : -1;
+  aa.n_coef = n_coef;
+  {
+    const int64_t total = (int64_t)geo.n_i * geo.n_c;
+    const int bx = (int)std::min<int64_t>((total + 255) / 256, 4096);
+    if (dim == 3) assemble_kernel<3><<<dim3(bx, n_leaves), 256, 0, st>>>(aa);
+    else assemble_kernel<2><<<dim3(bx, n_leaves), 256, 0, st>>>(aa);
+    HPS_LAUNCH_CHECK("assemble_kernel");
+    const int64_t tot2 = (int64_t)geo.n_b * n_g + (int64_t)geo.n_c * n_src;
+    leaf_init_kernel<<<dim3((int)std::min<int64_t>((tot2 + 255) / 256, 2048), n_leaves), 256, 0, st>>>(
+        geo.n_c, geo.n_b, n_g, n_src, P, src, Y, v);
+    HPS_LAUNCH_CHECK("leaf_init_kernel");
+  }
+  const int64_t sY = (int64_t)geo.n_c * n_g, sV = (int64_t)geo.n_c * n_src;
+  double* Yint = Y + (int64_t)geo.n_b * n_g;
+  double* vint = v + (int64_t)geo.n_b * n_src;
+  // Y_int := -A_ie P
+  HPS_TRY(dgemm(st, geo.n_i, n_g, geo.n_b, -1.0, Aie, geo.n_b, (int64_t)geo.n_i * geo.n_b, P, n_g, 0, 0.0, Yint, n_g, sY,
+                n_leaves));
+  // [Y_int | v_int] := A_ii^-1 [Y_int | v_int]
+  RhsDesc rhs[2] = {{Yint, n_g, sY, n_g}, {vint, n_src, sV, n_src}};
+  HPS_TRY(lu_solve(st, n_leaves, geo.n_i, Aii, geo.n_i, (int64_t)geo.n_i * geo.n_i, 2, rhs, lu_ws, lu_ws_bytes, info));
+  // T = Q Y, h = Q v
+  HPS_TRY(dgemm(st, n_g, n_g, geo.n_c, 1.0, Q, geo.n_c, 0, Y, n_g, sY, 0.0, T, n_g, (int64_t)n_g * n_g, n_leaves));
+  HPS_TRY(dgemm(st, n_g, n_src, geo.n_c, 1.0, Q, geo.n_c, 0, v, n_src, sV, 0.0, h, n_src, (int64_t)n_g * n_src, n_leaves));
+  return 0;
+}
+
+}  // namespace hps

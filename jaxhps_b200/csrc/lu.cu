@@ -1,0 +1,512 @@
+// Batched blocked LU with partial pivoting + in-place multi-RHS solve, FP64, sm_100a.
+//
+// Replaces the reference's `jnp.linalg.inv(X) @ Y` pairs (local_solve/_uniform_2D_DtN.py:257-259,
+// merge/_schur_complement.py:146,222,234): X^-1 Y is obtained from P X = L U with the right-hand
+// sides carried through the elimination (so L is never revisited) and one blocked back
+// substitution with U.
+//
+// Structure (right-looking, two-level blocking NB=128 / IB=32):
+//   panel_kernel   IB columns at a time; the panel's rows are split over G CTAs that keep
+//                  their chunk in shared memory.  One group barrier per column:
+//                  a thread-block cluster barrier for G<=8, a cooperative-launch global
+//                  barrier above that.  Candidates travel through a small global scratch.
+//   laswp_kernel   row interchanges on a column range (rows are contiguous: coalesced).
+//   inner_trsm     32x32 unit-lower solve inside the outer panel.
+//   trtri kernels  invert the NBxNB triangular diagonal blocks in shared memory so that every
+//                  triangular solve becomes a DMMA GEMM (in place, single tile row).
+//   hps::dgemm     all trailing updates.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace hps {
+
+namespace {
+
+constexpr int NB = 128;          // outer block
+constexpr int IB = 32;           // inner panel width
+constexpr int PANEL_ROWS = 768;  // rows of the panel one CTA keeps in shared memory
+constexpr int PANEL_LD = IB + 1;
+constexpr int PANEL_THREADS = 512;
+constexpr int MAX_G = 64;
+
+struct Cand {          // one CTA's pivot candidate for the current column
+  double val;          // |a|, negative when the CTA has no eligible row
+  int row;             // panel-relative row index
+  int pad;
+  double content[IB];  // that row's IB panel entries
+};
+
+struct PanelScratch {  // per matrix
+  Cand cand[2][MAX_G];
+  double diag[2][IB];
+  unsigned int counter;  // SYNC_GRID barrier
+  unsigned int pad[3];
+};
+
+enum { SYNC_NONE = 0, SYNC_CLUSTER = 1, SYNC_GRID = 2 };
+
+struct PanelArgs {
+  double* A; int64_t lda, sA;
+  int n, jj, ib, G;
+  int* ipiv;            // [batch][n]
+  int* info;            // [batch]
+  PanelScratch* scratch;  // [batch]
+};
+
+template <int SYNC>
+__device__ __forceinline__ void group_barrier(PanelScratch* sc, int G, unsigned& epoch) {
+  if (SYNC == SYNC_CLUSTER) {
+    __threadfence();
+    cg::this_cluster().sync();
+  } else if (SYNC == SYNC_GRID) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(&sc->counter, 1u);
+      const unsigned target = (epoch + 1u) * (unsigned)G;
+      volatile unsigned* c = &sc->counter;
+      while (*c < target) { __nanosleep(20); }
+      __threadfence();
+    }
+    ++epoch;
+    __syncthreads();
+  }
+}
+
+template <int SYNC>
+__global__ void __launch_bounds__(PANEL_THREADS, 1) panel_kernel(PanelArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = blockIdx.x, mat = blockIdx.y;
+  const int G = a.G, ib = a.ib;
+  const int rows = a.n - a.jj;
+  const int rpc = (rows + G - 1) / G;
+  const int r0 = min(rows, g * rpc), r1 = min(rows, r0 + rpc), nr = r1 - r0;
+  double* A = a.A + (int64_t)mat * a.sA + (int64_t)a.jj * a.lda + a.jj;
+  PanelScratch* sc = a.scratch + mat;
+  int* ipiv = a.ipiv + (int64_t)mat * a.n + a.jj;
+
+  double* tile = sm;                                   // [nr][PANEL_LD]
+  double* prow = sm + (size_t)PANEL_ROWS * PANEL_LD;   // [IB]
+  double* red_val = prow + IB;                         // [16]
+  int* red_idx = reinterpret_cast<int*>(red_val + 16); // [16]
+  __shared__ int s_piv;                                // panel-relative pivot row of this column
+
+  for (int idx = tid; idx < nr * ib; idx += PANEL_THREADS) {
+    const int r = idx / ib, c = idx - r * ib;
+    tile[r * PANEL_LD + c] = A[(int64_t)(r0 + r) * a.lda + c];
+  }
+  __syncthreads();
+
+  unsigned epoch = 0;
+  for (int c = 0; c < ib; ++c) {
+    // ---- local arg-max of |a[r][c]| over rows >= c (lowest row wins ties) ----
+    double best = -1.0;
+    int bidx = 0x7fffffff;
+    for (int r = tid; r < nr; r += PANEL_THREADS) {
+      if (r0 + r >= c) {
+        const double v = fabs(tile[r * PANEL_LD + c]);
+        if (v > best) { best = v; bidx = r; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    if (lane == 0) { red_val[warp] = best; red_idx[warp] = bidx; }
+    __syncthreads();
+    if (warp == 0) {
+      best = lane < PANEL_THREADS / 32 ? red_val[lane] : -1.0;
+      bidx = lane < PANEL_THREADS / 32 ? red_idx[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+      }
+      best = __shfl_sync(0xffffffffu, best, 0);
+      bidx = __shfl_sync(0xffffffffu, bidx, 0);
+      if (SYNC == SYNC_NONE) {
+        if (lane == 0) s_piv = (best >= 0.0) ? r0 + bidx : c;
+        if (best >= 0.0 && lane < ib) prow[lane] = tile[bidx * PANEL_LD + lane];
+      } else {
+        Cand* cd = &sc->cand[c & 1][g];
+        if (lane == 0) { cd->val = best; cd->row = (best >= 0.0) ? r0 + bidx : -1; }
+        if (best >= 0.0 && lane < ib) cd->content[lane] = tile[bidx * PANEL_LD + lane];
+        if (c >= r0 && c < r1 && lane < ib) sc->diag[c & 1][lane] = tile[(c - r0) * PANEL_LD + lane];
+      }
+    }
+    if (SYNC == SYNC_NONE) {
+      __syncthreads();
+    } else {
+      group_barrier<SYNC>(sc, G, epoch);
+      if (warp == 0) {
+        // every CTA elects the same winner: largest value, lowest row on ties
+        double wv = -1.0; int wg = 0, wr = 0x7fffffff;
+        for (int k = lane; k < G; k += 32) {
+          const double v = *(volatile const double*)&sc->cand[c & 1][k].val;
+          const int r = *(volatile const int*)&sc->cand[c & 1][k].row;
+          if (v >= 0.0 && (v > wv || (v == wv && r < wr))) { wv = v; wg = k; wr = r; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, wv, o);
+          const int og = __shfl_xor_sync(0xffffffffu, wg, o);
+          const int orr = __shfl_xor_sync(0xffffffffu, wr, o);
+          if (ov > wv || (ov == wv && orr < wr)) { wv = ov; wg = og; wr = orr; }
+        }
+        if (lane == 0) s_piv = (wv >= 0.0) ? wr : c;
+        if (lane < ib) prow[lane] = *(volatile const double*)&sc->cand[c & 1][wg].content[lane];
+      }
+      __syncthreads();
+    }
+    const int p = s_piv;
+    // ---- interchange rows c and p inside the panel ----
+    if (p != c && tid < ib) {
+      if (SYNC == SYNC_NONE) {
+        tile[(p - r0) * PANEL_LD + tid] = tile[(c - r0) * PANEL_LD + tid];
+        tile[(c - r0) * PANEL_LD + tid] = prow[tid];
+      } else {
+        if (p >= r0 && p < r1) tile[(p - r0) * PANEL_LD + tid] = *(volatile const double*)&sc->diag[c & 1][tid];
+        if (c >= r0 && c < r1) tile[(c - r0) * PANEL_LD + tid] = prow[tid];
+      }
+    }
+    if (g == 0 && tid == 0) ipiv[c] = a.jj + p;
+    __syncthreads();
+    const double piv = prow[c];
+    if (piv == 0.0) {
+      if (g == 0 && tid == 0 && a.info[mat] == 0) a.info[mat] = a.jj + c + 1;
+    } else {
+      // ---- scale the column and apply the rank-1 update to the rest of the panel ----
+      for (int r = tid; r < nr; r += PANEL_THREADS) {
+        if (r0 + r > c) {
+          double* row = tile + r * PANEL_LD;
+          const double l = row[c] / piv;
+          row[c] = l;
+          for (int cc = c + 1; cc < ib; ++cc) row[cc] = fma(-l, prow[cc], row[cc]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  for (int idx = tid; idx < nr * ib; idx += PANEL_THREADS) {
+    const int r = idx / ib, c = idx - r * ib;
+    A[(int64_t)(r0 + r) * a.lda + c] = tile[r * PANEL_LD + c];
+  }
+}
+
+constexpr size_t PANEL_SMEM = sizeof(double) * ((size_t)PANEL_ROWS * PANEL_LD + IB + 16) + sizeof(int) * 16;
+
+// rows k0..k1-1 of every matrix are exchanged with rows ipiv[k] on columns [c0, c0+ncols)
+__global__ void laswp_kernel(double* A, int64_t lda, int64_t sA, int c0, int ncols, const int* ipiv, int n_ipiv,
+                             int k0, int k1) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  double* a = A + (int64_t)blockIdx.y * sA + c0 + col;
+  const int* piv = ipiv + (int64_t)blockIdx.y * n_ipiv;
+  for (int k = k0; k < k1; ++k) {
+    const int p = piv[k];
+    if (p != k) {
+      const double t = a[(int64_t)k * lda];
+      a[(int64_t)k * lda] = a[(int64_t)p * lda];
+      a[(int64_t)p * lda] = t;
+    }
+  }
+}
+
+// X := L^-1 X for the unit-lower ib x ib block at A[jj,jj], X = A[jj:jj+ib, c0:c0+ncols)
+__global__ void inner_trsm_kernel(double* A, int64_t lda, int64_t sA, int jj, int ib, int c0, int ncols) {
+  __shared__ double L[IB][IB + 1];
+  double* a = A + (int64_t)blockIdx.y * sA;
+  for (int idx = threadIdx.x; idx < ib * ib; idx += blockDim.x) {
+    const int r = idx / ib, c = idx - r * ib;
+    L[r][c] = a[(int64_t)(jj + r) * lda + jj + c];
+  }
+  __syncthreads();
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  double x[IB];
+  double* xp = a + (int64_t)jj * lda + c0 + col;
+#pragma unroll
+  for (int r = 0; r < IB; ++r) x[r] = (r < ib) ? xp[(int64_t)r * lda] : 0.0;
+#pragma unroll
+  for (int r = 1; r < IB; ++r) {
+    double s = x[r];
+#pragma unroll
+    for (int t = 0; t < r; ++t) s = fma(-L[r][t], x[t], s);
+    x[r] = s;
+  }
+#pragma unroll
+  for (int r = 1; r < IB; ++r)
+    if (r < ib) xp[(int64_t)r * lda] = x[r];
+}
+
+// Dense inverse of the nb x nb triangular block at A[j,j] into W (ld = NB, zero elsewhere).
+// LOWER: unit lower triangle.  !LOWER: upper triangle with its diagonal.
+// In-place column sweep (LAPACK trti2 order) in shared memory; one thread per row.
+template <bool LOWER>
+__global__ void __launch_bounds__(NB) trtri_kernel(const double* A, int64_t lda, int64_t sA, int j, int nb,
+                                                   double* W, int64_t sW) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int LD = NB + 1;
+  double* Ts = sm;             // [NB][LD]
+  double* colv = sm + NB * LD; // [NB]
+  const int r = threadIdx.x;
+  const double* a = A + (int64_t)blockIdx.x * sA + (int64_t)j * lda + j;
+  for (int idx = threadIdx.x; idx < nb * nb; idx += NB) {
+    const int rr = idx / nb, cc = idx - rr * nb;
+    double v = a[(int64_t)rr * lda + cc];
+    if (LOWER) v = (cc < rr) ? v : (cc == rr ? 1.0 : 0.0);
+    else v = (cc >= rr) ? v : 0.0;
+    Ts[rr * LD + cc] = v;
+  }
+  __syncthreads();
+  if (LOWER) {
+    // columns from last to first: x = -Tinv[c+1:, c+1:] * l[c+1:, c]
+    for (int c = nb - 2; c >= 0; --c) {
+      if (r > c && r < nb) colv[r] = Ts[r * LD + c];
+      __syncthreads();
+      if (r > c && r < nb) {
+        double s = 0.0;
+        for (int t = c + 1; t <= r; ++t) s = fma(Ts[r * LD + t], colv[t], s);
+        Ts[r * LD + c] = -s;
+      }
+      __syncthreads();
+    }
+  } else {
+    // columns from first to last: diag = 1/u_cc ; x = -diag * Tinv[:c,:c] * u[:c, c]
+    for (int c = 0; c < nb; ++c) {
+      if (r <= c) colv[r] = Ts[r * LD + c];
+      __syncthreads();
+      const double d = 1.0 / colv[c];
+      if (r < c) {
+        double s = 0.0;
+        for (int t = r; t < c; ++t) s = fma(Ts[r * LD + t], colv[t], s);
+        Ts[r * LD + c] = -s * d;
+      } else if (r == c) {
+        Ts[r * LD + c] = d;
+      }
+      __syncthreads();
+    }
+  }
+  double* w = W + (int64_t)blockIdx.x * sW;
+  for (int idx = threadIdx.x; idx < nb * nb; idx += NB) {
+    const int rr = idx / nb, cc = idx - rr * nb;
+    w[rr * NB + cc] = Ts[rr * LD + cc];
+  }
+}
+
+// dst[b][r][c] = src[b][r][c] for an (rows x cols) block
+__global__ void copy_block_kernel(double* dst, int64_t ldd, int64_t sD, const double* src, int64_t lds, int64_t sS,
+                                  int rows, int cols) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int r = idx / cols, c = idx - r * cols;
+  dst[(int64_t)blockIdx.y * sD + (int64_t)r * ldd + c] = src[(int64_t)blockIdx.y * sS + (int64_t)r * lds + c];
+}
+
+constexpr size_t TRTRI_SMEM = sizeof(double) * (NB * (NB + 1) + NB);
+
+struct LuWorkspace {
+  int* ipiv;
+  double* Tinv;
+  double* tmp;  // [batch][NB][16] staging for narrow right-hand sides
+  PanelScratch* scratch;
+};
+
+bool carve(Arena& ar, int batch, int n, LuWorkspace& w) {
+  w.ipiv = ar.take<int>((size_t)batch * n);
+  w.Tinv = ar.take<double>((size_t)batch * NB * NB);
+  w.tmp = ar.take<double>((size_t)batch * NB * 16);
+  w.scratch = ar.take<PanelScratch>((size_t)batch);
+  return w.ipiv && w.Tinv && w.tmp && w.scratch;
+}
+
+int g_coop_capacity = -1;  // co-resident panel CTAs for the cooperative variant
+
+int launch_panel(cudaStream_t st, int batch, PanelArgs pa) {
+  const int rows = pa.n - pa.jj;
+  int G = (rows + PANEL_ROWS - 1) / PANEL_ROWS;
+  if (G <= 1) {
+    pa.G = 1;
+    panel_kernel<SYNC_NONE><<<dim3(1, batch), PANEL_THREADS, PANEL_SMEM, st>>>(pa);
+    HPS_LAUNCH_CHECK("panel_kernel<none>");
+    return 0;
+  }
+  if (G <= 8) {
+    G = G <= 2 ? 2 : (G <= 4 ? 4 : 8);
+    pa.G = G;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G, batch);
+    cfg.blockDim = dim3(PANEL_THREADS);
+    cfg.dynamicSmemBytes = PANEL_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HPS_CUDA(cudaLaunchKernelEx(&cfg, panel_kernel<SYNC_CLUSTER>, pa));
+    return 0;
+  }
+  if (G > MAX_G) return fail_arg(3, "matrix too tall for the panel kernel (n > 49152)");
+  pa.G = G;
+  if (g_coop_capacity < 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    HPS_CUDA(cudaGetDevice(&dev));
+    HPS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    HPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, panel_kernel<SYNC_GRID>, PANEL_THREADS,
+                                                           PANEL_SMEM));
+    g_coop_capacity = sms * per_sm;
+  }
+  const int per_launch = g_coop_capacity / G;
+  if (per_launch < 1) return fail_arg(3, "panel does not fit a cooperative launch");
+  for (int b0 = 0; b0 < batch; b0 += per_launch) {
+    const int nb = min(per_launch, batch - b0);
+    PanelArgs sub = pa;
+    sub.A = pa.A + (int64_t)b0 * pa.sA;
+    sub.ipiv = pa.ipiv + (int64_t)b0 * pa.n;
+    sub.info = pa.info + b0;
+    sub.scratch = pa.scratch + b0;
+    for (int b = 0; b < nb; ++b)
+      HPS_CUDA(cudaMemsetAsync(&sub.scratch[b].counter, 0, sizeof(unsigned), st));
+    void* args[] = {&sub};
+    HPS_CUDA(cudaLaunchCooperativeKernel((void*)panel_kernel<SYNC_GRID>, dim3(G, nb), dim3(PANEL_THREADS), args,
+                                         PANEL_SMEM, st));
+  }
+  return 0;
+}
+
+int laswp(cudaStream_t st, int batch, double* A, int64_t lda, int64_t sA, int c0, int ncols, const int* ipiv, int n,
+          int k0, int k1) {
+  if (ncols <= 0 || k1 <= k0) return 0;
+  laswp_kernel<<<dim3((ncols + 255) / 256, batch), 256, 0, st>>>(A, lda, sA, c0, ncols, ipiv, n, k0, k1);
+  HPS_LAUNCH_CHECK("laswp_kernel");
+  return 0;
+}
+
+// X := Tinv * X for a jb-row block X (in place).  Wide X goes through the DMMA GEMM (one tile
+// row, so in-place is safe); narrow X is staged through tmp because the row-per-warp kernel
+// would read rows other warps have already overwritten.
+int tri_mult(cudaStream_t st, int batch, int jb, const double* Tinv, double* X, int64_t ld, int64_t stride,
+             int ncols, double* tmp) {
+  const int64_t sW = (int64_t)NB * NB;
+  if (ncols >= 16) return dgemm(st, jb, ncols, jb, 1.0, Tinv, NB, sW, X, ld, stride, 0.0, X, ld, stride, batch);
+  const int64_t sT = (int64_t)NB * 16;
+  HPS_TRY(dgemm_skinny(st, jb, ncols, jb, 1.0, Tinv, NB, sW, X, ld, stride, 0.0, nullptr, 0, 0, tmp, ncols, sT, batch));
+  copy_block_kernel<<<dim3((jb * ncols + 255) / 256, batch), 256, 0, st>>>(X, ld, stride, tmp, ncols, sT, jb, ncols);
+  HPS_LAUNCH_CHECK("copy_block_kernel");
+  return 0;
+}
+
+}  // namespace
+
+size_t lu_workspace_bytes(int batch, int n) {
+  return align_up((size_t)batch * n * sizeof(int), 256) + align_up((size_t)batch * NB * NB * sizeof(double), 256) +
+         align_up((size_t)batch * NB * 16 * sizeof(double), 256) + align_up((size_t)batch * sizeof(PanelScratch), 256) +
+         1024;
+}
+
+int lu_solve(cudaStream_t st, int batch, int n, double* A, int64_t lda, int64_t sA, int n_rhs, const RhsDesc* rhs,
+             void* ws, size_t ws_bytes, int* info) {
+  if (batch <= 0 || n <= 0) return 0;
+  if (batch > 65535) return fail_arg(2, "lu_solve: batch > 65535");
+  Arena ar(ws, ws_bytes);
+  LuWorkspace w;
+  if (!carve(ar, batch, n, w)) return fail_arg(11, "lu_solve: workspace too small");
+
+  static bool configured = false;
+  if (!configured) {
+    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
+    configured = true;
+  }
+  HPS_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
+
+  const int64_t sW = (int64_t)NB * NB;
+  for (int j = 0; j < n; j += NB) {
+    const int jb = min(NB, n - j);
+    // ---- factor the outer panel A[j:n, j:j+jb] with IB-wide inner panels ----
+    for (int jj = j; jj < j + jb; jj += IB) {
+      const int ib = min(IB, j + jb - jj);
+      PanelArgs pa;
+      pa.A = A; pa.lda = lda; pa.sA = sA; pa.n = n; pa.jj = jj; pa.ib = ib; pa.G = 1;
+      pa.ipiv = w.ipiv; pa.info = info; pa.scratch = w.scratch;
+      HPS_TRY(launch_panel(st, batch, pa));
+      // interchanges on the rest of the outer panel
+      HPS_TRY(laswp(st, batch, A, lda, sA, j, jj - j, w.ipiv, n, jj, jj + ib));
+      const int right = j + jb - (jj + ib);
+      if (right > 0) {
+        HPS_TRY(laswp(st, batch, A, lda, sA, jj + ib, right, w.ipiv, n, jj, jj + ib));
+        inner_trsm_kernel<<<dim3((right + 127) / 128, batch), 128, 0, st>>>(A, lda, sA, jj, ib, jj + ib, right);
+        HPS_LAUNCH_CHECK("inner_trsm_kernel");
+        const int below = n - (jj + ib);
+        if (below > 0) {
+          double* a21 = A + (int64_t)(jj + ib) * lda + jj;
+          double* u12 = A + (int64_t)jj * lda + jj + ib;
+          double* a22 = A + (int64_t)(jj + ib) * lda + jj + ib;
+          HPS_TRY(dgemm(st, below, right, ib, -1.0, a21, lda, sA, u12, lda, sA, 1.0, a22, lda, sA, batch));
+        }
+      }
+    }
+    // ---- interchanges on the trailing columns and on every right-hand side ----
+    const int trail = n - (j + jb);
+    HPS_TRY(laswp(st, batch, A, lda, sA, j + jb, trail, w.ipiv, n, j, j + jb));
+    for (int k = 0; k < n_rhs; ++k)
+      HPS_TRY(laswp(st, batch, rhs[k].ptr, rhs[k].ld, rhs[k].stride, 0, rhs[k].ncols, w.ipiv, n, j, j + jb));
+    // ---- block row of U and forward substitution of the right-hand sides ----
+    trtri_kernel<true><<<batch, NB, TRTRI_SMEM, st>>>(A, lda, sA, j, jb, w.Tinv, sW);
+    HPS_LAUNCH_CHECK("trtri_kernel<lower>");
+    if (trail > 0) {
+      double* a12 = A + (int64_t)j * lda + j + jb;
+      HPS_TRY(dgemm(st, jb, trail, jb, 1.0, w.Tinv, NB, sW, a12, lda, sA, 0.0, a12, lda, sA, batch));
+    }
+    for (int k = 0; k < n_rhs; ++k) {
+      double* r1 = rhs[k].ptr + (int64_t)j * rhs[k].ld;
+      HPS_TRY(tri_mult(st, batch, jb, w.Tinv, r1, rhs[k].ld, rhs[k].stride, rhs[k].ncols, w.tmp));
+    }
+    // ---- trailing updates ----
+    if (trail > 0) {
+      double* a21 = A + (int64_t)(j + jb) * lda + j;
+      double* a12 = A + (int64_t)j * lda + j + jb;
+      double* a22 = A + (int64_t)(j + jb) * lda + j + jb;
+      HPS_TRY(dgemm(st, trail, trail, jb, -1.0, a21, lda, sA, a12, lda, sA, 1.0, a22, lda, sA, batch));
+      for (int k = 0; k < n_rhs; ++k) {
+        double* r1 = rhs[k].ptr + (int64_t)j * rhs[k].ld;
+        double* r2 = rhs[k].ptr + (int64_t)(j + jb) * rhs[k].ld;
+        HPS_TRY(dgemm(st, trail, rhs[k].ncols, jb, -1.0, a21, lda, sA, r1, rhs[k].ld, rhs[k].stride, 1.0, r2,
+                      rhs[k].ld, rhs[k].stride, batch));
+      }
+    }
+  }
+  // ---- back substitution with U, last block row first ----
+  const int nblk = (n + NB - 1) / NB;
+  for (int bi = nblk - 1; bi >= 0; --bi) {
+    const int j = bi * NB, jb = min(NB, n - j);
+    trtri_kernel<false><<<batch, NB, TRTRI_SMEM, st>>>(A, lda, sA, j, jb, w.Tinv, sW);
+    HPS_LAUNCH_CHECK("trtri_kernel<upper>");
+    for (int k = 0; k < n_rhs; ++k) {
+      double* ri = rhs[k].ptr + (int64_t)j * rhs[k].ld;
+      HPS_TRY(tri_mult(st, batch, jb, w.Tinv, ri, rhs[k].ld, rhs[k].stride, rhs[k].ncols, w.tmp));
+      if (j > 0) {
+        double* u0i = A + j;
+        HPS_TRY(dgemm(st, j, rhs[k].ncols, jb, -1.0, u0i, lda, sA, ri, rhs[k].ld, rhs[k].stride, 1.0, rhs[k].ptr,
+                      rhs[k].ld, rhs[k].stride, batch));
+      }
+    }
+  }
+  return 0;
+}
+
+}  // namespace hps

@@ -1,0 +1,311 @@
+// merge_stage (one tree level) and down_pass (one tree level) on the device.
+//
+// Reference: merge/_uniform_3D_DtN.py:127-541 + merge/_schur_complement.py:293-774 (oct),
+// merge/_uniform_2D_DtN.py:206-475 (quad), merge/_schur_complement.py:117-147,182-237 (Schur
+// step), down_pass/_uniform_3D_DtN.py:116-246, down_pass/_uniform_2D_DtN.py:125-189.
+//
+// Differences from the reference's formulation (same results, fewer bytes and flops):
+//   * D and -C are gathered straight from the children's T with the exterior unknowns already
+//     in the parent's face order, so the reference's final permutation (two more copies of T)
+//     disappears and structurally-zero blocks of B are never touched;
+//   * S = D^-1 (-C) and g~ = D^-1 (-h_int) come from one pivoted LU with the right-hand sides
+//     carried along (lu.cu), in place in the caller's S / g~ buffers — no explicit inverse;
+//   * T = A (+) B S only multiplies the 3 (2 in 2D) non-zero m x m blocks per block row of B.
+#include <vector>
+
+#include "common.cuh"
+
+namespace hps {
+
+namespace {
+
+constexpr int MAXC = 8;   // children per merge
+constexpr int MAXF = 6;   // faces per child
+constexpr int MAXS = 12;  // interface slots per merge
+constexpr int MAXE = 24;  // exterior panels per merge
+
+struct Topo {
+  int n_child, n_face, n_slot, n_ext, n_intf;  // n_intf: interior faces per child
+  // role[c][f] >= 0: interface slot; < 0: exterior panel -(role+1) in the parent's ordering
+  signed char role[MAXC][MAXF];
+  unsigned char flip[MAXC][MAXF];       // interface traversed in reverse by this child
+  signed char slot_face[MAXC][MAXS];    // face of child c lying on slot s, or -1
+  signed char slot_owner[MAXS][2];      // the two children sharing slot s
+  signed char ext_child[MAXE], ext_face[MAXE];
+  signed char ext_slot[MAXE][3];        // interface slots of the child owning panel e
+};
+
+// 3D: children a..h, faces x-,x+,y-,y+,z-,z+; interface ids 9..20 -> slots 0..11
+// (merge/_uniform_3D_DtN.py:238-380); exterior panels in face order, four panels per face:
+// Face0 [e,h,d,a] Face1 [f,g,c,b] Face2 [e,f,b,a] Face3 [h,g,c,d] Face4 [e,f,g,h] Face5 [a,b,c,d]
+// (merge/_uniform_3D_DtN.py:507-541).
+Topo make_oct() {
+  Topo t = {};
+  t.n_child = 8; t.n_face = 6; t.n_slot = 12; t.n_ext = 24; t.n_intf = 3;
+  const int X = -1;  // exterior
+  const int intf[8][6] = {
+      {X, 9, X, 12, 17, X},   // a
+      {9, X, X, 10, 18, X},   // b
+      {11, X, 10, X, 19, X},  // c
+      {X, 11, 12, X, 20, X},  // d
+      {X, 13, X, 16, X, 17},  // e
+      {13, X, X, 14, X, 18},  // f
+      {15, X, 14, X, X, 19},  // g
+      {X, 15, 16, X, X, 20},  // h
+  };
+  const int face_children[6][4] = {{4, 7, 3, 0}, {5, 6, 2, 1}, {4, 5, 1, 0}, {7, 6, 2, 3}, {4, 5, 6, 7}, {0, 1, 2, 3}};
+  for (int c = 0; c < 8; ++c)
+    for (int f = 0; f < 6; ++f) {
+      if (intf[c][f] >= 0) {
+        t.role[c][f] = (signed char)(intf[c][f] - 9);
+      } else {
+        int pos = -1;
+        for (int k = 0; k < 4; ++k)
+          if (face_children[f][k] == c) pos = k;
+        t.role[c][f] = (signed char)(-(f * 4 + pos) - 1);
+      }
+    }
+  return t;
+}
+
+// 2D: children SW,SE,NE,NW; sides S,E,N,W; interfaces 5:a|b 6:b|c 7:c|d 8:d|a -> slots 0..3; the
+// second child listed walks the interface backwards (merge/_uniform_2D_DtN.py:385-437);
+// exterior panels after the reference's roll: a.S b.S b.E c.E c.N d.N d.W a.W (:343-346).
+Topo make_quad() {
+  Topo t = {};
+  t.n_child = 4; t.n_face = 4; t.n_slot = 4; t.n_ext = 8; t.n_intf = 2;
+  const int X = -1;
+  const int intf[4][4] = {{X, 5, 8, X}, {X, X, 6, 5}, {6, X, X, 7}, {8, 7, X, X}};
+  const int flipped[4][4] = {{0, 0, 1, 0}, {0, 0, 0, 1}, {1, 0, 0, 0}, {0, 1, 0, 0}};
+  const int ext_panel[4][4] = {{0, X, X, 7}, {1, 2, X, X}, {X, 3, 4, X}, {X, X, 5, 6}};
+  for (int c = 0; c < 4; ++c)
+    for (int f = 0; f < 4; ++f) {
+      if (intf[c][f] >= 0) {
+        t.role[c][f] = (signed char)(intf[c][f] - 5);
+        t.flip[c][f] = (unsigned char)flipped[c][f];
+      } else {
+        t.role[c][f] = (signed char)(-ext_panel[c][f] - 1);
+      }
+    }
+  return t;
+}
+
+void finish(Topo& t) {
+  for (int c = 0; c < MAXC; ++c)
+    for (int s = 0; s < MAXS; ++s) t.slot_face[c][s] = -1;
+  int owners[MAXS] = {0};
+  for (int c = 0; c < t.n_child; ++c) {
+    int slots[3], ns = 0;
+    for (int f = 0; f < t.n_face; ++f)
+      if (t.role[c][f] >= 0) {
+        const int s = t.role[c][f];
+        t.slot_face[c][s] = (signed char)f;
+        t.slot_owner[s][owners[s]++] = (signed char)c;
+        slots[ns++] = s;
+      }
+    for (int f = 0; f < t.n_face; ++f)
+      if (t.role[c][f] < 0) {
+        const int e = -t.role[c][f] - 1;
+        t.ext_child[e] = (signed char)c;
+        t.ext_face[e] = (signed char)f;
+        for (int k = 0; k < 3; ++k) t.ext_slot[e][k] = (signed char)(k < ns ? slots[k] : -1);
+      }
+  }
+}
+
+const Topo& oct_topo() { static Topo t = [] { Topo x = make_oct(); finish(x); return x; }(); return t; }
+const Topo& quad_topo() { static Topo t = [] { Topo x = make_quad(); finish(x); return x; }(); return t; }
+
+__device__ __forceinline__ int face_index(const Topo& tp, int c, int f, int t, int m) {
+  return f * m + (tp.flip[c][f] ? m - 1 - t : t);
+}
+
+// ---- gather: D (workspace), S := -C, g~ := -h_int --------------------------------------
+// grid: (column tiles, rows = n_slot*m, merges)
+__global__ void __launch_bounds__(256) merge_gather_kernel(Topo tp, int m, int n_src, const double* __restrict__ T_in,
+                                                           const double* __restrict__ h_in, double* __restrict__ D,
+                                                           double* __restrict__ S, double* __restrict__ gt) {
+  const int n_int = tp.n_slot * m, n_ext = tp.n_ext * m, nf = tp.n_face * m;
+  const int row = blockIdx.y, mg = blockIdx.z;
+  const int s1 = row / m, t1 = row - s1 * m;
+  const int64_t child_sz = (int64_t)nf * nf;
+  const double* Tm = T_in + (int64_t)mg * tp.n_child * child_sz;
+  const int cA = tp.slot_owner[s1][0], cB = tp.slot_owner[s1][1];
+  const int fA = tp.slot_face[cA][s1], fB = tp.slot_face[cB][s1];
+  const double* rowA = Tm + cA * child_sz + (int64_t)face_index(tp, cA, fA, t1, m) * nf;
+  const double* rowB = Tm + cB * child_sz + (int64_t)face_index(tp, cB, fB, t1, m) * nf;
+  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < n_int + n_ext + n_src; col += gridDim.x * blockDim.x) {
+    if (col < n_int) {
+      const int s2 = col / m, t2 = col - s2 * m;
+      double v = 0.0;
+      const int f2A = tp.slot_face[cA][s2], f2B = tp.slot_face[cB][s2];
+      if (f2A >= 0) v += rowA[face_index(tp, cA, f2A, t2, m)];
+      if (f2B >= 0) v += rowB[face_index(tp, cB, f2B, t2, m)];
+      D[((int64_t)mg * n_int + row) * n_int + col] = v;
+    } else if (col < n_int + n_ext) {
+      const int ce = col - n_int;
+      const int e = ce / m, u = ce - e * m;
+      const int c = tp.ext_child[e], f = tp.ext_face[e];
+      double v = 0.0;
+      if (c == cA) v = rowA[f * m + u];
+      else if (c == cB) v = rowB[f * m + u];
+      S[((int64_t)mg * n_int + row) * n_ext + ce] = -v;
+    } else {
+      const int k = col - n_int - n_ext;
+      const double* hm = h_in + (int64_t)mg * tp.n_child * nf * n_src;
+      const double v = hm[((int64_t)cA * nf + face_index(tp, cA, fA, t1, m)) * n_src + k] +
+                       hm[((int64_t)cB * nf + face_index(tp, cB, fB, t1, m)) * n_src + k];
+      gt[((int64_t)mg * n_int + row) * n_src + k] = -v;
+    }
+  }
+}
+
+// ---- exterior part: T_out := A scattered (zero elsewhere), h_out := h_ext, and the non-zero
+// m x m blocks of B packed as Bg[merge][e][j][m][m] (j-th interface of the child owning e) ----
+__global__ void __launch_bounds__(256) merge_ext_kernel(Topo tp, int m, int n_src, const double* __restrict__ T_in,
+                                                        const double* __restrict__ h_in, double* __restrict__ T_out,
+                                                        double* __restrict__ h_out, double* __restrict__ Bg) {
+  const int n_ext = tp.n_ext * m, nf = tp.n_face * m;
+  const int row = blockIdx.y, mg = blockIdx.z;
+  const int e1 = row / m, u1 = row - e1 * m;
+  const int c = tp.ext_child[e1], f1 = tp.ext_face[e1];
+  const int64_t child_sz = (int64_t)nf * nf;
+  const double* trow = T_in + ((int64_t)mg * tp.n_child + c) * child_sz + (int64_t)(f1 * m + u1) * nf;
+  const int nB = tp.n_intf * m;
+  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < n_ext + nB + n_src; col += gridDim.x * blockDim.x) {
+    if (col < n_ext) {
+      const int e2 = col / m, u2 = col - e2 * m;
+      const double v = (tp.ext_child[e2] == c) ? trow[tp.ext_face[e2] * m + u2] : 0.0;
+      T_out[((int64_t)mg * n_ext + row) * n_ext + col] = v;
+    } else if (col < n_ext + nB) {
+      const int cb = col - n_ext;
+      const int j = cb / m, t = cb - j * m;
+      const int s = tp.ext_slot[e1][j];
+      const int fs = tp.slot_face[c][s];
+      Bg[((((int64_t)mg * tp.n_ext + e1) * tp.n_intf + j) * m + u1) * m + t] = trow[face_index(tp, c, fs, t, m)];
+    } else {
+      const int k = col - n_ext - nB;
+      h_out[((int64_t)mg * n_ext + row) * n_src + k] =
+          h_in[(((int64_t)mg * tp.n_child + c) * nf + f1 * m + u1) * n_src + k];
+    }
+  }
+}
+
+// ---- down pass scatter: children's boundary vectors from g_ext and g_int --------------------
+__global__ void __launch_bounds__(256) down_scatter_kernel(Topo tp, int m, int n_src, const double* __restrict__ g_ext,
+                                                           const double* __restrict__ g_int, double* __restrict__ out) {
+  const int node = blockIdx.y;
+  const int nf = tp.n_face * m;
+  const int64_t per_node = (int64_t)tp.n_child * nf * n_src;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < per_node; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % n_src);
+    const int64_t r = idx / n_src;
+    const int c = (int)(r / nf);
+    const int fr = (int)(r - (int64_t)c * nf);
+    const int f = fr / m, t = fr - f * m;
+    const int role = tp.role[c][f];
+    double v;
+    if (role < 0) {
+      const int e = -role - 1;
+      v = g_ext[((int64_t)node * tp.n_ext * m + e * m + t) * n_src + k];
+    } else {
+      const int tt = tp.flip[c][f] ? m - 1 - t : t;
+      v = g_int[((int64_t)node * tp.n_slot * m + role * m + tt) * n_src + k];
+    }
+    out[(int64_t)node * per_node + idx] = v;
+  }
+}
+
+size_t merge_ws_bytes(const Topo& tp, int n_merges, int m) {
+  const size_t n_int = (size_t)tp.n_slot * m;
+  return align_up((size_t)n_merges * n_int * n_int * sizeof(double), 256) +
+         align_up((size_t)n_merges * tp.n_ext * tp.n_intf * m * m * sizeof(double), 256) +
+         lu_workspace_bytes(n_merges, (int)n_int) + 1024;
+}
+
+int merge_level(const Topo& tp, cudaStream_t st, int n_merges, int m, int n_src, const double* T_in,
+                const double* h_in, double* S, double* gt, double* T_out, double* h_out, int want_T, void* ws,
+                size_t ws_bytes, int* info) {
+  if (n_merges <= 0 || m <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
+  if (n_merges > 65535) return fail_arg(2, "n_merges per call is limited to 65535");
+  const int n_int = tp.n_slot * m, n_ext = tp.n_ext * m;
+  Arena ar(ws, ws_bytes);
+  double* D = ar.take<double>((size_t)n_merges * n_int * n_int);
+  double* Bg = ar.take<double>((size_t)n_merges * tp.n_ext * tp.n_intf * m * m);
+  if (!D || !Bg) return fail_arg(13, "merge: workspace too small");
+  void* lu_ws = ar.base + ar.off;
+  const size_t lu_ws_bytes = ar.cap - ar.off;
+
+  {
+    const int cols = n_int + n_ext + n_src;
+    dim3 grid(std::min((cols + 255) / 256, 64), n_int, n_merges);
+    merge_gather_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, D, S, gt);
+    HPS_LAUNCH_CHECK("merge_gather_kernel");
+  }
+  const int64_t sS = (int64_t)n_int * n_ext, sG = (int64_t)n_int * n_src;
+  RhsDesc rhs[2] = {{S, n_ext, sS, n_ext}, {gt, n_src, sG, n_src}};
+  HPS_TRY(lu_solve(st, n_merges, n_int, D, n_int, (int64_t)n_int * n_int, 2, rhs, lu_ws, lu_ws_bytes, info));
+  if (!want_T) return 0;
+
+  {
+    const int cols = n_ext + tp.n_intf * m + n_src;
+    dim3 grid(std::min((cols + 255) / 256, 64), n_ext, n_merges);
+    merge_ext_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, T_out, h_out, Bg);
+    HPS_LAUNCH_CHECK("merge_ext_kernel");
+  }
+  const int64_t sT = (int64_t)n_ext * n_ext, sH = (int64_t)n_ext * n_src;
+  const int64_t sB = (int64_t)tp.n_ext * tp.n_intf * m * m;
+  for (int e = 0; e < tp.n_ext; ++e)
+    for (int j = 0; j < tp.n_intf; ++j) {
+      const int s = tp.ext_slot[e][j];
+      const double* Ablk = Bg + ((int64_t)e * tp.n_intf + j) * m * m;
+      // T_out[panel e rows, :] += B_block * S[slot s rows, :]
+      HPS_TRY(dgemm(st, m, n_ext, m, 1.0, Ablk, m, sB, S + (int64_t)s * m * n_ext, n_ext, sS, 1.0,
+                    T_out + (int64_t)e * m * n_ext, n_ext, sT, n_merges));
+      // h_out[panel e rows] += B_block * g~[slot s rows]
+      HPS_TRY(dgemm(st, m, n_src, m, 1.0, Ablk, m, sB, gt + (int64_t)s * m * n_src, n_src, sG, 1.0,
+                    h_out + (int64_t)e * m * n_src, n_src, sH, n_merges));
+    }
+  return 0;
+}
+
+int down_level(const Topo& tp, cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
+               const double* gt, double* g_children, void* ws) {
+  if (n_nodes <= 0 || m <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
+  if (n_nodes > 65535) return fail_arg(2, "n_nodes per call is limited to 65535");
+  const int n_int = tp.n_slot * m, n_ext = tp.n_ext * m;
+  double* g_int = static_cast<double*>(ws);
+  // g_int = S g_ext + g~
+  HPS_TRY(dgemm_affine(st, n_int, n_src, n_ext, S, n_ext, (int64_t)n_int * n_ext, g_ext, n_src, (int64_t)n_ext * n_src,
+                       gt, n_src, (int64_t)n_int * n_src, g_int, n_src, (int64_t)n_int * n_src, n_nodes));
+  const int64_t per_node = (int64_t)tp.n_child * tp.n_face * m * n_src;
+  dim3 grid((unsigned)std::min<int64_t>((per_node + 255) / 256, 1024), n_nodes);
+  down_scatter_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, g_ext, g_int, g_children);
+  HPS_LAUNCH_CHECK("down_scatter_kernel");
+  return 0;
+}
+
+}  // namespace
+
+size_t merge_oct_ws_bytes(int n_merges, int m) { return merge_ws_bytes(oct_topo(), n_merges, m); }
+size_t merge_quad_ws_bytes(int n_merges, int m) { return merge_ws_bytes(quad_topo(), n_merges, m); }
+
+int merge_oct_level(cudaStream_t st, int n_merges, int m, int n_src, const double* T_in, const double* h_in, double* S,
+                    double* gt, double* T_out, double* h_out, int want_T, void* ws, size_t ws_bytes, int* info) {
+  return merge_level(oct_topo(), st, n_merges, m, n_src, T_in, h_in, S, gt, T_out, h_out, want_T, ws, ws_bytes, info);
+}
+int merge_quad_level(cudaStream_t st, int n_merges, int m, int n_src, const double* T_in, const double* h_in,
+                     double* S, double* gt, double* T_out, double* h_out, int want_T, void* ws, size_t ws_bytes,
+                     int* info) {
+  return merge_level(quad_topo(), st, n_merges, m, n_src, T_in, h_in, S, gt, T_out, h_out, want_T, ws, ws_bytes, info);
+}
+int down_oct_level(cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
+                   const double* gt, double* g_children, void* ws) {
+  return down_level(oct_topo(), st, n_nodes, m, n_src, S, g_ext, gt, g_children, ws);
+}
+int down_quad_level(cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
+                    const double* gt, double* g_children, void* ws) {
+  return down_level(quad_topo(), st, n_nodes, m, n_src, S, g_ext, gt, g_children, ws);
+}
+
+}  // namespace hps
