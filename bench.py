@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — HPS build_solver + solve on B200, the metric BASELINE.json names.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--L L]
+
+One "step" = one full pass of the hot path over the batch of leaves:
+local_solve_stage -> merge_stage (all levels) -> down_pass, 3D Poisson-type operator with a
+synthetic variable coefficient field, p=12, q=10, FP64 (BASELINE config 3).  At N=1 the tree
+has L=3 levels (512 leaves) — the largest configuration whose operators fit one GPU (L=4 needs
+a 76 800^2 root merge, 47 GB for D alone plus 94 GB for S).
+
+value      = leaves per second through build+solve with inputs resident in HBM.
+e2e        = same through the public API with HOST (pinned) inputs and the solution read back.
+roofline   = DMMA GEMM kernel: algorithmic flops / summed CUDA-event launch time vs the measured
+             cuBLAS DGEMM rate on this pool's B200s (profiles/r01_fp64_probe.txt).
+cpu_baseline / --impl reference = the NumPy oracle (restatement of the reference's algorithm;
+             the reference's JAX runtime is not installable) on the box's host cores, on a
+             bounded sample of the workload (one depth-1 subtree: 8 leaves, 1 merge, 1 solve).
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P, Q = 12, 10
+# measured on this pool's B200 (profiles/r01_fp64_probe.txt): cuBLAS DGEMM 8192^3
+FP64_PEAK_TFLOPS = 35.4
+FP64_PEAK_TFLOPS_SUSTAINED = 35.4
+
+
+def synthetic_fields(L, p=P, leaf_slice=None):
+    """Seeded synthetic coefficient field c(x) = 1 + 0.5 exp(-|x-1/2|^2/0.1) on D_xx,D_yy,D_zz, a
+    wavefront-type source and Dirichlet data."""
+    import jaxhps_b200 as hps
+
+    root = hps.DiscretizationNode3D(0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+    dom = hps.Domain(p, Q, root, L)
+    x = dom.interior_points
+    r2 = ((x - 0.5) ** 2).sum(axis=-1)
+    c = 1.0 + 0.5 * np.exp(-r2 / 0.1)
+    rr = np.sqrt(((x + 0.05) ** 2).sum(axis=-1))
+    src = 10.0 / (1.0 + 100.0 * (rr - 0.7) ** 2)
+    b = dom.boundary_points
+    g = np.arctan(10.0 * (np.sqrt(((b + 0.05) ** 2).sum(axis=-1)) - 0.7))
+    return dom, c, src, g
+
+
+def lean_flops(L, p=P, q=Q, root_T=False):
+    """Algorithmic flops of one build: LU+solve formulation, block-sparse B."""
+    n_i, n_b, n_c, n_g = (p - 2) ** 3, p**3 - (p - 2) ** 3, p**3, 6 * q * q
+    leaf = (2 / 3) * n_i**3 + 2 * n_i**2 * (n_g + 1) + 2 * n_i * n_b * n_g + 2 * n_g * n_c * n_g
+    total = 8**L * leaf
+    m = q * q
+    for level in range(L, 0, -1):
+        n_merges = 8 ** (level - 1)
+        per = 11520 if (level > 1 or root_T) else 8064
+        total += n_merges * per * float(m) ** 3
+        m *= 4
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        load = [s for s in sm if s > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------- CPU arm
+
+
+def cpu_sample_step(pb_sample, g_sample):
+    from oracle import hps_oracle as orc
+
+    Y, T, v, h = orc.local_solve_stage_uniform_3D_DtN(pb_sample)
+    S, gt = orc.merge_stage_uniform_3D_DtN(T, h, 1)
+    return orc.down_pass_uniform_3D_DtN(g_sample, S, gt, Y, v)
+
+
+def cpu_sample_problem():
+    """One depth-1 subtree of the workload: 8 leaves of the p=12 problem, one oct merge, one solve."""
+    import jaxhps_b200 as hps
+
+    dom, c, src, g = synthetic_fields(1)
+    pb = hps.PDEProblem(dom, source=src, D_xx_coefficients=c, D_yy_coefficients=c, D_zz_coefficients=c)
+    _ = pb.D_xx, pb.D_yy, pb.D_zz  # operator pre-compute is not part of the timed path
+    return pb, g
+
+
+def time_cpu(steps, warmup):
+    pb, g = cpu_sample_problem()
+    for _ in range(warmup):
+        cpu_sample_step(pb, g)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_sample_step(pb, g)
+        ts.append(time.perf_counter() - t0)
+    return 8, ts
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = max((d.get("num_threads", 1) for d in threadpool_info()), default=1)
+        return int(n)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+SAMPLE_DESC = ("one depth-1 subtree of the workload (8 leaves p=12 q=10: local solves as written with explicit "
+               "inverses, 1 oct merge m=100, 1 down pass), NumPy oracle on OpenBLAS")
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n_leaves, ts = time_cpu(max(1, args.steps), max(1, min(args.warmup, 1)))
+    t = sum(ts) / len(ts)
+    val = n_leaves / t
+    line = {
+        "impl": "reference", "metric": "leaf_solves_per_s_build_plus_solve", "value": val, "unit": "leaves/s",
+        "n_gpus": args.gpus, "steps": len(ts), "warmup": max(1, min(args.warmup, 1)), "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3D variable-coefficient Poisson, uniform octree p={P} q={Q}, DtN, FP64", "L": args.L,
+                   "sample": SAMPLE_DESC},
+        "cpu_baseline": {"value": val, "unit": "leaves/s", "cores": cpu_threads(), "kind": "port", "sample": SAMPLE_DESC},
+        "e2e": {"value": val, "unit": "leaves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- GPU arm
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    import jaxhps_b200 as hps
+    from jaxhps_b200 import _lib
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    L = args.L
+    dom, c_h, src_h, g_h = synthetic_fields(L)
+    n_leaves = dom.n_leaves
+    if world > 1:
+        from jaxhps_b200 import _dist
+
+        plan = _dist.SubtreePlan(L, rank, world)
+        sl = plan.leaf_slice
+    else:
+        plan, sl = None, slice(0, n_leaves)
+    # host (pinned) and resident copies of this rank's inputs
+    c_pin = torch.from_numpy(np.ascontiguousarray(c_h[sl])).pin_memory()
+    s_pin = torch.from_numpy(np.ascontiguousarray(src_h[sl])).pin_memory()
+    g_pin = torch.from_numpy(g_h).pin_memory()
+    c_dev, s_dev, g_dev = c_pin.to(dev), s_pin.to(dev), g_pin.to(dev)
+
+    def make_problem(c, s):
+        if plan is None:
+            return hps.PDEProblem(dom, source=s, D_xx_coefficients=c, D_yy_coefficients=c, D_zz_coefficients=c)
+        return _dist.local_problem(dom, plan, source=s, D_xx_coefficients=c, D_yy_coefficients=c, D_zz_coefficients=c)
+
+    pb_res = make_problem(c_dev, s_dev)
+    pb_host = make_problem(c_pin, s_pin)
+
+    def step(pb, g, to_host):
+        pb.reset()
+        if plan is None:
+            hps.build_solver(pb, compute_device=dev, host_device=dev)
+            u = hps.solve(pb, g, compute_device=dev, host_device=dev)
+        else:
+            state = _dist.build_solver_sharded(pb, plan, dev)
+            u = _dist.solve_sharded(pb, state, plan, g, dev)
+        if to_host:
+            return u.cpu()
+        return u
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(pb, g, to_host, steps, sampler=None):
+        barrier()
+        if sampler:
+            sampler.start()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            step(pb, g, to_host)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+        # max over ranks
+        if dist is not None:
+            t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return ms, wall, clocks
+
+    for _ in range(args.warmup):
+        step(pb_res, g_dev, False)
+    # device-resident timing, with the library's kernel timers on (2 event records per GEMM /
+    # panel launch; ~0.5% of the step)
+    lib.hps_prof_enable(1)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, wall, clocks = timed(pb_res, g_dev, False, args.steps, sampler)
+    pm = (ctypes.c_double * 2)()
+    pw = (ctypes.c_double * 2)()
+    pl = (ctypes.c_int64 * 2)()
+    allk = ctypes.c_int64()
+    _lib.check(lib.hps_prof_read(_lib.stream_ptr(), pm, pw, pl, ctypes.byref(allk)), "hps_prof_read")
+    lib.hps_prof_enable(0)
+    ms_step = ms / args.steps
+    value = n_leaves / (ms_step * 1e-3)
+
+    # end-to-end: host inputs -> public API -> host result, copies inside the timed region
+    step(pb_host, g_pin, True)
+    ms_e, _, _ = timed(pb_host, g_pin, True, args.steps)
+    e2e_value = n_leaves / (ms_e / args.steps * 1e-3)
+    h2d = (c_pin.numel() + s_pin.numel() + g_pin.numel()) * 8
+    d2h = (n_leaves // world) * P**3 * 8
+
+    if rank != 0:
+        return
+    gemm_ms, gemm_flops, gemm_launches = pm[0], pw[0], pl[0]
+    achieved = gemm_flops / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
+    cpu_leaves, cpu_ts = time_cpu(1, 1) if world == 1 else (8, [float("nan")])
+    cpu_val = cpu_leaves / cpu_ts[0]
+    line = {
+        "metric": "leaf_solves_per_s_build_plus_solve", "value": value, "unit": "leaves/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3D variable-coefficient Poisson, uniform octree p={P} q={Q}, DtN, FP64", "L": L,
+                   "n_leaves": n_leaves, "n_bdry": int(g_h.shape[0]),
+                   "parallelism": "single GPU" if world == 1 else f"subtree-sharded x{world}, replicated root LU",
+                   "l2_policy": "working set (>=15 GB of operators per step) far exceeds the 126 MB L2; no flush needed"},
+        "build_solve_seconds": ms_step * 1e-3,
+        "algorithmic_tflop_per_step": lean_flops(L) * 1e-12,
+        "step_tflops": lean_flops(L) * 1e-12 / (ms_step * 1e-3),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "leaves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e / args.steps},
+        "gpu_launches": int(allk.value),
+        "roofline": {"kernel": "hps::gemm_kernel (DMMA m8n8k4 FP64)", "bound": "tensor", "achieved": achieved,
+                     "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
+                     "peak_source": "measured cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/r01_fp64_probe.txt); "
+                                    "MEASURED_PEAKS.json has no FP64 entry",
+                     "launches": int(gemm_launches), "gemm_ms_per_step": gemm_ms / args.steps,
+                     "share_of_step": gemm_ms / ms, "traffic": None,
+                     "panel_kernel_ms_per_step": pm[1] / args.steps, "panel_launches": int(pl[1])},
+        "cpu_baseline": {"value": cpu_val, "unit": "leaves/s", "cores": cpu_threads(), "kind": "port",
+                         "sample": SAMPLE_DESC},
+        "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--L", type=int, default=3)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,15 @@ extern "C" {
 int hps_version(void);
 const char* hps_last_error_string(void);
 
+/* Optional device-side timing of the two dominant kernels (CUDA events on the launching
+ * stream), used by bench.py for the roofline numbers.  hps_prof_enable(1) resets and starts
+ * recording, hps_prof_read synchronises `stream` and returns, per category (0 = DMMA GEMM:
+ * work in flops; 1 = LU panel kernel: work in panel entries), the summed launch time in ms,
+ * the summed work and the launch count, plus the number of kernel launches of any kind
+ * the library issued since the reset.  ms/work/launches: HOST arrays of length 2. */
+int hps_prof_enable(int on);
+int hps_prof_read(void* stream, double* ms, double* work, int64_t* launches, int64_t* all_launches);
+
 /* ---- dense building blocks (exported for tests, benches and the jax.ffi shim) ------
  * C[b] = alpha * A[b] (MxK) * B[b] (KxN) + beta * C[b], b < batch, element strides sX.
  * FP64 tensor-core (DMMA) kernel.  Replaces the XLA dot_general calls on the path

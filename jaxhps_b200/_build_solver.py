@@ -26,17 +26,20 @@ def build_solver(pde_problem: PDEProblem, return_top_T: bool = False, compute_de
         raise NotImplementedError("adaptive discretisations are outside the hot path built so far")
     if pde_problem.use_ItI:
         raise NotImplementedError("2D ItI merges run on the oracle only so far; the CUDA path covers DtN")
-    if pde_problem.domain.bool_2D:
-        Y, T, v, h = local_solve_stage_uniform_2D_DtN(pde_problem, device=compute_device, host_device=compute_device)
-        merge_fn = merge_stage_uniform_2D_DtN
-    else:
-        Y, T, v, h = local_solve_stage_uniform_3D_DtN(pde_problem, device=compute_device, host_device=compute_device)
-        merge_fn = merge_stage_uniform_3D_DtN
     from . import _lib
 
+    # leaf outputs stay on the compute device between the two stages (the reference round-trips
+    # them through the host, `_build_solver.py:136-169`, which its docs name as the bottleneck)
+    dev = _lib.require_cuda(compute_device)
+    if pde_problem.domain.bool_2D:
+        Y, T, v, h = local_solve_stage_uniform_2D_DtN(pde_problem, device=dev, host_device=dev)
+        merge_fn = merge_stage_uniform_2D_DtN
+    else:
+        Y, T, v, h = local_solve_stage_uniform_3D_DtN(pde_problem, device=dev, host_device=dev)
+        merge_fn = merge_stage_uniform_3D_DtN
     pde_problem.Y = _lib.to_result(Y, host_device)
     pde_problem.v = _lib.to_result(v, host_device)
-    out = merge_fn(T, h, l=pde_problem.domain.L, device=compute_device, host_device=host_device, return_T=return_top_T)
+    out = merge_fn(T, h, l=pde_problem.domain.L, device=dev, host_device=host_device, return_T=return_top_T)
     pde_problem.S_lst = out[0]
     pde_problem.g_tilde_lst = out[1]
     if return_top_T:

@@ -26,6 +26,8 @@ _sz = ctypes.c_size_t
 _SIGNATURES = {
     "hps_version": (_i, []),
     "hps_last_error_string": (ctypes.c_char_p, []),
+    "hps_prof_enable": (_i, [_i]),
+    "hps_prof_read": (_i, [_p, ctypes.POINTER(_d), ctypes.POINTER(_d), ctypes.POINTER(_l), ctypes.POINTER(_l)]),
     "hps_dgemm_strided_batched": (_i, [_p, _i, _i, _i, _d, _p, _l, _l, _p, _l, _l, _d, _p, _l, _l, _i]),
     "hps_lu_solve_workspace": (_i, [_i, _i, ctypes.POINTER(_sz)]),
     "hps_lu_solve": (_i, [_p, _i, _i, _p, _l, _l, _i, ctypes.POINTER(_p), ctypes.POINTER(_l),
@@ -85,6 +87,8 @@ def require_cuda(device=None) -> torch.device:
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     if dev.type != "cuda":
         raise HpsLibraryError(f"compute device must be a CUDA device, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
     return dev
 
 
@@ -122,8 +126,12 @@ def to_device(x, dev: torch.device, dtype=torch.float64) -> torch.Tensor:
 def to_result(t: torch.Tensor, host_device):
     """Device tensor -> what the caller asked for (NumPy on the host, or the tensor itself)."""
     if is_host(host_device):
-        return t.cpu().numpy()
+        return t.cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
     dev = torch.device(host_device)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    if not isinstance(t, torch.Tensor):
+        return to_device(t, dev)
     return t if t.device == dev else t.to(dev)
 
 

@@ -1,6 +1,8 @@
 // extern "C" surface of libhps_b200.so (declared in include/hps_b200.h).
 #include "../../include/hps_b200.h"
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace hps {
@@ -16,6 +18,40 @@ int fail_cuda(cudaError_t e, const char* where) {
   last_error() = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + where;
   return static_cast<int>(e);
 }
+long long g_launches = 0;
+
+namespace {
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { int cat; size_t e0, e1; double work; };
+  std::vector<Rec> recs;
+  size_t open_rec[PROF_NCAT] = {0, 0};
+  cudaEvent_t take() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+} g_prof;
+}  // namespace
+
+void prof_begin(int cat, cudaStream_t st, double work) {
+  if (!g_prof.on) return;
+  const size_t i0 = g_prof.used;
+  cudaEventRecord(g_prof.take(), st);
+  g_prof.open_rec[cat] = g_prof.recs.size();
+  g_prof.recs.push_back({cat, i0, i0, work});
+}
+void prof_end(int cat, cudaStream_t st) {
+  if (!g_prof.on) return;
+  const size_t i1 = g_prof.used;
+  cudaEventRecord(g_prof.take(), st);
+  g_prof.recs[g_prof.open_rec[cat]].e1 = i1;
+}
 }  // namespace hps
 
 using namespace hps;
@@ -24,6 +60,28 @@ extern "C" {
 
 int hps_version(void) { return 100; }
 const char* hps_last_error_string(void) { return last_error().c_str(); }
+
+int hps_prof_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.used = 0;
+  g_prof.recs.clear();
+  g_launches = 0;
+  return 0;
+}
+
+int hps_prof_read(void* stream, double* ms, double* work, int64_t* launches, int64_t* all_launches) {
+  HPS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  for (int c = 0; c < PROF_NCAT; ++c) { ms[c] = 0.0; work[c] = 0.0; launches[c] = 0; }
+  for (const auto& r : g_prof.recs) {
+    float t = 0.f;
+    HPS_CUDA(cudaEventElapsedTime(&t, g_prof.pool[r.e0], g_prof.pool[r.e1]));
+    ms[r.cat] += t;
+    work[r.cat] += r.work;
+    launches[r.cat] += 1;
+  }
+  *all_launches = g_launches;
+  return 0;
+}
 
 int hps_dgemm_strided_batched(void* stream, int M, int N, int K, double alpha, const double* A, int64_t lda,
                               int64_t sA, const double* B, int64_t ldb, int64_t sB, double beta, double* C,

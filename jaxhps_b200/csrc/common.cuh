@@ -18,11 +18,20 @@ int fail_cuda(cudaError_t e, const char* where);
     if (_e != cudaSuccess) return ::hps::fail_cuda(_e, #call);    \
   } while (0)
 
+// every kernel launch site goes through this (or bumps g_launches itself)
+extern long long g_launches;
 #define HPS_LAUNCH_CHECK(name)                                    \
   do {                                                            \
+    ++::hps::g_launches;                                          \
     cudaError_t _e = cudaGetLastError();                          \
     if (_e != cudaSuccess) return ::hps::fail_cuda(_e, name);     \
   } while (0)
+
+// Optional per-category device timing (CUDA events on the launching stream), used by bench.py
+// for the roofline of the dominant kernels.  Off by default: zero overhead on the product path.
+enum ProfCat { PROF_GEMM = 0, PROF_PANEL = 1, PROF_NCAT = 2 };
+void prof_begin(int cat, cudaStream_t st, double work);
+void prof_end(int cat, cudaStream_t st);
 
 #define HPS_TRY(expr)          \
   do {                         \

@@ -287,12 +287,14 @@ int dgemm(cudaStream_t st, int M, int N, int K, double alpha, const double* A, i
   g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
   g.lda = lda; g.sA = sA; g.ldb = ldb; g.sB = sB; g.ldc = ldc; g.sC = sC;
   g.vecA = vec_ok(A, lda, sA); g.vecB = vec_ok(B, ldb, sB); g.vecC = vec_ok(C, ldc, sC);
+  prof_begin(PROF_GEMM, st, 2.0 * M * N * (double)K * batch);
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = min(65535, batch - b0);
     g.A = A + (int64_t)b0 * sA; g.B = B + (int64_t)b0 * sB; g.C = C + (int64_t)b0 * sC;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, nb);
     gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(g);
   }
+  prof_end(PROF_GEMM, st);
   HPS_LAUNCH_CHECK("gemm_kernel");
   return 0;
 }

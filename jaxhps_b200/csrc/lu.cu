@@ -330,7 +330,14 @@ bool carve(Arena& ar, int batch, int n, LuWorkspace& w) {
 
 int g_coop_capacity = -1;  // co-resident panel CTAs for the cooperative variant
 
+int launch_panel_impl(cudaStream_t st, int batch, PanelArgs pa);
 int launch_panel(cudaStream_t st, int batch, PanelArgs pa) {
+  prof_begin(PROF_PANEL, st, (double)batch * (pa.n - pa.jj) * pa.ib);
+  const int rc = launch_panel_impl(st, batch, pa);
+  prof_end(PROF_PANEL, st);
+  return rc;
+}
+int launch_panel_impl(cudaStream_t st, int batch, PanelArgs pa) {
   const int rows = pa.n - pa.jj;
   int G = (rows + PANEL_ROWS - 1) / PANEL_ROWS;
   if (G <= 1) {
@@ -355,6 +362,7 @@ int launch_panel(cudaStream_t st, int batch, PanelArgs pa) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     HPS_CUDA(cudaLaunchKernelEx(&cfg, panel_kernel<SYNC_CLUSTER>, pa));
+    ++g_launches;
     return 0;
   }
   if (G > MAX_G) return fail_arg(3, "matrix too tall for the panel kernel (n > 49152)");
@@ -381,6 +389,7 @@ int launch_panel(cudaStream_t st, int batch, PanelArgs pa) {
     void* args[] = {&sub};
     HPS_CUDA(cudaLaunchCooperativeKernel((void*)panel_kernel<SYNC_GRID>, dim3(G, nb), dim3(PANEL_THREADS), args,
                                          PANEL_SMEM, st));
+    ++g_launches;
   }
   return 0;
 }

@@ -319,3 +319,127 @@ def down_pass_uniform_3D_DtN(boundary_data, S_lst, g_tilde_lst, Y_arr, v_arr):
     if bdry.ndim == 3:
         return np.einsum("ijk,ikl->ijl", Y_arr, bdry) + v_arr
     return np.einsum("ijk,ik->ij", Y_arr, bdry) + v_arr
+
+
+# =====================================================================================
+# 2D quad merge, DtN.  Children a..d = SW, SE, NE, NW; sides 0..3 = S, E, N, W, each walked
+# counter-clockwise (S: W->E, E: S->N, N: E->W, W: N->S).
+# =====================================================================================
+
+_QUAD_POS = [(0, 0), (1, 0), (1, 1), (0, 1)]
+# interfaces 5:a|b 6:b|c 7:c|d 8:d|a; the first child of each pair fixes the orientation
+# (`merge/_uniform_2D_DtN.py:385-437`)
+_QUAD_INTERFACES = [(0, 1), (1, 2), (2, 3), (3, 0)]
+# side -> (axis normal to it, which end): S is y-, E is x+, N is y+, W is x-
+_QUAD_SIDE_AXIS = [(1, 0), (0, 1), (1, 1), (0, 0)]
+
+
+def _quad_roles():
+    """roles[child][side] = ("ext", panel) with the parent's boundary panels numbered
+    counter-clockwise from the SW corner (a.S b.S b.E c.E c.N d.N d.W a.W), or
+    ("int", slot, flipped)."""
+    panel_order = [(0, 0), (1, 0), (1, 1), (2, 1), (2, 2), (3, 2), (3, 3), (0, 3)]  # (child, side)
+    roles = []
+    for c, pos in enumerate(_QUAD_POS):
+        r = []
+        for side in range(4):
+            axis, end = _QUAD_SIDE_AXIS[side]
+            if pos[axis] == end:
+                r.append(("ext", panel_order.index((c, side)), False))
+            else:
+                nb_pos = list(pos)
+                nb_pos[axis] = end
+                nb = _QUAD_POS.index(tuple(nb_pos))
+                slot = [i for i, pr in enumerate(_QUAD_INTERFACES) if set(pr) == {c, nb}][0]
+                r.append(("int", slot, _QUAD_INTERFACES[slot][0] != c))
+        roles.append(r)
+    return roles
+
+
+_QUAD_ROLES = _quad_roles()
+
+
+def _side_idx(side: int, m: int, flipped: bool) -> np.ndarray:
+    idx = np.arange(side * m, (side + 1) * m)
+    return idx[::-1] if flipped else idx
+
+
+def uniform_quad_merge_DtN(T_children: np.ndarray, h_children: np.ndarray):
+    """One quad merge with dense B, C, D and explicit ``inv(D)``
+    (`merge/_uniform_2D_DtN.py:206-348`); exterior unknowns come out in boundary order, which
+    is what the reference's ``roll(-n_int)`` achieves.  T_children (4, 4m, 4m)."""
+    m = T_children.shape[-1] // 4
+    tail = h_children.shape[2:]
+    # assemble in the reference's pre-roll order [a:(W,S) b:(S,E) c:(E,N) d:(N,W)]
+    pre = [(0, 3), (0, 0), (1, 0), (1, 1), (2, 1), (2, 2), (3, 2), (3, 3)]  # (child, side)
+    B = np.zeros((8 * m, 4 * m))
+    C = np.zeros((4 * m, 8 * m))
+    D = np.zeros((4 * m, 4 * m))
+    h_int = np.zeros((4 * m,) + tail)
+    h_ext = np.zeros((8 * m,) + tail)
+    A_lst = []
+    blk = lambda k: slice(k * m, (k + 1) * m)  # noqa: E731
+    for c in range(4):
+        T, h = T_children[c], h_children[c]
+        ext = [(pre.index((c, s)), _side_idx(s, m, False)) for s in range(4) if _QUAD_ROLES[c][s][0] == "ext"]
+        ext.sort(key=lambda t: t[0])
+        inte = [(_QUAD_ROLES[c][s][1], _side_idx(s, m, _QUAD_ROLES[c][s][2])) for s in range(4) if _QUAD_ROLES[c][s][0] == "int"]
+        ext_idx = np.concatenate([ix for _, ix in ext])
+        A_lst.append(T[np.ix_(ext_idx, ext_idx)])
+        for k, ix in ext:
+            h_ext[blk(k)] = h[ix]
+            for s, jx in inte:
+                B[blk(k), blk(s)] = T[np.ix_(ix, jx)]
+                C[blk(s), blk(k)] = T[np.ix_(jx, ix)]
+        for s, ix in inte:
+            h_int[blk(s)] += h[ix]
+            for s2, jx in inte:
+                D[blk(s), blk(s2)] += T[np.ix_(ix, jx)]
+    D_inv = np.linalg.inv(D)
+    T, S, h_out, g_tilde = assemble_merge_outputs(A_lst, B, C, D_inv, h_ext, h_int)
+    T = np.roll(np.roll(T, -m, axis=0), -m, axis=1)
+    return np.roll(S, -m, axis=1), T, np.roll(h_out, -m, axis=0), g_tilde
+
+
+def merge_stage_uniform_2D_DtN(T_arr: np.ndarray, h_arr: np.ndarray, l: int, return_T: bool = False):
+    """Level loop (`merge/_uniform_2D_DtN.py:13-203`); every entry of the lists keeps its batch
+    axis, the root's being 1 (`:192-197`)."""
+    S_lst, g_lst = [], []
+    for _ in range(l):
+        n = T_arr.shape[0] // 4
+        outs = [uniform_quad_merge_DtN(T_arr[4 * i : 4 * i + 4], h_arr[4 * i : 4 * i + 4]) for i in range(n)]
+        S_lst.append(np.stack([o[0] for o in outs]))
+        T_arr = np.stack([o[1] for o in outs])
+        h_arr = np.stack([o[2] for o in outs])
+        g_lst.append(np.stack([o[3] for o in outs]))
+    if return_T:
+        return S_lst, g_lst, T_arr[0]
+    return S_lst, g_lst
+
+
+def propagate_down_quad_DtN(S: np.ndarray, g_ext: np.ndarray, g_tilde: np.ndarray) -> np.ndarray:
+    """(4, 4m[, n_src]) child boundary data (`down_pass/_uniform_2D_DtN.py:125-189`)."""
+    m = g_ext.shape[0] // 8
+    g_int = S @ g_ext + g_tilde
+    kids = []
+    for c in range(4):
+        parts = []
+        for side in range(4):
+            kind, k, flipped = _QUAD_ROLES[c][side]
+            seg = g_ext[k * m : (k + 1) * m] if kind == "ext" else g_int[k * m : (k + 1) * m]
+            parts.append(seg[::-1] if flipped else seg)
+        kids.append(np.concatenate(parts))
+    return np.stack(kids)
+
+
+def down_pass_uniform_2D_DtN(boundary_data, S_lst, g_tilde_lst, Y_arr, v_arr):
+    """(`down_pass/_uniform_2D_DtN.py:7-122`); ``Y_arr=None`` returns the leaves' boundary data."""
+    bdry = np.asarray(boundary_data)[None]
+    for level in range(len(S_lst) - 1, -1, -1):
+        kids = [propagate_down_quad_DtN(S_lst[level][i], bdry[i], g_tilde_lst[level][i]) for i in range(bdry.shape[0])]
+        bdry = np.concatenate(kids, axis=0)
+    if Y_arr is None:
+        return bdry
+    if bdry.ndim == 3:
+        return np.einsum("ijk,ikl->ijl", Y_arr, bdry) + v_arr
+    return np.einsum("ijk,ik->ij", Y_arr, bdry) + v_arr

@@ -1,0 +1,56 @@
+"""Shared, seeded problem builders for the tests (same recipe as tests/golden/make_golden.py)."""
+import glob
+import os
+
+import numpy as np
+
+import jaxhps_b200 as hps
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+
+
+def make_domain(dim, p, q, L):
+    if dim == 3:
+        root = hps.DiscretizationNode3D(0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+    else:
+        root = hps.DiscretizationNode2D(-1.0, 1.0, -1.0, 1.0)
+    return hps.Domain(p, q, root, L)
+
+
+def seeded_inputs(dim, p, q, L, nsrc, seed):
+    rng = np.random.default_rng(seed)
+    n_leaves = (8 if dim == 3 else 4) ** L
+    shp = (n_leaves, p**dim)
+    names = ["D_xx", "D_yy"] + (["D_zz"] if dim == 3 else [])
+    co = {f"{k}_coefficients": 1 + 0.1 * rng.normal(size=shp) for k in names}
+    co["D_xy_coefficients"] = 0.1 * rng.normal(size=shp)
+    co["D_y_coefficients"] = rng.normal(size=shp)
+    co["I_coefficients"] = rng.normal(size=shp)
+    if dim == 3:
+        co["D_z_coefficients"] = rng.normal(size=shp)
+        co["D_yz_coefficients"] = 0.1 * rng.normal(size=shp)
+    src = rng.normal(size=shp if nsrc == 1 else shp + (nsrc,))
+    n_bdry = (6 * 4**L * q * q) if dim == 3 else (4 * 2**L * q)
+    bdry = rng.normal(size=(n_bdry,) if nsrc == 1 else (n_bdry, nsrc))
+    return co, src, bdry
+
+
+def seeded_problem(dim, p, q, L, nsrc=1, seed=0):
+    co, src, bdry = seeded_inputs(dim, p, q, L, nsrc, seed)
+    dom = make_domain(dim, p, q, L)
+    return hps.PDEProblem(dom, source=src, **co), bdry
+
+
+def rel_err(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))

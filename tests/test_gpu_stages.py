@@ -1,0 +1,92 @@
+"""GPU parity of the three stages against the CPU oracle and the reference-generated golden
+fixtures; every call goes through the reference-shaped stage functions -> ctypes -> C ABI.
+Tolerance: 1e-10 relative (max-norm), the bar BASELINE.json's north_star states for FP64."""
+import numpy as np
+import pytest
+
+import jaxhps_b200 as hps
+from jaxhps_b200.down_pass import down_pass_uniform_2D_DtN, down_pass_uniform_3D_DtN
+from jaxhps_b200.local_solve import local_solve_stage_uniform_2D_DtN, local_solve_stage_uniform_3D_DtN
+from jaxhps_b200.merge import merge_stage_uniform_2D_DtN, merge_stage_uniform_3D_DtN
+from oracle import hps_oracle as orc
+from _cases import golden_names, load_golden, rel_err, seeded_problem
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+GPU = {3: (local_solve_stage_uniform_3D_DtN, merge_stage_uniform_3D_DtN, down_pass_uniform_3D_DtN),
+       2: (local_solve_stage_uniform_2D_DtN, merge_stage_uniform_2D_DtN, down_pass_uniform_2D_DtN)}
+ORC = {3: (orc.local_solve_stage_uniform_3D_DtN, orc.merge_stage_uniform_3D_DtN, orc.down_pass_uniform_3D_DtN),
+       2: (orc.local_solve_stage_uniform_2D_DtN, orc.merge_stage_uniform_2D_DtN, orc.down_pass_uniform_2D_DtN)}
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_path_matches_reference_fixture(name):
+    G = load_golden(name)
+    dim, p, q, L, nsrc, seed = (int(x) for x in G["meta"])
+    pb, bdry = seeded_problem(dim, p, q, L, nsrc, seed)
+    ls, mg, dp = GPU[dim]
+    Y, T, v, h = ls(pb)
+    S_lst, g_lst, T_top = mg(T, h, L, return_T=True)
+    u = dp(bdry, S_lst, g_lst, Y, v)
+    assert rel_err(v, G["v"]) < TOL and rel_err(h, G["h"]) < TOL
+    for i, g in enumerate(g_lst):
+        assert rel_err(g, G[f"g_tilde_{i}"]) < TOL
+    probe = np.random.default_rng(seed + 1000).normal(size=T_top.shape[1])
+    assert rel_err(T_top @ probe, G["T_top_probe"]) < TOL
+    assert rel_err(u, G["u"]) < TOL
+    if "Y" in G:
+        assert rel_err(Y, G["Y"]) < TOL and rel_err(T, G["T"]) < TOL and rel_err(T_top, G["T_top"]) < TOL
+        for i, S in enumerate(S_lst):
+            assert S.shape == G[f"S_{i}"].shape
+            assert rel_err(S, G[f"S_{i}"]) < TOL
+
+
+@pytest.mark.parametrize(
+    "dim,p,q,L,nsrc",
+    [
+        (3, 6, 4, 2, 1),
+        (3, 7, 5, 1, 1),  # odd p, q: unaligned rows, coincident interpolation nodes
+        (3, 5, 3, 2, 3),  # multi-source
+        (3, 8, 6, 2, 1),
+        (3, 12, 10, 1, 1),  # the BASELINE leaf size (p=12, q=10), one merge
+        (2, 8, 6, 2, 1),
+        (2, 7, 5, 3, 2),
+        (2, 16, 14, 3, 1),  # BASELINE config 1 shape
+    ],
+)
+def test_stages_match_oracle(dim, p, q, L, nsrc):
+    pb, bdry = seeded_problem(dim, p, q, L, nsrc, seed=100 + p)
+    (ls, mg, dp), (ols, omg, odp) = GPU[dim], ORC[dim]
+    Yo, To, vo, ho = ols(pb)
+    Y, T, v, h = ls(pb)
+    for a, b in ((Y, Yo), (T, To), (v, vo), (h, ho)):
+        assert rel_err(a, b) < TOL
+    So, go, Tto = omg(To, ho, L, return_T=True)
+    S, g, Tt = mg(To, ho, L, return_T=True)
+    for a, b in zip(S + g + [Tt], So + go + [Tto]):
+        assert rel_err(a, b) < TOL
+    assert rel_err(dp(bdry, So, go, Yo, vo), odp(bdry, So, go, Yo, vo)) < TOL
+
+
+def test_results_can_stay_on_the_device():
+    import torch
+
+    pb, bdry = seeded_problem(3, 6, 4, 2, 1, seed=7)
+    Yo, To, vo, ho = orc.local_solve_stage_uniform_3D_DtN(pb)
+    dev = torch.device("cuda:0")
+    Y, T, v, h = local_solve_stage_uniform_3D_DtN(pb, device=dev, host_device=dev)
+    assert all(isinstance(t, torch.Tensor) and t.is_cuda for t in (Y, T, v, h))
+    S, g = merge_stage_uniform_3D_DtN(T, h, 2, device=dev, host_device=dev)
+    assert S[-1].ndim == 2 and S[0].ndim == 3 and S[0].is_cuda
+    u = down_pass_uniform_3D_DtN(bdry, S, g, Y, v, device=dev, host_device=None)
+    So, go = orc.merge_stage_uniform_3D_DtN(To, ho, 2)
+    assert rel_err(u, orc.down_pass_uniform_3D_DtN(bdry, So, go, Yo, vo)) < TOL
+
+
+def test_down_pass_rejects_bad_multisource_input():
+    pb, bdry = seeded_problem(3, 4, 2, 2, 2, seed=3)
+    Y, T, v, h = local_solve_stage_uniform_3D_DtN(pb)
+    S, g = merge_stage_uniform_3D_DtN(T, h, 2)
+    with pytest.raises(ValueError):
+        down_pass_uniform_3D_DtN(bdry[:, 0], S, g, Y, v)
