@@ -1,181 +1,24 @@
-// FP64 GEMM for sm_100a built on DMMA (mma.sync.m8n8k4.f64), the only FP64 tensor shape the
-// B200 executes natively (the m16n8k{4,8,16} PTX shapes lower to the same DMMA.8x8x4 SASS;
-// tcgen05 has no f64 kind).  Measured on B200: DMMA peak 37.0 TFLOP/s, cuBLAS DGEMM 35.4.
-//
-// C[b] = alpha * A[b] (MxK) * B[b] (KxN) + beta * C[b]; all row-major.
-//   CTA tile 128x128, K step 16, 4-stage cp.async (LDGSTS) ring, 16 warps each owning a
-//   32x32 accumulator (4x4 DMMA tiles, 32 FP64 accumulators per thread).
-//   Shared-memory leading dimensions are == 4 (mod 16) doubles, which makes both fragment
-//   loads (A: lane -> (row=lane/4, k=lane%4); B: lane -> (k=lane%4, col=lane/4))
-//   conflict-free per half-warp.
+// Host side of the FP64 GEMMs: the DMMA kernel lives in gemm_kernel.cuh (templated on the tile
+// configuration), the narrow-N bandwidth kernel and the dispatch are here.
 #include <algorithm>
 
 #include "common.cuh"
+#include "gemm_kernel.cuh"
 
 namespace hps {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 512;
-constexpr int LDA_S = BK + 4;   // 20 doubles
-constexpr int LDB_S = BN + 4;   // 132 doubles
-constexpr int A_STAGE = BM * LDA_S;
-constexpr int B_STAGE = BK * LDB_S;
-constexpr size_t SMEM_BYTES = sizeof(double) * STAGES * (A_STAGE + B_STAGE);
-
-struct GemmArgs {
-  int M, N, K;
-  double alpha, beta;
-  const double* A; int64_t lda, sA;
-  const double* B; int64_t ldb, sB;
-  double* C; int64_t ldc, sC;
-  int vecA, vecB, vecC;  // 16-byte vector access allowed for that operand
-};
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
-  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
-  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-
-__global__ void __launch_bounds__(THREADS, 1) gemm_kernel(GemmArgs g) {
-  extern __shared__ __align__(16) double smem[];
-  double* As = smem;
-  double* Bs = smem + STAGES * A_STAGE;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
-  const int bm0 = blockIdx.y * BM, bn0 = blockIdx.x * BN;
-  const int64_t batch = blockIdx.z;
-  const double* __restrict__ A = g.A + batch * g.sA;
-  const double* B = g.B + batch * g.sB;  // may alias C (in-place M<=BM products)
-  double* C = g.C + batch * g.sC;
-  const int M = g.M, N = g.N, K = g.K;
-
-  // each thread moves two 16-byte chunks of A and two of B per stage
-  auto load_tile = [&](int stage, int k0) {
-    double* as = As + stage * A_STAGE;
-    double* bs = Bs + stage * B_STAGE;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int c = tid + i * THREADS;
-      {  // A: 128 rows x 8 chunks
-        const int r = c >> 3, kc = (c & 7) * 2;
-        const int gr = bm0 + r, gk = k0 + kc;
-        double* dst = as + r * LDA_S + kc;
-        int valid = (gr < M) ? max(0, min(2, K - gk)) : 0;
-        const double* src = valid ? (A + (int64_t)gr * g.lda + gk) : A;
-        if (g.vecA) {
-          cp_async16(dst, src, valid * 8);
-        } else {
-          cp_async8(dst, src, valid >= 1 ? 8 : 0);
-          cp_async8(dst + 1, valid >= 2 ? src + 1 : A, valid >= 2 ? 8 : 0);
-        }
-      }
-      {  // B: 16 rows x 64 chunks
-        const int r = c >> 6, nc = (c & 63) * 2;
-        const int gk = k0 + r, gn = bn0 + nc;
-        double* dst = bs + r * LDB_S + nc;
-        int valid = (gk < K) ? max(0, min(2, N - gn)) : 0;
-        const double* src = valid ? (B + (int64_t)gk * g.ldb + gn) : B;
-        if (g.vecB) {
-          cp_async16(dst, src, valid * 8);
-        } else {
-          cp_async8(dst, src, valid >= 1 ? 8 : 0);
-          cp_async8(dst + 1, valid >= 2 ? src + 1 : B, valid >= 2 ? 8 : 0);
-        }
-      }
-    }
-  };
-
-  double acc[4][4][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  const int KT = (K + BK - 1) / BK;
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < KT) load_tile(s, s * BK);
-    cp_async_commit();
-  }
-
-  const int a_off = (wm + (lane >> 2)) * LDA_S + (lane & 3);
-  const int b_off = (lane & 3) * LDB_S + wn + (lane >> 2);
-
-  for (int kt = 0; kt < KT; ++kt) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    {
-      const int nk = kt + STAGES - 1;
-      if (nk < KT) load_tile(nk % STAGES, nk * BK);
-      cp_async_commit();
-    }
-    const double* as = As + (kt % STAGES) * A_STAGE + a_off;
-    const double* bs = Bs + (kt % STAGES) * B_STAGE + b_off;
-#pragma unroll
-    for (int k4 = 0; k4 < BK / 4; ++k4) {
-      double a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = as[i * 8 * LDA_S + k4 * 4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = bs[k4 * 4 * LDB_S + j * 8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    }
-  }
-  cp_async_wait<0>();
-
-  // epilogue: lane holds C[row = lane/4][col = 2*(lane%4) + {0,1}] of every 8x8 tile
-  const double alpha = g.alpha, beta = g.beta;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = bm0 + wm + i * 8 + (lane >> 2);
-    if (row >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = bn0 + wn + j * 8 + 2 * (lane & 3);
-      if (col >= N) continue;
-      double* cp = C + (int64_t)row * g.ldc + col;
-      double r0 = alpha * acc[i][j][0], r1 = alpha * acc[i][j][1];
-      if (col + 1 < N) {
-        if (g.vecC) {
-          if (beta != 0.0) {
-            double2 old = *reinterpret_cast<const double2*>(cp);
-            r0 += beta * old.x;
-            r1 += beta * old.y;
-          }
-          *reinterpret_cast<double2*>(cp) = make_double2(r0, r1);
-        } else {
-          if (beta != 0.0) {
-            r0 += beta * cp[0];
-            r1 += beta * cp[1];
-          }
-          cp[0] = r0;
-          cp[1] = r1;
-        }
-      } else {
-        if (beta != 0.0) r0 += beta * cp[0];
-        cp[0] = r0;
-      }
-    }
-  }
-}
+// Tile configuration chosen with tools/gemm_lab.cu on B200 (profiles/r01_gemm_lab.txt):
+// 128x64 CTA tile, 8 warps of 32x32, K step 16, 3-stage ring, two CTAs per SM, per-stage
+// full/empty mbarriers instead of a CTA barrier per K step.
+//   8192^3: 32.9 TF/s (cuBLAS 35.4);  15360^2 rank-128 update: 28.3 (cuBLAS 23.2);
+//   512 x (872^2 rank-128 update): 25.9 (cuBLAS 22.2).
+using Cfg = gemmk::Config<32, 32, 4, 2, 16, 3, 2>;
+using gemmk::GemmArgs;
+constexpr int BM = Cfg::BM, BN = Cfg::BN, THREADS = Cfg::THREADS;
+constexpr size_t SMEM_BYTES = Cfg::SMEM_BYTES;
+#define gemm_kernel gemmk::gemm_kernel_mb<Cfg>
 
 // ---- narrow-N kernel: one warp per output row, lanes stride over K ------------------
 template <int NMAX>
