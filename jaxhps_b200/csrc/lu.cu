@@ -1,20 +1,27 @@
 // Batched blocked LU with partial pivoting + in-place multi-RHS solve, FP64, sm_100a.
 //
 // Replaces the reference's `jnp.linalg.inv(X) @ Y` pairs (local_solve/_uniform_2D_DtN.py:257-259,
-// merge/_schur_complement.py:146,222,234): X^-1 Y is obtained from P X = L U with the right-hand
-// sides carried through the elimination (so L is never revisited) and one blocked back
-// substitution with U.
+// merge/_schur_complement.py:146,222,234): X^-1 Y comes from P X = L U and two blocked triangular
+// solves, never from an explicit inverse of X.
 //
-// Structure (right-looking, two-level blocking NB=128 / IB=32):
+//   1. Factorisation, right-looking, NB=128 outer / IB=32 inner blocking, with LOOK-AHEAD: the
+//      latency-bound chain (panel kernels, 32-wide inner updates, inversion of the 128x128 unit
+//      lower block) runs on an internal high-priority stream one block column ahead of the
+//      rank-128 DMMA trailing update on the caller's stream.
+//   2. Row interchanges applied to the right-hand sides.
+//   3. L Z = P B and U X = Z by RECURSIVE blocked substitution: diagonal 128-blocks are inverted
+//      once (batched over all blocks), everything else is GEMMs whose K grows with the recursion
+//      level, so the right-hand sides — the bulk of the flops in the HPS merges — run at the
+//      large-K rate of the DMMA kernel and are read/written O(log) times instead of n/128 times.
+//
+// Kernels:
 //   panel_kernel   IB columns at a time; the panel's rows are split over G CTAs that keep
-//                  their chunk in shared memory.  One group barrier per column:
-//                  a thread-block cluster barrier for G<=8, a cooperative-launch global
-//                  barrier above that.  Candidates travel through a small global scratch.
+//                  their chunk in shared memory.  One group barrier per column: a thread-block
+//                  cluster barrier for G<=8, a cooperative-launch global barrier above that.
 //   laswp_kernel   row interchanges on a column range (rows are contiguous: coalesced).
 //   inner_trsm     32x32 unit-lower solve inside the outer panel.
-//   trtri kernels  invert the NBxNB triangular diagonal blocks in shared memory so that every
+//   trtri kernels  invert NBxNB triangular diagonal blocks in shared memory so that every
 //                  triangular solve becomes a DMMA GEMM (in place, single tile row).
-//   hps::dgemm     all trailing updates.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -251,14 +258,16 @@ __global__ void inner_trsm_kernel(double* A, int64_t lda, int64_t sA, int jj, in
 // LOWER: unit lower triangle.  !LOWER: upper triangle with its diagonal.
 // In-place column sweep (LAPACK trti2 order) in shared memory; one thread per row.
 template <bool LOWER>
-__global__ void __launch_bounds__(NB) trtri_kernel(const double* A, int64_t lda, int64_t sA, int j, int nb,
+__global__ void __launch_bounds__(NB) trtri_kernel(const double* A, int64_t lda, int64_t sA, int j0, int n,
                                                    double* W, int64_t sW) {
   extern __shared__ __align__(16) double sm[];
   constexpr int LD = NB + 1;
   double* Ts = sm;             // [NB][LD]
   double* colv = sm + NB * LD; // [NB]
+  const int j = j0 + blockIdx.x * NB;      // diagonal block handled by this CTA
+  const int nb = min(NB, n - j);
   const int r = threadIdx.x;
-  const double* a = A + (int64_t)blockIdx.x * sA + (int64_t)j * lda + j;
+  const double* a = A + (int64_t)blockIdx.y * sA + (int64_t)j * lda + j;
   for (int idx = threadIdx.x; idx < nb * nb; idx += NB) {
     const int rr = idx / nb, cc = idx - rr * nb;
     double v = a[(int64_t)rr * lda + cc];
@@ -295,7 +304,7 @@ __global__ void __launch_bounds__(NB) trtri_kernel(const double* A, int64_t lda,
       __syncthreads();
     }
   }
-  double* w = W + (int64_t)blockIdx.x * sW;
+  double* w = W + (int64_t)blockIdx.y * sW + (int64_t)(j / NB) * NB * NB;
   for (int idx = threadIdx.x; idx < nb * nb; idx += NB) {
     const int rr = idx / nb, cc = idx - rr * nb;
     w[rr * NB + cc] = Ts[rr * LD + cc];
@@ -315,17 +324,20 @@ constexpr size_t TRTRI_SMEM = sizeof(double) * (NB * (NB + 1) + NB);
 
 struct LuWorkspace {
   int* ipiv;
-  double* Tinv;
-  double* tmp;  // [batch][NB][16] staging for narrow right-hand sides
+  double* Linv;  // [batch][nblk][NB][NB] inverses of the unit-lower diagonal blocks
+  double* Uinv;  // [batch][nblk][NB][NB] inverses of the upper diagonal blocks
+  double* tmp;   // [batch][NB][16] staging for narrow right-hand sides
   PanelScratch* scratch;
 };
 
 bool carve(Arena& ar, int batch, int n, LuWorkspace& w) {
+  const size_t nblk = (n + NB - 1) / NB;
   w.ipiv = ar.take<int>((size_t)batch * n);
-  w.Tinv = ar.take<double>((size_t)batch * NB * NB);
+  w.Linv = ar.take<double>((size_t)batch * nblk * NB * NB);
+  w.Uinv = ar.take<double>((size_t)batch * nblk * NB * NB);
   w.tmp = ar.take<double>((size_t)batch * NB * 16);
   w.scratch = ar.take<PanelScratch>((size_t)batch);
-  return w.ipiv && w.Tinv && w.tmp && w.scratch;
+  return w.ipiv && w.Linv && w.Uinv && w.tmp && w.scratch;
 }
 
 int g_coop_capacity = -1;  // co-resident panel CTAs for the cooperative variant
@@ -405,9 +417,9 @@ int laswp(cudaStream_t st, int batch, double* A, int64_t lda, int64_t sA, int c0
 // X := Tinv * X for a jb-row block X (in place).  Wide X goes through the DMMA GEMM (one tile
 // row, so in-place is safe); narrow X is staged through tmp because the row-per-warp kernel
 // would read rows other warps have already overwritten.
-int tri_mult(cudaStream_t st, int batch, int jb, const double* Tinv, double* X, int64_t ld, int64_t stride,
-             int ncols, double* tmp) {
-  const int64_t sW = (int64_t)NB * NB;
+int tri_mult(cudaStream_t st, int batch, int jb, const double* Tinv, int64_t sW, double* X, int64_t ld,
+             int64_t stride, int ncols, double* tmp) {
+  if (ncols <= 0) return 0;
   if (ncols >= 16) return dgemm(st, jb, ncols, jb, 1.0, Tinv, NB, sW, X, ld, stride, 0.0, X, ld, stride, batch);
   const int64_t sT = (int64_t)NB * 16;
   HPS_TRY(dgemm_skinny(st, jb, ncols, jb, 1.0, Tinv, NB, sW, X, ld, stride, 0.0, nullptr, 0, 0, tmp, ncols, sT, batch));
@@ -416,15 +428,125 @@ int tri_mult(cudaStream_t st, int batch, int jb, const double* Tinv, double* X, 
   return 0;
 }
 
+struct Mat {  // batched row-major matrix view
+  double* p;
+  int64_t ld, stride;
+  double* at(int64_t r, int64_t c) const { return p + r * ld + c; }
+};
+
+// internal look-ahead stream + events, created once per device
+struct Aux {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t panel_done[2] = {nullptr, nullptr};
+  cudaEvent_t update_done[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+int get_aux(Aux*& out) {
+  static Aux aux[64];
+  int dev = 0;
+  HPS_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail_arg(1, "device ordinal out of range");
+  Aux& a = aux[dev];
+  if (!a.stream) {
+    int lo = 0, hi = 0;
+    HPS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    HPS_CUDA(cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 2; ++i) {
+      HPS_CUDA(cudaEventCreateWithFlags(&a.panel_done[i], cudaEventDisableTiming));
+      HPS_CUDA(cudaEventCreateWithFlags(&a.update_done[i], cudaEventDisableTiming));
+    }
+    HPS_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
+    HPS_CUDA(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+  }
+  out = &a;
+  return 0;
+}
+
+// Factor the outer block column j (inner IB panels + updates inside the block column) and invert
+// its unit-lower diagonal block into Linv[j/NB].  Touches columns [j, j+jb) only.
+int factor_block_column(cudaStream_t st, int batch, int n, const Mat& A, int j, int jb, LuWorkspace& w, int* info) {
+  for (int jj = j; jj < j + jb; jj += IB) {
+    const int ib = min(IB, j + jb - jj);
+    PanelArgs pa;
+    pa.A = A.p; pa.lda = A.ld; pa.sA = A.stride; pa.n = n; pa.jj = jj; pa.ib = ib; pa.G = 1;
+    pa.ipiv = w.ipiv; pa.info = info; pa.scratch = w.scratch;
+    HPS_TRY(launch_panel(st, batch, pa));
+    HPS_TRY(laswp(st, batch, A.p, A.ld, A.stride, j, jj - j, w.ipiv, n, jj, jj + ib));
+    const int right = j + jb - (jj + ib);
+    if (right > 0) {
+      HPS_TRY(laswp(st, batch, A.p, A.ld, A.stride, jj + ib, right, w.ipiv, n, jj, jj + ib));
+      inner_trsm_kernel<<<dim3((right + 127) / 128, batch), 128, 0, st>>>(A.p, A.ld, A.stride, jj, ib, jj + ib, right);
+      HPS_LAUNCH_CHECK("inner_trsm_kernel");
+      const int below = n - (jj + ib);
+      if (below > 0)
+        HPS_TRY(dgemm(st, below, right, ib, -1.0, A.at(jj + ib, jj), A.ld, A.stride, A.at(jj, jj + ib), A.ld, A.stride,
+                      1.0, A.at(jj + ib, jj + ib), A.ld, A.stride, batch));
+    }
+  }
+  const int nblk = (n + NB - 1) / NB;
+  trtri_kernel<true><<<dim3(1, batch), NB, TRTRI_SMEM, st>>>(A.p, A.ld, A.stride, j, n, w.Linv, (int64_t)nblk * NB * NB);
+  HPS_LAUNCH_CHECK("trtri_kernel<lower>");
+  return 0;
+}
+
+// Apply block column j's interchanges, U12 = L11^-1 A12 and the rank-jb update to columns
+// [c0, c0+nc) of A (rows >= j).
+int update_columns(cudaStream_t st, int batch, int n, const Mat& A, int j, int jb, int c0, int nc, LuWorkspace& w) {
+  if (nc <= 0) return 0;
+  const int nblk = (n + NB - 1) / NB;
+  const int64_t sW = (int64_t)nblk * NB * NB;
+  const double* Linv = w.Linv + (int64_t)(j / NB) * NB * NB;
+  HPS_TRY(laswp(st, batch, A.p, A.ld, A.stride, c0, nc, w.ipiv, n, j, j + jb));
+  if (c0 >= j + jb) {  // right of the block column: needs U12 and the trailing update
+    HPS_TRY(tri_mult(st, batch, jb, Linv, sW, A.at(j, c0), A.ld, A.stride, nc, w.tmp));
+    const int below = n - (j + jb);
+    if (below > 0)
+      HPS_TRY(dgemm(st, below, nc, jb, -1.0, A.at(j + jb, j), A.ld, A.stride, A.at(j, c0), A.ld, A.stride, 1.0,
+                    A.at(j + jb, c0), A.ld, A.stride, batch));
+  }
+  return 0;
+}
+
+// L Z = B in place on rows [r0, r1) of X (unit lower, diagonal blocks pre-inverted)
+int trsm_lower(cudaStream_t st, int batch, int n, const Mat& A, const LuWorkspace& w, const RhsDesc& X, int r0, int r1) {
+  const int nblk = (n + NB - 1) / NB;
+  const int64_t sW = (int64_t)nblk * NB * NB;
+  if (r1 - r0 <= NB)
+    return tri_mult(st, batch, r1 - r0, w.Linv + (int64_t)(r0 / NB) * NB * NB, sW, X.ptr + (int64_t)r0 * X.ld, X.ld,
+                    X.stride, X.ncols, w.tmp);
+  const int blocks = (r1 - r0 + NB - 1) / NB;
+  const int mid = r0 + (blocks / 2) * NB;
+  HPS_TRY(trsm_lower(st, batch, n, A, w, X, r0, mid));
+  HPS_TRY(dgemm(st, r1 - mid, X.ncols, mid - r0, -1.0, A.at(mid, r0), A.ld, A.stride, X.ptr + (int64_t)r0 * X.ld, X.ld,
+                X.stride, 1.0, X.ptr + (int64_t)mid * X.ld, X.ld, X.stride, batch));
+  return trsm_lower(st, batch, n, A, w, X, mid, r1);
+}
+
+// U X = Z in place on rows [r0, r1) of X
+int trsm_upper(cudaStream_t st, int batch, int n, const Mat& A, const LuWorkspace& w, const RhsDesc& X, int r0, int r1) {
+  const int nblk = (n + NB - 1) / NB;
+  const int64_t sW = (int64_t)nblk * NB * NB;
+  if (r1 - r0 <= NB)
+    return tri_mult(st, batch, r1 - r0, w.Uinv + (int64_t)(r0 / NB) * NB * NB, sW, X.ptr + (int64_t)r0 * X.ld, X.ld,
+                    X.stride, X.ncols, w.tmp);
+  const int blocks = (r1 - r0 + NB - 1) / NB;
+  const int mid = r0 + (blocks / 2) * NB;
+  HPS_TRY(trsm_upper(st, batch, n, A, w, X, mid, r1));
+  HPS_TRY(dgemm(st, mid - r0, X.ncols, r1 - mid, -1.0, A.at(r0, mid), A.ld, A.stride, X.ptr + (int64_t)mid * X.ld, X.ld,
+                X.stride, 1.0, X.ptr + (int64_t)r0 * X.ld, X.ld, X.stride, batch));
+  return trsm_upper(st, batch, n, A, w, X, r0, mid);
+}
+
 }  // namespace
 
 size_t lu_workspace_bytes(int batch, int n) {
-  return align_up((size_t)batch * n * sizeof(int), 256) + align_up((size_t)batch * NB * NB * sizeof(double), 256) +
+  const size_t nblk = (n + NB - 1) / NB;
+  return align_up((size_t)batch * n * sizeof(int), 256) + 2 * align_up((size_t)batch * nblk * NB * NB * sizeof(double), 256) +
          align_up((size_t)batch * NB * 16 * sizeof(double), 256) + align_up((size_t)batch * sizeof(PanelScratch), 256) +
          1024;
 }
 
-int lu_solve(cudaStream_t st, int batch, int n, double* A, int64_t lda, int64_t sA, int n_rhs, const RhsDesc* rhs,
+int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t sA, int n_rhs, const RhsDesc* rhs,
              void* ws, size_t ws_bytes, int* info) {
   if (batch <= 0 || n <= 0) return 0;
   if (batch > 65535) return fail_arg(2, "lu_solve: batch > 65535");
@@ -441,79 +563,49 @@ int lu_solve(cudaStream_t st, int batch, int n, double* A, int64_t lda, int64_t 
     HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
     configured = true;
   }
-  HPS_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
-
-  const int64_t sW = (int64_t)NB * NB;
-  for (int j = 0; j < n; j += NB) {
-    const int jb = min(NB, n - j);
-    // ---- factor the outer panel A[j:n, j:j+jb] with IB-wide inner panels ----
-    for (int jj = j; jj < j + jb; jj += IB) {
-      const int ib = min(IB, j + jb - jj);
-      PanelArgs pa;
-      pa.A = A; pa.lda = lda; pa.sA = sA; pa.n = n; pa.jj = jj; pa.ib = ib; pa.G = 1;
-      pa.ipiv = w.ipiv; pa.info = info; pa.scratch = w.scratch;
-      HPS_TRY(launch_panel(st, batch, pa));
-      // interchanges on the rest of the outer panel
-      HPS_TRY(laswp(st, batch, A, lda, sA, j, jj - j, w.ipiv, n, jj, jj + ib));
-      const int right = j + jb - (jj + ib);
-      if (right > 0) {
-        HPS_TRY(laswp(st, batch, A, lda, sA, jj + ib, right, w.ipiv, n, jj, jj + ib));
-        inner_trsm_kernel<<<dim3((right + 127) / 128, batch), 128, 0, st>>>(A, lda, sA, jj, ib, jj + ib, right);
-        HPS_LAUNCH_CHECK("inner_trsm_kernel");
-        const int below = n - (jj + ib);
-        if (below > 0) {
-          double* a21 = A + (int64_t)(jj + ib) * lda + jj;
-          double* u12 = A + (int64_t)jj * lda + jj + ib;
-          double* a22 = A + (int64_t)(jj + ib) * lda + jj + ib;
-          HPS_TRY(dgemm(st, below, right, ib, -1.0, a21, lda, sA, u12, lda, sA, 1.0, a22, lda, sA, batch));
-        }
-      }
-    }
-    // ---- interchanges on the trailing columns and on every right-hand side ----
-    const int trail = n - (j + jb);
-    HPS_TRY(laswp(st, batch, A, lda, sA, j + jb, trail, w.ipiv, n, j, j + jb));
-    for (int k = 0; k < n_rhs; ++k)
-      HPS_TRY(laswp(st, batch, rhs[k].ptr, rhs[k].ld, rhs[k].stride, 0, rhs[k].ncols, w.ipiv, n, j, j + jb));
-    // ---- block row of U and forward substitution of the right-hand sides ----
-    trtri_kernel<true><<<batch, NB, TRTRI_SMEM, st>>>(A, lda, sA, j, jb, w.Tinv, sW);
-    HPS_LAUNCH_CHECK("trtri_kernel<lower>");
-    if (trail > 0) {
-      double* a12 = A + (int64_t)j * lda + j + jb;
-      HPS_TRY(dgemm(st, jb, trail, jb, 1.0, w.Tinv, NB, sW, a12, lda, sA, 0.0, a12, lda, sA, batch));
-    }
-    for (int k = 0; k < n_rhs; ++k) {
-      double* r1 = rhs[k].ptr + (int64_t)j * rhs[k].ld;
-      HPS_TRY(tri_mult(st, batch, jb, w.Tinv, r1, rhs[k].ld, rhs[k].stride, rhs[k].ncols, w.tmp));
-    }
-    // ---- trailing updates ----
-    if (trail > 0) {
-      double* a21 = A + (int64_t)(j + jb) * lda + j;
-      double* a12 = A + (int64_t)j * lda + j + jb;
-      double* a22 = A + (int64_t)(j + jb) * lda + j + jb;
-      HPS_TRY(dgemm(st, trail, trail, jb, -1.0, a21, lda, sA, a12, lda, sA, 1.0, a22, lda, sA, batch));
-      for (int k = 0; k < n_rhs; ++k) {
-        double* r1 = rhs[k].ptr + (int64_t)j * rhs[k].ld;
-        double* r2 = rhs[k].ptr + (int64_t)(j + jb) * rhs[k].ld;
-        HPS_TRY(dgemm(st, trail, rhs[k].ncols, jb, -1.0, a21, lda, sA, r1, rhs[k].ld, rhs[k].stride, 1.0, r2,
-                      rhs[k].ld, rhs[k].stride, batch));
-      }
-    }
-  }
-  // ---- back substitution with U, last block row first ----
+  Aux* aux = nullptr;
+  HPS_TRY(get_aux(aux));
+  cudaStream_t s0 = st, s1 = aux->stream;
+  const Mat A{Ap, lda, sA};
   const int nblk = (n + NB - 1) / NB;
-  for (int bi = nblk - 1; bi >= 0; --bi) {
-    const int j = bi * NB, jb = min(NB, n - j);
-    trtri_kernel<false><<<batch, NB, TRTRI_SMEM, st>>>(A, lda, sA, j, jb, w.Tinv, sW);
-    HPS_LAUNCH_CHECK("trtri_kernel<upper>");
-    for (int k = 0; k < n_rhs; ++k) {
-      double* ri = rhs[k].ptr + (int64_t)j * rhs[k].ld;
-      HPS_TRY(tri_mult(st, batch, jb, w.Tinv, ri, rhs[k].ld, rhs[k].stride, rhs[k].ncols, w.tmp));
-      if (j > 0) {
-        double* u0i = A + j;
-        HPS_TRY(dgemm(st, j, rhs[k].ncols, jb, -1.0, u0i, lda, sA, ri, rhs[k].ld, rhs[k].stride, 1.0, rhs[k].ptr,
-                      rhs[k].ld, rhs[k].stride, batch));
-      }
+
+  HPS_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, s0));
+  // ---- 1. factorisation with look-ahead --------------------------------------------------
+  // s1 owns the block column being factored; s0 applies finished block columns to everything
+  // to their right (and the interchanges to everything to their left).
+  HPS_CUDA(cudaEventRecord(aux->fork, s0));
+  HPS_CUDA(cudaStreamWaitEvent(s1, aux->fork, 0));
+  HPS_TRY(factor_block_column(s1, batch, n, A, 0, min(NB, n), w, info));
+  HPS_CUDA(cudaEventRecord(aux->panel_done[0], s1));
+  for (int b = 0; b < nblk; ++b) {
+    const int j = b * NB, jb = min(NB, n - j);
+    const int next = j + jb, nextb = (next < n) ? min(NB, n - next) : 0;
+    HPS_CUDA(cudaStreamWaitEvent(s0, aux->panel_done[b & 1], 0));
+    if (nextb > 0) {
+      // look-ahead: bring the next block column up to date and factor it on s1.  It was last
+      // written by s0's update for block b-1, which must have finished.
+      if (b > 0) HPS_CUDA(cudaStreamWaitEvent(s1, aux->update_done[(b - 1) & 1], 0));
+      HPS_TRY(update_columns(s1, batch, n, A, j, jb, next, nextb, w));
+      HPS_TRY(factor_block_column(s1, batch, n, A, next, nextb, w, info));
+      HPS_CUDA(cudaEventRecord(aux->panel_done[(b + 1) & 1], s1));
     }
+    // s0: interchanges on the columns to the left (L in LAPACK form), then the rest of the
+    // trailing matrix
+    HPS_TRY(update_columns(s0, batch, n, A, j, jb, 0, j, w));
+    HPS_TRY(update_columns(s0, batch, n, A, j, jb, next + nextb, n - (next + nextb), w));
+    HPS_CUDA(cudaEventRecord(aux->update_done[b & 1], s0));
+  }
+  // s1 has nothing pending beyond panel_done[(nblk-1)&1], which s0 has waited on.
+  if (n_rhs == 0) return 0;
+
+  // ---- 2. inverses of U's diagonal blocks (all at once), interchanges on the right-hand sides --
+  trtri_kernel<false><<<dim3(nblk, batch), NB, TRTRI_SMEM, s0>>>(A.p, A.ld, A.stride, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
+  HPS_LAUNCH_CHECK("trtri_kernel<upper>");
+  for (int k = 0; k < n_rhs; ++k) {
+    HPS_TRY(laswp(s0, batch, rhs[k].ptr, rhs[k].ld, rhs[k].stride, 0, rhs[k].ncols, w.ipiv, n, 0, n));
+    // ---- 3. recursive substitutions --------------------------------------------------------
+    HPS_TRY(trsm_lower(s0, batch, n, A, w, rhs[k], 0, n));
+    HPS_TRY(trsm_upper(s0, batch, n, A, w, rhs[k], 0, n));
   }
   return 0;
 }
