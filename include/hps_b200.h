@@ -92,6 +92,15 @@ int hps_merge_oct_dtn_level(void* stream, int n_merges, int m, int n_src,
                             double* S, double* g_tilde, double* T_out, double* h_out,
                             int want_T, void* ws, size_t ws_bytes, int* info);
 
+/* Multi-GPU root merge, column-sharded (no reference counterpart: the reference is single-device;
+ * this is the distributed form of the last `_uniform_oct_merge_DtN` call,
+ * merge/_uniform_3D_DtN.py:95-117).  Every rank holds the 8 subtree-root T's (all-gathered) and
+ * computes S[:, ext0:ext0+ncols] (row-major, leading dimension ncols) and the full g_tilde.
+ * Workspace: hps_merge_oct_dtn_level_workspace(1, m, n_src). */
+int hps_merge_oct_dtn_root_cols(void* stream, int m, int n_src, const double* T_in, const double* h_in,
+                                int ext0, int ncols, double* S_cols, double* g_tilde,
+                                void* ws, size_t ws_bytes, int* info);
+
 /* 2D quad merge, DtN (reference: merge/_uniform_2D_DtN.py:206-348).
  * T_in [4*n_merges][4m][4m] (children SW,SE,NE,NW; sides S,E,N,W), S [n][4m][8m],
  * T_out [n][8m][8m]. */
@@ -109,6 +118,10 @@ int hps_merge_quad_dtn_level(void* stream, int n_merges, int m, int n_src,
  * ws: n_nodes * n_int * n_src doubles. */
 int hps_down_oct_level(void* stream, int n_nodes, int m, int n_src, const double* S,
                        const double* g_ext, const double* g_tilde, double* g_children, void* ws);
+/* Children's boundary vectors from an already-reduced g_int (multi-GPU root level: g_int is the
+ * all-reduced sum of the ranks' partial products). */
+int hps_down_oct_scatter(void* stream, int n_nodes, int m, int n_src, const double* g_ext,
+                         const double* g_int, double* g_children);
 int hps_down_quad_level(void* stream, int n_nodes, int m, int n_src, const double* S,
                         const double* g_ext, const double* g_tilde, double* g_children, void* ws);
 

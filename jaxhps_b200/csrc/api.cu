@@ -133,6 +133,15 @@ int hps_merge_oct_dtn_level(void* stream, int n_merges, int m, int n_src, const 
   return merge_oct_level(static_cast<cudaStream_t>(stream), n_merges, m, n_src, T_in, h_in, S, g_tilde, T_out, h_out,
                          want_T, ws, ws_bytes, info);
 }
+int hps_merge_oct_dtn_root_cols(void* stream, int m, int n_src, const double* T_in, const double* h_in, int ext0,
+                                int ncols, double* S_cols, double* g_tilde, void* ws, size_t ws_bytes, int* info) {
+  return merge_oct_root_cols(static_cast<cudaStream_t>(stream), m, n_src, T_in, h_in, ext0, ncols, S_cols, g_tilde, ws,
+                             ws_bytes, info);
+}
+int hps_down_oct_scatter(void* stream, int n_nodes, int m, int n_src, const double* g_ext, const double* g_int,
+                         double* g_children) {
+  return down_oct_scatter(static_cast<cudaStream_t>(stream), n_nodes, m, n_src, g_ext, g_int, g_children);
+}
 int hps_merge_quad_dtn_level_workspace(int n_merges, int m, int n_src, size_t* bytes) {
   (void)n_src;
   if (!bytes) return fail_arg(4, "null output pointer");

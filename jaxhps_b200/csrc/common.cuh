@@ -95,6 +95,10 @@ int merge_oct_level(cudaStream_t st, int n_merges, int m, int n_src, const doubl
 int merge_quad_level(cudaStream_t st, int n_merges, int m, int n_src, const double* T_in, const double* h_in,
                      double* S, double* gt, double* T_out, double* h_out, int want_T, void* ws, size_t ws_bytes,
                      int* info);
+int merge_oct_root_cols(cudaStream_t st, int m, int n_src, const double* T_in, const double* h_in, int ext0, int ncols,
+                        double* S_cols, double* gt, void* ws, size_t ws_bytes, int* info);
+int down_oct_scatter(cudaStream_t st, int n_nodes, int m, int n_src, const double* g_ext, const double* g_int,
+                     double* g_children);
 int down_oct_level(cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
                    const double* gt, double* g_children, void* ws);
 int down_quad_level(cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,

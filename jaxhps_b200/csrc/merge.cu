@@ -122,10 +122,13 @@ __device__ __forceinline__ int face_index(const Topo& tp, int c, int f, int t, i
 
 // ---- gather: D (workspace), S := -C, g~ := -h_int --------------------------------------
 // grid: (column tiles, rows = n_slot*m, merges)
+// Only exterior columns [ext0, ext0 + n_ext) are produced (S has leading dimension n_ext): the
+// whole range for a normal merge, one rank's share for the column-sharded root merge.
 __global__ void __launch_bounds__(256) merge_gather_kernel(Topo tp, int m, int n_src, const double* __restrict__ T_in,
                                                            const double* __restrict__ h_in, double* __restrict__ D,
-                                                           double* __restrict__ S, double* __restrict__ gt) {
-  const int n_int = tp.n_slot * m, n_ext = tp.n_ext * m, nf = tp.n_face * m;
+                                                           double* __restrict__ S, double* __restrict__ gt, int ext0,
+                                                           int n_ext) {
+  const int n_int = tp.n_slot * m, nf = tp.n_face * m;
   const int row = blockIdx.y, mg = blockIdx.z;
   const int s1 = row / m, t1 = row - s1 * m;
   const int64_t child_sz = (int64_t)nf * nf;
@@ -143,13 +146,13 @@ __global__ void __launch_bounds__(256) merge_gather_kernel(Topo tp, int m, int n
       if (f2B >= 0) v += rowB[face_index(tp, cB, f2B, t2, m)];
       D[((int64_t)mg * n_int + row) * n_int + col] = v;
     } else if (col < n_int + n_ext) {
-      const int ce = col - n_int;
+      const int cl = col - n_int, ce = cl + ext0;
       const int e = ce / m, u = ce - e * m;
       const int c = tp.ext_child[e], f = tp.ext_face[e];
       double v = 0.0;
       if (c == cA) v = rowA[f * m + u];
       else if (c == cB) v = rowB[f * m + u];
-      S[((int64_t)mg * n_int + row) * n_ext + ce] = -v;
+      S[((int64_t)mg * n_int + row) * n_ext + cl] = -v;
     } else {
       const int k = col - n_int - n_ext;
       const double* hm = h_in + (int64_t)mg * tp.n_child * nf * n_src;
@@ -239,7 +242,7 @@ int merge_level(const Topo& tp, cudaStream_t st, int n_merges, int m, int n_src,
   {
     const int cols = n_int + n_ext + n_src;
     dim3 grid(std::min((cols + 255) / 256, 64), n_int, n_merges);
-    merge_gather_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, D, S, gt);
+    merge_gather_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, D, S, gt, 0, n_ext);
     HPS_LAUNCH_CHECK("merge_gather_kernel");
   }
   const int64_t sS = (int64_t)n_int * n_ext, sG = (int64_t)n_int * n_src;
@@ -285,7 +288,45 @@ int down_level(const Topo& tp, cudaStream_t st, int n_nodes, int m, int n_src, c
   return 0;
 }
 
+// Column-sharded merge for the multi-GPU root: S[:, ext0:ext0+ncols] and g~ from the children's T.
+int merge_cols(const Topo& tp, cudaStream_t st, int m, int n_src, const double* T_in, const double* h_in, int ext0,
+               int ncols, double* S_cols, double* gt, void* ws, size_t ws_bytes, int* info) {
+  if (m <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
+  const int n_int = tp.n_slot * m, n_ext = tp.n_ext * m;
+  if (ext0 < 0 || ncols <= 0 || ext0 + ncols > n_ext) return fail_arg(6, "column window out of range");
+  Arena ar(ws, ws_bytes);
+  double* D = ar.take<double>((size_t)n_int * n_int);
+  if (!D) return fail_arg(11, "merge_cols: workspace too small");
+  void* lu_ws = ar.base + ar.off;
+  const size_t lu_ws_bytes = ar.cap - ar.off;
+  const int cols = n_int + ncols + n_src;
+  dim3 grid(std::min((cols + 255) / 256, 64), n_int, 1);
+  merge_gather_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, D, S_cols, gt, ext0, ncols);
+  HPS_LAUNCH_CHECK("merge_gather_kernel");
+  RhsDesc rhs[2] = {{S_cols, ncols, (int64_t)n_int * ncols, ncols}, {gt, n_src, (int64_t)n_int * n_src, n_src}};
+  return lu_solve(st, 1, n_int, D, n_int, (int64_t)n_int * n_int, 2, rhs, lu_ws, lu_ws_bytes, info);
+}
+
+int down_scatter(const Topo& tp, cudaStream_t st, int n_nodes, int m, int n_src, const double* g_ext,
+                 const double* g_int, double* g_children) {
+  if (n_nodes <= 0 || m <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
+  const int64_t per_node = (int64_t)tp.n_child * tp.n_face * m * n_src;
+  dim3 grid((unsigned)std::min<int64_t>((per_node + 255) / 256, 1024), n_nodes);
+  down_scatter_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, g_ext, g_int, g_children);
+  HPS_LAUNCH_CHECK("down_scatter_kernel");
+  return 0;
+}
+
 }  // namespace
+
+int merge_oct_root_cols(cudaStream_t st, int m, int n_src, const double* T_in, const double* h_in, int ext0, int ncols,
+                        double* S_cols, double* gt, void* ws, size_t ws_bytes, int* info) {
+  return merge_cols(oct_topo(), st, m, n_src, T_in, h_in, ext0, ncols, S_cols, gt, ws, ws_bytes, info);
+}
+int down_oct_scatter(cudaStream_t st, int n_nodes, int m, int n_src, const double* g_ext, const double* g_int,
+                     double* g_children) {
+  return down_scatter(oct_topo(), st, n_nodes, m, n_src, g_ext, g_int, g_children);
+}
 
 size_t merge_oct_ws_bytes(int n_merges, int m) { return merge_ws_bytes(oct_topo(), n_merges, m); }
 size_t merge_quad_ws_bytes(int n_merges, int m) { return merge_ws_bytes(quad_topo(), n_merges, m); }

@@ -8,6 +8,45 @@ import torch
 from . import _lib
 
 
+def down_levels(g_cur: torch.Tensor, S_dev, g_dev, dim: int, dev) -> torch.Tensor:
+    """Push boundary data ``g_cur (n_nodes, n_ext, n_src)`` through the given levels (root-most
+    last in the lists); returns ``(n_nodes * n_child^levels, n_face*m, n_src)``."""
+    lib = _lib.load()
+    n_child = 8 if dim == 3 else 4
+    n_face = 6 if dim == 3 else 4
+    n_slot = 12 if dim == 3 else 4
+    down_fn = lib.hps_down_oct_level if dim == 3 else lib.hps_down_quad_level
+    n_src = g_cur.shape[-1]
+    for level in range(len(S_dev) - 1, -1, -1):
+        S = S_dev[level]
+        gt = g_dev[level].reshape(S.shape[0], S.shape[1], n_src)
+        n_nodes, n_int, n_ext = S.shape
+        m = n_int // n_slot
+        if g_cur.shape[0] != n_nodes or g_cur.shape[1] != n_ext:
+            raise ValueError(
+                f"level {level}: boundary data of shape {tuple(g_cur.shape)} does not match S {tuple(S.shape)}"
+            )
+        out = torch.empty((n_nodes * n_child, n_face * m, n_src), dtype=torch.float64, device=dev)
+        ws = torch.empty((n_nodes, n_int, n_src), dtype=torch.float64, device=dev)
+        rc = down_fn(_lib.stream_ptr(), n_nodes, m, n_src, _lib.ptr(S), _lib.ptr(g_cur), _lib.ptr(gt),
+                     _lib.ptr(out), _lib.ptr(ws))
+        _lib.check(rc, "hps_down_level")
+        g_cur = out
+    return g_cur
+
+
+def leaf_apply(Y: torch.Tensor, g_leaf: torch.Tensor, v: torch.Tensor, dev) -> torch.Tensor:
+    """``u = Y g + v`` on every leaf; all arguments 3-D device tensors."""
+    lib = _lib.load()
+    n_leaves, n_c, n_g = Y.shape
+    n_src = g_leaf.shape[-1]
+    u = torch.empty((n_leaves, n_c, n_src), dtype=torch.float64, device=dev)
+    rc = lib.hps_leaf_apply(_lib.stream_ptr(), n_leaves, n_c, n_g, n_src, _lib.ptr(Y), _lib.ptr(g_leaf),
+                            _lib.ptr(v.reshape(n_leaves, n_c, n_src)), _lib.ptr(u))
+    _lib.check(rc, "hps_leaf_apply")
+    return u
+
+
 def _down_pass(boundary_data, S_lst, g_tilde_lst, Y_arr, v_arr, dim: int, device, host_device):
     dev = _lib.require_cuda(device)
     lib = _lib.load()
@@ -31,31 +70,13 @@ def _down_pass(boundary_data, S_lst, g_tilde_lst, Y_arr, v_arr, dim: int, device
             raise ValueError("For multi-source downward pass, need to specify boundary data for each source.")
         n_src = bd.shape[-1] if multi else 1
         g_cur = bd.reshape(1, -1, n_src).contiguous()
-        for level in range(len(S_dev) - 1, -1, -1):
-            S = S_dev[level]
-            gt = g_dev[level].reshape(S.shape[0], S.shape[1], n_src)
-            n_nodes, n_int, n_ext = S.shape
-            m = n_int // n_slot
-            if g_cur.shape[0] != n_nodes or g_cur.shape[1] != n_ext:
-                raise ValueError(
-                    f"level {level}: boundary data of shape {tuple(g_cur.shape)} does not match S {tuple(S.shape)}"
-                )
-            out = torch.empty((n_nodes * n_child, n_face * m, n_src), dtype=torch.float64, device=dev)
-            ws = torch.empty((n_nodes, n_int, n_src), dtype=torch.float64, device=dev)
-            rc = down_fn(_lib.stream_ptr(), n_nodes, m, n_src, _lib.ptr(S), _lib.ptr(g_cur), _lib.ptr(gt),
-                         _lib.ptr(out), _lib.ptr(ws))
-            _lib.check(rc, "hps_down_level")
-            g_cur = out
+        g_cur = down_levels(g_cur, S_dev, g_dev, dim, dev)
         if Y_arr is None:
             res = g_cur if multi else g_cur[..., 0]
             return _lib.to_result(res, host_device)
         Y = _lib.to_device(Y_arr, dev)
         v = _lib.to_device(v_arr, dev)
-        n_leaves, n_c, n_g = Y.shape
-        u = torch.empty((n_leaves, n_c, n_src), dtype=torch.float64, device=dev)
-        rc = lib.hps_leaf_apply(_lib.stream_ptr(), n_leaves, n_c, n_g, n_src, _lib.ptr(Y), _lib.ptr(g_cur),
-                                _lib.ptr(v.reshape(n_leaves, n_c, n_src)), _lib.ptr(u))
-        _lib.check(rc, "hps_leaf_apply")
+        u = leaf_apply(Y, g_cur, v, dev)
         return _lib.to_result(u if multi else u[..., 0], host_device)
 
 

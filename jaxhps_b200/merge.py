@@ -11,7 +11,9 @@ from . import _lib
 
 
 def _merge_stage(T_arr, h_arr, l: int, dim: int, device, host_device, return_T: bool, subtree_recomp: bool,
-                 return_h: bool = False):
+                 return_h: bool = False, n_roots: int = 1):
+    """``l`` merge levels over ``n_roots`` independent subtrees stored back to back (``n_roots=1``: the
+    reference's whole-tree merge; ``n_roots>1``: the subtrees one GPU owns in the sharded build)."""
     dev = _lib.require_cuda(device)
     lib = _lib.load()
     n_child = 8 if dim == 3 else 4
@@ -25,8 +27,8 @@ def _merge_stage(T_arr, h_arr, l: int, dim: int, device, host_device, return_T: 
         if not multi:
             h = h.unsqueeze(-1)
         n_src = h.shape[-1]
-        if T.shape[0] != n_child**l:
-            raise ValueError(f"expected {n_child**l} leaf operators for l={l}, got {T.shape[0]}")
+        if T.shape[0] != n_roots * n_child**l:
+            raise ValueError(f"expected {n_roots * n_child**l} leaf operators for l={l}, got {T.shape[0]}")
         S_lst, g_lst = [], []
         for level in range(l, 0, -1):
             n_merges = T.shape[0] // n_child
@@ -83,3 +85,38 @@ def merge_stage_uniform_2D_DtN(T_arr, h_arr, l: int, device=None, host_device=No
     if return_T:
         return S_out, g_out, _lib.to_result(T_last[0], host_device)
     return S_out, g_out
+
+
+def merge_subtrees_3D_DtN(T_arr, h_arr, l: int, n_roots: int, device=None):
+    """Merge ``n_roots`` octree subtrees of depth ``l`` held back to back; everything stays on the
+    device.  Returns ``(S_lst, g_tilde_lst, T_roots, h_roots)`` — the per-GPU part of the sharded
+    build (the serial analogue is `_subtree_recomp.py:310-367`)."""
+    S_lst, g_lst, T_roots, h_roots = _merge_stage(T_arr, h_arr, l, 3, device, device, True, False, n_roots=n_roots)
+    return S_lst, g_lst, T_roots, h_roots
+
+
+def merge_root_columns_3D_DtN(T8, h8, col0: int, ncols: int, device=None):
+    """One rank's share of the root merge: ``S[:, col0:col0+ncols]`` and the full ``g_tilde`` from
+    the 8 subtree-root operators (``hps_merge_oct_dtn_root_cols``)."""
+    dev = _lib.require_cuda(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        T = _lib.to_device(T8, dev)
+        h = _lib.to_device(h8, dev)
+        multi = h.ndim == 3
+        if not multi:
+            h = h.unsqueeze(-1)
+        n_src = h.shape[-1]
+        m = T.shape[-1] // 6
+        n_int = 12 * m
+        S = torch.empty((n_int, ncols), dtype=torch.float64, device=dev)
+        g = torch.empty((n_int, n_src), dtype=torch.float64, device=dev)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        need = ctypes.c_size_t()
+        _lib.check(lib.hps_merge_oct_dtn_level_workspace(1, m, n_src, ctypes.byref(need)), "merge workspace query")
+        ws = _lib.WORKSPACE.get(need.value, dev)
+        rc = lib.hps_merge_oct_dtn_root_cols(_lib.stream_ptr(), m, n_src, _lib.ptr(T), _lib.ptr(h), col0, ncols,
+                                             _lib.ptr(S), _lib.ptr(g), _lib.ptr(ws), ws.numel(), _lib.ptr(info))
+        _lib.check(rc, "hps_merge_oct_dtn_root_cols")
+        _lib.check_info(info, "root merge")
+        return S, (g if multi else g[..., 0])
