@@ -110,6 +110,36 @@ int hps_merge_quad_dtn_level(void* stream, int n_merges, int m, int n_src,
                              double* S, double* g_tilde, double* T_out, double* h_out,
                              int want_T, void* ws, size_t ws_bytes, int* info);
 
+/* ---- 2D ItI (impedance-to-impedance, complex128).  Complex arrays are interleaved (re, im)
+ * doubles — the memory layout of numpy/torch complex128 — passed as double*.
+ * Leaf (reference: local_solve/_uniform_2D_ItI.py:10-193): coeffs real [n_coef][n_leaves][p^2] in
+ * the 2D order [xx,xy,yy,x,y,I]; P real [4(p-1)][4q]; G complex [4(p-1)][p^2]; QH complex [4q][p^2];
+ * src complex [n_leaves][p^2][n_src].  Outputs complex: Y [n][p^2][4q], R [n][4q][4q],
+ * v [n][p^2][n_src], h [n][4q][n_src].  Solved through the real embedding of the complex system. */
+int hps_local_solve_2d_iti_workspace(int n_leaves, int p, int q, int n_src, size_t* bytes);
+int hps_local_solve_2d_iti(void* stream, int n_leaves, int p, int q, int n_src,
+                           const uint8_t* which /* host */, const double* coeffs, const double* D1,
+                           const double* P, const double* G, const double* QH, const double* src,
+                           double* Y, double* R, double* v, double* h,
+                           void* ws, size_t ws_bytes, int* info);
+/* One ItI quad-merge level (reference: merge/_uniform_2D_ItI.py:182-405,
+ * merge/_schur_complement.py:6-41,78-114).  R_in [4n][4m][4m], h_in [4n][4m][n_src];
+ * S [n][8m][8m] and g_tilde [n][8m][n_src] with rows in the reference's returned order
+ * [a5,b5,b6,c6,c7,d7,d8,a8]; R_out [n][8m][8m], h_out [n][8m][n_src]. */
+int hps_merge_quad_iti_level_workspace(int n_merges, int m, int n_src, size_t* bytes);
+int hps_merge_quad_iti_level(void* stream, int n_merges, int m, int n_src,
+                             const double* R_in, const double* h_in,
+                             double* S, double* g_tilde, double* R_out, double* h_out,
+                             int want_T, void* ws, size_t ws_bytes, int* info);
+/* One ItI down-pass level (reference: down_pass/_uniform_2D_ItI.py:121-192).
+ * ws: n_nodes * 48 m n_src doubles. */
+int hps_down_quad_iti_level(void* stream, int n_nodes, int m, int n_src, const double* S,
+                            const double* g_ext, const double* g_tilde, double* g_children, void* ws);
+/* u = Y g + v, complex128 (reference: down_pass/_uniform_2D_ItI.py:107-116).
+ * ws: n_leaves * 4 n_g n_src doubles. */
+int hps_leaf_apply_complex(void* stream, int n_leaves, int n_c, int n_g, int n_src,
+                           const double* Y, const double* g, const double* v, double* u, void* ws);
+
 /* ---- down_pass (reference: down_pass/_uniform_3D_DtN.py:116-246,
  *      down_pass/_uniform_2D_DtN.py:125-189) -------------------------------------------
  * One level: g_int = S g_ext + g_tilde, then the children's boundary vectors.

@@ -6,8 +6,12 @@ so the driver is a straight line."""
 from __future__ import annotations
 
 from ._pdeproblem import PDEProblem
-from .local_solve import local_solve_stage_uniform_2D_DtN, local_solve_stage_uniform_3D_DtN
-from .merge import merge_stage_uniform_2D_DtN, merge_stage_uniform_3D_DtN
+from .local_solve import (
+    local_solve_stage_uniform_2D_DtN,
+    local_solve_stage_uniform_2D_ItI,
+    local_solve_stage_uniform_3D_DtN,
+)
+from .merge import merge_stage_uniform_2D_DtN, merge_stage_uniform_2D_ItI, merge_stage_uniform_3D_DtN
 
 
 def build_solver(pde_problem: PDEProblem, return_top_T: bool = False, compute_device=None, host_device=None):
@@ -24,14 +28,15 @@ def build_solver(pde_problem: PDEProblem, return_top_T: bool = False, compute_de
         )
     if not pde_problem.domain.bool_uniform:
         raise NotImplementedError("adaptive discretisations are outside the hot path built so far")
-    if pde_problem.use_ItI:
-        raise NotImplementedError("2D ItI merges run on the oracle only so far; the CUDA path covers DtN")
     from . import _lib
 
     # leaf outputs stay on the compute device between the two stages (the reference round-trips
     # them through the host, `_build_solver.py:136-169`, which its docs name as the bottleneck)
     dev = _lib.require_cuda(compute_device)
-    if pde_problem.domain.bool_2D:
+    if pde_problem.use_ItI:
+        Y, T, v, h = local_solve_stage_uniform_2D_ItI(pde_problem, device=dev, host_device=dev)
+        merge_fn = merge_stage_uniform_2D_ItI
+    elif pde_problem.domain.bool_2D:
         Y, T, v, h = local_solve_stage_uniform_2D_DtN(pde_problem, device=dev, host_device=dev)
         merge_fn = merge_stage_uniform_2D_DtN
     else:

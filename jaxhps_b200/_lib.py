@@ -40,6 +40,12 @@ _SIGNATURES = {
     "hps_down_oct_scatter": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "hps_merge_quad_dtn_level_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),
     "hps_merge_quad_dtn_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "hps_local_solve_2d_iti_workspace": (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),
+    "hps_local_solve_2d_iti": (_i, [_p, _i, _i, _i, _i, ctypes.c_char_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "hps_merge_quad_iti_level_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),
+    "hps_merge_quad_iti_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "hps_down_quad_iti_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "hps_leaf_apply_complex": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "hps_down_oct_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "hps_down_quad_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "hps_leaf_apply": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),

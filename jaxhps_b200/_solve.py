@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 from ._pdeproblem import PDEProblem
-from .down_pass import down_pass_uniform_2D_DtN, down_pass_uniform_3D_DtN
+from .down_pass import down_pass_uniform_2D_DtN, down_pass_uniform_2D_ItI, down_pass_uniform_3D_DtN
 
 
 def solve(pde_problem: PDEProblem, boundary_data, source=None, compute_device=None, host_device=None):
@@ -26,7 +26,8 @@ def solve(pde_problem: PDEProblem, boundary_data, source=None, compute_device=No
         else:
             boundary_data = np.concatenate([np.asarray(b) for b in boundary_data])
     if pde_problem.use_ItI:
-        raise NotImplementedError("2D ItI down pass runs on the oracle only so far")
-    down = down_pass_uniform_2D_DtN if pde_problem.domain.bool_2D else down_pass_uniform_3D_DtN
+        down = down_pass_uniform_2D_ItI
+    else:
+        down = down_pass_uniform_2D_DtN if pde_problem.domain.bool_2D else down_pass_uniform_3D_DtN
     return down(boundary_data, pde_problem.S_lst, pde_problem.g_tilde_lst, pde_problem.Y, pde_problem.v,
                 device=compute_device, host_device=host_device)

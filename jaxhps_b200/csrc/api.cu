@@ -164,6 +164,38 @@ int hps_down_quad_level(void* stream, int n_nodes, int m, int n_src, const doubl
   return down_quad_level(static_cast<cudaStream_t>(stream), n_nodes, m, n_src, S, g_ext, g_tilde, g_children, ws);
 }
 
+int hps_local_solve_2d_iti_workspace(int n_leaves, int p, int q, int n_src, size_t* bytes) {
+  if (!bytes) return fail_arg(5, "null output pointer");
+  *bytes = local_solve_iti_workspace_bytes(n_leaves, p, q, n_src);
+  return 0;
+}
+int hps_local_solve_2d_iti(void* stream, int n_leaves, int p, int q, int n_src, const uint8_t* which,
+                           const double* coeffs, const double* D1, const double* P, const double* G, const double* QH,
+                           const double* src, double* Y, double* R, double* v, double* h, void* ws, size_t ws_bytes,
+                           int* info) {
+  return local_solve_iti(static_cast<cudaStream_t>(stream), n_leaves, p, q, n_src, which, coeffs, D1, P, G, QH, src, Y, R,
+                         v, h, ws, ws_bytes, info);
+}
+int hps_merge_quad_iti_level_workspace(int n_merges, int m, int n_src, size_t* bytes) {
+  if (!bytes) return fail_arg(4, "null output pointer");
+  *bytes = merge_quad_iti_ws_bytes(n_merges, m, n_src);
+  return 0;
+}
+int hps_merge_quad_iti_level(void* stream, int n_merges, int m, int n_src, const double* R_in, const double* h_in,
+                             double* S, double* g_tilde, double* R_out, double* h_out, int want_T, void* ws,
+                             size_t ws_bytes, int* info) {
+  return merge_quad_iti_level(static_cast<cudaStream_t>(stream), n_merges, m, n_src, R_in, h_in, S, g_tilde, R_out, h_out,
+                              want_T, ws, ws_bytes, info);
+}
+int hps_down_quad_iti_level(void* stream, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
+                            const double* g_tilde, double* g_children, void* ws) {
+  return down_quad_iti_level(static_cast<cudaStream_t>(stream), n_nodes, m, n_src, S, g_ext, g_tilde, g_children, ws);
+}
+int hps_leaf_apply_complex(void* stream, int n_leaves, int n_c, int n_g, int n_src, const double* Y, const double* g,
+                           const double* v, double* u, void* ws) {
+  return leaf_apply_complex(static_cast<cudaStream_t>(stream), n_leaves, n_c, n_g, n_src, Y, g, v, u, ws);
+}
+
 int hps_leaf_apply(void* stream, int n_leaves, int n_c, int n_g, int n_src, const double* Y, const double* g,
                    const double* v, double* u) {
   if (n_leaves <= 0 || n_c <= 0 || n_g <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");

@@ -99,6 +99,18 @@ int merge_oct_root_cols(cudaStream_t st, int m, int n_src, const double* T_in, c
                         double* S_cols, double* gt, void* ws, size_t ws_bytes, int* info);
 int down_oct_scatter(cudaStream_t st, int n_nodes, int m, int n_src, const double* g_ext, const double* g_int,
                      double* g_children);
+size_t local_solve_iti_workspace_bytes(int n_leaves, int p, int q, int n_src);
+int local_solve_iti(cudaStream_t st, int n_leaves, int p, int q, int n_src, const uint8_t* which, const double* coeffs,
+                    const double* D1, const double* P, const double* G, const double* QH, const double* src, double* Y,
+                    double* R, double* v, double* h, void* ws, size_t ws_bytes, int* info);
+size_t merge_quad_iti_ws_bytes(int n_merges, int m, int n_src);
+int merge_quad_iti_level(cudaStream_t st, int n_merges, int m, int n_src, const double* R_in, const double* h_in,
+                         double* S, double* gt, double* R_out, double* h_out, int want_T, void* ws, size_t ws_bytes,
+                         int* info);
+int down_quad_iti_level(cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
+                        const double* gt, double* g_children, void* ws);
+int leaf_apply_complex(cudaStream_t st, int n_leaves, int n_c, int n_g, int n_src, const double* Y, const double* g,
+                       const double* v, double* u, void* ws);
 int down_oct_level(cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
                    const double* gt, double* g_children, void* ws);
 int down_quad_level(cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,

@@ -6,6 +6,8 @@
 //   [Y_int | v_int] = A_ii^-1 [ -A_ie P | f_i ]   (batched LU with partial pivoting, lu.cu)
 //   Y = [P ; Y_int],  v = [0 ; v_int],  T = Q Y,  h = Q v.
 // The solve runs in place inside the caller's Y and v buffers.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace hps {
@@ -67,6 +69,28 @@ struct AssembleArgs {
   double* Aie;             // [n_leaves][n_i][n_b]
 };
 
+// A[row][b] of the 2D leaf operator (row, b in leaf ordering).
+// D_x = kron(D, I); D_y = -kron(I, D) because y is stored descending; order xx, xy, yy, x, y, I
+__device__ __forceinline__ double entry2d(const AssembleArgs& g, const double* D, const double* D2, int p, int n_c,
+                                          int leaf, int row, int b) {
+  auto coef = [&](int k) -> double {
+    const int s = g.slot[k];
+    return s < 0 ? 0.0 : g.coeffs[((int64_t)s * g.n_leaves + leaf) * n_c + row];
+  };
+  int i, j, i2, j2;
+  decode2(row, p, i, j);
+  decode2(b, p, i2, j2);
+  const bool di = i == i2, dj = j == j2;
+  double val = 0.0;
+  if (dj) val = fma(coef(0), D2[i * p + i2], val);
+  val = fma(coef(1), -(D[i * p + i2] * D[j * p + j2]), val);
+  if (di) val = fma(coef(2), D2[j * p + j2], val);
+  if (dj) val = fma(coef(3), D[i * p + i2], val);
+  if (di) val = fma(coef(4), -D[j * p + j2], val);
+  if (di && dj) val += coef(5);
+  return val;
+}
+
 // one thread per (interior row a, column b) entry; blockIdx.y = leaf
 template <int DIM>
 __global__ void __launch_bounds__(256) assemble_kernel(AssembleArgs g) {
@@ -109,17 +133,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(AssembleArgs g) {
       if (di && dj) val = fma(coef(8), D[k * p + k2], val);
       if (di && dj && dk) val += coef(9);
     } else {
-      int i, j, i2, j2;
-      decode2(row, p, i, j);
-      decode2(b, p, i2, j2);
-      const bool di = i == i2, dj = j == j2;
-      // D_x = kron(D, I); D_y = -kron(I, D) because y is stored descending; order xx, xy, yy, x, y, I
-      if (dj) val = fma(coef(0), D2[i * p + i2], val);
-      val = fma(coef(1), -(D[i * p + i2] * D[j * p + j2]), val);
-      if (di) val = fma(coef(2), D2[j * p + j2], val);
-      if (dj) val = fma(coef(3), D[i * p + i2], val);
-      if (di) val = fma(coef(4), -D[j * p + j2], val);
-      if (di && dj) val += coef(5);
+      val = entry2d(g, D, D2, p, n_c, leaf, row, b);
     }
     if (b < n_b) g.Aie[((int64_t)leaf * n_i + a) * n_b + b] = val;
     else g.Aii[((int64_t)leaf * n_i + a) * n_i + (b - n_b)] = val;
@@ -153,6 +167,194 @@ LeafGeom geom(int dim, int p) {
   return g;
 }
 
+
+// =====================================================================================
+// 2D ItI leaf (complex128), reference local_solve/_uniform_2D_ItI.py:120-186.
+// The complex system  B X = R,  B = [G ; A_interior_rows],  is solved through its real
+// embedding  [[Br, -Bi], [Bi, Br]] [Xr ; Xi] = [Rr ; Ri]  with the same pivoted FP64 LU as the
+// DtN path: twice the flops of a native complex LU, no second copy of every kernel.
+// =====================================================================================
+
+struct ItiLeafArgs {
+  AssembleArgs a;          // coefficient slots, D1 (Aii/Aie unused)
+  const double2* G;        // [n_b][n_c] complex
+  double* Be;              // [n_leaves][2 n_c][2 n_c]
+};
+
+__global__ void __launch_bounds__(256) iti_assemble_kernel(ItiLeafArgs g) {
+  __shared__ double D[MAX_P * MAX_P];
+  __shared__ double D2[MAX_P * MAX_P];
+  const int p = g.a.geo.p, n_c = g.a.geo.n_c, n_b = g.a.geo.n_b;
+  for (int t = threadIdx.x; t < p * p; t += blockDim.x) D[t] = g.a.D1[t];
+  __syncthreads();
+  for (int t = threadIdx.x; t < p * p; t += blockDim.x) {
+    const int r = t / p, c = t - r * p;
+    double s = 0.0;
+    for (int u = 0; u < p; ++u) s = fma(D[r * p + u], D[u * p + c], s);
+    D2[t] = s;
+  }
+  __syncthreads();
+  const int leaf = blockIdx.y;
+  const int64_t total = (int64_t)n_c * n_c;
+  const int64_t ld = 2 * n_c;
+  double* Be = g.Be + (int64_t)leaf * ld * ld;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / n_c), c = (int)(e - (int64_t)r * n_c);
+    double re, im;
+    if (r < n_b) {
+      const double2 z = g.G[(int64_t)r * n_c + c];
+      re = z.x; im = z.y;
+    } else {
+      re = entry2d(g.a, D, D2, p, n_c, leaf, r, c);
+      im = 0.0;
+    }
+    Be[(int64_t)r * ld + c] = re;
+    Be[(int64_t)r * ld + n_c + c] = -im;
+    Be[(int64_t)(n_c + r) * ld + c] = im;
+    Be[(int64_t)(n_c + r) * ld + n_c + c] = re;
+  }
+}
+
+// stacked right-hand sides: Ys = [[P;0];[0;0]] (2n_c x n_g), vs = [[0;Re f_i];[0;Im f_i]] (2n_c x n_src)
+__global__ void iti_rhs_kernel(int n_c, int n_b, int n_g, int n_src, const double* __restrict__ P,
+                               const double2* __restrict__ src, double* __restrict__ Ys, double* __restrict__ vs) {
+  const int leaf = blockIdx.y;
+  const int64_t nY = (int64_t)2 * n_c * n_g, nV = (int64_t)2 * n_c * n_src;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nY + nV; e += (int64_t)gridDim.x * blockDim.x) {
+    if (e < nY) {
+      const int64_t r = e / n_g;
+      Ys[(int64_t)leaf * nY + e] = (r < n_b) ? P[e] : 0.0;
+    } else {
+      const int64_t t = e - nY;
+      const int64_t R = t / n_src, k = t - R * n_src;
+      const int64_t r = R % n_c;
+      double val = 0.0;
+      if (r >= n_b) {
+        const double2 z = src[((int64_t)leaf * n_c + r) * n_src + k];
+        val = (R < n_c) ? z.x : z.y;
+      }
+      vs[(int64_t)leaf * nV + t] = val;
+    }
+  }
+}
+
+}  // namespace
+
+// stacked real [Xr ; Xi] (2 rows x cols) -> interleaved complex X (rows x cols) and, optionally, the
+// expanded real form X2 (2 rows x 2 cols): row 2k = (re, im) pairs of row k, row 2k+1 = (-im, re) pairs,
+// which turns a complex product A X into the REAL product  A_view (M x 2K) * X2.
+__global__ void stacked_to_complex_kernel(int rows, int cols, const double* __restrict__ Xs, int64_t sXs,
+                                          double2* __restrict__ X, int64_t sX, double* __restrict__ X2, int64_t sX2) {
+  const int64_t b = blockIdx.y;
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / cols, c = e - r * cols;
+    const double re = Xs[b * sXs + e], im = Xs[b * sXs + total + e];
+    if (X) X[b * sX + e] = make_double2(re, im);
+    if (X2) {
+      double* x2 = X2 + b * sX2;
+      x2[(2 * r) * 2 * cols + 2 * c] = re;
+      x2[(2 * r) * 2 * cols + 2 * c + 1] = im;
+      x2[(2 * r + 1) * 2 * cols + 2 * c] = -im;
+      x2[(2 * r + 1) * 2 * cols + 2 * c + 1] = re;
+    }
+  }
+}
+
+// interleaved complex X (rows x cols) -> expanded real X2 (2 rows x 2 cols)
+__global__ void complex_expand_kernel(int rows, int cols, const double2* __restrict__ X, int64_t sX,
+                                      double* __restrict__ X2, int64_t sX2) {
+  const int64_t b = blockIdx.y;
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / cols, c = e - r * cols;
+    const double2 z = X[b * sX + e];
+    double* x2 = X2 + b * sX2;
+    x2[(2 * r) * 2 * cols + 2 * c] = z.x;
+    x2[(2 * r) * 2 * cols + 2 * c + 1] = z.y;
+    x2[(2 * r + 1) * 2 * cols + 2 * c] = -z.y;
+    x2[(2 * r + 1) * 2 * cols + 2 * c + 1] = z.x;
+  }
+}
+
+int stacked_to_complex(cudaStream_t st, int batch, int rows, int cols, const double* Xs, int64_t sXs, double* X,
+                       int64_t sX, double* X2, int64_t sX2) {
+  const int64_t total = (int64_t)rows * cols;
+  if (total <= 0 || batch <= 0) return 0;
+  dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, 4096), batch);
+  stacked_to_complex_kernel<<<grid, 256, 0, st>>>(rows, cols, Xs, sXs, reinterpret_cast<double2*>(X), sX, X2, sX2);
+  HPS_LAUNCH_CHECK("stacked_to_complex_kernel");
+  return 0;
+}
+
+int complex_expand(cudaStream_t st, int batch, int rows, int cols, const double* X, int64_t sX, double* X2, int64_t sX2) {
+  const int64_t total = (int64_t)rows * cols;
+  if (total <= 0 || batch <= 0) return 0;
+  dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, 4096), batch);
+  complex_expand_kernel<<<grid, 256, 0, st>>>(rows, cols, reinterpret_cast<const double2*>(X), sX, X2, sX2);
+  HPS_LAUNCH_CHECK("complex_expand_kernel");
+  return 0;
+}
+
+size_t local_solve_iti_workspace_bytes(int n_leaves, int p, int q, int n_src) {
+  const LeafGeom g = geom(2, p);
+  const size_t n_g = 4 * (size_t)q, n2 = 2 * (size_t)g.n_c;
+  return align_up((size_t)n_leaves * n2 * n2 * 8, 256) + align_up((size_t)n_leaves * n2 * n_g * 8, 256) +
+         align_up((size_t)n_leaves * n2 * n_src * 8, 256) + align_up((size_t)n_leaves * n2 * 2 * n_g * 8, 256) +
+         align_up((size_t)n_leaves * n2 * 2 * n_src * 8, 256) + lu_workspace_bytes(n_leaves, (int)n2) + 1024;
+}
+
+// Complex outputs are interleaved (re, im) doubles: Y [n][n_c][n_g], R [n][n_g][n_g], v [n][n_c][n_src],
+// h [n][n_g][n_src]; G [n_b][n_c], QH [n_g][n_c], src [n][n_c][n_src] likewise.
+int local_solve_iti(cudaStream_t st, int n_leaves, int p, int q, int n_src, const uint8_t* which, const double* coeffs,
+                    const double* D1, const double* P, const double* G, const double* QH, const double* src, double* Y,
+                    double* R, double* v, double* h, void* ws, size_t ws_bytes, int* info) {
+  if (p < 3 || p > MAX_P) return fail_arg(3, "p out of range [3, 32]");
+  if (n_leaves <= 0 || n_src <= 0 || q <= 0) return fail_arg(2, "non-positive size");
+  if (n_leaves > 65535) return fail_arg(2, "n_leaves per call is limited to 65535; chunk the leaves");
+  const LeafGeom geo = geom(2, p);
+  const int n_c = geo.n_c, n_b = geo.n_b, n_g = 4 * q, n2 = 2 * n_c;
+  Arena ar(ws, ws_bytes);
+  double* Be = ar.take<double>((size_t)n_leaves * n2 * n2);
+  double* Ys = ar.take<double>((size_t)n_leaves * n2 * n_g);
+  double* vs = ar.take<double>((size_t)n_leaves * n2 * n_src);
+  double* Y2 = ar.take<double>((size_t)n_leaves * n2 * 2 * n_g);
+  double* v2 = ar.take<double>((size_t)n_leaves * n2 * 2 * n_src);
+  if (!Be || !Ys || !vs || !Y2 || !v2) return fail_arg(17, "local_solve_iti: workspace too small");
+  void* lu_ws = ar.base + ar.off;
+  const size_t lu_ws_bytes = ar.cap - ar.off;
+
+  ItiLeafArgs ia;
+  ia.a.geo = geo; ia.a.n_leaves = n_leaves; ia.a.coeffs = coeffs; ia.a.D1 = D1; ia.a.Aii = nullptr; ia.a.Aie = nullptr;
+  int n_coef = 0;
+  for (int k = 0; k < 10; ++k) ia.a.slot[k] = (k < 6 && which[k]) ? n_coef++ : -1;
+  ia.a.n_coef = n_coef;
+  ia.G = reinterpret_cast<const double2*>(G);
+  ia.Be = Be;
+  {
+    const int64_t total = (int64_t)n_c * n_c;
+    iti_assemble_kernel<<<dim3((unsigned)std::min<int64_t>((total + 255) / 256, 1024), n_leaves), 256, 0, st>>>(ia);
+    HPS_LAUNCH_CHECK("iti_assemble_kernel");
+    const int64_t tot2 = (int64_t)n2 * (n_g + n_src);
+    iti_rhs_kernel<<<dim3((unsigned)std::min<int64_t>((tot2 + 255) / 256, 1024), n_leaves), 256, 0, st>>>(
+        n_c, n_b, n_g, n_src, P, reinterpret_cast<const double2*>(src), Ys, vs);
+    HPS_LAUNCH_CHECK("iti_rhs_kernel");
+  }
+  RhsDesc rhs[2] = {{Ys, n_g, (int64_t)n2 * n_g, n_g}, {vs, n_src, (int64_t)n2 * n_src, n_src}};
+  HPS_TRY(lu_solve(st, n_leaves, n2, Be, n2, (int64_t)n2 * n2, 2, rhs, lu_ws, lu_ws_bytes, info));
+  // complex outputs + expanded copies for the products with QH
+  HPS_TRY(stacked_to_complex(st, n_leaves, n_c, n_g, Ys, (int64_t)n2 * n_g, Y, (int64_t)n_c * n_g, Y2, (int64_t)n2 * 2 * n_g));
+  HPS_TRY(stacked_to_complex(st, n_leaves, n_c, n_src, vs, (int64_t)n2 * n_src, v, (int64_t)n_c * n_src, v2,
+                             (int64_t)n2 * 2 * n_src));
+  // R = QH Y and h = QH v as real products on the interleaved views
+  HPS_TRY(dgemm(st, n_g, 2 * n_g, n2, 1.0, QH, n2, 0, Y2, 2 * n_g, (int64_t)n2 * 2 * n_g, 0.0, R, 2 * n_g,
+                (int64_t)n_g * 2 * n_g, n_leaves));
+  HPS_TRY(dgemm(st, n_g, 2 * n_src, n2, 1.0, QH, n2, 0, v2, 2 * n_src, (int64_t)n2 * 2 * n_src, 0.0, h, 2 * n_src,
+                (int64_t)n_g * 2 * n_src, n_leaves));
+  return 0;
+}
+
+namespace {
 }  // namespace
 
 size_t local_solve_workspace_bytes(int dim, int n_leaves, int p) {

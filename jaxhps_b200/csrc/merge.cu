@@ -165,20 +165,24 @@ __global__ void __launch_bounds__(256) merge_gather_kernel(Topo tp, int m, int n
 
 // ---- exterior part: T_out := A scattered (zero elsewhere), h_out := h_ext, and the non-zero
 // m x m blocks of B packed as Bg[merge][e][j][m][m] (j-th interface of the child owning e) ----
-__global__ void __launch_bounds__(256) merge_ext_kernel(Topo tp, int m, int n_src, const double* __restrict__ T_in,
-                                                        const double* __restrict__ h_in, double* __restrict__ T_out,
-                                                        double* __restrict__ h_out, double* __restrict__ Bg) {
+__device__ __forceinline__ double zero_of(double) { return 0.0; }
+__device__ __forceinline__ double2 zero_of(double2) { return make_double2(0.0, 0.0); }
+
+template <typename E>
+__global__ void __launch_bounds__(256) merge_ext_kernel(Topo tp, int m, int n_src, const E* __restrict__ T_in,
+                                                        const E* __restrict__ h_in, E* __restrict__ T_out,
+                                                        E* __restrict__ h_out, E* __restrict__ Bg) {
   const int n_ext = tp.n_ext * m, nf = tp.n_face * m;
   const int row = blockIdx.y, mg = blockIdx.z;
   const int e1 = row / m, u1 = row - e1 * m;
   const int c = tp.ext_child[e1], f1 = tp.ext_face[e1];
   const int64_t child_sz = (int64_t)nf * nf;
-  const double* trow = T_in + ((int64_t)mg * tp.n_child + c) * child_sz + (int64_t)(f1 * m + u1) * nf;
+  const E* trow = T_in + ((int64_t)mg * tp.n_child + c) * child_sz + (int64_t)(f1 * m + u1) * nf;
   const int nB = tp.n_intf * m;
   for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < n_ext + nB + n_src; col += gridDim.x * blockDim.x) {
     if (col < n_ext) {
       const int e2 = col / m, u2 = col - e2 * m;
-      const double v = (tp.ext_child[e2] == c) ? trow[tp.ext_face[e2] * m + u2] : 0.0;
+      const E v = (tp.ext_child[e2] == c) ? trow[tp.ext_face[e2] * m + u2] : zero_of(E());
       T_out[((int64_t)mg * n_ext + row) * n_ext + col] = v;
     } else if (col < n_ext + nB) {
       const int cb = col - n_ext;
@@ -253,7 +257,7 @@ int merge_level(const Topo& tp, cudaStream_t st, int n_merges, int m, int n_src,
   {
     const int cols = n_ext + tp.n_intf * m + n_src;
     dim3 grid(std::min((cols + 255) / 256, 64), n_ext, n_merges);
-    merge_ext_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, T_out, h_out, Bg);
+    merge_ext_kernel<double><<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, T_out, h_out, Bg);
     HPS_LAUNCH_CHECK("merge_ext_kernel");
   }
   const int64_t sT = (int64_t)n_ext * n_ext, sH = (int64_t)n_ext * n_src;
@@ -286,6 +290,97 @@ int down_level(const Topo& tp, cudaStream_t st, int n_nodes, int m, int n_src, c
   down_scatter_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, g_ext, g_int, g_children);
   HPS_LAUNCH_CHECK("down_scatter_kernel");
   return 0;
+}
+
+
+// =====================================================================================
+// 2D ItI quad merge (complex128), reference merge/_uniform_2D_ItI.py:182-375 and
+// merge/_schur_complement.py:6-41,78-114.  Every interface carries two unknown vectors (the
+// incoming impedance data of each adjacent child); the unknowns are ordered as the reference
+// RETURNS them, [a5,b5,b6,c6,c7,d7,d8,a8], so no row permutation is needed afterwards.  The
+// complex system (I + coupling) X = -[C | h_int] is solved through its real embedding with the
+// FP64 LU (the reference forms W = I - D12 D21 and an explicit block inverse instead).
+// Complex products use the expanded-operand identity: A X == A_view (M x 2K, interleaved) times
+// X2 (2K x 2N real), which lands directly in interleaved complex storage.
+// =====================================================================================
+
+struct ItiTopo {
+  Topo base;                                    // role >= 0: slot of the child's own unknown on that face
+  signed char unk_child[8], unk_face[8];        // unknown u = incoming data of child X on its face
+  signed char unk_other[8], unk_other_face[8];  // the neighbour Y across that interface, and Y's face there
+};
+
+ItiTopo make_iti() {
+  ItiTopo t = {};
+  Topo q = make_quad();
+  const int intf[4][4] = {{-1, 5, 8, -1}, {-1, -1, 6, 5}, {6, -1, -1, 7}, {8, 7, -1, -1}};
+  const int out_child[8] = {0, 1, 1, 2, 2, 3, 3, 0};
+  const int out_intf[8] = {5, 5, 6, 6, 7, 7, 8, 8};
+  t.base = q;
+  t.base.n_slot = 8;
+  for (int u = 0; u < 8; ++u) {
+    const int X = out_child[u], s = out_intf[u];
+    int fX = -1, Y = -1, fY = -1;
+    for (int f = 0; f < 4; ++f)
+      if (intf[X][f] == s) fX = f;
+    for (int c = 0; c < 4; ++c)
+      for (int f = 0; f < 4; ++f)
+        if (c != X && intf[c][f] == s) { Y = c; fY = f; }
+    t.unk_child[u] = (signed char)X; t.unk_face[u] = (signed char)fX;
+    t.unk_other[u] = (signed char)Y; t.unk_other_face[u] = (signed char)fY;
+    t.base.role[X][fX] = (signed char)u;
+  }
+  finish(t.base);
+  return t;
+}
+const ItiTopo& iti_topo() { static ItiTopo t = make_iti(); return t; }
+
+// grid: (column tiles, rows = 8m, merges).  Writes the embedded De (16m x 16m) and the stacked
+// right-hand sides Cs (16m x 8m), gs (16m x n_src).
+__global__ void __launch_bounds__(256) iti_gather_kernel(ItiTopo tp, int m, int n_src, const double2* __restrict__ R_in,
+                                                         const double2* __restrict__ h_in, double* __restrict__ De,
+                                                         double* __restrict__ Cs, double* __restrict__ gs) {
+  const int n = 8 * m, nf = 4 * m;
+  const int row = blockIdx.y, mg = blockIdx.z;
+  const int u = row / m, t = row - u * m;
+  const int Y = tp.unk_other[u], fY = tp.unk_other_face[u];
+  const int64_t child_sz = (int64_t)nf * nf;
+  const double2* rrow = R_in + ((int64_t)mg * 4 + Y) * child_sz + (int64_t)face_index(tp.base, Y, fY, t, m) * nf;
+  double* De_m = De + (int64_t)mg * 4 * n * n;
+  double* Cs_m = Cs + (int64_t)mg * 2 * n * n;
+  double* gs_m = gs + (int64_t)mg * 2 * n * n_src;
+  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < 2 * n + n_src; col += gridDim.x * blockDim.x) {
+    if (col < n) {
+      const int u2 = col / m, t2 = col - u2 * m;
+      double2 z = make_double2(0.0, 0.0);
+      if (tp.unk_child[u2] == Y) z = rrow[face_index(tp.base, Y, tp.unk_face[u2], t2, m)];
+      if (col == row) z.x += 1.0;
+      De_m[(int64_t)row * 2 * n + col] = z.x;
+      De_m[(int64_t)row * 2 * n + n + col] = -z.y;
+      De_m[(int64_t)(n + row) * 2 * n + col] = z.y;
+      De_m[(int64_t)(n + row) * 2 * n + n + col] = z.x;
+    } else if (col < 2 * n) {
+      const int ce = col - n;
+      const int e = ce / m, uu = ce - e * m;
+      double2 z = make_double2(0.0, 0.0);
+      if (tp.base.ext_child[e] == Y) z = rrow[tp.base.ext_face[e] * m + uu];
+      Cs_m[(int64_t)row * n + ce] = -z.x;
+      Cs_m[(int64_t)(n + row) * n + ce] = -z.y;
+    } else {
+      const int k = col - 2 * n;
+      const double2 z = h_in[(((int64_t)mg * 4 + Y) * nf + face_index(tp.base, Y, fY, t, m)) * n_src + k];
+      gs_m[(int64_t)row * n_src + k] = -z.x;
+      gs_m[(int64_t)(n + row) * n_src + k] = -z.y;
+    }
+  }
+}
+
+size_t merge_iti_ws_bytes_impl(int n_merges, int m, int n_src) {
+  const size_t n = 8 * (size_t)m;
+  return align_up((size_t)n_merges * 4 * n * n * 8, 256) + align_up((size_t)n_merges * 2 * n * n * 8, 256) +
+         align_up((size_t)n_merges * 2 * n * n_src * 8, 256) + align_up((size_t)n_merges * 4 * n * n * 8, 256) +
+         align_up((size_t)n_merges * 4 * n * n_src * 8, 256) + align_up((size_t)n_merges * 8 * 2 * m * m * 16, 256) +
+         lu_workspace_bytes(n_merges, (int)(2 * n)) + 1024;
 }
 
 // Column-sharded merge for the multi-GPU root: S[:, ext0:ext0+ncols] and g~ from the children's T.
@@ -326,6 +421,95 @@ int merge_oct_root_cols(cudaStream_t st, int m, int n_src, const double* T_in, c
 int down_oct_scatter(cudaStream_t st, int n_nodes, int m, int n_src, const double* g_ext, const double* g_int,
                      double* g_children) {
   return down_scatter(oct_topo(), st, n_nodes, m, n_src, g_ext, g_int, g_children);
+}
+
+
+// helpers defined in leaf.cu
+int stacked_to_complex(cudaStream_t st, int batch, int rows, int cols, const double* Xs, int64_t sXs, double* X,
+                       int64_t sX, double* X2, int64_t sX2);
+int complex_expand(cudaStream_t st, int batch, int rows, int cols, const double* X, int64_t sX, double* X2, int64_t sX2);
+
+size_t merge_quad_iti_ws_bytes(int n_merges, int m, int n_src) { return merge_iti_ws_bytes_impl(n_merges, m, n_src); }
+
+// R_in [4n][4m][4m], h_in [4n][4m][n_src]; S [n][8m][8m], gt [n][8m][n_src], R_out [n][8m][8m], h_out [n][8m][n_src];
+// all complex128 stored interleaved.
+int merge_quad_iti_level(cudaStream_t st, int n_merges, int m, int n_src, const double* R_in, const double* h_in,
+                         double* S, double* gt, double* R_out, double* h_out, int want_T, void* ws, size_t ws_bytes,
+                         int* info) {
+  if (n_merges <= 0 || m <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
+  if (n_merges > 65535) return fail_arg(2, "n_merges per call is limited to 65535");
+  const ItiTopo& tp = iti_topo();
+  const int n = 8 * m, n2 = 2 * n;
+  Arena ar(ws, ws_bytes);
+  double* De = ar.take<double>((size_t)n_merges * n2 * n2);
+  double* Cs = ar.take<double>((size_t)n_merges * n2 * n);
+  double* gs = ar.take<double>((size_t)n_merges * n2 * n_src);
+  double* S2 = ar.take<double>((size_t)n_merges * n2 * n2);
+  double* g2 = ar.take<double>((size_t)n_merges * n2 * 2 * n_src);
+  double* Bg = ar.take<double>((size_t)n_merges * 8 * 2 * m * m * 2);
+  if (!De || !Cs || !gs || !S2 || !g2 || !Bg) return fail_arg(13, "merge_iti: workspace too small");
+  void* lu_ws = ar.base + ar.off;
+  const size_t lu_ws_bytes = ar.cap - ar.off;
+  {
+    const int cols = 2 * n + n_src;
+    dim3 grid(std::min((cols + 255) / 256, 64), n, n_merges);
+    iti_gather_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, reinterpret_cast<const double2*>(R_in),
+                                            reinterpret_cast<const double2*>(h_in), De, Cs, gs);
+    HPS_LAUNCH_CHECK("iti_gather_kernel");
+  }
+  RhsDesc rhs[2] = {{Cs, n, (int64_t)n2 * n, n}, {gs, n_src, (int64_t)n2 * n_src, n_src}};
+  HPS_TRY(lu_solve(st, n_merges, n2, De, n2, (int64_t)n2 * n2, 2, rhs, lu_ws, lu_ws_bytes, info));
+  HPS_TRY(stacked_to_complex(st, n_merges, n, n, Cs, (int64_t)n2 * n, S, (int64_t)n * n, S2, (int64_t)n2 * n2));
+  HPS_TRY(stacked_to_complex(st, n_merges, n, n_src, gs, (int64_t)n2 * n_src, gt, (int64_t)n * n_src, g2,
+                             (int64_t)n2 * 2 * n_src));
+  if (!want_T) return 0;
+  {
+    const int cols = n + 2 * m + n_src;
+    dim3 grid(std::min((cols + 255) / 256, 64), n, n_merges);
+    merge_ext_kernel<double2><<<grid, 256, 0, st>>>(
+        tp.base, m, n_src, reinterpret_cast<const double2*>(R_in), reinterpret_cast<const double2*>(h_in),
+        reinterpret_cast<double2*>(R_out), reinterpret_cast<double2*>(h_out), reinterpret_cast<double2*>(Bg));
+    HPS_LAUNCH_CHECK("merge_ext_kernel<complex>");
+  }
+  // R_out[panel e] += B_block (complex m x m) * S[unknown slot rows]; real GEMMs on the interleaved views
+  const int64_t sB = (int64_t)8 * 2 * m * m * 2, sS2 = (int64_t)n2 * n2, sR = (int64_t)n * n * 2;
+  const int64_t sg2 = (int64_t)n2 * 2 * n_src, sH = (int64_t)n * n_src * 2;
+  for (int e = 0; e < 8; ++e)
+    for (int j = 0; j < 2; ++j) {
+      const int slot = tp.base.ext_slot[e][j];
+      const double* Ablk = Bg + ((int64_t)e * 2 + j) * m * m * 2;
+      HPS_TRY(dgemm(st, m, 2 * n, 2 * m, 1.0, Ablk, 2 * m, sB, S2 + (int64_t)2 * slot * m * n2, n2, sS2, 1.0,
+                    R_out + (int64_t)e * m * n2, n2, sR, n_merges));
+      HPS_TRY(dgemm(st, m, 2 * n_src, 2 * m, 1.0, Ablk, 2 * m, sB, g2 + (int64_t)2 * slot * m * 2 * n_src, 2 * n_src, sg2,
+                    1.0, h_out + (int64_t)e * m * 2 * n_src, 2 * n_src, sH, n_merges));
+    }
+  return 0;
+}
+
+// ws: n_nodes * (16m * 2 n_src + 8m * 2 n_src) doubles
+int down_quad_iti_level(cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
+                        const double* gt, double* g_children, void* ws) {
+  if (n_nodes <= 0 || m <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
+  if (n_nodes > 65535) return fail_arg(2, "n_nodes per call is limited to 65535");
+  const ItiTopo& tp = iti_topo();
+  const int n = 8 * m, n2 = 2 * n, w = 2 * n_src;
+  double* G2 = static_cast<double*>(ws);
+  double* g_int = G2 + (int64_t)n_nodes * n2 * w;
+  HPS_TRY(complex_expand(st, n_nodes, n, n_src, g_ext, (int64_t)n * n_src, G2, (int64_t)n2 * w));
+  HPS_TRY(dgemm_affine(st, n, w, n2, S, n2, (int64_t)n * n2, G2, w, (int64_t)n2 * w, gt, w, (int64_t)n * w, g_int, w,
+                       (int64_t)n * w, n_nodes));
+  return down_scatter(tp.base, st, n_nodes, m, w, g_ext, g_int, g_children);
+}
+
+// u = Y g + v on every leaf, complex128.  ws: n_leaves * 2 n_g * 2 n_src doubles
+int leaf_apply_complex(cudaStream_t st, int n_leaves, int n_c, int n_g, int n_src, const double* Y, const double* g,
+                       const double* v, double* u, void* ws) {
+  if (n_leaves <= 0 || n_c <= 0 || n_g <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
+  const int w = 2 * n_src;
+  double* G2 = static_cast<double*>(ws);
+  HPS_TRY(complex_expand(st, n_leaves, n_g, n_src, g, (int64_t)n_g * n_src, G2, (int64_t)2 * n_g * w));
+  return dgemm_affine(st, n_c, w, 2 * n_g, Y, 2 * n_g, (int64_t)n_c * 2 * n_g, G2, w, (int64_t)2 * n_g * w, v, w,
+                      (int64_t)n_c * w, u, w, (int64_t)n_c * w, n_leaves);
 }
 
 size_t merge_oct_ws_bytes(int n_merges, int m) { return merge_ws_bytes(oct_topo(), n_merges, m); }

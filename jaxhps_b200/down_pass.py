@@ -90,3 +90,45 @@ def down_pass_uniform_2D_DtN(boundary_data, S_lst, g_tilde_lst, Y_arr, v_arr, de
     """2D analogue (reference `down_pass/_uniform_2D_DtN.py:7-122`); ``Y_arr=None`` returns the
     leaves' boundary data instead of the solution (`:111-112`)."""
     return _down_pass(boundary_data, S_lst, g_tilde_lst, Y_arr, v_arr, 2, device, host_device)
+
+
+def down_pass_uniform_2D_ItI(boundary_data, S_lst, g_tilde_lst, Y_arr, v_arr, device=None, host_device=None):
+    """ItI down pass, complex128 (reference `down_pass/_uniform_2D_ItI.py:8-118`): incoming impedance
+    data is pushed from the root to the leaves, then ``u = Y g + v``.  ``Y_arr=None`` returns the
+    leaves' incoming impedance data (`:105-106`)."""
+    dev = _lib.require_cuda(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        S_dev = [_lib.to_device(S, dev, dtype=torch.complex128) for S in S_lst]
+        g_dev = [_lib.to_device(g, dev, dtype=torch.complex128) for g in g_tilde_lst]
+        multi = bool(len(g_dev)) and g_dev[0].ndim == 3
+        bd = _lib.to_device(boundary_data, dev, dtype=torch.complex128)
+        if multi and bd.ndim == 1:
+            raise ValueError("For multi-source downward pass, need to specify boundary data for each source.")
+        n_src = bd.shape[-1] if multi else 1
+        g_cur = bd.reshape(1, -1, n_src).contiguous()
+        c128 = dict(dtype=torch.complex128, device=dev)
+        for level in range(len(S_dev) - 1, -1, -1):
+            S = S_dev[level]
+            n_nodes, n, _ = S.shape
+            m = n // 8
+            gt = g_dev[level].reshape(n_nodes, n, n_src)
+            if g_cur.shape[0] != n_nodes or g_cur.shape[1] != n:
+                raise ValueError(f"level {level}: boundary data {tuple(g_cur.shape)} does not match S {tuple(S.shape)}")
+            out = torch.empty((n_nodes * 4, 4 * m, n_src), **c128)
+            ws = torch.empty(n_nodes * 48 * m * n_src, dtype=torch.float64, device=dev)
+            rc = lib.hps_down_quad_iti_level(_lib.stream_ptr(), n_nodes, m, n_src, _lib.ptr(S), _lib.ptr(g_cur), _lib.ptr(gt),
+                                             _lib.ptr(out), _lib.ptr(ws))
+            _lib.check(rc, "hps_down_quad_iti_level")
+            g_cur = out
+        if Y_arr is None:
+            return _lib.to_result(g_cur if multi else g_cur[..., 0], host_device)
+        Y = _lib.to_device(Y_arr, dev, dtype=torch.complex128)
+        v = _lib.to_device(v_arr, dev, dtype=torch.complex128)
+        n_leaves, n_c, n_g = Y.shape
+        u = torch.empty((n_leaves, n_c, n_src), **c128)
+        ws = torch.empty(n_leaves * 4 * n_g * n_src, dtype=torch.float64, device=dev)
+        rc = lib.hps_leaf_apply_complex(_lib.stream_ptr(), n_leaves, n_c, n_g, n_src, _lib.ptr(Y), _lib.ptr(g_cur),
+                                        _lib.ptr(v.reshape(n_leaves, n_c, n_src)), _lib.ptr(u), _lib.ptr(ws))
+        _lib.check(rc, "hps_leaf_apply_complex")
+        return _lib.to_result(u if multi else u[..., 0], host_device)

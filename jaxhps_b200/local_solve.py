@@ -96,3 +96,59 @@ def local_solve_stage_uniform_2D_DtN(pde_problem, host_device=None, device=None)
     """Leaf DtN maps for a uniform quadtree; note the reference's argument order
     (`local_solve/_uniform_2D_DtN.py:9-13`)."""
     return _local_solve_dtn(pde_problem, 2, device, host_device)
+
+
+def local_solve_stage_uniform_2D_ItI(pde_problem, device=None, host_device=None):
+    """Leaf impedance-to-impedance maps, complex128.  Returns ``(Y, R, v, h)`` like the reference
+    (`local_solve/_uniform_2D_ItI.py:10-117`): ``(n, p^2, 4q)``, ``(n, 4q, 4q)``, ``(n, p^2[, n_src])``,
+    ``(n, 4q[, n_src])``."""
+    dev = _lib.require_cuda(device)
+    lib = _lib.load()
+    dom = pde_problem.domain
+    p, q = dom.p, dom.q
+    for name in _ORDER_2D:
+        a = getattr(pde_problem, f"{name}_coefficients", None)
+        if a is not None and (np.iscomplexobj(a) if not isinstance(a, torch.Tensor) else a.is_complex()):
+            raise NotImplementedError("complex-valued coefficient fields are not supported by the CUDA ItI leaf yet")
+    with torch.cuda.device(dev):
+        coeffs, which = _gather_coeffs(pde_problem, _ORDER_2D, dev)
+        src = _lib.to_device(pde_problem.source, dev, dtype=torch.complex128)
+        multi = src.ndim == 3
+        if not multi:
+            src = src.unsqueeze(-1)
+        n_leaves, n_c, n_src = src.shape
+        cache = pde_problem.__dict__.setdefault("_device_constants", {})
+        key = ("iti", str(dev))
+        if key not in cache:
+            cache[key] = (_lib.to_device(pde_problem.D1, dev), _lib.to_device(pde_problem.P, dev),
+                          _lib.to_device(pde_problem.G, dev, dtype=torch.complex128),
+                          _lib.to_device(pde_problem.QH, dev, dtype=torch.complex128))
+        D1, P, G, QH = cache[key]
+        n_g = QH.shape[0]
+        c128 = dict(dtype=torch.complex128, device=dev)
+        Y = torch.empty((n_leaves, n_c, n_g), **c128)
+        R = torch.empty((n_leaves, n_g, n_g), **c128)
+        v = torch.empty((n_leaves, n_c, n_src), **c128)
+        h = torch.empty((n_leaves, n_g, n_src), **c128)
+        info = torch.zeros(n_leaves, dtype=torch.int32, device=dev)
+        one = ctypes.c_size_t()
+        _lib.check(lib.hps_local_solve_2d_iti_workspace(1, p, q, n_src, ctypes.byref(one)), "workspace query")
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        budget = min(MAX_WORKSPACE_BYTES, int(0.6 * free_b))
+        chunk = int(max(1, min(n_leaves, budget // max(1, one.value), 65535)))
+        need = ctypes.c_size_t()
+        _lib.check(lib.hps_local_solve_2d_iti_workspace(chunk, p, q, n_src, ctypes.byref(need)), "workspace query")
+        ws = _lib.WORKSPACE.get(need.value, dev)
+        for s in range(0, n_leaves, chunk):
+            e = min(n_leaves, s + chunk)
+            c_chunk = coeffs[:, s:e].contiguous() if (s, e) != (0, n_leaves) else coeffs
+            rc = lib.hps_local_solve_2d_iti(
+                _lib.stream_ptr(), e - s, p, q, n_src, which, _lib.ptr(c_chunk), _lib.ptr(D1), _lib.ptr(P), _lib.ptr(G),
+                _lib.ptr(QH), _lib.ptr(src[s:e]), _lib.ptr(Y[s:e]), _lib.ptr(R[s:e]), _lib.ptr(v[s:e]), _lib.ptr(h[s:e]),
+                _lib.ptr(ws), ws.numel(), _lib.ptr(info[s:e]),
+            )
+            _lib.check(rc, "hps_local_solve_2d_iti")
+        _lib.check_info(info, "ItI local solve")
+        if not multi:
+            v, h = v[..., 0], h[..., 0]
+        return tuple(_lib.to_result(t, host_device) for t in (Y, R, v, h))

@@ -120,3 +120,54 @@ def merge_root_columns_3D_DtN(T8, h8, col0: int, ncols: int, device=None):
         _lib.check(rc, "hps_merge_oct_dtn_root_cols")
         _lib.check_info(info, "root merge")
         return S, (g if multi else g[..., 0])
+
+
+def merge_stage_uniform_2D_ItI(T_arr, h_arr, l: int, device=None, host_device=None, subtree_recomp: bool = False,
+                               return_T: bool = False, return_h: bool = False):
+    """ItI quad merges, complex128 (reference `merge/_uniform_2D_ItI.py:19-179`).  Returns
+    ``(S_lst, g_tilde_lst[, T_last][, h_last])``; every list entry keeps its batch axis (root: 1)."""
+    dev = _lib.require_cuda(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        T = _lib.to_device(T_arr, dev, dtype=torch.complex128)
+        h = _lib.to_device(h_arr, dev, dtype=torch.complex128)
+        if T.ndim == 4:  # the reference's (n/4, 4, n_ext, n_ext) carry
+            T = T.reshape(-1, T.shape[-2], T.shape[-1])
+            h = h.reshape(T.shape[0], T.shape[-1], -1) if h.ndim == 4 else h.reshape(T.shape[0], T.shape[-1])
+        multi = h.ndim == 3
+        if not multi:
+            h = h.unsqueeze(-1)
+        n_src = h.shape[-1]
+        if T.shape[0] != 4**l:
+            raise ValueError(f"expected {4**l} leaf operators for l={l}, got {T.shape[0]}")
+        S_lst, g_lst = [], []
+        c128 = dict(dtype=torch.complex128, device=dev)
+        for level in range(l, 0, -1):
+            n_merges = T.shape[0] // 4
+            m = T.shape[-1] // 4
+            n = 8 * m
+            want_T = (level > 1) or return_T or subtree_recomp or return_h
+            S = torch.empty((n_merges, n, n), **c128)
+            g = torch.empty((n_merges, n, n_src), **c128)
+            T_out = torch.empty((n_merges, n, n), **c128) if want_T else None
+            h_out = torch.empty((n_merges, n, n_src), **c128) if want_T else None
+            info = torch.zeros(n_merges, dtype=torch.int32, device=dev)
+            need = ctypes.c_size_t()
+            _lib.check(lib.hps_merge_quad_iti_level_workspace(n_merges, m, n_src, ctypes.byref(need)), "workspace query")
+            ws = _lib.WORKSPACE.get(need.value, dev)
+            rc = lib.hps_merge_quad_iti_level(_lib.stream_ptr(), n_merges, m, n_src, _lib.ptr(T), _lib.ptr(h), _lib.ptr(S),
+                                              _lib.ptr(g), _lib.ptr(T_out), _lib.ptr(h_out), 1 if want_T else 0,
+                                              _lib.ptr(ws), ws.numel(), _lib.ptr(info))
+            _lib.check(rc, "hps_merge_quad_iti_level")
+            _lib.check_info(info, f"ItI merge level {level}")
+            T, h = T_out, h_out
+            S_lst.append(S)
+            g_lst.append(g if multi else g[..., 0])
+        if subtree_recomp:
+            return _lib.to_result(T, host_device), _lib.to_result(h if multi else h[..., 0], host_device)
+        out = ([_lib.to_result(S, host_device) for S in S_lst], [_lib.to_result(g, host_device) for g in g_lst])
+        if return_T:
+            out = out + (_lib.to_result(T[0], host_device),)
+        if return_h:
+            out = out + (_lib.to_result((h if multi else h[..., 0])[0], host_device),)
+        return out

@@ -443,3 +443,128 @@ def down_pass_uniform_2D_DtN(boundary_data, S_lst, g_tilde_lst, Y_arr, v_arr):
     if bdry.ndim == 3:
         return np.einsum("ijk,ikl->ijl", Y_arr, bdry) + v_arr
     return np.einsum("ijk,ik->ij", Y_arr, bdry) + v_arr
+
+
+# =====================================================================================
+# 2D quad merge, ItI (impedance-to-impedance, complex128).
+# Every interface carries TWO unknown vectors: the incoming impedance data of each of the two
+# children that share it.  Reference: `merge/_uniform_2D_ItI.py:182-375`,
+# `merge/_schur_complement.py:6-41, 78-114`.
+# =====================================================================================
+
+# unknown order used while solving: [a5, a8, c6, c7 | b5, b6, d7, d8] as (child, interface slot)
+_ITI_SOLVE_ORDER = [(0, 0), (0, 3), (2, 1), (2, 2), (1, 0), (1, 1), (3, 2), (3, 3)]
+# order of the rows of S / g_tilde the reference returns: [a5, b5, b6, c6, c7, d7, d8, a8]
+_ITI_OUT_ORDER = [(0, 0), (1, 0), (1, 1), (2, 1), (2, 2), (3, 2), (3, 3), (0, 3)]
+
+
+def invert_D_ItI(D_12: np.ndarray, D_21: np.ndarray) -> np.ndarray:
+    """``(I + [[0, D12],[D21, 0]])^-1`` through the Schur complement ``W = I - D12 D21``
+    (`_schur_complement.py:78-114`)."""
+    n, m = D_12.shape[0], D_21.shape[0]
+    W_inv = np.linalg.inv(np.eye(n) - D_12 @ D_21)
+    out = np.zeros((n + m, n + m), dtype=D_12.dtype)
+    out[:n, :n] = W_inv
+    out[:n, n:] = -1 * W_inv @ D_12
+    out[n:, :n] = -1 * D_21 @ W_inv
+    out[n:, n:] = np.eye(m) + D_21 @ W_inv @ D_12
+    return out
+
+
+def uniform_quad_merge_ItI(R_children: np.ndarray, h_children: np.ndarray):
+    """One ItI quad merge.  R_children (4, 4m, 4m) complex; h_children (4, 4m, n_src).
+    Returns (S, R, h_out, g_tilde) with S (8m, 8m), g_tilde (8m, n_src)."""
+    m = R_children.shape[-1] // 4
+    n_src = h_children.shape[-1]
+    dt = np.complex128
+    pre = [(0, 3), (0, 0), (1, 0), (1, 1), (2, 1), (2, 2), (3, 2), (3, 3)]  # ext panels before the roll
+    blk = lambda k: slice(k * m, (k + 1) * m)  # noqa: E731
+    B = np.zeros((8 * m, 8 * m), dtype=dt)
+    C = np.zeros((8 * m, 8 * m), dtype=dt)
+    Dc = np.zeros((8 * m, 8 * m), dtype=dt)  # the coupling part of D (D = I + Dc)
+    h_int = np.zeros((8 * m, n_src), dtype=dt)
+    h_ext = np.zeros((8 * m, n_src), dtype=dt)
+    A_lst = []
+    pos = {key: i for i, key in enumerate(_ITI_SOLVE_ORDER)}
+    for c in range(4):
+        R, h = R_children[c], h_children[c]
+        ext = sorted((pre.index((c, s)), _side_idx(s, m, False)) for s in range(4) if _QUAD_ROLES[c][s][0] == "ext")
+        inte = [(_QUAD_ROLES[c][s][1], _side_idx(s, m, _QUAD_ROLES[c][s][2])) for s in range(4) if _QUAD_ROLES[c][s][0] == "int"]
+        ext_idx = np.concatenate([ix for _, ix in ext])
+        A_lst.append(R[np.ix_(ext_idx, ext_idx)])
+        for k, ix in ext:
+            h_ext[blk(k)] = h[ix]
+            for s, jx in inte:
+                B[blk(k), blk(pos[(c, s)])] = R[np.ix_(ix, jx)]  # own incoming interface data -> own exterior
+        for s, ix in inte:
+            # the equation for the OTHER child's unknown on interface s is driven by this child's outgoing data
+            other = [y for y in _QUAD_INTERFACES[s] if y != c][0]
+            row = pos[(other, s)]
+            h_int[blk(row)] = h[ix]
+            for k, jx in ext:
+                C[blk(row), blk(k)] = R[np.ix_(ix, jx)]
+            for s2, jx in inte:
+                Dc[blk(row), blk(pos[(c, s2)])] = R[np.ix_(ix, jx)]
+    half = 4 * m
+    assert not Dc[:half, :half].any() and not Dc[half:, half:].any()
+    D_inv = invert_D_ItI(Dc[:half, half:], Dc[half:, :half])
+    T, S, h_out, g_tilde = assemble_merge_outputs(A_lst, B, C, D_inv, h_ext, h_int)
+    T = np.roll(np.roll(T, -m, axis=0), -m, axis=1)
+    S = np.roll(S, -m, axis=1)
+    h_out = np.roll(h_out, -m, axis=0)
+    r = np.concatenate([np.arange(pos[key] * m, (pos[key] + 1) * m) for key in _ITI_OUT_ORDER])
+    return S[r], T, h_out, g_tilde[r]
+
+
+def merge_stage_uniform_2D_ItI(T_arr, h_arr, l: int, return_T: bool = False):
+    """Level loop (`merge/_uniform_2D_ItI.py:19-179`): lists keep their batch axis (root: 1);
+    single-source ``g_tilde`` entries are squeezed to (n, 8m)."""
+    multi = h_arr.ndim == 3
+    if not multi:
+        h_arr = h_arr[..., None]
+    S_lst, g_lst = [], []
+    for _ in range(l):
+        n = T_arr.shape[0] // 4
+        outs = [uniform_quad_merge_ItI(T_arr[4 * i : 4 * i + 4], h_arr[4 * i : 4 * i + 4]) for i in range(n)]
+        S_lst.append(np.stack([o[0] for o in outs]))
+        T_arr = np.stack([o[1] for o in outs])
+        h_arr = np.stack([o[2] for o in outs])
+        g = np.stack([o[3] for o in outs])
+        g_lst.append(g if multi else g[..., 0])
+    if return_T:
+        return S_lst, g_lst, T_arr[0]
+    return S_lst, g_lst
+
+
+def propagate_down_quad_ItI(S: np.ndarray, g_ext: np.ndarray, g_tilde: np.ndarray) -> np.ndarray:
+    """(4, 4m[, n_src]) incoming impedance data of the children
+    (`down_pass/_uniform_2D_ItI.py:121-192`)."""
+    m = g_ext.shape[0] // 8
+    t_int = S @ g_ext + g_tilde
+    where = {key: i for i, key in enumerate(_ITI_OUT_ORDER)}
+    kids = []
+    for c in range(4):
+        parts = []
+        for side in range(4):
+            kind, k, flipped = _QUAD_ROLES[c][side]
+            if kind == "ext":
+                seg = g_ext[k * m : (k + 1) * m]
+            else:
+                w = where[(c, k)]
+                seg = t_int[w * m : (w + 1) * m]
+            parts.append(seg[::-1] if flipped else seg)
+        kids.append(np.concatenate(parts))
+    return np.stack(kids)
+
+
+def down_pass_uniform_2D_ItI(boundary_data, S_lst, g_tilde_lst, Y_arr, v_arr):
+    """(`down_pass/_uniform_2D_ItI.py:8-118`)."""
+    bdry = np.asarray(boundary_data)[None]
+    for level in range(len(S_lst) - 1, -1, -1):
+        kids = [propagate_down_quad_ItI(S_lst[level][i], bdry[i], g_tilde_lst[level][i]) for i in range(bdry.shape[0])]
+        bdry = np.concatenate(kids, axis=0)
+    if Y_arr is None:
+        return bdry
+    if bdry.ndim == 3:
+        return np.einsum("ijk,ikl->ijl", Y_arr, bdry) + v_arr
+    return np.einsum("ijk,ik->ij", Y_arr, bdry) + v_arr

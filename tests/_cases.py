@@ -43,7 +43,27 @@ def seeded_inputs(dim, p, q, L, nsrc, seed):
     return co, src, bdry
 
 
+ETA = 4.0  # impedance parameter of the ItI cases (dim code 20 = 2D ItI)
+
+
+def seeded_inputs_iti(p, q, L, nsrc, seed):
+    rng = np.random.default_rng(seed)
+    shp = (4**L, p * p)
+    co = {"D_xx_coefficients": np.ones(shp), "D_yy_coefficients": np.ones(shp),
+          "I_coefficients": ETA**2 * (1 + 0.3 * rng.normal(size=shp))}
+    sshape = shp if nsrc == 1 else shp + (nsrc,)
+    src = rng.normal(size=sshape) + 1j * rng.normal(size=sshape)
+    n_bdry = 4 * 2**L * q
+    bshape = (n_bdry,) if nsrc == 1 else (n_bdry, nsrc)
+    bdry = rng.normal(size=bshape) + 1j * rng.normal(size=bshape)
+    return co, src, bdry
+
+
 def seeded_problem(dim, p, q, L, nsrc=1, seed=0):
+    if dim == 20:
+        co, src, bdry = seeded_inputs_iti(p, q, L, nsrc, seed)
+        dom = make_domain(2, p, q, L)
+        return hps.PDEProblem(dom, source=src, use_ItI=True, eta=ETA, **co), bdry
     co, src, bdry = seeded_inputs(dim, p, q, L, nsrc, seed)
     dom = make_domain(dim, p, q, L)
     return hps.PDEProblem(dom, source=src, **co), bdry

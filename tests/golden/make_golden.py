@@ -20,10 +20,35 @@ import jax.numpy as jnp  # noqa: E402  (the shim)
 import jaxhps as ref  # noqa: E402
 from jaxhps.local_solve import (  # noqa: E402
     local_solve_stage_uniform_2D_DtN,
+    local_solve_stage_uniform_2D_ItI,
     local_solve_stage_uniform_3D_DtN,
 )
-from jaxhps.merge import merge_stage_uniform_2D_DtN, merge_stage_uniform_3D_DtN  # noqa: E402
-from jaxhps.down_pass import down_pass_uniform_2D_DtN, down_pass_uniform_3D_DtN  # noqa: E402
+from jaxhps.merge import (  # noqa: E402
+    merge_stage_uniform_2D_DtN,
+    merge_stage_uniform_2D_ItI,
+    merge_stage_uniform_3D_DtN,
+)
+from jaxhps.down_pass import (  # noqa: E402
+    down_pass_uniform_2D_DtN,
+    down_pass_uniform_2D_ItI,
+    down_pass_uniform_3D_DtN,
+)
+
+ETA = 4.0  # impedance parameter of the ItI cases (dim code 20 = 2D ItI)
+
+
+def inputs_iti(p, q, L, nsrc, seed):
+    """Seeded Helmholtz-type ItI problem: u_xx + u_yy + k^2 (1 + 0.3 N(0,1)) u = f, complex f and data."""
+    rng = np.random.default_rng(seed)
+    shp = (4**L, p * p)
+    co = {"D_xx_coefficients": np.ones(shp), "D_yy_coefficients": np.ones(shp),
+          "I_coefficients": ETA**2 * (1 + 0.3 * rng.normal(size=shp))}
+    sshape = shp if nsrc == 1 else shp + (nsrc,)
+    src = rng.normal(size=sshape) + 1j * rng.normal(size=sshape)
+    n_bdry = 4 * 2**L * q
+    bshape = (n_bdry,) if nsrc == 1 else (n_bdry, nsrc)
+    bdry = rng.normal(size=bshape) + 1j * rng.normal(size=bshape)
+    return co, src, bdry
 
 
 def inputs(dim, p, q, L, nsrc, seed):
@@ -46,15 +71,20 @@ def inputs(dim, p, q, L, nsrc, seed):
 
 
 def run_case(dim, p, q, L, nsrc, seed, full):
-    co, src, bdry = inputs(dim, p, q, L, nsrc, seed)
-    if dim == 3:
+    iti = dim == 20
+    co, src, bdry = inputs_iti(p, q, L, nsrc, seed) if iti else inputs(dim, p, q, L, nsrc, seed)
+    if iti:
+        root = ref.DiscretizationNode2D(xmin=-1.0, xmax=1.0, ymin=-1.0, ymax=1.0)
+        ls, mg, dp = local_solve_stage_uniform_2D_ItI, merge_stage_uniform_2D_ItI, down_pass_uniform_2D_ItI
+    elif dim == 3:
         root = ref.DiscretizationNode3D(xmin=0.0, xmax=1.0, ymin=0.0, ymax=1.0, zmin=0.0, zmax=1.0)
         ls, mg, dp = local_solve_stage_uniform_3D_DtN, merge_stage_uniform_3D_DtN, down_pass_uniform_3D_DtN
     else:
         root = ref.DiscretizationNode2D(xmin=-1.0, xmax=1.0, ymin=-1.0, ymax=1.0)
         ls, mg, dp = local_solve_stage_uniform_2D_DtN, merge_stage_uniform_2D_DtN, down_pass_uniform_2D_DtN
     dom = ref.Domain(p=p, q=q, root=root, L=L)
-    pb = ref.PDEProblem(dom, source=jnp.array(src), **{k: jnp.array(v) for k, v in co.items()})
+    extra = dict(use_ItI=True, eta=ETA) if iti else {}
+    pb = ref.PDEProblem(dom, source=jnp.array(src), **{k: jnp.array(v) for k, v in co.items()}, **extra)
     Y, T, v, h = ls(pb)
     S_lst, g_lst, T_top = mg(T, h, l=L, return_T=True)
     u = dp(jnp.array(bdry), S_lst, g_lst, Y, v)
@@ -65,9 +95,13 @@ def run_case(dim, p, q, L, nsrc, seed, full):
     for i, g in enumerate(g_lst):
         out[f"g_tilde_{i}"] = np.asarray(g)
     if full:
-        out.update(Y=np.asarray(Y), T=np.asarray(T), T_top=np.asarray(T_top), P=np.asarray(pb.P), Q=np.asarray(pb.Q),
+        out.update(Y=np.asarray(Y), T=np.asarray(T), T_top=np.asarray(T_top), P=np.asarray(pb.P),
                    D_x=np.asarray(pb.D_x), interior_points=np.asarray(dom.interior_points),
                    boundary_points=np.asarray(dom.boundary_points))
+        if iti:
+            out.update(G=np.asarray(pb.G), QH=np.asarray(pb.QH))
+        else:
+            out.update(Q=np.asarray(pb.Q))
         for i, S in enumerate(S_lst):
             out[f"S_{i}"] = np.asarray(S)
     return out
@@ -82,6 +116,8 @@ CASES = {
     "ref3d_p5q3L1": (3, 5, 3, 1, 1, 14, True),
     "ref2d_p6q4L2": (2, 6, 4, 2, 1, 21, True),
     "ref2d_p7q5L1_ms": (2, 7, 5, 1, 3, 22, True),
+    "refiti_p6q4L2": (20, 6, 4, 2, 1, 31, True),
+    "refiti_p8q6L2_ms": (20, 8, 6, 2, 2, 32, False),
 }
 
 if __name__ == "__main__":

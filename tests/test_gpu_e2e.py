@@ -93,3 +93,31 @@ def test_full_size_properties_p12_L2():
     n_b = 12**3 - 10**3
     res = A[n_b:] @ u1[leaf] - src[leaf, n_b:]
     assert np.abs(res).max() / np.abs(A[n_b:]).max() / np.abs(u1[leaf]).max() < 1e-11
+
+
+def test_helmholtz_ItI_plane_wave_2D():
+    """2D ItI end to end (complex128): Delta u + k^2 u = 0 with u = exp(i k x), incoming impedance
+    data u_n + i eta u on the boundary (restates the reference's Helmholtz ItI accuracy case,
+    tests/test_accuracy/cases.py:135-209); GPU and oracle must reach the same error."""
+    k = 5.0
+    root = hps.DiscretizationNode2D(-1.0, 1.0, -1.0, 1.0)
+    dom = hps.Domain(16, 14, root, 2)
+    x = dom.interior_points
+    one = np.ones_like(x[..., 0])
+    pb = hps.PDEProblem(dom, source=np.zeros_like(one, dtype=np.complex128), D_xx_coefficients=one,
+                        D_yy_coefficients=one, I_coefficients=k**2 * one, use_ItI=True, eta=k)
+    b = dom.boundary_points
+    n = b.shape[0] // 4
+    u_b = np.exp(1j * k * b[:, 0])
+    dudx = 1j * k * u_b
+    normal_x = np.concatenate([np.zeros(n), np.ones(n), np.zeros(n), -np.ones(n)])  # S, E, N, W
+    g = normal_x * dudx + 1j * k * u_b
+    hps.build_solver(pb, host_device="cuda:0")
+    u = hps.solve(pb, g)
+    exact = np.exp(1j * k * x[..., 0])
+    Y, R, v, h = orc.local_solve_stage_uniform_2D_ItI(pb)
+    S, gt = orc.merge_stage_uniform_2D_ItI(R, h, 2)
+    uo = orc.down_pass_uniform_2D_ItI(g, S, gt, Y, v)
+    assert np.abs(uo - exact).max() < 1e-8
+    assert np.abs(u - exact).max() < 1e-8
+    assert np.abs(u - uo).max() < 1e-9
