@@ -140,6 +140,34 @@ int hps_down_quad_iti_level(void* stream, int n_nodes, int m, int n_src, const d
 int hps_leaf_apply_complex(void* stream, int n_leaves, int n_c, int n_g, int n_src,
                            const double* Y, const double* g, const double* v, double* u, void* ws);
 
+/* ---- source given at solve time (2D uniform): no-source build + upward pass ----------------
+ * No-source merges additionally return D^-1 [n][n_int][n_int] and B D^-1 [n][n_ext][n_int]
+ * (reference: merge/_nosource_uniform_2D_DtN.py:13-271, merge/_nosource_uniform_2D_ItI.py:19-344,
+ * merge/_schur_complement.py:240-290).  Layout here: D^-1 rows/cols in this library's unknown
+ * order (DtN: interfaces 5..8; ItI: [a5,b5,b6,c6,c7,d7,d8,a8]); B D^-1 rows in boundary order.  The
+ * Python shims convert to the reference's stored layout.  scratch: 28 m (DtN) / 64 m (ItI)
+ * doubles per merge.  Workspaces: the *_level_workspace queries with n_src = 1. */
+int hps_merge_quad_dtn_level_nosource(void* stream, int n_merges, int m, const double* T_in,
+                                      double* S, double* T_out, double* D_inv, double* BD_inv,
+                                      double* scratch, void* ws, size_t ws_bytes, int* info);
+int hps_merge_quad_iti_level_nosource(void* stream, int n_merges, int m, const double* R_in,
+                                      double* S, double* R_out, double* D_inv, double* BD_inv,
+                                      double* scratch, void* ws, size_t ws_bytes, int* info);
+/* Up-pass gathers (reference: up_pass/_uniform_2D_DtN.py:110-173, up_pass/_uniform_2D_ItI.py:139-219):
+ * children's outgoing data h_in [4n][4m][n_src] -> h_int [n][n_int][n_src], h_ext [n][8m][n_src];
+ * ext_shift = 1 writes the exterior panels in the reference's pre-roll order.  ItI: block u of
+ * h_int (the OTHER child's data for unknown u) lands at position pos8[u] (NULL = identity). */
+int hps_up_gather_quad(void* stream, int n_nodes, int m, int n_src, const double* h_in,
+                       double* h_int, double* h_ext, int ext_shift);
+int hps_up_gather_quad_iti(void* stream, int n_nodes, int m, int n_src, const double* h_in,
+                           double* h_int, double* h_ext, int ext_shift, const int* pos8 /* host */);
+/* C[b] = alpha A[b] B[b] + beta C[b], complex128 interleaved, alpha/beta real; B contiguous K x N;
+ * lda/ldc/strides in complex elements; ws: batch * 4 K N doubles.  One real DMMA GEMM on the
+ * interleaved views with B expanded to its 2K x 2N real form. */
+int hps_zgemm_strided_batched(void* stream, int M, int N, int K, double alpha,
+                              const double* A, int64_t lda, int64_t sA, const double* B, int64_t sB,
+                              double beta, double* C, int64_t ldc, int64_t sC, int batch, void* ws);
+
 /* ---- down_pass (reference: down_pass/_uniform_3D_DtN.py:116-246,
  *      down_pass/_uniform_2D_DtN.py:125-189) -------------------------------------------
  * One level: g_int = S g_ext + g_tilde, then the children's boundary vectors.

@@ -6,7 +6,7 @@ from ._domain import Domain
 from ._pdeproblem import PDEProblem
 from ._build_solver import build_solver
 from ._solve import solve
-from . import local_solve, merge, down_pass, quadrature  # noqa: F401
+from . import local_solve, merge, down_pass, up_pass, quadrature  # noqa: F401
 
 __all__ = [
     "Domain",

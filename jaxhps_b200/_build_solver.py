@@ -22,10 +22,11 @@ def build_solver(pde_problem: PDEProblem, return_top_T: bool = False, compute_de
     default; a CUDA device keeps them resident (recommended: ``solve`` then moves nothing).
     Returns the top-level Poincaré–Steklov matrix when ``return_top_T`` is set."""
     if pde_problem.source is None:
-        raise NotImplementedError(
-            "building without a source (up-pass formulation, reference `_build_solver.py:261-331`) "
-            "is not part of the hot path built so far"
-        )
+        if not pde_problem.domain.bool_uniform or not pde_problem.domain.bool_2D:
+            raise ValueError(
+                "Build stage for problems without source terms is only implemented for 2D uniform ItI problems."
+            )
+        return _nosource_build_solver(pde_problem, return_top_T, compute_device, host_device)
     if not pde_problem.domain.bool_uniform:
         raise NotImplementedError("adaptive discretisations are outside the hot path built so far")
     from . import _lib
@@ -50,3 +51,27 @@ def build_solver(pde_problem: PDEProblem, return_top_T: bool = False, compute_de
     if return_top_T:
         return out[2]
     return None
+
+
+def _nosource_build_solver(pde_problem: PDEProblem, return_top_T: bool, compute_device, host_device):
+    """Source-free build for 2D uniform problems: keeps ``Phi``, ``D_inv_lst`` and ``BD_inv_lst`` so
+    that ``solve(..., source=f)`` can run an upward pass (reference `_build_solver.py:261-331`)."""
+    from . import _lib
+    from .up_pass import (
+        nosource_local_solve_stage_uniform_2D_DtN,
+        nosource_local_solve_stage_uniform_2D_ItI,
+        nosource_merge_stage_uniform_2D_DtN,
+        nosource_merge_stage_uniform_2D_ItI,
+    )
+
+    dev = _lib.require_cuda(compute_device)
+    if pde_problem.use_ItI:
+        ls, mg = nosource_local_solve_stage_uniform_2D_ItI, nosource_merge_stage_uniform_2D_ItI
+    else:
+        ls, mg = nosource_local_solve_stage_uniform_2D_DtN, nosource_merge_stage_uniform_2D_DtN
+    Y, T, Phi = ls(pde_problem, device=dev, host_device=dev)
+    pde_problem.Y = _lib.to_result(Y, host_device)
+    pde_problem.Phi = _lib.to_result(Phi, host_device)
+    out = mg(T, pde_problem.domain.L, device=dev, host_device=host_device, return_T=return_top_T)
+    pde_problem.S_lst, pde_problem.D_inv_lst, pde_problem.BD_inv_lst = out[0], out[1], out[2]
+    return out[3] if return_top_T else None

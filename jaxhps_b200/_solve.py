@@ -17,7 +17,7 @@ def solve(pde_problem: PDEProblem, boundary_data, source=None, compute_device=No
                 "Source can only be specified for 2D uniform ItI problems. For other problems, the source must "
                 "be specified at the time the solver is built."
             )
-        raise NotImplementedError("solve-time sources (up pass) are not part of the hot path built so far")
+        return _up_then_down_pass(pde_problem, boundary_data, source, compute_device, host_device)
     if not pde_problem.domain.bool_uniform:
         raise NotImplementedError("adaptive discretisations are outside the hot path built so far")
     if isinstance(boundary_data, list):
@@ -31,3 +31,17 @@ def solve(pde_problem: PDEProblem, boundary_data, source=None, compute_device=No
         down = down_pass_uniform_2D_DtN if pde_problem.domain.bool_2D else down_pass_uniform_3D_DtN
     return down(boundary_data, pde_problem.S_lst, pde_problem.g_tilde_lst, pde_problem.Y, pde_problem.v,
                 device=compute_device, host_device=host_device)
+
+
+def _up_then_down_pass(pde_problem: PDEProblem, boundary_data, source, compute_device, host_device):
+    """Upward pass for the new source, then the ordinary downward pass (reference `_solve.py:115-151`)."""
+    from . import _lib
+    from .up_pass import up_pass_uniform_2D_DtN, up_pass_uniform_2D_ItI
+
+    dev = _lib.require_cuda(compute_device)
+    if pde_problem.use_ItI:
+        up, down = up_pass_uniform_2D_ItI, down_pass_uniform_2D_ItI
+    else:
+        up, down = up_pass_uniform_2D_DtN, down_pass_uniform_2D_DtN
+    v, g_tilde_lst = up(source, pde_problem, device=dev, host_device=dev)
+    return down(boundary_data, pde_problem.S_lst, g_tilde_lst, pde_problem.Y, v, device=dev, host_device=host_device)

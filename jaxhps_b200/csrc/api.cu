@@ -187,6 +187,38 @@ int hps_merge_quad_iti_level(void* stream, int n_merges, int m, int n_src, const
   return merge_quad_iti_level(static_cast<cudaStream_t>(stream), n_merges, m, n_src, R_in, h_in, S, g_tilde, R_out, h_out,
                               want_T, ws, ws_bytes, info);
 }
+int hps_merge_quad_dtn_level_nosource(void* stream, int n_merges, int m, const double* T_in, double* S, double* T_out,
+                                      double* D_inv, double* BD_inv, double* scratch, void* ws, size_t ws_bytes,
+                                      int* info) {
+  // scratch: n_merges * (16m + 12m) doubles; its first 16m-per-merge part must be zero (children's h)
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HPS_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (size_t)n_merges * 16 * m, st));
+  return merge_quad_level_nosource(st, n_merges, m, T_in, S, T_out, D_inv, BD_inv, scratch,
+                                   scratch + (int64_t)n_merges * 16 * m, ws, ws_bytes, info);
+}
+int hps_merge_quad_iti_level_nosource(void* stream, int n_merges, int m, const double* R_in, double* S, double* R_out,
+                                      double* D_inv, double* BD_inv, double* scratch, void* ws, size_t ws_bytes,
+                                      int* info) {
+  // scratch (complex): n_merges * (16m + 8m + 8m) complex numbers = 64 m doubles per merge
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HPS_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (size_t)n_merges * 32 * m, st));
+  double* gt = scratch + (int64_t)n_merges * 32 * m;
+  double* h_out = gt + (int64_t)n_merges * 16 * m;
+  return merge_quad_iti_level(st, n_merges, m, 1, R_in, scratch, S, gt, R_out, h_out, 1, ws, ws_bytes, info, D_inv, BD_inv);
+}
+int hps_up_gather_quad(void* stream, int n_nodes, int m, int n_src, const double* h_in, double* h_int, double* h_ext,
+                       int ext_shift) {
+  return up_gather_quad(static_cast<cudaStream_t>(stream), n_nodes, m, n_src, 0, h_in, h_int, h_ext, ext_shift);
+}
+int hps_up_gather_quad_iti(void* stream, int n_nodes, int m, int n_src, const double* h_in, double* h_int,
+                           double* h_ext, int ext_shift, const int* pos8) {
+  return up_gather_quad_iti(static_cast<cudaStream_t>(stream), n_nodes, m, n_src, h_in, h_int, h_ext, ext_shift, pos8);
+}
+int hps_zgemm_strided_batched(void* stream, int M, int N, int K, double alpha, const double* A, int64_t lda, int64_t sA,
+                              const double* B, int64_t sB, double beta, double* C, int64_t ldc, int64_t sC, int batch,
+                              void* ws) {
+  return zgemm(static_cast<cudaStream_t>(stream), M, N, K, alpha, A, lda, sA, B, sB, beta, C, ldc, sC, batch, ws);
+}
 int hps_down_quad_iti_level(void* stream, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
                             const double* g_tilde, double* g_children, void* ws) {
   return down_quad_iti_level(static_cast<cudaStream_t>(stream), n_nodes, m, n_src, S, g_ext, g_tilde, g_children, ws);

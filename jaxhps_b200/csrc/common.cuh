@@ -106,7 +106,16 @@ int local_solve_iti(cudaStream_t st, int n_leaves, int p, int q, int n_src, cons
 size_t merge_quad_iti_ws_bytes(int n_merges, int m, int n_src);
 int merge_quad_iti_level(cudaStream_t st, int n_merges, int m, int n_src, const double* R_in, const double* h_in,
                          double* S, double* gt, double* R_out, double* h_out, int want_T, void* ws, size_t ws_bytes,
-                         int* info);
+                         int* info, double* D_inv = nullptr, double* BD_inv = nullptr);
+int merge_quad_level_nosource(cudaStream_t st, int n_merges, int m, const double* T_in, double* S, double* T_out,
+                              double* D_inv, double* BD_inv, double* h_zero, double* scratch_h, void* ws,
+                              size_t ws_bytes, int* info);
+int up_gather_quad(cudaStream_t st, int n_nodes, int m, int n_src, int is_complex, const double* h_in, double* h_int,
+                   double* h_ext, int ext_shift);
+int up_gather_quad_iti(cudaStream_t st, int n_nodes, int m, int n_src, const double* h_in, double* h_int, double* h_ext,
+                       int ext_shift, const int* pos8);
+int zgemm(cudaStream_t st, int M, int N, int K, double alpha, const double* A, int64_t lda, int64_t sA, const double* B,
+          int64_t sB, double beta, double* C, int64_t ldc, int64_t sC, int batch, void* ws);
 int down_quad_iti_level(cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
                         const double* gt, double* g_children, void* ws);
 int leaf_apply_complex(cudaStream_t st, int n_leaves, int n_c, int n_g, int n_src, const double* Y, const double* g,

@@ -263,12 +263,13 @@ __global__ void stacked_to_complex_kernel(int rows, int cols, const double* __re
 
 // interleaved complex X (rows x cols) -> expanded real X2 (2 rows x 2 cols)
 __global__ void complex_expand_kernel(int rows, int cols, const double2* __restrict__ X, int64_t sX,
-                                      double* __restrict__ X2, int64_t sX2) {
+                                      double* __restrict__ X2, int64_t sX2, double alpha) {
   const int64_t b = blockIdx.y;
   const int64_t total = (int64_t)rows * cols;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = e / cols, c = e - r * cols;
-    const double2 z = X[b * sX + e];
+    double2 z = X[b * sX + e];
+    z.x *= alpha; z.y *= alpha;
     double* x2 = X2 + b * sX2;
     x2[(2 * r) * 2 * cols + 2 * c] = z.x;
     x2[(2 * r) * 2 * cols + 2 * c + 1] = z.y;
@@ -287,13 +288,24 @@ int stacked_to_complex(cudaStream_t st, int batch, int rows, int cols, const dou
   return 0;
 }
 
-int complex_expand(cudaStream_t st, int batch, int rows, int cols, const double* X, int64_t sX, double* X2, int64_t sX2) {
+int complex_expand(cudaStream_t st, int batch, int rows, int cols, const double* X, int64_t sX, double* X2, int64_t sX2,
+                   double alpha) {
   const int64_t total = (int64_t)rows * cols;
   if (total <= 0 || batch <= 0) return 0;
   dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, 4096), batch);
-  complex_expand_kernel<<<grid, 256, 0, st>>>(rows, cols, reinterpret_cast<const double2*>(X), sX, X2, sX2);
+  complex_expand_kernel<<<grid, 256, 0, st>>>(rows, cols, reinterpret_cast<const double2*>(X), sX, X2, sX2, alpha);
   HPS_LAUNCH_CHECK("complex_expand_kernel");
   return 0;
+}
+
+// C[b] = alpha * A[b] * B[b] + beta * C[b], complex128 interleaved, alpha/beta real.  B must be
+// contiguous (K x N); lda/ldc in complex elements.  ws: batch * 4 K N doubles.
+int zgemm(cudaStream_t st, int M, int N, int K, double alpha, const double* A, int64_t lda, int64_t sA, const double* B,
+          int64_t sB, double beta, double* C, int64_t ldc, int64_t sC, int batch, void* ws) {
+  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return 0;
+  double* B2 = static_cast<double*>(ws);
+  HPS_TRY(complex_expand(st, batch, K, N, B, sB, B2, (int64_t)4 * K * N, alpha));
+  return dgemm(st, M, 2 * N, 2 * K, 1.0, A, 2 * lda, 2 * sA, B2, 2 * N, (int64_t)4 * K * N, beta, C, 2 * ldc, 2 * sC, batch);
 }
 
 size_t local_solve_iti_workspace_bytes(int n_leaves, int p, int q, int n_src) {

@@ -223,6 +223,57 @@ __global__ void __launch_bounds__(256) down_scatter_kernel(Topo tp, int m, int n
   }
 }
 
+// X[b] (rows x cols, leading dim cols) = [I ; 0]: identity in the first `cols` rows
+__global__ void set_identity_kernel(double* X, int rows, int cols, int64_t stride) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / cols, c = e - r * cols;
+    X[(int64_t)blockIdx.y * stride + e] = (r == c) ? 1.0 : 0.0;
+  }
+}
+int set_identity(cudaStream_t st, int batch, double* X, int rows, int cols, int64_t stride) {
+  const int64_t total = (int64_t)rows * cols;
+  set_identity_kernel<<<dim3((unsigned)std::min<int64_t>((total + 255) / 256, 2048), batch), 256, 0, st>>>(X, rows, cols, stride);
+  HPS_LAUNCH_CHECK("set_identity_kernel");
+  return 0;
+}
+
+// Up pass gather (reference up_pass/_uniform_2D_DtN.py:110-173): from the children's outgoing data h
+// build h_int (sum of the two children sharing each interface) and h_ext.  ext_shift rotates the
+// exterior panels (1 = the reference's pre-roll order).  E = double or double2.
+template <typename E>
+__device__ __forceinline__ E add_e(E a, E b);
+template <>
+__device__ __forceinline__ double add_e<double>(double a, double b) { return a + b; }
+template <>
+__device__ __forceinline__ double2 add_e<double2>(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+
+template <typename E>
+__global__ void up_gather_dtn_kernel(Topo tp, int m, int n_src, const E* __restrict__ h_in, E* __restrict__ h_int,
+                                     E* __restrict__ h_ext, int ext_shift) {
+  const int node = blockIdx.y;
+  const int nf = tp.n_face * m, n_int = tp.n_slot * m, n_ext = tp.n_ext * m;
+  const E* hm = h_in + (int64_t)node * tp.n_child * nf * n_src;
+  const int64_t total = (int64_t)(n_int + n_ext) * n_src;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e % n_src);
+    const int r = (int)(e / n_src);
+    if (r < n_int) {
+      const int s = r / m, t = r - s * m;
+      const int cA = tp.slot_owner[s][0], cB = tp.slot_owner[s][1];
+      const E a = hm[((int64_t)cA * nf + face_index(tp, cA, tp.slot_face[cA][s], t, m)) * n_src + k];
+      const E b = hm[((int64_t)cB * nf + face_index(tp, cB, tp.slot_face[cB][s], t, m)) * n_src + k];
+      h_int[((int64_t)node * n_int + r) * n_src + k] = add_e<E>(a, b);
+    } else {
+      const int re = r - n_int;
+      const int ep = re / m, u = re - ep * m;
+      const int pos = (ep + ext_shift) % tp.n_ext;
+      const int c = tp.ext_child[ep], f = tp.ext_face[ep];
+      h_ext[((int64_t)node * n_ext + pos * m + u) * n_src + k] = hm[((int64_t)c * nf + f * m + u) * n_src + k];
+    }
+  }
+}
+
 size_t merge_ws_bytes(const Topo& tp, int n_merges, int m) {
   const size_t n_int = (size_t)tp.n_slot * m;
   return align_up((size_t)n_merges * n_int * n_int * sizeof(double), 256) +
@@ -232,7 +283,7 @@ size_t merge_ws_bytes(const Topo& tp, int n_merges, int m) {
 
 int merge_level(const Topo& tp, cudaStream_t st, int n_merges, int m, int n_src, const double* T_in,
                 const double* h_in, double* S, double* gt, double* T_out, double* h_out, int want_T, void* ws,
-                size_t ws_bytes, int* info) {
+                size_t ws_bytes, int* info, double* D_inv = nullptr, double* BD_inv = nullptr) {
   if (n_merges <= 0 || m <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
   if (n_merges > 65535) return fail_arg(2, "n_merges per call is limited to 65535");
   const int n_int = tp.n_slot * m, n_ext = tp.n_ext * m;
@@ -249,10 +300,11 @@ int merge_level(const Topo& tp, cudaStream_t st, int n_merges, int m, int n_src,
     merge_gather_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, D, S, gt, 0, n_ext);
     HPS_LAUNCH_CHECK("merge_gather_kernel");
   }
-  const int64_t sS = (int64_t)n_int * n_ext, sG = (int64_t)n_int * n_src;
-  RhsDesc rhs[2] = {{S, n_ext, sS, n_ext}, {gt, n_src, sG, n_src}};
-  HPS_TRY(lu_solve(st, n_merges, n_int, D, n_int, (int64_t)n_int * n_int, 2, rhs, lu_ws, lu_ws_bytes, info));
-  if (!want_T) return 0;
+  const int64_t sS = (int64_t)n_int * n_ext, sG = (int64_t)n_int * n_src, sDi = (int64_t)n_int * n_int;
+  RhsDesc rhs[3] = {{S, n_ext, sS, n_ext}, {gt, n_src, sG, n_src}, {D_inv, n_int, sDi, n_int}};
+  if (D_inv) HPS_TRY(set_identity(st, n_merges, D_inv, n_int, n_int, sDi));  // third right-hand side: D^-1 itself
+  HPS_TRY(lu_solve(st, n_merges, n_int, D, n_int, sDi, D_inv ? 3 : 2, rhs, lu_ws, lu_ws_bytes, info));
+  if (!want_T && !BD_inv) return 0;
 
   {
     const int cols = n_ext + tp.n_intf * m + n_src;
@@ -272,6 +324,10 @@ int merge_level(const Topo& tp, cudaStream_t st, int n_merges, int m, int n_src,
       // h_out[panel e rows] += B_block * g~[slot s rows]
       HPS_TRY(dgemm(st, m, n_src, m, 1.0, Ablk, m, sB, gt + (int64_t)s * m * n_src, n_src, sG, 1.0,
                     h_out + (int64_t)e * m * n_src, n_src, sH, n_merges));
+      // (B D^-1)[panel e rows] (+)= B_block * D^-1[slot s rows]   (no-source build)
+      if (BD_inv)
+        HPS_TRY(dgemm(st, m, n_int, m, 1.0, Ablk, m, sB, D_inv + (int64_t)s * m * n_int, n_int, sDi, j == 0 ? 0.0 : 1.0,
+                      BD_inv + (int64_t)e * m * n_int, n_int, (int64_t)n_ext * n_int, n_merges));
     }
   return 0;
 }
@@ -375,11 +431,40 @@ __global__ void __launch_bounds__(256) iti_gather_kernel(ItiTopo tp, int m, int 
   }
 }
 
+struct IntPos { int pos[8]; };
+
+// Up pass gather for ItI (reference up_pass/_uniform_2D_ItI.py:139-219): the equation of unknown u is
+// driven by the OTHER child's outgoing data; block u is written at position pos[u] of h_int.
+__global__ void up_gather_iti_kernel(ItiTopo tp, int m, int n_src, const double2* __restrict__ h_in,
+                                     double2* __restrict__ h_int, double2* __restrict__ h_ext, int ext_shift, IntPos ip) {
+  const int node = blockIdx.y;
+  const int nf = 4 * m, n = 8 * m;
+  const double2* hm = h_in + (int64_t)node * 4 * nf * n_src;
+  const int64_t total = (int64_t)2 * n * n_src;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e % n_src);
+    const int r = (int)(e / n_src);
+    if (r < n) {
+      const int u = r / m, t = r - u * m;
+      const int Y = tp.unk_other[u], fY = tp.unk_other_face[u];
+      h_int[((int64_t)node * n + ip.pos[u] * m + t) * n_src + k] =
+          hm[((int64_t)Y * nf + face_index(tp.base, Y, fY, t, m)) * n_src + k];
+    } else {
+      const int re = r - n;
+      const int ep = re / m, uu = re - ep * m;
+      const int pos = (ep + ext_shift) % 8;
+      const int c = tp.base.ext_child[ep], f = tp.base.ext_face[ep];
+      h_ext[((int64_t)node * n + pos * m + uu) * n_src + k] = hm[((int64_t)c * nf + f * m + uu) * n_src + k];
+    }
+  }
+}
+
 size_t merge_iti_ws_bytes_impl(int n_merges, int m, int n_src) {
   const size_t n = 8 * (size_t)m;
   return align_up((size_t)n_merges * 4 * n * n * 8, 256) + align_up((size_t)n_merges * 2 * n * n * 8, 256) +
          align_up((size_t)n_merges * 2 * n * n_src * 8, 256) + align_up((size_t)n_merges * 4 * n * n * 8, 256) +
          align_up((size_t)n_merges * 4 * n * n_src * 8, 256) + align_up((size_t)n_merges * 8 * 2 * m * m * 16, 256) +
+         align_up((size_t)n_merges * 2 * n * n * 8, 256) + align_up((size_t)n_merges * 4 * n * n * 8, 256) +
          lu_workspace_bytes(n_merges, (int)(2 * n)) + 1024;
 }
 
@@ -427,7 +512,8 @@ int down_oct_scatter(cudaStream_t st, int n_nodes, int m, int n_src, const doubl
 // helpers defined in leaf.cu
 int stacked_to_complex(cudaStream_t st, int batch, int rows, int cols, const double* Xs, int64_t sXs, double* X,
                        int64_t sX, double* X2, int64_t sX2);
-int complex_expand(cudaStream_t st, int batch, int rows, int cols, const double* X, int64_t sX, double* X2, int64_t sX2);
+int complex_expand(cudaStream_t st, int batch, int rows, int cols, const double* X, int64_t sX, double* X2, int64_t sX2,
+                   double alpha = 1.0);
 
 size_t merge_quad_iti_ws_bytes(int n_merges, int m, int n_src) { return merge_iti_ws_bytes_impl(n_merges, m, n_src); }
 
@@ -435,7 +521,7 @@ size_t merge_quad_iti_ws_bytes(int n_merges, int m, int n_src) { return merge_it
 // all complex128 stored interleaved.
 int merge_quad_iti_level(cudaStream_t st, int n_merges, int m, int n_src, const double* R_in, const double* h_in,
                          double* S, double* gt, double* R_out, double* h_out, int want_T, void* ws, size_t ws_bytes,
-                         int* info) {
+                         int* info, double* D_inv, double* BD_inv) {
   if (n_merges <= 0 || m <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
   if (n_merges > 65535) return fail_arg(2, "n_merges per call is limited to 65535");
   const ItiTopo& tp = iti_topo();
@@ -447,7 +533,9 @@ int merge_quad_iti_level(cudaStream_t st, int n_merges, int m, int n_src, const 
   double* S2 = ar.take<double>((size_t)n_merges * n2 * n2);
   double* g2 = ar.take<double>((size_t)n_merges * n2 * 2 * n_src);
   double* Bg = ar.take<double>((size_t)n_merges * 8 * 2 * m * m * 2);
-  if (!De || !Cs || !gs || !S2 || !g2 || !Bg) return fail_arg(13, "merge_iti: workspace too small");
+  double* Dis = ar.take<double>((size_t)n_merges * n2 * n);   // stacked D^-1 (no-source build)
+  double* Di2 = ar.take<double>((size_t)n_merges * n2 * n2);  // its expanded form
+  if (!De || !Cs || !gs || !S2 || !g2 || !Bg || !Dis || !Di2) return fail_arg(13, "merge_iti: workspace too small");
   void* lu_ws = ar.base + ar.off;
   const size_t lu_ws_bytes = ar.cap - ar.off;
   {
@@ -457,12 +545,14 @@ int merge_quad_iti_level(cudaStream_t st, int n_merges, int m, int n_src, const 
                                             reinterpret_cast<const double2*>(h_in), De, Cs, gs);
     HPS_LAUNCH_CHECK("iti_gather_kernel");
   }
-  RhsDesc rhs[2] = {{Cs, n, (int64_t)n2 * n, n}, {gs, n_src, (int64_t)n2 * n_src, n_src}};
-  HPS_TRY(lu_solve(st, n_merges, n2, De, n2, (int64_t)n2 * n2, 2, rhs, lu_ws, lu_ws_bytes, info));
+  RhsDesc rhs[3] = {{Cs, n, (int64_t)n2 * n, n}, {gs, n_src, (int64_t)n2 * n_src, n_src}, {Dis, n, (int64_t)n2 * n, n}};
+  if (D_inv) HPS_TRY(set_identity(st, n_merges, Dis, n2, n, (int64_t)n2 * n));  // stacked [I ; 0]
+  HPS_TRY(lu_solve(st, n_merges, n2, De, n2, (int64_t)n2 * n2, D_inv ? 3 : 2, rhs, lu_ws, lu_ws_bytes, info));
+  if (D_inv) HPS_TRY(stacked_to_complex(st, n_merges, n, n, Dis, (int64_t)n2 * n, D_inv, (int64_t)n * n, Di2, (int64_t)n2 * n2));
   HPS_TRY(stacked_to_complex(st, n_merges, n, n, Cs, (int64_t)n2 * n, S, (int64_t)n * n, S2, (int64_t)n2 * n2));
   HPS_TRY(stacked_to_complex(st, n_merges, n, n_src, gs, (int64_t)n2 * n_src, gt, (int64_t)n * n_src, g2,
                              (int64_t)n2 * 2 * n_src));
-  if (!want_T) return 0;
+  if (!want_T && !BD_inv) return 0;
   {
     const int cols = n + 2 * m + n_src;
     dim3 grid(std::min((cols + 255) / 256, 64), n, n_merges);
@@ -482,7 +572,23 @@ int merge_quad_iti_level(cudaStream_t st, int n_merges, int m, int n_src, const 
                     R_out + (int64_t)e * m * n2, n2, sR, n_merges));
       HPS_TRY(dgemm(st, m, 2 * n_src, 2 * m, 1.0, Ablk, 2 * m, sB, g2 + (int64_t)2 * slot * m * 2 * n_src, 2 * n_src, sg2,
                     1.0, h_out + (int64_t)e * m * 2 * n_src, 2 * n_src, sH, n_merges));
+      if (BD_inv)
+        HPS_TRY(dgemm(st, m, 2 * n, 2 * m, 1.0, Ablk, 2 * m, sB, Di2 + (int64_t)2 * slot * m * n2, n2, sS2,
+                      j == 0 ? 0.0 : 1.0, BD_inv + (int64_t)e * m * n2, n2, sR, n_merges));
     }
+  return 0;
+}
+
+int up_gather_quad_iti(cudaStream_t st, int n_nodes, int m, int n_src, const double* h_in, double* h_int, double* h_ext,
+                       int ext_shift, const int* pos8) {
+  if (n_nodes <= 0 || m <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
+  IntPos ip;
+  for (int u = 0; u < 8; ++u) ip.pos[u] = pos8 ? pos8[u] : u;
+  const int64_t total = (int64_t)16 * m * n_src;
+  dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, 1024), n_nodes);
+  up_gather_iti_kernel<<<grid, 256, 0, st>>>(iti_topo(), m, n_src, reinterpret_cast<const double2*>(h_in),
+                                             reinterpret_cast<double2*>(h_int), reinterpret_cast<double2*>(h_ext), ext_shift, ip);
+  HPS_LAUNCH_CHECK("up_gather_iti_kernel");
   return 0;
 }
 
@@ -524,6 +630,30 @@ int merge_quad_level(cudaStream_t st, int n_merges, int m, int n_src, const doub
                      int* info) {
   return merge_level(quad_topo(), st, n_merges, m, n_src, T_in, h_in, S, gt, T_out, h_out, want_T, ws, ws_bytes, info);
 }
+int merge_quad_level_nosource(cudaStream_t st, int n_merges, int m, const double* T_in, double* S, double* T_out,
+                              double* D_inv, double* BD_inv, double* h_zero, double* scratch_h, void* ws,
+                              size_t ws_bytes, int* info) {
+  // h_zero: n_merges*4*4m zeros (children's h), scratch_h: n_merges*(4m + 8m) doubles for g~/h_out (discarded)
+  const int n_int = 4 * m;
+  return merge_level(quad_topo(), st, n_merges, m, 1, T_in, h_zero, S, scratch_h, T_out,
+                     scratch_h + (int64_t)n_merges * n_int, 1, ws, ws_bytes, info, D_inv, BD_inv);
+}
+
+int up_gather_quad(cudaStream_t st, int n_nodes, int m, int n_src, int is_complex, const double* h_in, double* h_int,
+                   double* h_ext, int ext_shift) {
+  if (n_nodes <= 0 || m <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
+  const Topo& tp = quad_topo();
+  const int64_t total = (int64_t)(12 * m) * n_src;
+  dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, 1024), n_nodes);
+  if (is_complex)
+    up_gather_dtn_kernel<double2><<<grid, 256, 0, st>>>(tp, m, n_src, reinterpret_cast<const double2*>(h_in),
+                                                       reinterpret_cast<double2*>(h_int), reinterpret_cast<double2*>(h_ext), ext_shift);
+  else
+    up_gather_dtn_kernel<double><<<grid, 256, 0, st>>>(tp, m, n_src, h_in, h_int, h_ext, ext_shift);
+  HPS_LAUNCH_CHECK("up_gather_dtn_kernel");
+  return 0;
+}
+
 int down_oct_level(cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
                    const double* gt, double* g_children, void* ws) {
   return down_level(oct_topo(), st, n_nodes, m, n_src, S, g_ext, gt, g_children, ws);

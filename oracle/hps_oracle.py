@@ -364,7 +364,7 @@ def _side_idx(side: int, m: int, flipped: bool) -> np.ndarray:
     return idx[::-1] if flipped else idx
 
 
-def uniform_quad_merge_DtN(T_children: np.ndarray, h_children: np.ndarray):
+def uniform_quad_merge_DtN(T_children: np.ndarray, h_children: np.ndarray, return_ops: bool = False):
     """One quad merge with dense B, C, D and explicit ``inv(D)``
     (`merge/_uniform_2D_DtN.py:206-348`); exterior unknowns come out in boundary order, which
     is what the reference's ``roll(-n_int)`` achieves.  T_children (4, 4m, 4m)."""
@@ -398,6 +398,8 @@ def uniform_quad_merge_DtN(T_children: np.ndarray, h_children: np.ndarray):
     D_inv = np.linalg.inv(D)
     T, S, h_out, g_tilde = assemble_merge_outputs(A_lst, B, C, D_inv, h_ext, h_int)
     T = np.roll(np.roll(T, -m, axis=0), -m, axis=1)
+    if return_ops:  # the no-source build keeps D^-1 and B D^-1 (`_schur_complement.py:240-290`)
+        return np.roll(S, -m, axis=1), T, D_inv, B @ D_inv
     return np.roll(S, -m, axis=1), T, np.roll(h_out, -m, axis=0), g_tilde
 
 
@@ -471,7 +473,7 @@ def invert_D_ItI(D_12: np.ndarray, D_21: np.ndarray) -> np.ndarray:
     return out
 
 
-def uniform_quad_merge_ItI(R_children: np.ndarray, h_children: np.ndarray):
+def uniform_quad_merge_ItI(R_children: np.ndarray, h_children: np.ndarray, return_ops: bool = False):
     """One ItI quad merge.  R_children (4, 4m, 4m) complex; h_children (4, 4m, n_src).
     Returns (S, R, h_out, g_tilde) with S (8m, 8m), g_tilde (8m, n_src)."""
     m = R_children.shape[-1] // 4
@@ -513,6 +515,8 @@ def uniform_quad_merge_ItI(R_children: np.ndarray, h_children: np.ndarray):
     S = np.roll(S, -m, axis=1)
     h_out = np.roll(h_out, -m, axis=0)
     r = np.concatenate([np.arange(pos[key] * m, (pos[key] + 1) * m) for key in _ITI_OUT_ORDER])
+    if return_ops:  # D^-1 and B D^-1 stay in the solve order / pre-roll rows (`_nosource_uniform_2D_ItI.py:293-322`)
+        return S[r], T, D_inv, B @ D_inv
     return S[r], T, h_out, g_tilde[r]
 
 
@@ -568,3 +572,137 @@ def down_pass_uniform_2D_ItI(boundary_data, S_lst, g_tilde_lst, Y_arr, v_arr):
     if bdry.ndim == 3:
         return np.einsum("ijk,ikl->ijl", Y_arr, bdry) + v_arr
     return np.einsum("ijk,ik->ij", Y_arr, bdry) + v_arr
+
+
+# =====================================================================================
+# Source given at solve time (2D uniform): no-source build + upward pass.
+# Reference: local_solve/_nosource_uniform_2D_{DtN,ItI}.py, merge/_nosource_uniform_2D_{DtN,ItI}.py,
+# up_pass/_uniform_2D_{DtN,ItI}.py, _build_solver.py:261-331, _solve.py:115-151.
+# =====================================================================================
+
+
+def nosource_local_solve_stage_uniform_2D_DtN(pde_problem):
+    """(Y, T, Phi) with Phi = A_ii^-1, shape (n, n_i, n_i) (`_nosource_uniform_2D_DtN.py:76-123`)."""
+    coeffs, which = gather_coeffs(pde_problem, _COEFF_ORDER_2D)
+    ops = _leaf_operators(pde_problem, _COEFF_ORDER_2D)
+    nb = pde_problem.P.shape[0]
+    Ys, Ts, Phis = [], [], []
+    for leaf in range(coeffs.shape[1]):
+        A = assemble_diff_operator(coeffs[:, leaf], which, ops)
+        Y, T, _, _ = get_DtN(np.zeros((A.shape[0], 1)), A, pde_problem.Q, pde_problem.P)
+        Ys.append(Y), Ts.append(T), Phis.append(np.linalg.inv(A[nb:, nb:]))
+    return np.stack(Ys), np.stack(Ts), np.stack(Phis)
+
+
+def nosource_local_solve_stage_uniform_2D_ItI(pde_problem):
+    """(Y, R, Phi) with Phi = B^-1[:, n_b:], shape (n, p^2, n_i) (`_nosource_uniform_2D_ItI.py:80-146`)."""
+    coeffs, which = gather_coeffs(pde_problem, _COEFF_ORDER_2D)
+    ops = _leaf_operators(pde_problem, _COEFF_ORDER_2D)
+    nb = pde_problem.P.shape[0]
+    Ys, Rs, Phis = [], [], []
+    for leaf in range(coeffs.shape[1]):
+        A = assemble_diff_operator(coeffs[:, leaf], which, ops)
+        B_inv = np.linalg.inv(np.concatenate([pde_problem.G, A[nb:].astype(np.complex128)], axis=0))
+        Y = B_inv[:, :nb] @ pde_problem.P
+        Ys.append(Y), Rs.append(pde_problem.QH @ Y), Phis.append(B_inv[:, nb:])
+    return np.stack(Ys), np.stack(Rs), np.stack(Phis)
+
+
+def _nosource_merge_stage(T_arr, l, merge_fn, return_T):
+    S_lst, D_inv_lst, BD_inv_lst = [], [], []
+    h_dummy = np.zeros(T_arr.shape[:2] + (1,), dtype=T_arr.dtype)
+    for _ in range(l):
+        n = T_arr.shape[0] // 4
+        outs = [merge_fn(T_arr[4 * i : 4 * i + 4], h_dummy[4 * i : 4 * i + 4], return_ops=True) for i in range(n)]
+        S_lst.append(np.stack([o[0] for o in outs]))
+        T_arr = np.stack([o[1] for o in outs])
+        D_inv_lst.append(np.stack([o[2] for o in outs]))
+        BD_inv_lst.append(np.stack([o[3] for o in outs]))
+        h_dummy = np.zeros(T_arr.shape[:2] + (1,), dtype=T_arr.dtype)
+    if return_T:
+        return S_lst, D_inv_lst, BD_inv_lst, T_arr[0]
+    return S_lst, D_inv_lst, BD_inv_lst
+
+
+def nosource_merge_stage_uniform_2D_DtN(T_arr, l: int, return_T: bool = False):
+    """(S_lst, D_inv_lst, BD_inv_lst[, T_last]) (`merge/_nosource_uniform_2D_DtN.py:13-130`)."""
+    return _nosource_merge_stage(T_arr, l, uniform_quad_merge_DtN, return_T)
+
+
+def nosource_merge_stage_uniform_2D_ItI(T_arr, l: int, return_T: bool = False):
+    """(`merge/_nosource_uniform_2D_ItI.py:19-150`)."""
+    return _nosource_merge_stage(T_arr, l, uniform_quad_merge_ItI, return_T)
+
+
+def _children_h_parts(h4: np.ndarray, m: int):
+    """Exterior (pre-roll order) and per-(child, interface) pieces of four children's h."""
+    pre = [(0, 3), (0, 0), (1, 0), (1, 1), (2, 1), (2, 2), (3, 2), (3, 3)]
+    ext = np.concatenate([h4[c][_side_idx(s, m, False)] for c, s in pre])
+    part = {}
+    for c in range(4):
+        for s in range(4):
+            kind, k, flipped = _QUAD_ROLES[c][s]
+            if kind == "int":
+                part[(c, k)] = h4[c][_side_idx(s, m, flipped)]
+    return ext, part
+
+
+def up_pass_uniform_2D_DtN(source, pde_problem, return_h_last: bool = False):
+    """v = [0; Phi f_i], h = Q v, then per level g~ = -D^-1 h_int, h = roll(h_ext - B D^-1 h_int)
+    (`up_pass/_uniform_2D_DtN.py:8-173`).  Outputs keep the source axis (the reference does not
+    squeeze in the DtN up pass)."""
+    src = np.asarray(source)
+    if src.ndim == 2:
+        src = src[..., None]
+    nb = pde_problem.P.shape[0]
+    v = np.zeros_like(src)
+    v[:, nb:] = np.einsum("ijk,ikl->ijl", pde_problem.Phi, src[:, nb:])
+    h = np.einsum("ij,kjl->kil", pde_problem.Q, v)
+    g_lst = []
+    for D_inv, BD_inv in zip(pde_problem.D_inv_lst, pde_problem.BD_inv_lst):
+        m = h.shape[1] // 4
+        new_h, g = [], []
+        for i in range(h.shape[0] // 4):
+            ext, part = _children_h_parts(h[4 * i : 4 * i + 4], m)
+            h_int = np.concatenate([part[(a, s)] + part[(b, s)] for s, (a, b) in enumerate(_QUAD_INTERFACES)])
+            g.append(-1 * D_inv[i] @ h_int)
+            new_h.append(np.roll(ext - BD_inv[i] @ h_int, -m, axis=0))
+        h = np.stack(new_h)
+        g_lst.append(np.stack(g))
+    if return_h_last:
+        return v, g_lst, h[0]
+    return v, g_lst
+
+
+def up_pass_uniform_2D_ItI(source, pde_problem, return_h_last: bool = False):
+    """(`up_pass/_uniform_2D_ItI.py:8-219`): h_int lists the OTHER child's outgoing data in the solve
+    order, g~ is returned in the out order; single-source outputs are squeezed."""
+    src = np.asarray(source)
+    multi = src.ndim == 3
+    if not multi:
+        src = src[..., None]
+    nb = pde_problem.P.shape[0]
+    v = np.einsum("ijk,ikl->ijl", pde_problem.Phi, src[:, nb:])
+    h = np.einsum("ij,kjl->kil", pde_problem.QH, v)
+    pos = {key: i for i, key in enumerate(_ITI_SOLVE_ORDER)}
+    g_lst = []
+    for D_inv, BD_inv in zip(pde_problem.D_inv_lst, pde_problem.BD_inv_lst):
+        m = h.shape[1] // 4
+        r = np.concatenate([np.arange(pos[key] * m, (pos[key] + 1) * m) for key in _ITI_OUT_ORDER])
+        new_h, g = [], []
+        for i in range(h.shape[0] // 4):
+            ext, part = _children_h_parts(h[4 * i : 4 * i + 4], m)
+            rows = []
+            for (c, s) in _ITI_SOLVE_ORDER:
+                other = [y for y in _QUAD_INTERFACES[s] if y != c][0]
+                rows.append(part[(other, s)])
+            h_int = np.concatenate(rows)
+            g.append((-1 * D_inv[i] @ h_int)[r])
+            new_h.append(np.roll(ext - BD_inv[i] @ h_int, -m, axis=0))
+        h = np.stack(new_h)
+        g_lst.append(np.stack(g))
+    if not multi:
+        v, g_lst, h = v[..., 0], [g[..., 0] for g in g_lst], h[..., 0]
+    if return_h_last:
+        return v, g_lst, h[0]
+    return v, g_lst

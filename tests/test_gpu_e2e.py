@@ -121,3 +121,43 @@ def test_helmholtz_ItI_plane_wave_2D():
     assert np.abs(uo - exact).max() < 1e-8
     assert np.abs(u - exact).max() < 1e-8
     assert np.abs(u - uo).max() < 1e-9
+
+
+@pytest.mark.parametrize("iti,p,q,L,nsrc", [(False, 6, 4, 2, 1), (False, 8, 6, 3, 2), (True, 6, 4, 2, 1), (True, 8, 6, 3, 2)])
+def test_source_at_solve_time_matches_oracle(iti, p, q, L, nsrc):
+    """No-source build + up pass + down pass (reference `_build_solver.py:261-331`, `_solve.py:115-151`)
+    against the oracle, including the stored D^-1 / B D^-1 in the reference's layout."""
+    rng = np.random.default_rng(5)
+    k = 4.0
+    dom = hps.Domain(p, q, hps.DiscretizationNode2D(-1.0, 1.0, -1.0, 1.0), L)
+    shp = dom.interior_points[..., 0].shape
+    co = {"D_xx_coefficients": np.ones(shp), "D_yy_coefficients": np.ones(shp),
+          "I_coefficients": k**2 * (1 + 0.3 * rng.normal(size=shp))}
+    extra = dict(use_ItI=True, eta=k) if iti else {}
+    pb = hps.PDEProblem(dom, **co, **extra)
+    ref_pb = hps.PDEProblem(dom, **co, **extra)
+    T_top = hps.build_solver(pb, return_top_T=True)
+    if iti:
+        Y, T, Phi = orc.nosource_local_solve_stage_uniform_2D_ItI(ref_pb)
+        S, Di, BDi, Tt = orc.nosource_merge_stage_uniform_2D_ItI(T, L, return_T=True)
+        up, dn = orc.up_pass_uniform_2D_ItI, orc.down_pass_uniform_2D_ItI
+    else:
+        Y, T, Phi = orc.nosource_local_solve_stage_uniform_2D_DtN(ref_pb)
+        S, Di, BDi, Tt = orc.nosource_merge_stage_uniform_2D_DtN(T, L, return_T=True)
+        up, dn = orc.up_pass_uniform_2D_DtN, orc.down_pass_uniform_2D_DtN
+    ref_pb.Y, ref_pb.Phi, ref_pb.S_lst, ref_pb.D_inv_lst, ref_pb.BD_inv_lst = Y, Phi, S, Di, BDi
+    rel = lambda a, b: np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max()  # noqa: E731
+    tol = 1e-9
+    assert rel(pb.Y, Y) < tol and rel(pb.Phi, Phi) < tol and rel(T_top, Tt) < tol
+    for a, b in zip(pb.S_lst + pb.D_inv_lst + pb.BD_inv_lst, S + Di + BDi):
+        assert np.asarray(a).shape == b.shape and rel(a, b) < tol
+    sshape = shp if nsrc == 1 else shp + (nsrc,)
+    nb = dom.boundary_points.shape[0]
+    bshape = (nb,) if nsrc == 1 else (nb, nsrc)
+    src = rng.normal(size=sshape) + (1j * rng.normal(size=sshape) if iti else 0)
+    g = rng.normal(size=bshape) + (1j * rng.normal(size=bshape) if iti else 0)
+    g_in = g[..., None] if (not iti and nsrc == 1) else g  # the reference's DtN up pass keeps the source axis
+    u = hps.solve(pb, g_in, source=src)
+    v, gl = up(src, ref_pb)
+    uo = dn(g_in, S, gl, Y, v)
+    assert u.shape == uo.shape and rel(u, uo) < tol
