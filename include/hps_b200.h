@@ -37,10 +37,13 @@ const char* hps_last_error_string(void);
 
 /* Optional device-side timing of the two dominant kernels (CUDA events on the launching
  * stream), used by bench.py for the roofline numbers.  hps_prof_enable(1) resets and starts
- * recording, hps_prof_read synchronises `stream` and returns, per category (0 = DMMA GEMM:
- * work in flops; 1 = LU panel kernel: work in panel entries), the summed launch time in ms,
- * the summed work and the launch count, plus the number of kernel launches of any kind
- * the library issued since the reset.  ms/work/launches: HOST arrays of length 2. */
+ * recording, hps_prof_read synchronises `stream` and returns, per category, the summed launch
+ * time in ms, the summed work and the launch count, plus the number of kernel launches of any kind
+ * the library issued since the reset.  Categories: 0 DMMA GEMM (work = flops), 1 LU panel,
+ * 2 triangular-block inversion, 3 row interchanges, 4 inner 32x32 solves, 5 merge gather/scatter
+ * (work = bytes written), 6 narrow-N mat-vec kernel (bytes read), 7 leaf assembly (bytes written).
+ * ms/work/launches: HOST arrays of length HPS_PROF_NCAT = 8. */
+#define HPS_PROF_NCAT 8
 int hps_prof_enable(int on);
 int hps_prof_read(void* stream, double* ms, double* work, int64_t* launches, int64_t* all_launches);
 
@@ -100,6 +103,23 @@ int hps_merge_oct_dtn_level(void* stream, int n_merges, int m, int n_src,
 int hps_merge_oct_dtn_root_cols(void* stream, int m, int n_src, const double* T_in, const double* h_in,
                                 int ext0, int ncols, double* S_cols, double* g_tilde,
                                 void* ws, size_t ws_bytes, int* info);
+
+/* Multi-GPU root merge sharded BY CHILD (what jaxhps_b200/_dist.py uses).  Columns of the root S that
+ * belong to child X's exterior faces depend on T_X only, so each rank keeps its own C block and only
+ * the children's interface blocks travel:
+ *   hps_root_pack_oct: for the n_local subtree roots held by this rank (children child0.. of the root
+ *     merge; T [n_local][6m][6m], h [n_local][6m][n_src]) extract Dblk [n_local][3m][3m] =
+ *     T[int,int], Cblk [n_local][3m][3m] = T[int,ext], hblk [n_local][3m][n_src] (interior faces in
+ *     ascending interface order, exterior faces in ascending face order);
+ *   (all-gather Dblk and hblk over the ranks -> [8][3m][3m], [8][3m][n_src]);
+ *   hps_root_solve_oct: assemble D (12m x 12m) from the 8 Dblk, solve for this rank's columns:
+ *     S_r [12m][3m*n_local] (child-major, faces ascending) and g_tilde [12m][n_src]. */
+int hps_root_pack_oct(void* stream, int n_local, int child0, int m, int n_src,
+                      const double* T, const double* h, double* Dblk, double* Cblk, double* hblk);
+int hps_root_solve_oct_workspace(int m, size_t* bytes);
+int hps_root_solve_oct(void* stream, int m, int n_src, int child0, int n_local,
+                       const double* Dblk_all, const double* hblk_all, const double* Cblk_loc,
+                       double* S_r, double* g_tilde, void* ws, size_t ws_bytes, int* info);
 
 /* 2D quad merge, DtN (reference: merge/_uniform_2D_DtN.py:206-348).
  * T_in [4*n_merges][4m][4m] (children SW,SE,NE,NW; sides S,E,N,W), S [n][4m][8m],

@@ -9,9 +9,11 @@ boundary data flows back down the same way.  This module runs that scheme in par
   contiguous leaf range because leaves are stored in depth-first sibling order
   (`_grid_creation_3D.py:20-21`); it runs the local solves and every merge below the root with no
   communication and keeps its ``Y, v, S, g_tilde`` resident;
-* up: one all-gather of the subtree-root ``(T, h)`` (NCCL over NVLink);
-* the root merge is column-sharded: every rank factors the root ``D`` (replicated LU) and solves
-  only its ``24m/world`` columns of ``S``;
+* up: one all-gather of the subtree roots' interface blocks (NCCL over NVLink);
+* the root merge is column-sharded BY CHILD: the columns of the root ``S`` that belong to child X's
+  exterior faces depend on ``T_X`` only, so only the children's interface blocks ``T_X[int,int]``
+  (a quarter of ``T_X``) are all-gathered; every rank factors the root ``D`` (replicated LU) and
+  solves the columns of its own children;
 * down: each rank multiplies its column block of ``S`` with its slice of the boundary data, one
   all-reduce of the 12m-vector of interface values, then every rank continues down its own
   subtrees with no further communication.
@@ -28,6 +30,23 @@ import torch
 import torch.distributed as dist
 
 from ._pdeproblem import _COEFF_NAMES, PDEProblem
+
+
+# exterior faces of the root's children a..h (ascending) and, per parent face, the four children
+# in panel order (reference `merge/_uniform_3D_DtN.py:238-380, 507-541`)
+_CHILD_EXT_FACES = [(0, 2, 5), (1, 2, 5), (1, 3, 5), (0, 3, 5), (0, 2, 4), (1, 2, 4), (1, 3, 4), (0, 3, 4)]
+_FACE_CHILDREN = [(4, 7, 3, 0), (5, 6, 2, 1), (4, 5, 1, 0), (7, 6, 2, 3), (4, 5, 6, 7), (0, 1, 2, 3)]
+
+
+def child_column_index(first_child: int, n_children: int, m: int) -> np.ndarray:
+    """Positions, inside the root's face-ordered boundary vector (24 panels of m), of the exterior
+    unknowns of the given children — child-major, faces ascending: the column order of ``S_r``."""
+    idx = []
+    for c in range(first_child, first_child + n_children):
+        for f in _CHILD_EXT_FACES[c]:
+            panel = 4 * f + _FACE_CHILDREN[f].index(c)
+            idx.append(np.arange(panel * m, (panel + 1) * m))
+    return np.concatenate(idx)
 
 
 class SubtreePlan:
@@ -47,13 +66,6 @@ class SubtreePlan:
         self.n_local_leaves = self.octants_per_rank * self.leaves_per_octant
         self.leaf_slice = slice(self.first_octant * self.leaves_per_octant,
                                 (self.first_octant + self.octants_per_rank) * self.leaves_per_octant)
-
-    def column_window(self, n_ext: int):
-        """This rank's share of the root's exterior unknowns (columns of the root ``S``)."""
-        per = n_ext // self.world
-        if per * self.world != n_ext:
-            raise ValueError("root boundary size must divide by the number of ranks")
-        return self.rank * per, per
 
 
 def local_problem(domain, plan: SubtreePlan, source, **coeffs) -> PDEProblem:
@@ -111,13 +123,52 @@ class CudaOps:
 
         return merge_subtrees_3D_DtN(T, h, levels, n_roots, device=self.dev)
 
-    def root_columns(self, T8, h8, col0: int, ncols: int):
-        from .merge import merge_root_columns_3D_DtN
+    def root_pack(self, T_roots, h_roots, first_child: int):
+        """(Dblk, Cblk, hblk) of this rank's subtree roots (``hps_root_pack_oct``)."""
+        lib = self._lib.load()
+        n_local, n6, _ = T_roots.shape
+        m = n6 // 6
+        h3 = h_roots.reshape(n_local, n6, -1).contiguous()
+        n_src = h3.shape[-1]
+        Dblk = self.empty((n_local, 3 * m, 3 * m))
+        Cblk = self.empty((n_local, 3 * m, 3 * m))
+        hblk = self.empty((n_local, 3 * m, n_src))
+        rc = lib.hps_root_pack_oct(self._lib.stream_ptr(), n_local, first_child, m, n_src, T_roots.data_ptr(),
+                                   h3.data_ptr(), Dblk.data_ptr(), Cblk.data_ptr(), hblk.data_ptr())
+        self._lib.check(rc, "hps_root_pack_oct")
+        return Dblk, Cblk, hblk
 
-        return merge_root_columns_3D_DtN(T8, h8, col0, ncols, device=self.dev)
+    def root_solve(self, Dblk_all, hblk_all, Cblk_loc, first_child: int):
+        """This rank's columns of the root S (child-major) and the full g~ (``hps_root_solve_oct``)."""
+        import ctypes
+
+        lib = self._lib.load()
+        n_local, n3, _ = Cblk_loc.shape
+        m = n3 // 3
+        n_src = hblk_all.shape[-1]
+        S_r = self.empty((12 * m, n3 * n_local))
+        g = self.empty((12 * m, n_src))
+        info = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        need = ctypes.c_size_t()
+        self._lib.check(lib.hps_root_solve_oct_workspace(m, ctypes.byref(need)), "workspace query")
+        ws = self._lib.WORKSPACE.get(need.value, self.dev)
+        rc = lib.hps_root_solve_oct(self._lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),
+                                    hblk_all.data_ptr(), Cblk_loc.data_ptr(), S_r.data_ptr(), g.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), info.data_ptr())
+        self._lib.check(rc, "hps_root_solve_oct")
+        self._lib.check_info(info, "root merge")
+        return S_r, g
 
     def matvec(self, S_cols, g_slice):
-        return S_cols @ g_slice
+        """``S_cols @ g_slice`` with the library's bandwidth kernel (narrow N) / DMMA GEMM."""
+        lib = self._lib.load()
+        M, K = S_cols.shape
+        N = g_slice.shape[1]
+        out = self.empty((M, N))
+        rc = lib.hps_dgemm_strided_batched(self._lib.stream_ptr(), M, N, K, 1.0, S_cols.data_ptr(), K, 0,
+                                           g_slice.data_ptr(), N, 0, 0.0, out.data_ptr(), N, 0, 1)
+        self._lib.check(rc, "hps_dgemm_strided_batched (root matvec)")
+        return out
 
     def root_scatter(self, g_ext, g_int):
         """(24m, n_src), (12m, n_src) -> (8, 6m, n_src)."""
@@ -146,9 +197,9 @@ class ShardedState:
         self.Y = self.v = None
         self.S_lst: List = []
         self.g_tilde_lst: List = []
-        self.S_root_cols = None  # (12m, 24m/world)
-        self.g_tilde_root = None  # (12m[, n_src])
-        self.col0 = self.ncols = 0
+        self.S_root_cols = None  # (12m, 3m * octants_per_rank): columns of this rank's children
+        self.g_tilde_root = None  # (12m, n_src)
+        self.col_index = None  # where those columns sit in the root's boundary vector
 
 
 def _group_ok(plan: SubtreePlan) -> bool:
@@ -167,20 +218,27 @@ def build_solver_sharded(pde_problem: PDEProblem, plan: SubtreePlan, device=None
         st.S_lst, st.g_tilde_lst, T_roots, h_roots = ops.merge_subtrees(T, h, plan.L - 1, n_oct)
     else:
         T_roots, h_roots = T, h
-    # ---- up: gather the 8 subtree-root operators on every rank ----
+    # ---- up: only the children's interface blocks travel (a quarter of each subtree-root T) ----
+    multi = h_roots.ndim == 3
+    Dblk, Cblk, hblk = ops.root_pack(T_roots, h_roots, plan.first_octant)
+    m = T_roots.shape[-1] // 6
+    del T_roots, h_roots
     if plan.world > 1:
         if not _group_ok(plan):
             raise RuntimeError("torch.distributed must be initialised for world > 1")
-        T8 = ops.empty((8,) + tuple(T_roots.shape[1:]))
-        h8 = ops.empty((8,) + tuple(h_roots.shape[1:]))
-        dist.all_gather_into_tensor(T8, T_roots.contiguous(), group=group)
-        dist.all_gather_into_tensor(h8, h_roots.contiguous(), group=group)
+        D_all = ops.empty((8,) + tuple(Dblk.shape[1:]))
+        h_all = ops.empty((8,) + tuple(hblk.shape[1:]))
+        dist.all_gather_into_tensor(D_all, Dblk.contiguous(), group=group)
+        dist.all_gather_into_tensor(h_all, hblk.contiguous(), group=group)
     else:
-        T8, h8 = T_roots, h_roots
-    del T_roots, h_roots
-    n_ext = 4 * T8.shape[-1]  # 24 m
-    st.col0, st.ncols = plan.column_window(n_ext)
-    st.S_root_cols, st.g_tilde_root = ops.root_columns(T8, h8, st.col0, st.ncols)
+        D_all, h_all = Dblk, hblk
+    del Dblk
+    if D_all.numel() * 8 > (4 << 30) and D_all.is_cuda:
+        torch.cuda.empty_cache()  # the root D needs one large block; give freed subtree buffers back first
+    st.S_root_cols, g = ops.root_solve(D_all, h_all, Cblk, plan.first_octant)
+    st.g_tilde_root = g
+    st.multi = multi
+    st.col_index = ops.tensor(child_column_index(plan.first_octant, n_oct, m)).to(torch.int64)
     return st
 
 
@@ -194,7 +252,7 @@ def solve_sharded(pde_problem: PDEProblem, st: ShardedState, plan: SubtreePlan, 
     g_ext = g.reshape(g.shape[0], -1)
     gt = st.g_tilde_root.reshape(st.g_tilde_root.shape[0], -1)
     # ---- root level: partial product on this rank's columns, all-reduce, add g~ ----
-    part = ops.matvec(st.S_root_cols, g_ext[st.col0 : st.col0 + st.ncols].contiguous())
+    part = ops.matvec(st.S_root_cols, g_ext.index_select(0, st.col_index).contiguous())
     if plan.world > 1:
         dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
     g_int = part + gt

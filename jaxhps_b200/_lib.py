@@ -37,6 +37,9 @@ _SIGNATURES = {
     "hps_merge_oct_dtn_level_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),
     "hps_merge_oct_dtn_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "hps_merge_oct_dtn_root_cols": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p, _sz, _p]),
+    "hps_root_pack_oct": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "hps_root_solve_oct_workspace": (_i, [_i, ctypes.POINTER(_sz)]),
+    "hps_root_solve_oct": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "hps_down_oct_scatter": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "hps_merge_quad_dtn_level_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),
     "hps_merge_quad_dtn_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),

@@ -27,7 +27,7 @@ struct ProfState {
   size_t used = 0;
   struct Rec { int cat; size_t e0, e1; double work; };
   std::vector<Rec> recs;
-  size_t open_rec[PROF_NCAT] = {0, 0};
+  size_t open_rec[PROF_NCAT] = {};
   cudaEvent_t take() {
     if (used == pool.size()) {
       cudaEvent_t e;
@@ -137,6 +137,21 @@ int hps_merge_oct_dtn_root_cols(void* stream, int m, int n_src, const double* T_
                                 int ncols, double* S_cols, double* g_tilde, void* ws, size_t ws_bytes, int* info) {
   return merge_oct_root_cols(static_cast<cudaStream_t>(stream), m, n_src, T_in, h_in, ext0, ncols, S_cols, g_tilde, ws,
                              ws_bytes, info);
+}
+int hps_root_pack_oct(void* stream, int n_local, int child0, int m, int n_src, const double* T, const double* h,
+                      double* Dblk, double* Cblk, double* hblk) {
+  return root_pack_oct(static_cast<cudaStream_t>(stream), n_local, child0, m, n_src, T, h, Dblk, Cblk, hblk);
+}
+int hps_root_solve_oct_workspace(int m, size_t* bytes) {
+  if (!bytes) return fail_arg(2, "null output pointer");
+  *bytes = root_solve_oct_ws_bytes(m);
+  return 0;
+}
+int hps_root_solve_oct(void* stream, int m, int n_src, int child0, int n_local, const double* Dblk_all,
+                       const double* hblk_all, const double* Cblk_loc, double* S_r, double* g_tilde, void* ws,
+                       size_t ws_bytes, int* info) {
+  return root_solve_oct(static_cast<cudaStream_t>(stream), m, n_src, child0, n_local, Dblk_all, hblk_all, Cblk_loc, S_r,
+                        g_tilde, ws, ws_bytes, info);
 }
 int hps_down_oct_scatter(void* stream, int n_nodes, int m, int n_src, const double* g_ext, const double* g_int,
                          double* g_children) {

@@ -29,7 +29,8 @@ extern long long g_launches;
 
 // Optional per-category device timing (CUDA events on the launching stream), used by bench.py
 // for the roofline of the dominant kernels.  Off by default: zero overhead on the product path.
-enum ProfCat { PROF_GEMM = 0, PROF_PANEL = 1, PROF_NCAT = 2 };
+enum ProfCat { PROF_GEMM = 0, PROF_PANEL = 1, PROF_TRTRI = 2, PROF_LASWP = 3, PROF_INNER = 4, PROF_GATHER = 5,
+               PROF_SKINNY = 6, PROF_ASSEMBLE = 7, PROF_NCAT = 8 };
 void prof_begin(int cat, cudaStream_t st, double work);
 void prof_end(int cat, cudaStream_t st);
 
@@ -95,6 +96,12 @@ int merge_oct_level(cudaStream_t st, int n_merges, int m, int n_src, const doubl
 int merge_quad_level(cudaStream_t st, int n_merges, int m, int n_src, const double* T_in, const double* h_in,
                      double* S, double* gt, double* T_out, double* h_out, int want_T, void* ws, size_t ws_bytes,
                      int* info);
+int root_pack_oct(cudaStream_t st, int n_local, int child0, int m, int n_src, const double* T, const double* h,
+                  double* Dblk, double* Cblk, double* hblk);
+size_t root_solve_oct_ws_bytes(int m);
+int root_solve_oct(cudaStream_t st, int m, int n_src, int child0, int n_local, const double* Dblk_all,
+                   const double* hblk_all, const double* Cblk_loc, double* S_r, double* gt, void* ws, size_t ws_bytes,
+                   int* info);
 int merge_oct_root_cols(cudaStream_t st, int m, int n_src, const double* T_in, const double* h_in, int ext0, int ncols,
                         double* S_cols, double* gt, void* ws, size_t ws_bytes, int* info);
 int down_oct_scatter(cudaStream_t st, int n_nodes, int m, int n_src, const double* g_ext, const double* g_int,

@@ -74,6 +74,7 @@ int dgemm_skinny(cudaStream_t st, int M, int N, int K, double alpha, const doubl
                  int64_t ldcin, int64_t sCin, double* C, int64_t ldc, int64_t sC, int batch) {
   if (M <= 0 || N <= 0 || batch <= 0) return 0;
   const int wpb = 8;
+  prof_begin(PROF_SKINNY, st, 8.0 * M * (double)K * batch);
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = min(65535, batch - b0);
     dim3 grid((M + wpb - 1) / wpb, nb);
@@ -83,6 +84,7 @@ int dgemm_skinny(cudaStream_t st, int M, int N, int K, double alpha, const doubl
                                                   C + b0 * sC, ldc, sC, n0);
     }
   }
+  prof_end(PROF_SKINNY, st);
   HPS_LAUNCH_CHECK("skinny_kernel");
   return 0;
 }

@@ -401,8 +401,10 @@ int local_solve_dtn(cudaStream_t st, int dim, int n_leaves, int p, int q, int n_
   {
     const int64_t total = (int64_t)geo.n_i * geo.n_c;
     const int bx = (int)std::min<int64_t>((total + 255) / 256, 4096);
+    prof_begin(PROF_ASSEMBLE, st, 8.0 * n_leaves * (double)total);
     if (dim == 3) assemble_kernel<3><<<dim3(bx, n_leaves), 256, 0, st>>>(aa);
     else assemble_kernel<2><<<dim3(bx, n_leaves), 256, 0, st>>>(aa);
+    prof_end(PROF_ASSEMBLE, st);
     HPS_LAUNCH_CHECK("assemble_kernel");
     const int64_t tot2 = (int64_t)geo.n_b * n_g + (int64_t)geo.n_c * n_src;
     leaf_init_kernel<<<dim3((int)std::min<int64_t>((tot2 + 255) / 256, 2048), n_leaves), 256, 0, st>>>(

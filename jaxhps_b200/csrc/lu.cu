@@ -37,7 +37,7 @@ constexpr int IB = 32;           // inner panel width
 constexpr int PANEL_ROWS = 768;  // rows of the panel one CTA keeps in shared memory
 constexpr int PANEL_LD = IB + 1;
 constexpr int PANEL_THREADS = 512;
-constexpr int MAX_G = 64;
+constexpr int MAX_G = 128;
 
 struct Cand {          // one CTA's pivot candidate for the current column
   double val;          // |a|, negative when the CTA has no eligible row
@@ -377,7 +377,7 @@ int launch_panel_impl(cudaStream_t st, int batch, PanelArgs pa) {
     ++g_launches;
     return 0;
   }
-  if (G > MAX_G) return fail_arg(3, "matrix too tall for the panel kernel (n > 49152)");
+  if (G > MAX_G) return fail_arg(3, "matrix too tall for the panel kernel (n > 98304)");
   pa.G = G;
   if (g_coop_capacity < 0) {
     int dev = 0, sms = 0, per_sm = 0;
@@ -409,7 +409,9 @@ int launch_panel_impl(cudaStream_t st, int batch, PanelArgs pa) {
 int laswp(cudaStream_t st, int batch, double* A, int64_t lda, int64_t sA, int c0, int ncols, const int* ipiv, int n,
           int k0, int k1) {
   if (ncols <= 0 || k1 <= k0) return 0;
+  prof_begin(PROF_LASWP, st, (double)batch * ncols * (k1 - k0));
   laswp_kernel<<<dim3((ncols + 255) / 256, batch), 256, 0, st>>>(A, lda, sA, c0, ncols, ipiv, n, k0, k1);
+  prof_end(PROF_LASWP, st);
   HPS_LAUNCH_CHECK("laswp_kernel");
   return 0;
 }
@@ -475,7 +477,9 @@ int factor_block_column(cudaStream_t st, int batch, int n, const Mat& A, int j, 
     const int right = j + jb - (jj + ib);
     if (right > 0) {
       HPS_TRY(laswp(st, batch, A.p, A.ld, A.stride, jj + ib, right, w.ipiv, n, jj, jj + ib));
+      prof_begin(PROF_INNER, st, (double)batch * right * ib * ib);
       inner_trsm_kernel<<<dim3((right + 127) / 128, batch), 128, 0, st>>>(A.p, A.ld, A.stride, jj, ib, jj + ib, right);
+      prof_end(PROF_INNER, st);
       HPS_LAUNCH_CHECK("inner_trsm_kernel");
       const int below = n - (jj + ib);
       if (below > 0)
@@ -484,7 +488,9 @@ int factor_block_column(cudaStream_t st, int batch, int n, const Mat& A, int j, 
     }
   }
   const int nblk = (n + NB - 1) / NB;
+  prof_begin(PROF_TRTRI, st, (double)batch * NB * NB * NB / 3);
   trtri_kernel<true><<<dim3(1, batch), NB, TRTRI_SMEM, st>>>(A.p, A.ld, A.stride, j, n, w.Linv, (int64_t)nblk * NB * NB);
+  prof_end(PROF_TRTRI, st);
   HPS_LAUNCH_CHECK("trtri_kernel<lower>");
   return 0;
 }
@@ -599,7 +605,9 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
   if (n_rhs == 0) return 0;
 
   // ---- 2. inverses of U's diagonal blocks (all at once), interchanges on the right-hand sides --
+  prof_begin(PROF_TRTRI, s0, (double)batch * nblk * NB * NB * NB / 3);
   trtri_kernel<false><<<dim3(nblk, batch), NB, TRTRI_SMEM, s0>>>(A.p, A.ld, A.stride, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
+  prof_end(PROF_TRTRI, s0);
   HPS_LAUNCH_CHECK("trtri_kernel<upper>");
   for (int k = 0; k < n_rhs; ++k) {
     HPS_TRY(laswp(s0, batch, rhs[k].ptr, rhs[k].ld, rhs[k].stride, 0, rhs[k].ncols, w.ipiv, n, 0, n));

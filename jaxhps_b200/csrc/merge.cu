@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(256) merge_gather_kernel(Topo tp, int m, int n
                                                            double* __restrict__ S, double* __restrict__ gt, int ext0,
                                                            int n_ext) {
   const int n_int = tp.n_slot * m, nf = tp.n_face * m;
-  const int row = blockIdx.y, mg = blockIdx.z;
+  const int mg = blockIdx.z;
+  for (int row = blockIdx.y; row < n_int; row += gridDim.y) {
   const int s1 = row / m, t1 = row - s1 * m;
   const int64_t child_sz = (int64_t)nf * nf;
   const double* Tm = T_in + (int64_t)mg * tp.n_child * child_sz;
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(256) merge_gather_kernel(Topo tp, int m, int n
       gt[((int64_t)mg * n_int + row) * n_src + k] = -v;
     }
   }
+  }
 }
 
 // ---- exterior part: T_out := A scattered (zero elsewhere), h_out := h_ext, and the non-zero
@@ -173,7 +175,8 @@ __global__ void __launch_bounds__(256) merge_ext_kernel(Topo tp, int m, int n_sr
                                                         const E* __restrict__ h_in, E* __restrict__ T_out,
                                                         E* __restrict__ h_out, E* __restrict__ Bg) {
   const int n_ext = tp.n_ext * m, nf = tp.n_face * m;
-  const int row = blockIdx.y, mg = blockIdx.z;
+  const int mg = blockIdx.z;
+  for (int row = blockIdx.y; row < n_ext; row += gridDim.y) {
   const int e1 = row / m, u1 = row - e1 * m;
   const int c = tp.ext_child[e1], f1 = tp.ext_face[e1];
   const int64_t child_sz = (int64_t)nf * nf;
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(256) merge_ext_kernel(Topo tp, int m, int n_sr
       h_out[((int64_t)mg * n_ext + row) * n_src + k] =
           h_in[(((int64_t)mg * tp.n_child + c) * nf + f1 * m + u1) * n_src + k];
     }
+  }
   }
 }
 
@@ -296,8 +300,10 @@ int merge_level(const Topo& tp, cudaStream_t st, int n_merges, int m, int n_src,
 
   {
     const int cols = n_int + n_ext + n_src;
-    dim3 grid(std::min((cols + 255) / 256, 64), n_int, n_merges);
+    dim3 grid(std::min((cols + 255) / 256, 64), std::min(n_int, 65535), n_merges);
+    prof_begin(PROF_GATHER, st, 8.0 * n_merges * (double)n_int * (n_int + n_ext));
     merge_gather_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, D, S, gt, 0, n_ext);
+    prof_end(PROF_GATHER, st);
     HPS_LAUNCH_CHECK("merge_gather_kernel");
   }
   const int64_t sS = (int64_t)n_int * n_ext, sG = (int64_t)n_int * n_src, sDi = (int64_t)n_int * n_int;
@@ -308,8 +314,10 @@ int merge_level(const Topo& tp, cudaStream_t st, int n_merges, int m, int n_src,
 
   {
     const int cols = n_ext + tp.n_intf * m + n_src;
-    dim3 grid(std::min((cols + 255) / 256, 64), n_ext, n_merges);
+    dim3 grid(std::min((cols + 255) / 256, 64), std::min(n_ext, 65535), n_merges);
+    prof_begin(PROF_GATHER, st, 8.0 * n_merges * (double)n_ext * n_ext);
     merge_ext_kernel<double><<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, T_out, h_out, Bg);
+    prof_end(PROF_GATHER, st);
     HPS_LAUNCH_CHECK("merge_ext_kernel");
   }
   const int64_t sT = (int64_t)n_ext * n_ext, sH = (int64_t)n_ext * n_src;
@@ -468,6 +476,89 @@ size_t merge_iti_ws_bytes_impl(int n_merges, int m, int n_src) {
          lu_workspace_bytes(n_merges, (int)(2 * n)) + 1024;
 }
 
+
+// ---- multi-GPU root merge sharded by child ------------------------------------------------------
+// pack: for each local subtree root c (child index child0 + c of the root merge) extract
+//   Dblk[c] = T_c[int faces, int faces] (3m x 3m), Cblk[c] = T_c[int faces, ext faces] (3m x 3m),
+//   hblk[c] = h_c[int faces]; interior faces in ascending interface-slot order of that child,
+//   exterior faces in ascending face order.
+__global__ void __launch_bounds__(256) root_pack_kernel(Topo tp, int m, int n_src, int child0, const double* __restrict__ T,
+                                                        const double* __restrict__ h, double* __restrict__ Dblk,
+                                                        double* __restrict__ Cblk, double* __restrict__ hblk) {
+  const int c_loc = blockIdx.z, c = child0 + c_loc;
+  const int nf = 6 * m, n3 = 3 * m;
+  int int_face[3], ext_face[3], ni = 0, ne = 0;
+  // slots ascending: ext_slot of any exterior panel of this child lists them in face order; sort by slot
+  for (int f = 0; f < 6; ++f) {
+    if (tp.role[c][f] >= 0) int_face[ni++] = f; else ext_face[ne++] = f;
+  }
+  for (int a = 0; a < 3; ++a)
+    for (int b = a + 1; b < 3; ++b)
+      if (tp.role[c][int_face[b]] < tp.role[c][int_face[a]]) { const int t = int_face[a]; int_face[a] = int_face[b]; int_face[b] = t; }
+  const double* Tc = T + (int64_t)c_loc * nf * nf;
+  for (int row = blockIdx.y; row < n3; row += gridDim.y) {
+    const int i = row / m, t1 = row - i * m;
+    const double* trow = Tc + (int64_t)(int_face[i] * m + t1) * nf;
+    for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < 2 * n3 + n_src; col += gridDim.x * blockDim.x) {
+      if (col < n3) {
+        const int j = col / m, t2 = col - j * m;
+        Dblk[((int64_t)c_loc * n3 + row) * n3 + col] = trow[int_face[j] * m + t2];
+      } else if (col < 2 * n3) {
+        const int cc = col - n3;
+        const int j = cc / m, t2 = cc - j * m;
+        Cblk[((int64_t)c_loc * n3 + row) * n3 + cc] = trow[ext_face[j] * m + t2];
+      } else {
+        const int k = col - 2 * n3;
+        hblk[((int64_t)c_loc * n3 + row) * n_src + k] = h[((int64_t)c_loc * nf + int_face[i] * m + t1) * n_src + k];
+      }
+    }
+  }
+}
+
+// assemble: D (12m x 12m) from all 8 children's Dblk, C_r = -[C columns of the local children]
+// (12m x 3m*n_local), g~ := -h_int.
+__global__ void __launch_bounds__(256) root_assemble_kernel(Topo tp, int m, int n_src, int child0, int n_local,
+                                                            const double* __restrict__ Dblk_all,
+                                                            const double* __restrict__ hblk_all,
+                                                            const double* __restrict__ Cblk_loc, double* __restrict__ D,
+                                                            double* __restrict__ Cr, double* __restrict__ gt) {
+  const int n_int = 12 * m, n3 = 3 * m, ncr = n3 * n_local;
+  // local index (0..2) of slot s inside child c = number of that child's slots below s
+  auto loc = [&](int c, int s) {
+    int k = 0;
+    for (int s2 = 0; s2 < s; ++s2) k += (tp.slot_face[c][s2] >= 0);
+    return k;
+  };
+  for (int row = blockIdx.y; row < n_int; row += gridDim.y) {
+    const int s1 = row / m, t1 = row - s1 * m;
+    const int cA = tp.slot_owner[s1][0], cB = tp.slot_owner[s1][1];
+    const int iA = loc(cA, s1), iB = loc(cB, s1);
+    const double* rowA = Dblk_all + ((int64_t)cA * n3 + iA * m + t1) * n3;
+    const double* rowB = Dblk_all + ((int64_t)cB * n3 + iB * m + t1) * n3;
+    for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < n_int + ncr + n_src; col += gridDim.x * blockDim.x) {
+      if (col < n_int) {
+        const int s2 = col / m, t2 = col - s2 * m;
+        double v = 0.0;
+        if (tp.slot_face[cA][s2] >= 0) v += rowA[loc(cA, s2) * m + t2];
+        if (tp.slot_face[cB][s2] >= 0) v += rowB[loc(cB, s2) * m + t2];
+        D[(int64_t)row * n_int + col] = v;
+      } else if (col < n_int + ncr) {
+        const int cc = col - n_int;
+        const int cl = cc / n3, rest = cc - cl * n3;
+        const int c = child0 + cl;
+        double v = 0.0;
+        if (c == cA) v = Cblk_loc[((int64_t)cl * n3 + iA * m + t1) * n3 + rest];
+        else if (c == cB) v = Cblk_loc[((int64_t)cl * n3 + iB * m + t1) * n3 + rest];
+        Cr[(int64_t)row * ncr + cc] = -v;
+      } else {
+        const int k = col - n_int - ncr;
+        gt[(int64_t)row * n_src + k] = -(hblk_all[((int64_t)cA * n3 + iA * m + t1) * n_src + k] +
+                                         hblk_all[((int64_t)cB * n3 + iB * m + t1) * n_src + k]);
+      }
+    }
+  }
+}
+
 // Column-sharded merge for the multi-GPU root: S[:, ext0:ext0+ncols] and g~ from the children's T.
 int merge_cols(const Topo& tp, cudaStream_t st, int m, int n_src, const double* T_in, const double* h_in, int ext0,
                int ncols, double* S_cols, double* gt, void* ws, size_t ws_bytes, int* info) {
@@ -480,7 +571,7 @@ int merge_cols(const Topo& tp, cudaStream_t st, int m, int n_src, const double* 
   void* lu_ws = ar.base + ar.off;
   const size_t lu_ws_bytes = ar.cap - ar.off;
   const int cols = n_int + ncols + n_src;
-  dim3 grid(std::min((cols + 255) / 256, 64), n_int, 1);
+  dim3 grid(std::min((cols + 255) / 256, 64), std::min(n_int, 65535), 1);
   merge_gather_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, D, S_cols, gt, ext0, ncols);
   HPS_LAUNCH_CHECK("merge_gather_kernel");
   RhsDesc rhs[2] = {{S_cols, ncols, (int64_t)n_int * ncols, ncols}, {gt, n_src, (int64_t)n_int * n_src, n_src}};
@@ -498,6 +589,42 @@ int down_scatter(const Topo& tp, cudaStream_t st, int n_nodes, int m, int n_src,
 }
 
 }  // namespace
+
+
+int root_pack_oct(cudaStream_t st, int n_local, int child0, int m, int n_src, const double* T, const double* h,
+                  double* Dblk, double* Cblk, double* hblk) {
+  if (n_local <= 0 || m <= 0 || n_src <= 0 || child0 < 0 || child0 + n_local > 8) return fail_arg(2, "bad child range");
+  const int cols = 6 * m + n_src;
+  dim3 grid(std::min((cols + 255) / 256, 64), std::min(3 * m, 65535), n_local);
+  root_pack_kernel<<<grid, 256, 0, st>>>(oct_topo(), m, n_src, child0, T, h, Dblk, Cblk, hblk);
+  HPS_LAUNCH_CHECK("root_pack_kernel");
+  return 0;
+}
+
+size_t root_solve_oct_ws_bytes(int m) {
+  const size_t n_int = 12 * (size_t)m;
+  return align_up(n_int * n_int * sizeof(double), 256) + lu_workspace_bytes(1, (int)n_int) + 1024;
+}
+
+// S_r (12m x 3m*n_local) = columns of the root S belonging to the local children's exterior faces
+// (child-major, faces ascending), g~ (12m x n_src).
+int root_solve_oct(cudaStream_t st, int m, int n_src, int child0, int n_local, const double* Dblk_all,
+                   const double* hblk_all, const double* Cblk_loc, double* S_r, double* gt, void* ws, size_t ws_bytes,
+                   int* info) {
+  if (m <= 0 || n_src <= 0 || n_local <= 0 || child0 < 0 || child0 + n_local > 8) return fail_arg(2, "bad child range");
+  const int n_int = 12 * m, ncr = 3 * m * n_local;
+  Arena ar(ws, ws_bytes);
+  double* D = ar.take<double>((size_t)n_int * n_int);
+  if (!D) return fail_arg(11, "root_solve: workspace too small");
+  void* lu_ws = ar.base + ar.off;
+  const size_t lu_ws_bytes = ar.cap - ar.off;
+  const int cols = n_int + ncr + n_src;
+  dim3 grid(std::min((cols + 255) / 256, 64), std::min(n_int, 65535), 1);
+  root_assemble_kernel<<<grid, 256, 0, st>>>(oct_topo(), m, n_src, child0, n_local, Dblk_all, hblk_all, Cblk_loc, D, S_r, gt);
+  HPS_LAUNCH_CHECK("root_assemble_kernel");
+  RhsDesc rhs[2] = {{S_r, ncr, (int64_t)n_int * ncr, ncr}, {gt, n_src, (int64_t)n_int * n_src, n_src}};
+  return lu_solve(st, 1, n_int, D, n_int, (int64_t)n_int * n_int, 2, rhs, lu_ws, lu_ws_bytes, info);
+}
 
 int merge_oct_root_cols(cudaStream_t st, int m, int n_src, const double* T_in, const double* h_in, int ext0, int ncols,
                         double* S_cols, double* gt, void* ws, size_t ws_bytes, int* info) {

@@ -40,9 +40,38 @@ class OracleOps:
         assert T.shape[0] == n_roots
         return S_lst, g_lst, torch.from_numpy(T), torch.from_numpy(h)
 
-    def root_columns(self, T8, h8, col0, ncols):
-        S, _, _, g = orc.uniform_oct_merge_DtN(T8.numpy(), h8.numpy())
-        return torch.from_numpy(np.ascontiguousarray(S[:, col0 : col0 + ncols])), torch.from_numpy(g)
+    def root_pack(self, T_roots, h_roots, first_child):
+        T, h = T_roots.numpy(), h_roots.numpy().reshape(T_roots.shape[0], T_roots.shape[1], -1)
+        m = T.shape[-1] // 6
+        D, C, hb = [], [], []
+        for k in range(T.shape[0]):
+            roles = orc._OCT_ROLES[first_child + k]
+            int_faces = sorted((f for f in range(6) if roles[f][0] == "int"), key=lambda f: roles[f][1])
+            ext_faces = [f for f in range(6) if roles[f][0] == "ext"]
+            ii = np.concatenate([np.arange(f * m, (f + 1) * m) for f in int_faces])
+            ee = np.concatenate([np.arange(f * m, (f + 1) * m) for f in ext_faces])
+            D.append(T[k][np.ix_(ii, ii)]), C.append(T[k][np.ix_(ii, ee)]), hb.append(h[k][ii])
+        return tuple(torch.from_numpy(np.ascontiguousarray(np.stack(x))) for x in (D, C, hb))
+
+    def root_solve(self, Dblk_all, hblk_all, Cblk_loc, first_child):
+        Db, hb, Cb = Dblk_all.numpy(), hblk_all.numpy(), Cblk_loc.numpy()
+        m = Db.shape[-1] // 3
+        n_local = Cb.shape[0]
+        D = np.zeros((12 * m, 12 * m))
+        h_int = np.zeros((12 * m, hb.shape[-1]))
+        C = np.zeros((12 * m, 3 * m * n_local))
+        for c in range(8):
+            roles = orc._OCT_ROLES[c]
+            slots = sorted(roles[f][1] for f in range(6) if roles[f][0] == "int")
+            for i, si in enumerate(slots):
+                h_int[si * m : (si + 1) * m] += hb[c][i * m : (i + 1) * m]
+                for j, sj in enumerate(slots):
+                    D[si * m : (si + 1) * m, sj * m : (sj + 1) * m] += Db[c][i * m : (i + 1) * m, j * m : (j + 1) * m]
+                if first_child <= c < first_child + n_local:
+                    k = c - first_child
+                    C[si * m : (si + 1) * m, 3 * m * k : 3 * m * (k + 1)] = Cb[k][i * m : (i + 1) * m]
+        D_inv = np.linalg.inv(D)
+        return torch.from_numpy(-D_inv @ C), torch.from_numpy(-D_inv @ h_int)
 
     def matvec(self, S_cols, g_slice):
         return S_cols @ g_slice
@@ -117,7 +146,7 @@ def test_subtree_plan_partitions_the_leaves():
         slices = [_dist.SubtreePlan(3, r, world).leaf_slice for r in range(world)]
         covered = np.concatenate([np.arange(512)[s] for s in slices])
         assert np.array_equal(covered, np.arange(512))
-        c0, n = _dist.SubtreePlan(3, world - 1, world).column_window(38400)
-        assert c0 + n == 38400
+    cols = np.concatenate([_dist.child_column_index(c, 1, 5) for c in range(8)])
+    assert sorted(cols) == list(range(24 * 5))
     with pytest.raises(ValueError):
         _dist.SubtreePlan(3, 0, 3)

@@ -153,8 +153,10 @@ def test_sharded_driver_single_rank_matches_oracle(p, q, L, nsrc):
     else:
         ref = orc.down_pass_uniform_3D_DtN(bdry, S, g, Y, v)
     assert rel_err(u.cpu().numpy(), ref) < TOL
-    # a half-width column window reproduces the corresponding columns of S
-    from jaxhps_b200.merge import merge_root_columns_3D_DtN, merge_subtrees_3D_DtN
+    # the rank's columns of S are the root S restricted to its children's exterior unknowns
+    assert rel_err(st.S_root_cols.cpu().numpy(), S[-1][:, st.col_index.cpu().numpy()]) < TOL
+    # a half-width column window (the older equal-split entry point) still reproduces S
+    from jaxhps_b200.merge import merge_root_columns_3D_DtN
     if L == 1:
         n_ext = S[-1].shape[1]
         Sc, gt = merge_root_columns_3D_DtN(T, h, n_ext // 2, n_ext // 2, device="cuda:0")
