@@ -106,10 +106,10 @@ int hps_lu_solve(void* stream, int batch, int n, double* A, int64_t lda, int64_t
 }
 
 int hps_local_solve_dtn_workspace(int dim, int n_leaves, int p, int q, int n_src, size_t* bytes) {
-  (void)q; (void)n_src;
+  (void)n_src;
   if (!bytes) return fail_arg(6, "null output pointer");
   if (dim != 2 && dim != 3) return fail_arg(1, "dim must be 2 or 3");
-  *bytes = local_solve_workspace_bytes(dim, n_leaves, p);
+  *bytes = local_solve_workspace_bytes(dim, n_leaves, p, q);
   return 0;
 }
 

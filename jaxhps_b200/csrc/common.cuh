@@ -85,7 +85,7 @@ int lu_solve(cudaStream_t st, int batch, int n, double* A, int64_t lda, int64_t 
              const RhsDesc* rhs, void* ws, size_t ws_bytes, int* info);
 
 // ---- stages (leaf.cu / merge.cu) --------------------------------------------------------
-size_t local_solve_workspace_bytes(int dim, int n_leaves, int p);
+size_t local_solve_workspace_bytes(int dim, int n_leaves, int p, int q);
 int local_solve_dtn(cudaStream_t st, int dim, int n_leaves, int p, int q, int n_src, const uint8_t* which,
                     const double* coeffs, const double* D1, const double* P, const double* Q, const double* src,
                     double* Y, double* T, double* v, double* h, void* ws, size_t ws_bytes, int* info);

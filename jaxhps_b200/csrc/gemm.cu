@@ -20,7 +20,9 @@ constexpr int BM = Cfg::BM, BN = Cfg::BN, THREADS = Cfg::THREADS;
 constexpr size_t SMEM_BYTES = Cfg::SMEM_BYTES;
 #define gemm_kernel gemmk::gemm_kernel_mb<Cfg>
 
-// ---- narrow-N kernel: one warp per output row, lanes stride over K ------------------
+// ---- narrow-N kernels: one warp per output row, lanes stride over K -------------------------
+// These are the HBM-bound mat-vecs of the down pass (g_int = S g_ext + g~, u = Y g + v): every
+// entry of A is read exactly once, so the figure of merit is GB/s.
 template <int NMAX>
 __global__ void __launch_bounds__(256) skinny_kernel(int M, int N, int K, double alpha,
                                                      const double* __restrict__ A, int64_t lda, int64_t sA,
@@ -63,6 +65,45 @@ __global__ void __launch_bounds__(256) skinny_kernel(int M, int N, int K, double
   }
 }
 
+// N == 1 with 16-byte-aligned rows: the common single-source case.  Each lane streams double2
+// pairs with four independent loads in flight (2 KB per warp), the vector x stays in L1/L2.
+__global__ void __launch_bounds__(256) gemv_kernel(int M, int K, double alpha, const double* __restrict__ A, int64_t lda,
+                                                   int64_t sA, const double* __restrict__ x, int64_t sB, double beta,
+                                                   const double* __restrict__ Cin, int64_t ldcin, int64_t sCin,
+                                                   double* __restrict__ C, int64_t ldc, int64_t sC) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int64_t batch = blockIdx.y;
+  if (row >= M) return;
+  const double2* a = reinterpret_cast<const double2*>(A + batch * sA + (int64_t)row * lda);
+  const double2* xv = reinterpret_cast<const double2*>(x + batch * sB);
+  const int K2 = K >> 1;
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+  int k = lane;
+  for (; k + 96 < K2; k += 128) {
+    const double2 a0 = __ldcs(a + k), a1 = __ldcs(a + k + 32), a2 = __ldcs(a + k + 64), a3 = __ldcs(a + k + 96);
+    const double2 x0 = xv[k], x1 = xv[k + 32], x2 = xv[k + 64], x3 = xv[k + 96];
+    acc0 = fma(a0.x, x0.x, fma(a0.y, x0.y, acc0));
+    acc1 = fma(a1.x, x1.x, fma(a1.y, x1.y, acc1));
+    acc2 = fma(a2.x, x2.x, fma(a2.y, x2.y, acc2));
+    acc3 = fma(a3.x, x3.x, fma(a3.y, x3.y, acc3));
+  }
+  for (; k < K2; k += 32) {
+    const double2 a0 = __ldcs(a + k);
+    const double2 x0 = xv[k];
+    acc0 = fma(a0.x, x0.x, fma(a0.y, x0.y, acc0));
+  }
+  double acc = (acc0 + acc1) + (acc2 + acc3);
+  if ((K & 1) && lane == 0) acc = fma(A[batch * sA + (int64_t)row * lda + K - 1], x[batch * sB + K - 1], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    double r = alpha * acc;
+    if (beta != 0.0 && Cin) r += beta * Cin[batch * sCin + (int64_t)row * ldcin];
+    C[batch * sC + (int64_t)row * ldc] = r;
+  }
+}
+
 inline bool vec_ok(const void* p, int64_t ld, int64_t stride) {
   return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 2 == 0) && (stride % 2 == 0);
 }
@@ -75,9 +116,16 @@ int dgemm_skinny(cudaStream_t st, int M, int N, int K, double alpha, const doubl
   if (M <= 0 || N <= 0 || batch <= 0) return 0;
   const int wpb = 8;
   prof_begin(PROF_SKINNY, st, 8.0 * M * (double)K * batch);
+  const bool vec = N == 1 && ldb == 1 && (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (lda % 2 == 0) && (sA % 2 == 0) &&
+                   (reinterpret_cast<uintptr_t>(B) % 16 == 0) && (sB % 2 == 0);
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = min(65535, batch - b0);
     dim3 grid((M + wpb - 1) / wpb, nb);
+    if (vec) {
+      gemv_kernel<<<grid, wpb * 32, 0, st>>>(M, K, alpha, A + b0 * sA, lda, sA, B + b0 * sB, sB, beta,
+                                             Cin ? Cin + b0 * sCin : nullptr, ldcin, sCin, C + b0 * sC, ldc, sC);
+      continue;
+    }
     for (int n0 = 0; n0 < N; n0 += 4) {
       skinny_kernel<4><<<grid, wpb * 32, 0, st>>>(M, N, K, alpha, A + b0 * sA, lda, sA, B + b0 * sB, ldb, sB,
                                                   beta, Cin ? Cin + b0 * sCin : nullptr, ldcin, sCin,
