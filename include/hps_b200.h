@@ -121,6 +121,29 @@ int hps_root_solve_oct(void* stream, int m, int n_src, int child0, int n_local,
                        const double* Dblk_all, const double* hblk_all, const double* Cblk_loc,
                        double* S_r, double* g_tilde, void* ws, size_t ws_bytes, int* info);
 
+/* Distributed factorisation of the root D (driven step by step from jaxhps_b200/_dist.py, which
+ * issues the NCCL broadcasts in between).  Every rank holds the full n x n matrix (row-major, lda)
+ * but keeps up to date only the 128-wide block columns it owns (b % world == rank).  Per block
+ * column b: the owner calls hps_lu_dist_factor_pack (panel chain + pack of the column, its pivots and
+ * the inverse of its unit-lower diagonal block into buf, hps_lu_dist_buffer_doubles(n) doubles); buf
+ * is broadcast; the other ranks call hps_lu_dist_unpack; every rank calls hps_lu_dist_update for
+ * the block columns first_block + i*block_stride (i < n_blocks, all > b) it owns.  After the last
+ * block every rank holds the complete P A = L U and hps_lu_dist_solve solves its own right-hand sides
+ * (up to 4 matrices, n x ncols[k], in place).  One workspace for all calls: hps_lu_solve_workspace(1, n).
+ * hps_root_assemble_oct is the assembly half of hps_root_solve_oct (D, S_r := -C_r, g_tilde := -h_int). */
+int hps_root_assemble_oct(void* stream, int m, int n_src, int child0, int n_local,
+                          const double* Dblk_all, const double* hblk_all, const double* Cblk_loc,
+                          double* D, double* S_r, double* g_tilde);
+int hps_lu_dist_buffer_doubles(int n, size_t* count);
+int hps_lu_dist_factor_pack(void* stream, int n, double* A, int64_t lda, int b,
+                            void* ws, size_t ws_bytes, int* info, double* buf);
+int hps_lu_dist_unpack(void* stream, int n, double* A, int64_t lda, int b,
+                       void* ws, size_t ws_bytes, const double* buf);
+int hps_lu_dist_update(void* stream, int n, double* A, int64_t lda, int b,
+                       int first_block, int n_blocks, int block_stride, void* ws, size_t ws_bytes);
+int hps_lu_dist_solve(void* stream, int n, double* A, int64_t lda, int n_rhs, double* const* rhs,
+                      const int64_t* ld_rhs, const int* ncols, void* ws, size_t ws_bytes);
+
 /* 2D quad merge, DtN (reference: merge/_uniform_2D_DtN.py:206-348).
  * T_in [4*n_merges][4m][4m] (children SW,SE,NE,NW; sides S,E,N,W), S [n][4m][8m],
  * T_out [n][8m][8m]. */

@@ -138,14 +138,23 @@ class CudaOps:
         self._lib.check(rc, "hps_root_pack_oct")
         return Dblk, Cblk, hblk
 
-    def root_solve(self, Dblk_all, hblk_all, Cblk_loc, first_child: int):
-        """This rank's columns of the root S (child-major) and the full g~ (``hps_root_solve_oct``)."""
+    #: distribute the factorisation of the root D over the ranks when it is at least this large
+    DIST_LU_MIN_N = 32768
+    #: tests: run the step-wise (distributed) factorisation even on a single rank
+    FORCE_DIST_LU = False
+
+    def root_solve(self, Dblk_all, hblk_all, Cblk_loc, first_child: int, rank: int = 0, world: int = 1, group=None):
+        """This rank's columns of the root S (child-major) and the full g~.  Single rank or small root:
+        ``hps_root_solve_oct`` (replicated LU).  Otherwise the LU of D is distributed by block columns
+        with one NCCL broadcast per block column (``hps_lu_dist_*``)."""
         import ctypes
 
         lib = self._lib.load()
         n_local, n3, _ = Cblk_loc.shape
         m = n3 // 3
         n_src = hblk_all.shape[-1]
+        if (world > 1 or self.FORCE_DIST_LU) and 12 * m >= self.DIST_LU_MIN_N:
+            return self._root_solve_distributed(Dblk_all, hblk_all, Cblk_loc, first_child, rank, world, group)
         S_r = self.empty((12 * m, n3 * n_local))
         g = self.empty((12 * m, n_src))
         info = torch.zeros(1, dtype=torch.int32, device=self.dev)
@@ -188,6 +197,63 @@ class CudaOps:
         g_leaf = down_levels(g_roots.contiguous(), S_lst, [g.reshape(g.shape[0], g.shape[1], n_src) for g in g_lst],
                              3, self.dev)
         return leaf_apply(Y, g_leaf, v.reshape(v.shape[0], v.shape[1], n_src), self.dev)
+
+
+def _root_solve_distributed(self, Dblk_all, hblk_all, Cblk_loc, first_child, rank, world, group):
+    """Distributed LU of the root D: block column b is factored by rank b % world, broadcast, and
+    applied by every rank to the block columns it owns; then local solves of the rank's columns."""
+    import ctypes
+
+    lib = self._lib.load()
+    _lib = self._lib
+    n_local, n3, _ = Cblk_loc.shape
+    m = n3 // 3
+    n_src = hblk_all.shape[-1]
+    n = 12 * m
+    NB = 128
+    nblk = (n + NB - 1) // NB
+    D = self.empty((n, n))
+    S_r = self.empty((n, n3 * n_local))
+    g = self.empty((n, n_src))
+    rc = lib.hps_root_assemble_oct(_lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),
+                                   hblk_all.data_ptr(), Cblk_loc.data_ptr(), D.data_ptr(), S_r.data_ptr(), g.data_ptr())
+    _lib.check(rc, "hps_root_assemble_oct")
+    need = ctypes.c_size_t()
+    _lib.check(lib.hps_lu_solve_workspace(1, n, ctypes.byref(need)), "workspace query")
+    ws = _lib.WORKSPACE.get(need.value, self.dev)
+    cnt = ctypes.c_size_t()
+    _lib.check(lib.hps_lu_dist_buffer_doubles(n, ctypes.byref(cnt)), "buffer query")
+    bufs = [self.empty((cnt.value,)), self.empty((cnt.value,))]
+    info = torch.zeros(1, dtype=torch.int32, device=self.dev)
+    st = _lib.stream_ptr()
+    for b in range(nblk):
+        owner = b % world
+        buf = bufs[b & 1]
+        if rank == owner:
+            _lib.check(lib.hps_lu_dist_factor_pack(st, n, D.data_ptr(), n, b, ws.data_ptr(), ws.numel(), info.data_ptr(),
+                                                   buf.data_ptr()), "hps_lu_dist_factor_pack")
+        if world > 1:
+            dist.broadcast(buf, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+        if rank != owner:
+            _lib.check(lib.hps_lu_dist_unpack(st, n, D.data_ptr(), n, b, ws.data_ptr(), ws.numel(), buf.data_ptr()),
+                       "hps_lu_dist_unpack")
+        # block columns > b owned by this rank: rank, rank + world, ...
+        first = b + 1 + ((rank - (b + 1)) % world)
+        n_own = 0 if first >= nblk else (nblk - 1 - first) // world + 1
+        _lib.check(lib.hps_lu_dist_update(st, n, D.data_ptr(), n, b, first, n_own, world, ws.data_ptr(), ws.numel()),
+                   "hps_lu_dist_update")
+    if world > 1:
+        dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
+    _lib.check_info(info, "distributed root factorisation")
+    ptrs = (ctypes.c_void_p * 2)(S_r.data_ptr(), g.data_ptr())
+    lds = (ctypes.c_int64 * 2)(S_r.shape[1], n_src)
+    ncs = (ctypes.c_int * 2)(S_r.shape[1], n_src)
+    _lib.check(lib.hps_lu_dist_solve(st, n, D.data_ptr(), n, 2, ptrs, lds, ncs, ws.data_ptr(), ws.numel()),
+               "hps_lu_dist_solve")
+    return S_r, g
+
+
+CudaOps._root_solve_distributed = _root_solve_distributed
 
 
 class ShardedState:
@@ -235,7 +301,7 @@ def build_solver_sharded(pde_problem: PDEProblem, plan: SubtreePlan, device=None
     del Dblk
     if D_all.numel() * 8 > (4 << 30) and D_all.is_cuda:
         torch.cuda.empty_cache()  # the root D needs one large block; give freed subtree buffers back first
-    st.S_root_cols, g = ops.root_solve(D_all, h_all, Cblk, plan.first_octant)
+    st.S_root_cols, g = ops.root_solve(D_all, h_all, Cblk, plan.first_octant, plan.rank, plan.world, group)
     st.g_tilde_root = g
     st.multi = multi
     st.col_index = ops.tensor(child_column_index(plan.first_octant, n_oct, m)).to(torch.int64)

@@ -153,6 +153,34 @@ int hps_root_solve_oct(void* stream, int m, int n_src, int child0, int n_local, 
   return root_solve_oct(static_cast<cudaStream_t>(stream), m, n_src, child0, n_local, Dblk_all, hblk_all, Cblk_loc, S_r,
                         g_tilde, ws, ws_bytes, info);
 }
+int hps_root_assemble_oct(void* stream, int m, int n_src, int child0, int n_local, const double* Dblk_all,
+                          const double* hblk_all, const double* Cblk_loc, double* D, double* S_r, double* g_tilde) {
+  return root_assemble_oct(static_cast<cudaStream_t>(stream), m, n_src, child0, n_local, Dblk_all, hblk_all, Cblk_loc, D,
+                           S_r, g_tilde);
+}
+int hps_lu_dist_buffer_doubles(int n, size_t* count) {
+  if (!count) return fail_arg(2, "null output pointer");
+  *count = lu_dist_block_buffer_doubles(n);
+  return 0;
+}
+int hps_lu_dist_factor_pack(void* stream, int n, double* A, int64_t lda, int b, void* ws, size_t ws_bytes, int* info,
+                            double* buf) {
+  return lu_dist_factor_pack(static_cast<cudaStream_t>(stream), n, A, lda, b, ws, ws_bytes, info, buf);
+}
+int hps_lu_dist_unpack(void* stream, int n, double* A, int64_t lda, int b, void* ws, size_t ws_bytes, const double* buf) {
+  return lu_dist_unpack(static_cast<cudaStream_t>(stream), n, A, lda, b, ws, ws_bytes, buf);
+}
+int hps_lu_dist_update(void* stream, int n, double* A, int64_t lda, int b, int first_block, int n_blocks,
+                       int block_stride, void* ws, size_t ws_bytes) {
+  return lu_dist_update(static_cast<cudaStream_t>(stream), n, A, lda, b, first_block, n_blocks, block_stride, ws, ws_bytes);
+}
+int hps_lu_dist_solve(void* stream, int n, double* A, int64_t lda, int n_rhs, double* const* rhs, const int64_t* ld_rhs,
+                      const int* ncols, void* ws, size_t ws_bytes) {
+  if (n_rhs < 0 || n_rhs > 4) return fail_arg(5, "n_rhs must be in [0, 4]");
+  RhsDesc d[4];
+  for (int k = 0; k < n_rhs; ++k) d[k] = RhsDesc{rhs[k], ld_rhs[k], 0, ncols[k]};
+  return lu_dist_solve(static_cast<cudaStream_t>(stream), n, A, lda, n_rhs, d, ws, ws_bytes);
+}
 int hps_down_oct_scatter(void* stream, int n_nodes, int m, int n_src, const double* g_ext, const double* g_int,
                          double* g_children) {
   return down_oct_scatter(static_cast<cudaStream_t>(stream), n_nodes, m, n_src, g_ext, g_int, g_children);

@@ -84,6 +84,16 @@ size_t lu_workspace_bytes(int batch, int n);
 int lu_solve(cudaStream_t st, int batch, int n, double* A, int64_t lda, int64_t sA, int n_rhs,
              const RhsDesc* rhs, void* ws, size_t ws_bytes, int* info);
 
+// step-wise distributed factorisation (lu.cu), driven from jaxhps_b200/_dist.py
+size_t lu_dist_block_buffer_doubles(int n);
+int lu_dist_factor_pack(cudaStream_t st, int n, double* A, int64_t lda, int b, void* ws, size_t ws_bytes, int* info,
+                        double* buf);
+int lu_dist_unpack(cudaStream_t st, int n, double* A, int64_t lda, int b, void* ws, size_t ws_bytes, const double* buf);
+int lu_dist_update(cudaStream_t st, int n, double* A, int64_t lda, int b, int first_block, int n_blocks,
+                   int block_stride, void* ws, size_t ws_bytes);
+int lu_dist_solve(cudaStream_t st, int n, double* A, int64_t lda, int n_rhs, const RhsDesc* rhs, void* ws,
+                  size_t ws_bytes);
+
 // ---- stages (leaf.cu / merge.cu) --------------------------------------------------------
 size_t local_solve_workspace_bytes(int dim, int n_leaves, int p, int q);
 int local_solve_dtn(cudaStream_t st, int dim, int n_leaves, int p, int q, int n_src, const uint8_t* which,
@@ -99,6 +109,8 @@ int merge_quad_level(cudaStream_t st, int n_merges, int m, int n_src, const doub
 int root_pack_oct(cudaStream_t st, int n_local, int child0, int m, int n_src, const double* T, const double* h,
                   double* Dblk, double* Cblk, double* hblk);
 size_t root_solve_oct_ws_bytes(int m);
+int root_assemble_oct(cudaStream_t st, int m, int n_src, int child0, int n_local, const double* Dblk_all,
+                      const double* hblk_all, const double* Cblk_loc, double* D, double* S_r, double* gt);
 int root_solve_oct(cudaStream_t st, int m, int n_src, int child0, int n_local, const double* Dblk_all,
                    const double* hblk_all, const double* Cblk_loc, double* S_r, double* gt, void* ws, size_t ws_bytes,
                    int* info);

@@ -618,4 +618,136 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
   return 0;
 }
 
+
+// =====================================================================================
+// Step-wise entry points for the DISTRIBUTED factorisation of the multi-GPU root merge.
+// Every rank holds the full n x n matrix but owns (keeps up to date) only every
+// `block_stride`-th block column.  Per block column b the owner factors it, the caller broadcasts
+// the packed column (NCCL, from Python), every rank applies it to the block columns it owns.
+// After the last step every rank holds the complete P A = L U and solves its own right-hand sides.
+// All calls share one workspace (same pointer, lu_workspace_bytes(1, n)).
+// =====================================================================================
+
+namespace {
+__global__ void pack_block_kernel(int n, int jb, const double* __restrict__ A, int64_t lda, int j,
+                                  const int* __restrict__ ipiv, const double* __restrict__ Linv, double* __restrict__ buf,
+                                  int unpack, double* __restrict__ A_out, int* __restrict__ ipiv_out,
+                                  double* __restrict__ Linv_out) {
+  const int64_t n_col = (int64_t)n * jb;
+  const int64_t total = n_col + jb + (int64_t)NB * NB;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    if (e < n_col) {
+      const int64_t r = e / jb, c = e - r * jb;
+      if (unpack) A_out[r * lda + j + c] = buf[e]; else buf[e] = A[r * lda + j + c];
+    } else if (e < n_col + jb) {
+      const int k = (int)(e - n_col);
+      if (unpack) ipiv_out[j + k] = (int)buf[e]; else buf[e] = (double)ipiv[j + k];
+    } else {
+      const int64_t k = e - n_col - jb;
+      if (unpack) Linv_out[k] = buf[e]; else buf[e] = Linv[k];
+    }
+  }
+}
+}  // namespace
+
+size_t lu_dist_block_buffer_doubles(int n) { return (size_t)n * NB + NB + (size_t)NB * NB; }
+
+static int dist_setup(void* ws, size_t ws_bytes, int n, LuWorkspace& w) {
+  Arena ar(ws, ws_bytes);
+  if (!carve(ar, 1, n, w)) return fail_arg(5, "lu_dist: workspace too small");
+  static bool configured = false;
+  if (!configured) {
+    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
+    configured = true;
+  }
+  return 0;
+}
+
+// owner: factor block column b (must be up to date) and pack it, its pivots and the inverse of its
+// unit-lower diagonal block into buf
+int lu_dist_factor_pack(cudaStream_t st, int n, double* A, int64_t lda, int b, void* ws, size_t ws_bytes, int* info,
+                        double* buf) {
+  LuWorkspace w;
+  HPS_TRY(dist_setup(ws, ws_bytes, n, w));
+  const int j = b * NB, jb = min(NB, n - j);
+  if (j >= n) return fail_arg(4, "block index out of range");
+  const Mat Am{A, lda, 0};
+  HPS_TRY(factor_block_column(st, 1, n, Am, j, jb, w, info));
+  const double* Linv = w.Linv + (int64_t)b * NB * NB;
+  pack_block_kernel<<<1024, 256, 0, st>>>(n, jb, A, lda, j, w.ipiv, Linv, buf, 0, nullptr, nullptr, nullptr);
+  HPS_LAUNCH_CHECK("pack_block_kernel");
+  return 0;
+}
+
+// non-owner: install the broadcast block column
+int lu_dist_unpack(cudaStream_t st, int n, double* A, int64_t lda, int b, void* ws, size_t ws_bytes, const double* buf) {
+  LuWorkspace w;
+  HPS_TRY(dist_setup(ws, ws_bytes, n, w));
+  const int j = b * NB, jb = min(NB, n - j);
+  double* Linv = w.Linv + (int64_t)b * NB * NB;
+  pack_block_kernel<<<1024, 256, 0, st>>>(n, jb, nullptr, lda, j, nullptr, nullptr, const_cast<double*>(buf), 1, A, w.ipiv,
+                                          Linv);
+  HPS_LAUNCH_CHECK("pack_block_kernel(unpack)");
+  return 0;
+}
+
+// every rank: apply block column b to the block columns first_block + i*block_stride (i < n_blocks,
+// all > b) that it owns, and its interchanges to the columns on the left
+int lu_dist_update(cudaStream_t st, int n, double* A, int64_t lda, int b, int first_block, int n_blocks,
+                   int block_stride, void* ws, size_t ws_bytes) {
+  LuWorkspace w;
+  HPS_TRY(dist_setup(ws, ws_bytes, n, w));
+  const int j = b * NB, jb = min(NB, n - j);
+  const Mat Am{A, lda, 0};
+  HPS_TRY(laswp(st, 1, A, lda, 0, 0, j, w.ipiv, n, j, j + jb));  // L in LAPACK form
+  if (n_blocks <= 0) return 0;
+  if (first_block <= b) return fail_arg(6, "owned blocks must lie to the right of b");
+  const double* Linv = w.Linv + (int64_t)b * NB * NB;
+  const int below = n - (j + jb);
+  // full-width owned blocks as one strided batch; a ragged last block separately
+  int full = n_blocks;
+  const int last_c0 = (first_block + (n_blocks - 1) * block_stride) * NB;
+  const bool ragged = last_c0 + NB > n;
+  if (ragged) --full;
+  const int64_t sBlk = (int64_t)block_stride * NB;
+  auto apply = [&](int c0, int nc, int batch) -> int {
+    prof_begin(PROF_LASWP, st, (double)batch * nc * jb);
+    laswp_kernel<<<dim3((nc + 255) / 256, batch), 256, 0, st>>>(A, lda, sBlk, c0, nc, w.ipiv, 0, j, j + jb);
+    prof_end(PROF_LASWP, st);
+    HPS_LAUNCH_CHECK("laswp_kernel");
+    HPS_TRY(tri_mult(st, batch, jb, Linv, 0, Am.at(j, c0), lda, sBlk, nc, w.tmp));
+    if (below > 0)
+      HPS_TRY(dgemm(st, below, nc, jb, -1.0, Am.at(j + jb, j), lda, 0, Am.at(j, c0), lda, sBlk, 1.0, Am.at(j + jb, c0), lda,
+                    sBlk, batch));
+    return 0;
+  };
+  if (full > 0) HPS_TRY(apply(first_block * NB, NB, full));
+  if (ragged) HPS_TRY(apply(last_c0, n - last_c0, 1));
+  return 0;
+}
+
+// every rank, after the last block column: U's diagonal inverses, interchanges on the right-hand
+// sides and the two recursive substitutions
+int lu_dist_solve(cudaStream_t st, int n, double* A, int64_t lda, int n_rhs, const RhsDesc* rhs, void* ws,
+                  size_t ws_bytes) {
+  LuWorkspace w;
+  HPS_TRY(dist_setup(ws, ws_bytes, n, w));
+  const Mat Am{A, lda, 0};
+  const int nblk = (n + NB - 1) / NB;
+  prof_begin(PROF_TRTRI, st, (double)nblk * NB * NB * NB / 3);
+  trtri_kernel<false><<<dim3(nblk, 1), NB, TRTRI_SMEM, st>>>(A, lda, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
+  prof_end(PROF_TRTRI, st);
+  HPS_LAUNCH_CHECK("trtri_kernel<upper>");
+  for (int k = 0; k < n_rhs; ++k) {
+    HPS_TRY(laswp(st, 1, rhs[k].ptr, rhs[k].ld, rhs[k].stride, 0, rhs[k].ncols, w.ipiv, n, 0, n));
+    HPS_TRY(trsm_lower(st, 1, n, Am, w, rhs[k], 0, n));
+    HPS_TRY(trsm_upper(st, 1, n, Am, w, rhs[k], 0, n));
+  }
+  return 0;
+}
+
 }  // namespace hps

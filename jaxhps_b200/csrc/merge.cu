@@ -601,6 +601,18 @@ int root_pack_oct(cudaStream_t st, int n_local, int child0, int m, int n_src, co
   return 0;
 }
 
+// assembly only (distributed factorisation path): D (12m x 12m), S_r := -C_r, g~ := -h_int
+int root_assemble_oct(cudaStream_t st, int m, int n_src, int child0, int n_local, const double* Dblk_all,
+                      const double* hblk_all, const double* Cblk_loc, double* D, double* S_r, double* gt) {
+  if (m <= 0 || n_src <= 0 || n_local <= 0 || child0 < 0 || child0 + n_local > 8) return fail_arg(2, "bad child range");
+  const int n_int = 12 * m, ncr = 3 * m * n_local;
+  const int cols = n_int + ncr + n_src;
+  dim3 grid(std::min((cols + 255) / 256, 64), std::min(n_int, 65535), 1);
+  root_assemble_kernel<<<grid, 256, 0, st>>>(oct_topo(), m, n_src, child0, n_local, Dblk_all, hblk_all, Cblk_loc, D, S_r, gt);
+  HPS_LAUNCH_CHECK("root_assemble_kernel");
+  return 0;
+}
+
 size_t root_solve_oct_ws_bytes(int m) {
   const size_t n_int = 12 * (size_t)m;
   return align_up(n_int * n_int * sizeof(double), 256) + lu_workspace_bytes(1, (int)n_int) + 1024;

@@ -53,7 +53,7 @@ class OracleOps:
             D.append(T[k][np.ix_(ii, ii)]), C.append(T[k][np.ix_(ii, ee)]), hb.append(h[k][ii])
         return tuple(torch.from_numpy(np.ascontiguousarray(np.stack(x))) for x in (D, C, hb))
 
-    def root_solve(self, Dblk_all, hblk_all, Cblk_loc, first_child):
+    def root_solve(self, Dblk_all, hblk_all, Cblk_loc, first_child, rank=0, world=1, group=None):
         Db, hb, Cb = Dblk_all.numpy(), hblk_all.numpy(), Cblk_loc.numpy()
         m = Db.shape[-1] // 3
         n_local = Cb.shape[0]

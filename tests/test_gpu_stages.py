@@ -161,3 +161,25 @@ def test_sharded_driver_single_rank_matches_oracle(p, q, L, nsrc):
         n_ext = S[-1].shape[1]
         Sc, gt = merge_root_columns_3D_DtN(T, h, n_ext // 2, n_ext // 2, device="cuda:0")
         assert rel_err(Sc.cpu().numpy(), S[-1][:, n_ext // 2 :]) < TOL and rel_err(gt.cpu().numpy(), g[-1]) < TOL
+
+
+@pytest.mark.parametrize("p,q,L", [(6, 4, 2), (8, 6, 2)])
+def test_stepwise_root_factorisation_matches_oracle(p, q, L):
+    """The step-wise factorisation the multi-GPU root uses (hps_lu_dist_*: factor+pack a block column,
+    apply it to the owned block columns, final solves), forced on a single rank."""
+    from jaxhps_b200 import _dist
+    from _cases import make_domain, seeded_inputs
+
+    co, src, bdry = seeded_inputs(3, p, q, L, 1, seed=91)
+    dom = make_domain(3, p, q, L)
+    plan = _dist.SubtreePlan(L, 0, 1)
+    pb = _dist.local_problem(dom, plan, source=src, **co)
+    ops = _dist.CudaOps("cuda:0")
+    ops.FORCE_DIST_LU, ops.DIST_LU_MIN_N = True, 0
+    st = _dist.build_solver_sharded(pb, plan, ops=ops)
+    u = _dist.solve_sharded(pb, st, plan, bdry, ops=ops)
+    full = hps.PDEProblem(dom, source=src, **co)
+    Y, T, v, h = orc.local_solve_stage_uniform_3D_DtN(full)
+    S, g = orc.merge_stage_uniform_3D_DtN(T, h, L)
+    assert rel_err(st.S_root_cols.cpu().numpy(), S[-1][:, st.col_index.cpu().numpy()]) < TOL
+    assert rel_err(u.cpu().numpy(), orc.down_pass_uniform_3D_DtN(bdry, S, g, Y, v)) < TOL
