@@ -294,6 +294,43 @@ def run_ours(args, rank, world, local_rank):
     ms_step = ms / args.steps
     value = n_leaves / (ms_step * 1e-3)
 
+    # per-stage breakdown (not part of the timed region): the stage functions called one by one
+    stages = None
+    if plan is None:
+        from jaxhps_b200.down_pass import down_pass_uniform_3D_DtN
+        from jaxhps_b200.local_solve import local_solve_stage_uniform_3D_DtN
+        from jaxhps_b200.merge import merge_stage_uniform_3D_DtN
+
+        def ev():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+
+        pb_res.reset()
+        torch.cuda.synchronize()
+        e0 = ev()
+        Y, T, v, h = local_solve_stage_uniform_3D_DtN(pb_res, device=dev, host_device=dev)
+        e1 = ev()
+        S_lst, gt_lst = merge_stage_uniform_3D_DtN(T, h, L, device=dev, host_device=dev)
+        e2 = ev()
+        u_s = down_pass_uniform_3D_DtN(g_dev, S_lst, gt_lst, Y, v, device=dev, host_device=dev)
+        e3 = ev()
+        torch.cuda.synchronize()
+        t_loc, t_mrg, t_dwn = e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3)
+        down_bytes = 8 * (sum(int(S.numel()) for S in S_lst) + int(Y.numel()))
+        leaf_fl = lean_flops(0) * n_leaves  # lean_flops(0) = one leaf
+        stages = {
+            "local_solve_ms": t_loc, "merge_ms": t_mrg, "down_pass_ms": t_dwn,
+            "leaf_solves_per_s_local_solve_stage": n_leaves / (t_loc * 1e-3),
+            "local_solve_tflops_lean": leaf_fl / (t_loc * 1e-3) * 1e-12,
+            "local_solve_frac_of_fp64_peak": leaf_fl / (t_loc * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS,
+            "merge_tflops_lean": (lean_flops(L) - leaf_fl) / (t_mrg * 1e-3) * 1e-12,
+            "merge_frac_of_fp64_peak": (lean_flops(L) - leaf_fl) / (t_mrg * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS,
+            "down_pass_bytes": down_bytes, "down_pass_GBps": down_bytes / (t_dwn * 1e-3) * 1e-9,
+            "down_pass_frac_of_hbm_peak": down_bytes / (t_dwn * 1e-3) * 1e-9 / 6558.1,
+        }
+        del Y, T, v, h, S_lst, gt_lst, u_s
+
     # end-to-end: host inputs -> public API -> host result, copies inside the timed region
     step(pb_host, g_pin, True)
     ms_e, _, _ = timed(pb_host, g_pin, True, args.steps)
@@ -323,6 +360,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2_policy": "working set (>=15 GB of operators per step) far exceeds the 126 MB L2; no flush needed"},
         "build_solve_seconds": ms_step * 1e-3,
         "max_rel_error_vs_analytic_solution": max_rel_err,
+        "stages": stages,
         "algorithmic_tflop_per_step": lean_flops(L) * 1e-12,
         "step_tflops": lean_flops(L) * 1e-12 / (ms_step * 1e-3),
         "clocks": clocks,
