@@ -256,56 +256,101 @@ __global__ void inner_trsm_kernel(double* A, int64_t lda, int64_t sA, int jj, in
 
 // Dense inverse of the nb x nb triangular block at A[j,j] into W (ld = NB, zero elsewhere).
 // LOWER: unit lower triangle.  !LOWER: upper triangle with its diagonal.
-// In-place column sweep (LAPACK trti2 order) in shared memory; one thread per row.
+// Recursive blocked inversion inside one CTA: the four 32x32 diagonal blocks are inverted
+// column-per-lane by four warps with no barrier at all, then the off-diagonal blocks follow from
+//   inv([[A,0],[C,B]]) = [[A^-1, 0], [-B^-1 C A^-1, B^-1]]   (mirrored for the upper case)
+// as small shared-memory products at the 32 and 64 level: 3 barriers-separated phases instead of
+// the 128 sequential column sweeps of an unblocked trti2.
+constexpr int TRI_THREADS = 256;
+constexpr int TRI_LD = NB + 1;
+
+// dst (M x N) = alpha * A (M x K) * B (K x N), all in shared memory, executed by the whole CTA
+__device__ __forceinline__ void smem_mm(double* dst, int ldd, const double* A, int lda, const double* B, int ldb, int M,
+                                        int N, int K, double alpha) {
+  for (int idx = threadIdx.x; idx < M * N; idx += TRI_THREADS) {
+    const int r = idx / N, c = idx - r * N;
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s = fma(A[r * lda + k], B[k * ldb + c], s);
+    dst[r * ldd + c] = alpha * s;
+  }
+}
+
 template <bool LOWER>
-__global__ void __launch_bounds__(NB) trtri_kernel(const double* A, int64_t lda, int64_t sA, int j0, int n,
-                                                   double* W, int64_t sW) {
+__global__ void __launch_bounds__(TRI_THREADS) trtri_kernel(const double* A, int64_t lda, int64_t sA, int j0, int n,
+                                                            double* W, int64_t sW) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int LD = NB + 1;
-  double* Ts = sm;             // [NB][LD]
-  double* colv = sm + NB * LD; // [NB]
+  constexpr int LD = TRI_LD;
+  double* Ts = sm;                 // [NB][LD]   the triangle, inverted in place
+  double* Ws = sm + NB * LD;       // [64][65]   product scratch
+  double* Xs = Ws + 64 * 65;       // [4][32][33] columns of the 32x32 diagonal inverses
   const int j = j0 + blockIdx.x * NB;      // diagonal block handled by this CTA
   const int nb = min(NB, n - j);
-  const int r = threadIdx.x;
   const double* a = A + (int64_t)blockIdx.y * sA + (int64_t)j * lda + j;
-  for (int idx = threadIdx.x; idx < nb * nb; idx += NB) {
-    const int rr = idx / nb, cc = idx - rr * nb;
-    double v = a[(int64_t)rr * lda + cc];
-    if (LOWER) v = (cc < rr) ? v : (cc == rr ? 1.0 : 0.0);
-    else v = (cc >= rr) ? v : 0.0;
+  // ragged blocks are padded with the identity
+  for (int idx = threadIdx.x; idx < NB * NB; idx += TRI_THREADS) {
+    const int rr = idx / NB, cc = idx - rr * NB;
+    double v = (rr == cc) ? 1.0 : 0.0;
+    if (rr < nb && cc < nb) {
+      const double x = a[(int64_t)rr * lda + cc];
+      if (LOWER) v = (cc < rr) ? x : v;
+      else v = (cc >= rr) ? x : 0.0;
+    }
     Ts[rr * LD + cc] = v;
   }
   __syncthreads();
-  if (LOWER) {
-    // columns from last to first: x = -Tinv[c+1:, c+1:] * l[c+1:, c]
-    for (int c = nb - 2; c >= 0; --c) {
-      if (r > c && r < nb) colv[r] = Ts[r * LD + c];
-      __syncthreads();
-      if (r > c && r < nb) {
+  // ---- phase 1: the four 32x32 diagonal blocks, one column per lane ----
+  if (threadIdx.x < 128) {
+    const int blk = threadIdx.x >> 5, c = threadIdx.x & 31, base = blk * 32;
+    double* x = Xs + blk * 32 * 33;  // x[r*33 + c]
+    const double* T = Ts + base * LD + base;
+    if (LOWER) {
+      for (int r = 0; r < 32; ++r) x[r * 33 + c] = (r == c) ? 1.0 : 0.0;
+      for (int r = c + 1; r < 32; ++r) {
         double s = 0.0;
-        for (int t = c + 1; t <= r; ++t) s = fma(Ts[r * LD + t], colv[t], s);
-        Ts[r * LD + c] = -s;
+        for (int t = c; t < r; ++t) s = fma(T[r * LD + t], x[t * 33 + c], s);
+        x[r * 33 + c] = -s;
       }
-      __syncthreads();
-    }
-  } else {
-    // columns from first to last: diag = 1/u_cc ; x = -diag * Tinv[:c,:c] * u[:c, c]
-    for (int c = 0; c < nb; ++c) {
-      if (r <= c) colv[r] = Ts[r * LD + c];
-      __syncthreads();
-      const double d = 1.0 / colv[c];
-      if (r < c) {
+    } else {
+      for (int r = 0; r < 32; ++r) x[r * 33 + c] = 0.0;
+      x[c * 33 + c] = 1.0 / T[c * LD + c];
+      for (int r = c - 1; r >= 0; --r) {
         double s = 0.0;
-        for (int t = r; t < c; ++t) s = fma(Ts[r * LD + t], colv[t], s);
-        Ts[r * LD + c] = -s * d;
-      } else if (r == c) {
-        Ts[r * LD + c] = d;
+        for (int t = r + 1; t <= c; ++t) s = fma(T[r * LD + t], x[t * 33 + c], s);
+        x[r * 33 + c] = -s / T[r * LD + r];
       }
-      __syncthreads();
     }
+    __syncwarp();
+    for (int r = 0; r < 32; ++r) Ts[(base + r) * LD + base + c] = x[r * 33 + c];
   }
+  __syncthreads();
+  // ---- phase 2: 32-level off-diagonal blocks of both 64x64 halves ----
+  for (int half = 0; half < 2; ++half) {
+    const int b0 = half * 64, b1 = b0 + 32;
+    double* Wp = Ws + half * 32 * 65;
+    if (LOWER)  // W = L21 * inv(L11)
+      smem_mm(Wp, 65, Ts + b1 * LD + b0, LD, Ts + b0 * LD + b0, LD, 32, 32, 32, 1.0);
+    else        // W = U12 * inv(U22)
+      smem_mm(Wp, 65, Ts + b0 * LD + b1, LD, Ts + b1 * LD + b1, LD, 32, 32, 32, 1.0);
+  }
+  __syncthreads();
+  for (int half = 0; half < 2; ++half) {
+    const int b0 = half * 64, b1 = b0 + 32;
+    const double* Wp = Ws + half * 32 * 65;
+    if (LOWER)  // X21 = -inv(L22) * W
+      smem_mm(Ts + b1 * LD + b0, LD, Ts + b1 * LD + b1, LD, Wp, 65, 32, 32, 32, -1.0);
+    else        // X12 = -inv(U11) * W
+      smem_mm(Ts + b0 * LD + b1, LD, Ts + b0 * LD + b0, LD, Wp, 65, 32, 32, 32, -1.0);
+  }
+  __syncthreads();
+  // ---- phase 3: the 64-level off-diagonal block ----
+  if (LOWER) smem_mm(Ws, 65, Ts + 64 * LD, LD, Ts, LD, 64, 64, 64, 1.0);            // W = L21 * inv(L11)
+  else smem_mm(Ws, 65, Ts + 64, LD, Ts + 64 * LD + 64, LD, 64, 64, 64, 1.0);        // W = U12 * inv(U22)
+  __syncthreads();
+  if (LOWER) smem_mm(Ts + 64 * LD, LD, Ts + 64 * LD + 64, LD, Ws, 65, 64, 64, 64, -1.0);  // X21 = -inv(L22) * W
+  else smem_mm(Ts + 64, LD, Ts, LD, Ws, 65, 64, 64, 64, -1.0);                            // X12 = -inv(U11) * W
+  __syncthreads();
   double* w = W + (int64_t)blockIdx.y * sW + (int64_t)(j / NB) * NB * NB;
-  for (int idx = threadIdx.x; idx < nb * nb; idx += NB) {
+  for (int idx = threadIdx.x; idx < nb * nb; idx += TRI_THREADS) {
     const int rr = idx / nb, cc = idx - rr * nb;
     w[rr * NB + cc] = Ts[rr * LD + cc];
   }
@@ -320,7 +365,7 @@ __global__ void copy_block_kernel(double* dst, int64_t ldd, int64_t sD, const do
   dst[(int64_t)blockIdx.y * sD + (int64_t)r * ldd + c] = src[(int64_t)blockIdx.y * sS + (int64_t)r * lds + c];
 }
 
-constexpr size_t TRTRI_SMEM = sizeof(double) * (NB * (NB + 1) + NB);
+constexpr size_t TRTRI_SMEM = sizeof(double) * (NB * (NB + 1) + 64 * 65 + 4 * 32 * 33);
 
 struct LuWorkspace {
   int* ipiv;
@@ -489,7 +534,7 @@ int factor_block_column(cudaStream_t st, int batch, int n, const Mat& A, int j, 
   }
   const int nblk = (n + NB - 1) / NB;
   prof_begin(PROF_TRTRI, st, (double)batch * NB * NB * NB / 3);
-  trtri_kernel<true><<<dim3(1, batch), NB, TRTRI_SMEM, st>>>(A.p, A.ld, A.stride, j, n, w.Linv, (int64_t)nblk * NB * NB);
+  trtri_kernel<true><<<dim3(1, batch), TRI_THREADS, TRTRI_SMEM, st>>>(A.p, A.ld, A.stride, j, n, w.Linv, (int64_t)nblk * NB * NB);
   prof_end(PROF_TRTRI, st);
   HPS_LAUNCH_CHECK("trtri_kernel<lower>");
   return 0;
@@ -606,7 +651,7 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
 
   // ---- 2. inverses of U's diagonal blocks (all at once), interchanges on the right-hand sides --
   prof_begin(PROF_TRTRI, s0, (double)batch * nblk * NB * NB * NB / 3);
-  trtri_kernel<false><<<dim3(nblk, batch), NB, TRTRI_SMEM, s0>>>(A.p, A.ld, A.stride, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
+  trtri_kernel<false><<<dim3(nblk, batch), TRI_THREADS, TRTRI_SMEM, s0>>>(A.p, A.ld, A.stride, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
   prof_end(PROF_TRTRI, s0);
   HPS_LAUNCH_CHECK("trtri_kernel<upper>");
   for (int k = 0; k < n_rhs; ++k) {
@@ -739,7 +784,7 @@ int lu_dist_solve(cudaStream_t st, int n, double* A, int64_t lda, int n_rhs, con
   const Mat Am{A, lda, 0};
   const int nblk = (n + NB - 1) / NB;
   prof_begin(PROF_TRTRI, st, (double)nblk * NB * NB * NB / 3);
-  trtri_kernel<false><<<dim3(nblk, 1), NB, TRTRI_SMEM, st>>>(A, lda, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
+  trtri_kernel<false><<<dim3(nblk, 1), TRI_THREADS, TRTRI_SMEM, st>>>(A, lda, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
   prof_end(PROF_TRTRI, st);
   HPS_LAUNCH_CHECK("trtri_kernel<upper>");
   for (int k = 0; k < n_rhs; ++k) {
