@@ -7,8 +7,8 @@ using namespace hps::gemmk;
 #define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("CUDA error %s line %d\n",cudaGetErrorString(e),__LINE__);exit(1);}}while(0)
 __global__ void fill(double* p, size_t n, unsigned seed){ size_t i=blockIdx.x*(size_t)blockDim.x+threadIdx.x; size_t st=(size_t)gridDim.x*blockDim.x; for(;i<n;i+=st){ unsigned x=(unsigned)(i*2654435761u)^seed; x^=x>>13; x*=0x5bd1e995; x^=x>>15; p[i]=((x&0xffff)/65536.0)-0.5; } }
 __global__ void checksum(const double* p, size_t n, double* out){ __shared__ double s[256]; double a=0; size_t i=blockIdx.x*(size_t)blockDim.x+threadIdx.x; size_t st=(size_t)gridDim.x*blockDim.x; for(;i<n;i+=st) a+=p[i]*(1+(i%7)); s[threadIdx.x]=a; __syncthreads(); for(int o=128;o>0;o>>=1){ if(threadIdx.x<o) s[threadIdx.x]+=s[threadIdx.x+o]; __syncthreads(); } if(threadIdx.x==0) atomicAdd(out,s[0]); }
-template<class Cfg, bool MB=false> double run(const char* name, GemmArgs g, int batch, double* C0, size_t csz, double* d_sum){
-  auto kern = MB ? gemm_kernel_mb<Cfg> : gemm_kernel<Cfg>;
+template<class Cfg, int MB=0> double run(const char* name, GemmArgs g, int batch, double* C0, size_t csz, double* d_sum){
+  auto kern = MB == 2 ? gemm_kernel_tma<Cfg> : (MB == 1 ? gemm_kernel_mb<Cfg> : gemm_kernel<Cfg>);
   static bool conf=false; if(!conf){ CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,(int)Cfg::SMEM_BYTES)); conf=true; }
   dim3 grid((g.N+Cfg::BN-1)/Cfg::BN,(g.M+Cfg::BM-1)/Cfg::BM,batch);
   int occ=0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
@@ -36,18 +36,11 @@ int main(){
     GemmArgs g; g.M=s.M; g.N=s.N; g.K=s.K; g.alpha=-1.0; g.beta=s.beta; g.A=A; g.lda=s.K; g.sA=(int64_t)s.M*s.K; g.B=B; g.ldb=s.N; g.sB=(int64_t)s.K*s.N; g.C=C; g.ldc=s.N; g.sC=(int64_t)s.M*s.N; g.vecA=g.vecB=g.vecC=1;
     printf("shape M=%d N=%d K=%d batch=%d beta=%g\n",s.M,s.N,s.K,s.batch,s.beta);
     //                 WM  WN  WMs WNs BK  ST  minCTA
-    run<Config<32, 32, 4, 4, 32, 3, 1>>("A  128x128 16w(32x32) bk32 s3", g, s.batch, C0, csz, d_sum);
-    run<Config<32, 32, 4, 4, 32, 3, 1>, true>("A  mb", g, s.batch, C0, csz, d_sum);
-    run<Config<32, 32, 4, 4, 16, 4, 1>, true>("A' mb 128x128 16w bk16 s4", g, s.batch, C0, csz, d_sum);
-    run<Config<64, 32, 2, 4, 32, 3, 1>>("B  128x128 8w(64x32) bk32 s3", g, s.batch, C0, csz, d_sum);
-    run<Config<64, 32, 2, 4, 32, 3, 1>, true>("B  mb", g, s.batch, C0, csz, d_sum);
-    run<Config<64, 32, 2, 4, 16, 4, 1>, true>("B' mb 128x128 8w(64x32) bk16 s4", g, s.batch, C0, csz, d_sum);
-    run<Config<32, 64, 4, 2, 32, 3, 1>, true>("C  mb 128x128 8w(32x64) bk32 s3", g, s.batch, C0, csz, d_sum);
-    run<Config<64, 32, 2, 2, 16, 3, 2>>("F  128x64 4w(64x32) bk16 s3 x2cta", g, s.batch, C0, csz, d_sum);
-    run<Config<64, 32, 2, 2, 16, 3, 2>, true>("F  mb", g, s.batch, C0, csz, d_sum);
-    run<Config<64, 32, 2, 2, 32, 2, 2>, true>("F2 mb 128x64 4w(64x32) bk32 s2 x2cta", g, s.batch, C0, csz, d_sum);
-    run<Config<32, 64, 2, 2, 16, 3, 2>, true>("F3 mb 64x128 4w(32x64) bk16 s3 x2cta", g, s.batch, C0, csz, d_sum);
-    run<Config<32, 32, 4, 2, 16, 3, 2>, true>("G  mb 128x64 8w(32x32) bk16 s3 x2cta", g, s.batch, C0, csz, d_sum);
+    run<Config<32, 32, 4, 2, 16, 3, 2>, 1>("G  mb  128x64 8w(32x32) bk16 s3 x2cta", g, s.batch, C0, csz, d_sum);
+    run<Config<32, 32, 4, 2, 16, 3, 2>, 2>("G  tma 128x64 8w(32x32) bk16 s3 x2cta", g, s.batch, C0, csz, d_sum);
+    run<Config<32, 32, 4, 4, 32, 3, 1>, 1>("A  mb  128x128 16w bk32 s3", g, s.batch, C0, csz, d_sum);
+    run<Config<32, 32, 4, 4, 32, 3, 1>, 2>("A  tma 128x128 16w bk32 s3", g, s.batch, C0, csz, d_sum);
+    run<Config<32, 32, 4, 2, 32, 2, 2>, 2>("G2 tma 128x64 8w bk32 s2 x2cta", g, s.batch, C0, csz, d_sum);
     cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(C0);
   }
   return 0;
