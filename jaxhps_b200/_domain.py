@@ -14,6 +14,8 @@ from ._grid import (
     compute_interior_Chebyshev_points_uniform_2D,
     compute_interior_Chebyshev_points_uniform_3D,
 )
+from ._grid import uniform_leaf_bounds_2D, uniform_leaf_bounds_3D
+from ._interpolation_methods import interp_from_hps_2D, interp_from_hps_3D, interp_to_hps_2D, interp_to_hps_3D
 from ._tree import DiscretizationNode2D, DiscretizationNode3D
 
 
@@ -44,6 +46,34 @@ class Domain:
             #: (6 * 4^L * q^2, 3)
             self.boundary_points = compute_boundary_Gauss_points_uniform_3D(root, L, q)
             self.n_leaves = 8**L
+
+    def _leaf_bounds(self) -> np.ndarray:
+        fn = uniform_leaf_bounds_2D if self.bool_2D else uniform_leaf_bounds_3D
+        return fn(self.root, self.L)
+
+    def interp_to_interior_points(self, values, sample_points_x, sample_points_y, sample_points_z=None) -> np.ndarray:
+        """Values on a regular grid (``meshgrid(..., indexing="ij")``) -> samples on the HPS grid,
+        shape ``(n_leaves, p^d)`` (reference `_domain.py:99-208`)."""
+        values = np.asarray(values)
+        if values.ndim == 2:
+            assert sample_points_z is None and values.shape == (len(sample_points_x), len(sample_points_y))
+            return interp_to_hps_2D(self._leaf_bounds(), values, self.p, sample_points_x, sample_points_y)
+        assert sample_points_z is not None
+        assert values.shape == (len(sample_points_x), len(sample_points_y), len(sample_points_z))
+        return interp_to_hps_3D(self._leaf_bounds(), values, self.p, sample_points_x, sample_points_y, sample_points_z)
+
+    def interp_to_boundary_points(self, *args, **kwargs):
+        raise NotImplementedError("interp_to_boundary_points is not implemented yet.")  # as in the reference
+
+    def interp_from_interior_points(self, samples, eval_points_x, eval_points_y, eval_points_z=None):
+        """Samples on the HPS grid ``(n_leaves, p^d)`` -> values on a regular grid and the target points
+        (reference `_domain.py:218-294`)."""
+        samples = np.asarray(samples)
+        if self.bool_2D:
+            assert eval_points_z is None
+            return interp_from_hps_2D(self._leaf_bounds(), self.p, samples, eval_points_x, eval_points_y)
+        assert eval_points_z is not None
+        return interp_from_hps_3D(self._leaf_bounds(), self.p, samples, eval_points_x, eval_points_y, eval_points_z)
 
     @classmethod
     def from_adaptive_discretization(cls, *args, **kwargs):

@@ -120,7 +120,31 @@ CASES = {
     "refiti_p8q6L2_ms": (20, 8, 6, 2, 2, 32, False),
 }
 
+def interp_case():
+    """Domain.interp_{to,from}_interior_points of the reference on seeded data (2D and 3D)."""
+    rng = np.random.default_rng(77)
+    out = {}
+    d2 = ref.Domain(p=6, q=4, root=ref.DiscretizationNode2D(xmin=-1.0, xmax=1.0, ymin=0.0, ymax=2.0), L=2)
+    f2 = rng.normal(size=(16, 36))
+    xs, ys = np.linspace(-1, 1, 7), np.linspace(0, 2, 5)
+    v, t = d2.interp_from_interior_points(jnp.array(f2), jnp.array(xs), jnp.array(ys))
+    g2 = rng.normal(size=(9, 8))
+    sx, sy = np.linspace(-1, 1, 9), np.linspace(0, 2, 8)
+    out.update(f2=f2, from2=np.asarray(v), pts2=np.asarray(t), g2=g2,
+               to2=np.asarray(d2.interp_to_interior_points(jnp.array(g2), jnp.array(sx), jnp.array(sy))))
+    d3 = ref.Domain(p=4, q=2, root=ref.DiscretizationNode3D(xmin=0.0, xmax=1.0, ymin=0.0, ymax=1.0, zmin=-1.0, zmax=0.0), L=1)
+    f3 = rng.normal(size=(8, 64))
+    x3, y3, z3 = np.linspace(0, 1, 5), np.linspace(0, 1, 4), np.linspace(-1, 0, 3)
+    v, t = d3.interp_from_interior_points(jnp.array(f3), jnp.array(x3), jnp.array(y3), jnp.array(z3))
+    g3 = rng.normal(size=(5, 6, 7))
+    out.update(f3=f3, from3=np.asarray(v), pts3=np.asarray(t), g3=g3,
+               to3=np.asarray(d3.interp_to_interior_points(jnp.array(g3), jnp.array(np.linspace(0, 1, 5)),
+                                                           jnp.array(np.linspace(0, 1, 6)), jnp.array(np.linspace(-1, 0, 7)))))
+    return out
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "interp_reference.npz"), **interp_case())
     for name, args in CASES.items():
         data = run_case(*args)
         path = os.path.join(HERE, name + ".npz")

@@ -113,3 +113,30 @@ def test_pdeproblem_validation_matches_reference_errors():
         hps.PDEProblem(d2, source=s2, D_zz_coefficients=s2)
     with pytest.raises(ValueError):
         hps.PDEProblem(d2, source=s2, D_xx_coefficients=s2, use_ItI=True)
+
+
+def test_interpolation_matches_reference_fixture():
+    """Domain.interp_{to,from}_interior_points against outputs of the reference (tests/golden/make_golden.py)."""
+    import os
+
+    G = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "interp_reference.npz")))
+    d2 = hps.Domain(6, 4, hps.DiscretizationNode2D(-1.0, 1.0, 0.0, 2.0), 2)
+    v, t = d2.interp_from_interior_points(G["f2"], np.linspace(-1, 1, 7), np.linspace(0, 2, 5))
+    assert np.abs(v - G["from2"]).max() < 1e-13 and np.array_equal(t, G["pts2"])
+    to = d2.interp_to_interior_points(G["g2"], np.linspace(-1, 1, 9), np.linspace(0, 2, 8))
+    assert np.abs(to - G["to2"]).max() < 1e-12
+    d3 = hps.Domain(4, 2, hps.DiscretizationNode3D(0.0, 1.0, 0.0, 1.0, -1.0, 0.0), 1)
+    v, t = d3.interp_from_interior_points(G["f3"], np.linspace(0, 1, 5), np.linspace(0, 1, 4), np.linspace(-1, 0, 3))
+    assert np.abs(v - G["from3"]).max() < 1e-13 and np.array_equal(t, G["pts3"])
+    to = d3.interp_to_interior_points(G["g3"], np.linspace(0, 1, 5), np.linspace(0, 1, 6), np.linspace(-1, 0, 7))
+    assert np.abs(to - G["to3"]).max() < 1e-12
+
+
+def test_interpolation_is_exact_on_polynomials():
+    d3 = hps.Domain(6, 4, hps.DiscretizationNode3D(0.0, 1.0, 0.0, 1.0, 0.0, 1.0), 1)
+    x = d3.interior_points
+    f = x[..., 0] ** 3 - 2 * x[..., 1] * x[..., 2] ** 2
+    xs = np.linspace(0.05, 0.95, 4)
+    vals, pts = d3.interp_from_interior_points(f, xs, xs, xs)
+    exact = pts[..., 0] ** 3 - 2 * pts[..., 1] * pts[..., 2] ** 2
+    assert np.abs(vals - exact.reshape(vals.shape)).max() < 1e-12
