@@ -356,7 +356,7 @@ def run_ours(args, rank, world, local_rank):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"3D variable-coefficient Poisson, uniform octree p={P} q={Q}, DtN, FP64", "L": L,
                    "n_leaves": n_leaves, "n_bdry": int(g_h.shape[0]),
-                   "parallelism": "single GPU" if world == 1 else f"subtree-sharded x{world}; root merge column-sharded by child, root LU replicated below n=32768 and distributed by block columns above",
+                   "parallelism": "single GPU" if world == 1 else f"subtree-sharded x{world}; root merge column-sharded by child, root LU distributed by block columns with look-ahead (replicated below n=8192)",
                    "l2_policy": "working set (>=15 GB of operators per step) far exceeds the 126 MB L2; no flush needed"},
         "build_solve_seconds": ms_step * 1e-3,
         "max_rel_error_vs_analytic_solution": max_rel_err,

@@ -127,7 +127,9 @@ int hps_root_solve_oct(void* stream, int m, int n_src, int child0, int n_local,
  * column b: the owner calls hps_lu_dist_factor_pack (panel chain + pack of the column, its pivots and
  * the inverse of its unit-lower diagonal block into buf, hps_lu_dist_buffer_doubles(n) doubles); buf
  * is broadcast; the other ranks call hps_lu_dist_unpack; every rank calls hps_lu_dist_update for
- * the block columns first_block + i*block_stride (i < n_blocks, all > b) it owns.  After the last
+ * the block columns first_block + i*block_stride (i < n_blocks, all > b) it owns; apply_left != 0 also
+ * applies block b's interchanges to the columns on its left (exactly one call per block must do so;
+ * the look-ahead driver updates the next block column on a second stream with apply_left = 0).  After the last
  * block every rank holds the complete P A = L U and hps_lu_dist_solve solves its own right-hand sides
  * (up to 4 matrices, n x ncols[k], in place).  One workspace for all calls: hps_lu_solve_workspace(1, n).
  * hps_root_assemble_oct is the assembly half of hps_root_solve_oct (D, S_r := -C_r, g_tilde := -h_int). */
@@ -140,7 +142,8 @@ int hps_lu_dist_factor_pack(void* stream, int n, double* A, int64_t lda, int b,
 int hps_lu_dist_unpack(void* stream, int n, double* A, int64_t lda, int b,
                        void* ws, size_t ws_bytes, const double* buf);
 int hps_lu_dist_update(void* stream, int n, double* A, int64_t lda, int b,
-                       int first_block, int n_blocks, int block_stride, void* ws, size_t ws_bytes);
+                       int first_block, int n_blocks, int block_stride, int apply_left,
+                       void* ws, size_t ws_bytes);
 int hps_lu_dist_solve(void* stream, int n, double* A, int64_t lda, int n_rhs, double* const* rhs,
                       const int64_t* ld_rhs, const int* ncols, void* ws, size_t ws_bytes);
 

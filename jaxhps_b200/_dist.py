@@ -23,6 +23,7 @@ the C ABI) or a test double built on the CPU oracle for the ``gloo`` world-size-
 """
 from __future__ import annotations
 
+import os
 from typing import List
 
 import numpy as np
@@ -139,7 +140,7 @@ class CudaOps:
         return Dblk, Cblk, hblk
 
     #: distribute the factorisation of the root D over the ranks when it is at least this large
-    DIST_LU_MIN_N = 32768
+    DIST_LU_MIN_N = int(os.environ.get("HPS_DIST_LU_MIN_N", "8192"))
     #: tests: run the step-wise (distributed) factorisation even on a single rank
     FORCE_DIST_LU = False
 
@@ -199,6 +200,17 @@ class CudaOps:
         return leaf_apply(Y, g_leaf, v.reshape(v.shape[0], v.shape[1], n_src), self.dev)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    """One high-priority stream per device for the look-ahead panel chain."""
+    key = str(dev)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev, priority=-1)
+    return _SIDE_STREAMS[key]
+
+
 def _root_solve_distributed(self, Dblk_all, hblk_all, Cblk_loc, first_child, rank, world, group):
     """Distributed LU of the root D: block column b is factored by rank b % world, broadcast, and
     applied by every rank to the block columns it owns; then local solves of the rank's columns."""
@@ -225,23 +237,58 @@ def _root_solve_distributed(self, Dblk_all, hblk_all, Cblk_loc, first_child, ran
     _lib.check(lib.hps_lu_dist_buffer_doubles(n, ctypes.byref(cnt)), "buffer query")
     bufs = [self.empty((cnt.value,)), self.empty((cnt.value,))]
     info = torch.zeros(1, dtype=torch.int32, device=self.dev)
-    st = _lib.stream_ptr()
-    for b in range(nblk):
-        owner = b % world
-        buf = bufs[b & 1]
-        if rank == owner:
-            _lib.check(lib.hps_lu_dist_factor_pack(st, n, D.data_ptr(), n, b, ws.data_ptr(), ws.numel(), info.data_ptr(),
-                                                   buf.data_ptr()), "hps_lu_dist_factor_pack")
+    # Look-ahead: a high-priority side stream keeps the panel chain (update of the NEXT block column,
+    # its factorisation, the broadcast) one block ahead of the main stream's rank-128 updates.
+    main = torch.cuda.current_stream()
+    side = _side_stream(self.dev)
+    ev_panel = [torch.cuda.Event() for _ in range(2)]
+    ev_upd = [torch.cuda.Event() for _ in range(2)]
+    A, wsp, wsn = D.data_ptr(), ws.data_ptr(), ws.numel()
+
+    def owner_of(b):
+        return b % world
+
+    def bcast(buf, owner):
         if world > 1:
             dist.broadcast(buf, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
-        if rank != owner:
-            _lib.check(lib.hps_lu_dist_unpack(st, n, D.data_ptr(), n, b, ws.data_ptr(), ws.numel(), buf.data_ptr()),
-                       "hps_lu_dist_unpack")
-        # block columns > b owned by this rank: rank, rank + world, ...
-        first = b + 1 + ((rank - (b + 1)) % world)
+
+    side.wait_stream(main)  # D, S_r, g are ready
+    with torch.cuda.stream(side):
+        if rank == owner_of(0):
+            _lib.check(lib.hps_lu_dist_factor_pack(side.cuda_stream, n, A, n, 0, wsp, wsn, info.data_ptr(),
+                                                   bufs[0].data_ptr()), "hps_lu_dist_factor_pack")
+        bcast(bufs[0], owner_of(0))
+        if rank != owner_of(0):
+            _lib.check(lib.hps_lu_dist_unpack(side.cuda_stream, n, A, n, 0, wsp, wsn, bufs[0].data_ptr()), "hps_lu_dist_unpack")
+        ev_panel[0].record(side)
+    for b in range(nblk):
+        nb1 = b + 1
+        i_own_next = nb1 < nblk and rank == owner_of(nb1)
+        if nb1 < nblk:
+            with torch.cuda.stream(side):
+                buf = bufs[nb1 & 1]
+                if i_own_next:
+                    if b >= 1:
+                        side.wait_event(ev_upd[(b - 1) & 1])  # column nb1 has received blocks < b on the main stream
+                    _lib.check(lib.hps_lu_dist_update(side.cuda_stream, n, A, n, b, nb1, 1, 1, 0, wsp, wsn),
+                               "hps_lu_dist_update (look-ahead)")
+                    _lib.check(lib.hps_lu_dist_factor_pack(side.cuda_stream, n, A, n, nb1, wsp, wsn, info.data_ptr(),
+                                                           buf.data_ptr()), "hps_lu_dist_factor_pack")
+                bcast(buf, owner_of(nb1))
+                if not i_own_next:
+                    _lib.check(lib.hps_lu_dist_unpack(side.cuda_stream, n, A, n, nb1, wsp, wsn, buf.data_ptr()),
+                               "hps_lu_dist_unpack")
+                ev_panel[nb1 & 1].record(side)
+        # main stream: block b applied to this rank's remaining block columns (+ the left interchanges)
+        main.wait_event(ev_panel[b & 1])
+        start = nb1 + 1 if i_own_next else nb1
+        first = start + ((rank - start) % world)
         n_own = 0 if first >= nblk else (nblk - 1 - first) // world + 1
-        _lib.check(lib.hps_lu_dist_update(st, n, D.data_ptr(), n, b, first, n_own, world, ws.data_ptr(), ws.numel()),
+        _lib.check(lib.hps_lu_dist_update(main.cuda_stream, n, A, n, b, first, n_own, world, 1, wsp, wsn),
                    "hps_lu_dist_update")
+        ev_upd[b & 1].record(main)
+    main.wait_stream(side)
+    st = main.cuda_stream
     if world > 1:
         dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
     _lib.check_info(info, "distributed root factorisation")

@@ -44,7 +44,7 @@ _SIGNATURES = {
     "hps_lu_dist_buffer_doubles": (_i, [_i, ctypes.POINTER(_sz)]),
     "hps_lu_dist_factor_pack": (_i, [_p, _i, _p, _l, _i, _p, _sz, _p, _p]),
     "hps_lu_dist_unpack": (_i, [_p, _i, _p, _l, _i, _p, _sz, _p]),
-    "hps_lu_dist_update": (_i, [_p, _i, _p, _l, _i, _i, _i, _i, _p, _sz]),
+    "hps_lu_dist_update": (_i, [_p, _i, _p, _l, _i, _i, _i, _i, _i, _p, _sz]),
     "hps_lu_dist_solve": (_i, [_p, _i, _p, _l, _i, ctypes.POINTER(_p), ctypes.POINTER(_l), ctypes.POINTER(_i), _p, _sz]),
     "hps_down_oct_scatter": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "hps_merge_quad_dtn_level_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),

@@ -171,8 +171,9 @@ int hps_lu_dist_unpack(void* stream, int n, double* A, int64_t lda, int b, void*
   return lu_dist_unpack(static_cast<cudaStream_t>(stream), n, A, lda, b, ws, ws_bytes, buf);
 }
 int hps_lu_dist_update(void* stream, int n, double* A, int64_t lda, int b, int first_block, int n_blocks,
-                       int block_stride, void* ws, size_t ws_bytes) {
-  return lu_dist_update(static_cast<cudaStream_t>(stream), n, A, lda, b, first_block, n_blocks, block_stride, ws, ws_bytes);
+                       int block_stride, int apply_left, void* ws, size_t ws_bytes) {
+  return lu_dist_update(static_cast<cudaStream_t>(stream), n, A, lda, b, first_block, n_blocks, block_stride, apply_left, ws,
+                        ws_bytes);
 }
 int hps_lu_dist_solve(void* stream, int n, double* A, int64_t lda, int n_rhs, double* const* rhs, const int64_t* ld_rhs,
                       const int* ncols, void* ws, size_t ws_bytes) {

@@ -90,7 +90,7 @@ int lu_dist_factor_pack(cudaStream_t st, int n, double* A, int64_t lda, int b, v
                         double* buf);
 int lu_dist_unpack(cudaStream_t st, int n, double* A, int64_t lda, int b, void* ws, size_t ws_bytes, const double* buf);
 int lu_dist_update(cudaStream_t st, int n, double* A, int64_t lda, int b, int first_block, int n_blocks,
-                   int block_stride, void* ws, size_t ws_bytes);
+                   int block_stride, int apply_left, void* ws, size_t ws_bytes);
 int lu_dist_solve(cudaStream_t st, int n, double* A, int64_t lda, int n_rhs, const RhsDesc* rhs, void* ws,
                   size_t ws_bytes);
 

@@ -743,12 +743,12 @@ int lu_dist_unpack(cudaStream_t st, int n, double* A, int64_t lda, int b, void* 
 // every rank: apply block column b to the block columns first_block + i*block_stride (i < n_blocks,
 // all > b) that it owns, and its interchanges to the columns on the left
 int lu_dist_update(cudaStream_t st, int n, double* A, int64_t lda, int b, int first_block, int n_blocks,
-                   int block_stride, void* ws, size_t ws_bytes) {
+                   int block_stride, int apply_left, void* ws, size_t ws_bytes) {
   LuWorkspace w;
   HPS_TRY(dist_setup(ws, ws_bytes, n, w));
   const int j = b * NB, jb = min(NB, n - j);
   const Mat Am{A, lda, 0};
-  HPS_TRY(laswp(st, 1, A, lda, 0, 0, j, w.ipiv, n, j, j + jb));  // L in LAPACK form
+  if (apply_left) HPS_TRY(laswp(st, 1, A, lda, 0, 0, j, w.ipiv, n, j, j + jb));  // L in LAPACK form
   if (n_blocks <= 0) return 0;
   if (first_block <= b) return fail_arg(6, "owned blocks must lie to the right of b");
   const double* Linv = w.Linv + (int64_t)b * NB * NB;
