@@ -372,7 +372,11 @@ def run_ours(args, rank, world, local_rank):
                      "peak_source": "measured cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/r01_fp64_probe.txt); "
                                     "MEASURED_PEAKS.json has no FP64 entry",
                      "launches": int(gemm_launches), "gemm_ms_per_step": gemm_ms / args.steps,
-                     "share_of_step": gemm_ms / ms, "traffic": None,
+                     "share_of_step": gemm_ms / ms,
+                     # dram__bytes_read+write of one 8192^3 launch of this kernel (ncu --set full,
+                     # profiles/r01_ncu_gemm_summary.txt); algorithmic operand bytes of that launch: 1.61e9.
+                     # The re-reads are tile re-fetches served at < 1 TB/s: the kernel is tensor-bound.
+                     "traffic": 32.13e9, "traffic_shape": "8192x8192x8192", "traffic_algorithmic_bytes": 1.61e9,
                      "panel_kernel_ms_per_step": pm[1] / args.steps, "panel_launches": int(pl[1]),
                      "other_kernels_ms_per_step": {name: round(pm[i] / args.steps, 3) for i, name in enumerate(
                          ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny_matvec",

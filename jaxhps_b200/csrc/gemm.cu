@@ -171,10 +171,12 @@ int dgemm(cudaStream_t st, int M, int N, int K, double alpha, const double* A, i
   if (N < 16) {
     return dgemm_skinny(st, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, C, ldc, sC, batch);
   }
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};  // cudaFuncSetAttribute is per device
+  int dev = 0;
+  HPS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
     HPS_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    configured = true;
+    configured[dev] = true;
   }
   GemmArgs g;
   g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;

@@ -461,6 +461,21 @@ int laswp(cudaStream_t st, int batch, double* A, int64_t lda, int64_t sA, int c0
   return 0;
 }
 
+// opt the large-shared-memory kernels in, once per device
+int configure_lu_kernels() {
+  static bool configured[64] = {};
+  int dev = 0;
+  HPS_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || configured[dev]) return 0;
+    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
+  configured[dev] = true;
+  return 0;
+}
+
 // X := Tinv * X for a jb-row block X (in place).  Wide X goes through the DMMA GEMM (one tile
 // row, so in-place is safe); narrow X is staged through tmp because the row-per-warp kernel
 // would read rows other warps have already overwritten.
@@ -605,15 +620,7 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
   LuWorkspace w;
   if (!carve(ar, batch, n, w)) return fail_arg(11, "lu_solve: workspace too small");
 
-  static bool configured = false;
-  if (!configured) {
-    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
-    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
-    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
-    HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
-    HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
-    configured = true;
-  }
+  HPS_TRY(configure_lu_kernels());
   Aux* aux = nullptr;
   HPS_TRY(get_aux(aux));
   cudaStream_t s0 = st, s1 = aux->stream;
@@ -700,15 +707,7 @@ size_t lu_dist_block_buffer_doubles(int n) { return (size_t)n * NB + NB + (size_
 static int dist_setup(void* ws, size_t ws_bytes, int n, LuWorkspace& w) {
   Arena ar(ws, ws_bytes);
   if (!carve(ar, 1, n, w)) return fail_arg(5, "lu_dist: workspace too small");
-  static bool configured = false;
-  if (!configured) {
-    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
-    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
-    HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
-    HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
-    HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
-    configured = true;
-  }
+  HPS_TRY(configure_lu_kernels());
   return 0;
 }
 
