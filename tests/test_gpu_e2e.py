@@ -161,3 +161,31 @@ def test_source_at_solve_time_matches_oracle(iti, p, q, L, nsrc):
     v, gl = up(src, ref_pb)
     uo = dn(g_in, S, gl, Y, v)
     assert u.shape == uo.shape and rel(u, uo) < tol
+
+
+@pytest.mark.parametrize("iti", [False, True])
+def test_subtree_recomputation_matches_plain_build_and_solve(iti):
+    """solve_subtree / upward_pass_subtree + downward_pass_subtree (reference `_subtree_recomp.py`) give
+    the same solution as build_solver + solve (2D uniform, DtN and ItI)."""
+    rng = np.random.default_rng(9)
+    k = 3.0
+    dom = hps.Domain(8, 6, hps.DiscretizationNode2D(-1.0, 1.0, -1.0, 1.0), 3)
+    shp = dom.interior_points[..., 0].shape
+    co = {"D_xx_coefficients": np.ones(shp), "D_yy_coefficients": np.ones(shp),
+          "I_coefficients": k**2 * (1 + 0.3 * rng.normal(size=shp))}
+    extra = dict(use_ItI=True, eta=k) if iti else {}
+    src = rng.normal(size=shp) + (1j * rng.normal(size=shp) if iti else 0)
+    nb = dom.boundary_points.shape[0]
+    g = rng.normal(size=nb) + (1j * rng.normal(size=nb) if iti else 0)
+    pb = hps.PDEProblem(dom, source=src, **co, **extra)
+    T_plain = hps.build_solver(pb, return_top_T=True)
+    u_plain = hps.solve(pb, g)
+    pb2 = hps.PDEProblem(dom, source=src, **co, **extra)
+    u_sub = hps.solve_subtree(pb2, g, subtree_height=1)
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()  # noqa: E731
+    assert rel(u_sub, u_plain) < 1e-10
+    pb3 = hps.PDEProblem(dom, source=src, **co, **extra)
+    T_top = hps.upward_pass_subtree(pb3, subtree_height=2)
+    assert rel(T_top, T_plain) < 1e-10 and len(pb3.S_lst) == 1
+    u_two = hps.downward_pass_subtree(pb3, g, subtree_height=2)
+    assert rel(u_two, u_plain) < 1e-10
