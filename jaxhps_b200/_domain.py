@@ -1,14 +1,22 @@
 """``Domain``: discretisation parameters plus the leaf / boundary point clouds.
 
-API mirror of `src/jaxhps/_domain.py:38-97` for uniform trees (``L`` given).  Adaptive
-construction (``L=None`` / ``from_adaptive_discretization``) belongs to SURVEY §8(f) and is
-not built yet; it raises ``NotImplementedError`` instead of silently mis-behaving.
+API mirror of `src/jaxhps/_domain.py:38-434`: uniform trees (``L`` given) and adaptive trees
+(``L=None``; ``from_adaptive_discretization`` builds one from a function and a tolerance).
 """
 from __future__ import annotations
 
 import numpy as np
 
+from ._adaptive_discretization import (
+    generate_adaptive_mesh_level_restriction_2D,
+    generate_adaptive_mesh_level_restriction_3D,
+)
 from ._grid import (
+    compute_boundary_Gauss_points_adaptive_2D,
+    compute_boundary_Gauss_points_adaptive_3D,
+    compute_interior_Chebyshev_points_adaptive_2D,
+    compute_interior_Chebyshev_points_adaptive_3D,
+    leaf_bounds,
     compute_boundary_Gauss_points_uniform_2D,
     compute_boundary_Gauss_points_uniform_3D,
     compute_interior_Chebyshev_points_uniform_2D,
@@ -16,7 +24,7 @@ from ._grid import (
 )
 from ._grid import uniform_leaf_bounds_2D, uniform_leaf_bounds_3D
 from ._interpolation_methods import interp_from_hps_2D, interp_from_hps_3D, interp_to_hps_2D, interp_to_hps_3D
-from ._tree import DiscretizationNode2D, DiscretizationNode3D
+from ._tree import DiscretizationNode2D, DiscretizationNode3D, get_all_leaves
 
 
 class Domain:
@@ -29,10 +37,16 @@ class Domain:
         if not self.bool_2D and not isinstance(root, DiscretizationNode3D):
             raise TypeError("root must be a DiscretizationNode2D or DiscretizationNode3D")
         if L is None:
-            raise NotImplementedError(
-                "adaptive discretisations (L=None) are outside the hot path built so far "
-                "(SURVEY §8(f) item 2); pass the number of uniform refinement levels L"
-            )
+            # adaptive tree: whatever leaves `root` currently has (`_domain.py:82-97`)
+            self.bool_uniform = False
+            self.n_leaves = len(get_all_leaves(root))
+            if self.bool_2D:
+                self.interior_points = compute_interior_Chebyshev_points_adaptive_2D(root, p)
+                self.boundary_points = compute_boundary_Gauss_points_adaptive_2D(root, q)
+            else:
+                self.interior_points = compute_interior_Chebyshev_points_adaptive_3D(root, p)
+                self.boundary_points = compute_boundary_Gauss_points_adaptive_3D(root, q)
+            return
         self.bool_uniform = True
         if self.bool_2D:
             #: (n_leaves, p^2, 2)
@@ -48,6 +62,8 @@ class Domain:
             self.n_leaves = 8**L
 
     def _leaf_bounds(self) -> np.ndarray:
+        if not self.bool_uniform:
+            return leaf_bounds(self.root)
         fn = uniform_leaf_bounds_2D if self.bool_2D else uniform_leaf_bounds_3D
         return fn(self.root, self.L)
 
@@ -75,8 +91,26 @@ class Domain:
         assert eval_points_z is not None
         return interp_from_hps_3D(self._leaf_bounds(), self.p, samples, eval_points_x, eval_points_y, eval_points_z)
 
+    def get_adaptive_boundary_data_lst(self, f) -> list:
+        """Evaluate ``f`` ([..., d] -> [...]) on the boundary points, one array per side (2D: S,E,N,W)
+        or face (3D: x-,x+,y-,y+,z-,z+) — the input format of the adaptive down pass
+        (`_domain.py:296-365`)."""
+        b, r = self.boundary_points, self.root
+        if self.bool_2D:
+            masks = [b[:, 1] == r.ymin, b[:, 0] == r.xmax, b[:, 1] == r.ymax, b[:, 0] == r.xmin]
+        else:
+            masks = [b[:, 0] == r.xmin, b[:, 0] == r.xmax, b[:, 1] == r.ymin, b[:, 1] == r.ymax,
+                     b[:, 2] == r.zmin, b[:, 2] == r.zmax]
+        return [np.asarray(f(b[m])) for m in masks]
+
     @classmethod
-    def from_adaptive_discretization(cls, *args, **kwargs):
-        raise NotImplementedError(
-            "adaptive mesh generation is out of scope for the hot path (SURVEY §2, §8(f))"
-        )
+    def from_adaptive_discretization(cls, p: int, q: int, root, f, tol: float, use_level_restriction: bool = True,
+                                     use_l_2_norm: bool = False) -> "Domain":
+        """Refine ``root`` until ``f`` (one callable or a list, [..., d] -> [...]) is resolved to ``tol``
+        in the relative L_inf (default) or L_2 sense, then build the Domain (`_domain.py:367-434`)."""
+        fns = f if isinstance(f, list) else [f]
+        gen = (generate_adaptive_mesh_level_restriction_2D if isinstance(root, DiscretizationNode2D)
+               else generate_adaptive_mesh_level_restriction_3D)
+        for fn in fns:
+            gen(root=root, f_fn=fn, tol=tol, p=p, q=q, restrict_bool=use_level_restriction, l2_norm=use_l_2_norm)
+        return cls(p=p, q=q, root=root)

@@ -215,3 +215,69 @@ def compute_boundary_Gauss_points_uniform_3D(root, L: int, q: int) -> np.ndarray
             np.column_stack([xy, col(root.zmax)]),
         ]
     )
+
+
+# ------------------------------------------------------------------ adaptive trees
+
+
+def leaf_bounds(root) -> np.ndarray:
+    """(n_leaves, 2d) ``[xmin, xmax, ymin, ymax(, zmin, zmax)]`` of the leaves in depth-first order."""
+    from ._tree import _bounds, get_all_leaves
+
+    return np.array([[v for lim in _bounds(leaf) for v in lim] for leaf in get_all_leaves(root)], dtype=np.float64)
+
+
+def compute_interior_Chebyshev_points_adaptive_2D(root, p: int) -> np.ndarray:
+    """(n_leaves, p^2, 2) (`_grid_creation_2D.py:128-137`)."""
+    return bounds_to_cheby_points_2D(leaf_bounds(root), p)
+
+
+def compute_interior_Chebyshev_points_adaptive_3D(root, p: int) -> np.ndarray:
+    """(n_leaves, p^3, 3) (`_grid_creation_3D.py:238-253`)."""
+    return bounds_to_cheby_points_3D(leaf_bounds(root), p)
+
+
+def compute_boundary_Gauss_points_adaptive_2D(root, q: int) -> np.ndarray:
+    """Gauss points of the leaf sides on the domain boundary, counter-clockwise from the SW corner
+    (`_grid_creation_2D.py:142-200`)."""
+    from ._tree import get_ordered_lst_of_boundary_nodes
+
+    g = gauss_points(q)
+    S, E, N, W = get_ordered_lst_of_boundary_nodes(root)
+    cat = lambda parts: np.concatenate(parts) if parts else np.zeros(0)  # noqa: E731
+    xs = cat([affine_transform(g, (n.xmin, n.xmax)) for n in S])
+    ye = cat([affine_transform(g, (n.ymin, n.ymax)) for n in E])
+    xn = cat([affine_transform(g, (n.xmax, n.xmin)) for n in N])
+    yw = cat([affine_transform(g, (n.ymax, n.ymin)) for n in W])
+    return np.concatenate(
+        [
+            np.column_stack([xs, np.full(xs.shape[0], float(root.ymin))]),
+            np.column_stack([np.full(ye.shape[0], float(root.xmax)), ye]),
+            np.column_stack([xn, np.full(xn.shape[0], float(root.ymax))]),
+            np.column_stack([np.full(yw.shape[0], float(root.xmin)), yw]),
+        ]
+    )
+
+
+def compute_boundary_Gauss_points_adaptive_3D(root, q: int) -> np.ndarray:
+    """Gauss points of the leaf faces on the domain boundary, face by face (x-,x+,y-,y+,z-,z+), each
+    leaf face a q x q tensor grid with its first free coordinate slowest (`_grid_creation_3D.py:256-373`)."""
+    from ._tree import get_ordered_lst_of_boundary_nodes
+
+    faces = get_ordered_lst_of_boundary_nodes(root)
+    fixed = [root.xmin, root.xmax, root.ymin, root.ymax, root.zmin, root.zmax]
+    out = []
+    for f, leaves in enumerate(faces):
+        ax = f // 2
+        if ax == 0:
+            b = [[n.ymin, n.ymax, n.zmin, n.zmax] for n in leaves]
+        elif ax == 1:
+            b = [[n.xmin, n.xmax, n.zmin, n.zmax] for n in leaves]
+        else:
+            b = [[n.xmin, n.xmax, n.ymin, n.ymax] for n in leaves]
+        uv = _gauss_panels_2D(np.array(b, dtype=np.float64), q)
+        w = np.full(uv.shape[0], float(fixed[f]))
+        cols = [uv[:, 0], uv[:, 1]]
+        cols.insert(ax, w)
+        out.append(np.column_stack(cols))
+    return np.concatenate(out)

@@ -22,6 +22,7 @@ from .quadrature import (
     affine_transform,
     barycentric_lagrange_interpolation_matrix_1D,
     barycentric_lagrange_interpolation_matrix_2D,
+    barycentric_lagrange_interpolation_matrix_3D,
     chebyshev_points,
     differentiation_matrix_1D,
     gauss_points,
@@ -168,3 +169,58 @@ def precompute_Q_3D_DtN(p: int, q: int, du_dx, du_dy, du_dz) -> np.ndarray:
     faces = face_cheby_indices_3D(p)
     normal = [(-1.0, du_dx), (1.0, du_dx), (-1.0, du_dy), (1.0, du_dy), (-1.0, du_dz), (1.0, du_dz)]
     return np.concatenate([Q2 @ (s * D[faces[f]]) for f, (s, D) in enumerate(normal)], axis=0)
+
+
+# ------------------------------------------------------------------ adaptive discretisations
+
+
+def precompute_projection_ops_3D(q: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Refine (4q^2 x q^2) and coarsen (q^2 x 4q^2) maps between one Gauss face panel and its four
+    quarter panels A,B,C,D (quad order SW,SE,NE,NW in the face's two free coordinates).  The
+    coarsening map is *not* an interpolant of all four panels: each coarse Gauss point is evaluated
+    from the polynomial of the quarter panel that contains it (`_precompute_operators_3D.py:323-409`)."""
+    if q % 2:
+        raise ValueError("q must be even.")
+    g = gauss_points(q)
+    lo, hi = affine_transform(g, (-1.0, 0.0)), affine_transform(g, (0.0, 1.0))
+    quarter = ((lo, lo), (hi, lo), (hi, hi), (lo, hi))  # (first coordinate, second coordinate)
+    L_4f1 = np.concatenate([barycentric_lagrange_interpolation_matrix_2D(g, g, a, b) for a, b in quarter], axis=0)
+    h = q // 2
+    i, j = np.divmod(np.arange(q * q), q)  # coarse point = (first coordinate index, second)
+    L_1f4 = np.zeros((q * q, 4 * q * q))
+    for k, (a, b) in enumerate(quarter):
+        rows = ((i >= h) if a is hi else (i < h)) & ((j >= h) if b is hi else (j < h))
+        ga, gb = (g[h:] if a is hi else g[:h]), (g[h:] if b is hi else g[:h])
+        L_1f4[rows, k * q * q : (k + 1) * q * q] = barycentric_lagrange_interpolation_matrix_2D(a, b, ga, gb)
+    return L_4f1, L_1f4
+
+
+def precompute_L_4f1(p: int) -> np.ndarray:
+    """(4p^2, p^2) interpolation from a leaf's Chebyshev cloud to the clouds of its four children
+    a..d, all in the boundary-first leaf ordering (`_precompute_operators_2D.py:303-379`)."""
+    c = chebyshev_points(p)
+    fine = np.concatenate([affine_transform(c, (-1.0, 0.0)), affine_transform(c, (0.0, 1.0))])
+    M = barycentric_lagrange_interpolation_matrix_2D(c, c, fine, fine)
+    r = rearrange_indices_ext_int_2D(p)
+    ix, iy = np.divmod(np.arange(4 * p * p), 2 * p)
+    # the leaf grid runs north -> south in its fast index (`_grid_creation_2D.py:53-68`)
+    blocks = [(ix < p) & (iy >= p), (ix >= p) & (iy >= p), (ix >= p) & (iy < p), (ix < p) & (iy < p)]
+    rows = np.concatenate([np.flatnonzero(b)[r] for b in blocks])
+    return M[rows][:, r]
+
+
+def precompute_L_8f1(p: int) -> np.ndarray:
+    """(8p^3, p^3) interpolation from a leaf's Chebyshev cloud to those of its eight children a..h
+    (`_precompute_operators_3D.py:412-550`)."""
+    c = chebyshev_points(p)
+    fine = np.concatenate([affine_transform(c, (-1.0, 0.0)), affine_transform(c, (0.0, 1.0))])
+    M = barycentric_lagrange_interpolation_matrix_3D(c, c, c, fine, fine, fine)
+    r = rearrange_indices_ext_int_3D(p)
+    ii = np.arange(8 * p**3)
+    ix, iy, iz = ii // (4 * p * p), (ii // (2 * p)) % (2 * p), ii % (2 * p)
+    blocks = []
+    for zhi in (True, False):  # a..d sit at z+, e..h at z-
+        for xhi, yhi in ((False, False), (True, False), (True, True), (False, True)):
+            blocks.append(((ix >= p) == xhi) & ((iy >= p) == yhi) & ((iz >= p) == zhi))
+    rows = np.concatenate([np.flatnonzero(b)[r] for b in blocks])
+    return M[rows][:, r]

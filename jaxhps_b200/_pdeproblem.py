@@ -27,10 +27,12 @@ from ._operators import (
     precompute_Q_2D_DtN,
     precompute_Q_3D_DtN,
     precompute_QH_2D_ItI,
+    precompute_projection_ops_2D,
+    precompute_projection_ops_3D,
     scaled_diff_matrix_1D,
 )
 from ._grid import rearrange_indices_ext_int_3D
-from ._tree import DiscretizationNode3D
+from ._tree import DiscretizationNode3D, get_all_leaves
 
 _COEFF_NAMES = (
     "D_xx_coefficients",
@@ -120,8 +122,13 @@ class PDEProblem:
         self.use_ItI = bool(use_ItI)
         self.eta = eta
 
-        # uniform trees: every leaf has the same side, scale once (`_pdeproblem.py:129-138`)
-        self.half_side_len = (domain.root.xmax - domain.root.xmin) / (2 ** (domain.L + 1))
+        if domain.bool_uniform:
+            # uniform trees: every leaf has the same side, scale once (`_pdeproblem.py:129-138`)
+            self.half_side_len = (domain.root.xmax - domain.root.xmin) / (2 ** (domain.L + 1))
+        else:
+            # adaptive trees: unit-scaled operators + per-leaf side lengths (`_pdeproblem.py:139-145`)
+            self.half_side_len = 1.0
+            self.sidelens = np.array([leaf.xmax - leaf.xmin for leaf in get_all_leaves(domain.root)], dtype=np.float64)
         p, q = domain.p, domain.q
         #: scaled 1-D Chebyshev differentiation matrix (p, p); input of the CUDA leaf kernel
         self.D1 = scaled_diff_matrix_1D(p, self.half_side_len)
@@ -137,6 +144,8 @@ class PDEProblem:
                 self.P = precompute_P_2D_ItI(p, q)
                 self.G = precompute_G_2D_ItI(precompute_N_tilde_matrix_2D(self.D_x, self.D_y, p), eta)
                 self.QH = precompute_QH_2D_ItI(precompute_N_matrix_2D(self.D_x, self.D_y, p), p, q, eta)
+            if not domain.bool_uniform:
+                self.L_2f1, self.L_1f2 = precompute_projection_ops_2D(q)
         else:
             r = rearrange_indices_ext_int_3D(p)
             eye = np.eye(p)
@@ -146,6 +155,8 @@ class PDEProblem:
             self.D_z = np.kron(eye, np.kron(eye, self.D1))[ix]
             self.P = precompute_P_3D_DtN(p, q)
             self.Q = precompute_Q_3D_DtN(p, q, self.D_x, self.D_y, self.D_z)
+            if not domain.bool_uniform:
+                self.L_4f1, self.L_1f4 = precompute_projection_ops_3D(q)
 
         self.reset()
 
@@ -197,4 +208,6 @@ def _get_PDEProblem_chunk(pde_problem: PDEProblem, start_idx: int, end_idx: int)
     for name in _COEFF_NAMES + ("source",):
         val = getattr(pde_problem, name)
         setattr(new, name, None if val is None else val[start_idx:end_idx])
+    if not pde_problem.domain.bool_uniform:
+        new.sidelens = pde_problem.sidelens[start_idx:end_idx]
     return new
