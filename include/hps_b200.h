@@ -233,6 +233,45 @@ int hps_down_quad_level(void* stream, int n_nodes, int m, int n_src, const doubl
 int hps_leaf_apply(void* stream, int n_leaves, int n_c, int n_g, int n_src,
                    const double* Y, const double* g, const double* v, double* u);
 
+/* ---- adaptive (non-uniform) trees, ONE NODE per call ---------------------------------------
+ * reference: merge/_adaptive_3D_DtN.py:150-347 + merge/_utils_adaptive_3D_DtN.py:179-881,
+ * merge/_adaptive_2D_DtN.py:160-433 + merge/_utils_adaptive_2D_DtN.py:168-584,
+ * down_pass/_adaptive_3D_DtN.py:132-394, down_pass/_adaptive_2D_DtN.py:87-259.
+ * Boundary vectors are sequences of leaf-face panels of npp = q^(dim-1) Gauss points; all index
+ * tables are int32 DEVICE arrays at panel granularity, compiled on the host from the tree.
+ * group = 2^(dim-1) fine panels face one coarse panel across a level jump.
+ *
+ * hps_adaptive_compress: T (n x n), h (n x n_src) of a child -> interface-ready T' (n' x n'), h',
+ *   n' = n_out_panels * npp.  seg_tbl[P] = {start, width, rev}: panel P of T' is panel-run
+ *   [start, start + width*npp) of T (width 1: copied; width group: rows coarsened with
+ *   L_coarsen (npp x group*npp), columns with L_refine (group*npp x npp)); rev != 0 walks the run
+ *   backwards.  Replaces _compress_rows_from_lst / _compress_cols_from_lst and the index gathers of
+ *   get_{a..h}_submatrices / get_quadmerge_blocks_{a..d}. */
+int hps_adaptive_compress_workspace(int n, int n_out_panels, int npp, size_t* bytes);
+int hps_adaptive_compress(void* stream, int npp, int group, int n_src, int n, const double* T, const double* h,
+                          int n_out_panels, const int* seg_tbl, const double* L_refine, const double* L_coarsen,
+                          double* T_out, double* h_out, void* ws, size_t ws_bytes);
+/* hps_merge_adaptive: merge the n_child (4 or 8) children of one node.  T_child/h_child/ld_child are
+ * HOST arrays (device pointers to each child's interface-ready operator, its h, its order).
+ * int_tbl[I] = {child A, panel in A, child B, panel in B} for interface panel I (n_int = NI*npp);
+ * ext_tbl[E] = {child, panel} for exterior panel E in the parent's boundary order (n_ext = NE*npp).
+ * Outputs: S (n_int x n_ext), g_tilde (n_int x n_src), and if want_T: T_out (n_ext x n_ext),
+ * h_out (n_ext x n_src).  Replaces _oct_merge / _adaptive_quad_merge_2D_DtN +
+ * assemble_merge_outputs_DtN (merge/_schur_complement.py:117-237). */
+int hps_merge_adaptive_workspace(int n_int, int n_ext, size_t* bytes);
+int hps_merge_adaptive(void* stream, int npp, int n_src, int n_child, const double* const* T_child,
+                       const double* const* h_child, const int* ld_child, int n_int_panels, const int* int_tbl,
+                       int n_ext_panels, const int* ext_tbl, double* S, double* g_tilde, double* T_out, double* h_out,
+                       int want_T, void* ws, size_t ws_bytes, int* info);
+/* hps_down_adaptive: g_int = S g_ext + g_tilde, then every child's boundary vector.  g_child: HOST
+ * array of n_child device pointers; tbl[t] = {child, source panel, start, width, rev}: the run
+ * [start, start + width*npp) of that child's vector comes from source panel sp (sp < NE: exterior
+ * panel of g_ext, else interface panel sp - NE of g_int), re-refined with L_refine when width > 1.
+ * ws: n_int * n_src doubles.  Replaces _propagate_down_oct / _propogate_down_quad. */
+int hps_down_adaptive(void* stream, int npp, int n_src, int n_int, int n_ext, const double* S, const double* g_ext,
+                      const double* g_tilde, int n_child, double* const* g_child, int n_tbl, const int* tbl,
+                      const double* L_refine, void* ws);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,259 @@
+// Merges and down-pass steps of NON-UNIFORM (adaptive) trees, one node per call.
+//
+// Reference: merge/_adaptive_3D_DtN.py:150-347 + merge/_utils_adaptive_3D_DtN.py:179-881 (oct),
+// merge/_adaptive_2D_DtN.py:160-433 + merge/_utils_adaptive_2D_DtN.py:168-584 (quad),
+// down_pass/_adaptive_3D_DtN.py:132-394, down_pass/_adaptive_2D_DtN.py:87-259.
+//
+// Every boundary vector of every node is a sequence of leaf-face PANELS of npp = q^(d-1) Gauss
+// points, so all index maps are kept at panel granularity: the host (jaxhps_b200/_adaptive_plan.py)
+// compiles, per node, three small integer tables and the kernels below expand them on the fly.
+//   * seg table of a child: panel P of the child's "interface-ready" operator T' is either one
+//     panel of T (width 1) or a run of `group` = 2^(d-1) panels that is coarsened with L_1f4/L_4f1
+//     (width group); `rev` walks the run backwards (2D interfaces are traversed in opposite
+//     directions by the two children that share them).
+//   * interface table: for interface panel I the two owners (child, panel of T').
+//   * exterior table: for exterior panel E of the parent its owner (child, panel of T').
+// With those, D, -C, B, A, h_int and h_ext are produced by ONE gather kernel straight in the
+// parent's boundary order (the reference assembles region-ordered blocks and permutes T twice).
+// S = D^-1(-C), g~ = D^-1(-h_int) come from the pivoted LU of lu.cu; T = A + B S from the DMMA GEMM.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace hps {
+
+namespace {
+
+constexpr int MAXC = 8;
+
+struct ChildSet {
+  const double* T[MAXC];
+  const double* h[MAXC];
+  int ld[MAXC];
+};
+
+struct ChildOut {
+  double* g[MAXC];
+};
+
+__device__ __forceinline__ int seg_index(int start, int len, int rev, int j) { return rev ? start + len - 1 - j : start + j; }
+
+// tmp[r, P*npp + k] = T[r, seg_P(k)]                       (width 1)
+//                   = sum_j T[r, seg_P(j)] * Lr[j, k]      (coarsened run; Lr is (group*npp) x npp)
+// grid: (output panels, row tiles); block 256
+__global__ void __launch_bounds__(256) compress_cols_kernel(const double* __restrict__ T, int n, int npp, int group,
+                                                            const int* __restrict__ seg, const double* __restrict__ Lr,
+                                                            double* __restrict__ out, int n_out) {
+  const int P = blockIdx.x;
+  const int start = seg[3 * P], width = seg[3 * P + 1], rev = seg[3 * P + 2];
+  const int len = width * npp;
+  const int rows_per_block = max(1, 256 / npp);
+  for (int r0 = blockIdx.y * rows_per_block; r0 < n; r0 += gridDim.y * rows_per_block) {
+    for (int e = threadIdx.x; e < rows_per_block * npp; e += blockDim.x) {
+      const int r = r0 + e / npp, k = e % npp;
+      if (r >= n) continue;
+      const double* row = T + (int64_t)r * n;
+      double v;
+      if (width == 1) {
+        v = row[seg_index(start, len, rev, k)];
+      } else {
+        v = 0.0;
+        for (int j = 0; j < len; ++j) v += row[seg_index(start, len, rev, j)] * Lr[(int64_t)j * npp + k];
+      }
+      out[(int64_t)r * n_out + (int64_t)P * npp + k] = v;
+    }
+  }
+}
+
+// out[P*npp + k, c] = in[seg_P(k), c]                       (width 1)
+//                   = sum_j Lc[k, j] * in[seg_P(j), c]      (Lc is npp x (group*npp))
+// grid: (column tiles, output panels); block 256
+__global__ void __launch_bounds__(256) compress_rows_kernel(const double* __restrict__ in, int ncols, int npp, int group,
+                                                            const int* __restrict__ seg, const double* __restrict__ Lc,
+                                                            double* __restrict__ out) {
+  const int P = blockIdx.y;
+  const int start = seg[3 * P], width = seg[3 * P + 1], rev = seg[3 * P + 2];
+  const int len = width * npp;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x) {
+    for (int k = 0; k < npp; ++k) {
+      double v;
+      if (width == 1) {
+        v = in[(int64_t)seg_index(start, len, rev, k) * ncols + c];
+      } else {
+        v = 0.0;
+        for (int j = 0; j < len; ++j) v += Lc[(int64_t)k * len + j] * in[(int64_t)seg_index(start, len, rev, j) * ncols + c];
+      }
+      out[((int64_t)P * npp + k) * ncols + c] = v;
+    }
+  }
+}
+
+// One pass over the (n_int + n_ext) x (n_int + n_ext + n_src) block system of a merge:
+//   [ D   -S | -g~ ]        rows: interface panels, then exterior panels (parent order)
+//   [ B    A | h_ext ]
+// An entry couples two panels only through a child that owns both.
+__global__ void __launch_bounds__(256) adaptive_gather_kernel(ChildSet cs, int npp, int n_src, int NI, int NE,
+                                                              const int* __restrict__ int_tbl,
+                                                              const int* __restrict__ ext_tbl, double* __restrict__ D,
+                                                              double* __restrict__ S, double* __restrict__ gt,
+                                                              double* __restrict__ T_out, double* __restrict__ h_out,
+                                                              double* __restrict__ B, int want_T) {
+  const int n_int = NI * npp, n_ext = NE * npp;
+  const int n_rows = want_T ? n_int + n_ext : n_int;
+  const int n_cols = n_int + n_ext + n_src;
+  for (int row = blockIdx.y; row < n_rows; row += gridDim.y) {
+    const bool irow = row < n_int;
+    const int rl = irow ? row : row - n_int;
+    const int P = rl / npp, rr = rl - P * npp;
+    int c0, p0, c1 = -1, p1 = 0;
+    if (irow) {
+      c0 = int_tbl[4 * P], p0 = int_tbl[4 * P + 1], c1 = int_tbl[4 * P + 2], p1 = int_tbl[4 * P + 3];
+    } else {
+      c0 = ext_tbl[2 * P], p0 = ext_tbl[2 * P + 1];
+    }
+    const int i0 = p0 * npp + rr, i1 = p1 * npp + rr;
+    const double* row0 = cs.T[c0] + (int64_t)i0 * cs.ld[c0];
+    const double* row1 = c1 >= 0 ? cs.T[c1] + (int64_t)i1 * cs.ld[c1] : nullptr;
+    for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < n_cols; col += gridDim.x * blockDim.x) {
+      if (col < n_int + n_ext) {
+        const bool icol = col < n_int;
+        const int cl = icol ? col : col - n_int;
+        const int Q = cl / npp, cc = cl - Q * npp;
+        int d0, q0, d1 = -1, q1 = 0;
+        if (icol) {
+          d0 = int_tbl[4 * Q], q0 = int_tbl[4 * Q + 1], d1 = int_tbl[4 * Q + 2], q1 = int_tbl[4 * Q + 3];
+        } else {
+          d0 = ext_tbl[2 * Q], q0 = ext_tbl[2 * Q + 1];
+        }
+        double v = 0.0;
+        if (d0 == c0) v += row0[q0 * npp + cc];
+        else if (d0 == c1) v += row1[q0 * npp + cc];
+        if (d1 >= 0) {
+          if (d1 == c0) v += row0[q1 * npp + cc];
+          else if (d1 == c1) v += row1[q1 * npp + cc];
+        }
+        if (irow && icol) D[(int64_t)row * n_int + col] = v;
+        else if (irow) S[(int64_t)row * n_ext + cl] = -v;
+        else if (icol) B[(int64_t)rl * n_int + col] = v;
+        else T_out[(int64_t)rl * n_ext + cl] = v;
+      } else {
+        const int k = col - n_int - n_ext;
+        if (irow) gt[(int64_t)row * n_src + k] = -(cs.h[c0][(int64_t)i0 * n_src + k] + cs.h[c1][(int64_t)i1 * n_src + k]);
+        else h_out[(int64_t)rl * n_src + k] = cs.h[c0][(int64_t)i0 * n_src + k];
+      }
+    }
+  }
+}
+
+// Children's boundary data from the parent's: tbl[t] = {child, source panel, start, width, rev}.
+// Source panel sp < NE is exterior panel sp of g_ext, otherwise interface panel sp - NE of g_int.
+// A coarsened run is re-refined with Lr ((group*npp) x npp): out[seg(j)] = sum_i Lr[j, i] g[sp*npp + i].
+__global__ void __launch_bounds__(128) adaptive_down_kernel(ChildOut out, int npp, int n_src, int NE,
+                                                            const int* __restrict__ tbl, const double* __restrict__ g_ext,
+                                                            const double* __restrict__ g_int,
+                                                            const double* __restrict__ Lr) {
+  const int t = blockIdx.x;
+  const int c = tbl[5 * t], sp = tbl[5 * t + 1], start = tbl[5 * t + 2], width = tbl[5 * t + 3], rev = tbl[5 * t + 4];
+  const double* src = sp < NE ? g_ext + (int64_t)sp * npp * n_src : g_int + (int64_t)(sp - NE) * npp * n_src;
+  const int len = width * npp;
+  double* dst = out.g[c];
+  for (int e = threadIdx.x; e < len * n_src; e += blockDim.x) {
+    const int j = e / n_src, k = e - j * n_src;
+    double v;
+    if (width == 1) {
+      v = src[(int64_t)j * n_src + k];
+    } else {
+      v = 0.0;
+      for (int i = 0; i < npp; ++i) v += Lr[(int64_t)j * npp + i] * src[(int64_t)i * n_src + k];
+    }
+    dst[(int64_t)seg_index(start, len, rev, j) * n_src + k] = v;
+  }
+}
+
+}  // namespace
+
+size_t adaptive_compress_ws_bytes(int n, int n_out) { return align_up((size_t)n * n_out * sizeof(double), 256); }
+
+int adaptive_compress(cudaStream_t st, int npp, int group, int n_src, int n, const double* T, const double* h,
+                      int n_out_panels, const int* seg_tbl, const double* L_refine, const double* L_coarsen,
+                      double* T_out, double* h_out, void* ws, size_t ws_bytes) {
+  if (npp <= 0 || group <= 0 || n_src <= 0 || n <= 0 || n_out_panels <= 0) return fail_arg(2, "non-positive size");
+  const int n_out = n_out_panels * npp;
+  if (ws_bytes < adaptive_compress_ws_bytes(n, n_out)) return fail_arg(14, "adaptive_compress: workspace too small");
+  double* tmp = static_cast<double*>(ws);
+  const int rows_per_block = std::max(1, 256 / npp);
+  {
+    dim3 grid(n_out_panels, std::min((n + rows_per_block - 1) / rows_per_block, 512));
+    prof_begin(PROF_GATHER, st, 8.0 * (double)n * n_out);
+    compress_cols_kernel<<<grid, 256, 0, st>>>(T, n, npp, group, seg_tbl, L_refine, tmp, n_out);
+    prof_end(PROF_GATHER, st);
+    HPS_LAUNCH_CHECK("compress_cols_kernel");
+  }
+  {
+    dim3 grid(std::min((n_out + 255) / 256, 256), n_out_panels);
+    prof_begin(PROF_GATHER, st, 8.0 * (double)n_out * n_out);
+    compress_rows_kernel<<<grid, 256, 0, st>>>(tmp, n_out, npp, group, seg_tbl, L_coarsen, T_out);
+    prof_end(PROF_GATHER, st);
+    HPS_LAUNCH_CHECK("compress_rows_kernel");
+  }
+  {
+    dim3 grid(1, n_out_panels);
+    compress_rows_kernel<<<grid, 256, 0, st>>>(h, n_src, npp, group, seg_tbl, L_coarsen, h_out);
+    HPS_LAUNCH_CHECK("compress_rows_kernel(h)");
+  }
+  return 0;
+}
+
+size_t merge_adaptive_ws_bytes(int n_int, int n_ext) {
+  return align_up((size_t)n_int * n_int * sizeof(double), 256) + align_up((size_t)n_ext * n_int * sizeof(double), 256) +
+         lu_workspace_bytes(1, n_int);
+}
+
+int merge_adaptive(cudaStream_t st, int npp, int n_src, int n_child, const double* const* T_child,
+                   const double* const* h_child, const int* ld_child, int NI, const int* int_tbl, int NE,
+                   const int* ext_tbl, double* S, double* gt, double* T_out, double* h_out, int want_T, void* ws,
+                   size_t ws_bytes, int* info) {
+  if (npp <= 0 || n_src <= 0 || NI <= 0 || NE <= 0) return fail_arg(2, "non-positive size");
+  if (n_child <= 0 || n_child > MAXC) return fail_arg(4, "n_child must be 1..8");
+  const int n_int = NI * npp, n_ext = NE * npp;
+  Arena ar(ws, ws_bytes);
+  double* D = ar.take<double>((size_t)n_int * n_int);
+  double* B = ar.take<double>((size_t)n_ext * n_int);
+  if (!D || !B) return fail_arg(17, "merge_adaptive: workspace too small");
+  void* lu_ws = ar.base + ar.off;
+  const size_t lu_ws_bytes = ar.cap - ar.off;
+  ChildSet cs = {};
+  for (int c = 0; c < n_child; ++c) cs.T[c] = T_child[c], cs.h[c] = h_child[c], cs.ld[c] = ld_child[c];
+  {
+    const int rows = want_T ? n_int + n_ext : n_int;
+    const int cols = n_int + n_ext + n_src;
+    dim3 grid(std::min((cols + 255) / 256, 64), std::min(rows, 65535));
+    prof_begin(PROF_GATHER, st, 8.0 * (double)rows * (n_int + n_ext));
+    adaptive_gather_kernel<<<grid, 256, 0, st>>>(cs, npp, n_src, NI, NE, int_tbl, ext_tbl, D, S, gt, T_out, h_out, B, want_T);
+    prof_end(PROF_GATHER, st);
+    HPS_LAUNCH_CHECK("adaptive_gather_kernel");
+  }
+  RhsDesc rhs[2] = {{S, n_ext, 0, n_ext}, {gt, n_src, 0, n_src}};
+  HPS_TRY(lu_solve(st, 1, n_int, D, n_int, 0, 2, rhs, lu_ws, lu_ws_bytes, info));
+  if (!want_T) return 0;
+  // T = A + B S, h = h_ext + B g~
+  HPS_TRY(dgemm(st, n_ext, n_ext, n_int, 1.0, B, n_int, 0, S, n_ext, 0, 1.0, T_out, n_ext, 0, 1));
+  HPS_TRY(dgemm(st, n_ext, n_src, n_int, 1.0, B, n_int, 0, gt, n_src, 0, 1.0, h_out, n_src, 0, 1));
+  return 0;
+}
+
+int down_adaptive(cudaStream_t st, int npp, int n_src, int n_int, int n_ext, const double* S, const double* g_ext,
+                  const double* gt, int n_child, double* const* g_child, int n_tbl, const int* tbl,
+                  const double* L_refine, void* ws) {
+  if (npp <= 0 || n_src <= 0 || n_int <= 0 || n_ext <= 0 || n_tbl <= 0) return fail_arg(2, "non-positive size");
+  if (n_child <= 0 || n_child > MAXC) return fail_arg(10, "n_child must be 1..8");
+  double* g_int = static_cast<double*>(ws);
+  HPS_TRY(dgemm_affine(st, n_int, n_src, n_ext, S, n_ext, 0, g_ext, n_src, 0, gt, n_src, 0, g_int, n_src, 0, 1));
+  ChildOut out = {};
+  for (int c = 0; c < n_child; ++c) out.g[c] = g_child[c];
+  adaptive_down_kernel<<<n_tbl, 128, 0, st>>>(out, npp, n_src, n_ext / npp, tbl, g_ext, g_int, L_refine);
+  HPS_LAUNCH_CHECK("adaptive_down_kernel");
+  return 0;
+}
+
+}  // namespace hps

@@ -279,4 +279,34 @@ int hps_leaf_apply(void* stream, int n_leaves, int n_c, int n_g, int n_src, cons
                       (int64_t)n_g * n_src, v, n_src, (int64_t)n_c * n_src, u, n_src, (int64_t)n_c * n_src, n_leaves);
 }
 
+int hps_adaptive_compress_workspace(int n, int n_out_panels, int npp, size_t* bytes) {
+  if (!bytes) return fail_arg(4, "null output pointer");
+  *bytes = adaptive_compress_ws_bytes(n, n_out_panels * npp);
+  return 0;
+}
+int hps_adaptive_compress(void* stream, int npp, int group, int n_src, int n, const double* T, const double* h,
+                          int n_out_panels, const int* seg_tbl, const double* L_refine, const double* L_coarsen,
+                          double* T_out, double* h_out, void* ws, size_t ws_bytes) {
+  return adaptive_compress(static_cast<cudaStream_t>(stream), npp, group, n_src, n, T, h, n_out_panels, seg_tbl, L_refine,
+                           L_coarsen, T_out, h_out, ws, ws_bytes);
+}
+int hps_merge_adaptive_workspace(int n_int, int n_ext, size_t* bytes) {
+  if (!bytes) return fail_arg(3, "null output pointer");
+  *bytes = merge_adaptive_ws_bytes(n_int, n_ext);
+  return 0;
+}
+int hps_merge_adaptive(void* stream, int npp, int n_src, int n_child, const double* const* T_child,
+                       const double* const* h_child, const int* ld_child, int n_int_panels, const int* int_tbl,
+                       int n_ext_panels, const int* ext_tbl, double* S, double* g_tilde, double* T_out, double* h_out,
+                       int want_T, void* ws, size_t ws_bytes, int* info) {
+  return merge_adaptive(static_cast<cudaStream_t>(stream), npp, n_src, n_child, T_child, h_child, ld_child, n_int_panels,
+                        int_tbl, n_ext_panels, ext_tbl, S, g_tilde, T_out, h_out, want_T, ws, ws_bytes, info);
+}
+int hps_down_adaptive(void* stream, int npp, int n_src, int n_int, int n_ext, const double* S, const double* g_ext,
+                      const double* g_tilde, int n_child, double* const* g_child, int n_tbl, const int* tbl,
+                      const double* L_refine, void* ws) {
+  return down_adaptive(static_cast<cudaStream_t>(stream), npp, n_src, n_int, n_ext, S, g_ext, g_tilde, n_child, g_child,
+                       n_tbl, tbl, L_refine, ws);
+}
+
 }  // extern "C"
