@@ -28,7 +28,7 @@ def build_solver(pde_problem: PDEProblem, return_top_T: bool = False, compute_de
             )
         return _nosource_build_solver(pde_problem, return_top_T, compute_device, host_device)
     if not pde_problem.domain.bool_uniform:
-        raise NotImplementedError("adaptive discretisations are outside the hot path built so far")
+        return _adaptive_build_solver(pde_problem, return_top_T, compute_device, host_device)
     from . import _lib
 
     # leaf outputs stay on the compute device between the two stages (the reference round-trips
@@ -75,3 +75,34 @@ def _nosource_build_solver(pde_problem: PDEProblem, return_top_T: bool, compute_
     out = mg(T, pde_problem.domain.L, device=dev, host_device=host_device, return_T=return_top_T)
     pde_problem.S_lst, pde_problem.D_inv_lst, pde_problem.BD_inv_lst = out[0], out[1], out[2]
     return out[3] if return_top_T else None
+
+
+def _adaptive_build_solver(pde_problem: PDEProblem, return_top_T: bool, compute_device, host_device):
+    """Adaptive trees (reference `_build_solver.py:174-258`): leaf solves, then node-by-node merges.
+    Leaf outputs are also attached to ``leaf.data`` like the reference does; device copies of ``Y``
+    and ``v`` stay on the problem so that ``solve`` moves nothing."""
+    from . import _lib
+    from ._tree import get_all_leaves
+    from .adaptive import (
+        local_solve_stage_adaptive_2D_DtN,
+        local_solve_stage_adaptive_3D_DtN,
+        merge_stage_adaptive_2D_DtN,
+        merge_stage_adaptive_3D_DtN,
+    )
+
+    dev = _lib.require_cuda(compute_device)
+    two_d = pde_problem.domain.bool_2D
+    ls = local_solve_stage_adaptive_2D_DtN if two_d else local_solve_stage_adaptive_3D_DtN
+    mg = merge_stage_adaptive_2D_DtN if two_d else merge_stage_adaptive_3D_DtN
+    Y, T, v, h = ls(pde_problem, device=dev, host_device=dev)
+    pde_problem.__dict__["_adaptive_leaf"] = (Y, v)
+    pde_problem.Y = _lib.to_result(Y, host_device)
+    pde_problem.v = _lib.to_result(v, host_device)
+    T_res, h_res = _lib.to_result(T, host_device), _lib.to_result(h, host_device)
+    mg(pde_problem, T, h, device=dev, host_device=host_device, return_T=return_top_T)
+    for i, leaf in enumerate(get_all_leaves(pde_problem.domain.root)):
+        leaf.data.Y, leaf.data.v = pde_problem.Y[i], pde_problem.v[i]
+        leaf.data.T, leaf.data.h = T_res[i], h_res[i]
+    if return_top_T:
+        return pde_problem.domain.root.data.T
+    return None

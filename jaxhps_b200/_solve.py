@@ -19,7 +19,16 @@ def solve(pde_problem: PDEProblem, boundary_data, source=None, compute_device=No
             )
         return _up_then_down_pass(pde_problem, boundary_data, source, compute_device, host_device)
     if not pde_problem.domain.bool_uniform:
-        raise NotImplementedError("adaptive discretisations are outside the hot path built so far")
+        # adaptive trees: boundary data is a list with one array per side / face (`_solve.py:96-112`)
+        from .adaptive import down_pass_adaptive_2D_DtN, down_pass_adaptive_3D_DtN
+
+        if not isinstance(boundary_data, list):
+            raise ValueError(
+                "For adaptive solves, boundary data needs to be a list. Try using the "
+                "Domain.get_adaptive_boundary_data_lst() utility."
+            )
+        down = down_pass_adaptive_2D_DtN if pde_problem.domain.bool_2D else down_pass_adaptive_3D_DtN
+        return down(pde_problem, boundary_data, device=compute_device, host_device=host_device)
     if isinstance(boundary_data, list):
         if all(isinstance(b, torch.Tensor) for b in boundary_data):
             boundary_data = torch.cat(boundary_data)

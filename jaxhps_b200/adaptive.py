@@ -1,0 +1,383 @@
+"""Adaptive (non-uniform tree) DtN stages on the B200.
+
+API mirror of the reference's adaptive stage functions
+(`local_solve/_adaptive_2D_DtN.py:12-124`, `local_solve/_adaptive_3D_DtN.py:13-127`,
+`merge/_adaptive_2D_DtN.py:24-93`, `merge/_adaptive_3D_DtN.py:30-147`,
+`down_pass/_adaptive_2D_DtN.py:13-84`, `down_pass/_adaptive_3D_DtN.py:15-129`).
+
+How the work is laid out on the device (one implementation for 2D and 3D):
+
+* local solves: leaves are bucketed by side length; every bucket is one batched call of the uniform
+  leaf kernel with ``D1`` and ``Q`` rescaled for that bucket (the reference re-scales the full
+  p^d x p^d operators per leaf);
+* merges: nodes whose children are all leaves go through the batched uniform merge kernel in one
+  call; every other node is one ``hps_merge_adaptive`` call driven by the tables of
+  ``_adaptive_plan.TreePlan`` (uploaded once), children being coarsened first where a level jump
+  crosses an interface;
+* down pass: one ``hps_down_adaptive`` per planned node, top-down, writing straight into the
+  children's slots; parents of leaves are again one batched call; then ``hps_leaf_apply``.
+
+Per-node results are exposed on ``node.data`` like the reference does (``S``, ``g_tilde``, ``h``; ``T``
+only on the root — the children's ``T`` are released as soon as their parent is merged), in the form
+``host_device`` asks for; device-resident copies stay on the problem object for ``solve``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._adaptive_plan import TreePlan, get_plan
+from ._operators import scaled_diff_matrix_1D
+from .down_pass import leaf_apply
+from .local_solve import _ORDER_2D, _ORDER_3D, _gather_coeffs, MAX_WORKSPACE_BYTES
+
+__all__ = [
+    "local_solve_stage_adaptive_2D_DtN",
+    "local_solve_stage_adaptive_3D_DtN",
+    "merge_stage_adaptive_2D_DtN",
+    "merge_stage_adaptive_3D_DtN",
+    "down_pass_adaptive_2D_DtN",
+    "down_pass_adaptive_3D_DtN",
+]
+
+
+# ------------------------------------------------------------------------------- leaf stage
+
+
+def _local_solve_adaptive(pde_problem, dim: int, device, host_device):
+    dev = _lib.require_cuda(device)
+    lib = _lib.load()
+    dom = pde_problem.domain
+    p, q = dom.p, dom.q
+    order = _ORDER_3D if dim == 3 else _ORDER_2D
+    with torch.cuda.device(dev):
+        coeffs, which = _gather_coeffs(pde_problem, order, dev)
+        src = _lib.to_device(pde_problem.source, dev)
+        multi = src.ndim == 3
+        if not multi:
+            src = src.unsqueeze(-1)
+        n_leaves, n_c, n_src = src.shape
+        sidelens = np.asarray(pde_problem.sidelens, dtype=np.float64)
+        if sidelens.shape[0] != n_leaves:
+            raise ValueError("pde_problem.sidelens does not match the number of leaves")
+        P = _lib.to_device(pde_problem.P, dev)
+        Q_unit = _lib.to_device(pde_problem.Q, dev)  # built with half side length 1
+        n_g = Q_unit.shape[0]
+        f64 = dict(dtype=torch.float64, device=dev)
+        Y = torch.empty((n_leaves, n_c, n_g), **f64)
+        T = torch.empty((n_leaves, n_g, n_g), **f64)
+        v = torch.empty((n_leaves, n_c, n_src), **f64)
+        h = torch.empty((n_leaves, n_g, n_src), **f64)
+        info = torch.zeros(n_leaves, dtype=torch.int32, device=dev)
+        one = ctypes.c_size_t()
+        _lib.check(lib.hps_local_solve_dtn_workspace(dim, 1, p, q, n_src, ctypes.byref(one)), "workspace query")
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        budget = min(MAX_WORKSPACE_BYTES, int(0.5 * free_b))
+        max_chunk = int(max(1, min(budget // max(1, one.value), 65535)))
+        # one batched call (or a few) per distinct leaf size
+        for side in np.unique(sidelens):
+            idx_host = np.flatnonzero(sidelens == side)
+            contiguous = idx_host.size == idx_host[-1] - idx_host[0] + 1
+            idx = torch.from_numpy(idx_host).to(dev)
+            half = float(side) / 2
+            D1 = _lib.to_device(scaled_diff_matrix_1D(p, half), dev)
+            Q = (Q_unit / half).contiguous()
+            for s in range(0, idx_host.size, max_chunk):
+                e = min(idx_host.size, s + max_chunk)
+                k = e - s
+                if contiguous:
+                    lo = int(idx_host[s])
+                    sl = slice(lo, lo + k)
+                    c_b, s_b = coeffs[:, sl].contiguous(), src[sl]
+                    Y_b, T_b, v_b, h_b, i_b = Y[sl], T[sl], v[sl], h[sl], info[sl]
+                else:
+                    sel = idx[s:e]
+                    c_b, s_b = coeffs.index_select(1, sel).contiguous(), src.index_select(0, sel).contiguous()
+                    Y_b, T_b = torch.empty((k, n_c, n_g), **f64), torch.empty((k, n_g, n_g), **f64)
+                    v_b, h_b = torch.empty((k, n_c, n_src), **f64), torch.empty((k, n_g, n_src), **f64)
+                    i_b = torch.zeros(k, dtype=torch.int32, device=dev)
+                need = ctypes.c_size_t()
+                _lib.check(lib.hps_local_solve_dtn_workspace(dim, k, p, q, n_src, ctypes.byref(need)), "workspace query")
+                ws = _lib.WORKSPACE.get(need.value, dev)
+                rc = lib.hps_local_solve_dtn(
+                    _lib.stream_ptr(), dim, k, p, q, n_src, which, _lib.ptr(c_b), _lib.ptr(D1), _lib.ptr(P), _lib.ptr(Q),
+                    _lib.ptr(s_b), _lib.ptr(Y_b), _lib.ptr(T_b), _lib.ptr(v_b), _lib.ptr(h_b), _lib.ptr(ws), ws.numel(),
+                    _lib.ptr(i_b))
+                _lib.check(rc, "hps_local_solve_dtn")
+                if not contiguous:
+                    Y.index_copy_(0, sel, Y_b), T.index_copy_(0, sel, T_b)
+                    v.index_copy_(0, sel, v_b), h.index_copy_(0, sel, h_b), info.index_copy_(0, sel, i_b)
+        _lib.check_info(info, "adaptive local solve")
+        if not multi:
+            v, h = v[..., 0], h[..., 0]
+        return tuple(_lib.to_result(t, host_device) for t in (Y, T, v, h))
+
+
+def local_solve_stage_adaptive_3D_DtN(pde_problem, device=None, host_device=None):
+    """Leaf DtN maps of an adaptive octree: ``(Y, T, v, h)`` with shapes ``(n, p^3, 6q^2)``,
+    ``(n, 6q^2, 6q^2)``, ``(n, p^3)``, ``(n, 6q^2)`` (reference `local_solve/_adaptive_3D_DtN.py:13-127`)."""
+    return _local_solve_adaptive(pde_problem, 3, device, host_device)
+
+
+def local_solve_stage_adaptive_2D_DtN(pde_problem, device=None, host_device=None):
+    """Leaf DtN maps of an adaptive quadtree (reference `local_solve/_adaptive_2D_DtN.py:12-124`)."""
+    return _local_solve_adaptive(pde_problem, 2, device, host_device)
+
+
+# ------------------------------------------------------------------------------- merge stage
+
+
+class _State:
+    """Device-resident solver state of one adaptive problem."""
+
+    def __init__(self, plan: TreePlan, dev):
+        self.plan = plan
+        self.dev = dev
+        self.tables = _lib.to_device(plan.pack(), dev, dtype=torch.int32)
+        self.S: Dict[int, torch.Tensor] = {}
+        self.g: Dict[int, torch.Tensor] = {}
+        self.L_refine = None
+        self.L_coarsen = None
+
+    def tbl(self, node_plan, key: str) -> int:
+        return self.tables.data_ptr() + 4 * node_plan.off[key]
+
+
+def _ptr_array(tensors) -> ctypes.Array:
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _merge_adaptive(pde_problem, T_arr, h_arr, device, host_device, return_T: bool):
+    dev = _lib.require_cuda(device)
+    lib = _lib.load()
+    dom = pde_problem.domain
+    dim = 2 if dom.bool_2D else 3
+    plan = get_plan(pde_problem)
+    npp, group = plan.npp, plan.group
+    with torch.cuda.device(dev):
+        st = _State(plan, dev)
+        Lr, Lc = (pde_problem.L_2f1, pde_problem.L_1f2) if dom.bool_2D else (pde_problem.L_4f1, pde_problem.L_1f4)
+        st.L_refine, st.L_coarsen = _lib.to_device(Lr, dev), _lib.to_device(Lc, dev)
+        T_leaf = _lib.to_device(T_arr, dev)
+        h_leaf = _lib.to_device(h_arr, dev)
+        multi = h_leaf.ndim == 3
+        if not multi:
+            h_leaf = h_leaf.unsqueeze(-1)
+        n_src = h_leaf.shape[-1]
+        if T_leaf.shape[0] != len(plan.leaves):
+            raise ValueError(f"expected {len(plan.leaves)} leaf operators, got {T_leaf.shape[0]}")
+        f64 = dict(dtype=torch.float64, device=dev)
+        info = torch.zeros(max(1, len(plan.nodes)), dtype=torch.int32, device=dev)
+        cur: Dict[int, tuple] = {}  # id(node) -> (T, h) of nodes whose parent is not merged yet
+        root_T = None
+
+        # ---- parents of leaves: one batched uniform merge
+        first = [np_ for np_ in plan.nodes if np_.all_leaf_children]
+        if first:
+            n_child = len(first[0].children)
+            idx = torch.tensor([plan.leaf_index[id(k)] for np_ in first for k in np_.node.children], device=dev)
+            T_in, h_in = T_leaf.index_select(0, idx), h_leaf.index_select(0, idx)
+            n1, n_int, n_ext = len(first), first[0].n_int, first[0].n_ext
+            level_fn = lib.hps_merge_oct_dtn_level if dim == 3 else lib.hps_merge_quad_dtn_level
+            ws_fn = lib.hps_merge_oct_dtn_level_workspace if dim == 3 else lib.hps_merge_quad_dtn_level_workspace
+            S1, g1 = torch.empty((n1, n_int, n_ext), **f64), torch.empty((n1, n_int, n_src), **f64)
+            T1, h1 = torch.empty((n1, n_ext, n_ext), **f64), torch.empty((n1, n_ext, n_src), **f64)
+            i1 = torch.zeros(n1, dtype=torch.int32, device=dev)
+            need = ctypes.c_size_t()
+            step = min(n1, 16384)
+            _lib.check(ws_fn(step, npp, n_src, ctypes.byref(need)), "merge workspace query")
+            ws = _lib.WORKSPACE.get(need.value, dev)
+            for s in range(0, n1, step):
+                e = min(n1, s + step)
+                rc = level_fn(_lib.stream_ptr(), e - s, npp, n_src, _lib.ptr(T_in[s * n_child:]), _lib.ptr(h_in[s * n_child:]),
+                              _lib.ptr(S1[s:]), _lib.ptr(g1[s:]), _lib.ptr(T1[s:]), _lib.ptr(h1[s:]), 1, _lib.ptr(ws),
+                              ws.numel(), _lib.ptr(i1[s:]))
+                _lib.check(rc, "hps_merge_dtn_level")
+            _lib.check_info(i1, "merge of the leaves' parents")
+            del T_in, h_in
+            for k, np_ in enumerate(first):
+                st.S[id(np_.node)], st.g[id(np_.node)] = S1[k], g1[k]
+                cur[id(np_.node)] = (T1[k], h1[k])
+                np_.node.data.h = h1[k]
+            st.first = (first, S1, g1)
+            if first[0].node is dom.root:
+                root_T = T1[0]
+        else:
+            st.first = ([], None, None)
+
+        # ---- every other node, deepest first
+        for n_idx, np_ in enumerate(plan.nodes):
+            if np_.all_leaf_children:
+                continue
+            node = np_.node
+            Ts, hs, keep = [], [], []
+            for ch, kid in zip(np_.children, node.children):
+                if kid.children:
+                    Tk, hk = cur.pop(id(kid))
+                else:
+                    i = plan.leaf_index[id(kid)]
+                    Tk, hk = T_leaf[i], h_leaf[i]
+                if not ch.identity:
+                    need = ctypes.c_size_t()
+                    _lib.check(lib.hps_adaptive_compress_workspace(ch.n, ch.n_out // npp, npp, ctypes.byref(need)), "ws query")
+                    ws = _lib.WORKSPACE.get(need.value, dev)
+                    T2, h2 = torch.empty((ch.n_out, ch.n_out), **f64), torch.empty((ch.n_out, n_src), **f64)
+                    c = len(Ts)
+                    rc = lib.hps_adaptive_compress(_lib.stream_ptr(), npp, group, n_src, ch.n, _lib.ptr(Tk), _lib.ptr(hk),
+                                                   ch.n_out // npp, st.tbl(np_, f"seg{c}"), _lib.ptr(st.L_refine),
+                                                   _lib.ptr(st.L_coarsen), _lib.ptr(T2), _lib.ptr(h2), _lib.ptr(ws), ws.numel())
+                    _lib.check(rc, "hps_adaptive_compress")
+                    Tk, hk = T2, h2
+                Ts.append(Tk), hs.append(hk)
+            is_root = node is dom.root
+            want_T = (not is_root) or return_T
+            S = torch.empty((np_.n_int, np_.n_ext), **f64)
+            g = torch.empty((np_.n_int, n_src), **f64)
+            T_out = torch.empty((np_.n_ext, np_.n_ext), **f64) if want_T else None
+            h_out = torch.empty((np_.n_ext, n_src), **f64) if want_T else None
+            need = ctypes.c_size_t()
+            _lib.check(lib.hps_merge_adaptive_workspace(np_.n_int, np_.n_ext, ctypes.byref(need)), "ws query")
+            ws = _lib.WORKSPACE.get(need.value, dev)
+            lds = (ctypes.c_int * len(Ts))(*[t.shape[1] for t in Ts])
+            rc = lib.hps_merge_adaptive(_lib.stream_ptr(), npp, n_src, len(Ts), _ptr_array(Ts), _ptr_array(hs), lds,
+                                        np_.int_tbl.shape[0], st.tbl(np_, "int"), np_.ext_tbl.shape[0], st.tbl(np_, "ext"),
+                                        _lib.ptr(S), _lib.ptr(g), _lib.ptr(T_out), _lib.ptr(h_out), 1 if want_T else 0,
+                                        _lib.ptr(ws), ws.numel(), _lib.ptr(info[n_idx:]))
+            _lib.check(rc, "hps_merge_adaptive")
+            st.S[id(node)], st.g[id(node)] = S, g
+            if want_T:
+                node.data.h = h_out
+                if is_root:
+                    root_T = T_out
+                else:
+                    cur[id(node)] = (T_out, h_out)
+            del Ts, hs
+        _lib.check_info(info, "adaptive merge")
+
+        # ---- expose the results on the tree the way the reference does
+        pde_problem.__dict__["_adaptive_state"] = st
+        for np_ in plan.nodes:
+            d = np_.node.data
+            S, g = st.S[id(np_.node)], st.g[id(np_.node)]
+            d.S = _lib.to_result(S, host_device)
+            d.g_tilde = _lib.to_result(g if multi else g[..., 0], host_device)
+            if d.h is not None and isinstance(d.h, torch.Tensor):
+                d.h = _lib.to_result(d.h if multi else d.h[..., 0], host_device)
+            d.T = None
+        if root_T is not None:
+            dom.root.data.T = _lib.to_result(root_T, host_device)
+        return plan.by_id[id(dom.root)].n_int
+
+
+def merge_stage_adaptive_3D_DtN(pde_problem, T_arr, h_arr, device=None, host_device=None, return_T: bool = True):
+    """Merge the whole adaptive octree bottom-up; results are stored on the tree (``node.data.S``,
+    ``.g_tilde``, ``.h``; ``root.data.T`` when ``return_T``) and on the problem for :func:`solve`.
+    Returns the size of the root's interface system like the reference (`merge/_adaptive_3D_DtN.py:30-147`)."""
+    return _merge_adaptive(pde_problem, T_arr, h_arr, device, host_device, return_T)
+
+
+def merge_stage_adaptive_2D_DtN(pde_problem, T_arr=None, h_arr=None, device=None, host_device=None, return_T: bool = True):
+    """Quadtree version (`merge/_adaptive_2D_DtN.py:24-93`).  The reference takes the leaf operators
+    from ``leaf.data.T`` / ``leaf.data.h``; they may also be passed as arrays in leaf order."""
+    if T_arr is None:
+        leaves = get_plan(pde_problem).leaves
+        stack = torch.stack if isinstance(leaves[0].data.T, torch.Tensor) else np.stack
+        T_arr = stack([leaf.data.T for leaf in leaves])
+        h_arr = stack([leaf.data.h for leaf in leaves])
+    return _merge_adaptive(pde_problem, T_arr, h_arr, device, host_device, return_T)
+
+
+# ------------------------------------------------------------------------------- down pass
+
+
+def _down_adaptive(pde_problem, boundary_data, device, host_device, Y_arr=None, v_arr=None):
+    dev = _lib.require_cuda(device)
+    lib = _lib.load()
+    dom = pde_problem.domain
+    dim = 2 if dom.bool_2D else 3
+    st: _State = pde_problem.__dict__.get("_adaptive_state")
+    if st is None or st.dev != dev:
+        raise ValueError("build_solver (or merge_stage_adaptive_*_DtN) must be run on this device before the down pass")
+    plan = st.plan
+    npp = plan.npp
+    with torch.cuda.device(dev):
+        if isinstance(boundary_data, (list, tuple)):
+            parts = [_lib.to_device(b, dev) for b in boundary_data]
+            sizes = plan.face_sizes(dom.root)
+            if [int(b.shape[0]) for b in parts] != sizes:
+                raise ValueError(f"boundary data per face has sizes {[int(b.shape[0]) for b in parts]}, expected {sizes}")
+            g_root = torch.cat(parts)
+        else:
+            g_root = _lib.to_device(boundary_data, dev)
+        multi = g_root.ndim == 2
+        if not multi:
+            g_root = g_root.unsqueeze(-1)
+        g_root = g_root.contiguous()
+        n_src = g_root.shape[-1]
+        if g_root.shape[0] != plan.n_points(dom.root):
+            raise ValueError(f"boundary data has {g_root.shape[0]} entries, the root boundary has {plan.n_points(dom.root)}")
+        f64 = dict(dtype=torch.float64, device=dev)
+        n_leaves = len(plan.leaves)
+        n_g = plan.n_points(plan.leaves[0])
+        G_leaf = torch.empty((n_leaves, n_g, n_src), **f64)
+        first, S1, g1 = st.first
+        G1 = torch.empty((len(first), first[0].n_ext, n_src), **f64) if first else None
+        slot: Dict[int, torch.Tensor] = {id(np_.node): G1[k] for k, np_ in enumerate(first)}
+        for i, leaf in enumerate(plan.leaves):
+            slot[id(leaf)] = G_leaf[i]
+        if id(dom.root) in slot:
+            slot[id(dom.root)].copy_(g_root)
+        else:
+            slot[id(dom.root)] = g_root
+        max_int = max([np_.n_int for np_ in plan.nodes if not np_.all_leaf_children], default=1)
+        ws = torch.empty(max_int * n_src, **f64)
+        for np_ in reversed(plan.nodes):  # shallowest first
+            if np_.all_leaf_children:
+                continue
+            node = np_.node
+            outs: List[torch.Tensor] = []
+            for ch, kid in zip(np_.children, node.children):
+                if id(kid) not in slot:
+                    slot[id(kid)] = torch.empty((ch.n, n_src), **f64)
+                outs.append(slot[id(kid)])
+            g_t = st.g[id(node)]
+            if g_t.shape[-1] != n_src:
+                raise ValueError("boundary data and source term disagree on the number of right-hand sides")
+            rc = lib.hps_down_adaptive(_lib.stream_ptr(), npp, n_src, np_.n_int, np_.n_ext, _lib.ptr(st.S[id(node)]),
+                                       _lib.ptr(slot[id(node)]), _lib.ptr(g_t), len(outs), _ptr_array(outs),
+                                       np_.down_tbl.shape[0], st.tbl(np_, "down"), _lib.ptr(st.L_refine), _lib.ptr(ws))
+            _lib.check(rc, "hps_down_adaptive")
+            del slot[id(node)]
+        if first:
+            down_fn = lib.hps_down_oct_level if dim == 3 else lib.hps_down_quad_level
+            n1, n_int = len(first), first[0].n_int
+            n_child = len(first[0].children)
+            kids = torch.empty((n1 * n_child, n_g, n_src), **f64)
+            ws1 = torch.empty((n1, n_int, n_src), **f64)
+            rc = down_fn(_lib.stream_ptr(), n1, npp, n_src, _lib.ptr(S1), _lib.ptr(G1), _lib.ptr(g1), _lib.ptr(kids), _lib.ptr(ws1))
+            _lib.check(rc, "hps_down_level")
+            idx = torch.tensor([plan.leaf_index[id(k)] for np_ in first for k in np_.node.children], device=dev)
+            G_leaf.index_copy_(0, idx, kids)
+        resident = pde_problem.__dict__.get("_adaptive_leaf")  # device copies kept by build_solver
+        if Y_arr is None and resident is not None and resident[0].device == dev:
+            Y, v = resident
+        else:
+            Y = _lib.to_device(pde_problem.Y if Y_arr is None else Y_arr, dev)
+            v = _lib.to_device(pde_problem.v if v_arr is None else v_arr, dev)
+        u = leaf_apply(Y, G_leaf, v.reshape(n_leaves, -1, n_src), dev)
+        return _lib.to_result(u if multi else u[..., 0], host_device)
+
+
+def down_pass_adaptive_3D_DtN(pde_problem, boundary_data, device=None, host_device=None):
+    """Dirichlet data (a list with one array per face of the root, or their concatenation) -> solution
+    on every leaf, ``(n_leaves, p^3)`` (reference `down_pass/_adaptive_3D_DtN.py:15-129`)."""
+    return _down_adaptive(pde_problem, boundary_data, device, host_device)
+
+
+def down_pass_adaptive_2D_DtN(pde_problem, boundary_data, device=None, host_device=None):
+    """Quadtree version (reference `down_pass/_adaptive_2D_DtN.py:13-84`)."""
+    return _down_adaptive(pde_problem, boundary_data, device, host_device)

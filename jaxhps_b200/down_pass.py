@@ -132,3 +132,12 @@ def down_pass_uniform_2D_ItI(boundary_data, S_lst, g_tilde_lst, Y_arr, v_arr, de
                                         _lib.ptr(v.reshape(n_leaves, n_c, n_src)), _lib.ptr(u), _lib.ptr(ws))
         _lib.check(rc, "hps_leaf_apply_complex")
         return _lib.to_result(u if multi else u[..., 0], host_device)
+
+
+
+def __getattr__(name):  # the adaptive-tree stages live in adaptive.py (imported lazily: it imports this module)
+    if name in ('down_pass_adaptive_2D_DtN', 'down_pass_adaptive_3D_DtN'):
+        from . import adaptive
+
+        return getattr(adaptive, name)
+    raise AttributeError(name)

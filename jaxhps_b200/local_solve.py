@@ -152,3 +152,12 @@ def local_solve_stage_uniform_2D_ItI(pde_problem, device=None, host_device=None)
         if not multi:
             v, h = v[..., 0], h[..., 0]
         return tuple(_lib.to_result(t, host_device) for t in (Y, R, v, h))
+
+
+
+def __getattr__(name):  # the adaptive-tree stages live in adaptive.py (imported lazily: it imports this module)
+    if name in ('local_solve_stage_adaptive_2D_DtN', 'local_solve_stage_adaptive_3D_DtN'):
+        from . import adaptive
+
+        return getattr(adaptive, name)
+    raise AttributeError(name)

@@ -171,3 +171,12 @@ def merge_stage_uniform_2D_ItI(T_arr, h_arr, l: int, device=None, host_device=No
         if return_h:
             out = out + (_lib.to_result((h if multi else h[..., 0])[0], host_device),)
         return out
+
+
+
+def __getattr__(name):  # the adaptive-tree stages live in adaptive.py (imported lazily: it imports this module)
+    if name in ('merge_stage_adaptive_2D_DtN', 'merge_stage_adaptive_3D_DtN'):
+        from . import adaptive
+
+        return getattr(adaptive, name)
+    raise AttributeError(name)
