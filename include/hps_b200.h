@@ -256,13 +256,17 @@ int hps_adaptive_compress(void* stream, int npp, int group, int n_src, int n, co
  * int_tbl[I] = {child A, panel in A, child B, panel in B} for interface panel I (n_int = NI*npp);
  * ext_tbl[E] = {child, panel} for exterior panel E in the parent's boundary order (n_ext = NE*npp).
  * Outputs: S (n_int x n_ext), g_tilde (n_int x n_src), and if want_T: T_out (n_ext x n_ext),
- * h_out (n_ext x n_src).  Replaces _oct_merge / _adaptive_quad_merge_2D_DtN +
+ * h_out (n_ext x n_src).  B S is formed either from a dense B (n_blocks = 0; workspace query with
+ * dense_B = 1) or block by block from bs_tbl, a HOST array [n_blocks][7] = {child, row0, col0, M, K,
+ * first row of S, first row of T_out} listing the non-zero blocks of B inside the children's operators
+ * (an exterior face times an interface face of the same child: 72 blocks in 3D, 16 in 2D — a quarter of
+ * the dense flops).  Replaces _oct_merge / _adaptive_quad_merge_2D_DtN +
  * assemble_merge_outputs_DtN (merge/_schur_complement.py:117-237). */
-int hps_merge_adaptive_workspace(int n_int, int n_ext, size_t* bytes);
+int hps_merge_adaptive_workspace(int n_int, int n_ext, int dense_B, size_t* bytes);
 int hps_merge_adaptive(void* stream, int npp, int n_src, int n_child, const double* const* T_child,
                        const double* const* h_child, const int* ld_child, int n_int_panels, const int* int_tbl,
                        int n_ext_panels, const int* ext_tbl, double* S, double* g_tilde, double* T_out, double* h_out,
-                       int want_T, void* ws, size_t ws_bytes, int* info);
+                       int want_T, int n_blocks, const int* bs_tbl, void* ws, size_t ws_bytes, int* info);
 /* hps_down_adaptive: g_int = S g_ext + g_tilde, then every child's boundary vector.  g_child: HOST
  * array of n_child device pointers; tbl[t] = {child, source panel, start, width, rev}: the run
  * [start, start + width*npp) of that child's vector comes from source panel sp (sp < NE: exterior

@@ -11,6 +11,8 @@ points of one leaf face) which the CUDA kernels in ``csrc/adaptive.cu`` expand o
               copied; width ``group`` = 2^(d-1): coarsened), walked backwards if ``rev``;
 ``int_tbl``   (NI, 4) ``[child A, panel in A', child B, panel in B']`` per interface panel;
 ``ext_tbl``   (NE, 2) ``[child, panel in T']`` per exterior panel, already in the parent's boundary order;
+``bs_tbl``    (host only) the non-zero blocks of B = T'[exterior face, interface face] per child, as
+              [child, row0, col0, M, K, first row of S, first row of T_out] in points;
 ``down_tbl``  (sum n'_panels, 5) ``[child, source panel, start, width, rev]`` for the down pass, source
               panel < NE: exterior panel of the parent's data, otherwise interface panel - NE.
 
@@ -60,6 +62,7 @@ class NodePlan:
     int_tbl: np.ndarray
     ext_tbl: np.ndarray
     down_tbl: np.ndarray
+    bs_tbl: np.ndarray  #: (n_blocks, 7) non-zero blocks of B: [child, row0, col0 in T', M, K, row0 in S, row0 in T_out]
     n_int: int
     n_ext: int
     all_leaf_children: bool
@@ -172,6 +175,28 @@ class TreePlan:
             for c in self._face_children[f]:
                 for k in range(len(out[c][f])):
                     ext_rows.append((c, children[c].face_off_out[f] + k))
+        # non-zero blocks of B: (exterior face) x (interface face) of the same child
+        slot_off = np.concatenate([[0], np.cumsum([cnt for *_, cnt in slot_faces])])
+        face_slot = {}
+        for s_idx, (a, fa, b, fb, _) in enumerate(slot_faces):
+            face_slot[(a, fa)] = face_slot[(b, fb)] = s_idx
+        ext_first, at = {}, 0
+        for f in range(self.n_faces):
+            for c in self._face_children[f]:
+                ext_first[(c, f)] = at
+                at += len(out[c][f])
+        bs_rows = []
+        for c in range(len(kids)):
+            fo = children[c].face_off_out
+            for fe in range(self.n_faces):
+                if is_int[c][fe]:
+                    continue
+                for fi in range(self.n_faces):
+                    if not is_int[c][fi]:
+                        continue
+                    s_idx = face_slot[(c, fi)]
+                    bs_rows.append((c, fo[fe] * npp, fo[fi] * npp, (fo[fe + 1] - fo[fe]) * npp, (fo[fi + 1] - fo[fi]) * npp,
+                                    int(slot_off[s_idx]) * npp, ext_first[(c, fe)] * npp))
         int_tbl = np.array(int_rows, dtype=np.int32).reshape(-1, 4)
         ext_tbl = np.array(ext_rows, dtype=np.int32).reshape(-1, 2)
         NE = ext_tbl.shape[0]
@@ -184,7 +209,8 @@ class TreePlan:
         down = [(c, source[(c, P)], int(s[0]), int(s[1]), int(s[2])) for c in range(len(kids))
                 for P, s in enumerate(children[c].seg)]
         return NodePlan(node=node, npp=npp, group=group, children=children, int_tbl=int_tbl, ext_tbl=ext_tbl,
-                        down_tbl=np.array(down, dtype=np.int32).reshape(-1, 5), n_int=int_tbl.shape[0] * npp,
+                        down_tbl=np.array(down, dtype=np.int32).reshape(-1, 5),
+                        bs_tbl=np.array(bs_rows, dtype=np.int32).reshape(-1, 7), n_int=int_tbl.shape[0] * npp,
                         n_ext=NE * npp, all_leaf_children=all(not k.children for k in kids))
 
     # ---- flatten every table into one int32 buffer (one host->device copy for the whole tree)

@@ -35,6 +35,10 @@ from ._operators import scaled_diff_matrix_1D
 from .down_pass import leaf_apply
 from .local_solve import _ORDER_2D, _ORDER_3D, _gather_coeffs, MAX_WORKSPACE_BYTES
 
+#: interface size from which ``T = A + B S`` is formed from the non-zero blocks of B (72 / 16 GEMMs) instead
+#: of one dense product with 4x the flops
+SPARSE_B_MIN_INTERFACE = 1024
+
 __all__ = [
     "local_solve_stage_adaptive_2D_DtN",
     "local_solve_stage_adaptive_3D_DtN",
@@ -239,13 +243,18 @@ def _merge_adaptive(pde_problem, T_arr, h_arr, device, host_device, return_T: bo
             g = torch.empty((np_.n_int, n_src), **f64)
             T_out = torch.empty((np_.n_ext, np_.n_ext), **f64) if want_T else None
             h_out = torch.empty((np_.n_ext, n_src), **f64) if want_T else None
+            # small nodes: one dense B S product (fewer launches); large nodes: only the non-zero blocks of B
+            sparse = want_T and np_.n_int >= SPARSE_B_MIN_INTERFACE
+            blocks = np.ascontiguousarray(np_.bs_tbl) if sparse else None
             need = ctypes.c_size_t()
-            _lib.check(lib.hps_merge_adaptive_workspace(np_.n_int, np_.n_ext, ctypes.byref(need)), "ws query")
+            _lib.check(lib.hps_merge_adaptive_workspace(np_.n_int, np_.n_ext, 0 if sparse else 1, ctypes.byref(need)), "ws query")
             ws = _lib.WORKSPACE.get(need.value, dev)
             lds = (ctypes.c_int * len(Ts))(*[t.shape[1] for t in Ts])
             rc = lib.hps_merge_adaptive(_lib.stream_ptr(), npp, n_src, len(Ts), _ptr_array(Ts), _ptr_array(hs), lds,
                                         np_.int_tbl.shape[0], st.tbl(np_, "int"), np_.ext_tbl.shape[0], st.tbl(np_, "ext"),
                                         _lib.ptr(S), _lib.ptr(g), _lib.ptr(T_out), _lib.ptr(h_out), 1 if want_T else 0,
+                                        blocks.shape[0] if sparse else 0,
+                                        blocks.ctypes.data_as(ctypes.POINTER(ctypes.c_int)) if sparse else None,
                                         _lib.ptr(ws), ws.numel(), _lib.ptr(info[n_idx:]))
             _lib.check(rc, "hps_merge_adaptive")
             st.S[id(node)], st.g[id(node)] = S, g

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) adaptive_gather_kernel(ChildSet cs, int n
         }
         if (irow && icol) D[(int64_t)row * n_int + col] = v;
         else if (irow) S[(int64_t)row * n_ext + cl] = -v;
-        else if (icol) B[(int64_t)rl * n_int + col] = v;
+        else if (icol) { if (B) B[(int64_t)rl * n_int + col] = v; }
         else T_out[(int64_t)rl * n_ext + cl] = v;
       } else {
         const int k = col - n_int - n_ext;
@@ -204,22 +204,24 @@ int adaptive_compress(cudaStream_t st, int npp, int group, int n_src, int n, con
   return 0;
 }
 
-size_t merge_adaptive_ws_bytes(int n_int, int n_ext) {
-  return align_up((size_t)n_int * n_int * sizeof(double), 256) + align_up((size_t)n_ext * n_int * sizeof(double), 256) +
-         lu_workspace_bytes(1, n_int);
+// B is only materialised (dense) when the caller gives no block list
+size_t merge_adaptive_ws_bytes(int n_int, int n_ext, int dense_B) {
+  return align_up((size_t)n_int * n_int * sizeof(double), 256) +
+         (dense_B ? align_up((size_t)n_ext * n_int * sizeof(double), 256) : 0) + lu_workspace_bytes(1, n_int);
 }
 
 int merge_adaptive(cudaStream_t st, int npp, int n_src, int n_child, const double* const* T_child,
                    const double* const* h_child, const int* ld_child, int NI, const int* int_tbl, int NE,
-                   const int* ext_tbl, double* S, double* gt, double* T_out, double* h_out, int want_T, void* ws,
-                   size_t ws_bytes, int* info) {
+                   const int* ext_tbl, double* S, double* gt, double* T_out, double* h_out, int want_T, int n_blocks,
+                   const int* bs_tbl, void* ws, size_t ws_bytes, int* info) {
   if (npp <= 0 || n_src <= 0 || NI <= 0 || NE <= 0) return fail_arg(2, "non-positive size");
   if (n_child <= 0 || n_child > MAXC) return fail_arg(4, "n_child must be 1..8");
   const int n_int = NI * npp, n_ext = NE * npp;
   Arena ar(ws, ws_bytes);
   double* D = ar.take<double>((size_t)n_int * n_int);
-  double* B = ar.take<double>((size_t)n_ext * n_int);
-  if (!D || !B) return fail_arg(17, "merge_adaptive: workspace too small");
+  const bool dense_B = want_T && (n_blocks <= 0 || !bs_tbl);
+  double* B = dense_B ? ar.take<double>((size_t)n_ext * n_int) : nullptr;
+  if (!D || (dense_B && !B)) return fail_arg(19, "merge_adaptive: workspace too small");
   void* lu_ws = ar.base + ar.off;
   const size_t lu_ws_bytes = ar.cap - ar.off;
   ChildSet cs = {};
@@ -237,8 +239,23 @@ int merge_adaptive(cudaStream_t st, int npp, int n_src, int n_child, const doubl
   HPS_TRY(lu_solve(st, 1, n_int, D, n_int, 0, 2, rhs, lu_ws, lu_ws_bytes, info));
   if (!want_T) return 0;
   // T = A + B S, h = h_ext + B g~
-  HPS_TRY(dgemm(st, n_ext, n_ext, n_int, 1.0, B, n_int, 0, S, n_ext, 0, 1.0, T_out, n_ext, 0, 1));
-  HPS_TRY(dgemm(st, n_ext, n_src, n_int, 1.0, B, n_int, 0, gt, n_src, 0, 1.0, h_out, n_src, 0, 1));
+  if (dense_B) {
+    HPS_TRY(dgemm(st, n_ext, n_ext, n_int, 1.0, B, n_int, 0, S, n_ext, 0, 1.0, T_out, n_ext, 0, 1));
+    HPS_TRY(dgemm(st, n_ext, n_src, n_int, 1.0, B, n_int, 0, gt, n_src, 0, 1.0, h_out, n_src, 0, 1));
+    return 0;
+  }
+  // only the non-zero blocks of B (an exterior face times an interface face of the SAME child), read in
+  // place from the children's operators: bs_tbl[k] = {child, row0, col0, M, K, first row of S, first row of T}
+  for (int k = 0; k < n_blocks; ++k) {
+    const int* b = bs_tbl + 7 * k;
+    const int c = b[0];
+    if (c < 0 || c >= n_child) return fail_arg(18, "bs_tbl: child out of range");
+    const double* Ablk = cs.T[c] + (int64_t)b[1] * cs.ld[c] + b[2];
+    HPS_TRY(dgemm(st, b[3], n_ext, b[4], 1.0, Ablk, cs.ld[c], 0, S + (int64_t)b[5] * n_ext, n_ext, 0, 1.0,
+                  T_out + (int64_t)b[6] * n_ext, n_ext, 0, 1));
+    HPS_TRY(dgemm(st, b[3], n_src, b[4], 1.0, Ablk, cs.ld[c], 0, gt + (int64_t)b[5] * n_src, n_src, 0, 1.0,
+                  h_out + (int64_t)b[6] * n_src, n_src, 0, 1));
+  }
   return 0;
 }
 

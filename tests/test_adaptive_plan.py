@@ -45,6 +45,11 @@ def emu_merge(Tc, hc, plan):
     D, C, B, A = M[:ni, :ni], M[:ni, ni:], M[ni:, :ni], M[ni:, ni:]
     S = np.linalg.solve(D, -C)
     gt = np.linalg.solve(D, -rhs[:ni])
+    # the non-zero blocks of B listed in bs_tbl must reproduce B S exactly as the dense product does
+    BS = np.zeros_like(A)
+    for c, r0, c0, Mb, Kb, s0, t0 in plan.bs_tbl:
+        BS[t0 : t0 + Mb] += Tc[c][r0 : r0 + Mb, c0 : c0 + Kb] @ S[s0 : s0 + Kb]
+    assert np.abs(BS - B @ S).max() <= 1e-12 * max(1.0, np.abs(BS).max())
     return S, A + B @ S, rhs[ni:] + B @ gt, gt
 
 

@@ -53,6 +53,22 @@ def test_adaptive_stages_match_oracle_and_reference(name):
     assert rel_err(u, G["u"]) < TOL
 
 
+@pytest.mark.parametrize("name", ["adapt2d_p6q4_manual", "adapt3d_p4q2_manual", "adapt3d_p6q4"])
+def test_blockwise_B_times_S_matches_dense(name, monkeypatch):
+    """Large nodes form T = A + B S from the non-zero blocks of B only; force that path on small trees."""
+    from jaxhps_b200 import adaptive
+
+    G = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    monkeypatch.setattr(adaptive, "SPARSE_B_MIN_INTERFACE", 0)
+    case, dom, pb = adaptive_problem(name)
+    T_top = hps.build_solver(pb, return_top_T=True)
+    rng = np.random.default_rng(case["seed"] + 1000)
+    assert rel_err(T_top @ rng.normal(size=T_top.shape[1]), G["T_top_probe"]) < TOL
+    for i, node in enumerate(internal_nodes(dom.root)):
+        assert rel_err(node.data.h, G[f"h_{i}"]) < TOL and rel_err(node.data.g_tilde, G[f"g_tilde_{i}"]) < TOL
+    assert rel_err(hps.solve(pb, dom.get_adaptive_boundary_data_lst(boundary_fn)), G["u"]) < TOL
+
+
 @pytest.mark.parametrize("name", ["adapt2d_p8q6", "adapt3d_p6q4"])
 def test_adaptive_build_solver_and_solve(name):
     """Public API: build_solver / solve on an adaptive Domain, operators resident on the device."""
@@ -75,20 +91,24 @@ def test_adaptive_build_solver_and_solve(name):
 
 
 def test_wavefront_adaptive_3d_reaches_analytic_solution():
-    """Config 4 in small: adaptive octree refined on the source of a manufactured solution."""
-    def u_true(x):
-        return np.exp(-20 * ((x[..., 0] - 0.4) ** 2 + (x[..., 1] - 0.5) ** 2 + (x[..., 2] - 0.6) ** 2))
+    """BASELINE config 4 in small: the wavefront problem u = arctan(10 (|x + 0.05| - 0.7)) on an octree
+    refined on its own source (reference `examples/wavefront_adaptive_discretization_3D.py:297-400`)."""
+    import importlib.util
 
-    def lap(x):
-        r2 = (x[..., 0] - 0.4) ** 2 + (x[..., 1] - 0.5) ** 2 + (x[..., 2] - 0.6) ** 2
-        return (1600 * r2 - 120) * np.exp(-20 * r2)
-
-    root = hps.DiscretizationNode3D(0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
-    dom = hps.Domain.from_adaptive_discretization(p=8, q=6, root=root, f=lap, tol=1e-2)
-    assert not dom.bool_uniform and dom.n_leaves > 8
-    one = np.ones(dom.interior_points.shape[:2])
-    pb = hps.PDEProblem(dom, source=lap(dom.interior_points), D_xx_coefficients=one, D_yy_coefficients=one, D_zz_coefficients=one)
-    hps.build_solver(pb, host_device="cuda")
-    u = hps.solve(pb, dom.get_adaptive_boundary_data_lst(u_true))
-    err = np.abs(u - u_true(dom.interior_points)).max()
-    assert err < 5e-3, err
+    spec = importlib.util.spec_from_file_location(
+        "run_config4", os.path.join(os.path.dirname(GOLDEN_DIR), "..", "tools", "run_config4.py"))
+    cfg4 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cfg4)
+    errs = []
+    for tol in (1e-2, 1e-3):
+        root = hps.DiscretizationNode3D(0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+        dom = hps.Domain.from_adaptive_discretization(p=8, q=6, root=root, f=cfg4.source, tol=tol)
+        assert not dom.bool_uniform and dom.n_leaves > 8
+        one = np.ones(dom.interior_points.shape[:2])
+        pb = hps.PDEProblem(dom, source=cfg4.source(dom.interior_points), D_xx_coefficients=one, D_yy_coefficients=one,
+                            D_zz_coefficients=one)
+        hps.build_solver(pb, host_device="cuda")
+        u = hps.solve(pb, dom.get_adaptive_boundary_data_lst(cfg4.wavefront_soln))
+        exact = cfg4.wavefront_soln(dom.interior_points)
+        errs.append(np.abs(u - exact).max() / np.abs(exact).max())
+    assert errs[0] < 5e-2 and errs[1] < errs[0], errs
