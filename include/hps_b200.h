@@ -260,18 +260,22 @@ int hps_adaptive_compress(void* stream, int npp, int group, int n_src, int n, co
  * dense_B = 1) or block by block from bs_tbl, a HOST array [n_blocks][7] = {child, row0, col0, M, K,
  * first row of S, first row of T_out} listing the non-zero blocks of B inside the children's operators
  * (an exterior face times an interface face of the same child: 72 blocks in 3D, 16 in 2D — a quarter of
- * the dense flops).  Replaces _oct_merge / _adaptive_quad_merge_2D_DtN +
+ * the dense flops).  [ext_panel0, ext_panel0 + n_ext_panels_loc) selects the exterior COLUMNS of S that are
+ * produced (S then has n_ext_panels_loc*npp columns): the full range normally (required when want_T), one
+ * rank's share in the column-sharded root merge of the multi-GPU build.  Replaces _oct_merge / _adaptive_quad_merge_2D_DtN +
  * assemble_merge_outputs_DtN (merge/_schur_complement.py:117-237). */
 int hps_merge_adaptive_workspace(int n_int, int n_ext, int dense_B, size_t* bytes);
 int hps_merge_adaptive(void* stream, int npp, int n_src, int n_child, const double* const* T_child,
                        const double* const* h_child, const int* ld_child, int n_int_panels, const int* int_tbl,
                        int n_ext_panels, const int* ext_tbl, double* S, double* g_tilde, double* T_out, double* h_out,
-                       int want_T, int n_blocks, const int* bs_tbl, void* ws, size_t ws_bytes, int* info);
+                       int want_T, int n_blocks, const int* bs_tbl, int ext_panel0, int n_ext_panels_loc, void* ws,
+                       size_t ws_bytes, int* info);
 /* hps_down_adaptive: g_int = S g_ext + g_tilde, then every child's boundary vector.  g_child: HOST
  * array of n_child device pointers; tbl[t] = {child, source panel, start, width, rev}: the run
  * [start, start + width*npp) of that child's vector comes from source panel sp (sp < NE: exterior
  * panel of g_ext, else interface panel sp - NE of g_int), re-refined with L_refine when width > 1.
- * ws: n_int * n_src doubles.  Replaces _propagate_down_oct / _propogate_down_quad. */
+ * ws: n_int * n_src doubles.  S == NULL: ws already holds g_int (multi-GPU root level, where g_int is the
+ * all-reduced sum of the ranks' partial products).  Replaces _propagate_down_oct / _propogate_down_quad. */
 int hps_down_adaptive(void* stream, int npp, int n_src, int n_int, int n_ext, const double* S, const double* g_ext,
                       const double* g_tilde, int n_child, double* const* g_child, int n_tbl, const int* tbl,
                       const double* L_refine, void* ws);

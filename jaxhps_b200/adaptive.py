@@ -255,7 +255,7 @@ def _merge_adaptive(pde_problem, T_arr, h_arr, device, host_device, return_T: bo
                                         _lib.ptr(S), _lib.ptr(g), _lib.ptr(T_out), _lib.ptr(h_out), 1 if want_T else 0,
                                         blocks.shape[0] if sparse else 0,
                                         blocks.ctypes.data_as(ctypes.POINTER(ctypes.c_int)) if sparse else None,
-                                        _lib.ptr(ws), ws.numel(), _lib.ptr(info[n_idx:]))
+                                        0, np_.ext_tbl.shape[0], _lib.ptr(ws), ws.numel(), _lib.ptr(info[n_idx:]))
             _lib.check(rc, "hps_merge_adaptive")
             st.S[id(node)], st.g[id(node)] = S, g
             if want_T:

@@ -97,10 +97,13 @@ __global__ void __launch_bounds__(256) adaptive_gather_kernel(ChildSet cs, int n
                                                               const int* __restrict__ ext_tbl, double* __restrict__ D,
                                                               double* __restrict__ S, double* __restrict__ gt,
                                                               double* __restrict__ T_out, double* __restrict__ h_out,
-                                                              double* __restrict__ B, int want_T) {
+                                                              double* __restrict__ B, int want_T, int ext0,
+                                                              int n_ext_loc) {
+  // exterior COLUMNS [ext0, ext0 + n_ext_loc) only (S has leading dimension n_ext_loc): the whole range for
+  // an ordinary merge, one rank's share for the column-sharded root merge of the multi-GPU build
   const int n_int = NI * npp, n_ext = NE * npp;
   const int n_rows = want_T ? n_int + n_ext : n_int;
-  const int n_cols = n_int + n_ext + n_src;
+  const int n_cols = n_int + n_ext_loc + n_src;
   for (int row = blockIdx.y; row < n_rows; row += gridDim.y) {
     const bool irow = row < n_int;
     const int rl = irow ? row : row - n_int;
@@ -115,10 +118,11 @@ __global__ void __launch_bounds__(256) adaptive_gather_kernel(ChildSet cs, int n
     const double* row0 = cs.T[c0] + (int64_t)i0 * cs.ld[c0];
     const double* row1 = c1 >= 0 ? cs.T[c1] + (int64_t)i1 * cs.ld[c1] : nullptr;
     for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < n_cols; col += gridDim.x * blockDim.x) {
-      if (col < n_int + n_ext) {
+      if (col < n_int + n_ext_loc) {
         const bool icol = col < n_int;
         const int cl = icol ? col : col - n_int;
-        const int Q = cl / npp, cc = cl - Q * npp;
+        const int cg = icol ? col : cl + ext0;  // position among all interface / exterior points
+        const int Q = cg / npp, cc = cg - Q * npp;
         int d0, q0, d1 = -1, q1 = 0;
         if (icol) {
           d0 = int_tbl[4 * Q], q0 = int_tbl[4 * Q + 1], d1 = int_tbl[4 * Q + 2], q1 = int_tbl[4 * Q + 3];
@@ -133,11 +137,11 @@ __global__ void __launch_bounds__(256) adaptive_gather_kernel(ChildSet cs, int n
           else if (d1 == c1) v += row1[q1 * npp + cc];
         }
         if (irow && icol) D[(int64_t)row * n_int + col] = v;
-        else if (irow) S[(int64_t)row * n_ext + cl] = -v;
+        else if (irow) S[(int64_t)row * n_ext_loc + cl] = -v;
         else if (icol) { if (B) B[(int64_t)rl * n_int + col] = v; }
         else T_out[(int64_t)rl * n_ext + cl] = v;
       } else {
-        const int k = col - n_int - n_ext;
+        const int k = col - n_int - n_ext_loc;
         if (irow) gt[(int64_t)row * n_src + k] = -(cs.h[c0][(int64_t)i0 * n_src + k] + cs.h[c1][(int64_t)i1 * n_src + k]);
         else h_out[(int64_t)rl * n_src + k] = cs.h[c0][(int64_t)i0 * n_src + k];
       }
@@ -213,10 +217,12 @@ size_t merge_adaptive_ws_bytes(int n_int, int n_ext, int dense_B) {
 int merge_adaptive(cudaStream_t st, int npp, int n_src, int n_child, const double* const* T_child,
                    const double* const* h_child, const int* ld_child, int NI, const int* int_tbl, int NE,
                    const int* ext_tbl, double* S, double* gt, double* T_out, double* h_out, int want_T, int n_blocks,
-                   const int* bs_tbl, void* ws, size_t ws_bytes, int* info) {
+                   const int* bs_tbl, int ext_panel0, int n_ext_panels_loc, void* ws, size_t ws_bytes, int* info) {
   if (npp <= 0 || n_src <= 0 || NI <= 0 || NE <= 0) return fail_arg(2, "non-positive size");
+  if (ext_panel0 < 0 || n_ext_panels_loc <= 0 || ext_panel0 + n_ext_panels_loc > NE) return fail_arg(20, "exterior window out of range");
+  if (want_T && (ext_panel0 != 0 || n_ext_panels_loc != NE)) return fail_arg(20, "T needs the full exterior window");
   if (n_child <= 0 || n_child > MAXC) return fail_arg(4, "n_child must be 1..8");
-  const int n_int = NI * npp, n_ext = NE * npp;
+  const int n_int = NI * npp, n_ext = NE * npp, n_ext_loc = n_ext_panels_loc * npp;
   Arena ar(ws, ws_bytes);
   double* D = ar.take<double>((size_t)n_int * n_int);
   const bool dense_B = want_T && (n_blocks <= 0 || !bs_tbl);
@@ -228,14 +234,15 @@ int merge_adaptive(cudaStream_t st, int npp, int n_src, int n_child, const doubl
   for (int c = 0; c < n_child; ++c) cs.T[c] = T_child[c], cs.h[c] = h_child[c], cs.ld[c] = ld_child[c];
   {
     const int rows = want_T ? n_int + n_ext : n_int;
-    const int cols = n_int + n_ext + n_src;
+    const int cols = n_int + n_ext_loc + n_src;
     dim3 grid(std::min((cols + 255) / 256, 64), std::min(rows, 65535));
     prof_begin(PROF_GATHER, st, 8.0 * (double)rows * (n_int + n_ext));
-    adaptive_gather_kernel<<<grid, 256, 0, st>>>(cs, npp, n_src, NI, NE, int_tbl, ext_tbl, D, S, gt, T_out, h_out, B, want_T);
+    adaptive_gather_kernel<<<grid, 256, 0, st>>>(cs, npp, n_src, NI, NE, int_tbl, ext_tbl, D, S, gt, T_out, h_out, B, want_T,
+                                                 ext_panel0 * npp, n_ext_loc);
     prof_end(PROF_GATHER, st);
     HPS_LAUNCH_CHECK("adaptive_gather_kernel");
   }
-  RhsDesc rhs[2] = {{S, n_ext, 0, n_ext}, {gt, n_src, 0, n_src}};
+  RhsDesc rhs[2] = {{S, n_ext_loc, 0, n_ext_loc}, {gt, n_src, 0, n_src}};
   HPS_TRY(lu_solve(st, 1, n_int, D, n_int, 0, 2, rhs, lu_ws, lu_ws_bytes, info));
   if (!want_T) return 0;
   // T = A + B S, h = h_ext + B g~
@@ -265,7 +272,8 @@ int down_adaptive(cudaStream_t st, int npp, int n_src, int n_int, int n_ext, con
   if (npp <= 0 || n_src <= 0 || n_int <= 0 || n_ext <= 0 || n_tbl <= 0) return fail_arg(2, "non-positive size");
   if (n_child <= 0 || n_child > MAXC) return fail_arg(10, "n_child must be 1..8");
   double* g_int = static_cast<double*>(ws);
-  HPS_TRY(dgemm_affine(st, n_int, n_src, n_ext, S, n_ext, 0, g_ext, n_src, 0, gt, n_src, 0, g_int, n_src, 0, 1));
+  // S == NULL: ws already holds g_int (multi-GPU root: the all-reduced sum of the ranks' partial products)
+  if (S) HPS_TRY(dgemm_affine(st, n_int, n_src, n_ext, S, n_ext, 0, g_ext, n_src, 0, gt, n_src, 0, g_int, n_src, 0, 1));
   ChildOut out = {};
   for (int c = 0; c < n_child; ++c) out.g[c] = g_child[c];
   adaptive_down_kernel<<<n_tbl, 128, 0, st>>>(out, npp, n_src, n_ext / npp, tbl, g_ext, g_int, L_refine);

@@ -298,10 +298,11 @@ int hps_merge_adaptive_workspace(int n_int, int n_ext, int dense_B, size_t* byte
 int hps_merge_adaptive(void* stream, int npp, int n_src, int n_child, const double* const* T_child,
                        const double* const* h_child, const int* ld_child, int n_int_panels, const int* int_tbl,
                        int n_ext_panels, const int* ext_tbl, double* S, double* g_tilde, double* T_out, double* h_out,
-                       int want_T, int n_blocks, const int* bs_tbl, void* ws, size_t ws_bytes, int* info) {
+                       int want_T, int n_blocks, const int* bs_tbl, int ext_panel0, int n_ext_panels_loc, void* ws,
+                       size_t ws_bytes, int* info) {
   return merge_adaptive(static_cast<cudaStream_t>(stream), npp, n_src, n_child, T_child, h_child, ld_child, n_int_panels,
-                        int_tbl, n_ext_panels, ext_tbl, S, g_tilde, T_out, h_out, want_T, n_blocks, bs_tbl, ws, ws_bytes,
-                        info);
+                        int_tbl, n_ext_panels, ext_tbl, S, g_tilde, T_out, h_out, want_T, n_blocks, bs_tbl, ext_panel0,
+                        n_ext_panels_loc, ws, ws_bytes, info);
 }
 int hps_down_adaptive(void* stream, int npp, int n_src, int n_int, int n_ext, const double* S, const double* g_ext,
                       const double* g_tilde, int n_child, double* const* g_child, int n_tbl, const int* tbl,
