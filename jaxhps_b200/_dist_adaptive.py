@@ -91,6 +91,15 @@ class CudaAdaptiveOps:
         self.lib = _lib.load()
         self.dev = _lib.require_cuda(device)
         self._tables = None
+        self._resident = {}  # host array id -> device copy (kept alive: raw pointers are handed to the kernels)
+
+    def _dev(self, x):
+        if isinstance(x, torch.Tensor):
+            return x
+        key = id(x)
+        if key not in self._resident:
+            self._resident[key] = (x, self._lib.to_device(x, self.dev))
+        return self._resident[key][1]
 
     # -- plumbing
     def to_array(self, x):
@@ -149,9 +158,10 @@ class CudaAdaptiveOps:
         self._lib.check(self.lib.hps_adaptive_compress_workspace(ch.n, ch.n_out // npp, npp, ctypes.byref(need)), "ws query")
         ws = self._lib.WORKSPACE.get(need.value, self.dev)
         T2, h2 = self.empty((ch.n_out, ch.n_out)), self.empty((ch.n_out, h.shape[1]))
+        T, h = T.contiguous(), h.contiguous()
         rc = self.lib.hps_adaptive_compress(self._lib.stream_ptr(), npp, root_plan.group, h.shape[1], ch.n, T.data_ptr(),
-                                            h.contiguous().data_ptr(), ch.n_out // npp, self._root_tables(root_plan)[f"seg{c}"],
-                                            self.to_array(L_refine).data_ptr(), self.to_array(L_coarsen).data_ptr(),
+                                            h.data_ptr(), ch.n_out // npp, self._root_tables(root_plan)[f"seg{c}"],
+                                            self._dev(L_refine).data_ptr(), self._dev(L_coarsen).data_ptr(),
                                             T2.data_ptr(), h2.data_ptr(), ws.data_ptr(), ws.numel())
         self._lib.check(rc, "hps_adaptive_compress")
         return T2, h2
@@ -184,10 +194,10 @@ class CudaAdaptiveOps:
         n_src = g_ext.shape[1]
         outs = [self.empty((ch.n, n_src)) for ch in root_plan.children]
         ptrs = (ctypes.c_void_p * len(outs))(*[t.data_ptr() for t in outs])
-        ws = g_int.contiguous()
+        ws, g_ext = g_int.contiguous(), g_ext.contiguous()
         rc = self.lib.hps_down_adaptive(self._lib.stream_ptr(), root_plan.npp, n_src, root_plan.n_int, root_plan.n_ext, None,
-                                        g_ext.contiguous().data_ptr(), None, len(outs), ptrs, root_plan.down_tbl.shape[0],
-                                        self._root_tables(root_plan)["down"], self.to_array(L_refine).data_ptr(), ws.data_ptr())
+                                        g_ext.data_ptr(), None, len(outs), ptrs, root_plan.down_tbl.shape[0],
+                                        self._root_tables(root_plan)["down"], self._dev(L_refine).data_ptr(), ws.data_ptr())
         self._lib.check(rc, "hps_down_adaptive (root scatter)")
         return outs
 

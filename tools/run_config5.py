@@ -88,6 +88,65 @@ def build_problem(dom):
                           D_x_coefficients=d_perm_x(X), D_y_coefficients=d_perm_y(X), D_z_coefficients=d_perm_z(X))
 
 
+def main_sharded(args):
+    """One process per GPU (torchrun): root octants are split over the ranks (`jaxhps_b200/_dist_adaptive.py`)."""
+    import torch
+    import torch.distributed as dist
+
+    import jaxhps_b200 as hps
+    from jaxhps_b200 import _dist_adaptive as da
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    root = hps.DiscretizationNode3D(-1.0, 1.0, -1.0, 1.0, -1.0, 1.0)
+    dom = hps.Domain(p=args.p, q=args.p - 2, root=decode_tree(root, np.load(args.load_tree), args.p - 2))
+    pb = build_problem(dom)
+    g = dom.get_adaptive_boundary_data_lst(lambda x: np.zeros(x.shape[:-1]))
+    ops = da.CudaAdaptiveOps(torch.device("cuda", local))
+
+    def timed(fn):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return out, float(t) / 1e3
+
+    for _ in range(args.repeat):
+        st, t_build = timed(lambda: da.build_solver_sharded_adaptive(pb, ops))
+        (u, sl), t_solve = timed(lambda: da.solve_sharded_adaptive(st, g, ops))
+    parts = [torch.empty((n, u.shape[1], u.shape[2]), dtype=torch.float64, device="cuda") for n in st["shard"].leaves_per_rank]
+    if world > 1:
+        dist.all_gather(parts, u.contiguous())
+    else:
+        parts = [u]
+    if rank == 0:
+        u_all = torch.cat(parts)[..., 0].cpu().numpy()
+        rec = dict(config="Poisson-Boltzmann adaptive 3D, subtree-sharded", n_gpus=world, p=args.p, q=args.p - 2,
+                   n_leaves=dom.n_leaves, leaves_per_rank=st["shard"].leaves_per_rank, build_s=round(t_build, 4),
+                   solve_s=round(t_solve, 4), u_max=float(np.abs(u_all).max()),
+                   gpu_mem_GB=round(torch.cuda.max_memory_allocated() / 2**30, 2))
+        probe_file = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                                  f"config5_oracle_probe_p{args.p}.npz")
+        if os.path.exists(probe_file):
+            ref = np.load(probe_file)
+            mine = u_all.reshape(-1)[:: int(ref["stride"])]
+            if mine.shape == ref["u_probe"].shape:
+                rec["rel_err_vs_oracle"] = float(np.abs(mine - ref["u_probe"]).max() / np.abs(ref["u_probe"]).max())
+        print(json.dumps(rec), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--p", type=int, default=10)
@@ -96,7 +155,10 @@ def main():
     ap.add_argument("--repeat", type=int, default=2)
     ap.add_argument("--save-tree", default=None, help="write the refinement pattern (pre-order has-children flags) here")
     ap.add_argument("--load-tree", default=None, help="skip mesh generation and rebuild the octree from this file")
+    ap.add_argument("--sharded", action="store_true", help="subtree-sharded build over the ranks of a torchrun launch")
     args = ap.parse_args()
+    if args.sharded:
+        return main_sharded(args)
     import jaxhps_b200 as hps
     from jaxhps_b200._tree import get_all_leaves
 
