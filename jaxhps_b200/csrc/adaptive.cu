@@ -88,63 +88,86 @@ __global__ void __launch_bounds__(256) compress_rows_kernel(const double* __rest
   }
 }
 
-// One pass over the (n_int + n_ext) x (n_int + n_ext + n_src) block system of a merge:
-//   [ D   -S | -g~ ]        rows: interface panels, then exterior panels (parent order)
-//   [ B    A | h_ext ]
-// An entry couples two panels only through a child that owns both.
-__global__ void __launch_bounds__(256) adaptive_gather_kernel(ChildSet cs, int npp, int n_src, int NI, int NE,
+// The (n_int + n_ext) x (n_int + n_ext) block system of a merge, one npp x npp tile per CTA:
+//   [ D   -S ]        rows: interface panels, then exterior panels (parent order)
+//   [ B    A ]
+// A tile couples two panels only through a child that owns both, so the two table look-ups are done
+// once per tile and the body is a plain (sum of at most two) tile copy: HBM-bound, 512-byte rows.
+// Exterior COLUMNS are restricted to the window [ext0, ext0 + NEloc) panels (S has leading dimension
+// NEloc*npp): the whole range for an ordinary merge, one rank's share for the column-sharded root merge.
+// grid: (NI + NEloc column panels, row panels); block 256
+__global__ void __launch_bounds__(256) adaptive_gather_kernel(ChildSet cs, int npp, int NI, int NE,
                                                               const int* __restrict__ int_tbl,
                                                               const int* __restrict__ ext_tbl, double* __restrict__ D,
-                                                              double* __restrict__ S, double* __restrict__ gt,
-                                                              double* __restrict__ T_out, double* __restrict__ h_out,
-                                                              double* __restrict__ B, int want_T, int ext0,
-                                                              int n_ext_loc) {
-  // exterior COLUMNS [ext0, ext0 + n_ext_loc) only (S has leading dimension n_ext_loc): the whole range for
-  // an ordinary merge, one rank's share for the column-sharded root merge of the multi-GPU build
-  const int n_int = NI * npp, n_ext = NE * npp;
-  const int n_rows = want_T ? n_int + n_ext : n_int;
-  const int n_cols = n_int + n_ext_loc + n_src;
-  for (int row = blockIdx.y; row < n_rows; row += gridDim.y) {
-    const bool irow = row < n_int;
-    const int rl = irow ? row : row - n_int;
-    const int P = rl / npp, rr = rl - P * npp;
-    int c0, p0, c1 = -1, p1 = 0;
-    if (irow) {
-      c0 = int_tbl[4 * P], p0 = int_tbl[4 * P + 1], c1 = int_tbl[4 * P + 2], p1 = int_tbl[4 * P + 3];
+                                                              double* __restrict__ S, double* __restrict__ T_out,
+                                                              double* __restrict__ B, int ext0, int NEloc) {
+  const int n_int = NI * npp, n_ext = NE * npp, n_ext_loc = NEloc * npp;
+  const int Pr = blockIdx.y, Pc = blockIdx.x;
+  const bool irow = Pr < NI, icol = Pc < NI;
+  int c0, p0, c1 = -1, p1 = 0;
+  if (irow) {
+    c0 = int_tbl[4 * Pr], p0 = int_tbl[4 * Pr + 1], c1 = int_tbl[4 * Pr + 2], p1 = int_tbl[4 * Pr + 3];
+  } else {
+    c0 = ext_tbl[2 * (Pr - NI)], p0 = ext_tbl[2 * (Pr - NI) + 1];
+  }
+  int d0, q0, d1 = -1, q1 = 0;
+  if (icol) {
+    d0 = int_tbl[4 * Pc], q0 = int_tbl[4 * Pc + 1], d1 = int_tbl[4 * Pc + 2], q1 = int_tbl[4 * Pc + 3];
+  } else {
+    const int E = Pc - NI + ext0;
+    d0 = ext_tbl[2 * E], q0 = ext_tbl[2 * E + 1];
+  }
+  // up to two source tiles: (child, row panel, col panel)
+  const double* srcA = nullptr;
+  const double* srcB = nullptr;
+  int ldA = 0, ldB = 0;
+  auto add = [&](int c, int pr, int pc) {
+    const double* s = cs.T[c] + (int64_t)pr * npp * cs.ld[c] + (int64_t)pc * npp;
+    if (!srcA) srcA = s, ldA = cs.ld[c];
+    else srcB = s, ldB = cs.ld[c];
+  };
+  if (d0 == c0) add(c0, p0, q0);
+  else if (d0 == c1) add(c1, p1, q0);
+  if (d1 >= 0) {
+    if (d1 == c0) add(c0, p0, q1);
+    else if (d1 == c1) add(c1, p1, q1);
+  }
+  double* dst;
+  int64_t ldd;
+  double sign = 1.0;
+  if (irow && icol) dst = D + (int64_t)Pr * npp * n_int + (int64_t)Pc * npp, ldd = n_int;
+  else if (irow) dst = S + (int64_t)Pr * npp * n_ext_loc + (int64_t)(Pc - NI) * npp, ldd = n_ext_loc, sign = -1.0;
+  else if (icol) {
+    if (!B) return;
+    dst = B + (int64_t)(Pr - NI) * npp * n_int + (int64_t)Pc * npp, ldd = n_int;
+  } else dst = T_out + (int64_t)(Pr - NI) * npp * n_ext + (int64_t)(Pc - NI) * npp, ldd = n_ext;
+  for (int e = threadIdx.x; e < npp * npp; e += blockDim.x) {
+    const int rr = e / npp, cc = e - rr * npp;
+    double v = 0.0;
+    if (srcA) v = srcA[(int64_t)rr * ldA + cc];
+    if (srcB) v += srcB[(int64_t)rr * ldB + cc];
+    dst[(int64_t)rr * ldd + cc] = sign * v;
+  }
+}
+
+// right-hand sides: g~ := -(h_A + h_B) on the interface rows, h_out := h of the owner on the exterior rows
+__global__ void __launch_bounds__(256) adaptive_gather_rhs_kernel(ChildSet cs, int npp, int n_src, int NI, int NE,
+                                                                  const int* __restrict__ int_tbl,
+                                                                  const int* __restrict__ ext_tbl,
+                                                                  double* __restrict__ gt, double* __restrict__ h_out,
+                                                                  int want_T) {
+  const int n_int = NI * npp;
+  const int64_t total = (int64_t)(want_T ? (NI + NE) : NI) * npp * n_src;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(e / n_src), k = (int)(e - (int64_t)row * n_src);
+    if (row < n_int) {
+      const int P = row / npp, rr = row - P * npp;
+      const int c0 = int_tbl[4 * P], p0 = int_tbl[4 * P + 1], c1 = int_tbl[4 * P + 2], p1 = int_tbl[4 * P + 3];
+      gt[(int64_t)row * n_src + k] = -(cs.h[c0][(int64_t)(p0 * npp + rr) * n_src + k] + cs.h[c1][(int64_t)(p1 * npp + rr) * n_src + k]);
     } else {
-      c0 = ext_tbl[2 * P], p0 = ext_tbl[2 * P + 1];
-    }
-    const int i0 = p0 * npp + rr, i1 = p1 * npp + rr;
-    const double* row0 = cs.T[c0] + (int64_t)i0 * cs.ld[c0];
-    const double* row1 = c1 >= 0 ? cs.T[c1] + (int64_t)i1 * cs.ld[c1] : nullptr;
-    for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < n_cols; col += gridDim.x * blockDim.x) {
-      if (col < n_int + n_ext_loc) {
-        const bool icol = col < n_int;
-        const int cl = icol ? col : col - n_int;
-        const int cg = icol ? col : cl + ext0;  // position among all interface / exterior points
-        const int Q = cg / npp, cc = cg - Q * npp;
-        int d0, q0, d1 = -1, q1 = 0;
-        if (icol) {
-          d0 = int_tbl[4 * Q], q0 = int_tbl[4 * Q + 1], d1 = int_tbl[4 * Q + 2], q1 = int_tbl[4 * Q + 3];
-        } else {
-          d0 = ext_tbl[2 * Q], q0 = ext_tbl[2 * Q + 1];
-        }
-        double v = 0.0;
-        if (d0 == c0) v += row0[q0 * npp + cc];
-        else if (d0 == c1) v += row1[q0 * npp + cc];
-        if (d1 >= 0) {
-          if (d1 == c0) v += row0[q1 * npp + cc];
-          else if (d1 == c1) v += row1[q1 * npp + cc];
-        }
-        if (irow && icol) D[(int64_t)row * n_int + col] = v;
-        else if (irow) S[(int64_t)row * n_ext_loc + cl] = -v;
-        else if (icol) { if (B) B[(int64_t)rl * n_int + col] = v; }
-        else T_out[(int64_t)rl * n_ext + cl] = v;
-      } else {
-        const int k = col - n_int - n_ext_loc;
-        if (irow) gt[(int64_t)row * n_src + k] = -(cs.h[c0][(int64_t)i0 * n_src + k] + cs.h[c1][(int64_t)i1 * n_src + k]);
-        else h_out[(int64_t)rl * n_src + k] = cs.h[c0][(int64_t)i0 * n_src + k];
-      }
+      const int rl = row - n_int, P = rl / npp, rr = rl - P * npp;
+      const int c0 = ext_tbl[2 * P], p0 = ext_tbl[2 * P + 1];
+      h_out[(int64_t)rl * n_src + k] = cs.h[c0][(int64_t)(p0 * npp + rr) * n_src + k];
     }
   }
 }
@@ -233,14 +256,18 @@ int merge_adaptive(cudaStream_t st, int npp, int n_src, int n_child, const doubl
   ChildSet cs = {};
   for (int c = 0; c < n_child; ++c) cs.T[c] = T_child[c], cs.h[c] = h_child[c], cs.ld[c] = ld_child[c];
   {
-    const int rows = want_T ? n_int + n_ext : n_int;
-    const int cols = n_int + n_ext_loc + n_src;
-    dim3 grid(std::min((cols + 255) / 256, 64), std::min(rows, 65535));
-    prof_begin(PROF_GATHER, st, 8.0 * (double)rows * (n_int + n_ext));
-    adaptive_gather_kernel<<<grid, 256, 0, st>>>(cs, npp, n_src, NI, NE, int_tbl, ext_tbl, D, S, gt, T_out, h_out, B, want_T,
-                                                 ext_panel0 * npp, n_ext_loc);
+    const int row_panels = want_T ? NI + NE : NI;
+    if (row_panels > 65535) return fail_arg(8, "merge_adaptive: more than 65535 boundary panels");
+    dim3 grid(NI + n_ext_panels_loc, row_panels);
+    prof_begin(PROF_GATHER, st, 8.0 * (double)row_panels * npp * (n_int + n_ext_loc));
+    adaptive_gather_kernel<<<grid, 256, 0, st>>>(cs, npp, NI, NE, int_tbl, ext_tbl, D, S, T_out, B, ext_panel0,
+                                                 n_ext_panels_loc);
     prof_end(PROF_GATHER, st);
     HPS_LAUNCH_CHECK("adaptive_gather_kernel");
+    const int64_t total = (int64_t)row_panels * npp * n_src;
+    adaptive_gather_rhs_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 1024), 256, 0, st>>>(
+        cs, npp, n_src, NI, NE, int_tbl, ext_tbl, gt, h_out, want_T);
+    HPS_LAUNCH_CHECK("adaptive_gather_rhs_kernel");
   }
   RhsDesc rhs[2] = {{S, n_ext_loc, 0, n_ext_loc}, {gt, n_src, 0, n_src}};
   HPS_TRY(lu_solve(st, 1, n_int, D, n_int, 0, 2, rhs, lu_ws, lu_ws_bytes, info));

@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--repeat", type=int, default=2)
     ap.add_argument("--save-tree", default=None, help="write the refinement pattern (pre-order has-children flags) here")
     ap.add_argument("--load-tree", default=None, help="skip mesh generation and rebuild the octree from this file")
+    ap.add_argument("--prof", action="store_true", help="per-category device times of the library's kernels (CUDA events)")
     ap.add_argument("--sharded", action="store_true", help="subtree-sharded build over the ranks of a torchrun launch")
     args = ap.parse_args()
     if args.sharded:
@@ -181,12 +182,32 @@ def main():
 
         pb = build_problem(dom)
         g = dom.get_adaptive_boundary_data_lst(lambda x: np.zeros(x.shape[:-1]))
-        for _ in range(args.repeat):
+        import ctypes
+
+        from jaxhps_b200 import _lib
+
+        for rep in range(args.repeat):
+            if args.prof and rep == args.repeat - 1:
+                _lib.load().hps_prof_enable(1)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
+            a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_ev.record()
             hps.build_solver(pb, host_device="cuda")
+            b_ev.record()
             torch.cuda.synchronize()
             t_build = time.perf_counter() - t0
+            rec["build_device_s"] = round(a_ev.elapsed_time(b_ev) / 1e3, 4)
+            if args.prof and rep == args.repeat - 1:
+                pm, pw, pl = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_int64 * 8)()
+                allk = ctypes.c_int64()
+                _lib.load().hps_prof_read(_lib.stream_ptr(), pm, pw, pl, ctypes.byref(allk))
+                _lib.load().hps_prof_enable(0)
+                names = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "gather", "skinny", "leaf_assemble"]
+                rec["prof_ms"] = {n: round(pm[i], 1) for i, n in enumerate(names)}
+                rec["prof_launches"] = {n: int(pl[i]) for i, n in enumerate(names)}
+                rec["gemm_TFLOPs"] = round(pw[0] / 1e12, 2)
+                rec["all_launches"] = int(allk.value)
             t0 = time.perf_counter()
             u = hps.solve(pb, g)
             t_solve = time.perf_counter() - t0
