@@ -270,6 +270,12 @@ int hps_merge_adaptive(void* stream, int npp, int n_src, int n_child, const doub
                        int n_ext_panels, const int* ext_tbl, double* S, double* g_tilde, double* T_out, double* h_out,
                        int want_T, int n_blocks, const int* bs_tbl, int ext_panel0, int n_ext_panels_loc, void* ws,
                        size_t ws_bytes, int* info);
+/* Assembly half of hps_merge_adaptive for callers that factor D themselves (the multi-GPU root merge runs
+ * hps_lu_dist_* on it): D (n_int x n_int), S := -C over the exterior window, g_tilde := -h_int. */
+int hps_merge_adaptive_assemble(void* stream, int npp, int n_src, int n_child, const double* const* T_child,
+                                const double* const* h_child, const int* ld_child, int n_int_panels, const int* int_tbl,
+                                int n_ext_panels, const int* ext_tbl, double* D, double* S, double* g_tilde, int ext_panel0,
+                                int n_ext_panels_loc);
 /* hps_down_adaptive: g_int = S g_ext + g_tilde, then every child's boundary vector.  g_child: HOST
  * array of n_child device pointers; tbl[t] = {child, source panel, start, width, rev}: the run
  * [start, start + width*npp) of that child's vector comes from source panel sp (sp < NE: exterior

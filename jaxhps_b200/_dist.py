@@ -99,6 +99,86 @@ def _operator_template(domain) -> PDEProblem:
     return _TEMPLATES[key]
 
 
+def distributed_lu_solve(_lib, dev, D, rhs, rank: int, world: int, group=None) -> None:
+    """In-place ``rhs[k] := D^-1 rhs[k]`` with the factorisation of ``D`` (n x n, replicated on every rank)
+    distributed over the ranks: block column b (128 wide) is factored by rank ``b % world``, the packed column is
+    broadcast with NCCL and every rank applies it to the block columns it owns; a high-priority side stream keeps
+    the panel chain (update of the NEXT block column, its factorisation, the broadcast) one block ahead of the
+    main stream's rank-128 updates (look-ahead).  Afterwards every rank holds the complete factors and runs the
+    substitutions on its own right-hand sides (each rank may pass different ones)."""
+    import ctypes
+
+    lib = _lib.load()
+    n = D.shape[0]
+    NB = 128
+    nblk = (n + NB - 1) // NB
+    need = ctypes.c_size_t()
+    _lib.check(lib.hps_lu_solve_workspace(1, n, ctypes.byref(need)), "workspace query")
+    ws = _lib.WORKSPACE.get(need.value, dev)
+    cnt = ctypes.c_size_t()
+    _lib.check(lib.hps_lu_dist_buffer_doubles(n, ctypes.byref(cnt)), "buffer query")
+    bufs = [torch.empty((cnt.value,), dtype=torch.float64, device=dev) for _ in range(2)]
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    main = torch.cuda.current_stream()
+    side = _side_stream(dev)
+    ev_panel = [torch.cuda.Event() for _ in range(2)]
+    ev_upd = [torch.cuda.Event() for _ in range(2)]
+    A, wsp, wsn = D.data_ptr(), ws.data_ptr(), ws.numel()
+
+    def owner_of(b):
+        return b % world
+
+    def bcast(buf, owner):
+        if world > 1:
+            dist.broadcast(buf, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+
+    side.wait_stream(main)  # D and the right-hand sides are ready
+    with torch.cuda.stream(side):
+        if rank == owner_of(0):
+            _lib.check(lib.hps_lu_dist_factor_pack(side.cuda_stream, n, A, n, 0, wsp, wsn, info.data_ptr(),
+                                                   bufs[0].data_ptr()), "hps_lu_dist_factor_pack")
+        bcast(bufs[0], owner_of(0))
+        if rank != owner_of(0):
+            _lib.check(lib.hps_lu_dist_unpack(side.cuda_stream, n, A, n, 0, wsp, wsn, bufs[0].data_ptr()), "hps_lu_dist_unpack")
+        ev_panel[0].record(side)
+    for b in range(nblk):
+        nb1 = b + 1
+        i_own_next = nb1 < nblk and rank == owner_of(nb1)
+        if nb1 < nblk:
+            with torch.cuda.stream(side):
+                buf = bufs[nb1 & 1]
+                if i_own_next:
+                    if b >= 1:
+                        side.wait_event(ev_upd[(b - 1) & 1])  # column nb1 has received blocks < b on the main stream
+                    _lib.check(lib.hps_lu_dist_update(side.cuda_stream, n, A, n, b, nb1, 1, 1, 0, wsp, wsn),
+                               "hps_lu_dist_update (look-ahead)")
+                    _lib.check(lib.hps_lu_dist_factor_pack(side.cuda_stream, n, A, n, nb1, wsp, wsn, info.data_ptr(),
+                                                           buf.data_ptr()), "hps_lu_dist_factor_pack")
+                bcast(buf, owner_of(nb1))
+                if not i_own_next:
+                    _lib.check(lib.hps_lu_dist_unpack(side.cuda_stream, n, A, n, nb1, wsp, wsn, buf.data_ptr()),
+                               "hps_lu_dist_unpack")
+                ev_panel[nb1 & 1].record(side)
+        # main stream: block b applied to this rank's remaining block columns (+ the left interchanges)
+        main.wait_event(ev_panel[b & 1])
+        start = nb1 + 1 if i_own_next else nb1
+        first = start + ((rank - start) % world)
+        n_own = 0 if first >= nblk else (nblk - 1 - first) // world + 1
+        _lib.check(lib.hps_lu_dist_update(main.cuda_stream, n, A, n, b, first, n_own, world, 1, wsp, wsn),
+                   "hps_lu_dist_update")
+        ev_upd[b & 1].record(main)
+    main.wait_stream(side)
+    if world > 1:
+        dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
+    _lib.check_info(info, "distributed factorisation")
+    k = len(rhs)
+    ptrs = (ctypes.c_void_p * k)(*[r.data_ptr() for r in rhs])
+    lds = (ctypes.c_int64 * k)(*[r.shape[1] for r in rhs])
+    ncs = (ctypes.c_int * k)(*[r.shape[1] for r in rhs])
+    _lib.check(lib.hps_lu_dist_solve(main.cuda_stream, n, D.data_ptr(), n, k, ptrs, lds, ncs, ws.data_ptr(), ws.numel()),
+               "hps_lu_dist_solve")
+
+
 class CudaOps:
     """Device arithmetic of the sharded driver: thin calls into the stage shims / C ABI."""
 
@@ -172,89 +252,19 @@ class CudaOps:
     def _root_solve_distributed(self, Dblk_all, hblk_all, Cblk_loc, first_child, rank, world, group):
         """Distributed LU of the root D: block column b is factored by rank b % world, broadcast, and
         applied by every rank to the block columns it owns; then local solves of the rank's columns."""
-        import ctypes
-
         lib = self._lib.load()
         _lib = self._lib
         n_local, n3, _ = Cblk_loc.shape
         m = n3 // 3
         n_src = hblk_all.shape[-1]
         n = 12 * m
-        NB = 128
-        nblk = (n + NB - 1) // NB
         D = self.empty((n, n))
         S_r = self.empty((n, n3 * n_local))
         g = self.empty((n, n_src))
         rc = lib.hps_root_assemble_oct(_lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),
                                        hblk_all.data_ptr(), Cblk_loc.data_ptr(), D.data_ptr(), S_r.data_ptr(), g.data_ptr())
         _lib.check(rc, "hps_root_assemble_oct")
-        need = ctypes.c_size_t()
-        _lib.check(lib.hps_lu_solve_workspace(1, n, ctypes.byref(need)), "workspace query")
-        ws = _lib.WORKSPACE.get(need.value, self.dev)
-        cnt = ctypes.c_size_t()
-        _lib.check(lib.hps_lu_dist_buffer_doubles(n, ctypes.byref(cnt)), "buffer query")
-        bufs = [self.empty((cnt.value,)), self.empty((cnt.value,))]
-        info = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        # Look-ahead: a high-priority side stream keeps the panel chain (update of the NEXT block column,
-        # its factorisation, the broadcast) one block ahead of the main stream's rank-128 updates.
-        main = torch.cuda.current_stream()
-        side = _side_stream(self.dev)
-        ev_panel = [torch.cuda.Event() for _ in range(2)]
-        ev_upd = [torch.cuda.Event() for _ in range(2)]
-        A, wsp, wsn = D.data_ptr(), ws.data_ptr(), ws.numel()
-
-        def owner_of(b):
-            return b % world
-
-        def bcast(buf, owner):
-            if world > 1:
-                dist.broadcast(buf, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
-
-        side.wait_stream(main)  # D, S_r, g are ready
-        with torch.cuda.stream(side):
-            if rank == owner_of(0):
-                _lib.check(lib.hps_lu_dist_factor_pack(side.cuda_stream, n, A, n, 0, wsp, wsn, info.data_ptr(),
-                                                       bufs[0].data_ptr()), "hps_lu_dist_factor_pack")
-            bcast(bufs[0], owner_of(0))
-            if rank != owner_of(0):
-                _lib.check(lib.hps_lu_dist_unpack(side.cuda_stream, n, A, n, 0, wsp, wsn, bufs[0].data_ptr()), "hps_lu_dist_unpack")
-            ev_panel[0].record(side)
-        for b in range(nblk):
-            nb1 = b + 1
-            i_own_next = nb1 < nblk and rank == owner_of(nb1)
-            if nb1 < nblk:
-                with torch.cuda.stream(side):
-                    buf = bufs[nb1 & 1]
-                    if i_own_next:
-                        if b >= 1:
-                            side.wait_event(ev_upd[(b - 1) & 1])  # column nb1 has received blocks < b on the main stream
-                        _lib.check(lib.hps_lu_dist_update(side.cuda_stream, n, A, n, b, nb1, 1, 1, 0, wsp, wsn),
-                                   "hps_lu_dist_update (look-ahead)")
-                        _lib.check(lib.hps_lu_dist_factor_pack(side.cuda_stream, n, A, n, nb1, wsp, wsn, info.data_ptr(),
-                                                               buf.data_ptr()), "hps_lu_dist_factor_pack")
-                    bcast(buf, owner_of(nb1))
-                    if not i_own_next:
-                        _lib.check(lib.hps_lu_dist_unpack(side.cuda_stream, n, A, n, nb1, wsp, wsn, buf.data_ptr()),
-                                   "hps_lu_dist_unpack")
-                    ev_panel[nb1 & 1].record(side)
-            # main stream: block b applied to this rank's remaining block columns (+ the left interchanges)
-            main.wait_event(ev_panel[b & 1])
-            start = nb1 + 1 if i_own_next else nb1
-            first = start + ((rank - start) % world)
-            n_own = 0 if first >= nblk else (nblk - 1 - first) // world + 1
-            _lib.check(lib.hps_lu_dist_update(main.cuda_stream, n, A, n, b, first, n_own, world, 1, wsp, wsn),
-                       "hps_lu_dist_update")
-            ev_upd[b & 1].record(main)
-        main.wait_stream(side)
-        st = main.cuda_stream
-        if world > 1:
-            dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
-        _lib.check_info(info, "distributed root factorisation")
-        ptrs = (ctypes.c_void_p * 2)(S_r.data_ptr(), g.data_ptr())
-        lds = (ctypes.c_int64 * 2)(S_r.shape[1], n_src)
-        ncs = (ctypes.c_int * 2)(S_r.shape[1], n_src)
-        _lib.check(lib.hps_lu_dist_solve(st, n, D.data_ptr(), n, 2, ptrs, lds, ncs, ws.data_ptr(), ws.numel()),
-                   "hps_lu_dist_solve")
+        distributed_lu_solve(_lib, self.dev, D, [S_r, g], rank, world, group)
         return S_r, g
 
     def matvec(self, S_cols, g_slice):

@@ -9,8 +9,10 @@ Same scheme as ``_dist.py`` (the parallel form of the reference's serial subtree
   unbalanced: ``AdaptiveShardPlan.leaves_per_rank`` says by how much;
 * up: every owner coarsens its subtree roots' ``(T, h)`` for the root interfaces and broadcasts them
   (NCCL over NVLink) — the root merge needs blocks of all children;
-* the root merge is column-sharded: every rank factors the root's interface system (replicated LU) and
-  solves only its share of the exterior columns of ``S``;
+* the root merge is column-sharded: every rank assembles the root's interface system; below 8192 unknowns each
+  rank factors it on its own (replicated LU), above the ranks factor it together (``_dist.distributed_lu_solve``:
+  block columns dealt round-robin, NCCL broadcast per block column, look-ahead); each rank then solves only its
+  share of the exterior columns of ``S``;
 * down: ``g_int = sum_r S[:, cols_r] g[cols_r] + g_tilde`` is one all-reduce of an ``n_int`` vector; every
   rank then scatters the root data to its own children and runs its subtrees' down passes.
 
@@ -166,18 +168,33 @@ class CudaAdaptiveOps:
         self._lib.check(rc, "hps_adaptive_compress")
         return T2, h2
 
+    #: interface size from which the root's system is factored by all ranks together (``hps_lu_dist_*``)
+    DIST_LU_MIN_N = int(__import__("os").environ.get("HPS_DIST_LU_MIN_N", 8192))
+    FORCE_DIST_LU = False  # tests: exercise the distributed path with a single rank
+
     def root_merge(self, Ts, hs, root_plan, e0: int, e1: int):
         """This rank's columns of the root ``S`` (n_int x (e1-e0)*npp) and the full ``g_tilde``."""
         npp, n_src = root_plan.npp, hs[0].shape[1]
         off = self._root_tables(root_plan)
         S = self.empty((root_plan.n_int, (e1 - e0) * npp))
         g = self.empty((root_plan.n_int, n_src))
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        ptrs = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
+        lds = (ctypes.c_int * len(Ts))(*[t.shape[1] for t in Ts])
+        if (world > 1 or self.FORCE_DIST_LU) and root_plan.n_int >= self.DIST_LU_MIN_N:
+            from ._dist import distributed_lu_solve
+
+            D = self.empty((root_plan.n_int, root_plan.n_int))
+            rc = self.lib.hps_merge_adaptive_assemble(self._lib.stream_ptr(), npp, n_src, len(Ts), ptrs(Ts), ptrs(hs), lds,
+                                                      root_plan.int_tbl.shape[0], off["int"], root_plan.ext_tbl.shape[0],
+                                                      off["ext"], D.data_ptr(), S.data_ptr(), g.data_ptr(), e0, e1 - e0)
+            self._lib.check(rc, "hps_merge_adaptive_assemble")
+            distributed_lu_solve(self._lib, self.dev, D, [S, g], dist.get_rank() if world > 1 else 0, world)
+            return S, g
         info = torch.zeros(1, dtype=torch.int32, device=self.dev)
         need = ctypes.c_size_t()
         self._lib.check(self.lib.hps_merge_adaptive_workspace(root_plan.n_int, root_plan.n_ext, 0, ctypes.byref(need)), "ws query")
         ws = self._lib.WORKSPACE.get(need.value, self.dev)
-        ptrs = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
-        lds = (ctypes.c_int * len(Ts))(*[t.shape[1] for t in Ts])
         rc = self.lib.hps_merge_adaptive(self._lib.stream_ptr(), npp, n_src, len(Ts), ptrs(Ts), ptrs(hs), lds,
                                          root_plan.int_tbl.shape[0], off["int"], root_plan.ext_tbl.shape[0], off["ext"],
                                          S.data_ptr(), g.data_ptr(), None, None, 0, 0, None, e0, e1 - e0, ws.data_ptr(),

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "hps_merge_adaptive_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),
     "hps_merge_adaptive": (_i, [_p, _i, _i, _i, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_i), _i, _p, _i, _p,
                                 _p, _p, _p, _p, _i, _i, ctypes.POINTER(_i), _i, _i, _p, _sz, _p]),
+    "hps_merge_adaptive_assemble": (_i, [_p, _i, _i, _i, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_i), _i, _p, _i,
+                                         _p, _p, _p, _p, _i, _i]),
     "hps_down_adaptive": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, ctypes.POINTER(_p), _i, _p, _p, _p]),
 }
 

@@ -293,6 +293,30 @@ int merge_adaptive(cudaStream_t st, int npp, int n_src, int n_child, const doubl
   return 0;
 }
 
+// Assembly half of merge_adaptive (D, S := -C over the exterior window, g~ := -h_int) for callers that
+// factor D themselves: the multi-GPU root merge runs the distributed LU of lu.cu on it.
+int merge_adaptive_assemble(cudaStream_t st, int npp, int n_src, int n_child, const double* const* T_child,
+                            const double* const* h_child, const int* ld_child, int NI, const int* int_tbl, int NE,
+                            const int* ext_tbl, double* D, double* S, double* gt, int ext_panel0, int n_ext_panels_loc) {
+  if (npp <= 0 || n_src <= 0 || NI <= 0 || NE <= 0) return fail_arg(2, "non-positive size");
+  if (ext_panel0 < 0 || n_ext_panels_loc <= 0 || ext_panel0 + n_ext_panels_loc > NE) return fail_arg(15, "exterior window out of range");
+  if (n_child <= 0 || n_child > MAXC) return fail_arg(4, "n_child must be 1..8");
+  if (NI > 65535) return fail_arg(8, "merge_adaptive: more than 65535 interface panels");
+  ChildSet cs = {};
+  for (int c = 0; c < n_child; ++c) cs.T[c] = T_child[c], cs.h[c] = h_child[c], cs.ld[c] = ld_child[c];
+  dim3 grid(NI + n_ext_panels_loc, NI);
+  prof_begin(PROF_GATHER, st, 8.0 * (double)NI * npp * npp * (NI + n_ext_panels_loc));
+  adaptive_gather_kernel<<<grid, 256, 0, st>>>(cs, npp, NI, NE, int_tbl, ext_tbl, D, S, nullptr, nullptr, ext_panel0,
+                                               n_ext_panels_loc);
+  prof_end(PROF_GATHER, st);
+  HPS_LAUNCH_CHECK("adaptive_gather_kernel");
+  const int64_t total = (int64_t)NI * npp * n_src;
+  adaptive_gather_rhs_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 1024), 256, 0, st>>>(
+      cs, npp, n_src, NI, NE, int_tbl, ext_tbl, gt, nullptr, 0);
+  HPS_LAUNCH_CHECK("adaptive_gather_rhs_kernel");
+  return 0;
+}
+
 int down_adaptive(cudaStream_t st, int npp, int n_src, int n_int, int n_ext, const double* S, const double* g_ext,
                   const double* gt, int n_child, double* const* g_child, int n_tbl, const int* tbl,
                   const double* L_refine, void* ws) {

@@ -304,6 +304,13 @@ int hps_merge_adaptive(void* stream, int npp, int n_src, int n_child, const doub
                         int_tbl, n_ext_panels, ext_tbl, S, g_tilde, T_out, h_out, want_T, n_blocks, bs_tbl, ext_panel0,
                         n_ext_panels_loc, ws, ws_bytes, info);
 }
+int hps_merge_adaptive_assemble(void* stream, int npp, int n_src, int n_child, const double* const* T_child,
+                                const double* const* h_child, const int* ld_child, int n_int_panels, const int* int_tbl,
+                                int n_ext_panels, const int* ext_tbl, double* D, double* S, double* g_tilde, int ext_panel0,
+                                int n_ext_panels_loc) {
+  return merge_adaptive_assemble(static_cast<cudaStream_t>(stream), npp, n_src, n_child, T_child, h_child, ld_child,
+                                 n_int_panels, int_tbl, n_ext_panels, ext_tbl, D, S, g_tilde, ext_panel0, n_ext_panels_loc);
+}
 int hps_down_adaptive(void* stream, int npp, int n_src, int n_int, int n_ext, const double* S, const double* g_ext,
                       const double* g_tilde, int n_child, double* const* g_child, int n_tbl, const int* tbl,
                       const double* L_refine, void* ws) {

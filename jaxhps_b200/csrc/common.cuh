@@ -154,6 +154,9 @@ int merge_adaptive(cudaStream_t st, int npp, int n_src, int n_child, const doubl
                    const double* const* h_child, const int* ld_child, int NI, const int* int_tbl, int NE,
                    const int* ext_tbl, double* S, double* gt, double* T_out, double* h_out, int want_T, int n_blocks,
                    const int* bs_tbl, int ext_panel0, int n_ext_panels_loc, void* ws, size_t ws_bytes, int* info);
+int merge_adaptive_assemble(cudaStream_t st, int npp, int n_src, int n_child, const double* const* T_child,
+                            const double* const* h_child, const int* ld_child, int NI, const int* int_tbl, int NE,
+                            const int* ext_tbl, double* D, double* S, double* gt, int ext_panel0, int n_ext_panels_loc);
 int down_adaptive(cudaStream_t st, int npp, int n_src, int n_int, int n_ext, const double* S, const double* g_ext,
                   const double* gt, int n_child, double* const* g_child, int n_tbl, const int* tbl,
                   const double* L_refine, void* ws);

@@ -129,8 +129,12 @@ def test_sharded_driver_on_one_gpu_matches_reference(name):
     u, sl = da.solve_sharded_adaptive(st, dom.get_adaptive_boundary_data_lst(boundary_fn), ops)
     assert (sl.start, sl.stop) == (0, dom.n_leaves)
     assert rel_err(u[..., 0].cpu().numpy(), G["u"]) < TOL
-    # two "ranks" computed one after the other: the column blocks of the root S tile the full matrix
-    st0 = da.build_solver_sharded_adaptive(pb, da.CudaAdaptiveOps("cuda"), rank=0, world=1)
+    # the same through the distributed factorisation of the root system (single rank, forced)
+    ops_d = da.CudaAdaptiveOps("cuda")
+    ops_d.FORCE_DIST_LU, ops_d.DIST_LU_MIN_N = True, 0
+    st0 = da.build_solver_sharded_adaptive(pb, ops_d, rank=0, world=1)
+    u0, _ = da.solve_sharded_adaptive(st0, dom.get_adaptive_boundary_data_lst(boundary_fn), ops_d)
+    assert rel_err(u0[..., 0].cpu().numpy(), G["u"]) < TOL
     full = st0["S_r"].cpu().numpy()
     i = internal_nodes(dom.root).index(dom.root)
     if f"S_{i}" in G:
