@@ -67,24 +67,31 @@ __global__ void __launch_bounds__(256) compress_cols_kernel(const double* __rest
 
 // out[P*npp + k, c] = in[seg_P(k), c]                       (width 1)
 //                   = sum_j Lc[k, j] * in[seg_P(j), c]      (Lc is npp x (group*npp))
-// grid: (column tiles, output panels); block 256
+// One output ROW per CTA row (grid: column tiles x output rows), so that the group*npp-long dot products of
+// a coarsened panel are spread over npp times more threads than a per-panel loop would give.
 __global__ void __launch_bounds__(256) compress_rows_kernel(const double* __restrict__ in, int ncols, int npp, int group,
                                                             const int* __restrict__ seg, const double* __restrict__ Lc,
                                                             double* __restrict__ out) {
-  const int P = blockIdx.y;
+  const int row = blockIdx.y;
+  const int P = row / npp, k = row - P * npp;
   const int start = seg[3 * P], width = seg[3 * P + 1], rev = seg[3 * P + 2];
   const int len = width * npp;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x) {
-    for (int k = 0; k < npp; ++k) {
-      double v;
-      if (width == 1) {
-        v = in[(int64_t)seg_index(start, len, rev, k) * ncols + c];
-      } else {
-        v = 0.0;
-        for (int j = 0; j < len; ++j) v += Lc[(int64_t)k * len + j] * in[(int64_t)seg_index(start, len, rev, j) * ncols + c];
+    double v;
+    if (width == 1) {
+      v = in[(int64_t)seg_index(start, len, rev, k) * ncols + c];
+    } else {
+      const double* lrow = Lc + (int64_t)k * len;
+      double v0 = 0.0, v1 = 0.0;
+      int j = 0;
+      for (; j + 1 < len; j += 2) {
+        v0 += lrow[j] * in[(int64_t)seg_index(start, len, rev, j) * ncols + c];
+        v1 += lrow[j + 1] * in[(int64_t)seg_index(start, len, rev, j + 1) * ncols + c];
       }
-      out[((int64_t)P * npp + k) * ncols + c] = v;
+      if (j < len) v0 += lrow[j] * in[(int64_t)seg_index(start, len, rev, j) * ncols + c];
+      v = v0 + v1;
     }
+    out[(int64_t)row * ncols + c] = v;
   }
 }
 
@@ -217,14 +224,15 @@ int adaptive_compress(cudaStream_t st, int npp, int group, int n_src, int n, con
     HPS_LAUNCH_CHECK("compress_cols_kernel");
   }
   {
-    dim3 grid(std::min((n_out + 255) / 256, 256), n_out_panels);
+    if (n_out > 65535) return fail_arg(8, "adaptive_compress: more than 65535 boundary points");
+    dim3 grid(std::min((n_out + 255) / 256, 256), n_out);
     prof_begin(PROF_GATHER, st, 8.0 * (double)n_out * n_out);
     compress_rows_kernel<<<grid, 256, 0, st>>>(tmp, n_out, npp, group, seg_tbl, L_coarsen, T_out);
     prof_end(PROF_GATHER, st);
     HPS_LAUNCH_CHECK("compress_rows_kernel");
   }
   {
-    dim3 grid(1, n_out_panels);
+    dim3 grid(1, n_out);
     compress_rows_kernel<<<grid, 256, 0, st>>>(h, n_src, npp, group, seg_tbl, L_coarsen, h_out);
     HPS_LAUNCH_CHECK("compress_rows_kernel(h)");
   }
