@@ -22,6 +22,7 @@ oracle-backed test double of ``tests/test_dist_adaptive_gloo.py``.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List
 
 import numpy as np
@@ -169,7 +170,7 @@ class CudaAdaptiveOps:
         return T2, h2
 
     #: interface size from which the root's system is factored by all ranks together (``hps_lu_dist_*``)
-    DIST_LU_MIN_N = int(__import__("os").environ.get("HPS_DIST_LU_MIN_N", 8192))
+    DIST_LU_MIN_N = int(os.environ.get("HPS_DIST_LU_MIN_N", 8192))
     FORCE_DIST_LU = False  # tests: exercise the distributed path with a single rank
 
     def root_merge(self, Ts, hs, root_plan, e0: int, e1: int):
