@@ -161,13 +161,15 @@ int hps_merge_quad_dtn_level(void* stream, int n_merges, int m, int n_src,
  * Leaf (reference: local_solve/_uniform_2D_ItI.py:10-193): coeffs real [n_coef][n_leaves][p^2] in
  * the 2D order [xx,xy,yy,x,y,I]; P real [4(p-1)][4q]; G complex [4(p-1)][p^2]; QH complex [4q][p^2];
  * src complex [n_leaves][p^2][n_src].  Outputs complex: Y [n][p^2][4q], R [n][4q][4q],
- * v [n][p^2][n_src], h [n][4q][n_src].  Solved through the real embedding of the complex system. */
+ * v [n][p^2][n_src], h [n][4q][n_src].  Solved through the real embedding of the complex system.
+ * coeffs_imag: imaginary parts of the coefficient fields, same layout as coeffs, or NULL when they
+ * are real (complex fields: reference tests/test_accuracy/cases.py:212-265). */
 int hps_local_solve_2d_iti_workspace(int n_leaves, int p, int q, int n_src, size_t* bytes);
 int hps_local_solve_2d_iti(void* stream, int n_leaves, int p, int q, int n_src,
                            const uint8_t* which /* host */, const double* coeffs, const double* D1,
                            const double* P, const double* G, const double* QH, const double* src,
                            double* Y, double* R, double* v, double* h,
-                           void* ws, size_t ws_bytes, int* info);
+                           void* ws, size_t ws_bytes, int* info, const double* coeffs_imag);
 /* One ItI quad-merge level (reference: merge/_uniform_2D_ItI.py:182-405,
  * merge/_schur_complement.py:6-41,78-114).  R_in [4n][4m][4m], h_in [4n][4m][n_src];
  * S [n][8m][8m] and g_tilde [n][8m][n_src] with rows in the reference's returned order

@@ -50,7 +50,7 @@ _SIGNATURES = {
     "hps_merge_quad_dtn_level_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),
     "hps_merge_quad_dtn_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "hps_local_solve_2d_iti_workspace": (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),
-    "hps_local_solve_2d_iti": (_i, [_p, _i, _i, _i, _i, ctypes.c_char_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "hps_local_solve_2d_iti": (_i, [_p, _i, _i, _i, _i, ctypes.c_char_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
     "hps_merge_quad_iti_level_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),
     "hps_merge_quad_iti_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "hps_merge_quad_dtn_level_nosource": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),

@@ -216,9 +216,9 @@ int hps_local_solve_2d_iti_workspace(int n_leaves, int p, int q, int n_src, size
 int hps_local_solve_2d_iti(void* stream, int n_leaves, int p, int q, int n_src, const uint8_t* which,
                            const double* coeffs, const double* D1, const double* P, const double* G, const double* QH,
                            const double* src, double* Y, double* R, double* v, double* h, void* ws, size_t ws_bytes,
-                           int* info) {
+                           int* info, const double* coeffs_imag) {
   return local_solve_iti(static_cast<cudaStream_t>(stream), n_leaves, p, q, n_src, which, coeffs, D1, P, G, QH, src, Y, R,
-                         v, h, ws, ws_bytes, info);
+                         v, h, ws, ws_bytes, info, coeffs_imag);
 }
 int hps_merge_quad_iti_level_workspace(int n_merges, int m, int n_src, size_t* bytes) {
   if (!bytes) return fail_arg(4, "null output pointer");

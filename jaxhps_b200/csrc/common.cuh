@@ -121,7 +121,7 @@ int down_oct_scatter(cudaStream_t st, int n_nodes, int m, int n_src, const doubl
 size_t local_solve_iti_workspace_bytes(int n_leaves, int p, int q, int n_src);
 int local_solve_iti(cudaStream_t st, int n_leaves, int p, int q, int n_src, const uint8_t* which, const double* coeffs,
                     const double* D1, const double* P, const double* G, const double* QH, const double* src, double* Y,
-                    double* R, double* v, double* h, void* ws, size_t ws_bytes, int* info);
+                    double* R, double* v, double* h, void* ws, size_t ws_bytes, int* info, const double* coeffs_imag = nullptr);
 size_t merge_quad_iti_ws_bytes(int n_merges, int m, int n_src);
 int merge_quad_iti_level(cudaStream_t st, int n_merges, int m, int n_src, const double* R_in, const double* h_in,
                          double* S, double* gt, double* R_out, double* h_out, int want_T, void* ws, size_t ws_bytes,

@@ -195,6 +195,7 @@ struct ItiLeafArgs {
   AssembleArgs a;          // coefficient slots, D1 (Aii/Aie unused)
   const double2* G;        // [n_b][n_c] complex
   double* Be;              // [n_leaves][2 n_c][2 n_c]
+  const double* coeffs_im; // imaginary parts of the coefficient fields (same slots), or null
 };
 
 __global__ void __launch_bounds__(256) iti_assemble_kernel(ItiLeafArgs g) {
@@ -214,6 +215,8 @@ __global__ void __launch_bounds__(256) iti_assemble_kernel(ItiLeafArgs g) {
   const int64_t total = (int64_t)n_c * n_c;
   const int64_t ld = 2 * n_c;
   double* Be = g.Be + (int64_t)leaf * ld * ld;
+  AssembleArgs ai = g.a;  // A = sum_k diag(c_k) D_k with complex c_k: the imaginary part is the same sum over Im c_k
+  ai.coeffs = g.coeffs_im;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(e / n_c), c = (int)(e - (int64_t)r * n_c);
     double re, im;
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(256) iti_assemble_kernel(ItiLeafArgs g) {
       re = z.x; im = z.y;
     } else {
       re = entry2d(g.a, D, D2, p, n_c, leaf, r, c);
-      im = 0.0;
+      im = g.coeffs_im ? entry2d(ai, D, D2, p, n_c, leaf, r, c) : 0.0;
     }
     Be[(int64_t)r * ld + c] = re;
     Be[(int64_t)r * ld + n_c + c] = -im;
@@ -336,7 +339,7 @@ size_t local_solve_iti_workspace_bytes(int n_leaves, int p, int q, int n_src) {
 // h [n][n_g][n_src]; G [n_b][n_c], QH [n_g][n_c], src [n][n_c][n_src] likewise.
 int local_solve_iti(cudaStream_t st, int n_leaves, int p, int q, int n_src, const uint8_t* which, const double* coeffs,
                     const double* D1, const double* P, const double* G, const double* QH, const double* src, double* Y,
-                    double* R, double* v, double* h, void* ws, size_t ws_bytes, int* info) {
+                    double* R, double* v, double* h, void* ws, size_t ws_bytes, int* info, const double* coeffs_imag) {
   if (p < 3 || p > MAX_P) return fail_arg(3, "p out of range [3, 32]");
   if (n_leaves <= 0 || n_src <= 0 || q <= 0) return fail_arg(2, "non-positive size");
   if (n_leaves > 65535) return fail_arg(2, "n_leaves per call is limited to 65535; chunk the leaves");
@@ -359,6 +362,7 @@ int local_solve_iti(cudaStream_t st, int n_leaves, int p, int q, int n_src, cons
   ia.a.n_coef = n_coef;
   ia.G = reinterpret_cast<const double2*>(G);
   ia.Be = Be;
+  ia.coeffs_im = coeffs_imag;
   {
     const int64_t total = (int64_t)n_c * n_c;
     iti_assemble_kernel<<<dim3((unsigned)std::min<int64_t>((total + 255) / 256, 1024), n_leaves), 256, 0, st>>>(ia);

@@ -30,6 +30,31 @@ def _gather_coeffs(pde_problem, order, dev) -> Tuple[torch.Tensor, bytes]:
     return torch.stack(present).contiguous(), which
 
 
+def _gather_coeffs_complex(pde_problem, order, dev):
+    """Like :func:`_gather_coeffs` for fields that may be complex (ItI): real parts, imaginary parts
+    (``None`` when every field is real) and the presence mask."""
+    arrs = [getattr(pde_problem, f"{name}_coefficients", None) for name in order]
+    which = bytes(1 if a is not None else 0 for a in arrs)
+    present = [a for a in arrs if a is not None]
+    if not present:
+        raise ValueError("at least one differential-operator coefficient must be given")
+
+    def is_cplx(a):
+        return a.is_complex() if isinstance(a, torch.Tensor) else np.iscomplexobj(a)
+
+    def part(a, imag):
+        if isinstance(a, torch.Tensor):
+            return (a.imag if imag else a.real) if a.is_complex() else (torch.zeros_like(a) if imag else a)
+        a = np.asarray(a)
+        return np.ascontiguousarray(a.imag if imag else a.real) if np.iscomplexobj(a) else (np.zeros_like(a) if imag else a)
+
+    re = torch.stack([_lib.to_device(part(a, False), dev) for a in present]).contiguous()
+    im = None
+    if any(is_cplx(a) for a in present):
+        im = torch.stack([_lib.to_device(part(a, True), dev) for a in present]).contiguous()
+    return re, im, which
+
+
 def _constants(pde_problem, dev):
     """Device copies of D1, P, Q, cached on the problem object."""
     cache = pde_problem.__dict__.setdefault("_device_constants", {})
@@ -106,12 +131,8 @@ def local_solve_stage_uniform_2D_ItI(pde_problem, device=None, host_device=None)
     lib = _lib.load()
     dom = pde_problem.domain
     p, q = dom.p, dom.q
-    for name in _ORDER_2D:
-        a = getattr(pde_problem, f"{name}_coefficients", None)
-        if a is not None and (np.iscomplexobj(a) if not isinstance(a, torch.Tensor) else a.is_complex()):
-            raise NotImplementedError("complex-valued coefficient fields are not supported by the CUDA ItI leaf yet")
     with torch.cuda.device(dev):
-        coeffs, which = _gather_coeffs(pde_problem, _ORDER_2D, dev)
+        coeffs, coeffs_im, which = _gather_coeffs_complex(pde_problem, _ORDER_2D, dev)
         src = _lib.to_device(pde_problem.source, dev, dtype=torch.complex128)
         multi = src.ndim == 3
         if not multi:
@@ -141,11 +162,13 @@ def local_solve_stage_uniform_2D_ItI(pde_problem, device=None, host_device=None)
         ws = _lib.WORKSPACE.get(need.value, dev)
         for s in range(0, n_leaves, chunk):
             e = min(n_leaves, s + chunk)
-            c_chunk = coeffs[:, s:e].contiguous() if (s, e) != (0, n_leaves) else coeffs
+            whole = (s, e) == (0, n_leaves)
+            c_chunk = coeffs if whole else coeffs[:, s:e].contiguous()
+            ci_chunk = None if coeffs_im is None else (coeffs_im if whole else coeffs_im[:, s:e].contiguous())
             rc = lib.hps_local_solve_2d_iti(
                 _lib.stream_ptr(), e - s, p, q, n_src, which, _lib.ptr(c_chunk), _lib.ptr(D1), _lib.ptr(P), _lib.ptr(G),
                 _lib.ptr(QH), _lib.ptr(src[s:e]), _lib.ptr(Y[s:e]), _lib.ptr(R[s:e]), _lib.ptr(v[s:e]), _lib.ptr(h[s:e]),
-                _lib.ptr(ws), ws.numel(), _lib.ptr(info[s:e]),
+                _lib.ptr(ws), ws.numel(), _lib.ptr(info[s:e]), _lib.ptr(ci_chunk),
             )
             _lib.check(rc, "hps_local_solve_2d_iti")
         _lib.check_info(info, "ItI local solve")

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .local_solve import _ORDER_2D, _constants, _gather_coeffs
+from .local_solve import _ORDER_2D, _constants, _gather_coeffs, _gather_coeffs_complex
 
 # ItI unknown orders (child, interface): the reference solves in [a5,a8,c6,c7,b5,b6,d7,d8] and returns
 # rows of S / g~ in [a5,b5,b6,c6,c7,d7,d8,a8] (`merge/_uniform_2D_ItI.py:357-373`)
@@ -41,7 +41,10 @@ def _nosource_leaves(pde_problem, iti: bool, device, host_device):
     n_c, n_i = p * p, (p - 2) ** 2
     n_b, n_g = n_c - n_i, 4 * q
     with torch.cuda.device(dev):
-        coeffs, which = _gather_coeffs(pde_problem, _ORDER_2D, dev)
+        if iti:
+            coeffs, coeffs_im, which = _gather_coeffs_complex(pde_problem, _ORDER_2D, dev)
+        else:
+            (coeffs, which), coeffs_im = _gather_coeffs(pde_problem, _ORDER_2D, dev), None
         n_leaves = coeffs.shape[1]
         cdt = torch.complex128 if iti else torch.float64
         if iti:
@@ -83,10 +86,11 @@ def _nosource_leaves(pde_problem, iti: bool, device, host_device):
             info = torch.zeros(k, dtype=torch.int32, device=dev)
             c_chunk = coeffs[:, s:e].contiguous()
             if iti:
+                ci_chunk = None if coeffs_im is None else coeffs_im[:, s:e].contiguous()
                 rc = lib.hps_local_solve_2d_iti(_lib.stream_ptr(), k, p, q, n_i, which, _lib.ptr(c_chunk), _lib.ptr(D1),
                                                 _lib.ptr(P), _lib.ptr(G), _lib.ptr(QH), _lib.ptr(src), _lib.ptr(Y[s:e]),
                                                 _lib.ptr(T[s:e]), _lib.ptr(v), _lib.ptr(h), _lib.ptr(ws), ws.numel(),
-                                                _lib.ptr(info))
+                                                _lib.ptr(info), _lib.ptr(ci_chunk))
             else:
                 rc = lib.hps_local_solve_dtn(_lib.stream_ptr(), 2, k, p, q, n_i, which, _lib.ptr(c_chunk), _lib.ptr(D1),
                                              _lib.ptr(P), _lib.ptr(Q), _lib.ptr(src), _lib.ptr(Y[s:e]), _lib.ptr(T[s:e]),

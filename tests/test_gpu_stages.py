@@ -183,3 +183,29 @@ def test_stepwise_root_factorisation_matches_oracle(p, q, L):
     S, g = orc.merge_stage_uniform_3D_DtN(T, h, L)
     assert rel_err(st.S_root_cols.cpu().numpy(), S[-1][:, st.col_index.cpu().numpy()]) < TOL
     assert rel_err(u.cpu().numpy(), orc.down_pass_uniform_3D_DtN(bdry, S, g, Y, v)) < TOL
+
+
+@pytest.mark.parametrize("which", ["helmholtz", "complex_coefficient"])
+def test_iti_analytic_cases_incl_complex_coefficients(which):
+    """The reference's analytic ItI cases (tests/test_accuracy/cases.py:134-265) on the CUDA path: agreement
+    with the analytic solution at the reference's 1e-8 and with the oracle; the second case has a complex
+    coefficient field (k^2 + i gamma), assembled from the real and imaginary coefficient parts."""
+    import jaxhps_b200 as hps
+    from _iti_cases import COMPLEX, HELMHOLTZ, problem
+
+    case = HELMHOLTZ if which == "helmholtz" else COMPLEX
+    dom, pb, g_in = problem(case)
+    Yo, Ro, vo, ho = orc.local_solve_stage_uniform_2D_ItI(pb)
+    Y, R, v, h = local_solve_stage_uniform_2D_ItI(pb)
+    for a, b in ((Y, Yo), (R, Ro), (v, vo), (h, ho)):
+        assert rel_err(a, b) < 1e-9
+    hps.build_solver(pb)
+    u = hps.solve(pb, g_in)
+    assert np.abs(u - case["u"](dom.interior_points)).max() < 1e-8
+    So, go = orc.merge_stage_uniform_2D_ItI(Ro, ho, 1)
+    assert rel_err(u, orc.down_pass_uniform_2D_ItI(g_in, So, go, Yo, vo)) < 1e-9
+    # the source-free build + up pass takes the same complex coefficient path
+    pb2 = hps.PDEProblem(dom, source=None, D_xx_coefficients=pb.D_xx_coefficients, D_yy_coefficients=pb.D_yy_coefficients,
+                         I_coefficients=pb.I_coefficients, use_ItI=True, eta=pb.eta)
+    hps.build_solver(pb2)
+    assert rel_err(hps.solve(pb2, g_in, source=pb.source), u) < 1e-8

@@ -88,3 +88,16 @@ def test_interface_agreement_3D():
     # a|b across x, a|d across y, a|e across z
     assert np.array_equal(f(0, 1), f(1, 0)) and np.array_equal(f(0, 3), f(3, 2)) and np.array_equal(f(0, 4), f(4, 5))
     assert np.array_equal(f(6, 0), f(7, 1)) and np.array_equal(f(2, 4), f(6, 5))
+
+
+def test_iti_helmholtz_and_complex_coefficient_cases():
+    """reference test_single_merge_accuracy.py:297-421: ItI build + solve on 4 leaves reproduces the analytic
+    solution of a variable-coefficient Helmholtz problem and of one with a COMPLEX coefficient (atol 1e-8)."""
+    from _iti_cases import COMPLEX, HELMHOLTZ, problem
+
+    for case in (HELMHOLTZ, COMPLEX):
+        dom, pb, g_in = problem(case)
+        Y, R, v, h = orc.local_solve_stage_uniform_2D_ItI(pb)
+        S_lst, g_lst = orc.merge_stage_uniform_2D_ItI(R, h, 1)
+        u = orc.down_pass_uniform_2D_ItI(g_in, S_lst, g_lst, Y, v)
+        assert np.abs(u - case["u"](dom.interior_points)).max() < 1e-8
