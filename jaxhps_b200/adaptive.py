@@ -279,6 +279,9 @@ def _merge_adaptive(pde_problem, T_arr, h_arr, device, host_device, return_T: bo
             d.T = None
         if root_T is not None:
             dom.root.data.T = _lib.to_result(root_T, host_device)
+        if not plan.nodes:  # the root is itself a leaf: nothing to merge
+            dom.root.data.T = _lib.to_result(T_leaf[0], host_device)
+            return 0
         return plan.by_id[id(dom.root)].n_int
 
 

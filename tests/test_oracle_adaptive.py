@@ -48,3 +48,56 @@ def test_adaptive_oracle_matches_reference_fixture(name):
     if "T_top" in G:
         assert rel_err(T_top, G["T_top"]) < TOL and rel_err(Y, G["Y"]) < TOL
         assert rel_err(T, G["T_leaf"]) < TOL and rel_err(h, G["h_leaf"]) < TOL
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_adaptive_oracle_reproduces_polynomial_solution(dim):
+    """Known answer on a non-uniform tree: a quadratic solution is represented exactly by every leaf and by
+    the Gauss panels, and the 4-to-1 / 2-to-1 projections are exact for it, so the adaptive build + solve
+    must return it to rounding (the uniform analogue is the reference's `test_single_merge_accuracy.py`)."""
+    if dim == 2:
+        root = hps.DiscretizationNode2D(-1.0, 1.0, -1.0, 1.0)
+        add, p, q = add_four_children, 8, 6
+        paths = [[], [1], [1, 1], [3]]
+        u = lambda x: x[..., 0] ** 2 - x[..., 1] ** 2 + 0.5 * x[..., 0] * x[..., 1]  # noqa: E731
+        lap = lambda x: 3.0 * 2 * np.ones(x.shape[:-1])  # noqa: E731  u2 = u + 1.5 (x^2 + y^2)
+        u2 = lambda x: u(x) + 1.5 * (x[..., 0] ** 2 + x[..., 1] ** 2)  # noqa: E731
+    else:
+        root = hps.DiscretizationNode3D(0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+        add, p, q = add_eight_children, 6, 4
+        paths = [[], [6], [6, 6], [0]]
+        u = lambda x: x[..., 0] ** 2 - x[..., 2] ** 2 + x[..., 1] * x[..., 2]  # noqa: E731
+        lap = lambda x: 6.0 * np.ones(x.shape[:-1])  # noqa: E731
+        u2 = lambda x: u(x) + x[..., 0] ** 2 + x[..., 1] ** 2 + x[..., 2] ** 2  # noqa: E731
+    for path in paths:
+        node = root
+        for c in path:
+            node = node.children[c]
+        add(node, root=root, q=q)
+    dom = hps.Domain(p=p, q=q, root=root)
+    one = np.ones(dom.interior_points.shape[:2])
+    co = {"D_xx_coefficients": one, "D_yy_coefficients": one}
+    if dim == 3:
+        co["D_zz_coefficients"] = one
+    pb = hps.PDEProblem(dom, source=lap(dom.interior_points), **co)
+    Y, T, v, h = ora.local_solve_stage_adaptive_DtN(pb)
+    store = ora.merge_stage_adaptive_DtN(pb, T, h)
+    sol = ora.down_pass_adaptive_DtN(pb, store, dom.get_adaptive_boundary_data_lst(u2), Y, v)
+    assert np.abs(sol - u2(dom.interior_points)).max() < 1e-10
+    # the root DtN map applied to the trace of the harmonic part returns its normal derivative on every
+    # boundary panel: check through T g = du/dn summed against the Gauss weights (net flux of a harmonic function = 0)
+    g_h = np.concatenate(dom.get_adaptive_boundary_data_lst(u))
+    flux = store[id(root)]["T"] @ g_h
+    sizes = ora._face_index_ranges(root, dim)
+    # every leaf face panel has the same Gauss weights up to its area
+    from jaxhps_b200.quadrature import gauss_points  # noqa: F401
+    w1 = np.polynomial.legendre.leggauss(q)[1]
+    total = 0.0
+    for f, leaves in enumerate([ora._face_leaves(root, f) for f in range(2 * dim)]):
+        at = sizes[f][0]
+        for leaf in leaves:
+            side = leaf.xmax - leaf.xmin
+            w = (w1 * side / 2) if dim == 2 else np.outer(w1, w1).reshape(-1) * (side / 2) ** 2
+            total += float(w @ flux[at : at + w.size])
+            at += w.size
+    assert abs(total) < 1e-9
