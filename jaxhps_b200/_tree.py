@@ -21,6 +21,10 @@ __all__ = [
     "add_uniform_levels",
     "find_path_from_root",
     "get_ordered_lst_of_boundary_nodes",
+    "get_discretization_node_area",
+    "tree_equal",
+    "find_node_at_corner",
+    "find_nodes_along_interface_3D",
     "FACE_CHILDREN_2D",
     "FACE_CHILDREN_3D",
 ]
@@ -240,3 +244,46 @@ def get_ordered_lst_of_boundary_nodes(root) -> Tuple[List, ...]:
         return out
 
     return tuple(walk(root, f, []) for f in range(len(table)))
+
+
+def get_discretization_node_area(node) -> float:
+    """Area (2D) / volume (3D) of the box (`_discretization_tree.py:265-279`)."""
+    out = 1.0
+    for lo, hi in _bounds(node):
+        out *= hi - lo
+    return out
+
+
+def tree_equal(node_a, node_b) -> bool:
+    """Same box, same depth and recursively equal children (the reference compares the flattened
+    pytrees, `_discretization_tree_operations_2D.py:350-358`)."""
+    if type(node_a) is not type(node_b) or _bounds(node_a) != _bounds(node_b) or node_a.depth != node_b.depth:
+        return False
+    if len(node_a.children) != len(node_b.children):
+        return False
+    return all(tree_equal(a, b) for a, b in zip(node_a.children, node_b.children))
+
+
+def find_node_at_corner(root: DiscretizationNode2D, xmin=None, xmax=None, ymin=None, ymax=None):
+    """The LEAF of a quadtree having the given coordinates among its bounds (any subset of the four may be
+    given), e.g. ``xmin=root.xmin, ymin=root.ymin`` is the SW corner leaf
+    (`_discretization_tree_operations_2D.py:256-332`)."""
+    want = {"xmin": xmin, "xmax": xmax, "ymin": ymin, "ymax": ymax}
+    want = {k: v for k, v in want.items() if v is not None}
+    hits = [leaf for leaf in get_all_leaves(root) if all(getattr(leaf, k) == v for k, v in want.items())]
+    if not hits:
+        raise ValueError(f"no leaf with {want}")
+    return hits[0]
+
+
+def find_nodes_along_interface_3D(root: DiscretizationNode3D, xval=None, yval=None, zval=None):
+    """Leaves touching the plane ``x = xval`` (or y / z) from the negative and from the positive side
+    (`_discretization_tree_operations_3D.py:275-336`)."""
+    given = [(k, v) for k, v in (("x", xval), ("y", yval), ("z", zval)) if v is not None]
+    if len(given) != 1:
+        raise ValueError(f"Only one of xval, yval, or zval can be specified. Input args: {xval}, {yval}, {zval}")
+    ax, val = given[0]
+    leaves = get_all_leaves(root)
+    neg = [leaf for leaf in leaves if getattr(leaf, ax + "max") == val]
+    pos = [leaf for leaf in leaves if getattr(leaf, ax + "min") == val]
+    return neg, pos

@@ -178,9 +178,13 @@ def local_solve_stage_uniform_2D_ItI(pde_problem, device=None, host_device=None)
 
 
 
-def __getattr__(name):  # the adaptive-tree stages live in adaptive.py (imported lazily: it imports this module)
+def __getattr__(name):  # same public names as the reference's `jaxhps.local_solve` package; imported lazily (those modules import this one)
     if name in ('local_solve_stage_adaptive_2D_DtN', 'local_solve_stage_adaptive_3D_DtN'):
         from . import adaptive
 
         return getattr(adaptive, name)
+    if name in ('nosource_local_solve_stage_uniform_2D_DtN', 'nosource_local_solve_stage_uniform_2D_ItI'):
+        from . import up_pass
+
+        return getattr(up_pass, name)
     raise AttributeError(name)

@@ -174,9 +174,13 @@ def merge_stage_uniform_2D_ItI(T_arr, h_arr, l: int, device=None, host_device=No
 
 
 
-def __getattr__(name):  # the adaptive-tree stages live in adaptive.py (imported lazily: it imports this module)
+def __getattr__(name):  # same public names as the reference's `jaxhps.merge` package; imported lazily (those modules import this one)
     if name in ('merge_stage_adaptive_2D_DtN', 'merge_stage_adaptive_3D_DtN'):
         from . import adaptive
 
         return getattr(adaptive, name)
+    if name in ('nosource_merge_stage_uniform_2D_DtN', 'nosource_merge_stage_uniform_2D_ItI'):
+        from . import up_pass
+
+        return getattr(up_pass, name)
     raise AttributeError(name)

@@ -158,3 +158,36 @@ def test_uniform_tree_given_as_adaptive_domain_matches_uniform_domain():
         np.testing.assert_allclose(a.boundary_points, u.boundary_points, rtol=0, atol=1e-15)
         lst = a.get_adaptive_boundary_data_lst(lambda x: x[..., 0])
         assert sum(len(g) for g in lst) == u.boundary_points.shape[0]
+
+
+def test_tree_queries():
+    """reference test_discretization_tree_operations_2D.py:188-250, ..._3D.py:183-238."""
+    from jaxhps_b200._tree import (find_node_at_corner, find_nodes_along_interface_3D, get_discretization_node_area,
+                                   tree_equal)
+
+    root = hps.DiscretizationNode2D(0.0, 1.0, 0.0, 1.0)
+    add_uniform_levels(root, 2)
+    sw = find_node_at_corner(root, xmin=0.0, ymin=0.0)
+    assert tree_equal(sw, root.children[0].children[0]) and get_discretization_node_area(sw) == 1 / 16
+    ne = find_node_at_corner(root, xmax=1.0, ymax=1.0)
+    assert ne is root.children[2].children[2] and not tree_equal(sw, ne)
+    assert find_node_at_corner(root, xmin=0.25, ymin=0.0) is root.children[0].children[1]
+    root3 = hps.DiscretizationNode3D(0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+    add_uniform_levels(root3, 2)
+    for kw in ({"xval": 0.5}, {"yval": 0.5}, {"zval": 0.5}):
+        neg, pos = find_nodes_along_interface_3D(root3, **kw)
+        assert len(neg) == len(pos) == 16
+    root3 = hps.DiscretizationNode3D(0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+    add_eight_children(root3)
+    add_eight_children(root3.children[0])
+    neg, pos = find_nodes_along_interface_3D(root3, xval=0.5)  # child a is refined: 4 small + 3 big leaves on its side
+    assert (len(neg), len(pos)) == (7, 4)
+    with pytest.raises(ValueError):
+        find_nodes_along_interface_3D(root3, xval=0.5, yval=0.5)
+    import jaxhps_b200.local_solve as ls
+    import jaxhps_b200.merge as mg
+
+    for name in ("local_solve_stage_adaptive_3D_DtN", "nosource_local_solve_stage_uniform_2D_ItI"):
+        assert callable(getattr(ls, name))
+    for name in ("merge_stage_adaptive_2D_DtN", "nosource_merge_stage_uniform_2D_DtN"):
+        assert callable(getattr(mg, name))
