@@ -1,6 +1,7 @@
 // Host side of the FP64 GEMMs: the DMMA kernel lives in gemm_kernel.cuh (templated on the tile
 // configuration), the narrow-N bandwidth kernel and the dispatch are here.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "gemm_kernel.cuh"
@@ -19,6 +20,8 @@ using gemmk::GemmArgs;
 constexpr int BM = Cfg::BM, BN = Cfg::BN, THREADS = Cfg::THREADS;
 constexpr size_t SMEM_BYTES = Cfg::SMEM_BYTES;
 #define gemm_kernel gemmk::gemm_kernel_mb<Cfg>
+// candidate with the copy addressing hoisted out of the K loop; selected with HPS_GEMM_HOIST=1 (see gemm_kernel.cuh)
+#define gemm_kernel_alt gemmk::gemm_kernel_hoist<Cfg>
 
 // ---- narrow-N kernels: one warp per output row, lanes stride over K -------------------------
 // These are the HBM-bound mat-vecs of the down pass (g_int = S g_ext + g~, u = Y g + v): every
@@ -174,8 +177,10 @@ int dgemm(cudaStream_t st, int M, int N, int K, double alpha, const double* A, i
   static bool configured[64] = {};  // cudaFuncSetAttribute is per device
   int dev = 0;
   HPS_CUDA(cudaGetDevice(&dev));
+  static const bool use_alt = [] { const char* e = std::getenv("HPS_GEMM_HOIST"); return e && e[0] == '1'; }();
   if (dev >= 0 && dev < 64 && !configured[dev]) {
     HPS_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    HPS_CUDA(cudaFuncSetAttribute(gemm_kernel_alt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     configured[dev] = true;
   }
   GemmArgs g;
@@ -187,7 +192,8 @@ int dgemm(cudaStream_t st, int M, int N, int K, double alpha, const double* A, i
     const int nb = min(65535, batch - b0);
     g.A = A + (int64_t)b0 * sA; g.B = B + (int64_t)b0 * sB; g.C = C + (int64_t)b0 * sC;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, nb);
-    gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(g);
+    if (use_alt) gemm_kernel_alt<<<grid, THREADS, SMEM_BYTES, st>>>(g);
+    else gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(g);
   }
   prof_end(PROF_GEMM, st);
   HPS_LAUNCH_CHECK("gemm_kernel");

@@ -387,6 +387,158 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_kernel_mb(Ge
 }
 
 
+// Same pipeline as gemm_kernel_mb with the cp.async address arithmetic hoisted out of the K loop: interior
+// tiles (no M/N edge, 16-byte aligned operands) keep ONE running source pointer per operand and thread —
+// the copies of a thread differ by compile-time row strides — and issue full K steps without predicates;
+// edge tiles and the ragged last K step take the generic path.  CANDIDATE (opt-in with HPS_GEMM_HOIST=1 until
+// it has been measured on the GPU): the main loop of gemm_kernel_mb spends ~235 of its 484 instructions per
+// BK step on these addresses and predicates.
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_kernel_hoist(GemmArgs g) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, THREADS = Cfg::THREADS;
+  constexpr int LDA_S = Cfg::LDA_S, LDB_S = Cfg::LDB_S;
+  constexpr int MI = Cfg::MI, NJ = Cfg::NJ;
+  constexpr int A_CH = BK / 2, B_CH = BN / 2;
+  constexpr int NA = Cfg::A_CHUNKS / THREADS, NB = Cfg::B_CHUNKS / THREADS;
+  constexpr int A_ROWS = THREADS / A_CH, B_ROWS = THREADS / B_CH;  // rows covered by one pass of the CTA
+  static_assert(THREADS % A_CH == 0 && THREADS % B_CH == 0, "a thread keeps its column in every pass");
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  double* As = smem;
+  double* Bs = smem + STAGES * Cfg::A_STAGE;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp / Cfg::WARPS_N) * Cfg::WM, wn = (warp % Cfg::WARPS_N) * Cfg::WN;
+  const int bm0 = blockIdx.y * BM, bn0 = blockIdx.x * BN;
+  const int64_t batch = blockIdx.z;
+  const double* __restrict__ A = g.A + batch * g.sA;
+  const double* B = g.B + batch * g.sB;
+  double* C = g.C + batch * g.sC;
+  const int M = g.M, N = g.N, K = g.K;
+  const bool interior = (bm0 + BM <= M) && (bn0 + BN <= N) && g.vecA && g.vecB;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], THREADS);
+      mbar_init(&empty_bar[s], Cfg::NWARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  // running sources of this thread's first copy of each operand; pass i adds i * A_ROWS (B_ROWS) rows
+  const int a_dst = (tid / A_CH) * LDA_S + (tid % A_CH) * 2;
+  const int b_dst = (tid / B_CH) * LDB_S + (tid % B_CH) * 2;
+  const double* a_src = A + (int64_t)(bm0 + tid / A_CH) * g.lda + (tid % A_CH) * 2;
+  const double* b_src = B + (int64_t)(tid / B_CH) * g.ldb + bn0 + (tid % B_CH) * 2;
+  const int64_t a_pass = (int64_t)A_ROWS * g.lda, b_pass = (int64_t)B_ROWS * g.ldb, b_step = (int64_t)BK * g.ldb;
+
+  auto load_generic = [&](int stage, int k0) {
+    double* as = As + stage * Cfg::A_STAGE;
+    double* bs = Bs + stage * Cfg::B_STAGE;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int c = tid + i * THREADS;
+      const int r = c / A_CH, kc = (c % A_CH) * 2;
+      const int gr = bm0 + r, gk = k0 + kc;
+      double* dst = as + r * LDA_S + kc;
+      const int valid = (gr < M) ? max(0, min(2, K - gk)) : 0;
+      const double* src = valid ? (A + (int64_t)gr * g.lda + gk) : A;
+      if (g.vecA) {
+        cp_async16(dst, src, valid * 8);
+      } else {
+        cp_async8(dst, src, valid >= 1 ? 8 : 0);
+        cp_async8(dst + 1, valid >= 2 ? src + 1 : A, valid >= 2 ? 8 : 0);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int c = tid + i * THREADS;
+      const int r = c / B_CH, nc = (c % B_CH) * 2;
+      const int gk = k0 + r, gn = bn0 + nc;
+      double* dst = bs + r * LDB_S + nc;
+      const int valid = (gk < K) ? max(0, min(2, N - gn)) : 0;
+      const double* src = valid ? (B + (int64_t)gk * g.ldb + gn) : B;
+      if (g.vecB) {
+        cp_async16(dst, src, valid * 8);
+      } else {
+        cp_async8(dst, src, valid >= 1 ? 8 : 0);
+        cp_async8(dst + 1, valid >= 2 ? src + 1 : B, valid >= 2 ? 8 : 0);
+      }
+    }
+    mbar_cp_async_arrive(&full_bar[stage]);
+  };
+  // K steps are issued in order 0, 1, 2, ...: the fast path advances the running pointers itself
+  auto load_tile = [&](int stage, int k0) {
+    if (interior && k0 + BK <= K) {
+      double* as = As + stage * Cfg::A_STAGE + a_dst;
+      double* bs = Bs + stage * Cfg::B_STAGE + b_dst;
+#pragma unroll
+      for (int i = 0; i < NA; ++i) cp_async16(as + i * A_ROWS * LDA_S, a_src + i * a_pass, 16);
+#pragma unroll
+      for (int i = 0; i < NB; ++i) cp_async16(bs + i * B_ROWS * LDB_S, b_src + i * b_pass, 16);
+      a_src += BK;
+      b_src += b_step;
+      mbar_cp_async_arrive(&full_bar[stage]);
+    } else {
+      load_generic(stage, k0);
+    }
+  };
+
+  double acc[MI][NJ][2];
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int KT = (K + BK - 1) / BK;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s)
+    if (s < KT) load_tile(s, s * BK);
+
+  const int a_off = (wm + (lane >> 2)) * LDA_S + (lane & 3);
+  const int b_off = (lane & 3) * LDB_S + wn + (lane >> 2);
+
+  for (int kt = 0; kt < KT; ++kt) {
+    const int st = kt % STAGES;
+    mbar_wait(&full_bar[st], (unsigned)(kt / STAGES) & 1u);
+    const double* as = As + st * Cfg::A_STAGE + a_off;
+    const double* bs = Bs + st * Cfg::B_STAGE + b_off;
+    double a[2][MI], b[2][NJ];
+#pragma unroll
+    for (int i = 0; i < MI; ++i) a[0][i] = as[i * 8 * LDA_S];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) b[0][j] = bs[j * 8];
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      const int cur = k4 & 1, nxt = cur ^ 1;
+      if (k4 + 1 < BK / 4) {
+#pragma unroll
+        for (int i = 0; i < MI; ++i) a[nxt][i] = as[i * 8 * LDA_S + (k4 + 1) * 4];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) b[nxt][j] = bs[(k4 + 1) * 4 * LDB_S + j * 8];
+      }
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[st]);
+    const int nk = kt + STAGES - 1;
+    if (nk < KT) {
+      const int sp = nk % STAGES;
+      if (nk >= STAGES) mbar_wait(&empty_bar[sp], (unsigned)(nk / STAGES - 1) & 1u);
+      load_tile(sp, nk * BK);
+    }
+  }
+  cp_async_wait<0>();
+  epilogue<Cfg>(g, smem, acc, C, bm0, bn0, wm, wn, warp, lane);
+}
+
+
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP): one instruction moves a whole tile row ----
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(
