@@ -7,8 +7,14 @@ using namespace hps::gemmk;
 #define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("CUDA error %s line %d\n",cudaGetErrorString(e),__LINE__);exit(1);}}while(0)
 __global__ void fill(double* p, size_t n, unsigned seed){ size_t i=blockIdx.x*(size_t)blockDim.x+threadIdx.x; size_t st=(size_t)gridDim.x*blockDim.x; for(;i<n;i+=st){ unsigned x=(unsigned)(i*2654435761u)^seed; x^=x>>13; x*=0x5bd1e995; x^=x>>15; p[i]=((x&0xffff)/65536.0)-0.5; } }
 __global__ void checksum(const double* p, size_t n, double* out){ __shared__ double s[256]; double a=0; size_t i=blockIdx.x*(size_t)blockDim.x+threadIdx.x; size_t st=(size_t)gridDim.x*blockDim.x; for(;i<n;i+=st) a+=p[i]*(1+(i%7)); s[threadIdx.x]=a; __syncthreads(); for(int o=128;o>0;o>>=1){ if(threadIdx.x<o) s[threadIdx.x]+=s[threadIdx.x+o]; __syncthreads(); } if(threadIdx.x==0) atomicAdd(out,s[0]); }
+template<class Cfg, int MB> auto pick(){
+  if constexpr (MB == 3) return gemm_kernel_hoist<Cfg>;
+  else if constexpr (MB == 2) return gemm_kernel_tma<Cfg>;
+  else if constexpr (MB == 1) return gemm_kernel_mb<Cfg>;
+  else return gemm_kernel<Cfg>;
+}
 template<class Cfg, int MB=0> double run(const char* name, GemmArgs g, int batch, double* C0, size_t csz, double* d_sum){
-  auto kern = MB == 2 ? gemm_kernel_tma<Cfg> : (MB == 1 ? gemm_kernel_mb<Cfg> : gemm_kernel<Cfg>);
+  auto kern = pick<Cfg, MB>();
   static bool conf=false; if(!conf){ CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,(int)Cfg::SMEM_BYTES)); conf=true; }
   dim3 grid((g.N+Cfg::BN-1)/Cfg::BN,(g.M+Cfg::BM-1)/Cfg::BM,batch);
   int occ=0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES);
@@ -37,6 +43,12 @@ int main(){
     printf("shape M=%d N=%d K=%d batch=%d beta=%g\n",s.M,s.N,s.K,s.batch,s.beta);
     //                 WM  WN  WMs WNs BK  ST  minCTA
     run<Config<32, 32, 4, 2, 16, 3, 2>, 1>("G  mb  128x64 8w(32x32) bk16 s3 x2cta", g, s.batch, C0, csz, d_sum);
+    run<Config<32, 32, 4, 2, 16, 3, 2>, 3>("G  hoist 128x64 8w(32x32) bk16 s3 x2cta [product]", g, s.batch, C0, csz, d_sum);
+    run<Config<32, 32, 4, 2, 16, 4, 2>, 3>("G4 hoist 128x64 8w bk16 s4 x2cta", g, s.batch, C0, csz, d_sum);
+    run<Config<32, 32, 4, 2, 32, 2, 2>, 3>("G2 hoist 128x64 8w bk32 s2 x2cta", g, s.batch, C0, csz, d_sum);
+    run<Config<32, 32, 4, 4, 16, 3, 1>, 3>("A1 hoist 128x128 16w bk16 s3", g, s.batch, C0, csz, d_sum);
+    run<Config<32, 32, 4, 4, 32, 3, 1>, 3>("A  hoist 128x128 16w bk32 s3", g, s.batch, C0, csz, d_sum);
+    run<Config<64, 32, 2, 2, 16, 3, 2>, 3>("W  hoist 128x64 4w(64x32) bk16 s3 x2cta", g, s.batch, C0, csz, d_sum);
     run<Config<32, 32, 4, 2, 16, 3, 2>, 2>("G  tma 128x64 8w(32x32) bk16 s3 x2cta", g, s.batch, C0, csz, d_sum);
     run<Config<32, 32, 4, 4, 32, 3, 1>, 1>("A  mb  128x128 16w bk32 s3", g, s.batch, C0, csz, d_sum);
     run<Config<32, 32, 4, 4, 32, 3, 1>, 2>("A  tma 128x128 16w bk32 s3", g, s.batch, C0, csz, d_sum);
