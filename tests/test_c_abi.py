@@ -49,6 +49,28 @@ def test_product_path_fails_loudly_without_cuda():
     pb = hps.PDEProblem(dom, source=s, D_xx_coefficients=s + 1, D_yy_coefficients=s + 1, D_zz_coefficients=s + 1)
     with pytest.raises(_lib.HpsLibraryError, match="no CPU fallback"):
         hps.build_solver(pb)
+    # the adaptive, subtree-recomputation and sharded entry points fail the same way
+    from jaxhps_b200._tree import add_eight_children
+
+    root = hps.DiscretizationNode3D(0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+    add_eight_children(root, root=root, q=2)
+    add_eight_children(root.children[0], root=root, q=2)
+    dom = hps.Domain(4, 2, root)
+    s = np.zeros((dom.n_leaves, 64))
+    pb = hps.PDEProblem(dom, source=s, D_xx_coefficients=s + 1, D_yy_coefficients=s + 1, D_zz_coefficients=s + 1)
+    with pytest.raises(_lib.HpsLibraryError, match="no CPU fallback"):
+        hps.build_solver(pb)
+    with pytest.raises(_lib.HpsLibraryError, match="no CPU fallback"):
+        hps.solve(pb, dom.get_adaptive_boundary_data_lst(lambda x: x[..., 0]))
+    from jaxhps_b200 import _dist_adaptive
+
+    with pytest.raises(_lib.HpsLibraryError, match="no CPU fallback"):
+        _dist_adaptive.CudaAdaptiveOps(None)
+    dom2 = hps.Domain(4, 2, hps.DiscretizationNode2D(0.0, 1.0, 0.0, 1.0), 2)
+    s2 = np.zeros((16, 16))
+    pb2 = hps.PDEProblem(dom2, source=s2, D_xx_coefficients=s2 + 1, D_yy_coefficients=s2 + 1)
+    with pytest.raises(_lib.HpsLibraryError, match="no CPU fallback"):
+        hps.solve_subtree(pb2, np.zeros(dom2.boundary_points.shape[0]), subtree_height=1)
 
 
 def test_product_never_imports_the_oracle():
