@@ -26,10 +26,26 @@ def device_put(x, device=None):
     return _wrap_out(_np.asarray(x))
 
 
-def jit(fn=None, **kwargs):
+def jit(fn=None, static_argnums=(), static_argnames=(), **kwargs):
+    """Identity "compiler"; like the real one it hands plain NumPy inputs to the function as arrays of the
+    array type (so that `.at[...]` works on them), leaving static arguments alone."""
+    import functools
+
+    static_pos = (static_argnums,) if isinstance(static_argnums, int) else tuple(static_argnums or ())
+    static_kw = (static_argnames,) if isinstance(static_argnames, str) else tuple(static_argnames or ())
+
+    def deco(f):
+        @functools.wraps(f)
+        def wrapped(*args, **kw):
+            args = tuple(_wrap_out(a) if (type(a) is _np.ndarray and i not in static_pos) else a for i, a in enumerate(args))
+            kw = {k: (_wrap_out(v) if (type(v) is _np.ndarray and k not in static_kw) else v) for k, v in kw.items()}
+            return f(*args, **kw)
+
+        return wrapped
+
     if fn is None:
-        return lambda f: f
-    return fn
+        return deco
+    return deco(fn)
 
 
 def clear_caches():
