@@ -41,7 +41,13 @@ __all__ = [
     "generate_adaptive_mesh_level_restriction_3D",
     "get_squared_l2_norm_single_panel",
     "get_squared_l2_norm_single_voxel",
+    "node_to_bounds",
 ]
+
+
+def node_to_bounds(node) -> np.ndarray:
+    """``[xmin, xmax, ymin, ymax(, zmin, zmax)]`` of one node (`_adaptive_discretization_3D.py:28-32`)."""
+    return np.array([v for lim in _bounds(node) for v in lim], dtype=np.float64)
 
 
 def _node_bounds(nodes) -> np.ndarray:

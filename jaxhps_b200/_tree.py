@@ -25,6 +25,10 @@ __all__ = [
     "tree_equal",
     "find_node_at_corner",
     "find_nodes_along_interface_3D",
+    "find_path_from_root_2D",
+    "find_path_from_root_3D",
+    "node_at",
+    "get_all_leaves_special_ordering_3D",
     "FACE_CHILDREN_2D",
     "FACE_CHILDREN_3D",
 ]
@@ -287,3 +291,32 @@ def find_nodes_along_interface_3D(root: DiscretizationNode3D, xval=None, yval=No
     neg = [leaf for leaf in leaves if getattr(leaf, ax + "max") == val]
     pos = [leaf for leaf in leaves if getattr(leaf, ax + "min") == val]
     return neg, pos
+
+
+def find_path_from_root_2D(root, node):
+    """Reference name of :func:`find_path_from_root` (`_discretization_tree_operations_2D.py:108-146`)."""
+    return find_path_from_root(root, node)
+
+
+def find_path_from_root_3D(root, node):
+    """Reference name of :func:`find_path_from_root` (`_discretization_tree_operations_3D.py:212-272`)."""
+    return find_path_from_root(root, node)
+
+
+def node_at(node, xmin=None, xmax=None, ymin=None, ymax=None) -> bool:
+    """Whether ``node`` has the given coordinates among its bounds; ``None`` entries are ignored
+    (`_discretization_tree_operations_2D.py:335-347`)."""
+    want = {"xmin": xmin, "xmax": xmax, "ymin": ymin, "ymax": ymax}
+    return all(getattr(node, k) == v for k, v in want.items() if v is not None)
+
+
+def get_all_leaves_special_ordering_3D(node, child_traversal_order=None) -> Tuple:
+    """Leaves in depth-first order with the children visited in ``child_traversal_order``
+    (`_discretization_tree_operations_3D.py:7-22`)."""
+    order = range(8) if child_traversal_order is None else [int(c) for c in child_traversal_order]
+    if not node.children:
+        return (node,)
+    out = ()
+    for c in order:
+        out += get_all_leaves_special_ordering_3D(node.children[c], child_traversal_order)
+    return out
