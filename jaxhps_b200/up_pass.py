@@ -119,6 +119,7 @@ def nosource_local_solve_stage_uniform_2D_ItI(pde_problem, device=None, host_dev
 def _nosource_merge(T_arr, l: int, iti: bool, device, host_device, return_T: bool):
     dev = _lib.require_cuda(device)
     lib = _lib.load()
+    l = max(int(l), 1)  # as in the reference, l = 0 still performs the final merge
     cdt = torch.complex128 if iti else torch.float64
     with torch.cuda.device(dev):
         T = _lib.to_device(T_arr, dev, dtype=cdt)

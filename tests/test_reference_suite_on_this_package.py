@@ -47,3 +47,19 @@ def test_reference_host_tests_pass_against_this_package(tmp_path):
     assert " passed" in tail and "failed" not in tail, tail
     n_passed = int(tail.split(" passed")[0].split()[-1])
     assert n_passed >= 120, tail
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference checkout is not available here")
+def test_reference_accuracy_suite_passes_on_the_oracle(tmp_path):
+    """The reference's own analytic known-answer suite (`tests/test_accuracy`: leaf DtN / ItI maps, single merges,
+    source-free build + up pass) executed unmodified with the CPU ORACLE as the stage functions
+    (`tests/reference_alias_oracle`): the strongest pin of the oracle SURVEY section 8(c) asks for."""
+    dst = tmp_path / "tests"
+    shutil.copytree(os.path.join(REF_TESTS, "test_accuracy"), dst / "test_accuracy")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(HERE, "reference_alias_oracle"), ROOT, os.path.join(HERE, "golden", "jaxshim")])
+    out = subprocess.run([sys.executable, "-m", "pytest", str(dst), "-q", "-p", "no:cacheprovider"], cwd=tmp_path, env=env,
+                         capture_output=True, text=True, timeout=900)
+    tail = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-500:]
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
+    assert "failed" not in tail and int(tail.split(" passed")[0].split()[-1]) >= 14, tail
