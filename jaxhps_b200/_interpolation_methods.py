@@ -7,7 +7,6 @@ target point) instead of forming the Kronecker products the reference builds.
 """
 from __future__ import annotations
 
-from typing import Tuple
 
 import numpy as np
 

@@ -11,7 +11,6 @@ from __future__ import annotations
 import ctypes
 from typing import List
 
-import numpy as np
 import torch
 
 from . import _lib

@@ -21,7 +21,7 @@ from jaxhps._discretization_tree_operations_3D import add_eight_children  # noqa
 from jaxhps._precompute_operators_2D import precompute_L_4f1, precompute_projection_ops_2D  # noqa: E402
 from jaxhps._precompute_operators_3D import precompute_L_8f1, precompute_projection_ops_3D  # noqa: E402
 
-from adaptive_cases import ADAPTIVE_CASES, boundary_fn, build_domain, bump, internal_nodes, seeded_fields  # noqa: E402
+from adaptive_cases import ADAPTIVE_CASES, boundary_fn, build_domain, internal_nodes, seeded_fields  # noqa: E402
 
 
 def run(case):

@@ -16,7 +16,7 @@ from oracle import hps_oracle_adaptive as ora
 from _adaptive_emu import emu_compress, emu_down, emu_merge
 from test_oracle_adaptive import adaptive_problem
 
-from adaptive_cases import ADAPTIVE_CASES, boundary_fn
+from adaptive_cases import boundary_fn
 
 
 class OracleAdaptiveOps:

@@ -90,7 +90,6 @@ def test_adaptive_oracle_reproduces_polynomial_solution(dim):
     flux = store[id(root)]["T"] @ g_h
     sizes = ora._face_index_ranges(root, dim)
     # every leaf face panel has the same Gauss weights up to its area
-    from jaxhps_b200.quadrature import gauss_points  # noqa: F401
     w1 = np.polynomial.legendre.leggauss(q)[1]
     total = 0.0
     for f, leaves in enumerate([ora._face_leaves(root, f) for f in range(2 * dim)]):
