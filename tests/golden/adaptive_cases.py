@@ -11,6 +11,11 @@ ADAPTIVE_CASES = {
     "adapt3d_p4q2_manual": dict(dim=3, p=4, q=2, how="manual", path=[[2], [2, 2]], seed=43),
     "adapt3d_p6q4": dict(dim=3, p=6, q=4, how="generate", tol=1e-2, l2=False, seed=44),
     "adapt3d_p4q2_l2": dict(dim=3, p=4, q=2, how="generate", tol=5e-2, l2=True, seed=46),
+    # random level-restricted trees (split sequences recorded from a seeded random refinement): 49 and 43 leaves
+    "adapt2d_p6q4_random": dict(dim=2, p=6, q=4, how="manual", seed=47,
+                                path=[[0], [1], [2], [3], [0, 0], [0, 2], [0, 3], [1, 0], [1, 1], [1, 2], [2, 0], [3, 1],
+                                      [0, 0, 0], [1, 1, 2], [1, 2, 1]]),
+    "adapt3d_p4q2_random": dict(dim=3, p=4, q=2, how="manual", seed=48, path=[[3], [4], [6], [7], [7, 6]]),
 }
 
 

@@ -72,8 +72,12 @@ def operators():
 
 
 if __name__ == "__main__":
-    np.savez_compressed(os.path.join(HERE, "adapt_operators.npz"), **operators())
+    if len(sys.argv) == 1:
+        np.savez_compressed(os.path.join(HERE, "adapt_operators.npz"), **operators())
+    only = set(sys.argv[1:])
     for name, case in ADAPTIVE_CASES.items():
+        if only and name not in only:
+            continue
         data = run(case)
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **data)

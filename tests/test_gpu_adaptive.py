@@ -21,9 +21,12 @@ from adaptive_cases import ADAPTIVE_CASES, boundary_fn, internal_nodes
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
+# the two random-tree fixtures were added after the round's GPU budget was spent: they are CPU-checked (oracle, host
+# layer, plan tables) and join the GPU parametrisation once they have been run on a GPU
+GPU_CASES = sorted(k for k in ADAPTIVE_CASES if not k.endswith("_random"))
 
 
-@pytest.mark.parametrize("name", sorted(ADAPTIVE_CASES))
+@pytest.mark.parametrize("name", GPU_CASES)
 def test_adaptive_stages_match_oracle_and_reference(name):
     G = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
     case, dom, pb = adaptive_problem(name)
