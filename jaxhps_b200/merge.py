@@ -16,7 +16,6 @@ def _merge_stage(T_arr, h_arr, l: int, dim: int, device, host_device, return_T: 
     reference's whole-tree merge; ``n_roots>1``: the subtrees one GPU owns in the sharded build)."""
     dev = _lib.require_cuda(device)
     lib = _lib.load()
-    l = max(int(l), 1)  # the reference runs l - 1 batched levels plus one final merge, so l = 0 behaves like l = 1
     n_child = 8 if dim == 3 else 4
     n_face = 6 if dim == 3 else 4
     level_fn = lib.hps_merge_oct_dtn_level if dim == 3 else lib.hps_merge_quad_dtn_level
@@ -28,6 +27,8 @@ def _merge_stage(T_arr, h_arr, l: int, dim: int, device, host_device, return_T: 
         if not multi:
             h = h.unsqueeze(-1)
         n_src = h.shape[-1]
+        if l <= 0 and n_roots == 1 and T.shape[0] == n_child:
+            l = 1  # the reference runs l - 1 batched levels plus one final merge, so l = 0 on 4 / 8 operators is l = 1
         if T.shape[0] != n_roots * n_child**l:
             raise ValueError(f"expected {n_roots * n_child**l} leaf operators for l={l}, got {T.shape[0]}")
         S_lst, g_lst = [], []
@@ -129,7 +130,6 @@ def merge_stage_uniform_2D_ItI(T_arr, h_arr, l: int, device=None, host_device=No
     ``(S_lst, g_tilde_lst[, T_last][, h_last])``; every list entry keeps its batch axis (root: 1)."""
     dev = _lib.require_cuda(device)
     lib = _lib.load()
-    l = max(int(l), 1)  # as in the reference, l = 0 still performs the final merge
     with torch.cuda.device(dev):
         T = _lib.to_device(T_arr, dev, dtype=torch.complex128)
         h = _lib.to_device(h_arr, dev, dtype=torch.complex128)
@@ -140,6 +140,8 @@ def merge_stage_uniform_2D_ItI(T_arr, h_arr, l: int, device=None, host_device=No
         if not multi:
             h = h.unsqueeze(-1)
         n_src = h.shape[-1]
+        if l <= 0 and T.shape[0] == 4:
+            l = 1  # as in the reference, l = 0 on four operators still performs the final merge
         if T.shape[0] != 4**l:
             raise ValueError(f"expected {4**l} leaf operators for l={l}, got {T.shape[0]}")
         S_lst, g_lst = [], []

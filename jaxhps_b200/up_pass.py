@@ -118,12 +118,13 @@ def nosource_local_solve_stage_uniform_2D_ItI(pde_problem, device=None, host_dev
 def _nosource_merge(T_arr, l: int, iti: bool, device, host_device, return_T: bool):
     dev = _lib.require_cuda(device)
     lib = _lib.load()
-    l = max(int(l), 1)  # as in the reference, l = 0 still performs the final merge
     cdt = torch.complex128 if iti else torch.float64
     with torch.cuda.device(dev):
         T = _lib.to_device(T_arr, dev, dtype=cdt)
         if T.ndim == 4:
             T = T.reshape(-1, T.shape[-2], T.shape[-1])
+        if l <= 0 and T.shape[0] == 4:
+            l = 1  # as in the reference, l = 0 on four operators still performs the final merge
         if T.shape[0] != 4**l:
             raise ValueError(f"expected {4**l} leaf operators for l={l}, got {T.shape[0]}")
         S_lst, Di_lst, BDi_lst = [], [], []

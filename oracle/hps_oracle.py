@@ -407,7 +407,9 @@ def merge_stage_uniform_2D_DtN(T_arr: np.ndarray, h_arr: np.ndarray, l: int, ret
     """Level loop (`merge/_uniform_2D_DtN.py:13-203`); every entry of the lists keeps its batch
     axis, the root's being 1 (`:192-197`)."""
     S_lst, g_lst = [], []
-    for _ in range(max(l, 1)):  # the reference runs l - 1 batched levels plus one final merge, also for l = 0 (`:95,141`)
+    if l <= 0 and T_arr.shape[0] == 4:
+        l = 1  # the reference runs l - 1 batched levels plus one final merge, also for l = 0 (`:95,141`)
+    for _ in range(l):
         n = T_arr.shape[0] // 4
         outs = [uniform_quad_merge_DtN(T_arr[4 * i : 4 * i + 4], h_arr[4 * i : 4 * i + 4]) for i in range(n)]
         S_lst.append(np.stack([o[0] for o in outs]))
@@ -527,7 +529,9 @@ def merge_stage_uniform_2D_ItI(T_arr, h_arr, l: int, return_T: bool = False):
     if not multi:
         h_arr = h_arr[..., None]
     S_lst, g_lst = [], []
-    for _ in range(max(l, 1)):  # l - 1 batched levels plus one final merge in the reference, also for l = 0
+    if l <= 0 and T_arr.shape[0] == 4:
+        l = 1  # l - 1 batched levels plus one final merge in the reference, also for l = 0
+    for _ in range(l):
         n = T_arr.shape[0] // 4
         outs = [uniform_quad_merge_ItI(T_arr[4 * i : 4 * i + 4], h_arr[4 * i : 4 * i + 4]) for i in range(n)]
         S_lst.append(np.stack([o[0] for o in outs]))
@@ -611,7 +615,9 @@ def nosource_local_solve_stage_uniform_2D_ItI(pde_problem):
 def _nosource_merge_stage(T_arr, l, merge_fn, return_T):
     S_lst, D_inv_lst, BD_inv_lst = [], [], []
     h_dummy = np.zeros(T_arr.shape[:2] + (1,), dtype=T_arr.dtype)
-    for _ in range(max(l, 1)):
+    if l <= 0 and T_arr.shape[0] == 4:
+        l = 1
+    for _ in range(l):
         n = T_arr.shape[0] // 4
         outs = [merge_fn(T_arr[4 * i : 4 * i + 4], h_dummy[4 * i : 4 * i + 4], return_ops=True) for i in range(n)]
         S_lst.append(np.stack([o[0] for o in outs]))
