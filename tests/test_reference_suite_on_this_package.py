@@ -63,3 +63,59 @@ def test_reference_accuracy_suite_passes_on_the_oracle(tmp_path):
     tail = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-500:]
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
     assert "failed" not in tail and int(tail.split(" passed")[0].split()[-1]) >= 14, tail
+
+
+_MESH_SCRIPT = r"""
+import sys, json
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, "/root/reference/src")
+import jax.numpy as jnp
+import jaxhps as ref
+from jaxhps._discretization_tree import get_all_leaves
+out = {}
+for case in json.loads(sys.argv[2]):
+    dim, p, q, tol, l2, seed = case
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-0.6, 0.6, size=(3, dim)); w = rng.uniform(10, 60, size=3); a = rng.uniform(0.5, 1.5, size=3)
+    f = lambda x: sum(a[k] * jnp.exp(-w[k] * sum((x[..., d] - c[k, d]) ** 2 for d in range(dim))) for k in range(3))
+    root = (ref.DiscretizationNode2D(xmin=-1., xmax=1., ymin=-1., ymax=1.) if dim == 2 else
+            ref.DiscretizationNode3D(xmin=-1., xmax=1., ymin=-1., ymax=1., zmin=-1., zmax=1.))
+    ref.Domain.from_adaptive_discretization(p=p, q=q, root=root, f=f, tol=tol, use_l_2_norm=bool(l2))
+    keys = ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")[: 2 * dim]
+    out[str(seed)] = [[float(getattr(l, k)) for k in keys] for l in get_all_leaves(root)]
+print(json.dumps(out))
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference checkout is not available here")
+def test_mesh_generator_reproduces_the_reference_on_random_functions():
+    """Level-restricted adaptive meshes for sums of random Gaussian bumps (2D / 3D, L_inf / L_2 criterion): this
+    package's generator must produce exactly the leaves the reference's generator produces (run on the NumPy shim)."""
+    import json
+
+    import numpy as np
+
+    import jaxhps_b200 as hps
+    from jaxhps_b200._tree import get_all_leaves
+
+    cases = [(2, 8, 6, 1e-3, 0, 101), (2, 6, 4, 1e-2, 1, 102), (2, 10, 8, 1e-5, 0, 103), (3, 4, 2, 3e-2, 0, 104),
+             (3, 6, 4, 3e-2, 1, 105), (3, 5, 4, 1e-2, 0, 106)]
+    shim = os.path.join(HERE, "golden", "jaxshim")
+    out = subprocess.run([sys.executable, "-c", _MESH_SCRIPT, shim, json.dumps(cases)], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    ref_leaves = json.loads(out.stdout.strip().splitlines()[-1])
+    n_total = 0
+    for dim, p, q, tol, l2, seed in cases:
+        rng = np.random.default_rng(seed)
+        c, w, a = rng.uniform(-0.6, 0.6, size=(3, dim)), rng.uniform(10, 60, size=3), rng.uniform(0.5, 1.5, size=3)
+
+        def f(x, c=c, w=w, a=a, dim=dim):
+            return sum(a[k] * np.exp(-w[k] * sum((x[..., d] - c[k, d]) ** 2 for d in range(dim))) for k in range(3))
+
+        root = (hps.DiscretizationNode2D(-1.0, 1.0, -1.0, 1.0) if dim == 2 else hps.DiscretizationNode3D(-1.0, 1.0, -1.0, 1.0, -1.0, 1.0))
+        hps.Domain.from_adaptive_discretization(p=p, q=q, root=root, f=f, tol=tol, use_l_2_norm=bool(l2))
+        keys = ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")[: 2 * dim]
+        mine = [[float(getattr(leaf, k)) for k in keys] for leaf in get_all_leaves(root)]
+        assert mine == ref_leaves[str(seed)], (dim, p, q, tol, l2, len(mine), len(ref_leaves[str(seed)]))
+        n_total += len(mine)
+    assert n_total > 100
