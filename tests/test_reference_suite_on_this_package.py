@@ -119,3 +119,64 @@ def test_mesh_generator_reproduces_the_reference_on_random_functions():
         assert mine == ref_leaves[str(seed)], (dim, p, q, tol, l2, len(mine), len(ref_leaves[str(seed)]))
         n_total += len(mine)
     assert n_total > 100
+
+
+_OPS_SCRIPT = r"""
+import sys, json
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, "/root/reference/src")
+import jax.numpy as jnp
+import jaxhps as ref
+np.savez(sys.argv[3], **{})
+out = {}
+for dim, p, q, L, iti in json.loads(sys.argv[2]):
+    root = (ref.DiscretizationNode2D(xmin=-1., xmax=2., ymin=0., ymax=3.) if dim == 2 else
+            ref.DiscretizationNode3D(xmin=-1., xmax=1., ymin=0., ymax=2., zmin=1., zmax=3.))
+    dom = ref.Domain(p=p, q=q, root=root, L=L)
+    z = jnp.zeros(dom.interior_points[..., 0].shape)
+    pb = ref.PDEProblem(dom, source=z, D_xx_coefficients=z, **(dict(use_ItI=True, eta=2.5) if iti else {}))
+    tag = f"{dim}_{p}_{q}_{L}_{int(iti)}"
+    for name in ("P", "Q", "D_x", "D_y", "D_xx", "D_xy", "D_yy", "D_z", "D_zz", "D_xz", "D_yz", "G", "QH"):
+        v = getattr(pb, name, None)
+        if v is not None:
+            out[tag + ":" + name] = np.asarray(v)
+    out[tag + ":interior"] = np.asarray(dom.interior_points)
+    out[tag + ":boundary"] = np.asarray(dom.boundary_points)
+np.savez(sys.argv[3], **out)
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference checkout is not available here")
+def test_precomputed_operators_and_point_clouds_match_the_reference_live(tmp_path):
+    """Differential check over a range of orders: every pre-computed operator and both point clouds of the
+    reference's PDEProblem / Domain (run on the NumPy shim) against this package's host layer."""
+    import json
+
+    import numpy as np
+
+    import jaxhps_b200 as hps
+
+    cases = [(2, 5, 3, 1, 0), (2, 8, 6, 2, 0), (2, 9, 7, 1, 1), (2, 12, 10, 1, 1), (3, 4, 2, 1, 0), (3, 5, 4, 1, 0), (3, 7, 5, 1, 0)]
+    shim = os.path.join(HERE, "golden", "jaxshim")
+    npz = str(tmp_path / "ref_ops.npz")
+    out = subprocess.run([sys.executable, "-c", _OPS_SCRIPT, shim, json.dumps(cases), npz], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    R = np.load(npz)
+    checked = 0
+    for dim, p, q, L, iti in cases:
+        root = (hps.DiscretizationNode2D(-1.0, 2.0, 0.0, 3.0) if dim == 2 else hps.DiscretizationNode3D(-1.0, 1.0, 0.0, 2.0, 1.0, 3.0))
+        dom = hps.Domain(p, q, root, L)
+        z = np.zeros(dom.interior_points[..., 0].shape)
+        pb = hps.PDEProblem(dom, source=z, D_xx_coefficients=z, **(dict(use_ItI=True, eta=2.5) if iti else {}))
+        tag = f"{dim}_{p}_{q}_{L}_{int(iti)}"
+        for key in [k for k in R.files if k.startswith(tag + ":")]:
+            name = key.split(":")[1]
+            mine = {"interior": dom.interior_points, "boundary": dom.boundary_points}.get(name)
+            if mine is None:
+                mine = getattr(pb, name)
+            ref_v = R[key]
+            scale = max(1.0, float(np.abs(ref_v).max()))
+            assert mine.shape == ref_v.shape, key
+            assert np.abs(mine - ref_v).max() <= 1e-12 * scale, (key, float(np.abs(mine - ref_v).max()))
+            checked += 1
+    assert checked >= 50
