@@ -180,3 +180,72 @@ def test_precomputed_operators_and_point_clouds_match_the_reference_live(tmp_pat
             assert np.abs(mine - ref_v).max() <= 1e-12 * scale, (key, float(np.abs(mine - ref_v).max()))
             checked += 1
     assert checked >= 50
+
+
+_STAGE_SCRIPT = r"""
+import sys, json
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, "/root/reference/src"); sys.path.insert(0, sys.argv[4])
+import jax.numpy as jnp
+import jaxhps as ref
+from jaxhps.local_solve import local_solve_stage_uniform_2D_DtN, local_solve_stage_uniform_2D_ItI, local_solve_stage_uniform_3D_DtN
+from jaxhps.merge import merge_stage_uniform_2D_DtN, merge_stage_uniform_2D_ItI, merge_stage_uniform_3D_DtN
+from jaxhps.down_pass import down_pass_uniform_2D_DtN, down_pass_uniform_2D_ItI, down_pass_uniform_3D_DtN
+from _cases import seeded_inputs, seeded_inputs_iti, ETA
+out = {}
+for dim, p, q, L, nsrc, seed in json.loads(sys.argv[2]):
+    iti = dim == 20
+    co, src, bdry = seeded_inputs_iti(p, q, L, nsrc, seed) if iti else seeded_inputs(dim, p, q, L, nsrc, seed)
+    if dim == 3:
+        root = ref.DiscretizationNode3D(xmin=0., xmax=1., ymin=0., ymax=1., zmin=0., zmax=1.)
+        ls, mg, dp = local_solve_stage_uniform_3D_DtN, merge_stage_uniform_3D_DtN, down_pass_uniform_3D_DtN
+    else:
+        root = ref.DiscretizationNode2D(xmin=-1., xmax=1., ymin=-1., ymax=1.)
+        ls, mg, dp = ((local_solve_stage_uniform_2D_ItI, merge_stage_uniform_2D_ItI, down_pass_uniform_2D_ItI) if iti else
+                      (local_solve_stage_uniform_2D_DtN, merge_stage_uniform_2D_DtN, down_pass_uniform_2D_DtN))
+    dom = ref.Domain(p=p, q=q, root=root, L=L)
+    pb = ref.PDEProblem(dom, source=jnp.array(src), **{k: jnp.array(v) for k, v in co.items()}, **(dict(use_ItI=True, eta=ETA) if iti else {}))
+    Y, T, v, h = ls(pb)
+    S_lst, g_lst, T_top = mg(T, h, l=L, return_T=True)
+    u = dp(jnp.array(bdry), S_lst, g_lst, Y, v)
+    tag = f"{dim}_{p}_{q}_{L}_{nsrc}_{seed}"
+    out[tag + ":u"], out[tag + ":T_top"], out[tag + ":h"] = np.asarray(u), np.asarray(T_top), np.asarray(h)
+    out[tag + ":g_root"] = np.asarray(g_lst[-1])
+np.savez(sys.argv[3], **out)
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference checkout is not available here")
+def test_oracle_matches_the_reference_live_on_more_seeded_problems(tmp_path):
+    """Beyond the committed fixtures: the reference's uniform stage functions (on the NumPy shim) and the oracle on six
+    further seeded problems (2D DtN, 2D ItI, 3D DtN; single and multi-source)."""
+    import json
+
+    import numpy as np
+
+    from oracle import hps_oracle as orc
+    from _cases import rel_err, seeded_problem
+
+    cases = [(2, 9, 7, 2, 1, 201), (2, 6, 4, 3, 2, 202), (20, 7, 5, 2, 1, 203), (20, 6, 4, 1, 3, 204), (3, 5, 3, 2, 1, 205),
+             (3, 6, 4, 1, 1, 206)]
+    shim = os.path.join(HERE, "golden", "jaxshim")
+    npz = str(tmp_path / "ref_stage.npz")
+    out = subprocess.run([sys.executable, "-c", _STAGE_SCRIPT, shim, json.dumps(cases), npz, HERE], capture_output=True, text=True,
+                         timeout=1200, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert out.returncode == 0, out.stderr[-2000:]
+    R = np.load(npz)
+    for dim, p, q, L, nsrc, seed in cases:
+        pb, bdry = seeded_problem(dim, p, q, L, nsrc, seed)
+        if dim == 20:
+            ls, mg, dp = orc.local_solve_stage_uniform_2D_ItI, orc.merge_stage_uniform_2D_ItI, orc.down_pass_uniform_2D_ItI
+        elif dim == 3:
+            ls, mg, dp = orc.local_solve_stage_uniform_3D_DtN, orc.merge_stage_uniform_3D_DtN, orc.down_pass_uniform_3D_DtN
+        else:
+            ls, mg, dp = orc.local_solve_stage_uniform_2D_DtN, orc.merge_stage_uniform_2D_DtN, orc.down_pass_uniform_2D_DtN
+        Y, T, v, h = ls(pb)
+        S_lst, g_lst, T_top = mg(T, h, L, return_T=True)
+        u = dp(bdry, S_lst, g_lst, Y, v)
+        tag = f"{dim}_{p}_{q}_{L}_{nsrc}_{seed}"
+        tol = 1e-9 if dim == 20 else 1e-11
+        assert rel_err(h, R[tag + ":h"]) < tol and rel_err(T_top, R[tag + ":T_top"]) < tol, tag
+        assert rel_err(g_lst[-1], R[tag + ":g_root"]) < tol and rel_err(u, R[tag + ":u"]) < tol, tag
