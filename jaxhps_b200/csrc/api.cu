@@ -18,7 +18,36 @@ int fail_cuda(cudaError_t e, const char* where) {
   last_error() = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + where;
   return static_cast<int>(e);
 }
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
+
+int device_state(DeviceState*& out) {
+  static DeviceState states[64];
+  int dev = 0;
+  HPS_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail_arg(1, "device ordinal out of range");
+  out = &states[dev];
+  return 0;
+}
+
+int aux_for_stream(cudaStream_t st, Aux*& out) {
+  DeviceState* ds = nullptr;
+  HPS_TRY(device_state(ds));
+  std::lock_guard<std::mutex> lock(ds->mu);
+  Aux& a = ds->aux[st];  // node-based map: the reference stays valid
+  if (!a.stream) {
+    int lo = 0, hi = 0;
+    HPS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    HPS_CUDA(cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 2; ++i) {
+      HPS_CUDA(cudaEventCreateWithFlags(&a.panel_done[i], cudaEventDisableTiming));
+      HPS_CUDA(cudaEventCreateWithFlags(&a.update_done[i], cudaEventDisableTiming));
+    }
+    HPS_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
+    HPS_CUDA(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+  }
+  out = &a;
+  return 0;
+}
 
 namespace {
 struct ProfState {
@@ -28,6 +57,7 @@ struct ProfState {
   struct Rec { int cat; size_t e0, e1; double work; };
   std::vector<Rec> recs;
   size_t open_rec[PROF_NCAT] = {};
+  std::mutex mu;
   cudaEvent_t take() {
     if (used == pool.size()) {
       cudaEvent_t e;
@@ -41,6 +71,7 @@ struct ProfState {
 
 void prof_begin(int cat, cudaStream_t st, double work) {
   if (!g_prof.on) return;
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   const size_t i0 = g_prof.used;
   cudaEventRecord(g_prof.take(), st);
   g_prof.open_rec[cat] = g_prof.recs.size();
@@ -48,6 +79,7 @@ void prof_begin(int cat, cudaStream_t st, double work) {
 }
 void prof_end(int cat, cudaStream_t st) {
   if (!g_prof.on) return;
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   const size_t i1 = g_prof.used;
   cudaEventRecord(g_prof.take(), st);
   g_prof.recs[g_prof.open_rec[cat]].e1 = i1;
@@ -62,6 +94,7 @@ int hps_version(void) { return 100; }
 const char* hps_last_error_string(void) { return last_error().c_str(); }
 
 int hps_prof_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   g_prof.on = on != 0;
   g_prof.used = 0;
   g_prof.recs.clear();
@@ -70,7 +103,9 @@ int hps_prof_enable(int on) {
 }
 
 int hps_prof_read(void* stream, double* ms, double* work, int64_t* launches, int64_t* all_launches) {
-  HPS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  HPS_CUDA(cudaDeviceSynchronize());
+  (void)stream;
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   for (int c = 0; c < PROF_NCAT; ++c) { ms[c] = 0.0; work[c] = 0.0; launches[c] = 0; }
   for (const auto& r : g_prof.recs) {
     float t = 0.f;

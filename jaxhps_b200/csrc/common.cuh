@@ -1,9 +1,12 @@
 // Shared helpers for libhps_b200 (sm_100a).  Internal header.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 
 namespace hps {
 
@@ -19,7 +22,27 @@ int fail_cuda(cudaError_t e, const char* where);
   } while (0)
 
 // every kernel launch site goes through this (or bumps g_launches itself)
-extern long long g_launches;
+extern std::atomic<long long> g_launches;
+
+// Per-device library state.  Everything in it is either immutable after a once-only initialisation
+// (kernel attributes, occupancy numbers) or keyed by the CALLER'S stream under a mutex, so calls on
+// different streams / host threads / devices never share scratch streams or events.
+struct Aux {  // look-ahead stream + events of one (device, caller stream) pair
+  cudaStream_t stream = nullptr;
+  cudaEvent_t panel_done[2] = {nullptr, nullptr};
+  cudaEvent_t update_done[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+struct DeviceState {
+  std::atomic<bool> gemm_configured{false};
+  std::atomic<bool> lu_configured{false};
+  std::atomic<int> coop_capacity{-1};   // co-resident CTAs of the cooperative panel kernel
+  std::atomic<int> sm_count{0};
+  std::mutex mu;
+  std::unordered_map<cudaStream_t, Aux> aux;  // guarded by mu
+};
+int device_state(DeviceState*& out);            // state of the current device
+int aux_for_stream(cudaStream_t st, Aux*& out);  // created on first use
 #define HPS_LAUNCH_CHECK(name)                                    \
   do {                                                            \
     ++::hps::g_launches;                                          \

@@ -19,9 +19,8 @@ using Cfg = gemmk::Config<32, 32, 4, 2, 16, 3, 2>;
 using gemmk::GemmArgs;
 constexpr int BM = Cfg::BM, BN = Cfg::BN, THREADS = Cfg::THREADS;
 constexpr size_t SMEM_BYTES = Cfg::SMEM_BYTES;
-#define gemm_kernel gemmk::gemm_kernel_mb<Cfg>
-// copy addressing hoisted out of the K loop (default; HPS_GEMM_HOIST=0 selects gemm_kernel_mb)
-#define gemm_kernel_alt gemmk::gemm_kernel_hoist<Cfg>
+constexpr int RASTER = 12;  // 12 x 24 tiles of 128x64 = a 1536^2 block of C per wave of 296 CTAs
+#define gemm_kernel gemmk::gemm_kernel_hoist<Cfg>
 
 // ---- narrow-N kernels: one warp per output row, lanes stride over K -------------------------
 // These are the HBM-bound mat-vecs of the down pass (g_int = S g_ext + g~, u = Y g + v): every
@@ -174,16 +173,11 @@ int dgemm(cudaStream_t st, int M, int N, int K, double alpha, const double* A, i
   if (N < 16) {
     return dgemm_skinny(st, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, C, ldc, sC, batch);
   }
-  static bool configured[64] = {};  // cudaFuncSetAttribute is per device
-  int dev = 0;
-  HPS_CUDA(cudaGetDevice(&dev));
-  // hoisted-addressing kernel by default (31.3 vs 29.2 TF/s inside the L=3 build); HPS_GEMM_HOIST=0 selects the
-  // per-step-addressing kernel it was derived from
-  static const bool use_alt = [] { const char* e = std::getenv("HPS_GEMM_HOIST"); return !(e && e[0] == '0'); }();
-  if (dev >= 0 && dev < 64 && !configured[dev]) {
+  DeviceState* ds = nullptr;
+  HPS_TRY(device_state(ds));
+  if (!ds->gemm_configured.load(std::memory_order_acquire)) {  // per device; idempotent, so a race is harmless
     HPS_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    HPS_CUDA(cudaFuncSetAttribute(gemm_kernel_alt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    configured[dev] = true;
+    ds->gemm_configured.store(true, std::memory_order_release);
   }
   GemmArgs g;
   g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
@@ -194,8 +188,9 @@ int dgemm(cudaStream_t st, int M, int N, int K, double alpha, const double* A, i
     const int nb = min(65535, batch - b0);
     g.A = A + (int64_t)b0 * sA; g.B = B + (int64_t)b0 * sB; g.C = C + (int64_t)b0 * sC;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, nb);
-    if (use_alt) gemm_kernel_alt<<<grid, THREADS, SMEM_BYTES, st>>>(g);
-    else gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(g);
+    // large single products: launch order grouped into RASTER tile rows (profiles/r02_gemm_lab.txt)
+    g.raster = (grid.y >= 2 * RASTER && grid.x >= 8) ? RASTER : 0;
+    gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(g);
   }
   prof_end(PROF_GEMM, st);
   HPS_LAUNCH_CHECK("gemm_kernel");

@@ -15,14 +15,22 @@
 //      large-K rate of the DMMA kernel and are read/written O(log) times instead of n/128 times.
 //
 // Kernels:
-//   panel_kernel   IB columns at a time; the panel's rows are split over G CTAs that keep
-//                  their chunk in shared memory.  One group barrier per column: a thread-block
-//                  cluster barrier for G<=8, a cooperative-launch global barrier above that.
+//   blockcol_kernel  factors a whole NB-wide block column in ONE launch: the rows are split over G
+//                  co-scheduled CTAs (thread-block cluster for G<=8, cooperative launch above) that keep
+//                  their rows x NB chunk in shared memory.  Per column ONE exchange through L2: every
+//                  CTA publishes its pivot candidate (value, row, the row's NB entries) followed by a
+//                  release-stored epoch flag, every CTA acquires all flags and elects the same winner —
+//                  no atomics and no separate barrier.  After each IB-wide inner panel the first CTA
+//                  publishes U12 = L11^-1 A12 and every CTA updates its own rows from shared memory.
+//   panel_kernel   legacy IB-column panel for block columns too tall to be co-resident
+//                  (more than 148 x 196 rows: only the L=4 root); one group barrier per column.
 //   laswp_kernel   row interchanges on a column range (rows are contiguous: coalesced).
 //   inner_trsm     32x32 unit-lower solve inside the outer panel.
 //   trtri kernels  invert NBxNB triangular diagonal blocks in shared memory so that every
 //                  triangular solve becomes a DMMA GEMM (in place, single tile row).
 #include <cooperative_groups.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -208,6 +216,272 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) panel_kernel(PanelArgs a) {
   }
 }
 
+
+// =====================================================================================
+// Block-column kernel
+// =====================================================================================
+constexpr int BC_ROWS = 196;     // rows of the block column one CTA keeps in shared memory
+constexpr int BC_LD = NB + 1;    // odd leading dimension: column walks are bank-conflict free
+constexpr int BC_THREADS = 512;
+constexpr int BC_UW = NB - IB;   // widest U12 block
+constexpr int BC_MAX_G = 148;
+
+struct BcCand {        // content first, header last: the flag is release-stored after everything else
+  double content[NB];
+  double val;          // |a|, negative when the CTA has no eligible row
+  int row;             // block-column-relative row index
+  unsigned flag;       // epoch of the column this candidate belongs to
+};
+
+struct BcArgs {
+  double* A; int64_t lda, sA;
+  int n, j, jb, G, rpc;     // rpc: rows per CTA (>= jb when G > 1, so CTA 0 owns every pivot row)
+  int* ipiv;                // [batch][n]
+  int* info;                // [batch]
+  char* scratch;            // per matrix: BcCand[2][Gcap], diag[2][NB], u12[IB][BC_UW], u12 flag
+  size_t scratch_stride;
+  int Gcap;
+};
+
+__host__ __device__ inline size_t bc_scratch_bytes(int Gcap) {
+  return (size_t)2 * Gcap * sizeof(BcCand) + (size_t)2 * NB * sizeof(double) + (size_t)IB * BC_UW * sizeof(double) + 256;
+}
+inline size_t bc_smem_bytes(int rpc) {
+  return sizeof(double) * ((size_t)rpc * BC_LD + (size_t)IB * BC_UW + NB + 16) + sizeof(int) * 16;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// SHARED = false: one CTA per matrix, everything stays in shared memory.
+// SHARED = true : G co-scheduled CTAs per matrix exchange pivot candidates through global memory (L2).
+template <bool SHARED>
+__global__ void __launch_bounds__(BC_THREADS, 1) blockcol_kernel(BcArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int LD = BC_LD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = blockIdx.x, mat = blockIdx.y;
+  const int G = a.G, jb = a.jb;
+  const int rows = a.n - a.j;
+  const int r0 = min(rows, g * a.rpc), r1 = min(rows, r0 + a.rpc), nr = r1 - r0;
+  double* A = a.A + (int64_t)mat * a.sA + (int64_t)a.j * a.lda + a.j;
+  int* ipiv = a.ipiv + (int64_t)mat * a.n + a.j;
+
+  double* tile = sm;                                   // [rpc][LD]
+  double* U = tile + (size_t)a.rpc * LD;               // [IB][BC_UW]
+  double* prow = U + IB * BC_UW;                       // [NB]
+  double* red_val = prow + NB;                         // [16]
+  int* red_idx = reinterpret_cast<int*>(red_val + 16); // [16]
+  __shared__ int s_wg, s_wr;
+
+  char* sc = a.scratch + (size_t)mat * a.scratch_stride;
+  BcCand* cands = reinterpret_cast<BcCand*>(sc);                                       // [2][Gcap]
+  double* diag = reinterpret_cast<double*>(sc + (size_t)2 * a.Gcap * sizeof(BcCand));  // [2][NB]
+  double* u12g = diag + 2 * NB;                                                        // [IB][BC_UW]
+  unsigned* u12_flag = reinterpret_cast<unsigned*>(u12g + IB * BC_UW);
+
+  for (int idx = tid; idx < nr * jb; idx += BC_THREADS) {
+    const int r = idx / jb, c = idx - r * jb;
+    tile[r * LD + c] = A[(int64_t)(r0 + r) * a.lda + c];
+  }
+  __syncthreads();
+
+  for (int c = 0; c < jb; ++c) {
+    const int c0 = (c / IB) * IB, pe = min(c0 + IB, jb);
+    // ---- local arg-max of |a[r][c]| over rows >= c (lowest row wins ties) ----
+    double best = -1.0;
+    int bidx = 0x7fffffff;
+    for (int r = tid; r < nr; r += BC_THREADS) {
+      if (r0 + r >= c) {
+        const double v = fabs(tile[r * LD + c]);
+        if (v > best) { best = v; bidx = r; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    if (lane == 0) { red_val[warp] = best; red_idx[warp] = bidx; }
+    __syncthreads();
+    best = -1.0; bidx = 0x7fffffff;
+#pragma unroll
+    for (int w = 0; w < BC_THREADS / 32; ++w) {  // every thread reduces the 16 partials itself
+      const double ov = red_val[w];
+      const int oi = red_idx[w];
+      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+
+    int p;  // block-column-relative pivot row
+    if (!SHARED) {
+      p = (best >= 0.0) ? bidx : c;
+      if (tid < jb) {  // each thread swaps its own column: no cross-thread hazard
+        const double xp = tile[p * LD + tid], xc = tile[c * LD + tid];
+        tile[p * LD + tid] = xc;
+        tile[c * LD + tid] = xp;
+        prow[tid] = xp;
+      }
+      __syncthreads();
+    } else {
+      const unsigned epoch = (unsigned)(a.j + c + 1);
+      BcCand* mine = cands + (size_t)(c & 1) * a.Gcap + g;
+      double* dg = diag + (c & 1) * NB;
+      if (tid < jb) {
+        if (best >= 0.0) mine->content[tid] = tile[bidx * LD + tid];
+      } else if (tid >= NB && tid < NB + jb) {
+        if (c >= r0 && c < r1) dg[tid - NB] = tile[(c - r0) * LD + tid - NB];
+      }
+      __syncthreads();
+      if (tid == 0) {
+        mine->val = best;
+        mine->row = (best >= 0.0) ? r0 + bidx : -1;
+        __threadfence();
+        st_release_u32(&mine->flag, epoch);
+      }
+      if (warp == 0) {
+        // every CTA elects the same winner: largest value, lowest row on ties
+        double wv = -1.0; int wg = 0, wr = 0x7fffffff;
+        for (int k = lane; k < G; k += 32) {
+          const BcCand* ck = cands + (size_t)(c & 1) * a.Gcap + k;
+          while (ld_acquire_u32(&ck->flag) != epoch) { }
+          const double v = __ldcg(&ck->val);
+          const int r = __ldcg(&ck->row);
+          if (v >= 0.0 && (v > wv || (v == wv && r < wr))) { wv = v; wg = k; wr = r; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, wv, o);
+          const int og = __shfl_xor_sync(0xffffffffu, wg, o);
+          const int orr = __shfl_xor_sync(0xffffffffu, wr, o);
+          if (ov > wv || (ov == wv && orr < wr)) { wv = ov; wg = og; wr = orr; }
+        }
+        if (lane == 0) { s_wg = wg; s_wr = (wv >= 0.0) ? wr : c; }
+      }
+      __syncthreads();
+      p = s_wr;
+      if (tid < jb) {
+        const double x = __ldcg(&cands[(size_t)(c & 1) * a.Gcap + s_wg].content[tid]);
+        prow[tid] = x;
+        if (c >= r0 && c < r1) tile[(c - r0) * LD + tid] = x;  // the pivot row moves up to row c ...
+      } else if (tid >= NB && tid < NB + jb) {
+        if (p != c && p >= r0 && p < r1) tile[(p - r0) * LD + tid - NB] = __ldcg(&dg[tid - NB]);  // ... and row c takes its place
+      }
+      __syncthreads();
+    }
+    if (g == 0 && tid == 0) ipiv[c] = a.j + p;
+    const double piv = prow[c];
+    if (piv == 0.0) {
+      if (g == 0 && tid == 0 && a.info[mat] == 0) a.info[mat] = a.j + c + 1;
+    } else {
+      // ---- scale the column, rank-1 update of the rest of the inner panel ----
+      for (int r = tid; r < nr; r += BC_THREADS) {
+        if (r0 + r > c) {
+          double* row = tile + r * LD;
+          const double l = row[c] / piv;
+          row[c] = l;
+          for (int cc = c + 1; cc < pe; ++cc) row[cc] = fma(-l, prow[cc], row[cc]);
+        }
+      }
+    }
+    __syncthreads();
+
+    if (c == pe - 1 && pe < jb) {
+      // ---- inner panel finished: U12 = L11^-1 A12, then rows >= pe get A22 -= L21 U12 ----
+      const int W = jb - pe;  // pe < jb means this panel is IB wide
+      if (g == 0) {
+        if (tid < W) {  // one column of U12 per thread, forward substitution in registers
+          double x[IB];
+#pragma unroll
+          for (int r = 0; r < IB; ++r) x[r] = tile[(c0 + r) * LD + pe + tid];
+#pragma unroll
+          for (int r = 1; r < IB; ++r) {
+            double s = x[r];
+#pragma unroll
+            for (int t = 0; t < r; ++t) s = fma(-tile[(c0 + r) * LD + c0 + t], x[t], s);
+            x[r] = s;
+          }
+#pragma unroll
+          for (int r = 0; r < IB; ++r) {
+            tile[(c0 + r) * LD + pe + tid] = x[r];
+            U[r * BC_UW + tid] = x[r];
+            if (SHARED) u12g[r * BC_UW + tid] = x[r];
+          }
+        }
+        __syncthreads();
+        if (SHARED && tid == 0) {
+          __threadfence();
+          st_release_u32(u12_flag, (unsigned)(a.j + pe));
+        }
+      } else {
+        if (tid == 0) {
+          while (ld_acquire_u32(u12_flag) != (unsigned)(a.j + pe)) { }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < IB * W; idx += BC_THREADS) {
+          const int r = idx / W, x = idx - r * W;
+          U[r * BC_UW + x] = __ldcg(&u12g[r * BC_UW + x]);
+        }
+        __syncthreads();
+      }
+      // 4x4 register tiles: a warp covers 16 rows x 32 columns per pass
+      const int ly = lane >> 3, lx = lane & 7;
+      const int nstrips = (nr + 15) >> 4, ncp = (W + 31) >> 5;
+      for (int s = warp; s < nstrips; s += BC_THREADS / 32) {
+        const int rb = s * 16 + ly * 4;
+        if (r0 + s * 16 + 15 < pe) continue;  // whole strip above the trailing block
+        const double* ap[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ap[i] = tile + min(rb + i, a.rpc - 1) * LD + c0;
+        for (int cp = 0; cp < ncp; ++cp) {
+          const int cb = cp * 32 + lx * 4;
+          double acc[4][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
+          if (cb < BC_UW) {
+#pragma unroll 8
+            for (int k = 0; k < IB; ++k) {
+              const double2 b01 = *reinterpret_cast<const double2*>(U + k * BC_UW + cb);
+              const double2 b23 = *reinterpret_cast<const double2*>(U + k * BC_UW + cb + 2);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const double av = ap[i][k];
+                acc[i][0] = fma(av, b01.x, acc[i][0]);
+                acc[i][1] = fma(av, b01.y, acc[i][1]);
+                acc[i][2] = fma(av, b23.x, acc[i][2]);
+                acc[i][3] = fma(av, b23.y, acc[i][3]);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = rb + i;
+            if (r < nr && r0 + r >= pe) {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                if (cb + jj < W) tile[r * LD + pe + cb + jj] -= acc[i][jj];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  for (int idx = tid; idx < nr * jb; idx += BC_THREADS) {
+    const int r = idx / jb, c = idx - r * jb;
+    A[(int64_t)(r0 + r) * a.lda + c] = tile[r * LD + c];
+  }
+}
+
 constexpr size_t PANEL_SMEM = sizeof(double) * ((size_t)PANEL_ROWS * PANEL_LD + IB + 16) + sizeof(int) * 16;
 
 // rows k0..k1-1 of every matrix are exchanged with rows ipiv[k] on columns [c0, c0+ncols)
@@ -373,7 +647,16 @@ struct LuWorkspace {
   double* Uinv;  // [batch][nblk][NB][NB] inverses of the upper diagonal blocks
   double* tmp;   // [batch][NB][16] staging for narrow right-hand sides
   PanelScratch* scratch;
+  char* bc_scratch;  // block-column kernel exchange area, bc_stride bytes per matrix (flags must start at 0)
+  size_t bc_stride;
+  int bc_Gcap;
 };
+
+// CTAs per matrix the block-column kernel may need for an n x n factorisation (0: single-CTA only)
+inline int bc_gcap(int n) {
+  const int G0 = (n + BC_ROWS - 1) / BC_ROWS;
+  return G0 <= 1 ? 0 : std::min(G0, BC_MAX_G);
+}
 
 bool carve(Arena& ar, int batch, int n, LuWorkspace& w) {
   const size_t nblk = (n + NB - 1) / NB;
@@ -382,10 +665,27 @@ bool carve(Arena& ar, int batch, int n, LuWorkspace& w) {
   w.Uinv = ar.take<double>((size_t)batch * nblk * NB * NB);
   w.tmp = ar.take<double>((size_t)batch * NB * 16);
   w.scratch = ar.take<PanelScratch>((size_t)batch);
-  return w.ipiv && w.Linv && w.Uinv && w.tmp && w.scratch;
+  w.bc_Gcap = bc_gcap(n);
+  w.bc_stride = w.bc_Gcap ? align_up(bc_scratch_bytes(w.bc_Gcap), 256) : 0;
+  w.bc_scratch = w.bc_Gcap ? ar.take<char>((size_t)batch * w.bc_stride) : reinterpret_cast<char*>(w.scratch);
+  return w.ipiv && w.Linv && w.Uinv && w.tmp && w.scratch && w.bc_scratch;
 }
 
-int g_coop_capacity = -1;  // co-resident panel CTAs for the cooperative variant
+// co-resident CTAs of a cooperative kernel on the current device (queried once per device)
+template <typename K>
+int coop_capacity(K kernel, int threads, size_t smem, std::atomic<int>& cache, int& out) {
+  int cap = cache.load(std::memory_order_acquire);
+  if (cap < 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    HPS_CUDA(cudaGetDevice(&dev));
+    HPS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    HPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    cap = sms * per_sm;
+    cache.store(cap, std::memory_order_release);
+  }
+  out = cap;
+  return 0;
+}
 
 int launch_panel_impl(cudaStream_t st, int batch, PanelArgs pa);
 int launch_panel(cudaStream_t st, int batch, PanelArgs pa) {
@@ -424,15 +724,11 @@ int launch_panel_impl(cudaStream_t st, int batch, PanelArgs pa) {
   }
   if (G > MAX_G) return fail_arg(3, "matrix too tall for the panel kernel (n > 98304)");
   pa.G = G;
-  if (g_coop_capacity < 0) {
-    int dev = 0, sms = 0, per_sm = 0;
-    HPS_CUDA(cudaGetDevice(&dev));
-    HPS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    HPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, panel_kernel<SYNC_GRID>, PANEL_THREADS,
-                                                           PANEL_SMEM));
-    g_coop_capacity = sms * per_sm;
-  }
-  const int per_launch = g_coop_capacity / G;
+  DeviceState* ds = nullptr;
+  HPS_TRY(device_state(ds));
+  int capacity = 0;
+  HPS_TRY(coop_capacity(panel_kernel<SYNC_GRID>, PANEL_THREADS, PANEL_SMEM, ds->coop_capacity, capacity));
+  const int per_launch = capacity / G;
   if (per_launch < 1) return fail_arg(3, "panel does not fit a cooperative launch");
   for (int b0 = 0; b0 < batch; b0 += per_launch) {
     const int nb = min(per_launch, batch - b0);
@@ -463,16 +759,82 @@ int laswp(cudaStream_t st, int batch, double* A, int64_t lda, int64_t sA, int c0
 
 // opt the large-shared-memory kernels in, once per device
 int configure_lu_kernels() {
-  static bool configured[64] = {};
-  int dev = 0;
-  HPS_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || configured[dev]) return 0;
+  DeviceState* ds = nullptr;
+  HPS_TRY(device_state(ds));
+  if (ds->lu_configured.load(std::memory_order_acquire)) return 0;  // idempotent: a race only repeats the calls
+    HPS_CUDA(cudaFuncSetAttribute(blockcol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc_smem_bytes(BC_ROWS)));
+    HPS_CUDA(cudaFuncSetAttribute(blockcol_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc_smem_bytes(BC_ROWS)));
     HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
-  configured[dev] = true;
+  ds->lu_configured.store(true, std::memory_order_release);
+  return 0;
+}
+
+// One launch per block column (several when a cooperative batch does not fit the GPU at once).
+// Returns 1 through `done` when the kernel was used, 0 when the block column is too tall.
+int launch_blockcol(cudaStream_t st, int batch, int n, double* A, int64_t lda, int64_t sA, int j, int jb, LuWorkspace& w,
+                    int* info, bool& done) {
+  done = false;
+  const int rows = n - j;
+  const int G = (rows + BC_ROWS - 1) / BC_ROWS;
+  if (G > 1 && (G > w.bc_Gcap || G > BC_MAX_G)) return 0;
+  BcArgs a;
+  a.A = A; a.lda = lda; a.sA = sA; a.n = n; a.j = j; a.jb = jb; a.G = G;
+  a.rpc = (G == 1) ? rows : std::max(NB, (rows + G - 1) / G);
+  a.ipiv = w.ipiv; a.info = info; a.scratch = w.bc_scratch; a.scratch_stride = w.bc_stride; a.Gcap = w.bc_Gcap;
+  const size_t smem = bc_smem_bytes(a.rpc);
+  if (G == 1) {
+    prof_begin(PROF_PANEL, st, (double)batch * rows * jb);
+    blockcol_kernel<false><<<dim3(1, batch), BC_THREADS, smem, st>>>(a);
+    prof_end(PROF_PANEL, st);
+    HPS_LAUNCH_CHECK("blockcol_kernel<single>");
+    done = true;
+    return 0;
+  }
+  if (G <= 8) {  // one thread-block cluster per matrix: co-scheduled by the hardware
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G, batch);
+    cfg.blockDim = dim3(BC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    prof_begin(PROF_PANEL, st, (double)batch * rows * jb);
+    HPS_CUDA(cudaLaunchKernelEx(&cfg, blockcol_kernel<true>, a));
+    prof_end(PROF_PANEL, st);
+    ++g_launches;
+    done = true;
+    return 0;
+  }
+  // cooperative launch: every CTA of the grid is resident, so the flag polling cannot deadlock
+  int dev = 0, sms = 0, per_sm = 0;
+  HPS_CUDA(cudaGetDevice(&dev));
+  HPS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  HPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blockcol_kernel<true>, BC_THREADS, smem));
+  const int per_launch = (sms * per_sm) / G;
+  if (per_launch < 1) return 0;
+  prof_begin(PROF_PANEL, st, (double)batch * rows * jb);
+  for (int b0 = 0; b0 < batch; b0 += per_launch) {
+    const int nb = std::min(per_launch, batch - b0);
+    BcArgs sub = a;
+    sub.A = A + (int64_t)b0 * sA;
+    sub.ipiv = w.ipiv + (int64_t)b0 * n;
+    sub.info = info + b0;
+    sub.scratch = w.bc_scratch + (size_t)b0 * w.bc_stride;
+    void* args[] = {&sub};
+    HPS_CUDA(cudaLaunchCooperativeKernel((void*)blockcol_kernel<true>, dim3(G, nb), dim3(BC_THREADS), args, smem, st));
+    ++g_launches;
+  }
+  prof_end(PROF_PANEL, st);
+  done = true;
   return 0;
 }
 
@@ -496,38 +858,12 @@ struct Mat {  // batched row-major matrix view
   double* at(int64_t r, int64_t c) const { return p + r * ld + c; }
 };
 
-// internal look-ahead stream + events, created once per device
-struct Aux {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t panel_done[2] = {nullptr, nullptr};
-  cudaEvent_t update_done[2] = {nullptr, nullptr};
-  cudaEvent_t fork = nullptr, join = nullptr;
-};
-int get_aux(Aux*& out) {
-  static Aux aux[64];
-  int dev = 0;
-  HPS_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return fail_arg(1, "device ordinal out of range");
-  Aux& a = aux[dev];
-  if (!a.stream) {
-    int lo = 0, hi = 0;
-    HPS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    HPS_CUDA(cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, hi));
-    for (int i = 0; i < 2; ++i) {
-      HPS_CUDA(cudaEventCreateWithFlags(&a.panel_done[i], cudaEventDisableTiming));
-      HPS_CUDA(cudaEventCreateWithFlags(&a.update_done[i], cudaEventDisableTiming));
-    }
-    HPS_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
-    HPS_CUDA(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
-  }
-  out = &a;
-  return 0;
-}
-
 // Factor the outer block column j (inner IB panels + updates inside the block column) and invert
 // its unit-lower diagonal block into Linv[j/NB].  Touches columns [j, j+jb) only.
 int factor_block_column(cudaStream_t st, int batch, int n, const Mat& A, int j, int jb, LuWorkspace& w, int* info) {
-  for (int jj = j; jj < j + jb; jj += IB) {
+  bool done = false;
+  HPS_TRY(launch_blockcol(st, batch, n, A.p, A.ld, A.stride, j, jb, w, info, done));
+  for (int jj = j; !done && jj < j + jb; jj += IB) {
     const int ib = min(IB, j + jb - jj);
     PanelArgs pa;
     pa.A = A.p; pa.lda = A.ld; pa.sA = A.stride; pa.n = n; pa.jj = jj; pa.ib = ib; pa.G = 1;
@@ -609,7 +945,7 @@ size_t lu_workspace_bytes(int batch, int n) {
   const size_t nblk = (n + NB - 1) / NB;
   return align_up((size_t)batch * n * sizeof(int), 256) + 2 * align_up((size_t)batch * nblk * NB * NB * sizeof(double), 256) +
          align_up((size_t)batch * NB * 16 * sizeof(double), 256) + align_up((size_t)batch * sizeof(PanelScratch), 256) +
-         1024;
+         align_up((size_t)batch * align_up(bc_scratch_bytes(std::max(1, bc_gcap(n))), 256), 256) + 1024;
 }
 
 int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t sA, int n_rhs, const RhsDesc* rhs,
@@ -622,12 +958,13 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
 
   HPS_TRY(configure_lu_kernels());
   Aux* aux = nullptr;
-  HPS_TRY(get_aux(aux));
+  HPS_TRY(aux_for_stream(st, aux));
   cudaStream_t s0 = st, s1 = aux->stream;
   const Mat A{Ap, lda, sA};
   const int nblk = (n + NB - 1) / NB;
 
   HPS_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, s0));
+  if (w.bc_Gcap) HPS_CUDA(cudaMemsetAsync(w.bc_scratch, 0, (size_t)batch * w.bc_stride, s0));  // epoch flags start at 0
   // ---- 1. factorisation with look-ahead --------------------------------------------------
   // s1 owns the block column being factored; s0 applies finished block columns to everything
   // to their right (and the interchanges to everything to their left).
@@ -720,6 +1057,8 @@ int lu_dist_factor_pack(cudaStream_t st, int n, double* A, int64_t lda, int b, v
   const int j = b * NB, jb = min(NB, n - j);
   if (j >= n) return fail_arg(4, "block index out of range");
   const Mat Am{A, lda, 0};
+  // the exchange flags of the block-column kernel must not hold a stale epoch from another use of ws
+  if (w.bc_Gcap) HPS_CUDA(cudaMemsetAsync(w.bc_scratch, 0, w.bc_stride, st));
   HPS_TRY(factor_block_column(st, 1, n, Am, j, jb, w, info));
   const double* Linv = w.Linv + (int64_t)b * NB * NB;
   pack_block_kernel<<<1024, 256, 0, st>>>(n, jb, A, lda, j, w.ipiv, Linv, buf, 0, nullptr, nullptr, nullptr);

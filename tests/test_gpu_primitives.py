@@ -70,10 +70,15 @@ def _lu_solve(A, rhs):
         (33, 2, [40, 1]),  # ragged inner panel + narrow rhs
         (128, 2, [128]),
         (200, 3, [300, 1]),
-        (1000, 3, [600, 1]),  # leaf size: 2-CTA cluster panel
+        (196, 5, [57]),  # largest block column one CTA holds in shared memory
+        (197, 2, [10]),  # smallest 2-CTA cluster (128 + 69 rows)
+        (777, 2, [5]),  # ragged last block column, 4-CTA cluster
+        (1000, 3, [600, 1]),  # leaf size: 6-CTA cluster block column
         (1200, 2, [2400, 1]),  # first merge level size
-        (4800, 1, [96]),  # 8-CTA cluster panel
-        (7000, 1, [64]),  # cooperative (grid-barrier) panel
+        (1700, 2, [16]),  # 9 CTAs per matrix: smallest cooperative launch
+        (2500, 20, [8]),  # cooperative launch split over several batches of matrices
+        (4800, 1, [96]),  # 25 co-resident CTAs
+        (7000, 1, [64]),
     ],
 )
 def test_lu_solve_residual_and_agreement(n, batch, widths):

@@ -2,7 +2,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "../jaxhps_b200/csrc/gemm_kernel.cuh"
+#include "gemm_lab_kernels.cuh"
 using namespace hps::gemmk;
 #define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("CUDA error %s line %d\n",cudaGetErrorString(e),__LINE__);exit(1);}}while(0)
 __global__ void fill(double* p, size_t n, unsigned seed){ size_t i=blockIdx.x*(size_t)blockDim.x+threadIdx.x; size_t st=(size_t)gridDim.x*blockDim.x; for(;i<n;i+=st){ unsigned x=(unsigned)(i*2654435761u)^seed; x^=x>>13; x*=0x5bd1e995; x^=x>>15; p[i]=((x&0xffff)/65536.0)-0.5; } }
@@ -13,7 +13,8 @@ template<class Cfg, int MB> auto pick(){
   else if constexpr (MB == 1) return gemm_kernel_mb<Cfg>;
   else return gemm_kernel<Cfg>;
 }
-template<class Cfg, int MB=0> double run(const char* name, GemmArgs g, int batch, double* C0, size_t csz, double* d_sum){
+template<class Cfg, int MB=0> double run(const char* name, GemmArgs g, int batch, double* C0, size_t csz, double* d_sum, int raster=0){
+  g.raster = raster;
   auto kern = pick<Cfg, MB>();
   static bool conf=false; if(!conf){ CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,(int)Cfg::SMEM_BYTES)); conf=true; }
   dim3 grid((g.N+Cfg::BN-1)/Cfg::BN,(g.M+Cfg::BM-1)/Cfg::BM,batch);
@@ -33,7 +34,7 @@ template<class Cfg, int MB=0> double run(const char* name, GemmArgs g, int batch
 }
 int main(){
   struct Shape{int M,N,K,batch; double beta;};
-  std::vector<Shape> shapes={{8192,8192,8192,1,0.0},{15360,15360,128,1,1.0},{872,872,128,512,1.0},{1000,600,728,512,0.0}};
+  std::vector<Shape> shapes={{8192,8192,8192,1,0.0},{15360,15360,128,1,1.0},{19072,2304,128,1,1.0},{872,872,128,512,1.0},{1000,600,728,512,0.0},{19200,4800,9600,1,1.0}};
   double* d_sum; CK(cudaMalloc(&d_sum,8));
   for(auto s: shapes){
     size_t asz=(size_t)s.M*s.K*s.batch, bsz=(size_t)s.K*s.N*s.batch, csz=(size_t)s.M*s.N*s.batch;
@@ -44,6 +45,13 @@ int main(){
     //                 WM  WN  WMs WNs BK  ST  minCTA
     run<Config<32, 32, 4, 2, 16, 3, 2>, 1>("G  mb  128x64 8w(32x32) bk16 s3 x2cta", g, s.batch, C0, csz, d_sum);
     run<Config<32, 32, 4, 2, 16, 3, 2>, 3>("G  hoist 128x64 8w(32x32) bk16 s3 x2cta [product]", g, s.batch, C0, csz, d_sum);
+    run<Config<32, 32, 4, 2, 16, 3, 2>, 3>("G  hoist raster 8", g, s.batch, C0, csz, d_sum, 8);
+    run<Config<32, 32, 4, 2, 16, 3, 2>, 3>("G  hoist raster 12", g, s.batch, C0, csz, d_sum, 12);
+    run<Config<32, 32, 4, 2, 16, 3, 2>, 3>("G  hoist raster 16", g, s.batch, C0, csz, d_sum, 16);
+    run<Config<64, 32, 2, 4, 16, 3, 1>, 3>("X  hoist 128x128 8w(64x32) bk16 s3 x1cta", g, s.batch, C0, csz, d_sum);
+    run<Config<64, 32, 2, 4, 16, 4, 1>, 3>("X4 hoist 128x128 8w(64x32) bk16 s4 x1cta raster 8", g, s.batch, C0, csz, d_sum, 8);
+    run<Config<64, 32, 2, 2, 16, 4, 2>, 3>("W4 hoist 128x64 4w(64x32) bk16 s4 x2cta raster 12", g, s.batch, C0, csz, d_sum, 12);
+    run<Config<64, 32, 2, 2, 16, 3, 3>, 3>("W3 hoist 128x64 4w(64x32) bk16 s3 x3cta", g, s.batch, C0, csz, d_sum);
     run<Config<32, 32, 4, 2, 16, 4, 2>, 3>("G4 hoist 128x64 8w bk16 s4 x2cta", g, s.batch, C0, csz, d_sum);
     run<Config<32, 32, 4, 2, 32, 2, 2>, 3>("G2 hoist 128x64 8w bk32 s2 x2cta", g, s.batch, C0, csz, d_sum);
     run<Config<32, 32, 4, 4, 16, 3, 1>, 3>("A1 hoist 128x128 16w bk16 s3", g, s.batch, C0, csz, d_sum);
