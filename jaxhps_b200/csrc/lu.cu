@@ -247,7 +247,7 @@ __host__ __device__ inline size_t bc_scratch_bytes(int Gcap) {
   return (size_t)2 * Gcap * sizeof(BcCand) + (size_t)2 * NB * sizeof(double) + (size_t)IB * BC_UW * sizeof(double) + 256;
 }
 inline size_t bc_smem_bytes(int rpc) {
-  return sizeof(double) * ((size_t)rpc * BC_LD + (size_t)IB * BC_UW + NB + 16) + sizeof(int) * 16;
+  return sizeof(double) * ((((size_t)rpc * BC_LD + 1) & ~(size_t)1) + (size_t)IB * BC_UW + NB + 16) + sizeof(int) * 16;
 }
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol_kernel(BcArgs a) {
   int* ipiv = a.ipiv + (int64_t)mat * a.n + a.j;
 
   double* tile = sm;                                   // [rpc][LD]
-  double* U = tile + (size_t)a.rpc * LD;               // [IB][BC_UW]
+  double* U = tile + (((size_t)a.rpc * LD + 1) & ~(size_t)1);  // [IB][BC_UW], 16-byte aligned for the double2 loads
   double* prow = U + IB * BC_UW;                       // [NB]
   double* red_val = prow + NB;                         // [16]
   int* red_idx = reinterpret_cast<int*>(red_val + 16); // [16]
