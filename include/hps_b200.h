@@ -147,6 +147,38 @@ int hps_lu_dist_update(void* stream, int n, double* A, int64_t lda, int b,
 int hps_lu_dist_solve(void* stream, int n, double* A, int64_t lda, int n_rhs, double* const* rhs,
                       const int64_t* ld_rhs, const int* ncols, void* ws, size_t ws_bytes);
 
+/* ---- Library-owned communicator (SURVEY §8(b) hps_comm_*) and the distributed root factorisation on it.
+ * The reference is single-device (its only split is the serial subtree recomputation,
+ * _subtree_recomp.py:310-390); this is the exchange step of the multi-GPU root merge.
+ * One process per GPU.  Each rank owns one SYMMETRIC device segment (cudaMalloc) that every peer of the box
+ * maps through CUDA IPC, so kernels store straight into the peers' HBM over NVLink / NVSwitch:
+ *   hps_comm_create(rank, world <= 8)          handle bound to the current device
+ *   hps_comm_reserve(comm, bytes, &changed)    grow the local segment; changed = 1 -> every rank must
+ *                                              hps_comm_export (64-byte IPC handle), all-gather the handles
+ *                                              (any transport; jaxhps_b200/_dist.py uses torch.distributed)
+ *                                              and hps_comm_attach(comm, handles[world][64]); call
+ *                                              hps_comm_detach on every rank before growing a mapped segment
+ * hps_lu_dist_run: A (n x n, row-major, lda = n) assembled by every rank at hps_lu_dist_matrix_ptr (inside its
+ * segment, hps_lu_dist_segment_bytes(n) bytes).  Block column b (128 wide) is factored by rank b % world and
+ * stored — with its pivots and the inverse of its unit-lower diagonal block — into EVERY peer's segment by one
+ * fused copy+signal kernel (release flag per block column, acquire-wait kernel on the consumer's stream); every
+ * rank applies it to the block columns it owns and to its own right-hand sides rhs[k] (n x ncols[k], leading
+ * dimension ld_rhs[k], up to 4), which ride along as extra trailing columns, so the forward substitution ends
+ * with the factorisation; then U's diagonal inverses and the recursive backward substitution.  Everything is
+ * enqueued on `stream` (+ one internal look-ahead stream); no host synchronisation.  info[0] (LAPACK
+ * convention) is set by the owner of the offending block column only.  Workspace: hps_lu_solve_workspace(1, n). */
+int hps_memcpy_d2d(void* stream, void* dst, const void* src, size_t bytes); /* stream-ordered copy into / out of a segment */
+int hps_comm_create(int rank, int world, void** comm);
+int hps_comm_destroy(void* comm);
+int hps_comm_reserve(void* comm, size_t bytes, int* changed);
+int hps_comm_detach(void* comm);
+int hps_comm_export(void* comm, void* handle64);
+int hps_comm_attach(void* comm, const void* handles);
+int hps_lu_dist_segment_bytes(int n, size_t* bytes);
+int hps_lu_dist_matrix_ptr(void* comm, int n, double** A);
+int hps_lu_dist_run(void* comm, void* stream, int n, int n_rhs, double* const* rhs, const int64_t* ld_rhs,
+                    const int* ncols, void* ws, size_t ws_bytes, int* info);
+
 /* 2D quad merge, DtN (reference: merge/_uniform_2D_DtN.py:206-348).
  * T_in [4*n_merges][4m][4m] (children SW,SE,NE,NW; sides S,E,N,W), S [n][4m][8m],
  * T_out [n][8m][8m]. */

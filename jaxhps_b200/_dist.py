@@ -99,6 +99,100 @@ def _operator_template(domain) -> PDEProblem:
     return _TEMPLATES[key]
 
 
+class P2PComm:
+    """The library's symmetric-segment communicator (``hps_comm_*``): one per (process, device).  The 64-byte CUDA
+    IPC handles of the ranks' segments are exchanged once per (re)allocation with ``torch.distributed``; after
+    that every exchange of the distributed root factorisation is a kernel storing into the peers' HBM."""
+
+    _instances = {}
+
+    def __init__(self, _lib, dev, rank: int, world: int, group=None):
+        import ctypes
+
+        self._lib, self.dev, self.rank, self.world, self.group = _lib, dev, rank, world, group
+        self.lib = _lib.load()
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.hps_comm_create(rank, world, ctypes.byref(self.handle)), "hps_comm_create")
+
+    @classmethod
+    def get(cls, _lib, dev, rank: int, world: int, group=None):
+        key = (str(dev), rank, world, id(group))
+        if key not in cls._instances:
+            cls._instances[key] = cls(_lib, dev, rank, world, group)
+        return cls._instances[key]
+
+    def ensure(self, nbytes: int) -> None:
+        """Collective: make every rank's segment at least ``nbytes`` large and mapped by all peers."""
+        import ctypes
+
+        lib, _lib = self.lib, self._lib
+        with torch.cuda.device(self.dev):
+            changed = ctypes.c_int(0)
+            rc = lib.hps_comm_reserve(self.handle, nbytes, ctypes.byref(changed))
+            if rc != 0:  # a mapped segment has to grow: unmap everywhere first
+                _lib.check(lib.hps_comm_detach(self.handle), "hps_comm_detach")
+                if self.world > 1:
+                    torch.cuda.synchronize(self.dev)
+                    dist.barrier(group=self.group)
+                _lib.check(lib.hps_comm_reserve(self.handle, nbytes, ctypes.byref(changed)), "hps_comm_reserve")
+            if not changed.value:
+                return
+            mine = (ctypes.c_ubyte * 64)()
+            _lib.check(lib.hps_comm_export(self.handle, mine), "hps_comm_export")
+            if self.world > 1:
+                h = torch.tensor(list(mine), dtype=torch.uint8, device=self.dev)
+                allh = torch.empty(self.world * 64, dtype=torch.uint8, device=self.dev)
+                dist.all_gather_into_tensor(allh, h, group=self.group)
+                raw = bytes(allh.cpu().tolist())
+            else:
+                raw = bytes(mine)
+            buf = (ctypes.c_ubyte * len(raw)).from_buffer_copy(raw)
+            _lib.check(lib.hps_comm_attach(self.handle, buf), "hps_comm_attach")
+            if self.world > 1:
+                dist.barrier(group=self.group)
+
+    def matrix_ptr(self, n: int) -> int:
+        import ctypes
+
+        out = ctypes.c_void_p()
+        self._lib.check(self.lib.hps_lu_dist_matrix_ptr(self.handle, n, ctypes.byref(out)), "hps_lu_dist_matrix_ptr")
+        return out.value
+
+    def lu_segment_bytes(self, n: int) -> int:
+        import ctypes
+
+        need = ctypes.c_size_t()
+        self._lib.check(self.lib.hps_lu_dist_segment_bytes(n, ctypes.byref(need)), "hps_lu_dist_segment_bytes")
+        return need.value
+
+
+#: the distributed factorisation runs from C over the library's P2P communicator (0: the step-wise
+#: NCCL-broadcast driver below, kept as the fallback when CUDA IPC is unavailable)
+USE_P2P = os.environ.get("HPS_DIST_P2P", "1") != "0"
+
+
+def p2p_lu_solve(_lib, dev, comm: "P2PComm", n: int, rhs, group=None) -> None:
+    """``rhs[k] := D^-1 rhs[k]`` with D already assembled at ``comm.matrix_ptr(n)`` on every rank
+    (``hps_lu_dist_run``: one C call enqueues the whole factorisation, the P2P exchanges and the solves)."""
+    import ctypes
+
+    lib = _lib.load()
+    need = ctypes.c_size_t()
+    _lib.check(lib.hps_lu_solve_workspace(1, n, ctypes.byref(need)), "workspace query")
+    ws = _lib.workspace(need.value, dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    k = len(rhs)
+    ptrs = (ctypes.c_void_p * k)(*[r.data_ptr() for r in rhs])
+    lds = (ctypes.c_int64 * k)(*[r.shape[1] for r in rhs])
+    ncs = (ctypes.c_int * k)(*[r.shape[1] for r in rhs])
+    _lib.check(lib.hps_lu_dist_run(comm.handle, _lib.stream_ptr(), n, k, ptrs, lds, ncs, ws.data_ptr(), ws.numel(),
+                                   info.data_ptr()), "hps_lu_dist_run")
+    if comm.world > 1:
+        dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
+    _lib.check_info(info, "distributed factorisation")
+
+
 def distributed_lu_solve(_lib, dev, D, rhs, rank: int, world: int, group=None) -> None:
     """In-place ``rhs[k] := D^-1 rhs[k]`` with the factorisation of ``D`` (n x n, replicated on every rank)
     distributed over the ranks: block column b (128 wide) is factored by rank ``b % world``, the packed column is
@@ -110,6 +204,11 @@ def distributed_lu_solve(_lib, dev, D, rhs, rank: int, world: int, group=None) -
 
     lib = _lib.load()
     n = D.shape[0]
+    if USE_P2P:
+        comm = P2PComm.get(_lib, dev, rank, world, group)
+        comm.ensure(comm.lu_segment_bytes(n))
+        _copy_into_segment(comm.matrix_ptr(n), D)
+        return p2p_lu_solve(_lib, dev, comm, n, rhs, group)
     NB = 128
     nblk = (n + NB - 1) // NB
     need = ctypes.c_size_t()
@@ -177,6 +276,15 @@ def distributed_lu_solve(_lib, dev, D, rhs, rank: int, world: int, group=None) -
     ncs = (ctypes.c_int * k)(*[r.shape[1] for r in rhs])
     _lib.check(lib.hps_lu_dist_solve(main.cuda_stream, n, D.data_ptr(), n, k, ptrs, lds, ncs, ws.data_ptr(), ws.numel()),
                "hps_lu_dist_solve")
+
+
+def _copy_into_segment(dst_ptr: int, D: torch.Tensor) -> None:
+    """Device-to-device copy of a contiguous tensor to a raw device address, on the current stream."""
+    from . import _lib
+
+    D = D.contiguous()
+    _lib.check(_lib.load().hps_memcpy_d2d(_lib.stream_ptr(), dst_ptr, D.data_ptr(), D.numel() * D.element_size()),
+               "hps_memcpy_d2d")
 
 
 class CudaOps:
@@ -258,9 +366,20 @@ class CudaOps:
         m = n3 // 3
         n_src = hblk_all.shape[-1]
         n = 12 * m
-        D = self.empty((n, n))
         S_r = self.empty((n, n3 * n_local))
         g = self.empty((n, n_src))
+        if USE_P2P:
+            # D is assembled directly inside this rank's symmetric segment; the owners of the block columns
+            # later store the factored columns into the same place on every peer
+            comm = P2PComm.get(_lib, self.dev, rank, world, group)
+            comm.ensure(comm.lu_segment_bytes(n))
+            rc = lib.hps_root_assemble_oct(_lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),
+                                           hblk_all.data_ptr(), Cblk_loc.data_ptr(), comm.matrix_ptr(n), S_r.data_ptr(),
+                                           g.data_ptr())
+            _lib.check(rc, "hps_root_assemble_oct")
+            p2p_lu_solve(_lib, self.dev, comm, n, [S_r, g], group)
+            return S_r, g
+        D = self.empty((n, n))
         rc = lib.hps_root_assemble_oct(_lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),
                                        hblk_all.data_ptr(), Cblk_loc.data_ptr(), D.data_ptr(), S_r.data_ptr(), g.data_ptr())
         _lib.check(rc, "hps_root_assemble_oct")

@@ -205,7 +205,15 @@ class CudaAdaptiveOps:
         return S, g
 
     def matvec(self, S, x):
-        return S @ x
+        """``S @ x`` with the library's bandwidth kernel (narrow x) / DMMA GEMM — no vendor BLAS on the path."""
+        S, x = S.contiguous(), x.contiguous()
+        M, K = S.shape
+        N = x.shape[1]
+        out = self.empty((M, N))
+        rc = self.lib.hps_dgemm_strided_batched(self._lib.stream_ptr(), M, N, K, 1.0, S.data_ptr(), K, 0, x.data_ptr(), N, 0,
+                                                0.0, out.data_ptr(), N, 0, 1)
+        self._lib.check(rc, "hps_dgemm_strided_batched (root matvec)")
+        return out
 
     def down_root(self, root_plan, g_ext, g_int, L_refine):
         """Boundary vectors of ALL children of the root from the reduced interface data."""

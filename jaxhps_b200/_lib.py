@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from typing import Optional
 
 import numpy as np
@@ -46,6 +47,16 @@ _SIGNATURES = {
     "hps_lu_dist_unpack": (_i, [_p, _i, _p, _l, _i, _p, _sz, _p]),
     "hps_lu_dist_update": (_i, [_p, _i, _p, _l, _i, _i, _i, _i, _i, _p, _sz]),
     "hps_lu_dist_solve": (_i, [_p, _i, _p, _l, _i, ctypes.POINTER(_p), ctypes.POINTER(_l), ctypes.POINTER(_i), _p, _sz]),
+    "hps_memcpy_d2d": (_i, [_p, _p, _p, _sz]),
+    "hps_comm_create": (_i, [_i, _i, ctypes.POINTER(_p)]),
+    "hps_comm_destroy": (_i, [_p]),
+    "hps_comm_reserve": (_i, [_p, _sz, ctypes.POINTER(_i)]),
+    "hps_comm_detach": (_i, [_p]),
+    "hps_comm_export": (_i, [_p, _p]),
+    "hps_comm_attach": (_i, [_p, _p]),
+    "hps_lu_dist_segment_bytes": (_i, [_i, ctypes.POINTER(_sz)]),
+    "hps_lu_dist_matrix_ptr": (_i, [_p, _i, ctypes.POINTER(_p)]),
+    "hps_lu_dist_run": (_i, [_p, _p, _i, _i, ctypes.POINTER(_p), ctypes.POINTER(_l), ctypes.POINTER(_i), _p, _sz, _p]),
     "hps_down_oct_scatter": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "hps_merge_quad_dtn_level_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),
     "hps_merge_quad_dtn_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
@@ -139,12 +150,17 @@ def is_host(host_device) -> bool:
 
 
 def to_device(x, dev: torch.device, dtype=torch.float64) -> torch.Tensor:
-    """NumPy / torch (any device) -> contiguous tensor on ``dev``; host arrays go through pinned memory."""
+    """NumPy / torch (any device) -> contiguous tensor on ``dev``; host arrays go through pinned memory.
+    A complex array handed to a real-valued (DtN) stage is an error, not a silent drop of the imaginary part
+    (the reference would promote to complex; the DtN kernels are FP64-only — use the ItI path for complex fields)."""
     if isinstance(x, torch.Tensor):
         t = x
     else:
         t = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
     if t.dtype != dtype:
+        if t.is_complex() and not dtype.is_complex:
+            raise ValueError("complex-valued input reached a real-valued (DtN) stage; complex coefficient fields, "
+                             "sources and boundary data are supported on the ItI path only")
         t = t.to(dtype)
     if t.device != dev:
         if t.device.type == "cpu" and t.numel() > 1 << 16:
@@ -165,23 +181,43 @@ def to_result(t: torch.Tensor, host_device):
     return t if t.device == dev else t.to(dev)
 
 
+#: most matrices / merges / nodes one C-ABI call accepts (CUDA grid-dimension limit)
+MAX_BATCH = 65535
+
+
 class Workspace:
-    """Grow-only device scratch buffer handed to the library (which never allocates)."""
+    """Grow-only device scratch buffers handed to the library (which never allocates): one per
+    (device, CUDA stream), so that calls issued on different streams or devices — from one host thread or
+    several — never share scratch memory."""
 
     def __init__(self):
-        self._buf: Optional[torch.Tensor] = None
+        self._bufs = {}
+        self._lock = threading.Lock()
 
     def get(self, nbytes: int, dev: torch.device) -> torch.Tensor:
-        if self._buf is None or self._buf.numel() < nbytes or self._buf.device != dev:
-            self._buf = None
-            self._buf = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
-        return self._buf
+        dev = torch.device(dev)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+        with self._lock:
+            buf = self._bufs.get(key)
+            if buf is None or buf.numel() < nbytes:
+                self._bufs.pop(key, None)
+                del buf
+                buf = torch.empty(int(nbytes), dtype=torch.uint8, device=torch.device("cuda", idx))
+                self._bufs[key] = buf
+            return buf
 
     def release(self):
-        self._buf = None
+        with self._lock:
+            self._bufs.clear()
 
 
 WORKSPACE = Workspace()
+
+
+def workspace(nbytes: int, dev: torch.device) -> torch.Tensor:
+    """Scratch buffer of at least ``nbytes`` for the current stream of ``dev``."""
+    return WORKSPACE.get(nbytes, dev)
 
 
 def check_info(info: torch.Tensor, what: str) -> None:

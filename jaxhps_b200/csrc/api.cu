@@ -217,6 +217,29 @@ int hps_lu_dist_solve(void* stream, int n, double* A, int64_t lda, int n_rhs, do
   for (int k = 0; k < n_rhs; ++k) d[k] = RhsDesc{rhs[k], ld_rhs[k], 0, ncols[k]};
   return lu_dist_solve(static_cast<cudaStream_t>(stream), n, A, lda, n_rhs, d, ws, ws_bytes);
 }
+int hps_memcpy_d2d(void* stream, void* dst, const void* src, size_t bytes) {
+  HPS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int hps_comm_create(int rank, int world, void** comm) { return comm_create(rank, world, reinterpret_cast<Comm**>(comm)); }
+int hps_comm_destroy(void* comm) { return comm_destroy(static_cast<Comm*>(comm)); }
+int hps_comm_reserve(void* comm, size_t bytes, int* changed) { return comm_reserve(static_cast<Comm*>(comm), bytes, changed); }
+int hps_comm_detach(void* comm) { return comm_detach(static_cast<Comm*>(comm)); }
+int hps_comm_export(void* comm, void* handle64) { return comm_export(static_cast<Comm*>(comm), handle64); }
+int hps_comm_attach(void* comm, const void* handles) { return comm_attach(static_cast<Comm*>(comm), handles); }
+int hps_lu_dist_segment_bytes(int n, size_t* bytes) {
+  if (!bytes) return fail_arg(2, "null output pointer");
+  *bytes = lu_dist_segment_bytes(n);
+  return 0;
+}
+int hps_lu_dist_matrix_ptr(void* comm, int n, double** A) { return lu_dist_matrix_ptr(static_cast<Comm*>(comm), n, A); }
+int hps_lu_dist_run(void* comm, void* stream, int n, int n_rhs, double* const* rhs, const int64_t* ld_rhs, const int* ncols,
+                    void* ws, size_t ws_bytes, int* info) {
+  if (n_rhs < 0 || n_rhs > 4) return fail_arg(4, "n_rhs must be in [0, 4]");
+  RhsDesc d[4];
+  for (int k = 0; k < n_rhs; ++k) d[k] = RhsDesc{rhs[k], ld_rhs[k], 0, ncols[k]};
+  return lu_dist_run(static_cast<Comm*>(comm), static_cast<cudaStream_t>(stream), n, n_rhs, d, ws, ws_bytes, info);
+}
 int hps_down_oct_scatter(void* stream, int n_nodes, int m, int n_src, const double* g_ext, const double* g_int,
                          double* g_children) {
   return down_oct_scatter(static_cast<cudaStream_t>(stream), n_nodes, m, n_src, g_ext, g_int, g_children);

@@ -117,6 +117,18 @@ int lu_dist_update(cudaStream_t st, int n, double* A, int64_t lda, int b, int fi
 int lu_dist_solve(cudaStream_t st, int n, double* A, int64_t lda, int n_rhs, const RhsDesc* rhs, void* ws,
                   size_t ws_bytes);
 
+// library-owned P2P communicator + the distributed factorisation that runs on it (lu.cu)
+struct Comm;
+int comm_create(int rank, int world, Comm** out);
+int comm_destroy(Comm* c);
+int comm_reserve(Comm* c, size_t bytes, int* changed);
+int comm_detach(Comm* c);
+int comm_export(Comm* c, void* handle64);
+int comm_attach(Comm* c, const void* handles);
+size_t lu_dist_segment_bytes(int n);
+int lu_dist_matrix_ptr(Comm* c, int n, double** A);
+int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, void* ws, size_t ws_bytes, int* info);
+
 // ---- stages (leaf.cu / merge.cu) --------------------------------------------------------
 size_t local_solve_workspace_bytes(int dim, int n_leaves, int p, int q);
 int local_solve_dtn(cudaStream_t st, int dim, int n_leaves, int p, int q, int n_src, const uint8_t* which,

@@ -31,6 +31,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -226,7 +227,7 @@ constexpr int BC_THREADS = 512;
 constexpr int BC_UW = NB - IB;   // widest U12 block
 constexpr int BC_MAX_G = 148;
 
-struct BcCand {        // content first, header last: the flag is release-stored after everything else
+struct alignas(16) BcCand {  // content first; the 16-byte header {val, row, flag} is stored last, as ONE vector store
   double content[NB];
   double val;          // |a|, negative when the CTA has no eligible row
   int row;             // block-column-relative row index
@@ -257,6 +258,21 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;\n" ::: "memory"); }
+// The candidate header travels as one aligned 16-byte access (one L2 sector transaction), so a reader that sees
+// the new epoch in .y's upper half also sees the value and row stored with it.
+__device__ __forceinline__ void st_header(BcCand* c, double val, int row, unsigned flag) {
+  const unsigned long long lo = (unsigned long long)__double_as_longlong(val);
+  const unsigned long long hi = (unsigned long long)(unsigned)row | ((unsigned long long)flag << 32);
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};\n" ::"l"(&c->val), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ void ld_header(const BcCand* c, double& val, int& row, unsigned& flag) {
+  unsigned long long lo, hi;
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];\n" : "=l"(lo), "=l"(hi) : "l"(&c->val) : "memory");
+  val = __longlong_as_double((long long)lo);
+  row = (int)(unsigned)(hi & 0xffffffffull);
+  flag = (unsigned)(hi >> 32);
 }
 
 // SHARED = false: one CTA per matrix, everything stays in shared memory.
@@ -340,21 +356,30 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol_kernel(BcArgs a) {
       }
       __syncthreads();
       if (tid == 0) {
-        mine->val = best;
-        mine->row = (best >= 0.0) ? r0 + bidx : -1;
-        __threadfence();
-        st_release_u32(&mine->flag, epoch);
+        fence_acq_rel_gpu();  // the CTA's content / diag stores (ordered before by the barrier) become visible first
+        st_header(mine, best, (best >= 0.0) ? r0 + bidx : -1, epoch);
       }
       if (warp == 0) {
-        // every CTA elects the same winner: largest value, lowest row on ties
+        // every CTA elects the same winner: largest value, lowest row on ties.  All of a lane's headers are
+        // requested before the first one is examined; lanes spin only on the ones still carrying an old epoch.
         double wv = -1.0; int wg = 0, wr = 0x7fffffff;
-        for (int k = lane; k < G; k += 32) {
-          const BcCand* ck = cands + (size_t)(c & 1) * a.Gcap + k;
-          while (ld_acquire_u32(&ck->flag) != epoch) { }
-          const double v = __ldcg(&ck->val);
-          const int r = __ldcg(&ck->row);
-          if (v >= 0.0 && (v > wv || (v == wv && r < wr))) { wv = v; wg = k; wr = r; }
+        constexpr int KMAX = (BC_MAX_G + 31) / 32;
+        double hv[KMAX]; int hr[KMAX]; unsigned hf[KMAX];
+#pragma unroll
+        for (int i = 0; i < KMAX; ++i) {
+          const int k = lane + 32 * i;
+          hf[i] = epoch; hv[i] = -1.0; hr[i] = -1;
+          if (k < G) ld_header(cands + (size_t)(c & 1) * a.Gcap + k, hv[i], hr[i], hf[i]);
         }
+#pragma unroll
+        for (int i = 0; i < KMAX; ++i) {
+          const int k = lane + 32 * i;
+          if (k < G) {
+            while (hf[i] != epoch) ld_header(cands + (size_t)(c & 1) * a.Gcap + k, hv[i], hr[i], hf[i]);
+            if (hv[i] >= 0.0 && (hv[i] > wv || (hv[i] == wv && hr[i] < wr))) { wv = hv[i]; wg = k; wr = hr[i]; }
+          }
+        }
+        fence_acq_rel_gpu();  // acquire side: the winners' content is read after this (and after the barrier below)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const double ov = __shfl_xor_sync(0xffffffffu, wv, o);
@@ -386,7 +411,12 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol_kernel(BcArgs a) {
           double* row = tile + r * LD;
           const double l = row[c] / piv;
           row[c] = l;
-          for (int cc = c + 1; cc < pe; ++cc) row[cc] = fma(-l, prow[cc], row[cc]);
+          double x[IB];  // loads first, stores last: the compiler cannot prove prow and row distinct
+#pragma unroll
+          for (int t = 0; t < IB; ++t) x[t] = (c0 + t > c && c0 + t < pe) ? fma(-l, prow[c0 + t], row[c0 + t]) : 0.0;
+#pragma unroll
+          for (int t = 0; t < IB; ++t)
+            if (c0 + t > c && c0 + t < pe) row[c0 + t] = x[t];
         }
       }
     }
@@ -415,10 +445,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol_kernel(BcArgs a) {
           }
         }
         __syncthreads();
-        if (SHARED && tid == 0) {
-          __threadfence();
-          st_release_u32(u12_flag, (unsigned)(a.j + pe));
-        }
+        if (SHARED && tid == 0) st_release_u32(u12_flag, (unsigned)(a.j + pe));  // release: fence + store
       } else {
         if (tid == 0) {
           while (ld_acquire_u32(u12_flag) != (unsigned)(a.j + pe)) { }
@@ -781,6 +808,21 @@ int launch_blockcol(cudaStream_t st, int batch, int n, double* A, int64_t lda, i
   const int rows = n - j;
   const int G = (rows + BC_ROWS - 1) / BC_ROWS;
   if (G > 1 && (G > w.bc_Gcap || G > BC_MAX_G)) return 0;
+  if (G > 1) {
+    // Several CTAs per matrix pay an exchange through L2 per column: worth it when the factorisation is
+    // latency-bound (one wave of CTAs: big single matrices), not when many matrices queue for the SMs —
+    // those go through the narrower legacy panels, which need a quarter of the CTAs per matrix.
+    DeviceState* ds = nullptr;
+    HPS_TRY(device_state(ds));
+    int sms = ds->sm_count.load(std::memory_order_acquire);
+    if (sms == 0) {
+      int dev = 0;
+      HPS_CUDA(cudaGetDevice(&dev));
+      HPS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      ds->sm_count.store(sms, std::memory_order_release);
+    }
+    if ((long long)batch * G > sms) return 0;
+  }
   BcArgs a;
   a.A = A; a.lda = lda; a.sA = sA; a.n = n; a.j = j; a.jb = jb; a.G = G;
   a.rpc = (G == 1) ? rows : std::max(NB, (rows + G - 1) / G);
@@ -1130,6 +1172,340 @@ int lu_dist_solve(cudaStream_t st, int n, double* A, int64_t lda, int n_rhs, con
     HPS_TRY(trsm_lower(st, 1, n, Am, w, rhs[k], 0, n));
     HPS_TRY(trsm_upper(st, 1, n, Am, w, rhs[k], 0, n));
   }
+  return 0;
+}
+
+
+// =====================================================================================
+// Library-owned communicator: one SYMMETRIC device segment per rank (cudaMalloc + CUDA IPC), mapped into
+// every peer of the box, so that kernels store straight into the peers' HBM over NVLink / NVSwitch.
+// The distributed root factorisation below uses it for a fused "copy the factored block column to
+// every peer + signal": no pack buffer, no NCCL broadcast, no unpack, and the whole block-column loop
+// is issued from C.
+//
+// Segment layout (identical on every rank):
+//   [0, 4 KB)        ready[8]   barrier words, 128 bytes apart (written by the peers)
+//   [4 KB, 64 KB)    blk_flag[] one epoch word per block column (written by the column's owner)
+//   [64 KB, ...)     payload: ipiv[n] | Linv[nblk][NB][NB] | A[n][n]   (distributed LU)
+// Epochs grow by one per collective operation, so no flag is ever reset.
+// =====================================================================================
+constexpr size_t COMM_READY_OFF = 0, COMM_FLAG_OFF = 4096, COMM_PAYLOAD_OFF = 65536;
+constexpr int COMM_MAX_WORLD = 8;
+constexpr int COMM_MAX_BLOCKS = (int)((COMM_PAYLOAD_OFF - COMM_FLAG_OFF) / sizeof(unsigned));
+
+struct CommPtrs { char* peer[COMM_MAX_WORLD]; };
+
+struct Comm {
+  int rank = 0, world = 1, device = 0;
+  size_t bytes = 0;          // size of the local segment
+  char* local = nullptr;
+  CommPtrs ptrs{};           // ptrs.peer[rank] == local; the others are IPC mappings (null until attached)
+  bool attached = false;
+  unsigned epoch = 0;
+  unsigned* done = nullptr;  // completion counter of the copy kernel (local, not shared)
+};
+
+namespace {
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// Every rank tells every peer "I have reached epoch e" and waits until all peers said so.  <<<1, 32>>>
+__global__ void comm_barrier_kernel(CommPtrs p, int rank, int world, unsigned epoch) {
+  const int t = threadIdx.x;
+  if (t < world) {
+    unsigned* remote = reinterpret_cast<unsigned*>(p.peer[t] + COMM_READY_OFF) + rank * 32;
+    st_release_sys(remote, epoch);
+    const unsigned* mine = reinterpret_cast<const unsigned*>(p.peer[rank] + COMM_READY_OFF) + t * 32;
+    while ((int)(ld_acquire_sys(mine) - epoch) < 0) { }
+  }
+}
+
+// <<<1, 1>>>: stream-ordered wait until block column b of this epoch has arrived in the local segment
+__global__ void comm_wait_block_kernel(const unsigned* flag, unsigned epoch) {
+  while ((int)(ld_acquire_sys(flag) - epoch) < 0) { }
+}
+
+// Fused copy + signal: the owner stores its factored block column (all n rows: U above, L below), the
+// pivots and the inverted unit-lower diagonal block into every peer's segment, then releases flag b there.
+// Each element is read once and written world-1 times; the last CTA to finish raises the flags.
+__global__ void __launch_bounds__(256) comm_bcast_blockcol_kernel(CommPtrs p, int rank, int world, int n, int j, int jb,
+                                                                  size_t ipiv_off, size_t linv_off, size_t A_off, int b,
+                                                                  unsigned epoch, unsigned* done) {
+  const char* src = p.peer[rank];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = ((n | j | jb) & 1) == 0;
+  if (vec) {
+    const int h = jb >> 1;
+    const int64_t total = (int64_t)n * h;
+    for (int64_t e = t0; e < total; e += stride) {
+      const int64_t r = e / h, c = e - r * h;
+      const size_t off = A_off + ((size_t)r * n + j) * sizeof(double) + (size_t)c * sizeof(double2);
+      const double2 v = *reinterpret_cast<const double2*>(src + off);
+      for (int q = 0; q < world; ++q)
+        if (q != rank) *reinterpret_cast<double2*>(p.peer[q] + off) = v;
+    }
+  } else {
+    const int64_t total = (int64_t)n * jb;
+    for (int64_t e = t0; e < total; e += stride) {
+      const int64_t r = e / jb, c = e - r * jb;
+      const size_t off = A_off + ((size_t)r * n + j + c) * sizeof(double);
+      const double v = *reinterpret_cast<const double*>(src + off);
+      for (int q = 0; q < world; ++q)
+        if (q != rank) *reinterpret_cast<double*>(p.peer[q] + off) = v;
+    }
+  }
+  for (int64_t e = t0; e < jb; e += stride) {
+    const size_t off = ipiv_off + (size_t)(j + e) * sizeof(int);
+    const int v = *reinterpret_cast<const int*>(src + off);
+    for (int q = 0; q < world; ++q)
+      if (q != rank) *reinterpret_cast<int*>(p.peer[q] + off) = v;
+  }
+  for (int64_t e = t0; e < (int64_t)NB * NB / 2; e += stride) {
+    const size_t off = linv_off + (size_t)e * sizeof(double2);
+    const double2 v = *reinterpret_cast<const double2*>(src + off);
+    for (int q = 0; q < world; ++q)
+      if (q != rank) *reinterpret_cast<double2*>(p.peer[q] + off) = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {
+      *done = 0;  // launches of this kernel are stream-ordered
+      __threadfence_system();
+      for (int q = 0; q < world; ++q)
+        if (q != rank) st_release_sys(reinterpret_cast<unsigned*>(p.peer[q] + COMM_FLAG_OFF) + b, epoch);
+    }
+  }
+}
+
+struct DistLayout {
+  size_t ipiv_off, linv_off, A_off, bytes;
+};
+DistLayout dist_layout(int n) {
+  const size_t nblk = (n + NB - 1) / NB;
+  DistLayout L;
+  L.ipiv_off = COMM_PAYLOAD_OFF;
+  L.linv_off = L.ipiv_off + align_up((size_t)n * sizeof(int), 256);
+  L.A_off = L.linv_off + align_up(nblk * NB * NB * sizeof(double), 256);
+  L.bytes = L.A_off + align_up((size_t)n * n * sizeof(double), 256);
+  return L;
+}
+
+// block column b applied to `batch` column groups of width nc starting at X (leading dimension ld, groups
+// sX apart): interchanges, U12 = L11^-1 X[j:j+jb], X[j+jb:] -= L21 U12.  Used for the owned block columns
+// of A and, identically, for the right-hand sides carried along as extra columns.
+int dist_apply(cudaStream_t st, int n, const Mat& Am, int j, int jb, const LuWorkspace& w, int b, double* X, int64_t ld,
+               int64_t sX, int nc, int batch) {
+  if (nc <= 0 || batch <= 0) return 0;
+  const double* Linv = w.Linv + (int64_t)b * NB * NB;
+  const int below = n - (j + jb);
+  prof_begin(PROF_LASWP, st, (double)batch * nc * jb);
+  laswp_kernel<<<dim3((nc + 255) / 256, batch), 256, 0, st>>>(X, ld, sX, 0, nc, w.ipiv, 0, j, j + jb);
+  prof_end(PROF_LASWP, st);
+  HPS_LAUNCH_CHECK("laswp_kernel");
+  HPS_TRY(tri_mult(st, batch, jb, Linv, 0, X + (int64_t)j * ld, ld, sX, nc, w.tmp));
+  if (below > 0)
+    HPS_TRY(dgemm(st, below, nc, jb, -1.0, Am.at(j + jb, j), Am.ld, 0, X + (int64_t)j * ld, ld, sX, 1.0,
+                  X + (int64_t)(j + jb) * ld, ld, sX, batch));
+  return 0;
+}
+
+}  // namespace
+
+int comm_create(int rank, int world, Comm** out) {
+  if (!out) return fail_arg(3, "null output pointer");
+  if (world < 1 || world > COMM_MAX_WORLD || rank < 0 || rank >= world) return fail_arg(1, "rank / world out of range (world <= 8)");
+  Comm* c = new Comm();
+  c->rank = rank; c->world = world;
+  HPS_CUDA(cudaGetDevice(&c->device));
+  HPS_CUDA(cudaMalloc(&c->done, 256));
+  HPS_CUDA(cudaMemset(c->done, 0, 256));
+  *out = c;
+  return 0;
+}
+
+int comm_detach(Comm* c) {
+  if (!c) return fail_arg(1, "null communicator");
+  for (int q = 0; q < c->world; ++q) {
+    if (q != c->rank && c->ptrs.peer[q]) HPS_CUDA(cudaIpcCloseMemHandle(c->ptrs.peer[q]));
+    c->ptrs.peer[q] = nullptr;
+  }
+  c->attached = false;
+  return 0;
+}
+
+// Local (re)allocation.  *changed = 1 when the segment was replaced: the caller must then run the
+// export / all-gather / attach sequence on every rank (sizes are the same everywhere, so all ranks change together).
+// Call comm_detach on every rank (and synchronise the ranks) BEFORE a segment that peers have mapped is replaced.
+int comm_reserve(Comm* c, size_t bytes, int* changed) {
+  if (!c || !changed) return fail_arg(1, "null argument");
+  *changed = 0;
+  if (c->local && c->bytes >= bytes) return 0;
+  if (c->attached) return fail_arg(1, "detach the peers before growing the segment");
+  HPS_CUDA(cudaDeviceSynchronize());
+  if (c->local) HPS_CUDA(cudaFree(c->local));
+  c->local = nullptr;
+  HPS_CUDA(cudaMalloc(&c->local, bytes));
+  HPS_CUDA(cudaMemset(c->local, 0, COMM_PAYLOAD_OFF));  // flags and barrier words start at epoch 0
+  HPS_CUDA(cudaDeviceSynchronize());
+  c->bytes = bytes;
+  c->epoch = 0;
+  *changed = 1;
+  return 0;
+}
+
+int comm_export(Comm* c, void* handle64) {
+  if (!c || !c->local || !handle64) return fail_arg(1, "no local segment to export");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  HPS_CUDA(cudaIpcGetMemHandle(&h, c->local));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+int comm_attach(Comm* c, const void* handles) {
+  if (!c || !c->local || (!handles && c->world > 1)) return fail_arg(1, "no local segment / handles");
+  for (int q = 0; q < c->world; ++q) {
+    if (q == c->rank) { c->ptrs.peer[q] = c->local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + (size_t)q * 64, 64);
+    void* ptr = nullptr;
+    HPS_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->ptrs.peer[q] = static_cast<char*>(ptr);
+  }
+  c->attached = true;
+  return 0;
+}
+
+int comm_destroy(Comm* c) {
+  if (!c) return 0;
+  comm_detach(c);
+  if (c->local) cudaFree(c->local);
+  if (c->done) cudaFree(c->done);
+  delete c;
+  return 0;
+}
+
+size_t lu_dist_segment_bytes(int n) { return dist_layout(n).bytes; }
+
+int lu_dist_matrix_ptr(Comm* c, int n, double** A) {
+  if (!c || !A) return fail_arg(1, "null argument");
+  const DistLayout L = dist_layout(n);
+  if (!c->local || c->bytes < L.bytes) return fail_arg(2, "segment too small: hps_comm_reserve(hps_lu_dist_segment_bytes(n)) first");
+  *A = reinterpret_cast<double*>(c->local + L.A_off);
+  return 0;
+}
+
+// Whole distributed factorisation + solves, enqueued on `st` (and an internal look-ahead stream); no host sync.
+// A (n x n, lda = n) must have been assembled at lu_dist_matrix_ptr on EVERY rank.  Block column b is factored by
+// rank b % world (block-column kernel), stored into every peer's segment and signalled; every rank applies it to
+// the block columns it owns AND to its own right-hand sides, which ride along as extra trailing columns — the
+// forward substitution therefore finishes with the factorisation, hidden under the panel chain.  What remains
+// afterwards is U's diagonal inverses and the recursive backward substitution on each rank's right-hand sides.
+int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, void* ws, size_t ws_bytes, int* info) {
+  if (!c || !c->local) return fail_arg(1, "communicator has no segment");
+  if (c->world > 1 && !c->attached) return fail_arg(1, "peers are not attached");
+  if (n <= 0) return 0;
+  const DistLayout L = dist_layout(n);
+  if (c->bytes < L.bytes) return fail_arg(3, "segment too small for n");
+  const int nblk = (n + NB - 1) / NB;
+  if (nblk > COMM_MAX_BLOCKS) return fail_arg(3, "too many block columns for the flag area");
+  Arena ar(ws, ws_bytes);
+  LuWorkspace w;
+  if (!carve(ar, 1, n, w)) return fail_arg(7, "lu_dist_run: workspace too small");
+  HPS_TRY(configure_lu_kernels());
+  // pivots and inverted diagonal blocks live in the symmetric segment: their owners store them there
+  w.ipiv = reinterpret_cast<int*>(c->local + L.ipiv_off);
+  w.Linv = reinterpret_cast<double*>(c->local + L.linv_off);
+  double* A = reinterpret_cast<double*>(c->local + L.A_off);
+  const Mat Am{A, n, 0};
+  const int rank = c->rank, world = c->world;
+  const unsigned epoch = ++c->epoch;
+  unsigned* flags = reinterpret_cast<unsigned*>(c->local + COMM_FLAG_OFF);
+  Aux* aux = nullptr;
+  HPS_TRY(aux_for_stream(st, aux));
+  cudaStream_t s0 = st, s1 = aux->stream;
+
+  HPS_CUDA(cudaMemsetAsync(info, 0, sizeof(int), s0));
+  if (w.bc_Gcap) HPS_CUDA(cudaMemsetAsync(w.bc_scratch, 0, w.bc_stride, s0));
+  // every rank's matrix is assembled (and nobody still uses the segment from the previous operation)
+  if (world > 1) {
+    comm_barrier_kernel<<<1, 32, 0, s0>>>(c->ptrs, rank, world, epoch);
+    HPS_LAUNCH_CHECK("comm_barrier_kernel");
+  }
+  HPS_CUDA(cudaEventRecord(aux->fork, s0));
+  HPS_CUDA(cudaStreamWaitEvent(s1, aux->fork, 0));
+
+  auto factor_and_send = [&](int b) -> int {
+    const int j = b * NB, jb = std::min(NB, n - j);
+    HPS_TRY(factor_block_column(s1, 1, n, Am, j, jb, w, info));
+    if (world > 1) {
+      comm_bcast_blockcol_kernel<<<64, 256, 0, s1>>>(c->ptrs, rank, world, n, j, jb, L.ipiv_off,
+                                                     L.linv_off + (size_t)b * NB * NB * sizeof(double), L.A_off, b, epoch,
+                                                     c->done);
+      HPS_LAUNCH_CHECK("comm_bcast_blockcol_kernel");
+    }
+    return 0;
+  };
+  auto wait_block = [&](int b) -> int {
+    comm_wait_block_kernel<<<1, 1, 0, s1>>>(flags + b, epoch);
+    HPS_LAUNCH_CHECK("comm_wait_block_kernel");
+    return 0;
+  };
+  // owned block columns > lo as one strided batch (+ a ragged last block), then the right-hand sides
+  auto apply_owned = [&](cudaStream_t s, int b, int lo, bool with_rhs) -> int {
+    const int j = b * NB, jb = std::min(NB, n - j);
+    int first = lo + ((rank - lo) % world + world) % world;
+    int n_own = first >= nblk ? 0 : (nblk - 1 - first) / world + 1;
+    if (n_own > 0) {
+      const int last_c0 = (first + (n_own - 1) * world) * NB;
+      const bool ragged = last_c0 + NB > n;
+      const int full = ragged ? n_own - 1 : n_own;
+      if (full > 0) HPS_TRY(dist_apply(s, n, Am, j, jb, w, b, A + (int64_t)first * NB, n, (int64_t)world * NB, NB, full));
+      if (ragged) HPS_TRY(dist_apply(s, n, Am, j, jb, w, b, A + last_c0, n, 0, n - last_c0, 1));
+    }
+    if (with_rhs)
+      for (int k = 0; k < n_rhs; ++k) HPS_TRY(dist_apply(s, n, Am, j, jb, w, b, rhs[k].ptr, rhs[k].ld, 0, rhs[k].ncols, 1));
+    return 0;
+  };
+
+  if (rank == 0 % world) HPS_TRY(factor_and_send(0)); else HPS_TRY(wait_block(0));
+  HPS_CUDA(cudaEventRecord(aux->panel_done[0], s1));
+  for (int b = 0; b < nblk; ++b) {
+    const int nb1 = b + 1;
+    const bool own_next = nb1 < nblk && rank == nb1 % world;
+    if (nb1 < nblk) {
+      if (own_next) {
+        // look-ahead: block column nb1 received blocks < b on s0; bring it up to date with block b and factor it
+        if (b >= 1) HPS_CUDA(cudaStreamWaitEvent(s1, aux->update_done[(b - 1) & 1], 0));
+        const int j = b * NB, jb = std::min(NB, n - j);
+        const int c0 = nb1 * NB, nc = std::min(NB, n - c0);
+        HPS_TRY(dist_apply(s1, n, Am, j, jb, w, b, A + c0, n, 0, nc, 1));
+        HPS_TRY(factor_and_send(nb1));
+      } else {
+        HPS_TRY(wait_block(nb1));
+      }
+      HPS_CUDA(cudaEventRecord(aux->panel_done[nb1 & 1], s1));
+    }
+    HPS_CUDA(cudaStreamWaitEvent(s0, aux->panel_done[b & 1], 0));
+    HPS_TRY(apply_owned(s0, b, own_next ? nb1 + 1 : nb1, true));
+    HPS_CUDA(cudaEventRecord(aux->update_done[b & 1], s0));
+  }
+  if (n_rhs == 0) return 0;
+  prof_begin(PROF_TRTRI, s0, (double)nblk * NB * NB * NB / 3);
+  trtri_kernel<false><<<dim3(nblk, 1), TRI_THREADS, TRTRI_SMEM, s0>>>(A, n, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
+  prof_end(PROF_TRTRI, s0);
+  HPS_LAUNCH_CHECK("trtri_kernel<upper>");
+  for (int k = 0; k < n_rhs; ++k) HPS_TRY(trsm_upper(s0, 1, n, Am, w, rhs[k], 0, n));
   return 0;
 }
 

@@ -28,9 +28,12 @@ def down_levels(g_cur: torch.Tensor, S_dev, g_dev, dim: int, dev) -> torch.Tenso
             )
         out = torch.empty((n_nodes * n_child, n_face * m, n_src), dtype=torch.float64, device=dev)
         ws = torch.empty((n_nodes, n_int, n_src), dtype=torch.float64, device=dev)
-        rc = down_fn(_lib.stream_ptr(), n_nodes, m, n_src, _lib.ptr(S), _lib.ptr(g_cur), _lib.ptr(gt),
-                     _lib.ptr(out), _lib.ptr(ws))
-        _lib.check(rc, "hps_down_level")
+        step = min(n_nodes, _lib.MAX_BATCH)  # the C ABI takes at most MAX_BATCH nodes per call
+        for s0 in range(0, n_nodes, step):
+            s1 = min(n_nodes, s0 + step)
+            rc = down_fn(_lib.stream_ptr(), s1 - s0, m, n_src, _lib.ptr(S[s0:s1]), _lib.ptr(g_cur[s0:s1]),
+                         _lib.ptr(gt[s0:s1]), _lib.ptr(out[n_child * s0:n_child * s1]), _lib.ptr(ws[s0:s1]))
+            _lib.check(rc, "hps_down_level")
         g_cur = out
     return g_cur
 

@@ -45,13 +45,20 @@ def _merge_stage(T_arr, h_arr, l: int, dim: int, device, host_device, return_T: 
             T_out = torch.empty((n_merges, n_ext, n_ext), dtype=torch.float64, device=dev) if want_T else None
             h_out = torch.empty((n_merges, n_ext, n_src), dtype=torch.float64, device=dev) if want_T else None
             info = torch.zeros(n_merges, dtype=torch.int32, device=dev)
+            # the C ABI takes at most MAX_BATCH merges per call (grid limits); wide low levels of deep 2D trees
+            # are processed in contiguous slices, which also bounds the workspace
+            step = min(n_merges, _lib.MAX_BATCH)
             need = ctypes.c_size_t()
-            _lib.check(ws_fn(n_merges, m, n_src, ctypes.byref(need)), "merge workspace query")
-            ws = _lib.WORKSPACE.get(need.value, dev)
+            _lib.check(ws_fn(step, m, n_src, ctypes.byref(need)), "merge workspace query")
+            ws = _lib.workspace(need.value, dev)
             logging.debug("merge level %d: %d merges, m=%d, workspace %.2f GB", level, n_merges, m, need.value / 2**30)
-            rc = level_fn(_lib.stream_ptr(), n_merges, m, n_src, _lib.ptr(T), _lib.ptr(h), _lib.ptr(S), _lib.ptr(g),
-                          _lib.ptr(T_out), _lib.ptr(h_out), 1 if want_T else 0, _lib.ptr(ws), ws.numel(), _lib.ptr(info))
-            _lib.check(rc, "hps_merge_dtn_level")
+            for s0 in range(0, n_merges, step):
+                s1 = min(n_merges, s0 + step)
+                rc = level_fn(_lib.stream_ptr(), s1 - s0, m, n_src, _lib.ptr(T[n_child * s0:n_child * s1]),
+                              _lib.ptr(h[n_child * s0:n_child * s1]), _lib.ptr(S[s0:s1]), _lib.ptr(g[s0:s1]),
+                              _lib.ptr(T_out[s0:s1]) if want_T else None, _lib.ptr(h_out[s0:s1]) if want_T else None,
+                              1 if want_T else 0, _lib.ptr(ws), ws.numel(), _lib.ptr(info[s0:s1]))
+                _lib.check(rc, "hps_merge_dtn_level")
             _lib.check_info(info, f"merge level {level}")
             del T, h
             T, h = T_out, h_out
@@ -116,7 +123,7 @@ def merge_root_columns_3D_DtN(T8, h8, col0: int, ncols: int, device=None):
         info = torch.zeros(1, dtype=torch.int32, device=dev)
         need = ctypes.c_size_t()
         _lib.check(lib.hps_merge_oct_dtn_level_workspace(1, m, n_src, ctypes.byref(need)), "merge workspace query")
-        ws = _lib.WORKSPACE.get(need.value, dev)
+        ws = _lib.workspace(need.value, dev)
         rc = lib.hps_merge_oct_dtn_root_cols(_lib.stream_ptr(), m, n_src, _lib.ptr(T), _lib.ptr(h), col0, ncols,
                                              _lib.ptr(S), _lib.ptr(g), _lib.ptr(ws), ws.numel(), _lib.ptr(info))
         _lib.check(rc, "hps_merge_oct_dtn_root_cols")
@@ -156,13 +163,18 @@ def merge_stage_uniform_2D_ItI(T_arr, h_arr, l: int, device=None, host_device=No
             T_out = torch.empty((n_merges, n, n), **c128) if want_T else None
             h_out = torch.empty((n_merges, n, n_src), **c128) if want_T else None
             info = torch.zeros(n_merges, dtype=torch.int32, device=dev)
+            step = min(n_merges, _lib.MAX_BATCH)
             need = ctypes.c_size_t()
-            _lib.check(lib.hps_merge_quad_iti_level_workspace(n_merges, m, n_src, ctypes.byref(need)), "workspace query")
-            ws = _lib.WORKSPACE.get(need.value, dev)
-            rc = lib.hps_merge_quad_iti_level(_lib.stream_ptr(), n_merges, m, n_src, _lib.ptr(T), _lib.ptr(h), _lib.ptr(S),
-                                              _lib.ptr(g), _lib.ptr(T_out), _lib.ptr(h_out), 1 if want_T else 0,
-                                              _lib.ptr(ws), ws.numel(), _lib.ptr(info))
-            _lib.check(rc, "hps_merge_quad_iti_level")
+            _lib.check(lib.hps_merge_quad_iti_level_workspace(step, m, n_src, ctypes.byref(need)), "workspace query")
+            ws = _lib.workspace(need.value, dev)
+            for s0 in range(0, n_merges, step):
+                s1 = min(n_merges, s0 + step)
+                rc = lib.hps_merge_quad_iti_level(_lib.stream_ptr(), s1 - s0, m, n_src, _lib.ptr(T[4 * s0:4 * s1]),
+                                                  _lib.ptr(h[4 * s0:4 * s1]), _lib.ptr(S[s0:s1]), _lib.ptr(g[s0:s1]),
+                                                  _lib.ptr(T_out[s0:s1]) if want_T else None,
+                                                  _lib.ptr(h_out[s0:s1]) if want_T else None, 1 if want_T else 0,
+                                                  _lib.ptr(ws), ws.numel(), _lib.ptr(info[s0:s1]))
+                _lib.check(rc, "hps_merge_quad_iti_level")
             _lib.check_info(info, f"ItI merge level {level}")
             T, h = T_out, h_out
             S_lst.append(S)

@@ -217,12 +217,16 @@ _OCT_ROLES = _oct_face_roles()
 _OCT_FACE_CHILDREN = _oct_parent_face_children()
 
 
-def uniform_oct_merge_DtN(T_children: np.ndarray, h_children: np.ndarray):
+def uniform_oct_merge_DtN(T_children: np.ndarray, h_children: np.ndarray, need_T: bool = True, probe=None):
     """One oct merge as the reference performs it: dense B (24m x 12m), C, D assembled from
     the children's face blocks, explicit ``inv(D)``, then the region->face permutation
     (`merge/_uniform_3D_DtN.py:127-187`, `_schur_complement.py:293-774`).
 
-    T_children (8, 6m, 6m); h_children (8, 6m[, n_src]).  Returns (S, T, h_out, g_tilde)."""
+    T_children (8, 6m, 6m); h_children (8, 6m[, n_src]).  Returns (S, T, h_out, g_tilde).
+
+    ``need_T=False`` (fixture generation at BASELINE sizes, where the 24m x 24m ``T`` of the root
+    does not fit beside its factors): ``T`` is not formed; the second return value is ``T @ probe``
+    (``probe`` in the parent's face order) evaluated as ``A x (+) B (S x)``, or ``None``."""
     m = T_children.shape[-1] // 6
     tail = h_children.shape[2:]
     B = np.zeros((24 * m, 12 * m))
@@ -250,8 +254,24 @@ def uniform_oct_merge_DtN(T_children: np.ndarray, h_children: np.ndarray):
             for g in int_faces:
                 D[fs(int_slot[f]), fs(int_slot[g])] += T[fs(f), fs(g)]
     D_inv = np.linalg.inv(D)
-    T, S, h_out, g_tilde = assemble_merge_outputs(A_lst, B, C, D_inv, h_ext, h_int)
     r = oct_region_to_face_permutation(m)
+    if not need_T:
+        S = -1 * D_inv @ C
+        g_tilde = -1 * D_inv @ h_int
+        h_out = h_ext + B @ g_tilde
+        Tx = None
+        if probe is not None:
+            x = np.zeros_like(np.asarray(probe, dtype=float))
+            x[r] = probe  # face order -> region order
+            Tx = B @ (S @ x)
+            at = 0
+            for A in A_lst:
+                n = A.shape[0]
+                Tx[at : at + n] += A @ x[at : at + n]
+                at += n
+            Tx = Tx[r]
+        return S[:, r], Tx, h_out[r], g_tilde
+    T, S, h_out, g_tilde = assemble_merge_outputs(A_lst, B, C, D_inv, h_ext, h_int)
     return S[:, r], T[np.ix_(r, r)], h_out[r], g_tilde
 
 

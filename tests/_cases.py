@@ -74,3 +74,27 @@ def rel_err(a, b):
     b = np.asarray(b)
     assert a.shape == b.shape, (a.shape, b.shape)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+# ---- BASELINE config 3 at full leaf size (p=12, q=10): parity problem and the probe fixtures ----
+CONFIG3_P, CONFIG3_Q, CONFIG3_SEED = 12, 10, 3
+
+
+def config3_problem(L):
+    """SURVEY §8(d) config 3, random-coefficient variant for parity: D_xx, D_yy, D_zz = 1 + 0.1 N(0,1) (seed 3),
+    a first-order and a zeroth-order term so that every merge sees a non-symmetric operator, random source and
+    random Dirichlet data."""
+    rng = np.random.default_rng(CONFIG3_SEED)
+    shp = (8**L, CONFIG3_P**3)
+    co = {f"{k}_coefficients": 1 + 0.1 * rng.normal(size=shp) for k in ("D_xx", "D_yy", "D_zz")}
+    co["D_x_coefficients"] = rng.normal(size=shp)
+    co["I_coefficients"] = rng.normal(size=shp)
+    src = rng.normal(size=shp)
+    bdry = rng.normal(size=6 * 4**L * CONFIG3_Q**2)
+    dom = make_domain(3, CONFIG3_P, CONFIG3_Q, L)
+    return hps.PDEProblem(dom, source=src, **co), bdry
+
+
+def config3_probe(n, salt):
+    """Fixed probe vector of length n (operators are compared through their action on it)."""
+    return np.random.default_rng(1000 + salt).normal(size=n)

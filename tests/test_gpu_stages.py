@@ -163,12 +163,16 @@ def test_sharded_driver_single_rank_matches_oracle(p, q, L, nsrc):
         assert rel_err(Sc.cpu().numpy(), S[-1][:, n_ext // 2 :]) < TOL and rel_err(gt.cpu().numpy(), g[-1]) < TOL
 
 
-@pytest.mark.parametrize("p,q,L", [(6, 4, 2), (8, 6, 2)])
-def test_stepwise_root_factorisation_matches_oracle(p, q, L):
-    """The step-wise factorisation the multi-GPU root uses (hps_lu_dist_*: factor+pack a block column,
-    apply it to the owned block columns, final solves), forced on a single rank."""
+@pytest.mark.parametrize("p2p", [True, False])
+@pytest.mark.parametrize("p,q,L", [(6, 4, 2), (8, 6, 2), (12, 10, 1)])
+def test_stepwise_root_factorisation_matches_oracle(p, q, L, p2p, monkeypatch):
+    """The distributed factorisation the multi-GPU root uses, forced on a single rank: ``hps_lu_dist_run`` on the
+    library's symmetric segment (p2p: block-column loop in C, right-hand sides carried as trailing columns) and the
+    step-wise NCCL-broadcast fallback (hps_lu_dist_factor_pack / update / solve driven from Python)."""
     from jaxhps_b200 import _dist
     from _cases import make_domain, seeded_inputs
+
+    monkeypatch.setattr(_dist, "USE_P2P", p2p)
 
     co, src, bdry = seeded_inputs(3, p, q, L, 1, seed=91)
     dom = make_domain(3, p, q, L)
