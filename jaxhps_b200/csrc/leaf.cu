@@ -92,13 +92,14 @@ __device__ __forceinline__ double entry2d(const AssembleArgs& g, const double* D
 }
 
 // blockIdx.y = leaf, blockIdx.x strides over interior rows; the (i,j,k) of every column is decoded
-// once per CTA into shared memory, the row's once per row, so the inner loop is a few compares and
-// FMAs per entry and the kernel runs at the speed of its 13.8 MB/leaf of writes.
+// once per CTA into shared memory, the row's once per row; structurally-zero entries (all but ~3p per row
+// when no mixed derivative is present) skip the coefficient arithmetic, so the kernel is bound by its
+// 13.8 MB/leaf of writes.
 template <int DIM>
 __global__ void __launch_bounds__(256) assemble_kernel(AssembleArgs g) {
   __shared__ double D[MAX_P * MAX_P];
   __shared__ double D2[MAX_P * MAX_P];
-  extern __shared__ unsigned char colidx[];  // [n_c][4]: i, j, k of every leaf-ordered column
+  extern __shared__ __align__(4) unsigned char colidx[];  // [n_c][4]: i, j, k of every leaf-ordered column
   const int p = g.geo.p, n_c = g.geo.n_c, n_i = g.geo.n_i, n_b = g.geo.n_b;
   for (int t = threadIdx.x; t < p * p; t += blockDim.x) D[t] = g.D1[t];
   for (int b = threadIdx.x; b < n_c; b += blockDim.x) {
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(AssembleArgs g) {
   }
   __syncthreads();
   const int leaf = blockIdx.y;
+  const bool has_mixed = g.slot[1] >= 0 || g.slot[3] >= 0 || g.slot[4] >= 0;
   for (int a = blockIdx.x; a < n_i; a += gridDim.x) {
     const int row = n_b + a;
     const int i = colidx[4 * row], j = colidx[4 * row + 1], k = colidx[4 * row + 2];
@@ -127,10 +129,15 @@ __global__ void __launch_bounds__(256) assemble_kernel(AssembleArgs g) {
     double* out_ie = g.Aie + ((int64_t)leaf * n_i + a) * n_b;
     double* out_ii = g.Aii + ((int64_t)leaf * n_i + a) * n_i;
     for (int b = threadIdx.x; b < n_c; b += blockDim.x) {
-      const int i2 = colidx[4 * b], j2 = colidx[4 * b + 1], k2 = colidx[4 * b + 2];
+      const uchar4 cidx = reinterpret_cast<const uchar4*>(colidx)[b];
+      const int i2 = cidx.x, j2 = cidx.y, k2 = cidx.z;
       const bool di = i == i2, dj = j == j2, dk = k == k2;
       double val = 0.0;
-      if (DIM == 3) {
+      // an entry is structurally zero unless the two points share a grid line (two equal indices) or, when a
+      // mixed-derivative coefficient is present, a grid plane: 98% of a 3D row takes the short path
+      if (DIM == 3 && (int)di + (int)dj + (int)dk < (has_mixed ? 1 : 2)) {
+        // zero
+      } else if (DIM == 3) {
         // order of the reference's stack: xx, xy, yy, xz, yz, zz, x, y, z, I
         if (dj && dk) val = fma(cf[0], D2[i * p + i2], val);
         if (dk) val = fma(cf[1], D[i * p + i2] * D[j * p + j2], val);

@@ -202,6 +202,159 @@ __global__ void __launch_bounds__(256) merge_ext_kernel(Topo tp, int m, int n_sr
   }
 }
 
+
+// ---- tile-per-CTA variants of the two gathers (full exterior range) ------------------------------------
+// A CTA owns one m x m block of the output (or a horizontal slice of it): which child, which faces and
+// whether the block is structurally zero are decided ONCE per CTA from the topology, so the inner loop is
+// a plain row copy — a warp per row, lanes along the row, four rows of loads in flight before the first
+// store.  (The element-wise kernels above decode the role of every entry through lane-varying look-ups in
+// the kernel-parameter tables, which serialises in the constant cache: 0.22 of the HBM rate in round 1.)
+template <typename E>
+__device__ __forceinline__ E neg_e(E a);
+template <>
+__device__ __forceinline__ double neg_e<double>(double a) { return -a; }
+template <>
+__device__ __forceinline__ double2 neg_e<double2>(double2 a) { return make_double2(-a.x, -a.y); }
+template <typename E>
+__device__ __forceinline__ E add_e2(E a, E b);
+template <>
+__device__ __forceinline__ double add_e2<double>(double a, double b) { return a + b; }
+template <>
+__device__ __forceinline__ double2 add_e2<double2>(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+
+// dst[r][c] = sign * (srcA[r'][c'] (+ srcB[r''][c''])), r in [r_lo, r_hi), c in [0, m); null sources give zeros.
+// Row / column reversal (2D interfaces walked backwards by one of the two children) via stride signs.
+template <typename E, bool NEGATE>
+__device__ __forceinline__ void copy_block(E* __restrict__ dst, int64_t ldd, const E* __restrict__ A, int64_t rsA, int csA,
+                                           const E* __restrict__ B, int64_t rsB, int csB, int r_lo, int r_hi, int m) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = r_lo + warp; r < r_hi; r += nw) {
+    E* d = dst + (int64_t)r * ldd;
+    const E* a = A ? A + (int64_t)r * rsA : nullptr;
+    const E* b = B ? B + (int64_t)r * rsB : nullptr;
+    for (int c0 = lane; c0 < m; c0 += 128) {
+      E v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + 32 * i;
+        v[i] = zero_of(E());
+        if (c < m) {
+          if (a) v[i] = a[(int64_t)c * csA];
+          if (b) v[i] = add_e2<E>(v[i], b[(int64_t)c * csB]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + 32 * i;
+        if (c < m) d[c] = NEGATE ? neg_e<E>(v[i]) : v[i];
+      }
+    }
+  }
+}
+
+// grid: x = output block column (n_slot blocks of D, then n_ext blocks of -C, then one for g~),
+//       y = interface slot s1 * row_splits + slice, z = merge
+__global__ void __launch_bounds__(256) merge_gather_tile_kernel(Topo tp, int m, int n_src, const double* __restrict__ T_in,
+                                                                const double* __restrict__ h_in, double* __restrict__ D,
+                                                                double* __restrict__ S, double* __restrict__ gt,
+                                                                int row_splits) {
+  const int n_int = tp.n_slot * m, n_ext = tp.n_ext * m, nf = tp.n_face * m;
+  const int mg = blockIdx.z, cb = blockIdx.x;
+  const int s1 = blockIdx.y / row_splits, sl = blockIdx.y - s1 * row_splits;
+  const int rows_per = (m + row_splits - 1) / row_splits;
+  const int r_lo = sl * rows_per, r_hi = min(m, r_lo + rows_per);
+  const int64_t child_sz = (int64_t)nf * nf;
+  const int cA = tp.slot_owner[s1][0], cB = tp.slot_owner[s1][1];
+  const int fA = tp.slot_face[cA][s1], fB = tp.slot_face[cB][s1];
+  const double* TA = T_in + ((int64_t)mg * tp.n_child + cA) * child_sz;
+  const double* TB = T_in + ((int64_t)mg * tp.n_child + cB) * child_sz;
+  // row t1 of this slot inside child X: face row fX*m + t1, walked backwards when the child flips the interface
+  const int64_t rsA = tp.flip[cA][fA] ? -(int64_t)nf : (int64_t)nf, rsB = tp.flip[cB][fB] ? -(int64_t)nf : (int64_t)nf;
+  const double* rowA0 = TA + (int64_t)(fA * m + (tp.flip[cA][fA] ? m - 1 : 0)) * nf;
+  const double* rowB0 = TB + (int64_t)(fB * m + (tp.flip[cB][fB] ? m - 1 : 0)) * nf;
+  if (cb < tp.n_slot) {
+    const int s2 = cb;
+    const int f2A = tp.slot_face[cA][s2], f2B = tp.slot_face[cB][s2];
+    const double* A = nullptr; const double* B = nullptr;
+    int csA = 1, csB = 1;
+    if (f2A >= 0) { const bool fl = tp.flip[cA][f2A]; A = rowA0 + f2A * m + (fl ? m - 1 : 0); csA = fl ? -1 : 1; }
+    if (f2B >= 0) { const bool fl = tp.flip[cB][f2B]; B = rowB0 + f2B * m + (fl ? m - 1 : 0); csB = fl ? -1 : 1; }
+    double* dst = D + ((int64_t)mg * n_int + s1 * m) * n_int + s2 * m;
+    copy_block<double, false>(dst, n_int, A, rsA, csA, B, rsB, csB, r_lo, r_hi, m);
+  } else if (cb < tp.n_slot + tp.n_ext) {
+    const int e = cb - tp.n_slot;
+    const int c = tp.ext_child[e], f = tp.ext_face[e];
+    const double* A = nullptr;
+    int64_t rs = nf;
+    if (c == cA) { A = rowA0 + f * m; rs = rsA; } else if (c == cB) { A = rowB0 + f * m; rs = rsB; }
+    double* dst = S + ((int64_t)mg * n_int + s1 * m) * n_ext + e * m;
+    copy_block<double, true>(dst, n_ext, A, rs, 1, nullptr, 0, 1, r_lo, r_hi, m);
+  } else {
+    const double* hm = h_in + (int64_t)mg * tp.n_child * nf * n_src;
+    const int total = (r_hi - r_lo) * n_src;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int t1 = r_lo + idx / n_src, k = idx - (idx / n_src) * n_src;
+      const double v = hm[((int64_t)cA * nf + face_index(tp, cA, fA, t1, m)) * n_src + k] +
+                       hm[((int64_t)cB * nf + face_index(tp, cB, fB, t1, m)) * n_src + k];
+      gt[((int64_t)mg * n_int + s1 * m + t1) * n_src + k] = -v;
+    }
+  }
+}
+
+// grid: x = output block column (n_ext blocks of T_out, n_intf packed blocks of B, one for h_out),
+//       y = exterior panel e1 * row_splits + slice, z = merge
+template <typename E>
+__global__ void __launch_bounds__(256) merge_ext_tile_kernel(Topo tp, int m, int n_src, const E* __restrict__ T_in,
+                                                             const E* __restrict__ h_in, E* __restrict__ T_out,
+                                                             E* __restrict__ h_out, E* __restrict__ Bg, int row_splits) {
+  const int n_ext = tp.n_ext * m, nf = tp.n_face * m;
+  const int mg = blockIdx.z, cb = blockIdx.x;
+  const int e1 = blockIdx.y / row_splits, sl = blockIdx.y - e1 * row_splits;
+  const int rows_per = (m + row_splits - 1) / row_splits;
+  const int r_lo = sl * rows_per, r_hi = min(m, r_lo + rows_per);
+  const int c = tp.ext_child[e1], f1 = tp.ext_face[e1];
+  const int64_t child_sz = (int64_t)nf * nf;
+  const E* row0 = T_in + ((int64_t)mg * tp.n_child + c) * child_sz + (int64_t)(f1 * m) * nf;
+  if (cb < tp.n_ext) {
+    const int e2 = cb;
+    const E* A = (tp.ext_child[e2] == c) ? row0 + tp.ext_face[e2] * m : nullptr;
+    E* dst = T_out + ((int64_t)mg * n_ext + e1 * m) * n_ext + e2 * m;
+    copy_block<E, false>(dst, n_ext, A, nf, 1, nullptr, 0, 1, r_lo, r_hi, m);
+  } else if (cb < tp.n_ext + tp.n_intf) {
+    const int j = cb - tp.n_ext;
+    const int s = tp.ext_slot[e1][j];
+    const int fs = tp.slot_face[c][s];
+    const bool fl = tp.flip[c][fs];
+    const E* A = row0 + fs * m + (fl ? m - 1 : 0);
+    E* dst = Bg + (((int64_t)mg * tp.n_ext + e1) * tp.n_intf + j) * m * m;
+    copy_block<E, false>(dst, m, A, nf, fl ? -1 : 1, nullptr, 0, 1, r_lo, r_hi, m);
+  } else {
+    const int total = (r_hi - r_lo) * n_src;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int u1 = r_lo + idx / n_src, k = idx - (idx / n_src) * n_src;
+      h_out[((int64_t)mg * n_ext + e1 * m + u1) * n_src + k] =
+          h_in[(((int64_t)mg * tp.n_child + c) * nf + f1 * m + u1) * n_src + k];
+    }
+  }
+}
+
+// algorithmic bytes of the two gathers of one merge: every output entry written once, every source entry of
+// the children's T read once per use
+double gather_bytes(const Topo& tp, int m, int n_src) {
+  double blocks = (double)tp.n_slot * (tp.n_slot + tp.n_ext);  // written
+  for (int s1 = 0; s1 < tp.n_slot; ++s1) {
+    const int cA = tp.slot_owner[s1][0], cB = tp.slot_owner[s1][1];
+    for (int s2 = 0; s2 < tp.n_slot; ++s2) blocks += (tp.slot_face[cA][s2] >= 0) + (tp.slot_face[cB][s2] >= 0);
+    blocks += 2.0 * (tp.n_face - tp.n_intf);  // exterior faces of the two children sharing the slot
+  }
+  return 8.0 * (blocks * m * m + 3.0 * tp.n_slot * m * n_src);
+}
+double ext_bytes(const Topo& tp, int m, int n_src) {
+  const double ext_per_child = tp.n_face - tp.n_intf;
+  const double blocks = (double)tp.n_ext * tp.n_ext + tp.n_ext * ext_per_child + 2.0 * tp.n_ext * tp.n_intf;
+  return 8.0 * (blocks * m * m + 2.0 * tp.n_ext * m * n_src);
+}
+
 // ---- down pass scatter: children's boundary vectors from g_ext and g_int --------------------
 __global__ void __launch_bounds__(256) down_scatter_kernel(Topo tp, int m, int n_src, const double* __restrict__ g_ext,
                                                            const double* __restrict__ g_int, double* __restrict__ out) {
@@ -298,13 +451,13 @@ int merge_level(const Topo& tp, cudaStream_t st, int n_merges, int m, int n_src,
   void* lu_ws = ar.base + ar.off;
   const size_t lu_ws_bytes = ar.cap - ar.off;
 
+  const int row_splits = (m + 127) / 128;  // big blocks are cut into slices of <= 128 rows
   {
-    const int cols = n_int + n_ext + n_src;
-    dim3 grid(std::min((cols + 255) / 256, 64), std::min(n_int, 65535), n_merges);
-    prof_begin(PROF_GATHER, st, 8.0 * n_merges * (double)n_int * (n_int + n_ext));
-    merge_gather_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, D, S, gt, 0, n_ext);
+    dim3 grid(tp.n_slot + tp.n_ext + 1, tp.n_slot * row_splits, n_merges);
+    prof_begin(PROF_GATHER, st, n_merges * gather_bytes(tp, m, n_src));
+    merge_gather_tile_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, D, S, gt, row_splits);
     prof_end(PROF_GATHER, st);
-    HPS_LAUNCH_CHECK("merge_gather_kernel");
+    HPS_LAUNCH_CHECK("merge_gather_tile_kernel");
   }
   const int64_t sS = (int64_t)n_int * n_ext, sG = (int64_t)n_int * n_src, sDi = (int64_t)n_int * n_int;
   RhsDesc rhs[3] = {{S, n_ext, sS, n_ext}, {gt, n_src, sG, n_src}, {D_inv, n_int, sDi, n_int}};
@@ -313,12 +466,11 @@ int merge_level(const Topo& tp, cudaStream_t st, int n_merges, int m, int n_src,
   if (!want_T && !BD_inv) return 0;
 
   {
-    const int cols = n_ext + tp.n_intf * m + n_src;
-    dim3 grid(std::min((cols + 255) / 256, 64), std::min(n_ext, 65535), n_merges);
-    prof_begin(PROF_GATHER, st, 8.0 * n_merges * (double)n_ext * n_ext);
-    merge_ext_kernel<double><<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, T_out, h_out, Bg);
+    dim3 grid(tp.n_ext + tp.n_intf + 1, tp.n_ext * row_splits, n_merges);
+    prof_begin(PROF_GATHER, st, n_merges * ext_bytes(tp, m, n_src));
+    merge_ext_tile_kernel<double><<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, T_out, h_out, Bg, row_splits);
     prof_end(PROF_GATHER, st);
-    HPS_LAUNCH_CHECK("merge_ext_kernel");
+    HPS_LAUNCH_CHECK("merge_ext_tile_kernel");
   }
   const int64_t sT = (int64_t)n_ext * n_ext, sH = (int64_t)n_ext * n_src;
   const int64_t sB = (int64_t)tp.n_ext * tp.n_intf * m * m;
@@ -693,12 +845,12 @@ int merge_quad_iti_level(cudaStream_t st, int n_merges, int m, int n_src, const 
                              (int64_t)n2 * 2 * n_src));
   if (!want_T && !BD_inv) return 0;
   {
-    const int cols = n + 2 * m + n_src;
-    dim3 grid(std::min((cols + 255) / 256, 64), n, n_merges);
-    merge_ext_kernel<double2><<<grid, 256, 0, st>>>(
+    const int row_splits = (m + 127) / 128;
+    dim3 grid(tp.base.n_ext + tp.base.n_intf + 1, tp.base.n_ext * row_splits, n_merges);
+    merge_ext_tile_kernel<double2><<<grid, 256, 0, st>>>(
         tp.base, m, n_src, reinterpret_cast<const double2*>(R_in), reinterpret_cast<const double2*>(h_in),
-        reinterpret_cast<double2*>(R_out), reinterpret_cast<double2*>(h_out), reinterpret_cast<double2*>(Bg));
-    HPS_LAUNCH_CHECK("merge_ext_kernel<complex>");
+        reinterpret_cast<double2*>(R_out), reinterpret_cast<double2*>(h_out), reinterpret_cast<double2*>(Bg), row_splits);
+    HPS_LAUNCH_CHECK("merge_ext_tile_kernel<complex>");
   }
   // R_out[panel e] += B_block (complex m x m) * S[unknown slot rows]; real GEMMs on the interleaved views
   const int64_t sB = (int64_t)8 * 2 * m * m * 2, sS2 = (int64_t)n2 * n2, sR = (int64_t)n * n * 2;
