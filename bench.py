@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 
 P, Q = 12, 10
 HBM_FALLBACK_GBPS = 6650.0  # B200_PROFILING.md fallback, used only when MEASURED_PEAKS.json is absent
-PROF_NAMES = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny_matvec", "leaf_assemble"]
+PROF_NAMES = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny_matvec", "leaf_assemble", "p2p_send"]
 
 
 def u_exact(x):
@@ -330,9 +330,9 @@ class Runner:
 
 
 def read_prof(lib, _lib):
-    pm = (ctypes.c_double * 8)()
-    pw = (ctypes.c_double * 8)()
-    pl = (ctypes.c_int64 * 8)()
+    pm = (ctypes.c_double * 16)()
+    pw = (ctypes.c_double * 16)()
+    pl = (ctypes.c_int64 * 16)()
     allk = ctypes.c_int64()
     _lib.check(lib.hps_prof_read(_lib.stream_ptr(), pm, pw, pl, ctypes.byref(allk)), "hps_prof_read")
     return list(pm), list(pw), list(pl), int(allk.value)

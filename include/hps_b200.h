@@ -41,9 +41,10 @@ const char* hps_last_error_string(void);
  * time in ms, the summed work and the launch count, plus the number of kernel launches of any kind
  * the library issued since the reset.  Categories: 0 DMMA GEMM (work = flops), 1 LU panel,
  * 2 triangular-block inversion, 3 row interchanges, 4 inner 32x32 solves, 5 merge gather/scatter
- * (work = bytes written), 6 narrow-N mat-vec kernel (bytes read), 7 leaf assembly (bytes written).
- * ms/work/launches: HOST arrays of length HPS_PROF_NCAT = 8. */
-#define HPS_PROF_NCAT 8
+ * (work = bytes read + written), 6 narrow-N mat-vec kernel (bytes read), 7 leaf assembly (bytes written),
+ * 8 peer-to-peer block-column sends of the distributed factorisation (bytes sent).
+ * ms/work/launches: HOST arrays of length HPS_PROF_NCAT = 9. */
+#define HPS_PROF_NCAT 9
 int hps_prof_enable(int on);
 int hps_prof_read(void* stream, double* ms, double* work, int64_t* launches, int64_t* all_launches);
 
@@ -247,6 +248,15 @@ int hps_up_gather_quad_iti(void* stream, int n_nodes, int m, int n_src, const do
 int hps_zgemm_strided_batched(void* stream, int M, int N, int K, double alpha,
                               const double* A, int64_t lda, int64_t sA, const double* B, int64_t sB,
                               double beta, double* C, int64_t ldc, int64_t sC, int batch, void* ws);
+
+/* Dense complex solve X = A^-1 B (A n x n with leading dimension lda, B n x nrhs with ldb, X n x nrhs contiguous;
+ * complex128 interleaved; A and B are not modified).  Replaces jnp.linalg.solve in the reference's ItI -> DtN
+ * conversion of the top-level operator, T = -i eta (R - I)^-1 (R + I), and in its BIE coupling system
+ * (examples/wave_scattering_utils.py:31-49, 96-242): real embedding + the pivoted FP64 LU.  info[0]: LAPACK convention
+ * on the 2n x 2n embedded matrix. */
+int hps_zgesv_workspace(int n, int nrhs, size_t* bytes);
+int hps_zgesv(void* stream, int n, int nrhs, const double* A, int64_t lda, const double* B, int64_t ldb,
+              double* X, void* ws, size_t ws_bytes, int* info);
 
 /* ---- down_pass (reference: down_pass/_uniform_3D_DtN.py:116-246,
  *      down_pass/_uniform_2D_DtN.py:125-189) -------------------------------------------

@@ -69,6 +69,8 @@ _SIGNATURES = {
     "hps_up_gather_quad": (_i, [_p, _i, _i, _i, _p, _p, _p, _i]),
     "hps_up_gather_quad_iti": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, ctypes.POINTER(_i)]),
     "hps_zgemm_strided_batched": (_i, [_p, _i, _i, _i, _d, _p, _l, _l, _p, _l, _d, _p, _l, _l, _i, _p]),
+    "hps_zgesv_workspace": (_i, [_i, _i, ctypes.POINTER(_sz)]),
+    "hps_zgesv": (_i, [_p, _i, _i, _p, _l, _p, _l, _p, _p, _sz, _p]),
     "hps_down_quad_iti_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "hps_leaf_apply_complex": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "hps_down_oct_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),

@@ -44,6 +44,9 @@ int aux_for_stream(cudaStream_t st, Aux*& out) {
     }
     HPS_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
     HPS_CUDA(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+    HPS_CUDA(cudaStreamCreateWithPriority(&a.comm_stream, cudaStreamNonBlocking, hi));
+    HPS_CUDA(cudaEventCreateWithFlags(&a.factored, cudaEventDisableTiming));
+    HPS_CUDA(cudaEventCreateWithFlags(&a.sent, cudaEventDisableTiming));
   }
   out = &a;
   return 0;
@@ -320,6 +323,15 @@ int hps_zgemm_strided_batched(void* stream, int M, int N, int K, double alpha, c
                               const double* B, int64_t sB, double beta, double* C, int64_t ldc, int64_t sC, int batch,
                               void* ws) {
   return zgemm(static_cast<cudaStream_t>(stream), M, N, K, alpha, A, lda, sA, B, sB, beta, C, ldc, sC, batch, ws);
+}
+int hps_zgesv_workspace(int n, int nrhs, size_t* bytes) {
+  if (!bytes) return fail_arg(3, "null output pointer");
+  *bytes = zgesv_workspace_bytes(n, nrhs);
+  return 0;
+}
+int hps_zgesv(void* stream, int n, int nrhs, const double* A, int64_t lda, const double* B, int64_t ldb, double* X, void* ws,
+              size_t ws_bytes, int* info) {
+  return zgesv(static_cast<cudaStream_t>(stream), n, nrhs, A, lda, B, ldb, X, ws, ws_bytes, info);
 }
 int hps_down_quad_iti_level(void* stream, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
                             const double* g_tilde, double* g_children, void* ws) {

@@ -32,6 +32,8 @@ struct Aux {  // look-ahead stream + events of one (device, caller stream) pair
   cudaEvent_t panel_done[2] = {nullptr, nullptr};
   cudaEvent_t update_done[2] = {nullptr, nullptr};
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaStream_t comm_stream = nullptr;  // peer-to-peer sends that are off the critical path
+  cudaEvent_t factored = nullptr, sent = nullptr;
 };
 struct DeviceState {
   std::atomic<bool> gemm_configured{false};
@@ -53,7 +55,7 @@ int aux_for_stream(cudaStream_t st, Aux*& out);  // created on first use
 // Optional per-category device timing (CUDA events on the launching stream), used by bench.py
 // for the roofline of the dominant kernels.  Off by default: zero overhead on the product path.
 enum ProfCat { PROF_GEMM = 0, PROF_PANEL = 1, PROF_TRTRI = 2, PROF_LASWP = 3, PROF_INNER = 4, PROF_GATHER = 5,
-               PROF_SKINNY = 6, PROF_ASSEMBLE = 7, PROF_NCAT = 8 };
+               PROF_SKINNY = 6, PROF_ASSEMBLE = 7, PROF_COMM = 8, PROF_NCAT = 9 };
 void prof_begin(int cat, cudaStream_t st, double work);
 void prof_end(int cat, cudaStream_t st);
 
@@ -170,6 +172,9 @@ int up_gather_quad_iti(cudaStream_t st, int n_nodes, int m, int n_src, const dou
                        int ext_shift, const int* pos8);
 int zgemm(cudaStream_t st, int M, int N, int K, double alpha, const double* A, int64_t lda, int64_t sA, const double* B,
           int64_t sB, double beta, double* C, int64_t ldc, int64_t sC, int batch, void* ws);
+size_t zgesv_workspace_bytes(int n, int nrhs);
+int zgesv(cudaStream_t st, int n, int nrhs, const double* A, int64_t lda, const double* B, int64_t ldb, double* X, void* ws,
+          size_t ws_bytes, int* info);
 int down_quad_iti_level(cudaStream_t st, int n_nodes, int m, int n_src, const double* S, const double* g_ext,
                         const double* gt, double* g_children, void* ws);
 int leaf_apply_complex(cudaStream_t st, int n_leaves, int n_c, int n_g, int n_src, const double* Y, const double* g,

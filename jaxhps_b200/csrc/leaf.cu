@@ -334,6 +334,60 @@ int zgemm(cudaStream_t st, int M, int N, int K, double alpha, const double* A, i
   return dgemm(st, M, 2 * N, 2 * K, 1.0, A, 2 * lda, 2 * sA, B2, 2 * N, (int64_t)4 * K * N, beta, C, 2 * ldc, 2 * sC, batch);
 }
 
+// ---- dense complex solve  X = A^-1 B  (A: n x n, B: n x nrhs, complex128 interleaved, neither is modified) ----
+// Used by the ItI -> DtN conversion of the top-level operator and the BIE coupling system of the scattering
+// application (reference examples/wave_scattering_utils.py:31-49,96-242, where it is jnp.linalg.solve): the real
+// embedding [[Ar,-Ai],[Ai,Ar]] [Xr;Xi] = [Br;Bi] goes through the same pivoted FP64 LU as every other solve.
+namespace {
+__global__ void complex_embed_kernel(int n, const double2* __restrict__ A, int64_t lda, double* __restrict__ Ae) {
+  const int64_t total = (int64_t)n * n, ld = 2 * (int64_t)n;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / n, c = e - r * n;
+    const double2 z = A[r * lda + c];
+    Ae[r * ld + c] = z.x;
+    Ae[r * ld + n + c] = -z.y;
+    Ae[(n + r) * ld + c] = z.y;
+    Ae[(n + r) * ld + n + c] = z.x;
+  }
+}
+__global__ void complex_stack_kernel(int n, int nrhs, const double2* __restrict__ B, int64_t ldb, double* __restrict__ Bs) {
+  const int64_t total = (int64_t)n * nrhs;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / nrhs, c = e - r * nrhs;
+    const double2 z = B[r * ldb + c];
+    Bs[e] = z.x;
+    Bs[total + e] = z.y;
+  }
+}
+}  // namespace
+
+size_t zgesv_workspace_bytes(int n, int nrhs) {
+  const size_t n2 = 2 * (size_t)n;
+  return align_up(n2 * n2 * 8, 256) + align_up(n2 * (size_t)nrhs * 8, 256) + lu_workspace_bytes(1, (int)n2) + 1024;
+}
+
+int zgesv(cudaStream_t st, int n, int nrhs, const double* A, int64_t lda, const double* B, int64_t ldb, double* X, void* ws,
+          size_t ws_bytes, int* info) {
+  if (n <= 0 || nrhs <= 0) return fail_arg(2, "non-positive size");
+  const int n2 = 2 * n;
+  Arena ar(ws, ws_bytes);
+  double* Ae = ar.take<double>((size_t)n2 * n2);
+  double* Bs = ar.take<double>((size_t)n2 * nrhs);
+  if (!Ae || !Bs) return fail_arg(9, "zgesv: workspace too small");
+  void* lu_ws = ar.base + ar.off;
+  const size_t lu_ws_bytes = ar.cap - ar.off;
+  const int64_t tA = (int64_t)n * n, tB = (int64_t)n * nrhs;
+  complex_embed_kernel<<<(unsigned)std::min<int64_t>((tA + 255) / 256, 4096), 256, 0, st>>>(
+      n, reinterpret_cast<const double2*>(A), lda, Ae);
+  HPS_LAUNCH_CHECK("complex_embed_kernel");
+  complex_stack_kernel<<<(unsigned)std::min<int64_t>((tB + 255) / 256, 4096), 256, 0, st>>>(
+      n, nrhs, reinterpret_cast<const double2*>(B), ldb, Bs);
+  HPS_LAUNCH_CHECK("complex_stack_kernel");
+  RhsDesc rhs[1] = {{Bs, nrhs, (int64_t)n2 * nrhs, nrhs}};
+  HPS_TRY(lu_solve(st, 1, n2, Ae, n2, (int64_t)n2 * n2, 1, rhs, lu_ws, lu_ws_bytes, info));
+  return stacked_to_complex(st, 1, n, nrhs, Bs, (int64_t)n2 * nrhs, X, (int64_t)n * nrhs, nullptr, 0);
+}
+
 size_t local_solve_iti_workspace_bytes(int n_leaves, int p, int q, int n_src) {
   const LeafGeom g = geom(2, p);
   const size_t n_g = 4 * (size_t)q, n2 = 2 * (size_t)g.n_c;

@@ -31,6 +31,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -1235,9 +1236,9 @@ __global__ void comm_wait_block_kernel(const unsigned* flag, unsigned epoch) {
 // Fused copy + signal: the owner stores its factored block column (all n rows: U above, L below), the
 // pivots and the inverted unit-lower diagonal block into every peer's segment, then releases flag b there.
 // Each element is read once and written world-1 times; the last CTA to finish raises the flags.
-__global__ void __launch_bounds__(256) comm_bcast_blockcol_kernel(CommPtrs p, int rank, int world, int n, int j, int jb,
-                                                                  size_t ipiv_off, size_t linv_off, size_t A_off, int b,
-                                                                  unsigned epoch, unsigned* done) {
+__global__ void __launch_bounds__(256) comm_bcast_blockcol_kernel(CommPtrs p, int rank, int world, unsigned mask, int n,
+                                                                  int j, int jb, size_t ipiv_off, size_t linv_off,
+                                                                  size_t A_off, int b, unsigned epoch, unsigned* done) {
   const char* src = p.peer[rank];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1250,7 +1251,7 @@ __global__ void __launch_bounds__(256) comm_bcast_blockcol_kernel(CommPtrs p, in
       const size_t off = A_off + ((size_t)r * n + j) * sizeof(double) + (size_t)c * sizeof(double2);
       const double2 v = *reinterpret_cast<const double2*>(src + off);
       for (int q = 0; q < world; ++q)
-        if (q != rank) *reinterpret_cast<double2*>(p.peer[q] + off) = v;
+        if ((mask >> q) & 1u) *reinterpret_cast<double2*>(p.peer[q] + off) = v;
     }
   } else {
     const int64_t total = (int64_t)n * jb;
@@ -1259,20 +1260,20 @@ __global__ void __launch_bounds__(256) comm_bcast_blockcol_kernel(CommPtrs p, in
       const size_t off = A_off + ((size_t)r * n + j + c) * sizeof(double);
       const double v = *reinterpret_cast<const double*>(src + off);
       for (int q = 0; q < world; ++q)
-        if (q != rank) *reinterpret_cast<double*>(p.peer[q] + off) = v;
+        if ((mask >> q) & 1u) *reinterpret_cast<double*>(p.peer[q] + off) = v;
     }
   }
   for (int64_t e = t0; e < jb; e += stride) {
     const size_t off = ipiv_off + (size_t)(j + e) * sizeof(int);
     const int v = *reinterpret_cast<const int*>(src + off);
     for (int q = 0; q < world; ++q)
-      if (q != rank) *reinterpret_cast<int*>(p.peer[q] + off) = v;
+      if ((mask >> q) & 1u) *reinterpret_cast<int*>(p.peer[q] + off) = v;
   }
   for (int64_t e = t0; e < (int64_t)NB * NB / 2; e += stride) {
     const size_t off = linv_off + (size_t)e * sizeof(double2);
     const double2 v = *reinterpret_cast<const double2*>(src + off);
     for (int q = 0; q < world; ++q)
-      if (q != rank) *reinterpret_cast<double2*>(p.peer[q] + off) = v;
+      if ((mask >> q) & 1u) *reinterpret_cast<double2*>(p.peer[q] + off) = v;
   }
   __threadfence_system();
   __syncthreads();
@@ -1282,8 +1283,17 @@ __global__ void __launch_bounds__(256) comm_bcast_blockcol_kernel(CommPtrs p, in
       *done = 0;  // launches of this kernel are stream-ordered
       __threadfence_system();
       for (int q = 0; q < world; ++q)
-        if (q != rank) st_release_sys(reinterpret_cast<unsigned*>(p.peer[q] + COMM_FLAG_OFF) + b, epoch);
+        if ((mask >> q) & 1u) st_release_sys(reinterpret_cast<unsigned*>(p.peer[q] + COMM_FLAG_OFF) + b, epoch);
     }
+  }
+}
+
+// <<<1, 32>>>: raise flag b on the peers in `mask` (after stream-ordered copy-engine transfers)
+__global__ void comm_signal_kernel(CommPtrs p, int world, unsigned mask, int b, unsigned epoch) {
+  const int q = threadIdx.x;
+  if (q < world && ((mask >> q) & 1u)) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned*>(p.peer[q] + COMM_FLAG_OFF) + b, epoch);
   }
 }
 
@@ -1445,14 +1455,49 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
   HPS_CUDA(cudaEventRecord(aux->fork, s0));
   HPS_CUDA(cudaStreamWaitEvent(s1, aux->fork, 0));
 
+  // HPS_DIST_SEND=kernel: SM stores into the peers' segments; default: the copy engines move the column
+  // (cudaMemcpy2DAsync on the peer mapping) and a one-warp kernel raises the flags.
+  static const bool send_by_kernel = [] { const char* e = std::getenv("HPS_DIST_SEND"); return e && e[0] == 'k'; }();
+  cudaStream_t s2 = aux->comm_stream;
+  auto send = [&](cudaStream_t s, int b, unsigned mask, unsigned* done) -> int {
+    if (!mask) return 0;
+    const int j = b * NB, jb = std::min(NB, n - j);
+    const size_t linv_off = L.linv_off + (size_t)b * NB * NB * sizeof(double);
+    prof_begin(PROF_COMM, s, (double)n * jb * 8.0 * __builtin_popcount(mask));
+    if (send_by_kernel) {
+      comm_bcast_blockcol_kernel<<<64, 256, 0, s>>>(c->ptrs, rank, world, mask, n, j, jb, L.ipiv_off, linv_off, L.A_off, b,
+                                                    epoch, done);
+    } else {
+      for (int q = 0; q < world; ++q) {
+        if (!((mask >> q) & 1u)) continue;
+        char* dst = c->ptrs.peer[q];
+        HPS_CUDA(cudaMemcpy2DAsync(dst + L.A_off + (size_t)j * sizeof(double), (size_t)n * sizeof(double),
+                                   c->local + L.A_off + (size_t)j * sizeof(double), (size_t)n * sizeof(double),
+                                   (size_t)jb * sizeof(double), n, cudaMemcpyDeviceToDevice, s));
+        HPS_CUDA(cudaMemcpyAsync(dst + L.ipiv_off + (size_t)j * sizeof(int), c->local + L.ipiv_off + (size_t)j * sizeof(int),
+                                 (size_t)jb * sizeof(int), cudaMemcpyDeviceToDevice, s));
+        HPS_CUDA(cudaMemcpyAsync(dst + linv_off, c->local + linv_off, (size_t)NB * NB * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, s));
+      }
+      comm_signal_kernel<<<1, 32, 0, s>>>(c->ptrs, world, mask, b, epoch);
+    }
+    prof_end(PROF_COMM, s);
+    HPS_LAUNCH_CHECK("block-column send");
+    return 0;
+  };
+  // The owner of the NEXT block column is served first, on the chain's stream; everybody else gets the column
+  // from the communication stream, off the critical path.
   auto factor_and_send = [&](int b) -> int {
     const int j = b * NB, jb = std::min(NB, n - j);
     HPS_TRY(factor_block_column(s1, 1, n, Am, j, jb, w, info));
     if (world > 1) {
-      comm_bcast_blockcol_kernel<<<64, 256, 0, s1>>>(c->ptrs, rank, world, n, j, jb, L.ipiv_off,
-                                                     L.linv_off + (size_t)b * NB * NB * sizeof(double), L.A_off, b, epoch,
-                                                     c->done);
-      HPS_LAUNCH_CHECK("comm_bcast_blockcol_kernel");
+      const int next = (b + 1) % world;
+      const unsigned all = ((1u << world) - 1u) & ~(1u << rank);
+      const unsigned first = (b + 1 < nblk && next != rank) ? (1u << next) : 0u;
+      HPS_CUDA(cudaEventRecord(aux->factored, s1));
+      HPS_CUDA(cudaStreamWaitEvent(s2, aux->factored, 0));
+      HPS_TRY(send(s1, b, first, c->done));
+      HPS_TRY(send(s2, b, all & ~first, c->done + 32));
     }
     return 0;
   };
@@ -1499,6 +1544,10 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
     HPS_CUDA(cudaStreamWaitEvent(s0, aux->panel_done[b & 1], 0));
     HPS_TRY(apply_owned(s0, b, own_next ? nb1 + 1 : nb1, true));
     HPS_CUDA(cudaEventRecord(aux->update_done[b & 1], s0));
+  }
+  if (world > 1) {  // the caller's stream also covers the sends still in flight on the communication stream
+    HPS_CUDA(cudaEventRecord(aux->sent, s2));
+    HPS_CUDA(cudaStreamWaitEvent(s0, aux->sent, 0));
   }
   if (n_rhs == 0) return 0;
   prof_begin(PROF_TRTRI, s0, (double)nblk * NB * NB * NB / 3);

@@ -98,3 +98,20 @@ def config3_problem(L):
 def config3_probe(n, salt):
     """Fixed probe vector of length n (operators are compared through their action on it)."""
     return np.random.default_rng(1000 + salt).normal(size=n)
+
+
+# ---- scattering coupling (SURVEY §8(f).1): seeded inputs shared by the golden generator and the tests ----
+def scattering_inputs(n_side=12, n_src=3, seed=7):
+    """A random complex ItI-like matrix R (spectrum away from 1), synthetic single / double layer matrices S, D
+    (the reference loads them from MATLAB files), boundary points of [-1,1]^2 in the S, E, N, W order and a few
+    plane-wave directions."""
+    rng = np.random.default_rng(seed)
+    n = 4 * n_side
+    R = 0.3 * (rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))) / np.sqrt(n)
+    S = 0.2 * (rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))) / np.sqrt(n)
+    D = 0.2 * (rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))) / np.sqrt(n)
+    t = (np.arange(n_side) + 0.5) / n_side * 2 - 1
+    one = np.ones(n_side)
+    pts = np.concatenate([np.stack([t, -one], 1), np.stack([one, t], 1), np.stack([-t, one], 1), np.stack([-one, -t], 1)])
+    dirs = rng.uniform(0, 2 * np.pi, size=n_src)
+    return R, S, D, pts, dirs, 5.0, 5.0  # k, eta

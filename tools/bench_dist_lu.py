@@ -1,0 +1,56 @@
+"""Distributed LU micro-benchmark (developer tool; run under torchrun): hps_lu_dist_run on a random n x n matrix with
+`ncols` right-hand-side columns per rank, per-category kernel times of rank 0.
+usage: torchrun ... tools/bench_dist_lu.py n ncols [reps]"""
+import ctypes
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, ".")
+from jaxhps_b200 import _dist, _lib
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+lib = _lib.load()
+n, ncols = int(sys.argv[1]), int(sys.argv[2])
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+g = torch.Generator(device="cpu").manual_seed(0)
+A0 = torch.randn(n, n, dtype=torch.float64, generator=g).to(dev)  # same matrix on every rank
+B0 = torch.randn(n, ncols, dtype=torch.float64, device=dev)
+comm = _dist.P2PComm.get(_lib, dev, rank, world, None)
+comm.ensure(comm.lu_segment_bytes(n))
+names = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny", "assemble", "p2p_send"]
+for it in range(reps + 1):
+    B = B0.clone()
+    _dist._copy_into_segment(comm.matrix_ptr(n), A0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    if it == reps:
+        lib.hps_prof_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _dist.p2p_lu_solve(_lib, dev, comm, n, [B], None)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"world={world} n={n} ncols/rank={ncols} send={os.environ.get('HPS_DIST_SEND', 'copy')} iter {it}: {float(t):.2f} ms" + ("  (profiler on)" if it == reps else ""), flush=True)
+pm, pw, pl = (ctypes.c_double * 16)(), (ctypes.c_double * 16)(), (ctypes.c_int64 * 16)()
+allk = ctypes.c_int64()
+lib.hps_prof_read(_lib.stream_ptr(), pm, pw, pl, ctypes.byref(allk))
+res = float((A0 @ B - B0).abs().max() / (A0.abs().max() * B.abs().max() * n))
+if rank == 0:
+    print("   rank 0 per category ms:", {nm: round(pm[i], 2) for i, nm in enumerate(names) if pl[i]},
+          "launches", {nm: pl[i] for i, nm in enumerate(names) if pl[i]}, "p2p GB/s", round(pw[8] / max(pm[8], 1e-9) * 1e-6, 1),
+          "residual", res, flush=True)
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()

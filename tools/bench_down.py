@@ -29,7 +29,7 @@ c = torch.from_numpy(1 + 0.1 * rng.normal(size=shp)).to(dev); src = torch.from_n
 pb = hps.PDEProblem(dom, source=src, D_xx_coefficients=c, D_yy_coefficients=c, D_zz_coefficients=c)
 lib.hps_prof_enable(1)
 ms = ev(lambda: local_solve_stage_uniform_3D_DtN(pb, device=dev, host_device=dev), 3)
-pm = (ctypes.c_double * 8)(); pw = (ctypes.c_double * 8)(); pl = (ctypes.c_int64 * 8)(); al = ctypes.c_int64()
+pm = (ctypes.c_double * 16)(); pw = (ctypes.c_double * 16)(); pl = (ctypes.c_int64 * 16)(); al = ctypes.c_int64()
 lib.hps_prof_read(_lib.stream_ptr(), pm, pw, pl, ctypes.byref(al))
 print(f"leaf stage 512 leaves: {ms:.1f} ms  ({512/ms*1e3:.0f} leaves/s, {512*3.99e9/ms*1e-9:.1f} TF/s lean)")
 print("per-category ms over 4 calls:", {n: round(pm[i], 1) for i, n in enumerate(["gemm", "panel", "trtri", "laswp", "inner", "gather", "skinny", "assemble"])})

@@ -20,7 +20,7 @@ need = ctypes.c_size_t()
 _lib.check(lib.hps_lu_solve_workspace(batch, n, ctypes.byref(need)), "ws")
 ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
 info = torch.zeros(batch, dtype=torch.int32, device=dev)
-names = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny", "assemble"]
+names = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny", "assemble", "p2p_send"]
 
 
 def run(A, B):
@@ -46,9 +46,9 @@ for it in range(reps + 1):
     ms = e0.elapsed_time(e1)
     fl = batch * (2 / 3 * n**3 + 2.0 * n * n * ncols)
     print(f"n={n} batch={batch} ncols={ncols} iter {it}: {ms:.3f} ms  {fl / ms * 1e-9:.2f} TF/s" + ("  (profiler on)" if it == reps else ""))
-pm = (ctypes.c_double * 8)()
-pw = (ctypes.c_double * 8)()
-pl = (ctypes.c_int64 * 8)()
+pm = (ctypes.c_double * 16)()
+pw = (ctypes.c_double * 16)()
+pl = (ctypes.c_int64 * 16)()
 allk = ctypes.c_int64()
 lib.hps_prof_read(_lib.stream_ptr(), pm, pw, pl, ctypes.byref(allk))
 lib.hps_prof_enable(0)

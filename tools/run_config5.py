@@ -199,7 +199,7 @@ def main():
             t_build = time.perf_counter() - t0
             rec["build_device_s"] = round(a_ev.elapsed_time(b_ev) / 1e3, 4)
             if args.prof and rep == args.repeat - 1:
-                pm, pw, pl = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_int64 * 8)()
+                pm, pw, pl = (ctypes.c_double * 16)(), (ctypes.c_double * 16)(), (ctypes.c_int64 * 16)()
                 allk = ctypes.c_int64()
                 _lib.load().hps_prof_read(_lib.stream_ptr(), pm, pw, pl, ctypes.byref(allk))
                 _lib.load().hps_prof_enable(0)
