@@ -279,6 +279,44 @@ class Runner:
         return self._dist.local_problem(self.dom, self.plan, source=s, D_xx_coefficients=c, D_yy_coefficients=c,
                                         D_zz_coefficients=c)
 
+    def step_factored(self, g):
+        """One build+solve in the opt-in factored-root (S-free) mode of the sharded driver (any world size)."""
+        from jaxhps_b200 import _dist
+
+        if self.plan is not None:
+            plan, pb = self.plan, self.pb_res
+        else:
+            if not hasattr(self, "_plan1"):
+                self._plan1 = _dist.SubtreePlan(self.L, 0, 1)
+                self._pb1 = _dist.local_problem(self.dom, self._plan1, source=self.s_dev, D_xx_coefficients=self.c_dev,
+                                                D_yy_coefficients=self.c_dev, D_zz_coefficients=self.c_dev)
+            plan, pb = self._plan1, self._pb1
+        pb.reset()
+        state = _dist.build_solver_sharded(pb, plan, self.dev, root_mode="factored")
+        return _dist.solve_sharded(pb, state, plan, g, self.dev)
+
+    def timed_factored(self, steps):
+        torch = self.torch
+        u = self.step_factored(self.g_dev)  # warm-up
+        err = self.error_vs_analytic(u)
+        del u
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.step_factored(self.g_dev)
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return {"ms_per_step": ms / steps, "leaves_per_s": self.n_leaves / (ms / steps * 1e-3), "steps": steps, "warmup": 1,
+                "max_rel_error_vs_analytic_solution": err,
+                "note": "opt-in root_mode='factored': the root S = -D^-1 C is not formed (the reference's S_lst[-1] does not "
+                        "exist in this mode); every solve applies D^-1 from the kept LU factors instead"}
+
     def step(self, pb, g, to_host, host_device=None):
         dev = self.dev
         pb.reset()
@@ -446,6 +484,14 @@ def run_ours(args, rank, world, local_rank):
                     "note": "build_solver(host_device='cpu') returns Y, v, S_lst, g_tilde_lst as NumPy arrays like the "
                             "reference's default; solve() copies them back (pageable memory)"}
 
+    # ---- the opt-in factored-root (S-free) mode, same problem (not the headline: S_lst[-1] is not produced) ----
+    factored = None
+    if args.factored:
+        try:
+            factored = R.timed_factored(args.steps)
+        except Exception as e:  # the mode needs the P2P segment (CUDA IPC); report instead of failing the bench
+            factored = {"unavailable": repr(e)[:300]}
+
     # ---- like-for-like with the CPU arm: the identical 8-leaf depth-1 sample on the GPU (single GPU) ----
     same_sample = None
     if world == 1:
@@ -483,6 +529,11 @@ def run_ours(args, rank, world, local_rank):
                      "step_tflops_per_gpu": lean_flops(4) * 1e-12 / (ms4 / 2 * 1e-3) / world,
                      "gemm_tflops_rank0": (pw4[0] / (pm4[0] * 1e-3) * 1e-12) if pm4[0] > 0 else None,
                      "kernel_ms_rank0": {name: round(pm4[i], 2) for i, name in enumerate(PROF_NAMES)}}
+        if args.factored:
+            try:
+                target_L4["factored_root"] = R4.timed_factored(2)
+            except Exception as e:
+                target_L4["factored_root"] = {"unavailable": repr(e)[:300]}
         del R4
 
     if dist is not None:
@@ -515,6 +566,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "leaves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e / args.steps},
         "e2e_host_resident": e2e_host,
+        "factored_root": factored,
         "same_config_sample": same_sample,
         "target_L4": target_L4,
         "gpu_launches": launches_timed,
@@ -549,6 +601,8 @@ def main():
     ap.add_argument("--L", type=int, default=3)
     ap.add_argument("--target-L4", dest="target_L4", type=int, default=1,
                     help="with 8 ranks: also time BASELINE's target size L=4 (1 warm-up + 2 steps) and embed it")
+    ap.add_argument("--factored", type=int, default=1,
+                    help="also time the opt-in factored-root (S-free) mode of the sharded driver")
     ap.add_argument("--host-resident", dest="host_resident", type=int, default=1,
                     help="single GPU: also time one step with the reference-default host_device='cpu'")
     args = ap.parse_args()

@@ -179,6 +179,11 @@ int hps_lu_dist_segment_bytes(int n, size_t* bytes);
 int hps_lu_dist_matrix_ptr(void* comm, int n, double** A);
 int hps_lu_dist_run(void* comm, void* stream, int n, int n_rhs, double* const* rhs, const int64_t* ld_rhs,
                     const int* ncols, void* ws, size_t ws_bytes, int* info);
+/* rhs[k] := A^-1 rhs[k] with the factors the last hps_lu_dist_run left in this rank's segment (local; every rank
+ * holds all of them).  The "factored root" mode of the sharded solver: the root S = -D^-1 C — two thirds of the
+ * build's flops at L >= 3 — is never formed, each solve applies D^-1 to -C g - h_int instead. */
+int hps_lu_dist_apply(void* comm, void* stream, int n, int n_rhs, double* const* rhs, const int64_t* ld_rhs,
+                      const int* ncols, void* ws, size_t ws_bytes);
 
 /* 2D quad merge, DtN (reference: merge/_uniform_2D_DtN.py:206-348).
  * T_in [4*n_merges][4m][4m] (children SW,SE,NE,NW; sides S,E,N,W), S [n][4m][8m],
@@ -276,6 +281,22 @@ int hps_down_quad_level(void* stream, int n_nodes, int m, int n_src, const doubl
 /* Leaf evaluation u = Y g + v (reference: down_pass/_uniform_3D_DtN.py:104-111). */
 int hps_leaf_apply(void* stream, int n_leaves, int n_c, int n_g, int n_src,
                    const double* Y, const double* g, const double* v, double* u);
+
+/* ---- interpolation between regular grids and the HPS grid (reference _interpolation_methods.py:24-340,
+ * Domain.interp_{from,to}_interior_points _domain.py:99-294).  bounds [n_leaves][2 dim] = xmin,xmax,ymin,ymax(,zmin,zmax);
+ * cheb [p] Chebyshev-Lobatto points on [-1,1], left end first; index tables map between the natural (x slowest)
+ * and the leaf's storage order; 2D stores y descending.
+ *   hps_interp_from_hps: f [n_leaves][p^dim][n_src] -> out [n_pts][n_src] at arbitrary points pts [n_pts][dim]
+ *     (owning leaf = first leaf in storage order whose closed box contains the point).
+ *   hps_interp_to_hps: values [n_x][n_y]([n_z]) on a tensor grid (from_d sample points, w_d their inverse
+ *     barycentric weights prod_{c != b}(x_b - x_c)) -> out [n_leaves][p^dim]. */
+int hps_interp_from_hps(void* stream, int dim, int n_leaves, int p, int n_src, int n_pts, const double* bounds,
+                        const double* cheb, const int* nat2leaf, const double* f, const double* pts, double* out);
+int hps_interp_to_hps_workspace(int dim, int n_leaves, int p, int n_x, int n_y, int n_z, size_t* bytes);
+int hps_interp_to_hps(void* stream, int dim, int n_leaves, int p, int n_x, int n_y, int n_z, const double* bounds,
+                      const double* cheb, const double* from_x, const double* from_y, const double* from_z,
+                      const double* w_x, const double* w_y, const double* w_z, const int* leaf2nat,
+                      const double* values, double* out, void* ws, size_t ws_bytes);
 
 /* ---- adaptive (non-uniform) trees, ONE NODE per call ---------------------------------------
  * reference: merge/_adaptive_3D_DtN.py:150-347 + merge/_utils_adaptive_3D_DtN.py:179-881,

@@ -332,16 +332,23 @@ class CudaOps:
     #: tests: run the step-wise (distributed) factorisation even on a single rank
     FORCE_DIST_LU = False
 
-    def root_solve(self, Dblk_all, hblk_all, Cblk_loc, first_child: int, rank: int = 0, world: int = 1, group=None):
+    def root_solve(self, Dblk_all, hblk_all, Cblk_loc, first_child: int, rank: int = 0, world: int = 1, group=None,
+                   root_mode: str = "S"):
         """This rank's columns of the root S (child-major) and the full g~.  Single rank or small root:
-        ``hps_root_solve_oct`` (replicated LU).  Otherwise the LU of D is distributed by block columns
-        with one NCCL broadcast per block column (``hps_lu_dist_*``)."""
+        ``hps_root_solve_oct`` (replicated LU).  Otherwise the LU of D is distributed by block columns over the
+        library's P2P communicator (``hps_lu_dist_run``; NCCL-broadcast fallback ``hps_lu_dist_*``).
+        ``root_mode="factored"``: S is not formed — returns ``-C_r`` in its place and leaves the factors of D in
+        the communicator's segment for :meth:`root_apply`."""
         import ctypes
 
         lib = self._lib.load()
         n_local, n3, _ = Cblk_loc.shape
         m = n3 // 3
         n_src = hblk_all.shape[-1]
+        if root_mode == "factored":
+            if not USE_P2P:
+                raise ValueError("root_mode='factored' keeps the factors in the P2P segment (HPS_DIST_P2P=0 disables it)")
+            return self._root_solve_distributed(Dblk_all, hblk_all, Cblk_loc, first_child, rank, world, group, True)
         if (world > 1 or self.FORCE_DIST_LU) and 12 * m >= self.DIST_LU_MIN_N:
             return self._root_solve_distributed(Dblk_all, hblk_all, Cblk_loc, first_child, rank, world, group)
         S_r = self.empty((12 * m, n3 * n_local))
@@ -357,7 +364,24 @@ class CudaOps:
         self._lib.check_info(info, "root merge")
         return S_r, g
 
-    def _root_solve_distributed(self, Dblk_all, hblk_all, Cblk_loc, first_child, rank, world, group):
+    def root_apply(self, x, rank: int, world: int, group=None):
+        """In place ``x := D^-1 x`` with the factors of the last factored root build (``hps_lu_dist_apply``)."""
+        import ctypes
+
+        lib, _lib = self._lib.load(), self._lib
+        comm = P2PComm.get(_lib, self.dev, rank, world, group)
+        n = x.shape[0]
+        need = ctypes.c_size_t()
+        _lib.check(lib.hps_lu_solve_workspace(1, n, ctypes.byref(need)), "workspace query")
+        ws = _lib.workspace(need.value, self.dev)
+        ptrs = (ctypes.c_void_p * 1)(x.data_ptr())
+        lds = (ctypes.c_int64 * 1)(x.shape[1])
+        ncs = (ctypes.c_int * 1)(x.shape[1])
+        _lib.check(lib.hps_lu_dist_apply(comm.handle, _lib.stream_ptr(), n, 1, ptrs, lds, ncs, ws.data_ptr(), ws.numel()),
+                   "hps_lu_dist_apply")
+        return x
+
+    def _root_solve_distributed(self, Dblk_all, hblk_all, Cblk_loc, first_child, rank, world, group, factored=False):
         """Distributed LU of the root D: block column b is factored by rank b % world, broadcast, and
         applied by every rank to the block columns it owns; then local solves of the rank's columns."""
         lib = self._lib.load()
@@ -377,7 +401,8 @@ class CudaOps:
                                            hblk_all.data_ptr(), Cblk_loc.data_ptr(), comm.matrix_ptr(n), S_r.data_ptr(),
                                            g.data_ptr())
             _lib.check(rc, "hps_root_assemble_oct")
-            p2p_lu_solve(_lib, self.dev, comm, n, [S_r, g], group)
+            # factored root: only g~ goes through the solve; S_r keeps -C_r for the solves
+            p2p_lu_solve(_lib, self.dev, comm, n, [g] if factored else [S_r, g], group)
             return S_r, g
         D = self.empty((n, n))
         rc = lib.hps_root_assemble_oct(_lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),
@@ -438,17 +463,28 @@ class ShardedState:
         self.S_root_cols = None  # (12m, 3m * octants_per_rank): columns of this rank's children
         self.g_tilde_root = None  # (12m, n_src)
         self.col_index = None  # where those columns sit in the root's boundary vector
+        self.root_mode = "S"  # "factored": S_root_cols holds -C_r and the factors of D stay in the P2P segment
 
 
 def _group_ok(plan: SubtreePlan) -> bool:
     return plan.world > 1 and dist.is_available() and dist.is_initialized()
 
 
-def build_solver_sharded(pde_problem: PDEProblem, plan: SubtreePlan, device=None, ops=None, group=None) -> ShardedState:
+def build_solver_sharded(pde_problem: PDEProblem, plan: SubtreePlan, device=None, ops=None, group=None,
+                         root_mode: str = "S") -> ShardedState:
     """Local solves + merges on this rank's subtrees, all-gather of the subtree roots, column-sharded
-    root merge.  ``pde_problem`` holds this rank's leaves only (see :func:`local_problem`)."""
+    root merge.  ``pde_problem`` holds this rank's leaves only (see :func:`local_problem`).
+
+    ``root_mode="S"`` (default) forms the root ``S`` like the reference's ``S_lst[-1]``.  ``root_mode="factored"``
+    (opt-in; CUDA ops only) keeps ``P D = L U`` instead and applies ``D^-1`` to ``-C g - h_int`` in every solve:
+    the right-hand-side substitutions that form ``S`` — 28 of the 41.7 TFLOP of an L=3 build, 226 of 320 per rank
+    at L=4 on 8 GPUs — disappear from the build at the price of one pass over the factors per solve.  The factors
+    live in the process's P2P segment: the state is valid until the next sharded build on this process."""
+    if root_mode not in ("S", "factored"):
+        raise ValueError("root_mode must be 'S' or 'factored'")
     ops = ops or CudaOps(device)
     st = ShardedState()
+    st.root_mode = root_mode
     Y, T, v, h = ops.local_solve(pde_problem)
     st.Y, st.v = Y, v
     n_oct = plan.octants_per_rank
@@ -473,11 +509,29 @@ def build_solver_sharded(pde_problem: PDEProblem, plan: SubtreePlan, device=None
     del Dblk
     if D_all.numel() * 8 > (4 << 30) and D_all.is_cuda:
         torch.cuda.empty_cache()  # the root D needs one large block; give freed subtree buffers back first
-    st.S_root_cols, g = ops.root_solve(D_all, h_all, Cblk, plan.first_octant, plan.rank, plan.world, group)
+    if root_mode == "factored":
+        st.S_root_cols, g = ops.root_solve(D_all, h_all, Cblk, plan.first_octant, plan.rank, plan.world, group,
+                                           root_mode="factored")
+    else:
+        st.S_root_cols, g = ops.root_solve(D_all, h_all, Cblk, plan.first_octant, plan.rank, plan.world, group)
     st.g_tilde_root = g
     st.multi = multi
     st.col_index = ops.tensor(child_column_index(plan.first_octant, n_oct, m)).to(torch.int64)
     return st
+
+
+def root_S_action(st: ShardedState, plan: SubtreePlan, x, device=None, ops=None, group=None):
+    """``S_root @ x`` for a boundary vector / matrix ``x`` in the root's face order, in either root mode (the
+    quantity the reference stores as ``S_lst[-1]``, probed without forming it)."""
+    ops = ops or CudaOps(device)
+    xt = ops.tensor(x)
+    xt = xt.reshape(xt.shape[0], -1)
+    part = ops.matvec(st.S_root_cols, xt.index_select(0, st.col_index).contiguous())
+    if plan.world > 1:
+        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+    if st.root_mode == "factored":
+        part = ops.root_apply(part.contiguous(), plan.rank, plan.world, group)
+    return part
 
 
 def solve_sharded(pde_problem: PDEProblem, st: ShardedState, plan: SubtreePlan, boundary_data, device=None, ops=None,
@@ -493,6 +547,8 @@ def solve_sharded(pde_problem: PDEProblem, st: ShardedState, plan: SubtreePlan, 
     part = ops.matvec(st.S_root_cols, g_ext.index_select(0, st.col_index).contiguous())
     if plan.world > 1:
         dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+    if st.root_mode == "factored":  # part = -C g_ext: every rank applies D^-1 with its copy of the factors
+        part = ops.root_apply(part.contiguous(), plan.rank, plan.world, group)
     g_int = part + gt
     kids = ops.root_scatter(g_ext.contiguous(), g_int.contiguous())
     mine = kids[plan.first_octant : plan.first_octant + plan.octants_per_rank]

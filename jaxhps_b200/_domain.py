@@ -67,9 +67,16 @@ class Domain:
         fn = uniform_leaf_bounds_2D if self.bool_2D else uniform_leaf_bounds_3D
         return fn(self.root, self.L)
 
-    def interp_to_interior_points(self, values, sample_points_x, sample_points_y, sample_points_z=None) -> np.ndarray:
+    def interp_to_interior_points(self, values, sample_points_x, sample_points_y, sample_points_z=None, device=None,
+                                  host_device=None):
         """Values on a regular grid (``meshgrid(..., indexing="ij")``) -> samples on the HPS grid,
-        shape ``(n_leaves, p^d)`` (reference `_domain.py:99-208`)."""
+        shape ``(n_leaves, p^d)`` (reference `_domain.py:99-208`).  ``device=<cuda device>`` runs the CUDA kernels
+        (``hps_interp_to_hps``) and returns a tensor on that device (NumPy when ``host_device="cpu"``)."""
+        if device is not None:
+            from ._interpolation_methods import interp_to_hps_device
+
+            return interp_to_hps_device(self._leaf_bounds(), values, self.p, sample_points_x, sample_points_y,
+                                        sample_points_z, device=device, host_device=host_device)
         values = np.asarray(values)
         if values.ndim == 2:
             assert sample_points_z is None and values.shape == (len(sample_points_x), len(sample_points_y))
@@ -81,9 +88,17 @@ class Domain:
     def interp_to_boundary_points(self, *args, **kwargs):
         raise NotImplementedError("interp_to_boundary_points is not implemented yet.")  # as in the reference
 
-    def interp_from_interior_points(self, samples, eval_points_x, eval_points_y, eval_points_z=None):
+    def interp_from_interior_points(self, samples, eval_points_x, eval_points_y, eval_points_z=None, device=None,
+                                    host_device=None):
         """Samples on the HPS grid ``(n_leaves, p^d)`` -> values on a regular grid and the target points
-        (reference `_domain.py:218-294`)."""
+        (reference `_domain.py:218-294`).  ``device=<cuda device>`` runs the CUDA kernel (``hps_interp_from_hps``);
+        the values then stay on that device unless ``host_device="cpu"``."""
+        if device is not None:
+            from ._interpolation_methods import interp_from_hps_device
+
+            assert (eval_points_z is None) == self.bool_2D
+            return interp_from_hps_device(self._leaf_bounds(), self.p, samples, eval_points_x, eval_points_y, eval_points_z,
+                                          device=device, host_device=host_device)
         samples = np.asarray(samples)
         if self.bool_2D:
             assert eval_points_z is None

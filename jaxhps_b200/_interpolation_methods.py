@@ -1,4 +1,4 @@
-"""Interpolation between regular grids and the HPS grid (host side, NumPy).
+"""Interpolation between regular grids and the HPS grid: host side (NumPy) and device side (CUDA, ``*_device``).
 
 Behavioural restatement of `src/jaxhps/_interpolation_methods.py:24-340` — the pre/post-processing
 step on either side of the build+solve path in every example.  The tensor
@@ -126,3 +126,106 @@ def interp_to_hps_3D(leaf_bounds: np.ndarray, values: np.ndarray, p: int, from_x
         Ix, Iy, Iz = _factor_rows(fx, to[0][leaf]), _factor_rows(fy, to[1][leaf]), _factor_rows(fz, to[2][leaf])
         out[leaf] = np.einsum("ia,jb,kc,abc->ijk", Ix, Iy, Iz, values, optimize=True).reshape(-1)[r]
     return out
+
+
+# =====================================================================================
+# Device path (``hps_interp_from_hps`` / ``hps_interp_to_hps`` in libhps_b200.so; csrc/interp.cu)
+# =====================================================================================
+
+
+def _bary_weights_inv_host(x: np.ndarray) -> np.ndarray:
+    from .quadrature import _bary_weights_inv
+
+    return np.ascontiguousarray(_bary_weights_inv(np.asarray(x, dtype=np.float64)))
+
+
+def _index_tables(p: int, dim: int):
+    """(nat2leaf, leaf2nat): position in the leaf's storage order of each natural index, and the inverse."""
+    r = rearrange_indices_ext_int_2D(p) if dim == 2 else rearrange_indices_ext_int_3D(p)
+    leaf2nat = np.asarray(r, dtype=np.int32)
+    nat2leaf = np.empty_like(leaf2nat)
+    nat2leaf[leaf2nat] = np.arange(leaf2nat.shape[0], dtype=np.int32)
+    return nat2leaf, leaf2nat
+
+
+def interp_from_hps_device(leaf_bounds, p: int, f_evals, x_vals, y_vals, z_vals=None, device=None, host_device=None):
+    """Device version of :func:`interp_from_hps_2D` / :func:`interp_from_hps_3D`: same return convention
+    ``(vals, target_pts)``; ``vals`` is a torch tensor on the device unless ``host_device`` asks for NumPy."""
+    import torch
+
+    from . import _lib
+
+    dev = _lib.require_cuda(device)
+    lib = _lib.load()
+    dim = 2 if z_vals is None else 3
+    x_vals, y_vals = np.asarray(x_vals, float), np.asarray(y_vals, float)
+    if dim == 2:
+        X, Y = np.meshgrid(x_vals, y_vals)
+        target_pts = np.stack([X, Y], axis=2)
+        pts = target_pts.reshape(-1, 2)
+        shape = (x_vals.shape[0], y_vals.shape[0])
+    else:
+        z_vals = np.asarray(z_vals, float)
+        X, Y, Z = np.meshgrid(x_vals, y_vals, z_vals)
+        target_pts = np.stack([X, Y, Z], axis=3)
+        pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=-1)
+        shape = (x_vals.shape[0], y_vals.shape[0], z_vals.shape[0])
+    with torch.cuda.device(dev):
+        f = _lib.to_device(f_evals, dev)
+        multi = f.ndim == 3
+        f3 = f if multi else f.unsqueeze(-1)
+        n_leaves, npts_leaf, n_src = f3.shape
+        nat2leaf, _ = _index_tables(p, dim)
+        b = _lib.to_device(np.ascontiguousarray(np.asarray(leaf_bounds, float)), dev)
+        cheb = _lib.to_device(chebyshev_points(p), dev)
+        tbl = torch.from_numpy(nat2leaf).to(dev)
+        pd = _lib.to_device(np.ascontiguousarray(pts), dev)
+        out = torch.empty((pts.shape[0], n_src), dtype=torch.float64, device=dev)
+        rc = lib.hps_interp_from_hps(_lib.stream_ptr(), dim, n_leaves, p, n_src, pts.shape[0], b.data_ptr(), cheb.data_ptr(),
+                                     tbl.data_ptr(), f3.contiguous().data_ptr(), pd.data_ptr(), out.data_ptr())
+        _lib.check(rc, "hps_interp_from_hps")
+        vals = out.reshape(shape + (n_src,)) if multi else out[:, 0].reshape(shape)
+        return _lib.to_result(vals, host_device if host_device is not None else dev), target_pts
+
+
+def interp_to_hps_device(leaf_bounds, values, p: int, from_x, from_y, from_z=None, device=None, host_device=None):
+    """Device version of :func:`interp_to_hps_2D` / :func:`interp_to_hps_3D`: ``(n_leaves, p^d)``."""
+    import ctypes
+
+    import torch
+
+    from . import _lib
+
+    dev = _lib.require_cuda(device)
+    lib = _lib.load()
+    dim = 2 if from_z is None else 3
+    with torch.cuda.device(dev):
+        V = _lib.to_device(values, dev)
+        b_h = np.ascontiguousarray(np.asarray(leaf_bounds, float))
+        n_leaves = b_h.shape[0]
+        fr = [np.asarray(a, float) for a in ((from_x, from_y) if dim == 2 else (from_x, from_y, from_z))]
+        if tuple(V.shape) != tuple(a.shape[0] for a in fr):
+            raise ValueError(f"values of shape {tuple(V.shape)} do not match the sample grids {[a.shape[0] for a in fr]}")
+        b = _lib.to_device(b_h, dev)
+        cheb = _lib.to_device(chebyshev_points(p), dev)
+        _, leaf2nat = _index_tables(p, dim)
+        tbl = torch.from_numpy(leaf2nat).to(dev)
+        fd = [_lib.to_device(np.ascontiguousarray(a), dev) for a in fr]
+        wd = [_lib.to_device(_bary_weights_inv_host(a), dev) for a in fr]
+        n = [a.shape[0] for a in fr] + ([1] if dim == 2 else [])
+        out = torch.empty((n_leaves, p**dim), dtype=torch.float64, device=dev)
+        # leaves are processed in slices so that the per-leaf intermediates stay bounded
+        one = ctypes.c_size_t()
+        _lib.check(lib.hps_interp_to_hps_workspace(dim, 1, p, n[0], n[1], n[2], ctypes.byref(one)), "workspace query")
+        step = int(max(1, min(n_leaves, (4 << 30) // max(1, one.value), _lib.MAX_BATCH)))
+        need = ctypes.c_size_t()
+        _lib.check(lib.hps_interp_to_hps_workspace(dim, step, p, n[0], n[1], n[2], ctypes.byref(need)), "workspace query")
+        ws = _lib.workspace(need.value, dev)
+        for s0 in range(0, n_leaves, step):
+            s1 = min(n_leaves, s0 + step)
+            rc = lib.hps_interp_to_hps(_lib.stream_ptr(), dim, s1 - s0, p, n[0], n[1], n[2], b[s0:s1].data_ptr(), cheb.data_ptr(),
+                                       fd[0].data_ptr(), fd[1].data_ptr(), fd[2].data_ptr() if dim == 3 else None,
+                                       wd[0].data_ptr(), wd[1].data_ptr(), wd[2].data_ptr() if dim == 3 else None,
+                                       tbl.data_ptr(), V.contiguous().data_ptr(), out[s0:s1].data_ptr(), ws.data_ptr(), ws.numel())
+            _lib.check(rc, "hps_interp_to_hps")
+        return _lib.to_result(out, host_device if host_device is not None else dev)

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "hps_lu_dist_segment_bytes": (_i, [_i, ctypes.POINTER(_sz)]),
     "hps_lu_dist_matrix_ptr": (_i, [_p, _i, ctypes.POINTER(_p)]),
     "hps_lu_dist_run": (_i, [_p, _p, _i, _i, ctypes.POINTER(_p), ctypes.POINTER(_l), ctypes.POINTER(_i), _p, _sz, _p]),
+    "hps_lu_dist_apply": (_i, [_p, _p, _i, _i, ctypes.POINTER(_p), ctypes.POINTER(_l), ctypes.POINTER(_i), _p, _sz]),
     "hps_down_oct_scatter": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "hps_merge_quad_dtn_level_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),
     "hps_merge_quad_dtn_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
@@ -76,6 +77,9 @@ _SIGNATURES = {
     "hps_down_oct_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "hps_down_quad_level": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "hps_leaf_apply": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "hps_interp_from_hps": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "hps_interp_to_hps_workspace": (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(_sz)]),
+    "hps_interp_to_hps": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz]),
     "hps_adaptive_compress_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),
     "hps_adaptive_compress": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _sz]),
     "hps_merge_adaptive_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),

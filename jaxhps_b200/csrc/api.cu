@@ -243,6 +243,13 @@ int hps_lu_dist_run(void* comm, void* stream, int n, int n_rhs, double* const* r
   for (int k = 0; k < n_rhs; ++k) d[k] = RhsDesc{rhs[k], ld_rhs[k], 0, ncols[k]};
   return lu_dist_run(static_cast<Comm*>(comm), static_cast<cudaStream_t>(stream), n, n_rhs, d, ws, ws_bytes, info);
 }
+int hps_lu_dist_apply(void* comm, void* stream, int n, int n_rhs, double* const* rhs, const int64_t* ld_rhs, const int* ncols,
+                      void* ws, size_t ws_bytes) {
+  if (n_rhs < 0 || n_rhs > 4) return fail_arg(4, "n_rhs must be in [0, 4]");
+  RhsDesc d[4];
+  for (int k = 0; k < n_rhs; ++k) d[k] = RhsDesc{rhs[k], ld_rhs[k], 0, ncols[k]};
+  return lu_dist_apply(static_cast<Comm*>(comm), static_cast<cudaStream_t>(stream), n, n_rhs, d, ws, ws_bytes);
+}
 int hps_down_oct_scatter(void* stream, int n_nodes, int m, int n_src, const double* g_ext, const double* g_int,
                          double* g_children) {
   return down_oct_scatter(static_cast<cudaStream_t>(stream), n_nodes, m, n_src, g_ext, g_int, g_children);
@@ -349,6 +356,22 @@ int hps_leaf_apply(void* stream, int n_leaves, int n_c, int n_g, int n_src, cons
                       (int64_t)n_g * n_src, v, n_src, (int64_t)n_c * n_src, u, n_src, (int64_t)n_c * n_src, n_leaves);
 }
 
+int hps_interp_from_hps(void* stream, int dim, int n_leaves, int p, int n_src, int n_pts, const double* bounds,
+                        const double* cheb, const int* nat2leaf, const double* f, const double* pts, double* out) {
+  return interp_from_hps(static_cast<cudaStream_t>(stream), dim, n_leaves, p, n_src, n_pts, bounds, cheb, nat2leaf, f, pts, out);
+}
+int hps_interp_to_hps_workspace(int dim, int n_leaves, int p, int n_x, int n_y, int n_z, size_t* bytes) {
+  if (!bytes) return fail_arg(7, "null output pointer");
+  *bytes = interp_to_hps_ws_bytes(dim, n_leaves, p, n_x, n_y, n_z);
+  return 0;
+}
+int hps_interp_to_hps(void* stream, int dim, int n_leaves, int p, int n_x, int n_y, int n_z, const double* bounds,
+                      const double* cheb, const double* from_x, const double* from_y, const double* from_z,
+                      const double* w_x, const double* w_y, const double* w_z, const int* leaf2nat, const double* values,
+                      double* out, void* ws, size_t ws_bytes) {
+  return interp_to_hps(static_cast<cudaStream_t>(stream), dim, n_leaves, p, n_x, n_y, n_z, bounds, cheb, from_x, from_y, from_z,
+                       w_x, w_y, w_z, leaf2nat, values, out, ws, ws_bytes);
+}
 int hps_adaptive_compress_workspace(int n, int n_out_panels, int npp, size_t* bytes) {
   if (!bytes) return fail_arg(4, "null output pointer");
   *bytes = adaptive_compress_ws_bytes(n, n_out_panels * npp);

@@ -130,6 +130,7 @@ int comm_attach(Comm* c, const void* handles);
 size_t lu_dist_segment_bytes(int n);
 int lu_dist_matrix_ptr(Comm* c, int n, double** A);
 int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, void* ws, size_t ws_bytes, int* info);
+int lu_dist_apply(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, void* ws, size_t ws_bytes);
 
 // ---- stages (leaf.cu / merge.cu) --------------------------------------------------------
 size_t local_solve_workspace_bytes(int dim, int n_leaves, int p, int q);
@@ -200,5 +201,14 @@ int merge_adaptive_assemble(cudaStream_t st, int npp, int n_src, int n_child, co
 int down_adaptive(cudaStream_t st, int npp, int n_src, int n_int, int n_ext, const double* S, const double* g_ext,
                   const double* gt, int n_child, double* const* g_child, int n_tbl, const int* tbl,
                   const double* L_refine, void* ws);
+
+// ---- interpolation regular grid <-> HPS grid (interp.cu) ----------------------------------------
+int interp_from_hps(cudaStream_t st, int dim, int n_leaves, int p, int n_src, int n_pts, const double* bounds,
+                    const double* cheb, const int* nat2leaf, const double* f, const double* pts, double* out);
+size_t interp_to_hps_ws_bytes(int dim, int n_leaves, int p, int n_x, int n_y, int n_z);
+int interp_to_hps(cudaStream_t st, int dim, int n_leaves, int p, int n_x, int n_y, int n_z, const double* bounds,
+                  const double* cheb, const double* from_x, const double* from_y, const double* from_z, const double* w_x,
+                  const double* w_y, const double* w_z, const int* leaf2nat, const double* values, double* out, void* ws,
+                  size_t ws_bytes);
 
 }  // namespace hps

@@ -1298,14 +1298,15 @@ __global__ void comm_signal_kernel(CommPtrs p, int world, unsigned mask, int b, 
 }
 
 struct DistLayout {
-  size_t ipiv_off, linv_off, A_off, bytes;
+  size_t ipiv_off, linv_off, uinv_off, A_off, bytes;
 };
 DistLayout dist_layout(int n) {
   const size_t nblk = (n + NB - 1) / NB;
   DistLayout L;
   L.ipiv_off = COMM_PAYLOAD_OFF;
   L.linv_off = L.ipiv_off + align_up((size_t)n * sizeof(int), 256);
-  L.A_off = L.linv_off + align_up(nblk * NB * NB * sizeof(double), 256);
+  L.uinv_off = L.linv_off + align_up(nblk * NB * NB * sizeof(double), 256);  // local only (never sent)
+  L.A_off = L.uinv_off + align_up(nblk * NB * NB * sizeof(double), 256);
   L.bytes = L.A_off + align_up((size_t)n * n * sizeof(double), 256);
   return L;
 }
@@ -1436,6 +1437,7 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
   // pivots and inverted diagonal blocks live in the symmetric segment: their owners store them there
   w.ipiv = reinterpret_cast<int*>(c->local + L.ipiv_off);
   w.Linv = reinterpret_cast<double*>(c->local + L.linv_off);
+  w.Uinv = reinterpret_cast<double*>(c->local + L.uinv_off);  // stays with the factors for lu_dist_apply
   double* A = reinterpret_cast<double*>(c->local + L.A_off);
   const Mat Am{A, n, 0};
   const int rank = c->rank, world = c->world;
@@ -1549,12 +1551,41 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
     HPS_CUDA(cudaEventRecord(aux->sent, s2));
     HPS_CUDA(cudaStreamWaitEvent(s0, aux->sent, 0));
   }
-  if (n_rhs == 0) return 0;
   prof_begin(PROF_TRTRI, s0, (double)nblk * NB * NB * NB / 3);
   trtri_kernel<false><<<dim3(nblk, 1), TRI_THREADS, TRTRI_SMEM, s0>>>(A, n, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
   prof_end(PROF_TRTRI, s0);
   HPS_LAUNCH_CHECK("trtri_kernel<upper>");
   for (int k = 0; k < n_rhs; ++k) HPS_TRY(trsm_upper(s0, 1, n, Am, w, rhs[k], 0, n));
+  return 0;
+}
+
+// rhs[k] := A^-1 rhs[k] with the factors a previous lu_dist_run left in this rank's segment (every rank holds
+// all of them): the "factored root" mode of the sharded solver, where the root S = -D^-1 C is never formed and
+// each solve applies D^-1 instead.  Forward substitution in the order of the factorisation (interchanges of block
+// b, its inverted diagonal block, rank-jb update of the rows below), then the recursive backward substitution.
+// Purely local; ws: lu_workspace_bytes(1, n).
+int lu_dist_apply(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, void* ws, size_t ws_bytes) {
+  if (!c || !c->local) return fail_arg(1, "communicator has no segment");
+  if (n <= 0 || n_rhs <= 0) return 0;
+  const DistLayout L = dist_layout(n);
+  if (c->bytes < L.bytes) return fail_arg(3, "segment too small for n");
+  Arena ar(ws, ws_bytes);
+  LuWorkspace w;
+  if (!carve(ar, 1, n, w)) return fail_arg(6, "lu_dist_apply: workspace too small");
+  HPS_TRY(configure_lu_kernels());
+  w.ipiv = reinterpret_cast<int*>(c->local + L.ipiv_off);
+  w.Linv = reinterpret_cast<double*>(c->local + L.linv_off);
+  w.Uinv = reinterpret_cast<double*>(c->local + L.uinv_off);
+  double* A = reinterpret_cast<double*>(c->local + L.A_off);
+  const Mat Am{A, n, 0};
+  const int nblk = (n + NB - 1) / NB;
+  for (int k = 0; k < n_rhs; ++k) {
+    for (int b = 0; b < nblk; ++b) {
+      const int j = b * NB, jb = std::min(NB, n - j);
+      HPS_TRY(dist_apply(st, n, Am, j, jb, w, b, rhs[k].ptr, rhs[k].ld, 0, rhs[k].ncols, 1));
+    }
+    HPS_TRY(trsm_upper(st, 1, n, Am, w, rhs[k], 0, n));
+  }
   return 0;
 }
 

@@ -57,3 +57,35 @@ def test_config3_every_stage_matches_the_oracle_fixture(L):
     print(f"config 3 L={L}: " + ", ".join(f"{k} {e:.1e}" for k, e in errs.items()))
     bad = {k: e for k, e in errs.items() if not e < TOL}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("root_mode", ["S", "factored"])
+@pytest.mark.parametrize("L", [2, 3])
+def test_config3_sharded_driver_root_modes(L, root_mode):
+    """The sharded driver on one rank (root merge through hps_lu_dist_run on the P2P segment) in both root modes:
+    ``S`` (root S formed) and ``factored`` (S-free: LU of D kept, D^-1 applied per solve).  The action of the root S
+    on the fixture's probe vector, the root g~ and the solution must match the oracle fixture at 1e-10."""
+    from jaxhps_b200 import _dist
+
+    path = os.path.join(GOLDEN_DIR, f"config3_oracle_probe_L{L}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    G = dict(np.load(path))
+    u_stride = int(G["meta"][2])
+    dev = torch.device("cuda:0")
+    pb_full, bdry = config3_problem(L)
+    plan = _dist.SubtreePlan(L, 0, 1)
+    co = {k: getattr(pb_full, k) for k in ("D_xx_coefficients", "D_yy_coefficients", "D_zz_coefficients", "D_x_coefficients",
+                                           "I_coefficients")}
+    pb = _dist.local_problem(pb_full.domain, plan, source=pb_full.source, **co)
+    ops = _dist.CudaOps(dev)
+    ops.FORCE_DIST_LU, ops.DIST_LU_MIN_N = True, 0
+    st = _dist.build_solver_sharded(pb, plan, ops=ops, root_mode=root_mode)
+    k = L - 1
+    x = config3_probe(G[f"S_x_{k}"].shape[-1] * 2, 1)  # the root level's probe (salt = level 1), length 24 m
+    Sx = _dist.root_S_action(st, plan, x, ops=ops)[:, 0]
+    errs = {"S_x_root": _rel(Sx, G[f"S_x_{k}"][0]), "g_tilde_root": _rel(st.g_tilde_root[:, 0], G[f"g_tilde_{k}"][0])}
+    u = _dist.solve_sharded(pb, st, plan, bdry, ops=ops)
+    errs["u"] = float((u.reshape(-1)[::u_stride] - torch.as_tensor(G["u_probe"], device=dev)).abs().max() / float(G["u_max"]))
+    print(f"config 3 L={L} sharded root_mode={root_mode}: " + ", ".join(f"{a} {e:.1e}" for a, e in errs.items()))
+    assert all(e < TOL for e in errs.values()), errs
