@@ -21,9 +21,7 @@ from adaptive_cases import ADAPTIVE_CASES, boundary_fn, internal_nodes
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
-# the two random-tree fixtures were added after the round's GPU budget was spent: they are CPU-checked (oracle, host
-# layer, plan tables) and join the GPU parametrisation once they have been run on a GPU
-GPU_CASES = sorted(k for k in ADAPTIVE_CASES if not k.endswith("_random"))
+GPU_CASES = sorted(ADAPTIVE_CASES)
 
 
 @pytest.mark.parametrize("name", GPU_CASES)
