@@ -556,13 +556,13 @@ __global__ void inner_trsm_kernel(double* A, int64_t lda, int64_t sA, int jj, in
     if (r < ib) xp[(int64_t)r * lda] = x[r];
 }
 
-// Dense inverse of the nb x nb triangular block at A[j,j] into W (ld = NB, zero elsewhere).
-// LOWER: unit lower triangle.  !LOWER: upper triangle with its diagonal.
+// Dense inverse of the nb x nb UNIT-LOWER triangular block at A[j,j] into W (ld = NB, zero elsewhere).
 // Recursive blocked inversion inside one CTA: the four 32x32 diagonal blocks are inverted
 // column-per-lane by four warps with no barrier at all, then the off-diagonal blocks follow from
-//   inv([[A,0],[C,B]]) = [[A^-1, 0], [-B^-1 C A^-1, B^-1]]   (mirrored for the upper case)
+//   inv([[A,0],[C,B]]) = [[A^-1, 0], [-B^-1 (C A^-1), B^-1]]
 // as small shared-memory products at the 32 and 64 level: 3 barriers-separated phases instead of
-// the 128 sequential column sweeps of an unblocked trti2.
+// the 128 sequential column sweeps of an unblocked trti2.  (Partial pivoting keeps these blocks well
+// conditioned; the upper blocks need the column-wise kernel below.)
 constexpr int TRI_THREADS = 256;
 constexpr int TRI_LD = NB + 1;
 
@@ -577,9 +577,8 @@ __device__ __forceinline__ void smem_mm(double* dst, int ldd, const double* A, i
   }
 }
 
-template <bool LOWER>
-__global__ void __launch_bounds__(TRI_THREADS) trtri_kernel(const double* A, int64_t lda, int64_t sA, int j0, int n,
-                                                            double* W, int64_t sW) {
+__global__ void __launch_bounds__(TRI_THREADS) trtri_lower_kernel(const double* A, int64_t lda, int64_t sA, int j0, int n,
+                                                                  double* W, int64_t sW) {
   extern __shared__ __align__(16) double sm[];
   constexpr int LD = TRI_LD;
   double* Ts = sm;                 // [NB][LD]   the triangle, inverted in place
@@ -592,11 +591,7 @@ __global__ void __launch_bounds__(TRI_THREADS) trtri_kernel(const double* A, int
   for (int idx = threadIdx.x; idx < NB * NB; idx += TRI_THREADS) {
     const int rr = idx / NB, cc = idx - rr * NB;
     double v = (rr == cc) ? 1.0 : 0.0;
-    if (rr < nb && cc < nb) {
-      const double x = a[(int64_t)rr * lda + cc];
-      if (LOWER) v = (cc < rr) ? x : v;
-      else v = (cc >= rr) ? x : 0.0;
-    }
+    if (rr < nb && cc < nb && cc < rr) v = a[(int64_t)rr * lda + cc];
     Ts[rr * LD + cc] = v;
   }
   __syncthreads();
@@ -605,51 +600,31 @@ __global__ void __launch_bounds__(TRI_THREADS) trtri_kernel(const double* A, int
     const int blk = threadIdx.x >> 5, c = threadIdx.x & 31, base = blk * 32;
     double* x = Xs + blk * 32 * 33;  // x[r*33 + c]
     const double* T = Ts + base * LD + base;
-    if (LOWER) {
-      for (int r = 0; r < 32; ++r) x[r * 33 + c] = (r == c) ? 1.0 : 0.0;
-      for (int r = c + 1; r < 32; ++r) {
-        double s = 0.0;
-        for (int t = c; t < r; ++t) s = fma(T[r * LD + t], x[t * 33 + c], s);
-        x[r * 33 + c] = -s;
-      }
-    } else {
-      for (int r = 0; r < 32; ++r) x[r * 33 + c] = 0.0;
-      x[c * 33 + c] = 1.0 / T[c * LD + c];
-      for (int r = c - 1; r >= 0; --r) {
-        double s = 0.0;
-        for (int t = r + 1; t <= c; ++t) s = fma(T[r * LD + t], x[t * 33 + c], s);
-        x[r * 33 + c] = -s / T[r * LD + r];
-      }
+    for (int r = 0; r < 32; ++r) x[r * 33 + c] = (r == c) ? 1.0 : 0.0;
+    for (int r = c + 1; r < 32; ++r) {
+      double s = 0.0;
+      for (int t = c; t < r; ++t) s = fma(T[r * LD + t], x[t * 33 + c], s);
+      x[r * 33 + c] = -s;
     }
     __syncwarp();
     for (int r = 0; r < 32; ++r) Ts[(base + r) * LD + base + c] = x[r * 33 + c];
   }
   __syncthreads();
   // ---- phase 2: 32-level off-diagonal blocks of both 64x64 halves ----
-  for (int half = 0; half < 2; ++half) {
+  for (int half = 0; half < 2; ++half) {  // W = L21 * inv(L11)
     const int b0 = half * 64, b1 = b0 + 32;
-    double* Wp = Ws + half * 32 * 65;
-    if (LOWER)  // W = L21 * inv(L11)
-      smem_mm(Wp, 65, Ts + b1 * LD + b0, LD, Ts + b0 * LD + b0, LD, 32, 32, 32, 1.0);
-    else        // W = U12 * inv(U22)
-      smem_mm(Wp, 65, Ts + b0 * LD + b1, LD, Ts + b1 * LD + b1, LD, 32, 32, 32, 1.0);
+    smem_mm(Ws + half * 32 * 65, 65, Ts + b1 * LD + b0, LD, Ts + b0 * LD + b0, LD, 32, 32, 32, 1.0);
   }
   __syncthreads();
-  for (int half = 0; half < 2; ++half) {
+  for (int half = 0; half < 2; ++half) {  // X21 = -inv(L22) * W
     const int b0 = half * 64, b1 = b0 + 32;
-    const double* Wp = Ws + half * 32 * 65;
-    if (LOWER)  // X21 = -inv(L22) * W
-      smem_mm(Ts + b1 * LD + b0, LD, Ts + b1 * LD + b1, LD, Wp, 65, 32, 32, 32, -1.0);
-    else        // X12 = -inv(U11) * W
-      smem_mm(Ts + b0 * LD + b1, LD, Ts + b0 * LD + b0, LD, Wp, 65, 32, 32, 32, -1.0);
+    smem_mm(Ts + b1 * LD + b0, LD, Ts + b1 * LD + b1, LD, Ws + half * 32 * 65, 65, 32, 32, 32, -1.0);
   }
   __syncthreads();
   // ---- phase 3: the 64-level off-diagonal block ----
-  if (LOWER) smem_mm(Ws, 65, Ts + 64 * LD, LD, Ts, LD, 64, 64, 64, 1.0);            // W = L21 * inv(L11)
-  else smem_mm(Ws, 65, Ts + 64, LD, Ts + 64 * LD + 64, LD, 64, 64, 64, 1.0);        // W = U12 * inv(U22)
+  smem_mm(Ws, 65, Ts + 64 * LD, LD, Ts, LD, 64, 64, 64, 1.0);                       // W = L21 * inv(L11)
   __syncthreads();
-  if (LOWER) smem_mm(Ts + 64 * LD, LD, Ts + 64 * LD + 64, LD, Ws, 65, 64, 64, 64, -1.0);  // X21 = -inv(L22) * W
-  else smem_mm(Ts + 64, LD, Ts, LD, Ws, 65, 64, 64, 64, -1.0);                            // X12 = -inv(U11) * W
+  smem_mm(Ts + 64 * LD, LD, Ts + 64 * LD + 64, LD, Ws, 65, 64, 64, 64, -1.0);       // X21 = -inv(L22) * W
   __syncthreads();
   double* w = W + (int64_t)blockIdx.y * sW + (int64_t)(j / NB) * NB * NB;
   for (int idx = threadIdx.x; idx < nb * nb; idx += TRI_THREADS) {
@@ -657,6 +632,57 @@ __global__ void __launch_bounds__(TRI_THREADS) trtri_kernel(const double* A, int
     w[rr * NB + cc] = Ts[rr * LD + cc];
   }
 }
+
+// Inverse of the nb x nb UPPER-triangular diagonal blocks (with their diagonal) by COLUMN-WISE BACK SUBSTITUTION:
+// thread c solves U x_c = e_c, so every column of the inverse carries the backward error of a triangular solve.
+// The blocked formula  inv([[A,B],[0,C]]) = [[A^-1, -A^-1 (B C^-1)], [0, C^-1]]  used for the unit-lower blocks is
+// NOT accurate enough here: the pivot rows of the ItI leaf systems mix impedance rows (~1e2) with operator rows
+// (~1e5), |A^-1||B||C^-1| is then far larger than |X12| and the solve loses two digits against LAPACK
+// (tools/lu_accuracy.py, reproduced in NumPy).  All diagonal blocks of a factorisation are inverted by ONE launch
+// after the factorisation, off the critical path, so the 128 sequential rows per thread do not matter.
+// x_c is kept in row c of the tile's otherwise unused strictly-lower triangle (odd LD: conflict-free), the rows of
+// U are read as warp-wide broadcasts (every lane of a warp works on the same row r at the same time).
+__global__ void __launch_bounds__(NB) trtri_upper_kernel(const double* A, int64_t lda, int64_t sA, int j0, int n,
+                                                         double* W, int64_t sW) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int LD = TRI_LD;
+  double* Ts = sm;  // [NB][LD]
+  const int j = j0 + blockIdx.x * NB;
+  const int nb = min(NB, n - j);
+  const double* a = A + (int64_t)blockIdx.y * sA + (int64_t)j * lda + j;
+  for (int idx = threadIdx.x; idx < NB * NB; idx += NB) {  // ragged blocks are padded with the identity
+    const int rr = idx / NB, cc = idx - rr * NB;
+    double v = (rr == cc) ? 1.0 : 0.0;
+    if (rr < nb && cc < nb) v = (cc >= rr) ? a[(int64_t)rr * lda + cc] : 0.0;
+    Ts[rr * LD + cc] = v;
+  }
+  __syncthreads();
+  const int c = threadIdx.x;
+  double* x = Ts + c * LD;  // x[t] = X[t][c] for t < c
+  const double xc = 1.0 / x[c];
+  for (int r = (c | 31) - 1; r >= 0; --r) {  // warp-uniform row index
+    if (r < c) {
+      const double* u = Ts + r * LD;
+      double s0 = u[c] * xc, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int t = r + 1;
+      for (; t + 3 < c; t += 4) {
+        s0 = fma(u[t], x[t], s0);
+        s1 = fma(u[t + 1], x[t + 1], s1);
+        s2 = fma(u[t + 2], x[t + 2], s2);
+        s3 = fma(u[t + 3], x[t + 3], s3);
+      }
+      for (; t < c; ++t) s0 = fma(u[t], x[t], s0);
+      x[r] = -((s0 + s1) + (s2 + s3)) / u[r];
+    }
+  }
+  __syncthreads();
+  double* w = W + (int64_t)blockIdx.y * sW + (int64_t)(j / NB) * NB * NB;
+  for (int idx = threadIdx.x; idx < nb * nb; idx += NB) {
+    const int rr = idx / nb, cc = idx - rr * nb;
+    w[rr * NB + cc] = (rr < cc) ? Ts[cc * LD + rr] : ((rr == cc) ? 1.0 / Ts[rr * LD + rr] : 0.0);
+  }
+}
+constexpr size_t TRTRI_UPPER_SMEM = sizeof(double) * NB * (NB + 1);
 
 // dst[b][r][c] = src[b][r][c] for an (rows x cols) block
 __global__ void copy_block_kernel(double* dst, int64_t ldd, int64_t sD, const double* src, int64_t lds, int64_t sS,
@@ -795,8 +821,8 @@ int configure_lu_kernels() {
     HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
-    HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
-    HPS_CUDA(cudaFuncSetAttribute(trtri_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(trtri_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(trtri_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_UPPER_SMEM));
   ds->lu_configured.store(true, std::memory_order_release);
   return 0;
 }
@@ -928,9 +954,9 @@ int factor_block_column(cudaStream_t st, int batch, int n, const Mat& A, int j, 
   }
   const int nblk = (n + NB - 1) / NB;
   prof_begin(PROF_TRTRI, st, (double)batch * NB * NB * NB / 3);
-  trtri_kernel<true><<<dim3(1, batch), TRI_THREADS, TRTRI_SMEM, st>>>(A.p, A.ld, A.stride, j, n, w.Linv, (int64_t)nblk * NB * NB);
+  trtri_lower_kernel<<<dim3(1, batch), TRI_THREADS, TRTRI_SMEM, st>>>(A.p, A.ld, A.stride, j, n, w.Linv, (int64_t)nblk * NB * NB);
   prof_end(PROF_TRTRI, st);
-  HPS_LAUNCH_CHECK("trtri_kernel<lower>");
+  HPS_LAUNCH_CHECK("trtri_lower_kernel");
   return 0;
 }
 
@@ -1038,9 +1064,9 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
 
   // ---- 2. inverses of U's diagonal blocks (all at once), interchanges on the right-hand sides --
   prof_begin(PROF_TRTRI, s0, (double)batch * nblk * NB * NB * NB / 3);
-  trtri_kernel<false><<<dim3(nblk, batch), TRI_THREADS, TRTRI_SMEM, s0>>>(A.p, A.ld, A.stride, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
+  trtri_upper_kernel<<<dim3(nblk, batch), NB, TRTRI_UPPER_SMEM, s0>>>(A.p, A.ld, A.stride, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
   prof_end(PROF_TRTRI, s0);
-  HPS_LAUNCH_CHECK("trtri_kernel<upper>");
+  HPS_LAUNCH_CHECK("trtri_upper_kernel");
   for (int k = 0; k < n_rhs; ++k) {
     HPS_TRY(laswp(s0, batch, rhs[k].ptr, rhs[k].ld, rhs[k].stride, 0, rhs[k].ncols, w.ipiv, n, 0, n));
     // ---- 3. recursive substitutions --------------------------------------------------------
@@ -1165,9 +1191,9 @@ int lu_dist_solve(cudaStream_t st, int n, double* A, int64_t lda, int n_rhs, con
   const Mat Am{A, lda, 0};
   const int nblk = (n + NB - 1) / NB;
   prof_begin(PROF_TRTRI, st, (double)nblk * NB * NB * NB / 3);
-  trtri_kernel<false><<<dim3(nblk, 1), TRI_THREADS, TRTRI_SMEM, st>>>(A, lda, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
+  trtri_upper_kernel<<<dim3(nblk, 1), NB, TRTRI_UPPER_SMEM, st>>>(A, lda, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
   prof_end(PROF_TRTRI, st);
-  HPS_LAUNCH_CHECK("trtri_kernel<upper>");
+  HPS_LAUNCH_CHECK("trtri_upper_kernel");
   for (int k = 0; k < n_rhs; ++k) {
     HPS_TRY(laswp(st, 1, rhs[k].ptr, rhs[k].ld, rhs[k].stride, 0, rhs[k].ncols, w.ipiv, n, 0, n));
     HPS_TRY(trsm_lower(st, 1, n, Am, w, rhs[k], 0, n));
@@ -1552,9 +1578,9 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
     HPS_CUDA(cudaStreamWaitEvent(s0, aux->sent, 0));
   }
   prof_begin(PROF_TRTRI, s0, (double)nblk * NB * NB * NB / 3);
-  trtri_kernel<false><<<dim3(nblk, 1), TRI_THREADS, TRTRI_SMEM, s0>>>(A, n, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
+  trtri_upper_kernel<<<dim3(nblk, 1), NB, TRTRI_UPPER_SMEM, s0>>>(A, n, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
   prof_end(PROF_TRTRI, s0);
-  HPS_LAUNCH_CHECK("trtri_kernel<upper>");
+  HPS_LAUNCH_CHECK("trtri_upper_kernel");
   for (int k = 0; k < n_rhs; ++k) HPS_TRY(trsm_upper(s0, 1, n, Am, w, rhs[k], 0, n));
   return 0;
 }

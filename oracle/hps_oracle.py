@@ -41,6 +41,26 @@ import numpy as np
 # Leaf level
 # =====================================================================================
 
+
+def _inv(A: np.ndarray) -> np.ndarray:
+    """``numpy.linalg.inv``; x87 extended-precision inputs (``numpy.longdouble`` / ``clongdouble``, which LAPACK does
+    not serve) go through Gaussian elimination with partial pivoting in that precision.  Only the arbitration tests
+    (tests/_longdouble.py) feed such inputs: the same restated algorithm evaluated at eps = 1.1e-19 tells which of two
+    FP64 results that differ by more than the 1e-10 bar is the accurate one."""
+    if A.dtype not in (np.longdouble, np.clongdouble):
+        return np.linalg.inv(A)
+    n = A.shape[0]
+    M = np.concatenate([A, np.eye(n, dtype=A.dtype)], axis=1)
+    for k in range(n):
+        piv = k + int(np.argmax(np.abs(M[k:, k])))
+        if piv != k:
+            M[[k, piv]] = M[[piv, k]]
+        M[k] = M[k] / M[k, k]
+        others = np.arange(n) != k
+        M[others] -= np.outer(M[others, k], M[k])
+    return M[:, n:]
+
+
 _COEFF_ORDER_3D = ("D_xx", "D_xy", "D_yy", "D_xz", "D_yz", "D_zz", "D_x", "D_y", "D_z", "I")
 _COEFF_ORDER_2D = ("D_xx", "D_xy", "D_yy", "D_x", "D_y", "I")
 
@@ -486,7 +506,7 @@ def invert_D_ItI(D_12: np.ndarray, D_21: np.ndarray) -> np.ndarray:
     """``(I + [[0, D12],[D21, 0]])^-1`` through the Schur complement ``W = I - D12 D21``
     (`_schur_complement.py:78-114`)."""
     n, m = D_12.shape[0], D_21.shape[0]
-    W_inv = np.linalg.inv(np.eye(n) - D_12 @ D_21)
+    W_inv = _inv(np.eye(n) - D_12 @ D_21)
     out = np.zeros((n + m, n + m), dtype=D_12.dtype)
     out[:n, :n] = W_inv
     out[:n, n:] = -1 * W_inv @ D_12
@@ -500,7 +520,7 @@ def uniform_quad_merge_ItI(R_children: np.ndarray, h_children: np.ndarray, retur
     Returns (S, R, h_out, g_tilde) with S (8m, 8m), g_tilde (8m, n_src)."""
     m = R_children.shape[-1] // 4
     n_src = h_children.shape[-1]
-    dt = np.complex128
+    dt = np.result_type(R_children.dtype, np.complex128)  # complex128; clongdouble for the arbitration tests
     pre = [(0, 3), (0, 0), (1, 0), (1, 1), (2, 1), (2, 2), (3, 2), (3, 3)]  # ext panels before the roll
     blk = lambda k: slice(k * m, (k + 1) * m)  # noqa: E731
     B = np.zeros((8 * m, 8 * m), dtype=dt)

@@ -118,15 +118,18 @@ def scattering_inputs(n_side=12, n_src=3, seed=7):
 
 
 # ---- BASELINE config 2: 2D variable-coefficient Helmholtz, ItI, p=16 q=14, k=100 ----
-def config2_problem(L, k=100.0):
+def config2_problem(L, k=100.0, half_width=1.0):
     """``u_xx + u_yy + k^2 (1 + q(x)) u = -k^2 q e^{ikx}`` on [-1,1]^2, q = sum of 10 gauss bumps (centres U(-0.5,0.5)^2,
-    seed 0), eta = k; boundary data = incoming impedance of the plane wave e^{ikx}."""
-    dom = hps.Domain(16, 14, hps.DiscretizationNode2D(-1.0, 1.0, -1.0, 1.0), L)
+    seed 0), eta = k; boundary data = incoming impedance of the plane wave e^{ikx}.  ``half_width`` shrinks the domain
+    (bumps scaled with it): ``half_width = 2**L / 64`` keeps config 2's leaf size 1/32 — hence its leaf conditioning —
+    on a tree shallow enough for the extended-precision arbitration."""
+    w = float(half_width)
+    dom = hps.Domain(16, 14, hps.DiscretizationNode2D(-w, w, -w, w), L)
     x = dom.interior_points
     one = np.ones_like(x[..., 0])
     rng = np.random.default_rng(0)
-    centres = rng.uniform(-0.5, 0.5, size=(10, 2))
-    q = sum(np.exp(-50 * ((x[..., 0] - c[0]) ** 2 + (x[..., 1] - c[1]) ** 2)) for c in centres)
+    centres = rng.uniform(-0.5, 0.5, size=(10, 2)) * w
+    q = sum(np.exp(-50 * ((x[..., 0] - c[0]) ** 2 + (x[..., 1] - c[1]) ** 2) / w**2) for c in centres)
     pb = hps.PDEProblem(dom, source=-k**2 * q * np.exp(1j * k * x[..., 0]), D_xx_coefficients=one, D_yy_coefficients=one,
                         I_coefficients=k**2 * (1 + q), use_ItI=True, eta=k)
     b = dom.boundary_points

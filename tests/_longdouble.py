@@ -28,8 +28,8 @@ def lu_solve_ld(B, R):
     return X
 
 
-def iti_leaf_truth(pb, leaf):
-    """(Y, R, v, h) of one leaf in extended precision (rounded to complex128 on return)."""
+def iti_leaf_truth(pb, leaf, rounded=True):
+    """(Y, R, v, h) of one leaf in extended precision (rounded to complex128 on return unless ``rounded=False``)."""
     Dx, Dy = np.asarray(pb.D_x, dtype=LD), np.asarray(pb.D_y, dtype=LD)
     ops = {"D_xx": Dx @ Dx, "D_xy": Dx @ Dy, "D_yy": Dy @ Dy, "D_x": Dx, "D_y": Dy, "I": np.eye(Dx.shape[0], dtype=LD)}
     n_c = Dx.shape[0]
@@ -49,4 +49,22 @@ def iti_leaf_truth(pb, leaf):
     X = lu_solve_ld(B, rhs)
     Y, v = X[:, : P.shape[1]], X[:, P.shape[1]:]
     R, h = QH @ Y, QH @ v
+    if not rounded:
+        return Y, R, v, h
     return tuple(np.asarray(t, dtype=np.complex128) for t in (Y, R, v, h))
+
+
+def iti_pipeline_truth(pb, L, boundary_data):
+    """The whole 2D ItI build + solve in extended precision: leaf solves above, then the ORACLE's own merge and down-pass
+    code evaluated on ``clongdouble`` arrays (oracle/hps_oracle.py dispatches its inverses to extended-precision
+    Gaussian elimination for such inputs).  Returns ``(Y, R, v, h, S_lst, g_lst, R_top, u)`` rounded to complex128;
+    single-source only.  Cost: ~0.2 s per p=16 leaf, seconds per merge level — meant for L <= 3."""
+    from oracle import hps_oracle as orc
+
+    n_leaves = 4**L
+    leaves = [iti_leaf_truth(pb, i, rounded=False) for i in range(n_leaves)]
+    Y, R, v, h = (np.stack([lf[k] for lf in leaves]) for k in range(4))
+    S_lst, g_lst, R_top = orc.merge_stage_uniform_2D_ItI(R, h[..., 0], L, return_T=True)
+    u = orc.down_pass_uniform_2D_ItI(np.asarray(boundary_data, dtype=CLD), S_lst, g_lst, Y, v[..., 0])
+    c = lambda a: np.asarray(a, dtype=np.complex128)  # noqa: E731
+    return c(Y), c(R), c(v[..., 0]), c(h[..., 0]), [c(S) for S in S_lst], [c(g) for g in g_lst], c(R_top), c(u)

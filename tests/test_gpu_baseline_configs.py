@@ -22,9 +22,9 @@ def _fixture(name):
 
 
 def test_config2_helmholtz_iti_k100_L6_matches_oracle_probe():
-    """4096 leaves, p=16, q=14, k=100, complex128.  The ItI leaf systems are ill-conditioned (cond ~ 1e5..1e6 at
-    k h ~ 3), so two correct FP64 evaluations agree to ~1e-10..1e-9 only (extended-precision arbitration of the
-    leaf operators: test_gpu_stages.py); the bar here is 1e-9 on every probed quantity."""
+    """4096 leaves, p=16, q=14, k=100, complex128, every probed quantity within 1e-10 of the oracle.  (The ItI leaf
+    systems are ill-conditioned, cond ~ 5e5; the device row-equilibrates them, which puts the CUDA result ~1e-13 from
+    the exact one — what is left here, 1e-11..5e-11, is the oracle's own error: test_gpu_iti_arbitration.py.)"""
     G = _fixture("config2_oracle_probe_L6.npz")
     from jaxhps_b200.local_solve import local_solve_stage_uniform_2D_ItI
     from jaxhps_b200.merge import merge_stage_uniform_2D_ItI
@@ -41,7 +41,7 @@ def test_config2_helmholtz_iti_k100_L6_matches_oracle_probe():
     u = down_pass_uniform_2D_ItI(g, S, gt, Y, v)
     errs["u"] = float(np.abs(u.reshape(-1)[:: int(G["stride"])] - G["u_probe"]).max() / float(G["u_max"]))
     print("config 2 L=6: " + ", ".join(f"{k} {e:.1e}" for k, e in errs.items()))
-    assert all(e < 1e-9 for e in errs.values()), errs
+    assert all(e < 1e-10 for e in errs.values()), errs
 
 
 def test_config4_wavefront_adaptive_p10_tol1e5_matches_oracle_probe():

@@ -120,7 +120,7 @@ def test_helmholtz_ItI_plane_wave_2D():
     uo = orc.down_pass_uniform_2D_ItI(g, S, gt, Y, v)
     assert np.abs(uo - exact).max() < 1e-8
     assert np.abs(u - exact).max() < 1e-8
-    assert np.abs(u - uo).max() < 1e-9
+    assert np.abs(u - uo).max() < 1e-10
 
 
 @pytest.mark.parametrize("iti,p,q,L,nsrc", [(False, 6, 4, 2, 1), (False, 8, 6, 3, 2), (True, 6, 4, 2, 1), (True, 8, 6, 3, 2)])
@@ -147,7 +147,7 @@ def test_source_at_solve_time_matches_oracle(iti, p, q, L, nsrc):
         up, dn = orc.up_pass_uniform_2D_DtN, orc.down_pass_uniform_2D_DtN
     ref_pb.Y, ref_pb.Phi, ref_pb.S_lst, ref_pb.D_inv_lst, ref_pb.BD_inv_lst = Y, Phi, S, Di, BDi
     rel = lambda a, b: np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max()  # noqa: E731
-    tol = 1e-9
+    tol = 1e-10
     assert rel(pb.Y, Y) < tol and rel(pb.Phi, Phi) < tol and rel(T_top, Tt) < tol
     for a, b in zip(pb.S_lst + pb.D_inv_lst + pb.BD_inv_lst, S + Di + BDi):
         assert np.asarray(a).shape == b.shape and rel(a, b) < tol

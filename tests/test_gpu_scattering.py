@@ -40,4 +40,4 @@ def test_top_level_iti_operator_to_dtn(p, q, L):
     dirs = np.array([0.3, 2.0])
     pts = pb.domain.boundary_points
     imp = sc.get_scattering_uscat_impedance(S, D, T, dirs, pts, 3.0, pb.eta)
-    assert rel_err(imp, osc.get_scattering_uscat_impedance(S, D, To, dirs, pts, 3.0, pb.eta)) < 1e-9
+    assert rel_err(imp, osc.get_scattering_uscat_impedance(S, D, To, dirs, pts, 3.0, pb.eta)) < 1e-10

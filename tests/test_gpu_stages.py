@@ -35,7 +35,7 @@ def test_cuda_path_matches_reference_fixture(name):
     Y, T, v, h = ls(pb)
     S_lst, g_lst, T_top = mg(T, h, L, return_T=True)
     u = dp(bdry, S_lst, g_lst, Y, v)
-    tol = TOL if dim != 20 else 1e-9  # small ItI cases (p <= 8); see test_stages_match_oracle for the bar
+    tol = TOL
     assert rel_err(v, G["v"]) < tol and rel_err(h, G["h"]) < tol
     for i, g in enumerate(g_lst):
         assert rel_err(g, G[f"g_tilde_{i}"]) < tol
@@ -47,22 +47,6 @@ def test_cuda_path_matches_reference_fixture(name):
         for i, S in enumerate(S_lst):
             assert S.shape == G[f"S_{i}"].shape
             assert rel_err(S, G[f"S_{i}"]) < tol
-
-
-def _one_ulp_sensitivity(pb, ols, ref_outputs):
-    """How far the ORACLE's own leaf outputs move when every coefficient is perturbed by one unit
-    in the last place: the floor below which two correct FP64 implementations cannot be expected
-    to agree (the CUDA path assembles the leaf operator from the 1-D matrix, so its entries differ
-    from the oracle's dense-operator sum in the last bit)."""
-    import copy
-
-    rng = np.random.default_rng(0)
-    pert = copy.copy(pb)
-    for name in ("D_xx", "D_yy", "D_zz", "I"):
-        c = getattr(pb, f"{name}_coefficients", None)
-        if c is not None:
-            setattr(pert, f"{name}_coefficients", c * (1.0 + rng.choice([-1.0, 1.0], size=c.shape) * 2.0**-52))
-    return max(rel_err(a, b) for a, b in zip(ols(pert), ref_outputs))
 
 
 @pytest.mark.parametrize(
@@ -86,16 +70,10 @@ def test_stages_match_oracle(dim, p, q, L, nsrc):
     (ls, mg, dp), (ols, omg, odp) = GPU[dim], ORC[dim]
     Yo, To, vo, ho = ols(pb)
     Y, T, v, h = ls(pb)
+    # ItI (dim 20): the leaf systems are row-equilibrated on the device (csrc/leaf.cu), which puts the CUDA result within
+    # ~1e-13 of the exact one; what is left against the oracle is the oracle's own error (1e-12 at p=16, cond(B) ~ 2e5),
+    # so the 1e-10 bar holds there too.  test_gpu_iti_arbitration.py arbitrates in extended precision.
     tol = TOL
-    if dim == 20:
-        # ItI leaves are ill-conditioned (cond(B) ~ 2e5 at p=16) and D_xx = D_x @ D_x carries
-        # cancellation, so entries of the assembled operator legitimately differ by many ulps
-        # between two summation orders.  The bar is 1e-10 or 1000x the oracle's own response to a
-        # 1-ulp perturbation of its coefficients, whichever is larger (measured: GPU-vs-oracle is
-        # ~150x that response); the reference's own ItI equivalence tests use 1e-8
-        # (tests/test_accuracy/test_nosource_accuracy.py:166-279).
-        tol = max(TOL, 1000.0 * _one_ulp_sensitivity(pb, ols, (Yo, To, vo, ho)))
-        assert tol < 1e-7
     for a, b in ((Y, Yo), (T, To), (v, vo), (h, ho)):
         assert rel_err(a, b) < tol
     So, go, Tto = omg(To, ho, L, return_T=True)
@@ -202,12 +180,12 @@ def test_iti_analytic_cases_incl_complex_coefficients(which):
     Yo, Ro, vo, ho = orc.local_solve_stage_uniform_2D_ItI(pb)
     Y, R, v, h = local_solve_stage_uniform_2D_ItI(pb)
     for a, b in ((Y, Yo), (R, Ro), (v, vo), (h, ho)):
-        assert rel_err(a, b) < 1e-9
+        assert rel_err(a, b) < 1e-10
     hps.build_solver(pb)
     u = hps.solve(pb, g_in)
     assert np.abs(u - case["u"](dom.interior_points)).max() < 1e-8
     So, go = orc.merge_stage_uniform_2D_ItI(Ro, ho, 1)
-    assert rel_err(u, orc.down_pass_uniform_2D_ItI(g_in, So, go, Yo, vo)) < 1e-9
+    assert rel_err(u, orc.down_pass_uniform_2D_ItI(g_in, So, go, Yo, vo)) < 1e-10
     # the source-free build + up pass takes the same complex coefficient path
     pb2 = hps.PDEProblem(dom, source=None, D_xx_coefficients=pb.D_xx_coefficients, D_yy_coefficients=pb.D_yy_coefficients,
                          I_coefficients=pb.I_coefficients, use_ItI=True, eta=pb.eta)
