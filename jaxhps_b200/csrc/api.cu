@@ -57,7 +57,7 @@ struct ProfState {
   bool on = false;
   std::vector<cudaEvent_t> pool;
   size_t used = 0;
-  struct Rec { int cat; size_t e0, e1; double work; };
+  struct Rec { int cat; size_t e0, e1; double work; cudaStream_t st; };
   std::vector<Rec> recs;
   size_t open_rec[PROF_NCAT] = {};
   std::mutex mu;
@@ -78,7 +78,7 @@ void prof_begin(int cat, cudaStream_t st, double work) {
   const size_t i0 = g_prof.used;
   cudaEventRecord(g_prof.take(), st);
   g_prof.open_rec[cat] = g_prof.recs.size();
-  g_prof.recs.push_back({cat, i0, i0, work});
+  g_prof.recs.push_back({cat, i0, i0, work, st});
 }
 void prof_end(int cat, cudaStream_t st) {
   if (!g_prof.on) return;
@@ -118,6 +118,28 @@ int hps_prof_read(void* stream, double* ms, double* work, int64_t* launches, int
     launches[r.cat] += 1;
   }
   *all_launches = g_launches;
+  return 0;
+}
+
+// Timeline of the recorded launches: start / end in ms relative to the first record, category and a small integer
+// naming the stream (in order of first appearance).  Developer aid for the multi-stream drivers (tools/bench_dist_lu.py).
+int hps_prof_timeline(double* t0_ms, double* t1_ms, int* cat, int* stream_id, int64_t cap, int64_t* n) {
+  HPS_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  std::vector<cudaStream_t> seen;
+  int64_t k = 0;
+  for (const auto& r : g_prof.recs) {
+    if (k >= cap) break;
+    float a = 0.f, b = 0.f;
+    HPS_CUDA(cudaEventElapsedTime(&a, g_prof.pool[g_prof.recs[0].e0], g_prof.pool[r.e0]));
+    HPS_CUDA(cudaEventElapsedTime(&b, g_prof.pool[g_prof.recs[0].e0], g_prof.pool[r.e1]));
+    size_t sid = 0;
+    while (sid < seen.size() && seen[sid] != r.st) ++sid;
+    if (sid == seen.size()) seen.push_back(r.st);
+    t0_ms[k] = a; t1_ms[k] = b; cat[k] = r.cat; stream_id[k] = (int)sid;
+    ++k;
+  }
+  *n = k;
   return 0;
 }
 

@@ -1314,6 +1314,44 @@ __global__ void __launch_bounds__(256) comm_bcast_blockcol_kernel(CommPtrs p, in
   }
 }
 
+constexpr int DIST_NSLOT = 2 * COMM_MAX_WORLD + 2;
+constexpr size_t SLOT_LINV_OFF = 1024, SLOT_PANEL_OFF = SLOT_LINV_OFF + (size_t)NB * NB * sizeof(double);
+
+// PACK = true : slot <- (ipiv[j:j+jb], Linv_b, A[:, j:j+jb])   (owner, after the factorisation of block column b)
+// PACK = false: the reverse (receiver, after the flag of block column b)
+template <bool PACK>
+__global__ void __launch_bounds__(256) comm_slot_kernel(double* __restrict__ A, int n, int j, int jb, int* __restrict__ ipiv_j,
+                                                        double* __restrict__ Linv_b, char* __restrict__ slot) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double* panel = reinterpret_cast<double*>(slot + SLOT_PANEL_OFF);
+  if (((n | jb) & 1) == 0) {  // j is a multiple of NB: 16-byte accesses on both sides
+    const int h = jb >> 1;
+    const int64_t total = (int64_t)n * h;
+    for (int64_t e = t0; e < total; e += stride) {
+      const int64_t r = e / h, c = e - r * h;
+      double2* a = reinterpret_cast<double2*>(A + r * n + j) + c;
+      double2* q = reinterpret_cast<double2*>(panel + r * jb) + c;
+      if (PACK) *q = *a; else *a = *q;
+    }
+  } else {
+    const int64_t total = (int64_t)n * jb;
+    for (int64_t e = t0; e < total; e += stride) {
+      const int64_t r = e / jb, c = e - r * jb;
+      if (PACK) panel[e] = A[r * n + j + c]; else A[r * n + j + c] = panel[e];
+    }
+  }
+  int* sp = reinterpret_cast<int*>(slot);
+  for (int64_t e = t0; e < jb; e += stride) {
+    if (PACK) sp[e] = ipiv_j[e]; else ipiv_j[e] = sp[e];
+  }
+  double2* sl = reinterpret_cast<double2*>(slot + SLOT_LINV_OFF);
+  double2* li = reinterpret_cast<double2*>(Linv_b);
+  for (int64_t e = t0; e < (int64_t)NB * NB / 2; e += stride) {
+    if (PACK) sl[e] = li[e]; else li[e] = sl[e];
+  }
+}
+
 // <<<1, 32>>>: raise flag b on the peers in `mask` (after stream-ordered copy-engine transfers)
 __global__ void comm_signal_kernel(CommPtrs p, int world, unsigned mask, int b, unsigned epoch) {
   const int q = threadIdx.x;
@@ -1323,8 +1361,16 @@ __global__ void comm_signal_kernel(CommPtrs p, int world, unsigned mask, int b, 
   }
 }
 
+// Staging slots of the block-column exchange.  A factored block column is a strided window of the row-major
+// matrix (n rows of jb doubles): the copy engines move such a window at ~30 GB/s (per-row overhead) but a
+// CONTIGUOUS buffer at NVLink speed, so the owner packs the column (+ pivots + inverted diagonal block) into a
+// slot, one contiguous peer copy per destination carries it into the SAME slot of the peer's segment, and the
+// peer unpacks it into its matrix (two local HBM passes of 20 MB: ~10 us each).  Slot b % DIST_NSLOT is reused by
+// block b + DIST_NSLOT; by then every rank has factored a block column later than b, which it could only do after
+// receiving AND unpacking block b (stream order on its chain stream), so DIST_NSLOT >= world + 1 is enough.
+
 struct DistLayout {
-  size_t ipiv_off, linv_off, uinv_off, A_off, bytes;
+  size_t ipiv_off, linv_off, uinv_off, A_off, slot_off, slot_bytes, bytes;
 };
 DistLayout dist_layout(int n) {
   const size_t nblk = (n + NB - 1) / NB;
@@ -1333,7 +1379,9 @@ DistLayout dist_layout(int n) {
   L.linv_off = L.ipiv_off + align_up((size_t)n * sizeof(int), 256);
   L.uinv_off = L.linv_off + align_up(nblk * NB * NB * sizeof(double), 256);  // local only (never sent)
   L.A_off = L.uinv_off + align_up(nblk * NB * NB * sizeof(double), 256);
-  L.bytes = L.A_off + align_up((size_t)n * n * sizeof(double), 256);
+  L.slot_off = L.A_off + align_up((size_t)n * n * sizeof(double), 256);
+  L.slot_bytes = align_up(SLOT_PANEL_OFF + (size_t)n * NB * sizeof(double), 256);
+  L.bytes = L.slot_off + (size_t)DIST_NSLOT * L.slot_bytes;
   return L;
 }
 
@@ -1483,8 +1531,8 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
   HPS_CUDA(cudaEventRecord(aux->fork, s0));
   HPS_CUDA(cudaStreamWaitEvent(s1, aux->fork, 0));
 
-  // HPS_DIST_SEND=kernel: SM stores into the peers' segments; default: the copy engines move the column
-  // (cudaMemcpy2DAsync on the peer mapping) and a one-warp kernel raises the flags.
+  // HPS_DIST_SEND=kernel: SM stores straight into the peers' matrices; default: pack into a staging slot, one
+  // contiguous copy-engine transfer per peer, a one-warp kernel raises the flags, the peer unpacks.
   static const bool send_by_kernel = [] { const char* e = std::getenv("HPS_DIST_SEND"); return e && e[0] == 'k'; }();
   cudaStream_t s2 = aux->comm_stream;
   auto send = [&](cudaStream_t s, int b, unsigned mask, unsigned* done) -> int {
@@ -1496,16 +1544,11 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
       comm_bcast_blockcol_kernel<<<64, 256, 0, s>>>(c->ptrs, rank, world, mask, n, j, jb, L.ipiv_off, linv_off, L.A_off, b,
                                                     epoch, done);
     } else {
+      const size_t so = L.slot_off + (size_t)(b % DIST_NSLOT) * L.slot_bytes;
+      const size_t used = SLOT_PANEL_OFF + (size_t)n * jb * sizeof(double);
       for (int q = 0; q < world; ++q) {
         if (!((mask >> q) & 1u)) continue;
-        char* dst = c->ptrs.peer[q];
-        HPS_CUDA(cudaMemcpy2DAsync(dst + L.A_off + (size_t)j * sizeof(double), (size_t)n * sizeof(double),
-                                   c->local + L.A_off + (size_t)j * sizeof(double), (size_t)n * sizeof(double),
-                                   (size_t)jb * sizeof(double), n, cudaMemcpyDeviceToDevice, s));
-        HPS_CUDA(cudaMemcpyAsync(dst + L.ipiv_off + (size_t)j * sizeof(int), c->local + L.ipiv_off + (size_t)j * sizeof(int),
-                                 (size_t)jb * sizeof(int), cudaMemcpyDeviceToDevice, s));
-        HPS_CUDA(cudaMemcpyAsync(dst + linv_off, c->local + linv_off, (size_t)NB * NB * sizeof(double),
-                                 cudaMemcpyDeviceToDevice, s));
+        HPS_CUDA(cudaMemcpyAsync(c->ptrs.peer[q] + so, c->local + so, used, cudaMemcpyDeviceToDevice, s));
       }
       comm_signal_kernel<<<1, 32, 0, s>>>(c->ptrs, world, mask, b, epoch);
     }
@@ -1519,6 +1562,11 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
     const int j = b * NB, jb = std::min(NB, n - j);
     HPS_TRY(factor_block_column(s1, 1, n, Am, j, jb, w, info));
     if (world > 1) {
+      if (!send_by_kernel) {
+        comm_slot_kernel<true><<<128, 256, 0, s1>>>(A, n, j, jb, w.ipiv + j, w.Linv + (int64_t)b * NB * NB,
+                                                    c->local + L.slot_off + (size_t)(b % DIST_NSLOT) * L.slot_bytes);
+        HPS_LAUNCH_CHECK("comm_slot_kernel<pack>");
+      }
       const int next = (b + 1) % world;
       const unsigned all = ((1u << world) - 1u) & ~(1u << rank);
       const unsigned first = (b + 1 < nblk && next != rank) ? (1u << next) : 0u;
@@ -1530,8 +1578,16 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
     return 0;
   };
   auto wait_block = [&](int b) -> int {
+    prof_begin(PROF_WAIT, s1, 0.0);
     comm_wait_block_kernel<<<1, 1, 0, s1>>>(flags + b, epoch);
+    prof_end(PROF_WAIT, s1);
     HPS_LAUNCH_CHECK("comm_wait_block_kernel");
+    if (!send_by_kernel) {
+      const int j = b * NB, jb = std::min(NB, n - j);
+      comm_slot_kernel<false><<<128, 256, 0, s1>>>(A, n, j, jb, w.ipiv + j, w.Linv + (int64_t)b * NB * NB,
+                                                   c->local + L.slot_off + (size_t)(b % DIST_NSLOT) * L.slot_bytes);
+      HPS_LAUNCH_CHECK("comm_slot_kernel<unpack>");
+    }
     return 0;
   };
   // owned block columns > lo as one strided batch (+ a ragged last block), then the right-hand sides

@@ -24,7 +24,7 @@ A0 = torch.randn(n, n, dtype=torch.float64, generator=g).to(dev)  # same matrix 
 B0 = torch.randn(n, ncols, dtype=torch.float64, device=dev)
 comm = _dist.P2PComm.get(_lib, dev, rank, world, None)
 comm.ensure(comm.lu_segment_bytes(n))
-names = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny", "assemble", "p2p_send"]
+names = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny", "assemble", "p2p_send", "wait_block"]
 for it in range(reps + 1):
     B = B0.clone()
     _dist._copy_into_segment(comm.matrix_ptr(n), A0)
@@ -51,6 +51,24 @@ if rank == 0:
     print("   rank 0 per category ms:", {nm: round(pm[i], 2) for i, nm in enumerate(names) if pl[i]},
           "launches", {nm: pl[i] for i, nm in enumerate(names) if pl[i]}, "p2p GB/s", round(pw[8] / max(pm[8], 1e-9) * 1e-6, 1),
           "residual", res, flush=True)
+# per-launch timeline of the profiled iteration, every rank: gpurun_out/dist_lu_timeline_w{world}_r{rank}.csv
+cap = 200000
+t0, t1 = (ctypes.c_double * cap)(), (ctypes.c_double * cap)()
+cat, sid = (ctypes.c_int * cap)(), (ctypes.c_int * cap)()
+nrec = ctypes.c_int64()
+lib.hps_prof_timeline(t0, t1, cat, sid, cap, ctypes.byref(nrec))
+os.makedirs("gpurun_out", exist_ok=True)
+with open(f"gpurun_out/dist_lu_timeline_w{world}_r{rank}.csv", "w") as f:
+    f.write("t0_ms,t1_ms,category,stream\n")
+    for i in range(nrec.value):
+        f.write(f"{t0[i]:.4f},{t1[i]:.4f},{names[cat[i]]},{sid[i]}\n")
+if rank == 0:
+    busy = {}
+    for i in range(nrec.value):
+        busy.setdefault((sid[i], names[cat[i]]), [0, 0.0])
+        busy[(sid[i], names[cat[i]])][0] += 1
+        busy[(sid[i], names[cat[i]])][1] += t1[i] - t0[i]
+    print("   rank 0 (stream, category): launches, ms:", {k: (v[0], round(v[1], 2)) for k, v in sorted(busy.items())}, flush=True)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
