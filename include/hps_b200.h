@@ -48,8 +48,10 @@ const char* hps_last_error_string(void);
 int hps_prof_enable(int on);
 int hps_prof_read(void* stream, double* ms, double* work, int64_t* launches, int64_t* all_launches);
 /* per-launch timeline of the recording (ms relative to the first record; stream_id numbers the streams in order of
- * first appearance); at most cap records, *n returned */
-int hps_prof_timeline(double* t0_ms, double* t1_ms, int* cat, int* stream_id, int64_t cap, int64_t* n);
+ * first appearance; work = flops or bytes of the launch as in hps_prof_read; dims[4k..4k+3] = M, N, K, batch
+ * of a GEMM launch, zeros otherwise); at most cap records, *n returned */
+int hps_prof_timeline(double* t0_ms, double* t1_ms, double* work, int* cat, int* stream_id, int* dims, int64_t cap,
+                      int64_t* n);
 
 /* ---- dense building blocks (exported for tests, benches and the jax.ffi shim) ------
  * C[b] = alpha * A[b] (MxK) * B[b] (KxN) + beta * C[b], b < batch, element strides sX.

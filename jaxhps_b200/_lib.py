@@ -29,7 +29,8 @@ _SIGNATURES = {
     "hps_last_error_string": (ctypes.c_char_p, []),
     "hps_prof_enable": (_i, [_i]),
     "hps_prof_read": (_i, [_p, ctypes.POINTER(_d), ctypes.POINTER(_d), ctypes.POINTER(_l), ctypes.POINTER(_l)]),
-    "hps_prof_timeline": (_i, [ctypes.POINTER(_d), ctypes.POINTER(_d), ctypes.POINTER(_i), ctypes.POINTER(_i), _l, ctypes.POINTER(_l)]),
+    "hps_prof_timeline": (_i, [ctypes.POINTER(_d), ctypes.POINTER(_d), ctypes.POINTER(_d), ctypes.POINTER(_i), ctypes.POINTER(_i),
+                          ctypes.POINTER(_i), _l, ctypes.POINTER(_l)]),
     "hps_dgemm_strided_batched": (_i, [_p, _i, _i, _i, _d, _p, _l, _l, _p, _l, _l, _d, _p, _l, _l, _i]),
     "hps_lu_solve_workspace": (_i, [_i, _i, ctypes.POINTER(_sz)]),
     "hps_lu_solve": (_i, [_p, _i, _i, _p, _l, _l, _i, ctypes.POINTER(_p), ctypes.POINTER(_l),

@@ -57,7 +57,7 @@ struct ProfState {
   bool on = false;
   std::vector<cudaEvent_t> pool;
   size_t used = 0;
-  struct Rec { int cat; size_t e0, e1; double work; cudaStream_t st; };
+  struct Rec { int cat; size_t e0, e1; double work; cudaStream_t st; int dims[4]; };
   std::vector<Rec> recs;
   size_t open_rec[PROF_NCAT] = {};
   std::mutex mu;
@@ -78,7 +78,13 @@ void prof_begin(int cat, cudaStream_t st, double work) {
   const size_t i0 = g_prof.used;
   cudaEventRecord(g_prof.take(), st);
   g_prof.open_rec[cat] = g_prof.recs.size();
-  g_prof.recs.push_back({cat, i0, i0, work, st});
+  g_prof.recs.push_back({cat, i0, i0, work, st, {0, 0, 0, 0}});
+}
+void prof_dims(int cat, int a, int b, int c, int d) {
+  if (!g_prof.on) return;
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  int* q = g_prof.recs[g_prof.open_rec[cat]].dims;
+  q[0] = a; q[1] = b; q[2] = c; q[3] = d;
 }
 void prof_end(int cat, cudaStream_t st) {
   if (!g_prof.on) return;
@@ -123,7 +129,8 @@ int hps_prof_read(void* stream, double* ms, double* work, int64_t* launches, int
 
 // Timeline of the recorded launches: start / end in ms relative to the first record, category and a small integer
 // naming the stream (in order of first appearance).  Developer aid for the multi-stream drivers (tools/bench_dist_lu.py).
-int hps_prof_timeline(double* t0_ms, double* t1_ms, int* cat, int* stream_id, int64_t cap, int64_t* n) {
+int hps_prof_timeline(double* t0_ms, double* t1_ms, double* work, int* cat, int* stream_id, int* dims, int64_t cap,
+                      int64_t* n) {
   HPS_CUDA(cudaDeviceSynchronize());
   std::lock_guard<std::mutex> lock(g_prof.mu);
   std::vector<cudaStream_t> seen;
@@ -136,7 +143,8 @@ int hps_prof_timeline(double* t0_ms, double* t1_ms, int* cat, int* stream_id, in
     size_t sid = 0;
     while (sid < seen.size() && seen[sid] != r.st) ++sid;
     if (sid == seen.size()) seen.push_back(r.st);
-    t0_ms[k] = a; t1_ms[k] = b; cat[k] = r.cat; stream_id[k] = (int)sid;
+    t0_ms[k] = a; t1_ms[k] = b; work[k] = r.work; cat[k] = r.cat; stream_id[k] = (int)sid;
+    for (int q = 0; q < 4; ++q) dims[4 * k + q] = r.dims[q];
     ++k;
   }
   *n = k;

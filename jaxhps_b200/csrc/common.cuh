@@ -58,6 +58,7 @@ enum ProfCat { PROF_GEMM = 0, PROF_PANEL = 1, PROF_TRTRI = 2, PROF_LASWP = 3, PR
                PROF_SKINNY = 6, PROF_ASSEMBLE = 7, PROF_COMM = 8, PROF_WAIT = 9, PROF_NCAT = 10 };
 void prof_begin(int cat, cudaStream_t st, double work);
 void prof_end(int cat, cudaStream_t st);
+void prof_dims(int cat, int a, int b, int c, int d);  // optional shape note on the open record (GEMM: M, N, K, batch)
 
 #define HPS_TRY(expr)          \
   do {                         \

@@ -184,6 +184,7 @@ int dgemm(cudaStream_t st, int M, int N, int K, double alpha, const double* A, i
   g.lda = lda; g.sA = sA; g.ldb = ldb; g.sB = sB; g.ldc = ldc; g.sC = sC;
   g.vecA = vec_ok(A, lda, sA); g.vecB = vec_ok(B, ldb, sB); g.vecC = vec_ok(C, ldc, sC);
   prof_begin(PROF_GEMM, st, 2.0 * M * N * (double)K * batch);
+  prof_dims(PROF_GEMM, M, N, K, batch);
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = min(65535, batch - b0);
     g.A = A + (int64_t)b0 * sA; g.B = B + (int64_t)b0 * sB; g.C = C + (int64_t)b0 * sC;

@@ -633,56 +633,87 @@ __global__ void __launch_bounds__(TRI_THREADS) trtri_lower_kernel(const double* 
   }
 }
 
-// Inverse of the nb x nb UPPER-triangular diagonal blocks (with their diagonal) by COLUMN-WISE BACK SUBSTITUTION:
-// thread c solves U x_c = e_c, so every column of the inverse carries the backward error of a triangular solve.
-// The blocked formula  inv([[A,B],[0,C]]) = [[A^-1, -A^-1 (B C^-1)], [0, C^-1]]  used for the unit-lower blocks is
-// NOT accurate enough here: the pivot rows of the ItI leaf systems mix impedance rows (~1e2) with operator rows
-// (~1e5), |A^-1||B||C^-1| is then far larger than |X12| and the solve loses two digits against LAPACK
-// (tools/lu_accuracy.py, reproduced in NumPy).  All diagonal blocks of a factorisation are inverted by ONE launch
-// after the factorisation, off the critical path, so the 128 sequential rows per thread do not matter.
-// x_c is kept in row c of the tile's otherwise unused strictly-lower triangle (odd LD: conflict-free), the rows of
-// U are read as warp-wide broadcasts (every lane of a warp works on the same row r at the same time).
-__global__ void __launch_bounds__(NB) trtri_upper_kernel(const double* A, int64_t lda, int64_t sA, int j0, int n,
-                                                         double* W, int64_t sW) {
+// Inverse of the nb x nb UPPER-triangular diagonal blocks (with their diagonal) by BACK SUBSTITUTION, U X = I:
+// every column of the inverse carries the backward error of a triangular solve.  The blocked formula
+//   inv([[A,B],[0,C]]) = [[A^-1, -A^-1 (B C^-1)], [0, C^-1]]
+// used for the unit-lower blocks is NOT accurate enough here: the pivot rows of the ItI leaf systems mix impedance
+// rows with operator rows three orders of magnitude larger, |A^-1||B||C^-1| is then far larger than |X12| and the
+// solve loses two digits against LAPACK (tools/lu_accuracy.py, reproduced in NumPy).  Organisation: 32x32 blocks,
+// four phases by block distance d = J - I.  d = 0: the diagonal blocks, one column per lane.  d >= 1:
+//   W = sum_{K=I+1..J} U[I][K] X[K][J]   (all threads; plain products with finished blocks of X, no inverses)
+//   U[I][I] X[I][J] = -W                 (one column per lane, 32 sequential rows)
+// i.e. exactly the terms of the column-wise substitution, re-associated.  X[I][J], I < J, is kept in the unused
+// block (J, I) of the tile's lower triangle, the diagonal blocks of X in Xd.
+__global__ void __launch_bounds__(TRI_THREADS) trtri_upper_kernel(const double* A, int64_t lda, int64_t sA, int j0, int n,
+                                                                  double* W, int64_t sW) {
   extern __shared__ __align__(16) double sm[];
   constexpr int LD = TRI_LD;
-  double* Ts = sm;  // [NB][LD]
+  double* Ts = sm;                  // [NB][LD]     U in the upper triangle, X[I][J] (I < J) in block (J, I)
+  double* Xd = Ts + NB * LD;        // [4][32][33]  diagonal blocks of X
+  double* Ws = Xd + 4 * 32 * 33;    // [3][32][33]  right-hand sides of the current phase
   const int j = j0 + blockIdx.x * NB;
   const int nb = min(NB, n - j);
   const double* a = A + (int64_t)blockIdx.y * sA + (int64_t)j * lda + j;
-  for (int idx = threadIdx.x; idx < NB * NB; idx += NB) {  // ragged blocks are padded with the identity
+  for (int idx = threadIdx.x; idx < NB * NB; idx += TRI_THREADS) {  // ragged blocks are padded with the identity
     const int rr = idx / NB, cc = idx - rr * NB;
     double v = (rr == cc) ? 1.0 : 0.0;
     if (rr < nb && cc < nb) v = (cc >= rr) ? a[(int64_t)rr * lda + cc] : 0.0;
     Ts[rr * LD + cc] = v;
   }
   __syncthreads();
-  const int c = threadIdx.x;
-  double* x = Ts + c * LD;  // x[t] = X[t][c] for t < c
-  const double xc = 1.0 / x[c];
-  for (int r = (c | 31) - 1; r >= 0; --r) {  // warp-uniform row index
-    if (r < c) {
-      const double* u = Ts + r * LD;
-      double s0 = u[c] * xc, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int t = r + 1;
-      for (; t + 3 < c; t += 4) {
-        s0 = fma(u[t], x[t], s0);
-        s1 = fma(u[t + 1], x[t + 1], s1);
-        s2 = fma(u[t + 2], x[t + 2], s2);
-        s3 = fma(u[t + 3], x[t + 3], s3);
-      }
-      for (; t < c; ++t) s0 = fma(u[t], x[t], s0);
-      x[r] = -((s0 + s1) + (s2 + s3)) / u[r];
+  // ---- d = 0 ----
+  if (threadIdx.x < 128) {
+    const int blk = threadIdx.x >> 5, c = threadIdx.x & 31, base = blk * 32;
+    double* x = Xd + blk * 32 * 33;
+    const double* T = Ts + base * LD + base;
+    for (int r = c + 1; r < 32; ++r) x[r * 33 + c] = 0.0;
+    x[c * 33 + c] = 1.0 / T[c * LD + c];
+    for (int r = c - 1; r >= 0; --r) {
+      double s = 0.0;
+      for (int t = r + 1; t <= c; ++t) s = fma(T[r * LD + t], x[t * 33 + c], s);
+      x[r * 33 + c] = -s / T[r * LD + r];
     }
   }
   __syncthreads();
+  for (int d = 1; d < 4; ++d) {
+    const int nblk = 4 - d;
+    for (int idx = threadIdx.x; idx < nblk * 1024; idx += TRI_THREADS) {
+      const int I = idx >> 10, r = (idx >> 5) & 31, c = idx & 31, J = I + d;
+      const double* urow = Ts + (32 * I + r) * LD;
+      double s = 0.0;
+      for (int K = I + 1; K <= J; ++K) {
+        const double* xb = (K == J) ? (Xd + J * 32 * 33 + c) : (Ts + (32 * J) * LD + 32 * K + c);
+        const int xs = (K == J) ? 33 : LD;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) s = fma(urow[32 * K + k], xb[k * xs], s);
+      }
+      Ws[I * 32 * 33 + r * 33 + c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < nblk * 32) {
+      const int I = threadIdx.x >> 5, c = threadIdx.x & 31, J = I + d;
+      const double* T = Ts + (32 * I) * LD + 32 * I;   // U[I][I]
+      double* x = Ts + (32 * J) * LD + 32 * I + c;     // X[I][J][t][c] at x[t * LD]
+      const double* w = Ws + I * 32 * 33 + c;
+      for (int r = 31; r >= 0; --r) {
+        double s = w[r * 33];
+        for (int t = r + 1; t < 32; ++t) s = fma(T[r * LD + t], x[t * LD], s);
+        x[r * LD] = -s / T[r * LD + r];
+      }
+    }
+    __syncthreads();
+  }
   double* w = W + (int64_t)blockIdx.y * sW + (int64_t)(j / NB) * NB * NB;
-  for (int idx = threadIdx.x; idx < nb * nb; idx += NB) {
+  for (int idx = threadIdx.x; idx < nb * nb; idx += TRI_THREADS) {
     const int rr = idx / nb, cc = idx - rr * nb;
-    w[rr * NB + cc] = (rr < cc) ? Ts[cc * LD + rr] : ((rr == cc) ? 1.0 / Ts[rr * LD + rr] : 0.0);
+    const int I = rr >> 5, J = cc >> 5;
+    double v = 0.0;
+    if (I == J) v = Xd[I * 32 * 33 + (rr & 31) * 33 + (cc & 31)];   // zero below the diagonal by construction
+    else if (I < J) v = Ts[(32 * J + (rr & 31)) * LD + 32 * I + (cc & 31)];
+    w[rr * NB + cc] = v;
   }
 }
-constexpr size_t TRTRI_UPPER_SMEM = sizeof(double) * NB * (NB + 1);
+constexpr size_t TRTRI_UPPER_SMEM = sizeof(double) * (NB * (NB + 1) + 7 * 32 * 33);
 
 // dst[b][r][c] = src[b][r][c] for an (rows x cols) block
 __global__ void copy_block_kernel(double* dst, int64_t ldd, int64_t sD, const double* src, int64_t lds, int64_t sS,
@@ -1064,7 +1095,7 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
 
   // ---- 2. inverses of U's diagonal blocks (all at once), interchanges on the right-hand sides --
   prof_begin(PROF_TRTRI, s0, (double)batch * nblk * NB * NB * NB / 3);
-  trtri_upper_kernel<<<dim3(nblk, batch), NB, TRTRI_UPPER_SMEM, s0>>>(A.p, A.ld, A.stride, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
+  trtri_upper_kernel<<<dim3(nblk, batch), TRI_THREADS, TRTRI_UPPER_SMEM, s0>>>(A.p, A.ld, A.stride, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
   prof_end(PROF_TRTRI, s0);
   HPS_LAUNCH_CHECK("trtri_upper_kernel");
   for (int k = 0; k < n_rhs; ++k) {
@@ -1191,7 +1222,7 @@ int lu_dist_solve(cudaStream_t st, int n, double* A, int64_t lda, int n_rhs, con
   const Mat Am{A, lda, 0};
   const int nblk = (n + NB - 1) / NB;
   prof_begin(PROF_TRTRI, st, (double)nblk * NB * NB * NB / 3);
-  trtri_upper_kernel<<<dim3(nblk, 1), NB, TRTRI_UPPER_SMEM, st>>>(A, lda, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
+  trtri_upper_kernel<<<dim3(nblk, 1), TRI_THREADS, TRTRI_UPPER_SMEM, st>>>(A, lda, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
   prof_end(PROF_TRTRI, st);
   HPS_LAUNCH_CHECK("trtri_upper_kernel");
   for (int k = 0; k < n_rhs; ++k) {
@@ -1634,7 +1665,7 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
     HPS_CUDA(cudaStreamWaitEvent(s0, aux->sent, 0));
   }
   prof_begin(PROF_TRTRI, s0, (double)nblk * NB * NB * NB / 3);
-  trtri_upper_kernel<<<dim3(nblk, 1), NB, TRTRI_UPPER_SMEM, s0>>>(A, n, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
+  trtri_upper_kernel<<<dim3(nblk, 1), TRI_THREADS, TRTRI_UPPER_SMEM, s0>>>(A, n, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
   prof_end(PROF_TRTRI, s0);
   HPS_LAUNCH_CHECK("trtri_upper_kernel");
   for (int k = 0; k < n_rhs; ++k) HPS_TRY(trsm_upper(s0, 1, n, Am, w, rhs[k], 0, n));

@@ -53,10 +53,10 @@ if rank == 0:
           "residual", res, flush=True)
 # per-launch timeline of the profiled iteration, every rank: gpurun_out/dist_lu_timeline_w{world}_r{rank}.csv
 cap = 200000
-t0, t1 = (ctypes.c_double * cap)(), (ctypes.c_double * cap)()
-cat, sid = (ctypes.c_int * cap)(), (ctypes.c_int * cap)()
+t0, t1, wk = (ctypes.c_double * cap)(), (ctypes.c_double * cap)(), (ctypes.c_double * cap)()
+cat, sid, dims = (ctypes.c_int * cap)(), (ctypes.c_int * cap)(), (ctypes.c_int * (4 * cap))()
 nrec = ctypes.c_int64()
-lib.hps_prof_timeline(t0, t1, cat, sid, cap, ctypes.byref(nrec))
+lib.hps_prof_timeline(t0, t1, wk, cat, sid, dims, cap, ctypes.byref(nrec))
 os.makedirs("gpurun_out", exist_ok=True)
 with open(f"gpurun_out/dist_lu_timeline_w{world}_r{rank}.csv", "w") as f:
     f.write("t0_ms,t1_ms,category,stream\n")
