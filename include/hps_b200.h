@@ -184,6 +184,18 @@ int hps_lu_dist_segment_bytes(int n, size_t* bytes);
 int hps_lu_dist_matrix_ptr(void* comm, int n, double** A);
 int hps_lu_dist_run(void* comm, void* stream, int n, int n_rhs, double* const* rhs, const int64_t* ld_rhs,
                     const int* ncols, void* ws, size_t ws_bytes, int* info);
+/* hps_lu_dist_run with declared structure of rhs[0] (the root's -C_r in child-major order): its columns are n_seg
+ * segments of seg_cols columns, rows [0, seg_first_row[k]) of segment k exactly zero, seg_first_row non-decreasing
+ * (hps_root_cols_structure fills these for a range of root children).  The forward substitution then skips the
+ * leading zero rows (a third of its flops for an oct merge).  Valid only if the factorisation interchanges no rows
+ * — true for the HPS merge matrices in practice, verified on the device: info = -1 means rows DID move and the
+ * call must be repeated with hps_lu_dist_run on a freshly assembled matrix. */
+int hps_lu_dist_run_structured(void* comm, void* stream, int n, int n_rhs, double* const* rhs, const int64_t* ld_rhs,
+                               const int* ncols, int n_seg, int seg_cols, const int* seg_first_row, void* ws,
+                               size_t ws_bytes, int* info);
+/* seg_first_row[3 * n_local], *n_seg = 3 * n_local, *seg_cols = m for the root children child0 .. child0+n_local-1
+ * (reference interface order 9..20, merge/_uniform_3D_DtN.py:238-380). */
+int hps_root_cols_structure(int child0, int n_local, int m, int* n_seg, int* seg_cols, int* seg_first_row);
 /* rhs[k] := A^-1 rhs[k] with the factors the last hps_lu_dist_run left in this rank's segment (local; every rank
  * holds all of them).  The "factored root" mode of the sharded solver: the root S = -D^-1 C — two thirds of the
  * build's flops at L >= 3 — is never formed, each solve applies D^-1 to -C g - h_int instead. */

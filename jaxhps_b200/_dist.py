@@ -172,9 +172,27 @@ class P2PComm:
 USE_P2P = os.environ.get("HPS_DIST_P2P", "1") != "0"
 
 
-def p2p_lu_solve(_lib, dev, comm: "P2PComm", n: int, rhs, group=None) -> None:
+class StructureInvalid(Exception):
+    """The factorisation interchanged rows: a solve that skipped declared zero rows must be repeated without."""
+
+
+def root_cols_structure(_lib, first_child: int, n_local: int, m: int):
+    """``(n_seg, seg_cols, seg_first_row)`` of the root's ``-C_r`` for children ``first_child ..`` (child-major
+    columns): a child's exterior columns are zero above that child's first interface (``hps_root_cols_structure``)."""
+    import ctypes
+
+    n_seg, seg_cols = ctypes.c_int(), ctypes.c_int()
+    first = (ctypes.c_int * (3 * n_local))()
+    _lib.check(_lib.load().hps_root_cols_structure(first_child, n_local, m, ctypes.byref(n_seg), ctypes.byref(seg_cols), first),
+               "hps_root_cols_structure")
+    return n_seg.value, seg_cols.value, first
+
+
+def p2p_lu_solve(_lib, dev, comm: "P2PComm", n: int, rhs, group=None, structure=None) -> None:
     """``rhs[k] := D^-1 rhs[k]`` with D already assembled at ``comm.matrix_ptr(n)`` on every rank
-    (``hps_lu_dist_run``: one C call enqueues the whole factorisation, the P2P exchanges and the solves)."""
+    (``hps_lu_dist_run``: one C call enqueues the whole factorisation, the P2P exchanges and the solves).
+    ``structure``: leading-zero description of ``rhs[0]`` (:func:`root_cols_structure`); raises
+    :class:`StructureInvalid` when the factorisation moved rows (the caller re-assembles and solves without it)."""
     import ctypes
 
     lib = _lib.load()
@@ -186,10 +204,17 @@ def p2p_lu_solve(_lib, dev, comm: "P2PComm", n: int, rhs, group=None) -> None:
     ptrs = (ctypes.c_void_p * k)(*[r.data_ptr() for r in rhs])
     lds = (ctypes.c_int64 * k)(*[r.shape[1] for r in rhs])
     ncs = (ctypes.c_int * k)(*[r.shape[1] for r in rhs])
-    _lib.check(lib.hps_lu_dist_run(comm.handle, _lib.stream_ptr(), n, k, ptrs, lds, ncs, ws.data_ptr(), ws.numel(),
-                                   info.data_ptr()), "hps_lu_dist_run")
+    if structure is not None:
+        n_seg, seg_cols, first = structure
+        _lib.check(lib.hps_lu_dist_run_structured(comm.handle, _lib.stream_ptr(), n, k, ptrs, lds, ncs, n_seg, seg_cols, first,
+                                                  ws.data_ptr(), ws.numel(), info.data_ptr()), "hps_lu_dist_run_structured")
+    else:
+        _lib.check(lib.hps_lu_dist_run(comm.handle, _lib.stream_ptr(), n, k, ptrs, lds, ncs, ws.data_ptr(), ws.numel(),
+                                       info.data_ptr()), "hps_lu_dist_run")
     if comm.world > 1:
         dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
+    if int(info[0]) < 0:
+        raise StructureInvalid()
     _lib.check_info(info, "distributed factorisation")
 
 
@@ -331,6 +356,8 @@ class CudaOps:
     DIST_LU_MIN_N = int(os.environ.get("HPS_DIST_LU_MIN_N", "8192"))
     #: tests: run the step-wise (distributed) factorisation even on a single rank
     FORCE_DIST_LU = False
+    #: skip the structurally-zero leading rows of -C_r in the root's forward substitution (HPS_MERGE_STRUCT=0: off)
+    STRUCTURED = os.environ.get("HPS_MERGE_STRUCT", "1") != "0"
 
     def root_solve(self, Dblk_all, hblk_all, Cblk_loc, first_child: int, rank: int = 0, world: int = 1, group=None,
                    root_mode: str = "S"):
@@ -397,12 +424,23 @@ class CudaOps:
             # later store the factored columns into the same place on every peer
             comm = P2PComm.get(_lib, self.dev, rank, world, group)
             comm.ensure(comm.lu_segment_bytes(n))
-            rc = lib.hps_root_assemble_oct(_lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),
-                                           hblk_all.data_ptr(), Cblk_loc.data_ptr(), comm.matrix_ptr(n), S_r.data_ptr(),
-                                           g.data_ptr())
-            _lib.check(rc, "hps_root_assemble_oct")
+            def assemble():
+                rc = lib.hps_root_assemble_oct(_lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),
+                                               hblk_all.data_ptr(), Cblk_loc.data_ptr(), comm.matrix_ptr(n), S_r.data_ptr(),
+                                               g.data_ptr())
+                _lib.check(rc, "hps_root_assemble_oct")
+
+            assemble()
             # factored root: only g~ goes through the solve; S_r keeps -C_r for the solves
-            p2p_lu_solve(_lib, self.dev, comm, n, [g] if factored else [S_r, g], group)
+            if factored:
+                p2p_lu_solve(_lib, self.dev, comm, n, [g], group)
+                return S_r, g
+            structure = root_cols_structure(_lib, first_child, n_local, m) if self.STRUCTURED else None
+            try:
+                p2p_lu_solve(_lib, self.dev, comm, n, [S_r, g], group, structure)
+            except StructureInvalid:  # rows were interchanged: the zero-row shortcut does not apply to this matrix
+                assemble()
+                p2p_lu_solve(_lib, self.dev, comm, n, [S_r, g], group)
             return S_r, g
         D = self.empty((n, n))
         rc = lib.hps_root_assemble_oct(_lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),

@@ -59,6 +59,9 @@ _SIGNATURES = {
     "hps_lu_dist_segment_bytes": (_i, [_i, ctypes.POINTER(_sz)]),
     "hps_lu_dist_matrix_ptr": (_i, [_p, _i, ctypes.POINTER(_p)]),
     "hps_lu_dist_run": (_i, [_p, _p, _i, _i, ctypes.POINTER(_p), ctypes.POINTER(_l), ctypes.POINTER(_i), _p, _sz, _p]),
+    "hps_lu_dist_run_structured": (_i, [_p, _p, _i, _i, ctypes.POINTER(_p), ctypes.POINTER(_l), ctypes.POINTER(_i), _i, _i,
+                                        ctypes.POINTER(_i), _p, _sz, _p]),
+    "hps_root_cols_structure": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "hps_lu_dist_apply": (_i, [_p, _p, _i, _i, ctypes.POINTER(_p), ctypes.POINTER(_l), ctypes.POINTER(_i), _p, _sz]),
     "hps_down_oct_scatter": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "hps_merge_quad_dtn_level_workspace": (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),

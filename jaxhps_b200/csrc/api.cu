@@ -47,6 +47,7 @@ int aux_for_stream(cudaStream_t st, Aux*& out) {
     HPS_CUDA(cudaStreamCreateWithPriority(&a.comm_stream, cudaStreamNonBlocking, hi));
     HPS_CUDA(cudaEventCreateWithFlags(&a.factored, cudaEventDisableTiming));
     HPS_CUDA(cudaEventCreateWithFlags(&a.sent, cudaEventDisableTiming));
+    HPS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&a.host_flag), sizeof(int), cudaHostAllocDefault));
   }
   out = &a;
   return 0;
@@ -272,6 +273,28 @@ int hps_lu_dist_run(void* comm, void* stream, int n, int n_rhs, double* const* r
   RhsDesc d[4];
   for (int k = 0; k < n_rhs; ++k) d[k] = RhsDesc{rhs[k], ld_rhs[k], 0, ncols[k]};
   return lu_dist_run(static_cast<Comm*>(comm), static_cast<cudaStream_t>(stream), n, n_rhs, d, ws, ws_bytes, info);
+}
+int hps_lu_dist_run_structured(void* comm, void* stream, int n, int n_rhs, double* const* rhs, const int64_t* ld_rhs,
+                               const int* ncols, int n_seg, int seg_cols, const int* seg_first_row, void* ws,
+                               size_t ws_bytes, int* info) {
+  if (n_rhs < 1 || n_rhs > 4) return fail_arg(4, "n_rhs must be in [1, 4]");
+  if (n_seg < 0 || n_seg > RHS_MAX_SEG || (n_seg > 0 && (!seg_first_row || seg_cols <= 0 || (int64_t)n_seg * seg_cols != ncols[0])))
+    return fail_arg(8, "segments must tile rhs[0]: n_seg * seg_cols == ncols[0], n_seg <= 24");
+  RhsDesc d[4];
+  for (int k = 0; k < n_rhs; ++k) d[k] = RhsDesc{rhs[k], ld_rhs[k], 0, ncols[k]};
+  d[0].n_seg = n_seg;
+  d[0].seg_cols = seg_cols;
+  for (int k = 0; k < n_seg; ++k) {
+    if (k > 0 && seg_first_row[k] < seg_first_row[k - 1]) return fail_arg(10, "seg_first_row must be non-decreasing");
+    d[0].seg_first_row[k] = seg_first_row[k];
+  }
+  return lu_dist_run(static_cast<Comm*>(comm), static_cast<cudaStream_t>(stream), n, n_rhs, d, ws, ws_bytes, info);
+}
+int hps_root_cols_structure(int child0, int n_local, int m, int* n_seg, int* seg_cols, int* seg_first_row) {
+  if (n_local <= 0 || m <= 0 || child0 < 0 || child0 + n_local > 8 || !n_seg || !seg_cols || !seg_first_row)
+    return fail_arg(1, "bad child range / null output");
+  root_cols_structure(child0, n_local, m, *n_seg, *seg_cols, seg_first_row);
+  return 0;
 }
 int hps_lu_dist_apply(void* comm, void* stream, int n, int n_rhs, double* const* rhs, const int64_t* ld_rhs, const int* ncols,
                       void* ws, size_t ws_bytes) {

@@ -34,6 +34,7 @@ struct Aux {  // look-ahead stream + events of one (device, caller stream) pair
   cudaEvent_t fork = nullptr, join = nullptr;
   cudaStream_t comm_stream = nullptr;  // peer-to-peer sends that are off the critical path
   cudaEvent_t factored = nullptr, sent = nullptr;
+  int* host_flag = nullptr;  // pinned: "did the factorisation move rows?" read back by the structured solve
 };
 struct DeviceState {
   std::atomic<bool> gemm_configured{false};
@@ -100,11 +101,27 @@ int dgemm_affine(cudaStream_t st, int M, int N, int K, const double* A, int64_t 
                  int64_t ldb, int64_t sB, const double* Cin, int64_t ldcin, int64_t sCin, double* C, int64_t ldc,
                  int64_t sC, int batch);
 
+// A block of right-hand-side columns.  Optional structure (n_seg > 0): the columns form n_seg segments of seg_cols
+// columns each, and rows [0, seg_first_row[k]) of segment k are EXACTLY zero on entry, seg_first_row non-decreasing.
+// (The -C of an HPS merge in the reference's region order: a child's exterior columns are non-zero only on that
+// child's three interfaces.)  When the factorisation moved no rows, the forward substitution then never touches the
+// leading zero rows: L Z = B with B[:r] = 0 gives Z[:r] = 0.  Results are bit-identical to the unstructured solve.
+constexpr int RHS_MAX_SEG = 24;
 struct RhsDesc {
   double* ptr;
   int64_t ld;
   int64_t stride;
   int ncols;
+  int n_seg;
+  int seg_cols;
+  int seg_first_row[RHS_MAX_SEG];
+  // columns whose rows [0, r_end) can hold a non-zero: a prefix, because seg_first_row is sorted
+  int active_cols(int r_end) const {
+    if (n_seg <= 0) return ncols;
+    int k = 0;
+    while (k < n_seg && seg_first_row[k] < r_end) ++k;
+    return k == n_seg ? ncols : k * seg_cols;
+  }
 };
 size_t lu_workspace_bytes(int batch, int n);
 int lu_solve(cudaStream_t st, int batch, int n, double* A, int64_t lda, int64_t sA, int n_rhs,
@@ -150,6 +167,7 @@ int root_pack_oct(cudaStream_t st, int n_local, int child0, int m, int n_src, co
 size_t root_solve_oct_ws_bytes(int m);
 int root_assemble_oct(cudaStream_t st, int m, int n_src, int child0, int n_local, const double* Dblk_all,
                       const double* hblk_all, const double* Cblk_loc, double* D, double* S_r, double* gt);
+void root_cols_structure(int child0, int n_local, int m, int& n_seg, int& seg_cols, int* seg_first_row);
 int root_solve_oct(cudaStream_t st, int m, int n_src, int child0, int n_local, const double* Dblk_all,
                    const double* hblk_all, const double* Cblk_loc, double* S_r, double* gt, void* ws, size_t ws_bytes,
                    int* info);

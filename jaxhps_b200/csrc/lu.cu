@@ -245,8 +245,16 @@ struct BcArgs {
   int Gcap;
 };
 
-__host__ __device__ inline size_t bc_scratch_bytes(int Gcap) {
-  return (size_t)2 * Gcap * sizeof(BcCand) + (size_t)2 * NB * sizeof(double) + (size_t)IB * BC_UW * sizeof(double) + 256;
+// Tagged exchange (blockcol2_kernel): every 16-byte unit carries its own epoch, so no fence is needed anywhere.
+struct alignas(16) BcChunk { double v; unsigned long long tag; };
+struct alignas(16) BcCand2 {
+  BcChunk content[NB];
+  double val;          // |a|, negative when the CTA has no eligible row
+  int row;             // block-column-relative row index
+  unsigned flag;       // epoch of the column this candidate belongs to
+};
+__host__ __device__ inline size_t bc_scratch_bytes(int Gcap) {  // large enough for either layout
+  return (size_t)2 * Gcap * sizeof(BcCand2) + (size_t)2 * NB * sizeof(BcChunk) + (size_t)IB * BC_UW * sizeof(double) + 256;
 }
 inline size_t bc_smem_bytes(int rpc) {
   return sizeof(double) * ((((size_t)rpc * BC_LD + 1) & ~(size_t)1) + (size_t)IB * BC_UW + NB + 16) + sizeof(int) * 16;
@@ -263,12 +271,26 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;\n" ::: "memory"); }
 // The candidate header travels as one aligned 16-byte access (one L2 sector transaction), so a reader that sees
 // the new epoch in .y's upper half also sees the value and row stored with it.
-__device__ __forceinline__ void st_header(BcCand* c, double val, int row, unsigned flag) {
+template <typename C>
+__device__ __forceinline__ void st_header(C* c, double val, int row, unsigned flag) {
   const unsigned long long lo = (unsigned long long)__double_as_longlong(val);
   const unsigned long long hi = (unsigned long long)(unsigned)row | ((unsigned long long)flag << 32);
   asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};\n" ::"l"(&c->val), "l"(lo), "l"(hi) : "memory");
 }
-__device__ __forceinline__ void ld_header(const BcCand* c, double& val, int& row, unsigned& flag) {
+__device__ __forceinline__ void st_chunk(BcChunk* p, double v, unsigned tag) {
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};\n" ::"l"(p), "l"((unsigned long long)__double_as_longlong(v)),
+               "l"((unsigned long long)tag)
+               : "memory");
+}
+__device__ __forceinline__ double ld_chunk_spin(const BcChunk* p, unsigned tag) {  // until the unit carries this epoch
+  unsigned long long lo, hi;
+  do {
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];\n" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+  } while ((unsigned)hi != tag);
+  return __longlong_as_double((long long)lo);
+}
+template <typename C>
+__device__ __forceinline__ void ld_header(const C* c, double& val, int& row, unsigned& flag) {
   unsigned long long lo, hi;
   asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];\n" : "=l"(lo), "=l"(hi) : "l"(&c->val) : "memory");
   val = __longlong_as_double((long long)lo);
@@ -510,6 +532,249 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol_kernel(BcArgs a) {
   }
 }
 
+// Block column shared by G co-scheduled CTAs, second generation.  ncu on the kernel above (n = 19200, G = 96) showed
+// 71 % of its 6.9 us per column in the pivot election: a fence before the header store, ONE warp polling all G
+// headers four per lane (each re-poll a full L2 round trip), a second fence, and 15 of 16 warps parked at the barrier.
+// Here every 16-byte unit that crosses CTAs carries its own epoch (BcChunk / header), so nothing is fenced and no
+// barrier sits between the content stores and the header store; thread k < G polls header k and nothing else, the
+// polling warps reduce by shuffles and every thread finishes the <= 5 partials itself; the next column's local
+// arg-max is taken from the registers of the rank-1 update (no shared-memory scan, no barrier after the update).
+// Three CTA barriers per column instead of six.
+constexpr int BC_NPW = (BC_MAX_G + 31) / 32;  // polling warps
+__global__ void __launch_bounds__(BC_THREADS, 1) blockcol2_kernel(BcArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int LD = BC_LD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = blockIdx.x, mat = blockIdx.y;
+  const int G = a.G, jb = a.jb;
+  const int rows = a.n - a.j;
+  const int r0 = min(rows, g * a.rpc), r1 = min(rows, r0 + a.rpc), nr = r1 - r0;
+  double* A = a.A + (int64_t)mat * a.sA + (int64_t)a.j * a.lda + a.j;
+  int* ipiv = a.ipiv + (int64_t)mat * a.n + a.j;
+
+  double* tile = sm;                                   // [rpc][LD]
+  double* U = tile + (((size_t)a.rpc * LD + 1) & ~(size_t)1);  // [IB][BC_UW]
+  double* prow = U + IB * BC_UW;                       // [NB]
+  double* red_val = prow + NB;                         // [16]
+  int* red_idx = reinterpret_cast<int*>(red_val + 16); // [16]
+  __shared__ double s_pv[BC_NPW];
+  __shared__ int s_pr[BC_NPW], s_pg[BC_NPW];
+
+  char* sc = a.scratch + (size_t)mat * a.scratch_stride;
+  BcCand2* cands = reinterpret_cast<BcCand2*>(sc);                                         // [2][Gcap]
+  BcChunk* diag = reinterpret_cast<BcChunk*>(sc + (size_t)2 * a.Gcap * sizeof(BcCand2));   // [2][NB]
+  double* u12g = reinterpret_cast<double*>(diag + 2 * NB);                                 // [IB][BC_UW]
+  unsigned* u12_flag = reinterpret_cast<unsigned*>(u12g + IB * BC_UW);
+
+  for (int idx = tid; idx < nr * jb; idx += BC_THREADS) {
+    const int r = idx / jb, c = idx - r * jb;
+    tile[r * LD + c] = A[(int64_t)(r0 + r) * a.lda + c];
+  }
+  __syncthreads();
+
+  double cv = -1.0;       // this thread's candidate for the next column, taken from the rows it has just updated
+  int cr = 0x7fffffff;
+  bool scan = true;       // no carried candidate: scan the column in shared memory
+  for (int c = 0; c < jb; ++c) {
+    const int c0 = (c / IB) * IB, pe = min(c0 + IB, jb);
+    // ---- local arg-max of |a[r][c]| over rows >= c (lowest row wins ties) ----
+    double best = -1.0;
+    int bidx = 0x7fffffff;
+    if (scan) {
+      for (int r = tid; r < nr; r += BC_THREADS) {
+        if (r0 + r >= c) {
+          const double v = fabs(tile[r * LD + c]);
+          if (v > best) { best = v; bidx = r; }
+        }
+      }
+    } else {
+      best = cv; bidx = cr;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    if (lane == 0) { red_val[warp] = best; red_idx[warp] = bidx; }
+    __syncthreads();  // (1) also orders the previous column's update before the content stores below
+    best = -1.0; bidx = 0x7fffffff;
+#pragma unroll
+    for (int w = 0; w < BC_THREADS / 32; ++w) {
+      const double ov = red_val[w];
+      const int oi = red_idx[w];
+      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+
+    // ---- publish: candidate row, the row that will be displaced (row c), header; no fence, no barrier ----
+    const unsigned epoch = (unsigned)(a.j + c + 1);
+    BcCand2* mine = cands + (size_t)(c & 1) * a.Gcap + g;
+    BcChunk* dg = diag + (c & 1) * NB;
+    if (tid < jb) {
+      if (best >= 0.0) st_chunk(&mine->content[tid], tile[bidx * LD + tid], epoch);
+    } else if (tid >= NB && tid < NB + jb) {
+      if (c >= r0 && c < r1) st_chunk(&dg[tid - NB], tile[(c - r0) * LD + tid - NB], epoch);
+    } else if (tid == 2 * NB) {
+      st_header(mine, best, (best >= 0.0) ? r0 + bidx : -1, epoch);
+    }
+    // ---- election: thread k polls CTA k's header; largest value, lowest row on ties ----
+    double wv = -1.0;
+    int wr = 0x7fffffff, wg = 0;
+    if (warp < BC_NPW) {
+      if (tid < G) {
+        double hv; int hr; unsigned hf;
+        const BcCand2* his = cands + (size_t)(c & 1) * a.Gcap + tid;
+        do { ld_header(his, hv, hr, hf); } while (hf != epoch);
+        if (hv >= 0.0) { wv = hv; wr = hr; wg = tid; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, wv, o);
+        const int og = __shfl_xor_sync(0xffffffffu, wg, o);
+        const int orr = __shfl_xor_sync(0xffffffffu, wr, o);
+        if (ov > wv || (ov == wv && orr < wr)) { wv = ov; wg = og; wr = orr; }
+      }
+      if (lane == 0) { s_pv[warp] = wv; s_pr[warp] = wr; s_pg[warp] = wg; }
+    }
+    __syncthreads();  // (2)
+    wv = -1.0; wr = 0x7fffffff; wg = 0;
+#pragma unroll
+    for (int w = 0; w < BC_NPW; ++w) {
+      const double ov = s_pv[w];
+      const int orr = s_pr[w], og = s_pg[w];
+      if (ov > wv || (ov == wv && orr < wr)) { wv = ov; wg = og; wr = orr; }
+    }
+    const bool has = wv >= 0.0;      // false only for a column of NaNs (or an empty one): reported as singular
+    const int p = has ? wr : c;      // block-column-relative pivot row
+    if (has) {
+      if (tid < jb) {
+        const double x = ld_chunk_spin(&cands[(size_t)(c & 1) * a.Gcap + wg].content[tid], epoch);
+        prow[tid] = x;
+        if (c >= r0 && c < r1) tile[(c - r0) * LD + tid] = x;  // the pivot row moves up to row c ...
+      } else if (tid >= NB && tid < NB + jb) {
+        if (p != c && p >= r0 && p < r1) tile[(p - r0) * LD + tid - NB] = ld_chunk_spin(&dg[tid - NB], epoch);  // ... row c takes its place
+      }
+    }
+    __syncthreads();  // (3)
+    if (g == 0 && tid == 0) ipiv[c] = a.j + p;
+    const double piv = has ? prow[c] : 0.0;
+    cv = -1.0; cr = 0x7fffffff;
+    scan = true;
+    if (piv == 0.0) {
+      if (g == 0 && tid == 0 && a.info[mat] == 0) a.info[mat] = a.j + c + 1;
+    } else {
+      // ---- scale the column, rank-1 update of the rest of the inner panel; keep |a[r][c+1]| for the next election ----
+      for (int r = tid; r < nr; r += BC_THREADS) {
+        if (r0 + r > c) {
+          double* row = tile + r * LD;
+          const double l = row[c] / piv;
+          row[c] = l;
+          double nv = -1.0;
+#pragma unroll
+          for (int h = 0; h < IB; h += 16) {  // loads first, stores last (prow / row may alias for the compiler); 16 at a time
+            double x[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+              x[t] = (c0 + h + t > c && c0 + h + t < pe) ? fma(-l, prow[c0 + h + t], row[c0 + h + t]) : 0.0;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              if (c0 + h + t > c && c0 + h + t < pe) row[c0 + h + t] = x[t];
+              if (c0 + h + t == c + 1) nv = fabs(x[t]);
+            }
+          }
+          if (nv > cv) { cv = nv; cr = r; }
+        }
+      }
+      scan = (c + 1 >= pe);  // the first column of the next inner panel comes out of the trailing update below
+    }
+
+    if (c == pe - 1 && pe < jb) {
+      __syncthreads();
+      // ---- inner panel finished: U12 = L11^-1 A12, then rows >= pe get A22 -= L21 U12 ----
+      const int W = jb - pe;
+      if (g == 0) {
+        if (tid < W) {
+          double x[IB];
+#pragma unroll
+          for (int r = 0; r < IB; ++r) x[r] = tile[(c0 + r) * LD + pe + tid];
+#pragma unroll
+          for (int r = 1; r < IB; ++r) {
+            double s = x[r];
+#pragma unroll
+            for (int t = 0; t < r; ++t) s = fma(-tile[(c0 + r) * LD + c0 + t], x[t], s);
+            x[r] = s;
+          }
+#pragma unroll
+          for (int r = 0; r < IB; ++r) {
+            tile[(c0 + r) * LD + pe + tid] = x[r];
+            U[r * BC_UW + tid] = x[r];
+            u12g[r * BC_UW + tid] = x[r];
+          }
+        }
+        __syncthreads();
+        if (tid == 0) st_release_u32(u12_flag, (unsigned)(a.j + pe));
+      } else {
+        if (tid == 0) {
+          while (ld_acquire_u32(u12_flag) != (unsigned)(a.j + pe)) { }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < IB * W; idx += BC_THREADS) {
+          const int r = idx / W, x = idx - r * W;
+          U[r * BC_UW + x] = __ldcg(&u12g[r * BC_UW + x]);
+        }
+        __syncthreads();
+      }
+      const int ly = lane >> 3, lx = lane & 7;
+      const int nstrips = (nr + 15) >> 4, ncp = (W + 31) >> 5;
+      for (int s = warp; s < nstrips; s += BC_THREADS / 32) {
+        const int rb = s * 16 + ly * 4;
+        if (r0 + s * 16 + 15 < pe) continue;
+        const double* ap[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ap[i] = tile + min(rb + i, a.rpc - 1) * LD + c0;
+        for (int cp = 0; cp < ncp; ++cp) {
+          const int cb = cp * 32 + lx * 4;
+          double acc[4][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
+          if (cb < BC_UW) {
+#pragma unroll 8
+            for (int k = 0; k < IB; ++k) {
+              const double2 b01 = *reinterpret_cast<const double2*>(U + k * BC_UW + cb);
+              const double2 b23 = *reinterpret_cast<const double2*>(U + k * BC_UW + cb + 2);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const double av = ap[i][k];
+                acc[i][0] = fma(av, b01.x, acc[i][0]);
+                acc[i][1] = fma(av, b01.y, acc[i][1]);
+                acc[i][2] = fma(av, b23.x, acc[i][2]);
+                acc[i][3] = fma(av, b23.y, acc[i][3]);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = rb + i;
+            if (r < nr && r0 + r >= pe) {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                if (cb + jj < W) tile[r * LD + pe + cb + jj] -= acc[i][jj];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nr * jb; idx += BC_THREADS) {
+    const int r = idx / jb, c = idx - r * jb;
+    A[(int64_t)(r0 + r) * a.lda + c] = tile[r * LD + c];
+  }
+}
+
 constexpr size_t PANEL_SMEM = sizeof(double) * ((size_t)PANEL_ROWS * PANEL_LD + IB + 16) + sizeof(int) * 16;
 
 // rows k0..k1-1 of every matrix are exchanged with rows ipiv[k] on columns [c0, c0+ncols)
@@ -526,6 +791,98 @@ __global__ void laswp_kernel(double* A, int64_t lda, int64_t sA, int c0, int nco
       a[(int64_t)k * lda] = a[(int64_t)p * lda];
       a[(int64_t)p * lda] = t;
     }
+  }
+}
+
+// Same interchanges for a SHORT pivot range (k1 - k0 <= NB), in two parallel phases instead of k1 - k0 dependent
+// swaps per thread (which made every call cost ~0.6 us x 128 whatever the column count — on the critical chain
+// of the factorisation):
+//   1. warp 0 composes the swaps into a move list "row dst[e] receives old row src[e]" (at most 2 (k1 - k0) rows
+//      are touched: the range itself and the distinct pivot rows below it);
+//   2. all threads gather the source rows of a 32-column tile into shared memory and scatter them to their
+//      destinations (coalesced row segments, nmov/8 independent loads per thread).
+// A CTA composes once and then walks over column tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+constexpr int LASWP_COLS = 32, LASWP_THREADS = 256;
+constexpr size_t LASWP_SMEM = sizeof(double) * 2 * NB * LASWP_COLS;
+__global__ void __launch_bounds__(LASWP_THREADS) laswp_block_kernel(double* A, int64_t lda, int64_t sA, int c0, int ncols,
+                                                                    const int* ipiv, int n_ipiv, int k0, int k1) {
+  extern __shared__ __align__(16) double sm[];  // [nmov][LASWP_COLS]
+  __shared__ int s_piv[NB], cur_top[NB], out_row[NB], out_cur[NB], dst[2 * NB], src[2 * NB];
+  __shared__ int s_nmov;
+  const int nk = k1 - k0, tid = threadIdx.x;
+  const int* piv = ipiv + (int64_t)blockIdx.y * n_ipiv + k0;
+  for (int i = tid; i < nk; i += LASWP_THREADS) { s_piv[i] = piv[i]; cur_top[i] = k0 + i; }
+  __syncthreads();
+  if (tid < 32) {
+    const int lane = tid;
+    int nout = 0;  // warp-uniform
+    for (int k = 0; k < nk; ++k) {
+      const int p = s_piv[k];
+      if (p == k0 + k) continue;
+      if (p < k1) {
+        if (lane == 0) { const int t = cur_top[k]; cur_top[k] = cur_top[p - k0]; cur_top[p - k0] = t; }
+      } else {
+        int found = -1;
+        for (int base = 0; base < nout; base += 32) {
+          const int i = base + lane;
+          const unsigned m = __ballot_sync(0xffffffffu, i < nout && out_row[i] == p);
+          if (m) { found = base + __ffs(m) - 1; break; }
+        }
+        if (found < 0) {
+          found = nout++;
+          if (lane == 0) { out_row[found] = p; out_cur[found] = p; }
+        }
+        __syncwarp();
+        if (lane == 0) { const int t = cur_top[k]; cur_top[k] = out_cur[found]; out_cur[found] = t; }
+      }
+      __syncwarp();
+    }
+    int cnt = 0;
+    for (int base = 0; base < nk; base += 32) {
+      const int i = base + lane;
+      const bool mv = i < nk && cur_top[i] != k0 + i;
+      const unsigned m = __ballot_sync(0xffffffffu, mv);
+      if (mv) { const int pos = cnt + __popc(m & ((1u << lane) - 1u)); dst[pos] = k0 + i; src[pos] = cur_top[i]; }
+      cnt += __popc(m);
+    }
+    for (int base = 0; base < nout; base += 32) {
+      const int i = base + lane;
+      const bool mv = i < nout && out_cur[i] != out_row[i];
+      const unsigned m = __ballot_sync(0xffffffffu, mv);
+      if (mv) { const int pos = cnt + __popc(m & ((1u << lane) - 1u)); dst[pos] = out_row[i]; src[pos] = out_cur[i]; }
+      cnt += __popc(m);
+    }
+    if (lane == 0) s_nmov = cnt;
+  }
+  __syncthreads();
+  const int nmov = s_nmov;
+  if (nmov == 0) return;
+  const int tx = tid & 31, ty = tid >> 5;
+  const int ntiles = (ncols + LASWP_COLS - 1) / LASWP_COLS;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int col = t * LASWP_COLS + tx;
+    double* a = A + (int64_t)blockIdx.y * sA + c0 + col;
+    if (col < ncols)
+      for (int e = ty; e < nmov; e += LASWP_THREADS / 32) sm[e * LASWP_COLS + tx] = a[(int64_t)src[e] * lda];
+    __syncthreads();
+    if (col < ncols)
+      for (int e = ty; e < nmov; e += LASWP_THREADS / 32) a[(int64_t)dst[e] * lda] = sm[e * LASWP_COLS + tx];
+    __syncthreads();
+  }
+}
+
+// interchanges k0..k1-1 on columns [c0, c0 + ncols) of `batch` matrices sA apart (no profiling, no checks)
+inline void launch_laswp(cudaStream_t st, int batch, double* A, int64_t lda, int64_t sA, int c0, int ncols, const int* ipiv,
+                         int n_ipiv, int k0, int k1) {
+  // Measured on B200 (gpurun_out/c18_bench_lu.txt): 87 us per call against 74 us for the serial kernel inside a
+  // factorisation (composition + 64 KB of shared memory next to the GEMM CTAs), so it is opt-in: HPS_LASWP=block.
+  static const bool block = [] { const char* e = std::getenv("HPS_LASWP"); return e && e[0] == 'b'; }();
+  if (k1 - k0 <= NB && block) {
+    const int ntiles = (ncols + LASWP_COLS - 1) / LASWP_COLS;
+    const int gx = std::max(1, std::min(ntiles, 888 / std::max(1, batch)));
+    laswp_block_kernel<<<dim3(gx, batch), LASWP_THREADS, LASWP_SMEM, st>>>(A, lda, sA, c0, ncols, ipiv, n_ipiv, k0, k1);
+  } else {
+    laswp_kernel<<<dim3((ncols + 255) / 256, batch), 256, 0, st>>>(A, lda, sA, c0, ncols, ipiv, n_ipiv, k0, k1);
   }
 }
 
@@ -836,7 +1193,7 @@ int laswp(cudaStream_t st, int batch, double* A, int64_t lda, int64_t sA, int c0
           int k0, int k1) {
   if (ncols <= 0 || k1 <= k0) return 0;
   prof_begin(PROF_LASWP, st, (double)batch * ncols * (k1 - k0));
-  laswp_kernel<<<dim3((ncols + 255) / 256, batch), 256, 0, st>>>(A, lda, sA, c0, ncols, ipiv, n, k0, k1);
+  launch_laswp(st, batch, A, lda, sA, c0, ncols, ipiv, n, k0, k1);
   prof_end(PROF_LASWP, st);
   HPS_LAUNCH_CHECK("laswp_kernel");
   return 0;
@@ -849,11 +1206,13 @@ int configure_lu_kernels() {
   if (ds->lu_configured.load(std::memory_order_acquire)) return 0;  // idempotent: a race only repeats the calls
     HPS_CUDA(cudaFuncSetAttribute(blockcol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc_smem_bytes(BC_ROWS)));
     HPS_CUDA(cudaFuncSetAttribute(blockcol_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc_smem_bytes(BC_ROWS)));
+    HPS_CUDA(cudaFuncSetAttribute(blockcol2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc_smem_bytes(BC_ROWS)));
     HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(trtri_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(trtri_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_UPPER_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(laswp_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LASWP_SMEM));
   ds->lu_configured.store(true, std::memory_order_release);
   return 0;
 }
@@ -894,6 +1253,9 @@ int launch_blockcol(cudaStream_t st, int batch, int n, double* A, int64_t lda, i
     done = true;
     return 0;
   }
+  // HPS_BLOCKCOL=fenced selects the first-generation exchange (fence + header polled by one warp)
+  static const bool fenced = [] { const char* e = std::getenv("HPS_BLOCKCOL"); return e && e[0] == 'f'; }();
+  void (*shared_kernel)(BcArgs) = fenced ? blockcol_kernel<true> : blockcol2_kernel;
   if (G <= 8) {  // one thread-block cluster per matrix: co-scheduled by the hardware
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G, batch);
@@ -908,7 +1270,7 @@ int launch_blockcol(cudaStream_t st, int batch, int n, double* A, int64_t lda, i
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     prof_begin(PROF_PANEL, st, (double)batch * rows * jb);
-    HPS_CUDA(cudaLaunchKernelEx(&cfg, blockcol_kernel<true>, a));
+    HPS_CUDA(cudaLaunchKernelEx(&cfg, shared_kernel, a));
     prof_end(PROF_PANEL, st);
     ++g_launches;
     done = true;
@@ -918,7 +1280,7 @@ int launch_blockcol(cudaStream_t st, int batch, int n, double* A, int64_t lda, i
   int dev = 0, sms = 0, per_sm = 0;
   HPS_CUDA(cudaGetDevice(&dev));
   HPS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  HPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blockcol_kernel<true>, BC_THREADS, smem));
+  HPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shared_kernel, BC_THREADS, smem));
   const int per_launch = (sms * per_sm) / G;
   if (per_launch < 1) return 0;
   prof_begin(PROF_PANEL, st, (double)batch * rows * jb);
@@ -930,7 +1292,7 @@ int launch_blockcol(cudaStream_t st, int batch, int n, double* A, int64_t lda, i
     sub.info = info + b0;
     sub.scratch = w.bc_scratch + (size_t)b0 * w.bc_stride;
     void* args[] = {&sub};
-    HPS_CUDA(cudaLaunchCooperativeKernel((void*)blockcol_kernel<true>, dim3(G, nb), dim3(BC_THREADS), args, smem, st));
+    HPS_CUDA(cudaLaunchCooperativeKernel((void*)shared_kernel, dim3(G, nb), dim3(BC_THREADS), args, smem, st));
     ++g_launches;
   }
   prof_end(PROF_PANEL, st);
@@ -1009,19 +1371,59 @@ int update_columns(cudaStream_t st, int batch, int n, const Mat& A, int j, int j
   return 0;
 }
 
-// L Z = B in place on rows [r0, r1) of X (unit lower, diagonal blocks pre-inverted)
-int trsm_lower(cudaStream_t st, int batch, int n, const Mat& A, const LuWorkspace& w, const RhsDesc& X, int r0, int r1) {
+// L Z = B in place on rows [r0, r1) of X (unit lower, diagonal blocks pre-inverted).  With `structured` the
+// leading zero rows described by X.seg_first_row are never touched: a node of the recursion works on the columns
+// that can be non-zero in its row range, which is a prefix of X because the segments are sorted.
+int trsm_lower(cudaStream_t st, int batch, int n, const Mat& A, const LuWorkspace& w, const RhsDesc& X, int r0, int r1,
+               bool structured = false) {
   const int nblk = (n + NB - 1) / NB;
   const int64_t sW = (int64_t)nblk * NB * NB;
+  const int nc = structured ? X.active_cols(r1) : X.ncols;  // columns with a possibly non-zero row below r1
+  if (nc <= 0) return 0;
   if (r1 - r0 <= NB)
     return tri_mult(st, batch, r1 - r0, w.Linv + (int64_t)(r0 / NB) * NB * NB, sW, X.ptr + (int64_t)r0 * X.ld, X.ld,
-                    X.stride, X.ncols, w.tmp);
+                    X.stride, nc, w.tmp);
   const int blocks = (r1 - r0 + NB - 1) / NB;
   const int mid = r0 + (blocks / 2) * NB;
-  HPS_TRY(trsm_lower(st, batch, n, A, w, X, r0, mid));
-  HPS_TRY(dgemm(st, r1 - mid, X.ncols, mid - r0, -1.0, A.at(mid, r0), A.ld, A.stride, X.ptr + (int64_t)r0 * X.ld, X.ld,
-                X.stride, 1.0, X.ptr + (int64_t)mid * X.ld, X.ld, X.stride, batch));
-  return trsm_lower(st, batch, n, A, w, X, mid, r1);
+  HPS_TRY(trsm_lower(st, batch, n, A, w, X, r0, mid, structured));
+  if (!structured) {
+    HPS_TRY(dgemm(st, r1 - mid, X.ncols, mid - r0, -1.0, A.at(mid, r0), A.ld, A.stride, X.ptr + (int64_t)r0 * X.ld, X.ld,
+                  X.stride, 1.0, X.ptr + (int64_t)mid * X.ld, X.ld, X.stride, batch));
+  } else {
+    // X[mid:r1) -= L[mid:r1, r0:mid) Z[r0:mid), column group by column group: a group whose first non-zero row is f
+    // has Z[r0:f) == 0, so its product starts at row max(r0, f) (rounded down to an even row: 16-byte alignment);
+    // groups that share the same start go out as one product, groups with f >= mid contribute nothing
+    int k = 0;
+    while (k < X.n_seg) {
+      const int f = X.seg_first_row[k];
+      if (f >= mid) break;
+      const int ks = std::max(r0, f & ~1);
+      int k2 = k + 1;
+      while (k2 < X.n_seg && std::max(r0, X.seg_first_row[k2] & ~1) == ks && X.seg_first_row[k2] < mid) ++k2;
+      const int c_lo = k * X.seg_cols, c_hi = (k2 == X.n_seg) ? X.ncols : k2 * X.seg_cols;
+      HPS_TRY(dgemm(st, r1 - mid, c_hi - c_lo, mid - ks, -1.0, A.at(mid, ks), A.ld, A.stride,
+                    X.ptr + (int64_t)ks * X.ld + c_lo, X.ld, X.stride, 1.0, X.ptr + (int64_t)mid * X.ld + c_lo, X.ld, X.stride,
+                    batch));
+      k = k2;
+    }
+  }
+  return trsm_lower(st, batch, n, A, w, X, mid, r1, structured);
+}
+
+// info[0] := -1 (if still 0) when some ipiv[k] != k: the structured forward substitution of a run that could not
+// ask the host (lu_dist_run) was not valid and the caller must repeat the solve without the structure
+__global__ void pivots_moved_info_kernel(const int* __restrict__ ipiv, int n, int* __restrict__ info) {
+  bool moved = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) moved |= ipiv[i] != i;
+  if (__syncthreads_or(moved) && threadIdx.x == 0) atomicCAS(info, 0, -1);
+}
+
+// flag[0] != 0 iff some ipiv[k] != k (the factorisation moved rows)
+__global__ void pivots_moved_kernel(const int* __restrict__ ipiv, int64_t total, int n, int* __restrict__ flag) {
+  bool moved = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    moved |= ipiv[i] != (int)(i % n);
+  if (__syncthreads_or(moved) && threadIdx.x == 0) atomicOr(flag, 1);
 }
 
 // U X = Z in place on rows [r0, r1) of X
@@ -1086,9 +1488,13 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
     }
     // s0: interchanges on the columns to the left (L in LAPACK form), then the rest of the
     // trailing matrix
-    HPS_TRY(update_columns(s0, batch, n, A, j, jb, 0, j, w));
-    HPS_TRY(update_columns(s0, batch, n, A, j, jb, next + nextb, n - (next + nextb), w));
+    // The block column that s1 factors at the NEXT step goes first and gets its own event, so the chain never waits
+    // for the bulk of this trailing update.
+    const int rest0 = next + nextb, pri = (rest0 < n) ? min(NB, n - rest0) : 0;
+    HPS_TRY(update_columns(s0, batch, n, A, j, jb, rest0, pri, w));
     HPS_CUDA(cudaEventRecord(aux->update_done[b & 1], s0));
+    HPS_TRY(update_columns(s0, batch, n, A, j, jb, rest0 + pri, n - (rest0 + pri), w));
+    HPS_TRY(update_columns(s0, batch, n, A, j, jb, 0, j, w));
   }
   // s1 has nothing pending beyond panel_done[(nblk-1)&1], which s0 has waited on.
   if (n_rhs == 0) return 0;
@@ -1098,10 +1504,28 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
   trtri_upper_kernel<<<dim3(nblk, batch), TRI_THREADS, TRTRI_UPPER_SMEM, s0>>>(A.p, A.ld, A.stride, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
   prof_end(PROF_TRTRI, s0);
   HPS_LAUNCH_CHECK("trtri_upper_kernel");
+  // Right-hand sides with declared leading zero rows: the shortcut is valid only if no interchange happened (the
+  // HPS merge matrices D never pivot in practice).  ONE host round trip decides; it costs a pipeline bubble of a
+  // few tens of microseconds and removes ~37 % of an oct merge's forward-substitution flops.
+  bool structured = false;
+  for (int k = 0; k < n_rhs; ++k) structured |= rhs[k].n_seg > 0;
+  static const bool no_struct = [] { const char* e = std::getenv("HPS_LU_STRUCT"); return e && e[0] == '0'; }();
+  if (structured && no_struct) structured = false;
+  if (structured) {
+    int* flag = reinterpret_cast<int*>(w.tmp);  // tmp is idle until the substitutions start
+    HPS_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s0));
+    const int64_t total = (int64_t)batch * n;
+    pivots_moved_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 1024), 256, 0, s0>>>(w.ipiv, total, n, flag);
+    HPS_LAUNCH_CHECK("pivots_moved_kernel");
+    HPS_CUDA(cudaMemcpyAsync(aux->host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, s0));
+    HPS_CUDA(cudaStreamSynchronize(s0));
+    structured = *aux->host_flag == 0;
+  }
   for (int k = 0; k < n_rhs; ++k) {
-    HPS_TRY(laswp(s0, batch, rhs[k].ptr, rhs[k].ld, rhs[k].stride, 0, rhs[k].ncols, w.ipiv, n, 0, n));
+    if (!structured)  // with `structured` every ipiv[k] == k: nothing to interchange
+      HPS_TRY(laswp(s0, batch, rhs[k].ptr, rhs[k].ld, rhs[k].stride, 0, rhs[k].ncols, w.ipiv, n, 0, n));
     // ---- 3. recursive substitutions --------------------------------------------------------
-    HPS_TRY(trsm_lower(s0, batch, n, A, w, rhs[k], 0, n));
+    HPS_TRY(trsm_lower(s0, batch, n, A, w, rhs[k], 0, n, structured));
     HPS_TRY(trsm_upper(s0, batch, n, A, w, rhs[k], 0, n));
   }
   return 0;
@@ -1199,7 +1623,7 @@ int lu_dist_update(cudaStream_t st, int n, double* A, int64_t lda, int b, int fi
   const int64_t sBlk = (int64_t)block_stride * NB;
   auto apply = [&](int c0, int nc, int batch) -> int {
     prof_begin(PROF_LASWP, st, (double)batch * nc * jb);
-    laswp_kernel<<<dim3((nc + 255) / 256, batch), 256, 0, st>>>(A, lda, sBlk, c0, nc, w.ipiv, 0, j, j + jb);
+    launch_laswp(st, batch, A, lda, sBlk, c0, nc, w.ipiv, 0, j, j + jb);
     prof_end(PROF_LASWP, st);
     HPS_LAUNCH_CHECK("laswp_kernel");
     HPS_TRY(tri_mult(st, batch, jb, Linv, 0, Am.at(j, c0), lda, sBlk, nc, w.tmp));
@@ -1425,7 +1849,7 @@ int dist_apply(cudaStream_t st, int n, const Mat& Am, int j, int jb, const LuWor
   const double* Linv = w.Linv + (int64_t)b * NB * NB;
   const int below = n - (j + jb);
   prof_begin(PROF_LASWP, st, (double)batch * nc * jb);
-  laswp_kernel<<<dim3((nc + 255) / 256, batch), 256, 0, st>>>(X, ld, sX, 0, nc, w.ipiv, 0, j, j + jb);
+  launch_laswp(st, batch, X, ld, sX, 0, nc, w.ipiv, 0, j, j + jb);
   prof_end(PROF_LASWP, st);
   HPS_LAUNCH_CHECK("laswp_kernel");
   HPS_TRY(tri_mult(st, batch, jb, Linv, 0, X + (int64_t)j * ld, ld, sX, nc, w.tmp));
@@ -1562,6 +1986,12 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
   HPS_CUDA(cudaEventRecord(aux->fork, s0));
   HPS_CUDA(cudaStreamWaitEvent(s1, aux->fork, 0));
 
+  bool structured = false;
+  for (int k = 0; k < n_rhs; ++k) structured |= rhs[k].n_seg > 0;
+  {
+    static const bool no_struct = [] { const char* e = std::getenv("HPS_LU_STRUCT"); return e && e[0] == '0'; }();
+    if (no_struct) structured = false;
+  }
   // HPS_DIST_SEND=kernel: SM stores straight into the peers' matrices; default: pack into a staging slot, one
   // contiguous copy-engine transfer per peer, a one-warp kernel raises the flags, the peer unpacks.
   static const bool send_by_kernel = [] { const char* e = std::getenv("HPS_DIST_SEND"); return e && e[0] == 'k'; }();
@@ -1634,7 +2064,11 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
       if (ragged) HPS_TRY(dist_apply(s, n, Am, j, jb, w, b, A + last_c0, n, 0, n - last_c0, 1));
     }
     if (with_rhs)
-      for (int k = 0; k < n_rhs; ++k) HPS_TRY(dist_apply(s, n, Am, j, jb, w, b, rhs[k].ptr, rhs[k].ld, 0, rhs[k].ncols, 1));
+      for (int k = 0; k < n_rhs; ++k) {
+        // declared leading zero rows (RhsDesc): block b leaves the columns that are still zero down to row j + jb alone
+        const int nc = structured ? rhs[k].active_cols(j + jb) : rhs[k].ncols;
+        HPS_TRY(dist_apply(s, n, Am, j, jb, w, b, rhs[k].ptr, rhs[k].ld, 0, nc, 1));
+      }
     return 0;
   };
 
@@ -1657,12 +2091,26 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
       HPS_CUDA(cudaEventRecord(aux->panel_done[nb1 & 1], s1));
     }
     HPS_CUDA(cudaStreamWaitEvent(s0, aux->panel_done[b & 1], 0));
-    HPS_TRY(apply_owned(s0, b, own_next ? nb1 + 1 : nb1, true));
+    // The block column this rank factors at the NEXT step (b + 2) is brought up to date first and gets its own
+    // event: the chain then never waits for the bulk of the trailing update (owned block columns + right-hand sides).
+    const int nb2 = b + 2;
+    int lo = own_next ? nb1 + 1 : nb1;
+    if (nb2 < nblk && rank == nb2 % world) {
+      const int j = b * NB, jb = std::min(NB, n - j);
+      const int c0 = nb2 * NB, nc = std::min(NB, n - c0);
+      HPS_TRY(dist_apply(s0, n, Am, j, jb, w, b, A + c0, n, 0, nc, 1));
+      lo = nb2 + 1;
+    }
     HPS_CUDA(cudaEventRecord(aux->update_done[b & 1], s0));
+    HPS_TRY(apply_owned(s0, b, lo, true));
   }
   if (world > 1) {  // the caller's stream also covers the sends still in flight on the communication stream
     HPS_CUDA(cudaEventRecord(aux->sent, s2));
     HPS_CUDA(cudaStreamWaitEvent(s0, aux->sent, 0));
+  }
+  if (structured) {  // the shortcut assumed that no row moved: verified here, reported as info = -1
+    pivots_moved_info_kernel<<<64, 256, 0, s0>>>(w.ipiv, n, info);
+    HPS_LAUNCH_CHECK("pivots_moved_info_kernel");
   }
   prof_begin(PROF_TRTRI, s0, (double)nblk * NB * NB * NB / 3);
   trtri_upper_kernel<<<dim3(nblk, 1), TRI_THREADS, TRTRI_UPPER_SMEM, s0>>>(A, n, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);

@@ -11,6 +11,7 @@
 //   * S = D^-1 (-C) and g~ = D^-1 (-h_int) come from one pivoted LU with the right-hand sides
 //     carried along (lu.cu), in place in the caller's S / g~ buffers — no explicit inverse;
 //   * T = A (+) B S only multiplies the 3 (2 in 2D) non-zero m x m blocks per block row of B.
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -33,6 +34,12 @@ struct Topo {
   signed char slot_owner[MAXS][2];      // the two children sharing slot s
   signed char ext_child[MAXE], ext_face[MAXE];
   signed char ext_slot[MAXE][3];        // interface slots of the child owning panel e
+  // Order in which the exterior panels sit in the right-hand side -C during the solve: sorted by the first
+  // interface slot of the owning child (for the octree: the reference's region order a..h, faces ascending), so
+  // that the columns with leading zero rows form a suffix at every row (lu.cu, RhsDesc).
+  signed char ext_pos[MAXE];            // panel e -> position in the solve order
+  signed char ext_at[MAXE];             // position -> panel
+  signed char ext_first_slot[MAXE];     // position -> first interface slot of that panel's child
 };
 
 // 3D: children a..h, faces x-,x+,y-,y+,z-,z+; interface ids 9..20 -> slots 0..11
@@ -110,6 +117,21 @@ void finish(Topo& t) {
         t.ext_face[e] = (signed char)f;
         for (int k = 0; k < 3; ++k) t.ext_slot[e][k] = (signed char)(k < ns ? slots[k] : -1);
       }
+  }
+  // solve order: stable sort of the panels by (first slot of the child, child, face)
+  int key[MAXE], order[MAXE];
+  for (int e = 0; e < t.n_ext; ++e) {
+    int first = MAXS;
+    for (int k = 0; k < t.n_intf; ++k) first = std::min<int>(first, t.ext_slot[e][k]);
+    key[e] = (first * MAXC + t.ext_child[e]) * MAXF + t.ext_face[e];
+    order[e] = e;
+  }
+  std::sort(order, order + t.n_ext, [&](int a, int b) { return key[a] < key[b]; });
+  for (int pos = 0; pos < t.n_ext; ++pos) {
+    const int e = order[pos];
+    t.ext_at[pos] = (signed char)e;
+    t.ext_pos[e] = (signed char)pos;
+    t.ext_first_slot[pos] = (signed char)(key[e] / (MAXC * MAXF));
   }
 }
 
@@ -257,7 +279,7 @@ __device__ __forceinline__ void copy_block(E* __restrict__ dst, int64_t ldd, con
 __global__ void __launch_bounds__(256) merge_gather_tile_kernel(Topo tp, int m, int n_src, const double* __restrict__ T_in,
                                                                 const double* __restrict__ h_in, double* __restrict__ D,
                                                                 double* __restrict__ S, double* __restrict__ gt,
-                                                                int row_splits) {
+                                                                int row_splits, int sorted) {
   const int n_int = tp.n_slot * m, n_ext = tp.n_ext * m, nf = tp.n_face * m;
   const int mg = blockIdx.z, cb = blockIdx.x;
   const int s1 = blockIdx.y / row_splits, sl = blockIdx.y - s1 * row_splits;
@@ -287,7 +309,7 @@ __global__ void __launch_bounds__(256) merge_gather_tile_kernel(Topo tp, int m, 
     const double* A = nullptr;
     int64_t rs = nf;
     if (c == cA) { A = rowA0 + f * m; rs = rsA; } else if (c == cB) { A = rowB0 + f * m; rs = rsB; }
-    double* dst = S + ((int64_t)mg * n_int + s1 * m) * n_ext + e * m;
+    double* dst = S + ((int64_t)mg * n_int + s1 * m) * n_ext + (sorted ? tp.ext_pos[e] : e) * m;
     copy_block<double, true>(dst, n_ext, A, rs, 1, nullptr, 0, 1, r_lo, r_hi, m);
   } else {
     const double* hm = h_in + (int64_t)mg * tp.n_child * nf * n_src;
@@ -431,6 +453,75 @@ __global__ void up_gather_dtn_kernel(Topo tp, int m, int n_src, const E* __restr
   }
 }
 
+// ---- S columns from the solve order back to the parent's face order, in place ----------------------
+// new panel e = old panel ext_pos[e]: the panel permutation is walked cycle by cycle; a thread owns one column
+// offset t of one row in every panel of its cycle, so nothing is shared between threads.
+struct PanelCycles {
+  int n_cyc;
+  signed char start[MAXE + 1];
+  signed char elem[MAXE];
+};
+PanelCycles make_cycles(const Topo& tp) {
+  PanelCycles pc = {};
+  bool seen[MAXE] = {};
+  int at = 0;
+  for (int e = 0; e < tp.n_ext; ++e) {
+    if (seen[e] || tp.ext_pos[e] == e) continue;
+    pc.start[pc.n_cyc++] = (signed char)at;
+    for (int d = e; !seen[d]; d = tp.ext_pos[d]) { pc.elem[at++] = (signed char)d; seen[d] = true; }
+  }
+  pc.start[pc.n_cyc] = (signed char)at;
+  return pc;
+}
+constexpr int CYC_CHUNK = 1024;
+__global__ void __launch_bounds__(256) panel_cycle_kernel(PanelCycles pc, int m, int chunks, double* __restrict__ S,
+                                                          int64_t ld, int64_t rows) {
+  const int cyc = blockIdx.x / chunks, ch = blockIdx.x - cyc * chunks;
+  const int b = pc.start[cyc], e = pc.start[cyc + 1];
+  const int t0 = ch * CYC_CHUNK + threadIdx.x;
+  for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+    double* base = S + row * ld;
+    double tmp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 + 256 * i;
+      if (t < m) tmp[i] = base[pc.elem[b] * m + t];
+    }
+    for (int k = b; k + 1 < e; ++k) {
+      double v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = t0 + 256 * i;
+        if (t < m) v[i] = base[pc.elem[k + 1] * m + t];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = t0 + 256 * i;
+        if (t < m) base[pc.elem[k] * m + t] = v[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 + 256 * i;
+      if (t < m) base[pc.elem[e - 1] * m + t] = tmp[i];
+    }
+  }
+}
+int unsort_panels(const Topo& tp, cudaStream_t st, int m, double* S, int64_t ld, int64_t rows) {
+  const PanelCycles pc = make_cycles(tp);
+  if (pc.n_cyc == 0 || rows <= 0) return 0;
+  const int chunks = (m + CYC_CHUNK - 1) / CYC_CHUNK;
+  dim3 grid(pc.n_cyc * chunks, (unsigned)std::min<int64_t>(rows, 65535));
+  panel_cycle_kernel<<<grid, 256, 0, st>>>(pc, m, chunks, S, ld, rows);
+  HPS_LAUNCH_CHECK("panel_cycle_kernel");
+  return 0;
+}
+// HPS_MERGE_STRUCT=0 switches the structured forward substitution (and the panel sort it needs) off
+bool merge_structured() {
+  static const bool on = [] { const char* e = std::getenv("HPS_MERGE_STRUCT"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 size_t merge_ws_bytes(const Topo& tp, int n_merges, int m) {
   const size_t n_int = (size_t)tp.n_slot * m;
   return align_up((size_t)n_merges * n_int * n_int * sizeof(double), 256) +
@@ -452,17 +543,24 @@ int merge_level(const Topo& tp, cudaStream_t st, int n_merges, int m, int n_src,
   const size_t lu_ws_bytes = ar.cap - ar.off;
 
   const int row_splits = (m + 127) / 128;  // big blocks are cut into slices of <= 128 rows
+  const bool sorted = merge_structured() && tp.n_ext <= RHS_MAX_SEG;
   {
     dim3 grid(tp.n_slot + tp.n_ext + 1, tp.n_slot * row_splits, n_merges);
     prof_begin(PROF_GATHER, st, n_merges * gather_bytes(tp, m, n_src));
-    merge_gather_tile_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, D, S, gt, row_splits);
+    merge_gather_tile_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, D, S, gt, row_splits, sorted ? 1 : 0);
     prof_end(PROF_GATHER, st);
     HPS_LAUNCH_CHECK("merge_gather_tile_kernel");
   }
   const int64_t sS = (int64_t)n_int * n_ext, sG = (int64_t)n_int * n_src, sDi = (int64_t)n_int * n_int;
   RhsDesc rhs[3] = {{S, n_ext, sS, n_ext}, {gt, n_src, sG, n_src}, {D_inv, n_int, sDi, n_int}};
+  if (sorted) {  // -C sits in the solve order: panel at position k is zero above its child's first interface
+    rhs[0].n_seg = tp.n_ext;
+    rhs[0].seg_cols = m;
+    for (int k = 0; k < tp.n_ext; ++k) rhs[0].seg_first_row[k] = tp.ext_first_slot[k] * m;
+  }
   if (D_inv) HPS_TRY(set_identity(st, n_merges, D_inv, n_int, n_int, sDi));  // third right-hand side: D^-1 itself
   HPS_TRY(lu_solve(st, n_merges, n_int, D, n_int, sDi, D_inv ? 3 : 2, rhs, lu_ws, lu_ws_bytes, info));
+  if (sorted) HPS_TRY(unsort_panels(tp, st, m, S, n_ext, (int64_t)n_merges * n_int));
   if (!want_T && !BD_inv) return 0;
 
   {
@@ -787,7 +885,21 @@ int root_solve_oct(cudaStream_t st, int m, int n_src, int child0, int n_local, c
   root_assemble_kernel<<<grid, 256, 0, st>>>(oct_topo(), m, n_src, child0, n_local, Dblk_all, hblk_all, Cblk_loc, D, S_r, gt);
   HPS_LAUNCH_CHECK("root_assemble_kernel");
   RhsDesc rhs[2] = {{S_r, ncr, (int64_t)n_int * ncr, ncr}, {gt, n_src, (int64_t)n_int * n_src, n_src}};
+  if (merge_structured()) root_cols_structure(child0, n_local, m, rhs[0].n_seg, rhs[0].seg_cols, rhs[0].seg_first_row);
   return lu_solve(st, 1, n_int, D, n_int, (int64_t)n_int * n_int, 2, rhs, lu_ws, lu_ws_bytes, info);
+}
+
+// Leading-zero structure of the root's -C_r (columns of children child0 .. child0+n_local-1, child-major: already
+// sorted by first interface): 3 segments of m columns per child, zero above the child's first interface.
+void root_cols_structure(int child0, int n_local, int m, int& n_seg, int& seg_cols, int* seg_first_row) {
+  const Topo& tp = oct_topo();
+  n_seg = 3 * n_local;
+  seg_cols = m;
+  for (int cl = 0; cl < n_local; ++cl) {
+    int first = 0;
+    while (tp.slot_face[child0 + cl][first] < 0) ++first;
+    for (int k = 0; k < 3; ++k) seg_first_row[3 * cl + k] = first * m;
+  }
 }
 
 int merge_oct_root_cols(cudaStream_t st, int m, int n_src, const double* T_in, const double* h_in, int ext0, int ncols,
