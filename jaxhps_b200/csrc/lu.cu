@@ -541,6 +541,12 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol_kernel(BcArgs a) {
 // arg-max is taken from the registers of the rank-1 update (no shared-memory scan, no barrier after the update).
 // Three CTA barriers per column instead of six.
 constexpr int BC_NPW = (BC_MAX_G + 31) / 32;  // polling warps
+#ifdef HPS_BC_TIMING  // tools/panel_lab.cu: SM-clock stamps of thread 0 at the phase boundaries of every column
+__device__ long long* g_bc_timing = nullptr;  // [G][NB][8]
+#define BC_STAMP(k) do { if (g_bc_timing && tid == 0) g_bc_timing[((size_t)g * NB + c) * 8 + (k)] = clock64(); } while (0)
+#else
+#define BC_STAMP(k) do { } while (0)
+#endif
 __global__ void __launch_bounds__(BC_THREADS, 1) blockcol2_kernel(BcArgs a) {
   extern __shared__ __align__(16) double sm[];
   constexpr int LD = BC_LD;
@@ -577,6 +583,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol2_kernel(BcArgs a) {
   bool scan = true;       // no carried candidate: scan the column in shared memory
   for (int c = 0; c < jb; ++c) {
     const int c0 = (c / IB) * IB, pe = min(c0 + IB, jb);
+    BC_STAMP(0);
     // ---- local arg-max of |a[r][c]| over rows >= c (lowest row wins ties) ----
     double best = -1.0;
     int bidx = 0x7fffffff;
@@ -607,6 +614,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol2_kernel(BcArgs a) {
     }
 
     // ---- publish: candidate row, the row that will be displaced (row c), header; no fence, no barrier ----
+    BC_STAMP(1);
     const unsigned epoch = (unsigned)(a.j + c + 1);
     BcCand2* mine = cands + (size_t)(c & 1) * a.Gcap + g;
     BcChunk* dg = diag + (c & 1) * NB;
@@ -626,6 +634,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol2_kernel(BcArgs a) {
         const BcCand2* his = cands + (size_t)(c & 1) * a.Gcap + tid;
         do { ld_header(his, hv, hr, hf); } while (hf != epoch);
         if (hv >= 0.0) { wv = hv; wr = hr; wg = tid; }
+        BC_STAMP(2);  // thread 0: CTA 0's header seen
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -637,6 +646,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol2_kernel(BcArgs a) {
       if (lane == 0) { s_pv[warp] = wv; s_pr[warp] = wr; s_pg[warp] = wg; }
     }
     __syncthreads();  // (2)
+    BC_STAMP(3);  // every header seen by this CTA
     wv = -1.0; wr = 0x7fffffff; wg = 0;
 #pragma unroll
     for (int w = 0; w < BC_NPW; ++w) {
@@ -656,6 +666,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol2_kernel(BcArgs a) {
       }
     }
     __syncthreads();  // (3)
+    BC_STAMP(4);  // pivot row fetched
     if (g == 0 && tid == 0) ipiv[c] = a.j + p;
     const double piv = has ? prow[c] : 0.0;
     cv = -1.0; cr = 0x7fffffff;
@@ -687,6 +698,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol2_kernel(BcArgs a) {
       }
       scan = (c + 1 >= pe);  // the first column of the next inner panel comes out of the trailing update below
     }
+    BC_STAMP(5);  // thread 0's own row updated
 
     if (c == pe - 1 && pe < jb) {
       __syncthreads();
@@ -1386,7 +1398,7 @@ int trsm_lower(cudaStream_t st, int batch, int n, const Mat& A, const LuWorkspac
   const int blocks = (r1 - r0 + NB - 1) / NB;
   const int mid = r0 + (blocks / 2) * NB;
   HPS_TRY(trsm_lower(st, batch, n, A, w, X, r0, mid, structured));
-  if (!structured) {
+  if (!structured || X.n_seg <= 0) {  // (a right-hand side without declared structure inside a structured solve)
     HPS_TRY(dgemm(st, r1 - mid, X.ncols, mid - r0, -1.0, A.at(mid, r0), A.ld, A.stride, X.ptr + (int64_t)r0 * X.ld, X.ld,
                   X.stride, 1.0, X.ptr + (int64_t)mid * X.ld, X.ld, X.stride, batch));
   } else {
