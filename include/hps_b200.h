@@ -193,6 +193,12 @@ int hps_lu_dist_run(void* comm, void* stream, int n, int n_rhs, double* const* r
 int hps_lu_dist_run_structured(void* comm, void* stream, int n, int n_rhs, double* const* rhs, const int64_t* ld_rhs,
                                const int* ncols, int n_seg, int seg_cols, const int* seg_first_row, void* ws,
                                size_t ws_bytes, int* info);
+/* Speculative block columns of the merge factorisations (default on; HPS_LU_SPEC=0 starts with them off).  The HPS
+ * merge matrices D are never pivoted below their 128 x 128 diagonal blocks, so a block column is factored as
+ * diagonal-block LU + one tensor-core product L21 = A21 U11^-1, with a device-side check that every multiplier is
+ * <= 1 in magnitude (the condition under which partial pivoting makes the same choices).  When the check fails the
+ * merge / root-solve / hps_lu_dist_run call reports info = -2: switch the speculation off and repeat the call. */
+int hps_lu_set_speculative(int on);
 /* seg_first_row[3 * n_local], *n_seg = 3 * n_local, *seg_cols = m for the root children child0 .. child0+n_local-1
  * (reference interface order 9..20, merge/_uniform_3D_DtN.py:238-380). */
 int hps_root_cols_structure(int child0, int n_local, int m, int* n_seg, int* seg_cols, int* seg_first_row);

@@ -211,11 +211,18 @@ def p2p_lu_solve(_lib, dev, comm: "P2PComm", n: int, rhs, group=None, structure=
     else:
         _lib.check(lib.hps_lu_dist_run(comm.handle, _lib.stream_ptr(), n, k, ptrs, lds, ncs, ws.data_ptr(), ws.numel(),
                                        info.data_ptr()), "hps_lu_dist_run")
+    # zero pivots (> 0) are seen by the owner of the block column only, and so are the assumption codes (< 0: -1 rows
+    # moved under a structured solve, -2 a speculative block column needed pivoting): reduce both signs separately
+    codes = torch.stack([info[0].clamp(min=0), (-info[0]).clamp(min=0)])
     if comm.world > 1:
-        dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
-    if int(info[0]) < 0:
+        dist.all_reduce(codes, op=dist.ReduceOp.MAX, group=group)
+    pos, neg = int(codes[0]), int(codes[1])
+    if pos:
+        raise np.linalg.LinAlgError(f"distributed factorisation: exact zero pivot at column {pos}")
+    if neg >= 2:
+        raise _lib.AssumptionViolated("distributed factorisation")
+    if neg == 1:
         raise StructureInvalid()
-    _lib.check_info(info, "distributed factorisation")
 
 
 def distributed_lu_solve(_lib, dev, D, rhs, rank: int, world: int, group=None) -> None:
@@ -384,11 +391,14 @@ class CudaOps:
         need = ctypes.c_size_t()
         self._lib.check(lib.hps_root_solve_oct_workspace(m, ctypes.byref(need)), "workspace query")
         ws = self._lib.WORKSPACE.get(need.value, self.dev)
-        rc = lib.hps_root_solve_oct(self._lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),
-                                    hblk_all.data_ptr(), Cblk_loc.data_ptr(), S_r.data_ptr(), g.data_ptr(), ws.data_ptr(),
-                                    ws.numel(), info.data_ptr())
-        self._lib.check(rc, "hps_root_solve_oct")
-        self._lib.check_info(info, "root merge")
+        def run():
+            rc = lib.hps_root_solve_oct(self._lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),
+                                        hblk_all.data_ptr(), Cblk_loc.data_ptr(), S_r.data_ptr(), g.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), info.data_ptr())
+            self._lib.check(rc, "hps_root_solve_oct")
+            self._lib.check_info(info, "root merge")
+
+        self._lib.with_pivoting_fallback(run)
         return S_r, g
 
     def root_apply(self, x, rank: int, world: int, group=None):
@@ -430,17 +440,18 @@ class CudaOps:
                                                g.data_ptr())
                 _lib.check(rc, "hps_root_assemble_oct")
 
-            assemble()
             # factored root: only g~ goes through the solve; S_r keeps -C_r for the solves
-            if factored:
-                p2p_lu_solve(_lib, self.dev, comm, n, [g], group)
-                return S_r, g
-            structure = root_cols_structure(_lib, first_child, n_local, m) if self.STRUCTURED else None
-            try:
-                p2p_lu_solve(_lib, self.dev, comm, n, [S_r, g], group, structure)
-            except StructureInvalid:  # rows were interchanged: the zero-row shortcut does not apply to this matrix
+            structure = root_cols_structure(_lib, first_child, n_local, m) if (self.STRUCTURED and not factored) else None
+
+            def run(structure=structure):
                 assemble()
-                p2p_lu_solve(_lib, self.dev, comm, n, [S_r, g], group)
+                try:
+                    p2p_lu_solve(_lib, self.dev, comm, n, [g] if factored else [S_r, g], group, structure)
+                except StructureInvalid:  # rows were interchanged: the zero-row shortcut does not apply to this matrix
+                    assemble()
+                    p2p_lu_solve(_lib, self.dev, comm, n, [g] if factored else [S_r, g], group)
+
+            _lib.with_pivoting_fallback(run)  # (info = -2: the speculative block columns did not apply either)
             return S_r, g
         D = self.empty((n, n))
         rc = lib.hps_root_assemble_oct(_lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),

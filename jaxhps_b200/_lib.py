@@ -61,6 +61,7 @@ _SIGNATURES = {
     "hps_lu_dist_run": (_i, [_p, _p, _i, _i, ctypes.POINTER(_p), ctypes.POINTER(_l), ctypes.POINTER(_i), _p, _sz, _p]),
     "hps_lu_dist_run_structured": (_i, [_p, _p, _i, _i, ctypes.POINTER(_p), ctypes.POINTER(_l), ctypes.POINTER(_i), _i, _i,
                                         ctypes.POINTER(_i), _p, _sz, _p]),
+    "hps_lu_set_speculative": (_i, [_i]),
     "hps_root_cols_structure": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "hps_lu_dist_apply": (_i, [_p, _p, _i, _i, ctypes.POINTER(_p), ctypes.POINTER(_l), ctypes.POINTER(_i), _p, _sz]),
     "hps_down_oct_scatter": (_i, [_p, _i, _i, _i, _p, _p, _p]),
@@ -231,9 +232,31 @@ def workspace(nbytes: int, dev: torch.device) -> torch.Tensor:
     return WORKSPACE.get(nbytes, dev)
 
 
+class AssumptionViolated(Exception):
+    """A structural shortcut of the library did not apply to this matrix (``info < 0``: the factorisation of a merge
+    matrix needed row interchanges below a diagonal block).  The operation is repeated with the shortcut off."""
+
+
 def check_info(info: torch.Tensor, what: str) -> None:
     """LAPACK-style singularity report (one host sync; the stages call it once per level)."""
     bad = torch.nonzero(info)
     if bad.numel():
-        k = int(bad[0, 0])
-        raise np.linalg.LinAlgError(f"{what}: exact zero pivot in matrix {k} at column {int(info[k])}")
+        pos = torch.nonzero(info > 0)
+        if pos.numel():
+            k = int(pos[0, 0])
+            raise np.linalg.LinAlgError(f"{what}: exact zero pivot in matrix {k} at column {int(info[k])}")
+        raise AssumptionViolated(what)
+
+
+def with_pivoting_fallback(fn):
+    """Run ``fn()``; if the library reports that its no-pivoting speculation failed, run it again with the
+    speculation switched off (``hps_lu_set_speculative``)."""
+    try:
+        return fn()
+    except AssumptionViolated:
+        lib = load()
+        lib.hps_lu_set_speculative(0)
+        try:
+            return fn()
+        finally:
+            lib.hps_lu_set_speculative(0 if os.environ.get("HPS_LU_SPEC", "1") == "0" else 1)

@@ -195,13 +195,17 @@ def _merge_adaptive(pde_problem, T_arr, h_arr, device, host_device, return_T: bo
             step = min(n1, 16384)
             _lib.check(ws_fn(step, npp, n_src, ctypes.byref(need)), "merge workspace query")
             ws = _lib.WORKSPACE.get(need.value, dev)
-            for s in range(0, n1, step):
-                e = min(n1, s + step)
-                rc = level_fn(_lib.stream_ptr(), e - s, npp, n_src, _lib.ptr(T_in[s * n_child:]), _lib.ptr(h_in[s * n_child:]),
-                              _lib.ptr(S1[s:]), _lib.ptr(g1[s:]), _lib.ptr(T1[s:]), _lib.ptr(h1[s:]), 1, _lib.ptr(ws),
-                              ws.numel(), _lib.ptr(i1[s:]))
-                _lib.check(rc, "hps_merge_dtn_level")
-            _lib.check_info(i1, "merge of the leaves' parents")
+            def run_first_level():
+                i1.zero_()
+                for s in range(0, n1, step):
+                    e = min(n1, s + step)
+                    rc = level_fn(_lib.stream_ptr(), e - s, npp, n_src, _lib.ptr(T_in[s * n_child:]), _lib.ptr(h_in[s * n_child:]),
+                                  _lib.ptr(S1[s:]), _lib.ptr(g1[s:]), _lib.ptr(T1[s:]), _lib.ptr(h1[s:]), 1, _lib.ptr(ws),
+                                  ws.numel(), _lib.ptr(i1[s:]))
+                    _lib.check(rc, "hps_merge_dtn_level")
+                _lib.check_info(i1, "merge of the leaves' parents")
+
+            _lib.with_pivoting_fallback(run_first_level)
             del T_in, h_in
             for k, np_ in enumerate(first):
                 st.S[id(np_.node)], st.g[id(np_.node)] = S1[k], g1[k]

@@ -290,6 +290,7 @@ int hps_lu_dist_run_structured(void* comm, void* stream, int n, int n_rhs, doubl
   }
   return lu_dist_run(static_cast<Comm*>(comm), static_cast<cudaStream_t>(stream), n, n_rhs, d, ws, ws_bytes, info);
 }
+int hps_lu_set_speculative(int on) { lu_set_speculative(on); return 0; }
 int hps_root_cols_structure(int child0, int n_local, int m, int* n_seg, int* seg_cols, int* seg_first_row) {
   if (n_local <= 0 || m <= 0 || child0 < 0 || child0 + n_local > 8 || !n_seg || !seg_cols || !seg_first_row)
     return fail_arg(1, "bad child range / null output");

@@ -124,8 +124,13 @@ struct RhsDesc {
   }
 };
 size_t lu_workspace_bytes(int batch, int n);
+// flags: LU_NO_PIVOT_EXPECTED — the caller expects partial pivoting to stay inside the 128 x 128 diagonal blocks
+// (HPS merge matrices): block columns are then factored without any cross-CTA pivot election and the assumption is
+// verified on the device; info = -2 means it did not hold and the call must be repeated after lu_set_speculative(0).
+constexpr int LU_NO_PIVOT_EXPECTED = 1;
 int lu_solve(cudaStream_t st, int batch, int n, double* A, int64_t lda, int64_t sA, int n_rhs,
-             const RhsDesc* rhs, void* ws, size_t ws_bytes, int* info);
+             const RhsDesc* rhs, void* ws, size_t ws_bytes, int* info, int flags = 0);
+void lu_set_speculative(int on);
 
 // step-wise distributed factorisation (lu.cu), driven from jaxhps_b200/_dist.py
 size_t lu_dist_block_buffer_doubles(int n);

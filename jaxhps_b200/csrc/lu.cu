@@ -243,6 +243,7 @@ struct BcArgs {
   char* scratch;            // per matrix: BcCand[2][Gcap], diag[2][NB], u12[IB][BC_UW], u12 flag
   size_t scratch_stride;
   int Gcap;
+  int rows_cap;             // > 0: only the first rows_cap rows below the diagonal take part (speculative path)
 };
 
 // Tagged exchange (blockcol2_kernel): every 16-byte unit carries its own epoch, so no fence is needed anywhere.
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol_kernel(BcArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = blockIdx.x, mat = blockIdx.y;
   const int G = a.G, jb = a.jb;
-  const int rows = a.n - a.j;
+  const int rows = a.rows_cap > 0 ? min(a.rows_cap, a.n - a.j) : a.n - a.j;
   const int r0 = min(rows, g * a.rpc), r1 = min(rows, r0 + a.rpc), nr = r1 - r0;
   double* A = a.A + (int64_t)mat * a.sA + (int64_t)a.j * a.lda + a.j;
   int* ipiv = a.ipiv + (int64_t)mat * a.n + a.j;
@@ -1104,6 +1105,7 @@ struct LuWorkspace {
   char* bc_scratch;  // block-column kernel exchange area, bc_stride bytes per matrix (flags must start at 0)
   size_t bc_stride;
   int bc_Gcap;
+  double* P;         // [batch][n][NB] the speculative path's L21 before it is committed
 };
 
 // CTAs per matrix the block-column kernel may need for an n x n factorisation (0: single-CTA only)
@@ -1122,7 +1124,8 @@ bool carve(Arena& ar, int batch, int n, LuWorkspace& w) {
   w.bc_Gcap = bc_gcap(n);
   w.bc_stride = w.bc_Gcap ? align_up(bc_scratch_bytes(w.bc_Gcap), 256) : 0;
   w.bc_scratch = w.bc_Gcap ? ar.take<char>((size_t)batch * w.bc_stride) : reinterpret_cast<char*>(w.scratch);
-  return w.ipiv && w.Linv && w.Uinv && w.tmp && w.scratch && w.bc_scratch;
+  w.P = ar.take<double>((size_t)batch * n * NB);
+  return w.ipiv && w.Linv && w.Uinv && w.tmp && w.scratch && w.bc_scratch && w.P;
 }
 
 // co-resident CTAs of a cooperative kernel on the current device (queried once per device)
@@ -1256,6 +1259,7 @@ int launch_blockcol(cudaStream_t st, int batch, int n, double* A, int64_t lda, i
   a.A = A; a.lda = lda; a.sA = sA; a.n = n; a.j = j; a.jb = jb; a.G = G;
   a.rpc = (G == 1) ? rows : std::max(NB, (rows + G - 1) / G);
   a.ipiv = w.ipiv; a.info = info; a.scratch = w.bc_scratch; a.scratch_stride = w.bc_stride; a.Gcap = w.bc_Gcap;
+  a.rows_cap = 0;
   const size_t smem = bc_smem_bytes(a.rpc);
   if (G == 1) {
     prof_begin(PROF_PANEL, st, (double)batch * rows * jb);
@@ -1332,9 +1336,71 @@ struct Mat {  // batched row-major matrix view
   double* at(int64_t r, int64_t c) const { return p + r * ld + c; }
 };
 
+// A21 := P (rows x jb), and the check that makes the speculation below equivalent to partial pivoting: every
+// multiplier must satisfy |l| <= 1, otherwise info := -2 (kept if info already reports a zero pivot).
+__global__ void __launch_bounds__(256) spec_commit_kernel(double* __restrict__ A21, int64_t lda, int64_t sA,
+                                                          const double* __restrict__ P, int64_t sP, int rows, int jb,
+                                                          int* __restrict__ info) {
+  const int mat = blockIdx.y;
+  const double* p = P + (int64_t)mat * sP;
+  double* a = A21 + (int64_t)mat * sA;
+  const int64_t total = (int64_t)rows * jb;
+  bool bad = false;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / jb, c = e - r * jb;
+    const double v = p[e];
+    bad |= !(fabs(v) <= 1.0 + 1e-8);  // also catches NaN
+    a[r * lda + c] = v;
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicCAS(&info[mat], 0, -2);
+}
+
+// Process-wide switch of the speculative block columns (hps_lu_set_speculative; HPS_LU_SPEC=0 starts with it off)
+std::atomic<int> g_lu_speculate{[] { const char* e = std::getenv("HPS_LU_SPEC"); return (e && e[0] == '0') ? 0 : 1; }()};
+
+// Block column j WITHOUT any cross-CTA exchange, for matrices that partial pivoting leaves alone below the diagonal
+// block (the HPS merge matrices D; measured: the 128 per-column elections through L2 cost 3 us each and make up
+// two thirds of the pivoted kernel, profiles/r02_blockcol_phase_timing.txt):
+//   1. one CTA factors the jb x jb diagonal block (pivot search restricted to the block),
+//   2. its unit-lower and upper inverses (the solves need both anyway),
+//   3. L21 = A21 U11^-1 as ONE tensor-core product over all rows below,
+//   4. commit + verification that every multiplier is <= 1 in magnitude — exactly the condition under which
+//      partial pivoting over the whole column would have chosen the same pivots.  Otherwise info = -2 and the
+//      caller repeats the operation with hps_lu_set_speculative(0).
+int factor_block_column_spec(cudaStream_t st, int batch, int n, const Mat& A, int j, int jb, LuWorkspace& w, int* info) {
+  const int nblk = (n + NB - 1) / NB;
+  const int64_t sW = (int64_t)nblk * NB * NB;
+  BcArgs a;
+  a.A = A.p; a.lda = A.ld; a.sA = A.stride; a.n = n; a.j = j; a.jb = jb; a.G = 1; a.rpc = jb;
+  a.ipiv = w.ipiv; a.info = info; a.scratch = w.bc_scratch; a.scratch_stride = w.bc_stride; a.Gcap = w.bc_Gcap;
+  a.rows_cap = jb;
+  prof_begin(PROF_PANEL, st, (double)batch * jb * jb);
+  blockcol_kernel<false><<<dim3(1, batch), BC_THREADS, bc_smem_bytes(jb), st>>>(a);
+  prof_end(PROF_PANEL, st);
+  HPS_LAUNCH_CHECK("blockcol_kernel<diagonal block>");
+  prof_begin(PROF_TRTRI, st, (double)batch * NB * NB * NB * 2 / 3);
+  trtri_lower_kernel<<<dim3(1, batch), TRI_THREADS, TRTRI_SMEM, st>>>(A.p, A.ld, A.stride, j, n, w.Linv, sW);
+  trtri_upper_kernel<<<dim3(1, batch), TRI_THREADS, TRTRI_UPPER_SMEM, st>>>(A.p, A.ld, A.stride, j, n, w.Uinv, sW);
+  prof_end(PROF_TRTRI, st);
+  HPS_LAUNCH_CHECK("trtri kernels");
+  const int rows = n - (j + jb);
+  if (rows > 0) {
+    const int64_t sP = (int64_t)n * NB;
+    HPS_TRY(dgemm(st, rows, jb, jb, 1.0, A.at(j + jb, j), A.ld, A.stride, w.Uinv + (int64_t)(j / NB) * NB * NB, NB, sW, 0.0,
+                  w.P, jb, sP, batch));
+    const int64_t total = (int64_t)rows * jb;
+    spec_commit_kernel<<<dim3((unsigned)std::min<int64_t>((total + 255) / 256, 1184), batch), 256, 0, st>>>(
+        A.at(j + jb, j), A.ld, A.stride, w.P, sP, rows, jb, info);
+    HPS_LAUNCH_CHECK("spec_commit_kernel");
+  }
+  return 0;
+}
+
 // Factor the outer block column j (inner IB panels + updates inside the block column) and invert
 // its unit-lower diagonal block into Linv[j/NB].  Touches columns [j, j+jb) only.
-int factor_block_column(cudaStream_t st, int batch, int n, const Mat& A, int j, int jb, LuWorkspace& w, int* info) {
+int factor_block_column(cudaStream_t st, int batch, int n, const Mat& A, int j, int jb, LuWorkspace& w, int* info,
+                        bool speculate = false) {
+  if (speculate) return factor_block_column_spec(st, batch, n, A, j, jb, w, info);
   bool done = false;
   HPS_TRY(launch_blockcol(st, batch, n, A.p, A.ld, A.stride, j, jb, w, info, done));
   for (int jj = j; !done && jj < j + jb; jj += IB) {
@@ -1459,11 +1525,14 @@ size_t lu_workspace_bytes(int batch, int n) {
   const size_t nblk = (n + NB - 1) / NB;
   return align_up((size_t)batch * n * sizeof(int), 256) + 2 * align_up((size_t)batch * nblk * NB * NB * sizeof(double), 256) +
          align_up((size_t)batch * NB * 16 * sizeof(double), 256) + align_up((size_t)batch * sizeof(PanelScratch), 256) +
-         align_up((size_t)batch * align_up(bc_scratch_bytes(std::max(1, bc_gcap(n))), 256), 256) + 1024;
+         align_up((size_t)batch * align_up(bc_scratch_bytes(std::max(1, bc_gcap(n))), 256), 256) +
+         align_up((size_t)batch * n * NB * sizeof(double), 256) + 1024;
 }
 
 int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t sA, int n_rhs, const RhsDesc* rhs,
-             void* ws, size_t ws_bytes, int* info) {
+             void* ws, size_t ws_bytes, int* info, int flags) {
+  static const bool force_spec = [] { const char* e = std::getenv("HPS_LU_FORCE_SPEC"); return e && e[0] == '1'; }();  // tools/bench_lu.py
+  const bool speculate = ((flags & LU_NO_PIVOT_EXPECTED) || force_spec) && g_lu_speculate.load(std::memory_order_relaxed) != 0;
   if (batch <= 0 || n <= 0) return 0;
   if (batch > 65535) return fail_arg(2, "lu_solve: batch > 65535");
   Arena ar(ws, ws_bytes);
@@ -1484,7 +1553,7 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
   // to their right (and the interchanges to everything to their left).
   HPS_CUDA(cudaEventRecord(aux->fork, s0));
   HPS_CUDA(cudaStreamWaitEvent(s1, aux->fork, 0));
-  HPS_TRY(factor_block_column(s1, batch, n, A, 0, min(NB, n), w, info));
+  HPS_TRY(factor_block_column(s1, batch, n, A, 0, min(NB, n), w, info, speculate));
   HPS_CUDA(cudaEventRecord(aux->panel_done[0], s1));
   for (int b = 0; b < nblk; ++b) {
     const int j = b * NB, jb = min(NB, n - j);
@@ -1495,7 +1564,7 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
       // written by s0's update for block b-1, which must have finished.
       if (b > 0) HPS_CUDA(cudaStreamWaitEvent(s1, aux->update_done[(b - 1) & 1], 0));
       HPS_TRY(update_columns(s1, batch, n, A, j, jb, next, nextb, w));
-      HPS_TRY(factor_block_column(s1, batch, n, A, next, nextb, w, info));
+      HPS_TRY(factor_block_column(s1, batch, n, A, next, nextb, w, info, speculate));
       HPS_CUDA(cudaEventRecord(aux->panel_done[(b + 1) & 1], s1));
     }
     // s0: interchanges on the columns to the left (L in LAPACK form), then the rest of the
@@ -1574,6 +1643,8 @@ __global__ void pack_block_kernel(int n, int jb, const double* __restrict__ A, i
   }
 }
 }  // namespace
+
+void lu_set_speculative(int on) { g_lu_speculate.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 size_t lu_dist_block_buffer_doubles(int n) { return (size_t)n * NB + NB + (size_t)NB * NB; }
 
@@ -1998,6 +2069,7 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
   HPS_CUDA(cudaEventRecord(aux->fork, s0));
   HPS_CUDA(cudaStreamWaitEvent(s1, aux->fork, 0));
 
+  const bool speculate = g_lu_speculate.load(std::memory_order_relaxed) != 0;  // the root D of a merge: see lu_solve
   bool structured = false;
   for (int k = 0; k < n_rhs; ++k) structured |= rhs[k].n_seg > 0;
   {
@@ -2033,7 +2105,7 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
   // from the communication stream, off the critical path.
   auto factor_and_send = [&](int b) -> int {
     const int j = b * NB, jb = std::min(NB, n - j);
-    HPS_TRY(factor_block_column(s1, 1, n, Am, j, jb, w, info));
+    HPS_TRY(factor_block_column(s1, 1, n, Am, j, jb, w, info, speculate));
     if (world > 1) {
       if (!send_by_kernel) {
         comm_slot_kernel<true><<<128, 256, 0, s1>>>(A, n, j, jb, w.ipiv + j, w.Linv + (int64_t)b * NB * NB,

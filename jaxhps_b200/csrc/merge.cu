@@ -559,7 +559,7 @@ int merge_level(const Topo& tp, cudaStream_t st, int n_merges, int m, int n_src,
     for (int k = 0; k < tp.n_ext; ++k) rhs[0].seg_first_row[k] = tp.ext_first_slot[k] * m;
   }
   if (D_inv) HPS_TRY(set_identity(st, n_merges, D_inv, n_int, n_int, sDi));  // third right-hand side: D^-1 itself
-  HPS_TRY(lu_solve(st, n_merges, n_int, D, n_int, sDi, D_inv ? 3 : 2, rhs, lu_ws, lu_ws_bytes, info));
+  HPS_TRY(lu_solve(st, n_merges, n_int, D, n_int, sDi, D_inv ? 3 : 2, rhs, lu_ws, lu_ws_bytes, info, LU_NO_PIVOT_EXPECTED));
   if (sorted) HPS_TRY(unsort_panels(tp, st, m, S, n_ext, (int64_t)n_merges * n_int));
   if (!want_T && !BD_inv) return 0;
 
@@ -825,7 +825,7 @@ int merge_cols(const Topo& tp, cudaStream_t st, int m, int n_src, const double* 
   merge_gather_kernel<<<grid, 256, 0, st>>>(tp, m, n_src, T_in, h_in, D, S_cols, gt, ext0, ncols);
   HPS_LAUNCH_CHECK("merge_gather_kernel");
   RhsDesc rhs[2] = {{S_cols, ncols, (int64_t)n_int * ncols, ncols}, {gt, n_src, (int64_t)n_int * n_src, n_src}};
-  return lu_solve(st, 1, n_int, D, n_int, (int64_t)n_int * n_int, 2, rhs, lu_ws, lu_ws_bytes, info);
+  return lu_solve(st, 1, n_int, D, n_int, (int64_t)n_int * n_int, 2, rhs, lu_ws, lu_ws_bytes, info, LU_NO_PIVOT_EXPECTED);
 }
 
 int down_scatter(const Topo& tp, cudaStream_t st, int n_nodes, int m, int n_src, const double* g_ext,
@@ -886,7 +886,7 @@ int root_solve_oct(cudaStream_t st, int m, int n_src, int child0, int n_local, c
   HPS_LAUNCH_CHECK("root_assemble_kernel");
   RhsDesc rhs[2] = {{S_r, ncr, (int64_t)n_int * ncr, ncr}, {gt, n_src, (int64_t)n_int * n_src, n_src}};
   if (merge_structured()) root_cols_structure(child0, n_local, m, rhs[0].n_seg, rhs[0].seg_cols, rhs[0].seg_first_row);
-  return lu_solve(st, 1, n_int, D, n_int, (int64_t)n_int * n_int, 2, rhs, lu_ws, lu_ws_bytes, info);
+  return lu_solve(st, 1, n_int, D, n_int, (int64_t)n_int * n_int, 2, rhs, lu_ws, lu_ws_bytes, info, LU_NO_PIVOT_EXPECTED);
 }
 
 // Leading-zero structure of the root's -C_r (columns of children child0 .. child0+n_local-1, child-major: already

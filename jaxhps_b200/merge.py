@@ -52,14 +52,18 @@ def _merge_stage(T_arr, h_arr, l: int, dim: int, device, host_device, return_T: 
             _lib.check(ws_fn(step, m, n_src, ctypes.byref(need)), "merge workspace query")
             ws = _lib.workspace(need.value, dev)
             logging.debug("merge level %d: %d merges, m=%d, workspace %.2f GB", level, n_merges, m, need.value / 2**30)
-            for s0 in range(0, n_merges, step):
-                s1 = min(n_merges, s0 + step)
-                rc = level_fn(_lib.stream_ptr(), s1 - s0, m, n_src, _lib.ptr(T[n_child * s0:n_child * s1]),
-                              _lib.ptr(h[n_child * s0:n_child * s1]), _lib.ptr(S[s0:s1]), _lib.ptr(g[s0:s1]),
-                              _lib.ptr(T_out[s0:s1]) if want_T else None, _lib.ptr(h_out[s0:s1]) if want_T else None,
-                              1 if want_T else 0, _lib.ptr(ws), ws.numel(), _lib.ptr(info[s0:s1]))
-                _lib.check(rc, "hps_merge_dtn_level")
-            _lib.check_info(info, f"merge level {level}")
+            def run_level():
+                info.zero_()
+                for s0 in range(0, n_merges, step):
+                    s1 = min(n_merges, s0 + step)
+                    rc = level_fn(_lib.stream_ptr(), s1 - s0, m, n_src, _lib.ptr(T[n_child * s0:n_child * s1]),
+                                  _lib.ptr(h[n_child * s0:n_child * s1]), _lib.ptr(S[s0:s1]), _lib.ptr(g[s0:s1]),
+                                  _lib.ptr(T_out[s0:s1]) if want_T else None, _lib.ptr(h_out[s0:s1]) if want_T else None,
+                                  1 if want_T else 0, _lib.ptr(ws), ws.numel(), _lib.ptr(info[s0:s1]))
+                    _lib.check(rc, "hps_merge_dtn_level")
+                _lib.check_info(info, f"merge level {level}")
+
+            _lib.with_pivoting_fallback(run_level)  # the merge reads T, h only: a repeated level starts from the same inputs
             del T, h
             T, h = T_out, h_out
             S_lst.append(S)
@@ -124,10 +128,13 @@ def merge_root_columns_3D_DtN(T8, h8, col0: int, ncols: int, device=None):
         need = ctypes.c_size_t()
         _lib.check(lib.hps_merge_oct_dtn_level_workspace(1, m, n_src, ctypes.byref(need)), "merge workspace query")
         ws = _lib.workspace(need.value, dev)
-        rc = lib.hps_merge_oct_dtn_root_cols(_lib.stream_ptr(), m, n_src, _lib.ptr(T), _lib.ptr(h), col0, ncols,
-                                             _lib.ptr(S), _lib.ptr(g), _lib.ptr(ws), ws.numel(), _lib.ptr(info))
-        _lib.check(rc, "hps_merge_oct_dtn_root_cols")
-        _lib.check_info(info, "root merge")
+        def run():
+            rc = lib.hps_merge_oct_dtn_root_cols(_lib.stream_ptr(), m, n_src, _lib.ptr(T), _lib.ptr(h), col0, ncols,
+                                                 _lib.ptr(S), _lib.ptr(g), _lib.ptr(ws), ws.numel(), _lib.ptr(info))
+            _lib.check(rc, "hps_merge_oct_dtn_root_cols")
+            _lib.check_info(info, "root merge")
+
+        _lib.with_pivoting_fallback(run)
         return S, (g if multi else g[..., 0])
 
 

@@ -147,10 +147,14 @@ def _nosource_merge(T_arr, l: int, iti: bool, device, host_device, return_T: boo
                 _lib.check(lib.hps_merge_quad_dtn_level_workspace(n_merges, m, 1, ctypes.byref(need)), "workspace query")
                 fn = lib.hps_merge_quad_dtn_level_nosource
             ws = _lib.WORKSPACE.get(need.value, dev)
-            rc = fn(_lib.stream_ptr(), n_merges, m, _lib.ptr(T), _lib.ptr(S), _lib.ptr(T_out), _lib.ptr(D_inv),
-                    _lib.ptr(BD_inv), _lib.ptr(scratch), _lib.ptr(ws), ws.numel(), _lib.ptr(info))
-            _lib.check(rc, "hps_merge_quad_level_nosource")
-            _lib.check_info(info, f"no-source merge level {level}")
+            def run_level(fn=fn, n_merges=n_merges, m=m, T=T, S=S, T_out=T_out, D_inv=D_inv, BD_inv=BD_inv, scratch=scratch,
+                          ws=ws, info=info, level=level):
+                rc = fn(_lib.stream_ptr(), n_merges, m, _lib.ptr(T), _lib.ptr(S), _lib.ptr(T_out), _lib.ptr(D_inv),
+                        _lib.ptr(BD_inv), _lib.ptr(scratch), _lib.ptr(ws), ws.numel(), _lib.ptr(info))
+                _lib.check(rc, "hps_merge_quad_level_nosource")
+                _lib.check_info(info, f"no-source merge level {level}")
+
+            _lib.with_pivoting_fallback(run_level)
             # convert to the reference's stored layout: B D^-1 rows in pre-roll order, ItI D^-1 in solve order
             BD_inv = torch.roll(BD_inv, shifts=m, dims=1)
             if iti:

@@ -1,6 +1,7 @@
 """Time hps_lu_solve (factorisation only, or with right-hand sides) through the C ABI and split the time by
 kernel category (developer tool).  usage: bench_lu.py n batch [n_rhs_cols] [reps]"""
 import ctypes
+import os
 import sys
 
 import torch
@@ -15,6 +16,8 @@ ncols = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 torch.manual_seed(0)
 A0 = torch.randn(batch, n, n, dtype=torch.float64, device=dev) + 0.0
+if os.environ.get("HPS_LU_FORCE_SPEC") == "1":  # a matrix that partial pivoting leaves alone, like the merges' D
+    A0 += 4.0 * n**0.5 * torch.eye(n, dtype=torch.float64, device=dev)
 B0 = torch.randn(batch, n, max(ncols, 1), dtype=torch.float64, device=dev)
 need = ctypes.c_size_t()
 _lib.check(lib.hps_lu_solve_workspace(batch, n, ctypes.byref(need)), "ws")
@@ -58,4 +61,4 @@ if ncols:
     R = torch.bmm(A0, X) - B0
     print("   residual", float(R.abs().max() / (A0.abs().max() * X.abs().max() * n)))
 else:
-    assert int(info.abs().max()) == 0
+    assert int(info.abs().max()) == 0, info
