@@ -127,6 +127,21 @@ int hps_root_solve_oct(void* stream, int m, int n_src, int child0, int n_local,
                        const double* Dblk_all, const double* hblk_all, const double* Cblk_loc,
                        double* S_r, double* g_tilde, void* ws, size_t ws_bytes, int* info);
 
+/* The same two steps for an ARBITRARY set of exterior panels (one panel = one exterior face of one root child =
+ * m columns of S), which lets the ranks trade panels so that the leading zero rows of -C_r (hps_root_cols_structure)
+ * are spread evenly: jaxhps_b200/_dist.py assigns 24 / world panels to every rank, sorted by their child's first
+ * interface.  Cpan [n_panels][3m][m]: panel k = Cblk[child][:, i*m:(i+1)*m] of child panel_child[k] (its i-th
+ * exterior face).  S_r [12m][n_panels*m]; hps_root_panels_structure fills the segment description of such a set
+ * (error if the panels are not sorted by first interface).  Workspace: hps_root_solve_oct_workspace(m). */
+int hps_root_assemble_panels(void* stream, int m, int n_src, int n_panels, const int* panel_child,
+                             const double* Dblk_all, const double* hblk_all, const double* Cpan,
+                             double* D, double* S_r, double* g_tilde);
+int hps_root_solve_panels(void* stream, int m, int n_src, int n_panels, const int* panel_child,
+                          const double* Dblk_all, const double* hblk_all, const double* Cpan,
+                          double* S_r, double* g_tilde, void* ws, size_t ws_bytes, int* info);
+int hps_root_panels_structure(int n_panels, const int* panel_child, int m, int* n_seg, int* seg_cols,
+                              int* seg_first_row);
+
 /* Distributed factorisation of the root D (driven step by step from jaxhps_b200/_dist.py, which
  * issues the NCCL broadcasts in between).  Every rank holds the full n x n matrix (row-major, lda)
  * but keeps up to date only the 128-wide block columns it owns (b % world == rank).  Per block

@@ -50,6 +50,67 @@ def child_column_index(first_child: int, n_children: int, m: int) -> np.ndarray:
     return np.concatenate(idx)
 
 
+#: first interface (slot 0..11 of the root's interfaces 9..20) touched by the root's children a..h: the rows of
+#: -C above it are structurally zero in that child's columns (`hps_root_cols_structure`)
+_FIRST_SLOT = [0, 0, 1, 2, 4, 4, 5, 6]
+
+
+def balanced_panels(world: int):
+    """Which exterior panels ``(child, i)`` (the i-th exterior face of a root child: m columns of the root S) every
+    rank solves for.  A column that starts with s/12 zero rows costs (1 - s/12)^2 of a full one in the forward
+    substitution, so children a, b are the expensive ones and h the cheapest: the 24 panels are dealt out greedily,
+    heaviest first, 24 / world per rank, and sorted by first interface inside a rank (the order the structured
+    solve needs).  With one rank this is the reference's region order a..h."""
+    w = [(1.0 - s / 12.0) ** 2 for s in _FIRST_SLOT]
+    panels = sorted(((c, i) for c in range(8) for i in range(3)), key=lambda p: (-w[p[0]], p))
+    cap = 24 // world
+    bins, load = [[] for _ in range(world)], [0.0] * world
+    for p in panels:
+        r = min((q for q in range(world) if len(bins[q]) < cap), key=lambda q: (load[q], q))
+        bins[r].append(p)
+        load[r] += w[p[0]]
+    return [sorted(b, key=lambda p: (_FIRST_SLOT[p[0]], p)) for b in bins]
+
+
+def panel_column_index(panels, m: int) -> np.ndarray:
+    """Positions of the given panels' unknowns inside the root's face-ordered boundary vector."""
+    idx = []
+    for c, i in panels:
+        f = _CHILD_EXT_FACES[c][i]
+        panel = 4 * f + _FACE_CHILDREN[f].index(c)
+        idx.append(np.arange(panel * m, (panel + 1) * m))
+    return np.concatenate(idx)
+
+
+def exchange_panels(ops, Cblk, plan: "SubtreePlan", assign, m: int, group=None):
+    """``Cpan`` (n_panels, 3m, m) of this rank's panels, in ``assign[rank]`` order: its own children's panels are
+    sliced out of ``Cblk`` (n_local, 3m, 3m), the others arrive through one all-to-all (each rank sends most of its
+    three-per-child panels away; 61 MB per panel at L=3, under 1 GB at L=4 — NVLink-trivial next to the solve)."""
+    world, rank, per = plan.world, plan.rank, plan.octants_per_rank
+    first = plan.first_octant
+    mine = assign[rank]
+
+    def cut(c, i):
+        return Cblk[c - first][:, i * m : (i + 1) * m]
+
+    if world == 1:
+        return torch.stack([cut(c, i) for c, i in mine]).contiguous()
+    send_parts, send_counts = [], []
+    for q in range(world):
+        ps = [p for p in assign[q] if p[0] // per == rank]
+        send_counts.append(len(ps))
+        send_parts += [cut(c, i) for c, i in ps]
+    send = torch.stack(send_parts).contiguous() if send_parts else ops.empty((0, 3 * m, m))
+    arrival = [p for q in range(world) for p in mine if p[0] // per == q]  # order in which the panels arrive
+    recv_counts = [sum(1 for p in mine if p[0] // per == q) for q in range(world)]
+    recv = ops.empty((len(mine), 3 * m, m))
+    dist.all_to_all_single(recv, send, recv_counts, send_counts, group=group)
+    order = [arrival.index(p) for p in mine]
+    if order == list(range(len(mine))):
+        return recv
+    return recv[torch.as_tensor(order, device=recv.device)].contiguous()
+
+
 class SubtreePlan:
     """Which part of a uniform octree of depth ``L`` a rank owns."""
 
@@ -366,36 +427,38 @@ class CudaOps:
     #: skip the structurally-zero leading rows of -C_r in the root's forward substitution (HPS_MERGE_STRUCT=0: off)
     STRUCTURED = os.environ.get("HPS_MERGE_STRUCT", "1") != "0"
 
-    def root_solve(self, Dblk_all, hblk_all, Cblk_loc, first_child: int, rank: int = 0, world: int = 1, group=None,
+    def root_solve(self, Dblk_all, hblk_all, Cpan, panels, rank: int = 0, world: int = 1, group=None,
                    root_mode: str = "S"):
-        """This rank's columns of the root S (child-major) and the full g~.  Single rank or small root:
-        ``hps_root_solve_oct`` (replicated LU).  Otherwise the LU of D is distributed by block columns over the
-        library's P2P communicator (``hps_lu_dist_run``; NCCL-broadcast fallback ``hps_lu_dist_*``).
-        ``root_mode="factored"``: S is not formed — returns ``-C_r`` in its place and leaves the factors of D in
-        the communicator's segment for :meth:`root_apply`."""
+        """This rank's columns of the root S (one block of m columns per panel in ``panels`` = [(child, i), ...],
+        sorted by first interface) and the full g~.  ``Cpan`` (n_panels, 3m, m): see :func:`exchange_panels`.
+        Single rank or small root: ``hps_root_solve_panels`` (replicated LU).  Otherwise the LU of D is distributed
+        by block columns over the library's P2P communicator (``hps_lu_dist_run``; NCCL-broadcast fallback
+        ``hps_lu_dist_*``).  ``root_mode="factored"``: S is not formed — returns ``-C_r`` in its place and leaves the
+        factors of D in the communicator's segment for :meth:`root_apply`."""
         import ctypes
 
         lib = self._lib.load()
-        n_local, n3, _ = Cblk_loc.shape
-        m = n3 // 3
+        n_pan, n3, m = Cpan.shape
         n_src = hblk_all.shape[-1]
+        pc = (ctypes.c_int * n_pan)(*[c for c, _ in panels])
         if root_mode == "factored":
             if not USE_P2P:
                 raise ValueError("root_mode='factored' keeps the factors in the P2P segment (HPS_DIST_P2P=0 disables it)")
-            return self._root_solve_distributed(Dblk_all, hblk_all, Cblk_loc, first_child, rank, world, group, True)
+            return self._root_solve_distributed(Dblk_all, hblk_all, Cpan, pc, rank, world, group, True)
         if (world > 1 or self.FORCE_DIST_LU) and 12 * m >= self.DIST_LU_MIN_N:
-            return self._root_solve_distributed(Dblk_all, hblk_all, Cblk_loc, first_child, rank, world, group)
-        S_r = self.empty((12 * m, n3 * n_local))
+            return self._root_solve_distributed(Dblk_all, hblk_all, Cpan, pc, rank, world, group)
+        S_r = self.empty((12 * m, n_pan * m))
         g = self.empty((12 * m, n_src))
         info = torch.zeros(1, dtype=torch.int32, device=self.dev)
         need = ctypes.c_size_t()
         self._lib.check(lib.hps_root_solve_oct_workspace(m, ctypes.byref(need)), "workspace query")
         ws = self._lib.WORKSPACE.get(need.value, self.dev)
+
         def run():
-            rc = lib.hps_root_solve_oct(self._lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),
-                                        hblk_all.data_ptr(), Cblk_loc.data_ptr(), S_r.data_ptr(), g.data_ptr(), ws.data_ptr(),
-                                        ws.numel(), info.data_ptr())
-            self._lib.check(rc, "hps_root_solve_oct")
+            rc = lib.hps_root_solve_panels(self._lib.stream_ptr(), m, n_src, n_pan, pc, Dblk_all.data_ptr(),
+                                           hblk_all.data_ptr(), Cpan.data_ptr(), S_r.data_ptr(), g.data_ptr(), ws.data_ptr(),
+                                           ws.numel(), info.data_ptr())
+            self._lib.check(rc, "hps_root_solve_panels")
             self._lib.check_info(info, "root merge")
 
         self._lib.with_pivoting_fallback(run)
@@ -418,45 +481,50 @@ class CudaOps:
                    "hps_lu_dist_apply")
         return x
 
-    def _root_solve_distributed(self, Dblk_all, hblk_all, Cblk_loc, first_child, rank, world, group, factored=False):
-        """Distributed LU of the root D: block column b is factored by rank b % world, broadcast, and
-        applied by every rank to the block columns it owns; then local solves of the rank's columns."""
+    def _root_solve_distributed(self, Dblk_all, hblk_all, Cpan, pc, rank, world, group, factored=False):
+        """Distributed LU of the root D: block column b is factored by rank b % world, stored into the peers'
+        segments, and applied by every rank to the block columns it owns; the rank's right-hand sides ride along."""
+        import ctypes
+
         lib = self._lib.load()
         _lib = self._lib
-        n_local, n3, _ = Cblk_loc.shape
-        m = n3 // 3
+        n_pan, n3, m = Cpan.shape
         n_src = hblk_all.shape[-1]
         n = 12 * m
-        S_r = self.empty((n, n3 * n_local))
+        S_r = self.empty((n, n_pan * m))
         g = self.empty((n, n_src))
+
+        def assemble(D_ptr):
+            rc = lib.hps_root_assemble_panels(_lib.stream_ptr(), m, n_src, n_pan, pc, Dblk_all.data_ptr(), hblk_all.data_ptr(),
+                                              Cpan.data_ptr(), D_ptr, S_r.data_ptr(), g.data_ptr())
+            _lib.check(rc, "hps_root_assemble_panels")
+
         if USE_P2P:
             # D is assembled directly inside this rank's symmetric segment; the owners of the block columns
             # later store the factored columns into the same place on every peer
             comm = P2PComm.get(_lib, self.dev, rank, world, group)
             comm.ensure(comm.lu_segment_bytes(n))
-            def assemble():
-                rc = lib.hps_root_assemble_oct(_lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),
-                                               hblk_all.data_ptr(), Cblk_loc.data_ptr(), comm.matrix_ptr(n), S_r.data_ptr(),
-                                               g.data_ptr())
-                _lib.check(rc, "hps_root_assemble_oct")
+            structure = None
+            if self.STRUCTURED and not factored:  # leading zero rows of -C_r, panel by panel
+                n_seg, seg_cols = ctypes.c_int(), ctypes.c_int()
+                first = (ctypes.c_int * n_pan)()
+                _lib.check(lib.hps_root_panels_structure(n_pan, pc, m, ctypes.byref(n_seg), ctypes.byref(seg_cols), first),
+                           "hps_root_panels_structure")
+                structure = (n_seg.value, seg_cols.value, first)
 
-            # factored root: only g~ goes through the solve; S_r keeps -C_r for the solves
-            structure = root_cols_structure(_lib, first_child, n_local, m) if (self.STRUCTURED and not factored) else None
-
-            def run(structure=structure):
-                assemble()
+            def run():
+                assemble(comm.matrix_ptr(n))
+                # factored root: only g~ goes through the solve; S_r keeps -C_r for the solves
                 try:
                     p2p_lu_solve(_lib, self.dev, comm, n, [g] if factored else [S_r, g], group, structure)
                 except StructureInvalid:  # rows were interchanged: the zero-row shortcut does not apply to this matrix
-                    assemble()
+                    assemble(comm.matrix_ptr(n))
                     p2p_lu_solve(_lib, self.dev, comm, n, [g] if factored else [S_r, g], group)
 
             _lib.with_pivoting_fallback(run)  # (info = -2: the speculative block columns did not apply either)
             return S_r, g
         D = self.empty((n, n))
-        rc = lib.hps_root_assemble_oct(_lib.stream_ptr(), m, n_src, first_child, n_local, Dblk_all.data_ptr(),
-                                       hblk_all.data_ptr(), Cblk_loc.data_ptr(), D.data_ptr(), S_r.data_ptr(), g.data_ptr())
-        _lib.check(rc, "hps_root_assemble_oct")
+        assemble(D.data_ptr())
         distributed_lu_solve(_lib, self.dev, D, [S_r, g], rank, world, group)
         return S_r, g
 
@@ -509,7 +577,8 @@ class ShardedState:
         self.Y = self.v = None
         self.S_lst: List = []
         self.g_tilde_lst: List = []
-        self.S_root_cols = None  # (12m, 3m * octants_per_rank): columns of this rank's children
+        self.S_root_cols = None  # (12m, m * 24 / world): this rank's exterior panels (balanced_panels), m columns each
+        self.panels = None  # [(child, i)] behind those column blocks
         self.g_tilde_root = None  # (12m, n_src)
         self.col_index = None  # where those columns sit in the root's boundary vector
         self.root_mode = "S"  # "factored": S_root_cols holds -C_r and the factors of D stay in the P2P segment
@@ -546,6 +615,13 @@ def build_solver_sharded(pde_problem: PDEProblem, plan: SubtreePlan, device=None
     Dblk, Cblk, hblk = ops.root_pack(T_roots, h_roots, plan.first_octant)
     m = T_roots.shape[-1] // 6
     del T_roots, h_roots
+    # which exterior panels this rank solves for: balanced over the ranks (see balanced_panels); one all-to-all
+    assign = balanced_panels(plan.world)
+    panels = assign[plan.rank]
+    if plan.world > 1 and not _group_ok(plan):
+        raise RuntimeError("torch.distributed must be initialised for world > 1")
+    Cpan = exchange_panels(ops, Cblk, plan, assign, m, group)
+    del Cblk
     if plan.world > 1:
         if not _group_ok(plan):
             raise RuntimeError("torch.distributed must be initialised for world > 1")
@@ -559,13 +635,13 @@ def build_solver_sharded(pde_problem: PDEProblem, plan: SubtreePlan, device=None
     if D_all.numel() * 8 > (4 << 30) and D_all.is_cuda:
         torch.cuda.empty_cache()  # the root D needs one large block; give freed subtree buffers back first
     if root_mode == "factored":
-        st.S_root_cols, g = ops.root_solve(D_all, h_all, Cblk, plan.first_octant, plan.rank, plan.world, group,
-                                           root_mode="factored")
+        st.S_root_cols, g = ops.root_solve(D_all, h_all, Cpan, panels, plan.rank, plan.world, group, root_mode="factored")
     else:
-        st.S_root_cols, g = ops.root_solve(D_all, h_all, Cblk, plan.first_octant, plan.rank, plan.world, group)
+        st.S_root_cols, g = ops.root_solve(D_all, h_all, Cpan, panels, plan.rank, plan.world, group)
     st.g_tilde_root = g
     st.multi = multi
-    st.col_index = ops.tensor(child_column_index(plan.first_octant, n_oct, m)).to(torch.int64)
+    st.panels = panels
+    st.col_index = ops.tensor(panel_column_index(panels, m)).to(torch.int64)
     return st
 
 

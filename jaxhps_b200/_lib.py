@@ -44,6 +44,9 @@ _SIGNATURES = {
     "hps_root_solve_oct_workspace": (_i, [_i, ctypes.POINTER(_sz)]),
     "hps_root_solve_oct": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "hps_root_assemble_oct": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "hps_root_assemble_panels": (_i, [_p, _i, _i, _i, ctypes.POINTER(_i), _p, _p, _p, _p, _p, _p]),
+    "hps_root_solve_panels": (_i, [_p, _i, _i, _i, ctypes.POINTER(_i), _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "hps_root_panels_structure": (_i, [_i, ctypes.POINTER(_i), _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "hps_lu_dist_buffer_doubles": (_i, [_i, ctypes.POINTER(_sz)]),
     "hps_lu_dist_factor_pack": (_i, [_p, _i, _p, _l, _i, _p, _sz, _p, _p]),
     "hps_lu_dist_unpack": (_i, [_p, _i, _p, _l, _i, _p, _sz, _p]),

@@ -227,6 +227,21 @@ int hps_root_assemble_oct(void* stream, int m, int n_src, int child0, int n_loca
   return root_assemble_oct(static_cast<cudaStream_t>(stream), m, n_src, child0, n_local, Dblk_all, hblk_all, Cblk_loc, D,
                            S_r, g_tilde);
 }
+int hps_root_assemble_panels(void* stream, int m, int n_src, int n_panels, const int* panel_child, const double* Dblk_all,
+                             const double* hblk_all, const double* Cpan, double* D, double* S_r, double* g_tilde) {
+  return root_assemble_panels(static_cast<cudaStream_t>(stream), m, n_src, n_panels, panel_child, Dblk_all, hblk_all, Cpan,
+                              D, S_r, g_tilde);
+}
+int hps_root_solve_panels(void* stream, int m, int n_src, int n_panels, const int* panel_child, const double* Dblk_all,
+                          const double* hblk_all, const double* Cpan, double* S_r, double* g_tilde, void* ws,
+                          size_t ws_bytes, int* info) {
+  return root_solve_panels(static_cast<cudaStream_t>(stream), m, n_src, n_panels, panel_child, Dblk_all, hblk_all, Cpan, S_r,
+                           g_tilde, ws, ws_bytes, info);
+}
+int hps_root_panels_structure(int n_panels, const int* panel_child, int m, int* n_seg, int* seg_cols, int* seg_first_row) {
+  if (!n_seg || !seg_cols || !seg_first_row || m <= 0) return fail_arg(3, "null output / non-positive m");
+  return root_panels_structure(n_panels, panel_child, m, *n_seg, *seg_cols, seg_first_row);
+}
 int hps_lu_dist_buffer_doubles(int n, size_t* count) {
   if (!count) return fail_arg(2, "null output pointer");
   *count = lu_dist_block_buffer_doubles(n);

@@ -176,6 +176,12 @@ void root_cols_structure(int child0, int n_local, int m, int& n_seg, int& seg_co
 int root_solve_oct(cudaStream_t st, int m, int n_src, int child0, int n_local, const double* Dblk_all,
                    const double* hblk_all, const double* Cblk_loc, double* S_r, double* gt, void* ws, size_t ws_bytes,
                    int* info);
+int root_assemble_panels(cudaStream_t st, int m, int n_src, int n_panels, const int* panel_child, const double* Dblk_all,
+                         const double* hblk_all, const double* Cpan, double* D, double* S_r, double* gt);
+int root_panels_structure(int n_panels, const int* panel_child, int m, int& n_seg, int& seg_cols, int* seg_first_row);
+int root_solve_panels(cudaStream_t st, int m, int n_src, int n_panels, const int* panel_child, const double* Dblk_all,
+                      const double* hblk_all, const double* Cpan, double* S_r, double* gt, void* ws, size_t ws_bytes,
+                      int* info);
 int merge_oct_root_cols(cudaStream_t st, int m, int n_src, const double* T_in, const double* h_in, int ext0, int ncols,
                         double* S_cols, double* gt, void* ws, size_t ws_bytes, int* info);
 int down_oct_scatter(cudaStream_t st, int n_nodes, int m, int n_src, const double* g_ext, const double* g_int,

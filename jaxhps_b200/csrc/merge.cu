@@ -809,6 +809,65 @@ __global__ void __launch_bounds__(256) root_assemble_kernel(Topo tp, int m, int 
   }
 }
 
+// The same assembly for an arbitrary set of exterior PANELS (one panel = one exterior face of one child, m columns):
+// the balanced column distribution of the multi-GPU root.  Cpan[k] (3m x m) = T_c[int faces (slot order), that face]
+// of the child c = pan.child[k]; columns of C_r follow the order of the panels.
+struct PanelList { int n; signed char child[MAXE]; };
+__global__ void __launch_bounds__(256) root_assemble_panels_kernel(Topo tp, int m, int n_src, PanelList pan,
+                                                                   const double* __restrict__ Dblk_all,
+                                                                   const double* __restrict__ hblk_all,
+                                                                   const double* __restrict__ Cpan, double* __restrict__ D,
+                                                                   double* __restrict__ Cr, double* __restrict__ gt) {
+  const int n_int = 12 * m, n3 = 3 * m, ncr = pan.n * m;
+  auto loc = [&](int c, int s) {
+    int k = 0;
+    for (int s2 = 0; s2 < s; ++s2) k += (tp.slot_face[c][s2] >= 0);
+    return k;
+  };
+  for (int row = blockIdx.y; row < n_int; row += gridDim.y) {
+    const int s1 = row / m, t1 = row - s1 * m;
+    const int cA = tp.slot_owner[s1][0], cB = tp.slot_owner[s1][1];
+    const int iA = loc(cA, s1), iB = loc(cB, s1);
+    const double* rowA = Dblk_all + ((int64_t)cA * n3 + iA * m + t1) * n3;
+    const double* rowB = Dblk_all + ((int64_t)cB * n3 + iB * m + t1) * n3;
+    for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < n_int + ncr + n_src; col += gridDim.x * blockDim.x) {
+      if (col < n_int) {
+        const int s2 = col / m, t2 = col - s2 * m;
+        double v = 0.0;
+        if (tp.slot_face[cA][s2] >= 0) v += rowA[loc(cA, s2) * m + t2];
+        if (tp.slot_face[cB][s2] >= 0) v += rowB[loc(cB, s2) * m + t2];
+        D[(int64_t)row * n_int + col] = v;
+      } else if (col < n_int + ncr) {
+        const int cc = col - n_int;
+        const int k = cc / m, t2 = cc - k * m;
+        const int c = pan.child[k];
+        double v = 0.0;
+        if (c == cA) v = Cpan[((int64_t)k * n3 + iA * m + t1) * m + t2];
+        else if (c == cB) v = Cpan[((int64_t)k * n3 + iB * m + t1) * m + t2];
+        Cr[(int64_t)row * ncr + cc] = -v;
+      } else {
+        const int k = col - n_int - ncr;
+        gt[(int64_t)row * n_src + k] = -(hblk_all[((int64_t)cA * n3 + iA * m + t1) * n_src + k] +
+                                         hblk_all[((int64_t)cB * n3 + iB * m + t1) * n_src + k]);
+      }
+    }
+  }
+}
+int first_slot_of_child(const Topo& tp, int c) {
+  int first = 0;
+  while (tp.slot_face[c][first] < 0) ++first;
+  return first;
+}
+int make_panel_list(int n_panels, const int* panel_child, PanelList& pan) {
+  if (n_panels <= 0 || n_panels > MAXE || !panel_child) return fail_arg(4, "1..24 panels expected");
+  pan.n = n_panels;
+  for (int k = 0; k < n_panels; ++k) {
+    if (panel_child[k] < 0 || panel_child[k] > 7) return fail_arg(5, "panel child out of range");
+    pan.child[k] = (signed char)panel_child[k];
+  }
+  return 0;
+}
+
 // Column-sharded merge for the multi-GPU root: S[:, ext0:ext0+ncols] and g~ from the children's T.
 int merge_cols(const Topo& tp, cudaStream_t st, int m, int n_src, const double* T_in, const double* h_in, int ext0,
                int ncols, double* S_cols, double* gt, void* ws, size_t ws_bytes, int* info) {
@@ -900,6 +959,53 @@ void root_cols_structure(int child0, int n_local, int m, int& n_seg, int& seg_co
     while (tp.slot_face[child0 + cl][first] < 0) ++first;
     for (int k = 0; k < 3; ++k) seg_first_row[3 * cl + k] = first * m;
   }
+}
+
+// Panel versions (balanced multi-GPU root): panel_child[k] = child owning the k-th panel of this rank.
+int root_assemble_panels(cudaStream_t st, int m, int n_src, int n_panels, const int* panel_child, const double* Dblk_all,
+                         const double* hblk_all, const double* Cpan, double* D, double* S_r, double* gt) {
+  if (m <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
+  PanelList pan;
+  HPS_TRY(make_panel_list(n_panels, panel_child, pan));
+  const int n_int = 12 * m, cols = n_int + n_panels * m + n_src;
+  dim3 grid(std::min((cols + 255) / 256, 64), std::min(n_int, 65535), 1);
+  root_assemble_panels_kernel<<<grid, 256, 0, st>>>(oct_topo(), m, n_src, pan, Dblk_all, hblk_all, Cpan, D, S_r, gt);
+  HPS_LAUNCH_CHECK("root_assemble_panels_kernel");
+  return 0;
+}
+// leading-zero structure of such a panel set; fails unless the panels are sorted by their child's first interface
+int root_panels_structure(int n_panels, const int* panel_child, int m, int& n_seg, int& seg_cols, int* seg_first_row) {
+  PanelList pan;
+  HPS_TRY(make_panel_list(n_panels, panel_child, pan));
+  const Topo& tp = oct_topo();
+  n_seg = n_panels;
+  seg_cols = m;
+  for (int k = 0; k < n_panels; ++k) {
+    seg_first_row[k] = first_slot_of_child(tp, pan.child[k]) * m;
+    if (k > 0 && seg_first_row[k] < seg_first_row[k - 1]) return fail_arg(2, "panels must be sorted by first interface");
+  }
+  return 0;
+}
+int root_solve_panels(cudaStream_t st, int m, int n_src, int n_panels, const int* panel_child, const double* Dblk_all,
+                      const double* hblk_all, const double* Cpan, double* S_r, double* gt, void* ws, size_t ws_bytes,
+                      int* info) {
+  if (m <= 0 || n_src <= 0) return fail_arg(2, "non-positive size");
+  const int n_int = 12 * m, ncr = n_panels * m;
+  Arena ar(ws, ws_bytes);
+  double* D = ar.take<double>((size_t)n_int * n_int);
+  if (!D) return fail_arg(11, "root_solve: workspace too small");
+  void* lu_ws = ar.base + ar.off;
+  const size_t lu_ws_bytes = ar.cap - ar.off;
+  HPS_TRY(root_assemble_panels(st, m, n_src, n_panels, panel_child, Dblk_all, hblk_all, Cpan, D, S_r, gt));
+  RhsDesc rhs[2] = {{S_r, ncr, (int64_t)n_int * ncr, ncr}, {gt, n_src, (int64_t)n_int * n_src, n_src}};
+  if (merge_structured()) {
+    int first[RHS_MAX_SEG];
+    if (root_panels_structure(n_panels, panel_child, m, rhs[0].n_seg, rhs[0].seg_cols, first) == 0)
+      for (int k = 0; k < n_panels; ++k) rhs[0].seg_first_row[k] = first[k];
+    else
+      rhs[0].n_seg = 0;  // unsorted panels: solve without the shortcut
+  }
+  return lu_solve(st, 1, n_int, D, n_int, (int64_t)n_int * n_int, 2, rhs, lu_ws, lu_ws_bytes, info, LU_NO_PIVOT_EXPECTED);
 }
 
 int merge_oct_root_cols(cudaStream_t st, int m, int n_src, const double* T_in, const double* h_in, int ext0, int ncols,

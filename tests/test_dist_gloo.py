@@ -53,13 +53,12 @@ class OracleOps:
             D.append(T[k][np.ix_(ii, ii)]), C.append(T[k][np.ix_(ii, ee)]), hb.append(h[k][ii])
         return tuple(torch.from_numpy(np.ascontiguousarray(np.stack(x))) for x in (D, C, hb))
 
-    def root_solve(self, Dblk_all, hblk_all, Cblk_loc, first_child, rank=0, world=1, group=None):
-        Db, hb, Cb = Dblk_all.numpy(), hblk_all.numpy(), Cblk_loc.numpy()
+    def root_solve(self, Dblk_all, hblk_all, Cpan, panels, rank=0, world=1, group=None):
+        Db, hb, Cp = Dblk_all.numpy(), hblk_all.numpy(), Cpan.numpy()
         m = Db.shape[-1] // 3
-        n_local = Cb.shape[0]
         D = np.zeros((12 * m, 12 * m))
         h_int = np.zeros((12 * m, hb.shape[-1]))
-        C = np.zeros((12 * m, 3 * m * n_local))
+        C = np.zeros((12 * m, m * len(panels)))
         for c in range(8):
             roles = orc._OCT_ROLES[c]
             slots = sorted(roles[f][1] for f in range(6) if roles[f][0] == "int")
@@ -67,9 +66,9 @@ class OracleOps:
                 h_int[si * m : (si + 1) * m] += hb[c][i * m : (i + 1) * m]
                 for j, sj in enumerate(slots):
                     D[si * m : (si + 1) * m, sj * m : (sj + 1) * m] += Db[c][i * m : (i + 1) * m, j * m : (j + 1) * m]
-                if first_child <= c < first_child + n_local:
-                    k = c - first_child
-                    C[si * m : (si + 1) * m, 3 * m * k : 3 * m * (k + 1)] = Cb[k][i * m : (i + 1) * m]
+                for k, (pc, _) in enumerate(panels):  # panel k: m columns of child pc's C block
+                    if pc == c:
+                        C[si * m : (si + 1) * m, k * m : (k + 1) * m] = Cp[k][i * m : (i + 1) * m]
         D_inv = np.linalg.inv(D)
         return torch.from_numpy(-D_inv @ C), torch.from_numpy(-D_inv @ h_int)
 
@@ -148,5 +147,18 @@ def test_subtree_plan_partitions_the_leaves():
         assert np.array_equal(covered, np.arange(512))
     cols = np.concatenate([_dist.child_column_index(c, 1, 5) for c in range(8)])
     assert sorted(cols) == list(range(24 * 5))
+    for world in (1, 2, 4, 8):  # the balanced panel assignment covers every exterior panel once, sorted inside a rank
+        assign = _dist.balanced_panels(world)
+        assert sorted(p for b in assign for p in b) == [(c, i) for c in range(8) for i in range(3)]
+        assert all(len(b) == 24 // world for b in assign)
+        for b in assign:
+            first = [_dist._FIRST_SLOT[c] for c, _ in b]
+            assert first == sorted(first)
+        cols = np.concatenate([_dist.panel_column_index(b, 5) for b in assign])
+        assert sorted(cols) == list(range(24 * 5))
+        loads = [sum((1 - _dist._FIRST_SLOT[c] / 12) ** 2 for c, _ in b) for b in assign]
+        assert max(loads) < 1.05 * 15.05 / world + 0.1  # forward-substitution weights: within 5 % of the mean
+    assert np.array_equal(_dist.panel_column_index(_dist.balanced_panels(1)[0], 5), cols_ref := np.concatenate(
+        [_dist.child_column_index(c, 1, 5) for c in range(8)]))
     with pytest.raises(ValueError):
         _dist.SubtreePlan(3, 0, 3)
