@@ -21,6 +21,7 @@ n, ncols = int(sys.argv[1]), int(sys.argv[2])
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 g = torch.Generator(device="cpu").manual_seed(0)
 A0 = torch.randn(n, n, dtype=torch.float64, generator=g).to(dev)  # same matrix on every rank
+A0 += 4.0 * n**0.5 * torch.eye(n, dtype=torch.float64, device=dev)  # like the merges' D: partial pivoting leaves it alone
 B0 = torch.randn(n, ncols, dtype=torch.float64, device=dev)
 comm = _dist.P2PComm.get(_lib, dev, rank, world, None)
 comm.ensure(comm.lu_segment_bytes(n))
