@@ -424,6 +424,23 @@ def run_ours(args, rank, world, local_rank):
     pm, pw, pl, _ = read_prof(lib, _lib)
     lib.hps_prof_enable(0)
 
+    # ---- sharded runs: stage boundaries of one more untimed build on rank 0 (CUDA events; developer breakdown) ----
+    sharded_stages = None
+    if R.plan is not None:
+        R._dist.STAGE_TIMING = True
+        R.pb_res.reset()
+        st_dbg = R._dist.build_solver_sharded(R.pb_res, R.plan, dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        R._dist.solve_sharded(R.pb_res, st_dbg, R.plan, R.g_dev, dev)
+        e1.record()
+        torch.cuda.synchronize()
+        sharded_stages = dict(st_dbg.timing or {})
+        sharded_stages["solve"] = e0.elapsed_time(e1)
+        R._dist.STAGE_TIMING = False
+        del st_dbg
+        R.barrier()
+
     # ---- per-stage breakdown (single GPU; not part of the timed region): the stage functions one by one ----
     stages = None
     fp64_peak_for_stages = fp64_sustained
@@ -563,6 +580,7 @@ def run_ours(args, rank, world, local_rank):
         "build_solve_seconds": ms_step * 1e-3,
         "max_rel_error_vs_analytic_solution": max_rel_err,
         "stages": stages,
+        "sharded_stages_ms_rank0": sharded_stages,
         "algorithmic_tflop_per_step": lean_flops(L) * 1e-12,
         "step_tflops": lean_flops(L) * 1e-12 / (ms_step * 1e-3),
         "step_frac_of_fp64_peak": lean_flops(L) * 1e-12 / (ms_step * 1e-3) / world / fp64_sustained,

@@ -228,6 +228,9 @@ class P2PComm:
         return need.value
 
 
+#: record CUDA events at the stage boundaries of build_solver_sharded (``ShardedState.timing``, ms; one extra sync)
+STAGE_TIMING = os.environ.get("HPS_DIST_TIMING", "0") == "1"
+
 #: the distributed factorisation runs from C over the library's P2P communicator (0: the step-wise
 #: NCCL-broadcast driver below, kept as the fallback when CUDA IPC is unavailable)
 USE_P2P = os.environ.get("HPS_DIST_P2P", "1") != "0"
@@ -581,6 +584,7 @@ class ShardedState:
         self.panels = None  # [(child, i)] behind those column blocks
         self.g_tilde_root = None  # (12m, n_src)
         self.col_index = None  # where those columns sit in the root's boundary vector
+        self.timing = None  # stage -> ms when STAGE_TIMING is on
         self.root_mode = "S"  # "factored": S_root_cols holds -C_r and the factors of D stay in the P2P segment
 
 
@@ -603,13 +607,24 @@ def build_solver_sharded(pde_problem: PDEProblem, plan: SubtreePlan, device=None
     ops = ops or CudaOps(device)
     st = ShardedState()
     st.root_mode = root_mode
+    marks = [] if STAGE_TIMING else None  # developer aid (HPS_DIST_TIMING=1 / bench.py): CUDA events at stage boundaries
+
+    def mark(name):
+        if marks is not None and torch.cuda.is_available():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
+
+    mark("start")
     Y, T, v, h = ops.local_solve(pde_problem)
+    mark("local_solve")
     st.Y, st.v = Y, v
     n_oct = plan.octants_per_rank
     if plan.L > 1:
         st.S_lst, st.g_tilde_lst, T_roots, h_roots = ops.merge_subtrees(T, h, plan.L - 1, n_oct)
     else:
         T_roots, h_roots = T, h
+    mark("subtree_merges")
     # ---- up: only the children's interface blocks travel (a quarter of each subtree-root T) ----
     multi = h_roots.ndim == 3
     Dblk, Cblk, hblk = ops.root_pack(T_roots, h_roots, plan.first_octant)
@@ -620,8 +635,10 @@ def build_solver_sharded(pde_problem: PDEProblem, plan: SubtreePlan, device=None
     panels = assign[plan.rank]
     if plan.world > 1 and not _group_ok(plan):
         raise RuntimeError("torch.distributed must be initialised for world > 1")
+    mark("root_pack")
     Cpan = exchange_panels(ops, Cblk, plan, assign, m, group)
     del Cblk
+    mark("panel_exchange")
     if plan.world > 1:
         if not _group_ok(plan):
             raise RuntimeError("torch.distributed must be initialised for world > 1")
@@ -632,12 +649,17 @@ def build_solver_sharded(pde_problem: PDEProblem, plan: SubtreePlan, device=None
     else:
         D_all, h_all = Dblk, hblk
     del Dblk
+    mark("interface_all_gather")
     if D_all.numel() * 8 > (4 << 30) and D_all.is_cuda:
         torch.cuda.empty_cache()  # the root D needs one large block; give freed subtree buffers back first
     if root_mode == "factored":
         st.S_root_cols, g = ops.root_solve(D_all, h_all, Cpan, panels, plan.rank, plan.world, group, root_mode="factored")
     else:
         st.S_root_cols, g = ops.root_solve(D_all, h_all, Cpan, panels, plan.rank, plan.world, group)
+    mark("root_solve")
+    if marks:
+        torch.cuda.synchronize()
+        st.timing = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
     st.g_tilde_root = g
     st.multi = multi
     st.panels = panels

@@ -947,16 +947,16 @@ __device__ __forceinline__ void smem_mm(double* dst, int ldd, const double* A, i
   }
 }
 
-__global__ void __launch_bounds__(TRI_THREADS) trtri_lower_kernel(const double* A, int64_t lda, int64_t sA, int j0, int n,
-                                                                  double* W, int64_t sW) {
+__device__ __forceinline__ void trtri_lower_body(const double* A, int64_t lda, int64_t sA, int j0, int n,
+                                                                  double* W, int64_t sW, int bx, int by) {
   extern __shared__ __align__(16) double sm[];
   constexpr int LD = TRI_LD;
   double* Ts = sm;                 // [NB][LD]   the triangle, inverted in place
   double* Ws = sm + NB * LD;       // [64][65]   product scratch
   double* Xs = Ws + 64 * 65;       // [4][32][33] columns of the 32x32 diagonal inverses
-  const int j = j0 + blockIdx.x * NB;      // diagonal block handled by this CTA
+  const int j = j0 + bx * NB;      // diagonal block handled by this CTA
   const int nb = min(NB, n - j);
-  const double* a = A + (int64_t)blockIdx.y * sA + (int64_t)j * lda + j;
+  const double* a = A + (int64_t)by * sA + (int64_t)j * lda + j;
   // ragged blocks are padded with the identity
   for (int idx = threadIdx.x; idx < NB * NB; idx += TRI_THREADS) {
     const int rr = idx / NB, cc = idx - rr * NB;
@@ -967,17 +967,25 @@ __global__ void __launch_bounds__(TRI_THREADS) trtri_lower_kernel(const double* 
   __syncthreads();
   // ---- phase 1: the four 32x32 diagonal blocks, one column per lane ----
   if (threadIdx.x < 128) {
+    // column c of the inverse of a unit-lower 32 x 32 block, in this lane's registers (static indices, two accumulators)
     const int blk = threadIdx.x >> 5, c = threadIdx.x & 31, base = blk * 32;
-    double* x = Xs + blk * 32 * 33;  // x[r*33 + c]
     const double* T = Ts + base * LD + base;
-    for (int r = 0; r < 32; ++r) x[r * 33 + c] = (r == c) ? 1.0 : 0.0;
-    for (int r = c + 1; r < 32; ++r) {
-      double s = 0.0;
-      for (int t = c; t < r; ++t) s = fma(T[r * LD + t], x[t * 33 + c], s);
-      x[r * 33 + c] = -s;
+    double x[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        if (t < r) {
+          if (t & 1) s1 = fma(T[r * LD + t], x[t], s1);
+          else s0 = fma(T[r * LD + t], x[t], s0);
+        }
+      }
+      x[r] = (r == c) ? 1.0 : ((r > c) ? -(s0 + s1) : 0.0);
     }
-    __syncwarp();
-    for (int r = 0; r < 32; ++r) Ts[(base + r) * LD + base + c] = x[r * 33 + c];
+    __syncwarp();  // every lane has read the block before any lane overwrites it
+#pragma unroll
+    for (int r = 0; r < 32; ++r) Ts[(base + r) * LD + base + c] = x[r];
   }
   __syncthreads();
   // ---- phase 2: 32-level off-diagonal blocks of both 64x64 halves ----
@@ -996,11 +1004,15 @@ __global__ void __launch_bounds__(TRI_THREADS) trtri_lower_kernel(const double* 
   __syncthreads();
   smem_mm(Ts + 64 * LD, LD, Ts + 64 * LD + 64, LD, Ws, 65, 64, 64, 64, -1.0);       // X21 = -inv(L22) * W
   __syncthreads();
-  double* w = W + (int64_t)blockIdx.y * sW + (int64_t)(j / NB) * NB * NB;
+  double* w = W + (int64_t)by * sW + (int64_t)(j / NB) * NB * NB;
   for (int idx = threadIdx.x; idx < nb * nb; idx += TRI_THREADS) {
     const int rr = idx / nb, cc = idx - rr * nb;
     w[rr * NB + cc] = Ts[rr * LD + cc];
   }
+}
+__global__ void __launch_bounds__(TRI_THREADS) trtri_lower_kernel(const double* A, int64_t lda, int64_t sA, int j0, int n,
+                                                                  double* W, int64_t sW) {
+  trtri_lower_body(A, lda, sA, j0, n, W, sW, blockIdx.x, blockIdx.y);
 }
 
 // Inverse of the nb x nb UPPER-triangular diagonal blocks (with their diagonal) by BACK SUBSTITUTION, U X = I:
@@ -1014,16 +1026,37 @@ __global__ void __launch_bounds__(TRI_THREADS) trtri_lower_kernel(const double* 
 //   U[I][I] X[I][J] = -W                 (one column per lane, 32 sequential rows)
 // i.e. exactly the terms of the column-wise substitution, re-associated.  X[I][J], I < J, is kept in the unused
 // block (J, I) of the tile's lower triangle, the diagonal blocks of X in Xd.
-__global__ void __launch_bounds__(TRI_THREADS) trtri_upper_kernel(const double* A, int64_t lda, int64_t sA, int j0, int n,
-                                                                  double* W, int64_t sW) {
+// Back substitution U x = b for ONE column held in this lane's registers (static indices: both loops are unrolled).
+// On entry x[r] = b[r]; rows above `top` are the only ones that can be non-zero.  U: 32 x 32 upper block at T (ld),
+// rdiag[r] = 1 / U[r][r].  Two accumulators halve the dependent FMA chain of each row's dot product.
+__device__ __forceinline__ void backsub32(const double* __restrict__ T, int ld, const double* __restrict__ rdiag,
+                                          double (&x)[32], int top) {
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) {
+    const int r = 31 - rr;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      if (t > r) {
+        if (t & 1) s1 = fma(T[r * ld + t], x[t], s1);
+        else s0 = fma(T[r * ld + t], x[t], s0);
+      }
+    }
+    x[r] = (r <= top) ? (x[r] - (s0 + s1)) * rdiag[r] : 0.0;
+  }
+}
+
+__device__ __forceinline__ void trtri_upper_body(const double* A, int64_t lda, int64_t sA, int j0, int n,
+                                                  double* W, int64_t sW, int bx, int by) {
   extern __shared__ __align__(16) double sm[];
   constexpr int LD = TRI_LD;
   double* Ts = sm;                  // [NB][LD]     U in the upper triangle, X[I][J] (I < J) in block (J, I)
   double* Xd = Ts + NB * LD;        // [4][32][33]  diagonal blocks of X
   double* Ws = Xd + 4 * 32 * 33;    // [3][32][33]  right-hand sides of the current phase
-  const int j = j0 + blockIdx.x * NB;
+  double* rdiag = Ws + 3 * 32 * 33; // [NB]         reciprocals of U's diagonal
+  const int j = j0 + bx * NB;
   const int nb = min(NB, n - j);
-  const double* a = A + (int64_t)blockIdx.y * sA + (int64_t)j * lda + j;
+  const double* a = A + (int64_t)by * sA + (int64_t)j * lda + j;
   for (int idx = threadIdx.x; idx < NB * NB; idx += TRI_THREADS) {  // ragged blocks are padded with the identity
     const int rr = idx / NB, cc = idx - rr * NB;
     double v = (rr == cc) ? 1.0 : 0.0;
@@ -1031,20 +1064,21 @@ __global__ void __launch_bounds__(TRI_THREADS) trtri_upper_kernel(const double* 
     Ts[rr * LD + cc] = v;
   }
   __syncthreads();
-  // ---- d = 0 ----
+  if (threadIdx.x < NB) rdiag[threadIdx.x] = 1.0 / Ts[threadIdx.x * LD + threadIdx.x];
+  __syncthreads();
+  // ---- d = 0: the diagonal blocks, one column per lane, the column in registers ----
   if (threadIdx.x < 128) {
     const int blk = threadIdx.x >> 5, c = threadIdx.x & 31, base = blk * 32;
-    double* x = Xd + blk * 32 * 33;
-    const double* T = Ts + base * LD + base;
-    for (int r = c + 1; r < 32; ++r) x[r * 33 + c] = 0.0;
-    x[c * 33 + c] = 1.0 / T[c * LD + c];
-    for (int r = c - 1; r >= 0; --r) {
-      double s = 0.0;
-      for (int t = r + 1; t <= c; ++t) s = fma(T[r * LD + t], x[t * 33 + c], s);
-      x[r * 33 + c] = -s / T[r * LD + r];
-    }
+    double x[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) x[r] = (r == c) ? 1.0 : 0.0;
+    backsub32(Ts + base * LD + base, LD, rdiag + base, x, c);
+    double* xd = Xd + blk * 32 * 33 + c;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) xd[r * 33] = x[r];
   }
   __syncthreads();
+#pragma unroll 1  // one copy of the unrolled substitution below (three would push its register array into local memory)
   for (int d = 1; d < 4; ++d) {
     const int nblk = 4 - d;
     for (int idx = threadIdx.x; idx < nblk * 1024; idx += TRI_THREADS) {
@@ -1062,18 +1096,18 @@ __global__ void __launch_bounds__(TRI_THREADS) trtri_upper_kernel(const double* 
     __syncthreads();
     if (threadIdx.x < nblk * 32) {
       const int I = threadIdx.x >> 5, c = threadIdx.x & 31, J = I + d;
-      const double* T = Ts + (32 * I) * LD + 32 * I;   // U[I][I]
-      double* x = Ts + (32 * J) * LD + 32 * I + c;     // X[I][J][t][c] at x[t * LD]
       const double* w = Ws + I * 32 * 33 + c;
-      for (int r = 31; r >= 0; --r) {
-        double s = w[r * 33];
-        for (int t = r + 1; t < 32; ++t) s = fma(T[r * LD + t], x[t * LD], s);
-        x[r * LD] = -s / T[r * LD + r];
-      }
+      double x[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) x[r] = -w[r * 33];
+      backsub32(Ts + (32 * I) * LD + 32 * I, LD, rdiag + 32 * I, x, 31);
+      double* xo = Ts + (32 * J) * LD + 32 * I + c;  // X[I][J][t][c] at xo[t * LD]
+#pragma unroll
+      for (int r = 0; r < 32; ++r) xo[r * LD] = x[r];
     }
     __syncthreads();
   }
-  double* w = W + (int64_t)blockIdx.y * sW + (int64_t)(j / NB) * NB * NB;
+  double* w = W + (int64_t)by * sW + (int64_t)(j / NB) * NB * NB;
   for (int idx = threadIdx.x; idx < nb * nb; idx += TRI_THREADS) {
     const int rr = idx / nb, cc = idx - rr * nb;
     const int I = rr >> 5, J = cc >> 5;
@@ -1083,7 +1117,20 @@ __global__ void __launch_bounds__(TRI_THREADS) trtri_upper_kernel(const double* 
     w[rr * NB + cc] = v;
   }
 }
-constexpr size_t TRTRI_UPPER_SMEM = sizeof(double) * (NB * (NB + 1) + 7 * 32 * 33);
+__global__ void __launch_bounds__(TRI_THREADS) trtri_upper_kernel(const double* A, int64_t lda, int64_t sA, int j0, int n,
+                                                                  double* W, int64_t sW) {
+  trtri_upper_body(A, lda, sA, j0, n, W, sW, blockIdx.x, blockIdx.y);
+}
+constexpr size_t TRTRI_UPPER_SMEM = sizeof(double) * (NB * (NB + 1) + 7 * 32 * 33 + NB);
+
+constexpr size_t TRTRI_SMEM = sizeof(double) * (NB * (NB + 1) + 64 * 65 + 4 * 32 * 33);
+constexpr size_t TRTRI_PAIR_SMEM = TRTRI_SMEM > TRTRI_UPPER_SMEM ? TRTRI_SMEM : TRTRI_UPPER_SMEM;
+// both inverses of ONE diagonal block (at A[j,j]) in one launch: CTA x = 0 the unit-lower one, x = 1 the upper one
+__global__ void __launch_bounds__(TRI_THREADS) trtri_pair_kernel(const double* A, int64_t lda, int64_t sA, int j, int n,
+                                                                 double* Wl, double* Wu, int64_t sW) {
+  if (blockIdx.x == 0) trtri_lower_body(A, lda, sA, j, n, Wl, sW, 0, blockIdx.y);
+  else trtri_upper_body(A, lda, sA, j, n, Wu, sW, 0, blockIdx.y);
+}
 
 // dst[b][r][c] = src[b][r][c] for an (rows x cols) block
 __global__ void copy_block_kernel(double* dst, int64_t ldd, int64_t sD, const double* src, int64_t lds, int64_t sS,
@@ -1094,7 +1141,6 @@ __global__ void copy_block_kernel(double* dst, int64_t ldd, int64_t sD, const do
   dst[(int64_t)blockIdx.y * sD + (int64_t)r * ldd + c] = src[(int64_t)blockIdx.y * sS + (int64_t)r * lds + c];
 }
 
-constexpr size_t TRTRI_SMEM = sizeof(double) * (NB * (NB + 1) + 64 * 65 + 4 * 32 * 33);
 
 struct LuWorkspace {
   int* ipiv;
@@ -1214,6 +1260,173 @@ int laswp(cudaStream_t st, int batch, double* A, int64_t lda, int64_t sA, int c0
   return 0;
 }
 
+// LU with partial pivoting of the jb x jb diagonal block at A[j,j] of every matrix (jb <= NB), the pivot search
+// restricted to the block: one CTA of 128 threads per matrix, thread r owns row r.  The row's entries in the current
+// 32-column panel live in REGISTERS (the column loop is fully unrolled, so every index is static): a column step is
+// one shuffle reduction, two barriers of four warps and up to 31 FMAs per thread — about 300 cycles instead of the
+// ~2 us the shared-memory panel of blockcol_kernel<false> needs on a 128-row block.  The block itself sits in shared
+// memory for the (rare) row interchanges, U12 = L11^-1 A12 and the trailing update, whose L21 operand is the register
+// panel just computed.
+constexpr int DB_THREADS = 128;
+constexpr int DB_LD = NB + 1;
+constexpr int DB_UW = NB - IB;
+constexpr size_t DB_SMEM = sizeof(double) * ((size_t)NB * DB_LD + 1 + 2 * (IB + 1) + (size_t)IB * DB_UW);
+// PIVOT = false: the diagonal is taken as the pivot without looking (no reduction, one barrier per column, the
+// owner of the pivot row hands out the reciprocal); a multiplier above 1 in magnitude sets info = -2 like the check
+// on the rows below the block (spec_commit_kernel), so the result is accepted only where partial pivoting would have
+// made the same choice.
+template <bool PIVOT>
+__global__ void __launch_bounds__(DB_THREADS) diagblk_kernel(double* __restrict__ A, int64_t lda, int64_t sA, int n, int j,
+                                                             int jb, int* __restrict__ ipiv_all, int* __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int LD = DB_LD;
+  double* T = sm;                                  // [NB][LD]
+  double* U = T + (((size_t)NB * LD + 1) & ~(size_t)1);  // [IB][DB_UW], 16-byte aligned
+  double* prow = U + IB * DB_UW;                   // [2][IB + 1]: pivot row of the panel (+ the reciprocal of the pivot)
+  __shared__ double s_val[DB_THREADS / 32];
+  __shared__ int s_row[DB_THREADS / 32];
+  const int r = threadIdx.x, lane = r & 31, warp = r >> 5, mat = blockIdx.x;
+  double* a = A + (int64_t)mat * sA + (int64_t)j * lda + j;
+  int* ipiv = ipiv_all + (int64_t)mat * n + j;
+  const bool live = r < jb;
+  bool bad = false;  // PIVOT = false: a multiplier larger than 1 was seen
+  for (int rr = 0; rr < jb; ++rr)
+    if (live) T[rr * LD + r] = a[(int64_t)rr * lda + r];
+  __syncthreads();
+  for (int c0 = 0; c0 < jb; c0 += IB) {
+    const int pw = min(IB, jb - c0);  // panel width
+    double x[IB];
+#pragma unroll
+    for (int k = 0; k < IB; ++k) x[k] = (live && k < pw) ? T[r * LD + c0 + k] : 0.0;
+#pragma unroll
+    for (int c = 0; c < IB; ++c) {
+      if (c < pw) {  // uniform
+        const int col = c0 + c;
+        if (!PIVOT) {
+          double* pr = prow + (c & 1) * (IB + 1);
+          if (r == col) {
+#pragma unroll
+            for (int k = 0; k < IB; ++k) pr[k] = x[k];
+            pr[IB] = 1.0 / x[c];
+          }
+          if (r == 0) ipiv[col] = j + col;
+          __syncthreads();
+          const double piv = pr[c];
+          if (piv == 0.0) {
+            if (r == 0 && info[mat] == 0) info[mat] = j + col + 1;
+          } else if (live && r > col) {
+            const double l = x[c] * pr[IB];
+            if (!(fabs(l) <= 1.0 + 1e-8)) bad = true;
+            x[c] = l;
+#pragma unroll
+            for (int k = c + 1; k < IB; ++k) x[k] = fma(-l, pr[k], x[k]);
+          }
+          continue;
+        }
+        // ---- arg-max of |a[r][col]| over rows >= col (lowest row wins ties) ----
+        double v = (live && r >= col) ? fabs(x[c]) : -1.0;
+        int vr = r;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+          const int orr = __shfl_xor_sync(0xffffffffu, vr, o);
+          if (ov > v || (ov == v && orr < vr)) { v = ov; vr = orr; }
+        }
+        if (lane == 0) { s_val[warp] = v; s_row[warp] = vr; }
+        __syncthreads();
+        v = s_val[0]; vr = s_row[0];
+#pragma unroll
+        for (int w = 1; w < DB_THREADS / 32; ++w) {
+          const double ov = s_val[w];
+          const int orr = s_row[w];
+          if (ov > v || (ov == v && orr < vr)) { v = ov; vr = orr; }
+        }
+        const int p = (v >= 0.0) ? vr : col;
+        if (p != col) {  // uniform: rows col and p change places (registers of the two owners + the block in smem)
+          if (r == col || r == p) {
+#pragma unroll
+            for (int k = 0; k < IB; ++k)
+              if (k < pw) T[r * LD + c0 + k] = x[k];
+          }
+          __syncthreads();
+          if (live) { const double t1 = T[col * LD + r], t2 = T[p * LD + r]; T[col * LD + r] = t2; T[p * LD + r] = t1; }
+          __syncthreads();
+          if (r == col || r == p) {
+#pragma unroll
+            for (int k = 0; k < IB; ++k)
+              if (k < pw) x[k] = T[r * LD + c0 + k];
+          }
+        }
+        if (r == 0) ipiv[col] = j + p;
+        double* pr = prow + (c & 1) * (IB + 1);  // double-buffered: the previous column's readers may still be at work
+        if (r == col) {
+#pragma unroll
+          for (int k = 0; k < IB; ++k) pr[k] = x[k];
+        }
+        __syncthreads();
+        const double piv = pr[c];
+        if (piv == 0.0) {
+          if (r == 0 && info[mat] == 0) info[mat] = j + col + 1;
+        } else if (live && r > col) {
+          const double l = x[c] / piv;
+          x[c] = l;
+#pragma unroll
+          for (int k = c + 1; k < IB; ++k) x[k] = fma(-l, pr[k], x[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < IB; ++k)
+      if (live && k < pw) T[r * LD + c0 + k] = x[k];
+    __syncthreads();
+    const int pe = c0 + pw, W = jb - pe;
+    if (W > 0) {  // pw == IB here
+      // ---- U12 = L11^-1 A12: one column per thread, forward substitution in registers ----
+      if (r < W) {
+        double y[IB];
+#pragma unroll
+        for (int i = 0; i < IB; ++i) y[i] = T[(c0 + i) * LD + pe + r];
+#pragma unroll
+        for (int i = 1; i < IB; ++i) {
+          double s = y[i];
+#pragma unroll
+          for (int t = 0; t < i; ++t) s = fma(-T[(c0 + i) * LD + c0 + t], y[t], s);
+          y[i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < IB; ++i) { T[(c0 + i) * LD + pe + r] = y[i]; U[i * DB_UW + r] = y[i]; }
+      }
+      __syncthreads();
+      // ---- A22 -= L21 U12 on rows >= pe: this thread's row of L21 is the register panel ----
+      if (live && r >= pe) {
+        double* trow = T + r * LD + pe;
+        int w = 0;
+        for (; w + 1 < W; w += 2) {
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int k = 0; k < IB; ++k) {
+            const double2 u = *reinterpret_cast<const double2*>(U + k * DB_UW + w);
+            s0 = fma(x[k], u.x, s0);
+            s1 = fma(x[k], u.y, s1);
+          }
+          trow[w] -= s0;
+          trow[w + 1] -= s1;
+        }
+        if (w < W) {
+          double s0 = 0.0;
+#pragma unroll
+          for (int k = 0; k < IB; ++k) s0 = fma(x[k], U[k * DB_UW + w], s0);
+          trow[w] -= s0;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int rr = 0; rr < jb; ++rr)
+    if (live) a[(int64_t)rr * lda + r] = T[rr * LD + r];
+  if (!PIVOT && __syncthreads_or(bad) && r == 0) atomicCAS(&info[mat], 0, -2);
+}
+
 // opt the large-shared-memory kernels in, once per device
 int configure_lu_kernels() {
   DeviceState* ds = nullptr;
@@ -1227,6 +1440,9 @@ int configure_lu_kernels() {
     HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(trtri_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(trtri_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_UPPER_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(trtri_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_PAIR_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(diagblk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
+    HPS_CUDA(cudaFuncSetAttribute(diagblk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(laswp_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LASWP_SMEM));
   ds->lu_configured.store(true, std::memory_order_release);
   return 0;
@@ -1370,17 +1586,30 @@ std::atomic<int> g_lu_speculate{[] { const char* e = std::getenv("HPS_LU_SPEC");
 int factor_block_column_spec(cudaStream_t st, int batch, int n, const Mat& A, int j, int jb, LuWorkspace& w, int* info) {
   const int nblk = (n + NB - 1) / NB;
   const int64_t sW = (int64_t)nblk * NB * NB;
-  BcArgs a;
-  a.A = A.p; a.lda = A.ld; a.sA = A.stride; a.n = n; a.j = j; a.jb = jb; a.G = 1; a.rpc = jb;
-  a.ipiv = w.ipiv; a.info = info; a.scratch = w.bc_scratch; a.scratch_stride = w.bc_stride; a.Gcap = w.bc_Gcap;
-  a.rows_cap = jb;
+  static const bool smem_panel = [] { const char* e = std::getenv("HPS_DIAGBLK"); return e && e[0] == 's'; }();  // A/B switch
+  static const bool pivot_in_block = [] { const char* e = std::getenv("HPS_DIAGBLK"); return e && e[0] == 'p'; }();
   prof_begin(PROF_PANEL, st, (double)batch * jb * jb);
-  blockcol_kernel<false><<<dim3(1, batch), BC_THREADS, bc_smem_bytes(jb), st>>>(a);
+  if (smem_panel) {
+    BcArgs a;
+    a.A = A.p; a.lda = A.ld; a.sA = A.stride; a.n = n; a.j = j; a.jb = jb; a.G = 1; a.rpc = jb;
+    a.ipiv = w.ipiv; a.info = info; a.scratch = w.bc_scratch; a.scratch_stride = w.bc_stride; a.Gcap = w.bc_Gcap;
+    a.rows_cap = jb;
+    blockcol_kernel<false><<<dim3(1, batch), BC_THREADS, bc_smem_bytes(jb), st>>>(a);
+  } else {
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+      const int nb = std::min(65535, batch - b0);
+      if (pivot_in_block)
+        diagblk_kernel<true><<<nb, DB_THREADS, DB_SMEM, st>>>(A.p + (int64_t)b0 * A.stride, A.ld, A.stride, n, j, jb,
+                                                              w.ipiv + (int64_t)b0 * n, info + b0);
+      else
+        diagblk_kernel<false><<<nb, DB_THREADS, DB_SMEM, st>>>(A.p + (int64_t)b0 * A.stride, A.ld, A.stride, n, j, jb,
+                                                               w.ipiv + (int64_t)b0 * n, info + b0);
+    }
+  }
   prof_end(PROF_PANEL, st);
-  HPS_LAUNCH_CHECK("blockcol_kernel<diagonal block>");
+  HPS_LAUNCH_CHECK("diagonal block LU");
   prof_begin(PROF_TRTRI, st, (double)batch * NB * NB * NB * 2 / 3);
-  trtri_lower_kernel<<<dim3(1, batch), TRI_THREADS, TRTRI_SMEM, st>>>(A.p, A.ld, A.stride, j, n, w.Linv, sW);
-  trtri_upper_kernel<<<dim3(1, batch), TRI_THREADS, TRTRI_UPPER_SMEM, st>>>(A.p, A.ld, A.stride, j, n, w.Uinv, sW);
+  trtri_pair_kernel<<<dim3(2, batch), TRI_THREADS, TRTRI_PAIR_SMEM, st>>>(A.p, A.ld, A.stride, j, n, w.Linv, w.Uinv, sW);
   prof_end(PROF_TRTRI, st);
   HPS_LAUNCH_CHECK("trtri kernels");
   const int rows = n - (j + jb);
