@@ -304,7 +304,10 @@ def distributed_lu_solve(_lib, dev, D, rhs, rank: int, world: int, group=None) -
         comm = P2PComm.get(_lib, dev, rank, world, group)
         comm.ensure(comm.lu_segment_bytes(n))
         _copy_into_segment(comm.matrix_ptr(n), D)
-        return p2p_lu_solve(_lib, dev, comm, n, rhs, group)
+        # a general matrix (the adaptive root's interface system): the right-hand sides are overwritten in place, so a
+        # failed speculation could not be repeated — factor with full partial pivoting from the start
+        with _lib.speculation(False):
+            return p2p_lu_solve(_lib, dev, comm, n, rhs, group)
     NB = 128
     nblk = (n + NB - 1) // NB
     need = ctypes.c_size_t()

@@ -251,6 +251,23 @@ def check_info(info: torch.Tensor, what: str) -> None:
         raise AssumptionViolated(what)
 
 
+_SPEC_DEFAULT = 0 if os.environ.get("HPS_LU_SPEC", "1") == "0" else 1
+
+
+class speculation:
+    """Context manager: switch the library's speculative (no-pivot) block columns on or off for the calls inside."""
+
+    def __init__(self, on: bool):
+        self.on = 1 if on else 0
+
+    def __enter__(self):
+        load().hps_lu_set_speculative(self.on)
+
+    def __exit__(self, *exc):
+        load().hps_lu_set_speculative(_SPEC_DEFAULT)
+        return False
+
+
 def with_pivoting_fallback(fn):
     """Run ``fn()``; if the library reports that its no-pivoting speculation failed, run it again with the
     speculation switched off (``hps_lu_set_speculative``)."""
@@ -262,4 +279,4 @@ def with_pivoting_fallback(fn):
         try:
             return fn()
         finally:
-            lib.hps_lu_set_speculative(0 if os.environ.get("HPS_LU_SPEC", "1") == "0" else 1)
+            lib.hps_lu_set_speculative(_SPEC_DEFAULT)
