@@ -196,12 +196,15 @@ class CudaAdaptiveOps:
         need = ctypes.c_size_t()
         self._lib.check(self.lib.hps_merge_adaptive_workspace(root_plan.n_int, root_plan.n_ext, 0, ctypes.byref(need)), "ws query")
         ws = self._lib.WORKSPACE.get(need.value, self.dev)
-        rc = self.lib.hps_merge_adaptive(self._lib.stream_ptr(), npp, n_src, len(Ts), ptrs(Ts), ptrs(hs), lds,
-                                         root_plan.int_tbl.shape[0], off["int"], root_plan.ext_tbl.shape[0], off["ext"],
-                                         S.data_ptr(), g.data_ptr(), None, None, 0, 0, None, e0, e1 - e0, ws.data_ptr(),
-                                         ws.numel(), info.data_ptr())
-        self._lib.check(rc, "hps_merge_adaptive (root columns)")
-        self._lib.check_info(info, "root merge")
+        def run():
+            rc = self.lib.hps_merge_adaptive(self._lib.stream_ptr(), npp, n_src, len(Ts), ptrs(Ts), ptrs(hs), lds,
+                                             root_plan.int_tbl.shape[0], off["int"], root_plan.ext_tbl.shape[0], off["ext"],
+                                             S.data_ptr(), g.data_ptr(), None, None, 0, 0, None, e0, e1 - e0, ws.data_ptr(),
+                                             ws.numel(), info.data_ptr())
+            self._lib.check(rc, "hps_merge_adaptive (root columns)")
+            self._lib.check_info(info, "root merge")
+
+        self._lib.with_pivoting_fallback(run)  # the call only reads the children's operators: repeatable
         return S, g
 
     def matvec(self, S, x):

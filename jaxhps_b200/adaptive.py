@@ -156,6 +156,12 @@ def _ptr_array(tensors) -> ctypes.Array:
 
 
 def _merge_adaptive(pde_problem, T_arr, h_arr, device, host_device, return_T: bool):
+    """The whole bottom-up merge; repeated with full partial pivoting if one of the interface systems turned out to
+    need interchanges below a diagonal block (the stage only reads the leaf operators, so a repeat starts clean)."""
+    return _lib.with_pivoting_fallback(lambda: _merge_adaptive_once(pde_problem, T_arr, h_arr, device, host_device, return_T))
+
+
+def _merge_adaptive_once(pde_problem, T_arr, h_arr, device, host_device, return_T: bool):
     dev = _lib.require_cuda(device)
     lib = _lib.load()
     dom = pde_problem.domain

@@ -278,7 +278,9 @@ int merge_adaptive(cudaStream_t st, int npp, int n_src, int n_child, const doubl
     HPS_LAUNCH_CHECK("adaptive_gather_rhs_kernel");
   }
   RhsDesc rhs[2] = {{S, n_ext_loc, 0, n_ext_loc}, {gt, n_src, 0, n_src}};
-  HPS_TRY(lu_solve(st, 1, n_int, D, n_int, 0, 2, rhs, lu_ws, lu_ws_bytes, info));
+  // interface systems of non-uniform merges: the coarsening operators can make rows change places locally, so the
+  // speculative block columns keep partial pivoting inside each diagonal block (info = -2 if that was not enough)
+  HPS_TRY(lu_solve(st, 1, n_int, D, n_int, 0, 2, rhs, lu_ws, lu_ws_bytes, info, LU_NO_PIVOT_EXPECTED | LU_PIVOT_IN_BLOCK));
   if (!want_T) return 0;
   // T = A + B S, h = h_ext + B g~
   if (dense_B) {

@@ -953,7 +953,6 @@ __device__ __forceinline__ void trtri_lower_body(const double* A, int64_t lda, i
   constexpr int LD = TRI_LD;
   double* Ts = sm;                 // [NB][LD]   the triangle, inverted in place
   double* Ws = sm + NB * LD;       // [64][65]   product scratch
-  double* Xs = Ws + 64 * 65;       // [4][32][33] columns of the 32x32 diagonal inverses
   const int j = j0 + bx * NB;      // diagonal block handled by this CTA
   const int nb = min(NB, n - j);
   const double* a = A + (int64_t)by * sA + (int64_t)j * lda + j;
@@ -1583,11 +1582,13 @@ std::atomic<int> g_lu_speculate{[] { const char* e = std::getenv("HPS_LU_SPEC");
 //   4. commit + verification that every multiplier is <= 1 in magnitude — exactly the condition under which
 //      partial pivoting over the whole column would have chosen the same pivots.  Otherwise info = -2 and the
 //      caller repeats the operation with hps_lu_set_speculative(0).
-int factor_block_column_spec(cudaStream_t st, int batch, int n, const Mat& A, int j, int jb, LuWorkspace& w, int* info) {
+int factor_block_column_spec(cudaStream_t st, int batch, int n, const Mat& A, int j, int jb, LuWorkspace& w, int* info,
+                             bool in_block_pivoting) {
   const int nblk = (n + NB - 1) / NB;
   const int64_t sW = (int64_t)nblk * NB * NB;
   static const bool smem_panel = [] { const char* e = std::getenv("HPS_DIAGBLK"); return e && e[0] == 's'; }();  // A/B switch
-  static const bool pivot_in_block = [] { const char* e = std::getenv("HPS_DIAGBLK"); return e && e[0] == 'p'; }();
+  static const bool force_pivot = [] { const char* e = std::getenv("HPS_DIAGBLK"); return e && e[0] == 'p'; }();
+  const bool pivot_in_block = in_block_pivoting || force_pivot;
   prof_begin(PROF_PANEL, st, (double)batch * jb * jb);
   if (smem_panel) {
     BcArgs a;
@@ -1627,9 +1628,11 @@ int factor_block_column_spec(cudaStream_t st, int batch, int n, const Mat& A, in
 
 // Factor the outer block column j (inner IB panels + updates inside the block column) and invert
 // its unit-lower diagonal block into Linv[j/NB].  Touches columns [j, j+jb) only.
+// speculate: 0 = pivoted kernels, 1 = speculative with the diagonal taken as pivot, 2 = speculative with partial
+// pivoting inside the diagonal block (matrices that interchange rows locally, e.g. the adaptive interface systems)
 int factor_block_column(cudaStream_t st, int batch, int n, const Mat& A, int j, int jb, LuWorkspace& w, int* info,
-                        bool speculate = false) {
-  if (speculate) return factor_block_column_spec(st, batch, n, A, j, jb, w, info);
+                        int speculate = 0) {
+  if (speculate) return factor_block_column_spec(st, batch, n, A, j, jb, w, info, speculate == 2);
   bool done = false;
   HPS_TRY(launch_blockcol(st, batch, n, A.p, A.ld, A.stride, j, jb, w, info, done));
   for (int jj = j; !done && jj < j + jb; jj += IB) {
@@ -1761,7 +1764,8 @@ size_t lu_workspace_bytes(int batch, int n) {
 int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t sA, int n_rhs, const RhsDesc* rhs,
              void* ws, size_t ws_bytes, int* info, int flags) {
   static const bool force_spec = [] { const char* e = std::getenv("HPS_LU_FORCE_SPEC"); return e && e[0] == '1'; }();  // tools/bench_lu.py
-  const bool speculate = ((flags & LU_NO_PIVOT_EXPECTED) || force_spec) && g_lu_speculate.load(std::memory_order_relaxed) != 0;
+  const bool spec_on = ((flags & LU_NO_PIVOT_EXPECTED) || force_spec) && g_lu_speculate.load(std::memory_order_relaxed) != 0;
+  const int speculate = spec_on ? ((flags & LU_PIVOT_IN_BLOCK) ? 2 : 1) : 0;
   if (batch <= 0 || n <= 0) return 0;
   if (batch > 65535) return fail_arg(2, "lu_solve: batch > 65535");
   Arena ar(ws, ws_bytes);
@@ -2298,7 +2302,7 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
   HPS_CUDA(cudaEventRecord(aux->fork, s0));
   HPS_CUDA(cudaStreamWaitEvent(s1, aux->fork, 0));
 
-  const bool speculate = g_lu_speculate.load(std::memory_order_relaxed) != 0;  // the root D of a merge: see lu_solve
+  const int speculate = g_lu_speculate.load(std::memory_order_relaxed) != 0 ? 1 : 0;  // the root D of a merge: see lu_solve
   bool structured = false;
   for (int k = 0; k < n_rhs; ++k) structured |= rhs[k].n_seg > 0;
   {
