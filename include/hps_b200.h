@@ -62,6 +62,15 @@ int hps_dgemm_strided_batched(void* stream, int M, int N, int K, double alpha,
                               const double* B, int64_t ldb, int64_t sB, double beta,
                               double* C, int64_t ldc, int64_t sC, int batch);
 
+/* C[b] (K x N) = alpha * A[b]^T (A: M x K) * X[b] (M x N) + beta * C[b] for narrow N (bandwidth kernel, a thread per
+ * column of A).  is_complex: complex128 interleaved, plain transpose (no conjugation); leading dimensions and strides
+ * in elements.  The transposed mat-vecs of the adjoint passes (jaxhps_b200/adjoint.py: S^T g, Y^T w, Phi^T v), which
+ * the reference obtains from jax.vjp through its einsum / matmul calls (examples/inverse_scattering_utils.py:110-171). */
+int hps_gemv_t_strided_batched(void* stream, int M, int K, int N, double alpha,
+                               const double* A, int64_t lda, int64_t sA,
+                               const double* X, int64_t ldx, int64_t sX, double beta,
+                               double* C, int64_t ldc, int64_t sC, int batch, int is_complex);
+
 /* Batched LU with partial pivoting of A[b] (n x n) followed by the in-place solve
  * rhs_k[b] := A[b]^-1 rhs_k[b] for up to 4 right-hand-side matrices (n x ncols[k]).
  * A is overwritten (U in the upper triangle).  Replaces the `jnp.linalg.inv` + matmul

@@ -12,6 +12,8 @@ stage functions        ``local_solve``, ``merge``, ``down_pass``, ``up_pass``, `
                        names and signatures; bodies are calls into ``libhps_b200.so`` (``_lib``)
 drivers                ``build_solver`` / ``solve`` (``_build_solver``, ``_solve``), subtree recomputation
                        (``_subtree_recomp``), multi-GPU sharding (``_dist``, ``_dist_adaptive``)
+derivatives            ``adjoint`` — ``solve_jvp`` / ``solve_vjp`` of the 2D uniform solve (what the reference gets from
+                       ``jax.jvp`` / ``jax.vjp``), ``scattering`` — ItI -> DtN conversion and the BIE coupling solve
 =====================  ==========================================================================
 
 There is no CPU fallback: every stage raises ``_lib.HpsLibraryError`` without CUDA or without the library.

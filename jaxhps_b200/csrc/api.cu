@@ -159,6 +159,13 @@ int hps_dgemm_strided_batched(void* stream, int M, int N, int K, double alpha, c
   return dgemm(static_cast<cudaStream_t>(stream), M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
 }
 
+int hps_gemv_t_strided_batched(void* stream, int M, int K, int N, double alpha, const double* A, int64_t lda, int64_t sA,
+                               const double* X, int64_t ldx, int64_t sX, double beta, double* C, int64_t ldc, int64_t sC,
+                               int batch, int is_complex) {
+  if (M < 0 || N < 0 || K < 0) return fail_arg(2, "negative dimension");
+  return gemv_t(static_cast<cudaStream_t>(stream), M, K, N, alpha, A, lda, sA, X, ldx, sX, beta, C, ldc, sC, batch, is_complex);
+}
+
 int hps_lu_solve_workspace(int batch, int n, size_t* bytes) {
   if (!bytes) return fail_arg(3, "null output pointer");
   *bytes = lu_workspace_bytes(batch, n);

@@ -101,6 +101,11 @@ int dgemm_affine(cudaStream_t st, int M, int N, int K, const double* A, int64_t 
                  int64_t ldb, int64_t sB, const double* Cin, int64_t ldcin, int64_t sCin, double* C, int64_t ldc,
                  int64_t sC, int batch);
 
+// C[b] (K x N) = alpha A[b]^T X[b] + beta C[b] for narrow N; complex128 interleaved when is_complex (plain transpose;
+// leading dimensions and strides in elements)
+int gemv_t(cudaStream_t st, int M, int K, int N, double alpha, const double* A, int64_t lda, int64_t sA, const double* X,
+           int64_t ldx, int64_t sX, double beta, double* C, int64_t ldc, int64_t sC, int batch, int is_complex);
+
 // A block of right-hand-side columns.  Optional structure (n_seg > 0): the columns form n_seg segments of seg_cols
 // columns each, and rows [0, seg_first_row[k]) of segment k are EXACTLY zero on entry, seg_first_row non-decreasing.
 // (The -C of an HPS merge in the reference's region order: a child's exterior columns are non-zero only on that

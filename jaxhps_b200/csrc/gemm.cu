@@ -106,6 +106,70 @@ __global__ void __launch_bounds__(256) gemv_kernel(int M, int K, double alpha, c
   }
 }
 
+// C[b] (K x N) = alpha * A[b]^T * X[b] + beta * C[b] for narrow N (adjoint passes: S^T g, Y^T w, Phi^T v): A is M x K
+// row-major, so a thread per COLUMN k reads coalesced rows; X[b] (M x N) is broadcast.  E = double or double2
+// (complex128, plain transpose — no conjugation).  grid: (column tiles, batch, row splits); with more than one row
+// split the partial sums are added atomically onto a C that gemv_t_scale_kernel has already scaled by beta.
+template <typename E>
+__device__ __forceinline__ E e_zero();
+template <>
+__device__ __forceinline__ double e_zero<double>() { return 0.0; }
+template <>
+__device__ __forceinline__ double2 e_zero<double2>() { return make_double2(0.0, 0.0); }
+__device__ __forceinline__ double e_fma(double a, double x, double acc) { return fma(a, x, acc); }
+__device__ __forceinline__ double2 e_fma(double2 a, double2 x, double2 acc) {
+  acc.x = fma(a.x, x.x, fma(-a.y, x.y, acc.x));
+  acc.y = fma(a.x, x.y, fma(a.y, x.x, acc.y));
+  return acc;
+}
+__device__ __forceinline__ double e_scale(double s, double a) { return s * a; }
+__device__ __forceinline__ double2 e_scale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+__device__ __forceinline__ double e_add(double a, double b) { return a + b; }
+__device__ __forceinline__ double2 e_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ void e_atomic_add(double* p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void e_atomic_add(double2* p, double2 v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
+
+constexpr int GT_NMAX = 8;
+template <typename E>
+__global__ void __launch_bounds__(128) gemv_t_kernel(int M, int K, int N, double alpha, const E* __restrict__ A, int64_t lda,
+                                                     int64_t sA, const E* __restrict__ X, int64_t ldx, int64_t sX, double beta,
+                                                     E* __restrict__ C, int64_t ldc, int64_t sC, int rows_per_split) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t b = blockIdx.y;
+  const int m0 = blockIdx.z * rows_per_split, m1 = min(M, m0 + rows_per_split);
+  if (k >= K) return;
+  const E* a = A + b * sA + k;
+  const E* x = X + b * sX;
+  E acc[GT_NMAX];
+#pragma unroll
+  for (int n = 0; n < GT_NMAX; ++n) acc[n] = e_zero<E>();
+  for (int m = m0; m < m1; ++m) {
+    const E av = a[(int64_t)m * lda];
+#pragma unroll
+    for (int n = 0; n < GT_NMAX; ++n)
+      if (n < N) acc[n] = e_fma(av, x[(int64_t)m * ldx + n], acc[n]);
+  }
+  E* c = C + b * sC + (int64_t)k * ldc;
+  if (gridDim.z == 1) {
+#pragma unroll
+    for (int n = 0; n < GT_NMAX; ++n)
+      if (n < N) c[n] = (beta != 0.0) ? e_add(e_scale(alpha, acc[n]), e_scale(beta, c[n])) : e_scale(alpha, acc[n]);
+  } else {
+#pragma unroll
+    for (int n = 0; n < GT_NMAX; ++n)
+      if (n < N) e_atomic_add(&c[n], e_scale(alpha, acc[n]));
+  }
+}
+template <typename E>
+__global__ void gemv_t_scale_kernel(int K, int N, double beta, E* __restrict__ C, int64_t ldc, int64_t sC) {
+  const int64_t total = (int64_t)K * N;
+  E* c = C + (int64_t)blockIdx.y * sC;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = e / N, n = e - k * N;
+    c[k * ldc + n] = (beta != 0.0) ? e_scale(beta, c[k * ldc + n]) : e_zero<E>();
+  }
+}
+
 inline bool vec_ok(const void* p, int64_t ld, int64_t stride) {
   return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 2 == 0) && (stride % 2 == 0);
 }
@@ -196,6 +260,46 @@ int dgemm(cudaStream_t st, int M, int N, int K, double alpha, const double* A, i
   prof_end(PROF_GEMM, st);
   HPS_LAUNCH_CHECK("gemm_kernel");
   return 0;
+}
+
+
+template <typename E>
+static int gemv_t_impl(cudaStream_t st, int M, int K, int N, double alpha, const E* A, int64_t lda, int64_t sA, const E* X,
+                       int64_t ldx, int64_t sX, double beta, E* C, int64_t ldc, int64_t sC, int batch) {
+  for (int n0 = 0; n0 < N; n0 += GT_NMAX) {
+    const int nn = std::min(GT_NMAX, N - n0);
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+      const int nb = std::min(65535, batch - b0);
+      const int tiles = (K + 127) / 128;
+      // few CTAs (the upper tree levels): split the rows so that every SM has work
+      int splits = 1;
+      if ((int64_t)tiles * nb < 296 && M >= 512) splits = (int)std::min<int64_t>((M + 255) / 256, 296 / ((int64_t)tiles * nb) + 1);
+      const int rps = (M + splits - 1) / splits;
+      const E* Ab = A + (int64_t)b0 * sA;
+      const E* Xb = X + (int64_t)b0 * sX + n0;
+      E* Cb = C + (int64_t)b0 * sC + n0;
+      if (splits > 1) {
+        gemv_t_scale_kernel<E><<<dim3((unsigned)std::min<int64_t>(((int64_t)K * nn + 255) / 256, 256), nb), 256, 0, st>>>(K, nn, beta, Cb, ldc, sC);
+      }
+      gemv_t_kernel<E><<<dim3(tiles, nb, splits), 128, 0, st>>>(M, K, nn, alpha, Ab, lda, sA, Xb, ldx, sX, beta, Cb, ldc, sC, rps);
+    }
+  }
+  HPS_LAUNCH_CHECK("gemv_t_kernel");
+  return 0;
+}
+
+int gemv_t(cudaStream_t st, int M, int K, int N, double alpha, const double* A, int64_t lda, int64_t sA, const double* X,
+           int64_t ldx, int64_t sX, double beta, double* C, int64_t ldc, int64_t sC, int batch, int is_complex) {
+  if (M <= 0 || K <= 0 || N <= 0 || batch <= 0) return 0;
+  prof_begin(PROF_SKINNY, st, (is_complex ? 16.0 : 8.0) * M * (double)K * batch);
+  int rc;
+  if (is_complex)
+    rc = gemv_t_impl<double2>(st, M, K, N, alpha, reinterpret_cast<const double2*>(A), lda, sA,
+                              reinterpret_cast<const double2*>(X), ldx, sX, beta, reinterpret_cast<double2*>(C), ldc, sC, batch);
+  else
+    rc = gemv_t_impl<double>(st, M, K, N, alpha, A, lda, sA, X, ldx, sX, beta, C, ldc, sC, batch);
+  prof_end(PROF_SKINNY, st);
+  return rc;
 }
 
 }  // namespace hps

@@ -1,0 +1,64 @@
+"""GPU: derivatives of the 2D uniform solve (`jaxhps_b200/adjoint.py`) against the oracle's closed-form
+tangent (itself checked against finite differences on the CPU, `tests/test_oracle_adjoint.py`), the dot-product
+identity between tangent and adjoint, and a dense adjoint assembled by the oracle on a tiny problem."""
+import numpy as np
+import pytest
+
+import jaxhps_b200 as hps
+from jaxhps_b200 import adjoint
+from oracle import hps_oracle_adjoint as oadj
+from test_oracle_adjoint import _problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max()
+
+
+@pytest.mark.parametrize("iti,p,q,L", [(False, 6, 4, 2), (True, 6, 4, 2), (False, 8, 6, 3), (True, 8, 6, 3)])
+def test_tangent_matches_the_oracle(iti, p, q, L):
+    pb, f, g, df, dg, dco = _problem(iti, p, q, L, 21)
+    built = oadj._build(hps.PDEProblem(pb.domain, **{k: getattr(pb, k) for k in dco}, **(dict(use_ItI=True, eta=pb.eta) if iti else {})))
+    uo = oadj._solve_built(built, f, g)
+    duo = oadj.jvp_identity(built, uo, df, dg, dco)
+    hps.build_solver(pb)
+    u, du = adjoint.solve_jvp(pb, g, f, d_source=df, d_boundary_data=dg, d_coefficients=dco)
+    assert u.shape == uo.shape and _rel(u, uo) < 1e-10
+    assert du.shape == duo.shape and _rel(du, duo) < 1e-9
+    # single-source calling convention (no trailing axis)
+    u1, du1 = adjoint.solve_jvp(pb, g[:, 0], f[..., 0], d_source=df[..., 0], d_boundary_data=dg[:, 0], d_coefficients=dco)
+    assert u1.shape == uo.shape[:2] and _rel(du1, duo[..., 0]) < 1e-9
+
+
+@pytest.mark.parametrize("iti,p,q,L,nsrc", [(False, 6, 4, 2, 1), (True, 6, 4, 2, 1), (False, 8, 6, 3, 2), (True, 8, 6, 3, 3)])
+def test_adjoint_and_tangent_satisfy_the_dot_product_identity(iti, p, q, L, nsrc):
+    pb, f, g, df, dg, dco = _problem(iti, p, q, L, 31)
+    rng = np.random.default_rng(7)
+    if nsrc > 1:
+        rep = lambda a: np.concatenate([a * (1 + 0.3 * s) for s in range(nsrc)], axis=-1)  # noqa: E731
+        f, g, df, dg = rep(f), rep(g), rep(df), rep(dg)
+    hps.build_solver(pb)
+    u, du = adjoint.solve_jvp(pb, g, f, d_source=df, d_boundary_data=dg, d_coefficients=dco)
+    w = rng.normal(size=u.shape) + (1j * rng.normal(size=u.shape) if iti else 0)
+    bars = adjoint.solve_vjp(pb, u, w)
+    lhs = np.sum(w * du)
+    rhs = np.sum(bars["source"] * df) + np.sum(bars["boundary_data"] * dg) + sum(np.sum(bars[k] * v) for k, v in dco.items())
+    assert abs(lhs - rhs) < 1e-10 * max(1.0, abs(lhs)), (lhs, rhs)
+    nb = pb.P.shape[0]
+    assert np.all(np.asarray(bars["source"])[:, :nb] == 0)  # the source enters through the interior rows only
+
+
+def test_adjoint_matches_the_dense_oracle_adjoint():
+    pb, f, g, df, dg, dco = _problem(False, 4, 2, 1, 41)
+    built = oadj._build(hps.PDEProblem(pb.domain, **{k: getattr(pb, k) for k in dco}))
+    uo = oadj._solve_built(built, f, g)
+    rng = np.random.default_rng(1)
+    w = rng.normal(size=uo.shape)
+    f_bar, g_bar, c_bar = oadj.vjp_dense(built, uo, w, ["I", "D_xx"])
+    hps.build_solver(pb)
+    u = hps.solve(pb, g, source=f)
+    bars = adjoint.solve_vjp(pb, u, w)
+    assert _rel(np.asarray(bars["source"])[..., 0], f_bar) < 1e-9
+    assert _rel(np.asarray(bars["boundary_data"])[..., 0], g_bar) < 1e-9
+    assert _rel(bars["I_coefficients"], c_bar["I"]) < 1e-9 and _rel(bars["D_xx_coefficients"], c_bar["D_xx"]) < 1e-9
