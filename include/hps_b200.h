@@ -398,6 +398,17 @@ int hps_down_adaptive(void* stream, int npp, int n_src, int n_int, int n_ext, co
                       const double* g_tilde, int n_child, double* const* g_child, int n_tbl, const int* tbl,
                       const double* L_refine, void* ws);
 
+/* Refinement check of the adaptive mesh generator for a whole queue of boxes (reference: the vmapped
+ * check_current_discretization_global_{linf,l2}_norm, _adaptive_discretization_3D.py:114-165, 466-503;
+ * _adaptive_discretization_2D.py:96-140).  f0 [n][n_c]: samples on each box's own Chebyshev cloud; f1 [n][n_f]: samples on
+ * the clouds of its 2^d children (n_f = 2^d n_c); LT [n_c][n_f]: the transposed refinement operator (L_4f1 / L_8f1);
+ * w [n][n_f]: quadrature weights of the children (NULL for the L_inf criterion).  Outputs per box: err_inf = max|L f0 - f1|,
+ * err_l2 = sum w (L f0 - f1)^2 (0 without w), ref_max = max|f1|; the accept / split decision and the running global norm
+ * stay with the caller (jaxhps_b200/_adaptive_discretization.py), as in the reference.  One DMMA GEMM + one reduction. */
+int hps_refine_check_workspace(int n, int n_f, size_t* bytes);
+int hps_refine_check(void* stream, int n, int n_c, int n_f, const double* f0, const double* f1, const double* LT,
+                     const double* w, double* err_inf, double* err_l2, double* ref_max, void* ws, size_t ws_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,7 +101,45 @@ def _ensure_box(root, depth: int, pos, q: int):
     return None
 
 
-def _generate(root, f_fn: Callable, tol: float, p: int, q: int, restrict_bool: bool, l2_norm: bool) -> None:
+class _DeviceCheck:
+    """The per-round refinement criterion on the GPU (``hps_refine_check``): the interpolation of the whole queue to
+    the children's clouds is one DMMA GEMM, the comparison one reduction per box; the samples of ``f`` travel host ->
+    device (``f`` is a host callable, as in the reference), three numbers per box come back."""
+
+    def __init__(self, refine_op: np.ndarray, device):
+        import torch
+
+        from . import _lib
+
+        self.torch, self._lib = torch, _lib
+        self.dev = _lib.require_cuda(device)
+        self.lib = _lib.load()
+        self.LT = _lib.to_device(np.ascontiguousarray(refine_op.T), self.dev)
+
+    def __call__(self, f0: np.ndarray, f1: np.ndarray, w):
+        import ctypes
+
+        torch, _lib = self.torch, self._lib
+        n, n_c = f0.shape
+        n_f = f1.shape[1]
+        with torch.cuda.device(self.dev):
+            d0, d1 = _lib.to_device(f0, self.dev), _lib.to_device(f1, self.dev)
+            dw = None if w is None else _lib.to_device(w, self.dev)
+            out = torch.empty((3, n), dtype=torch.float64, device=self.dev)
+            need = ctypes.c_size_t()
+            _lib.check(self.lib.hps_refine_check_workspace(n, n_f, ctypes.byref(need)), "workspace query")
+            ws = _lib.workspace(need.value, self.dev)
+            rc = self.lib.hps_refine_check(_lib.stream_ptr(), n, n_c, n_f, _lib.ptr(d0), _lib.ptr(d1), _lib.ptr(self.LT),
+                                           _lib.ptr(dw), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), _lib.ptr(ws),
+                                           ws.numel())
+            _lib.check(rc, "hps_refine_check")
+            res = out.cpu().numpy()
+        return res[0], res[1], res[2]
+
+
+def _generate(root, f_fn: Callable, tol: float, p: int, q: int, restrict_bool: bool, l2_norm: bool, device=None) -> None:
+    """``device``: a CUDA device runs the per-round criterion through ``hps_refine_check``; ``None`` keeps it in NumPy
+    (the two agree to rounding: `tests/test_gpu_adaptive.py`)."""
     two_d = _is_2D(root)
     d = 2 if two_d else 3
     to_pts = bounds_to_cheby_points_2D if two_d else bounds_to_cheby_points_3D
@@ -124,6 +162,7 @@ def _generate(root, f_fn: Callable, tol: float, p: int, q: int, restrict_bool: b
         _, fine, _ = clouds(_node_bounds([root]))
         global_nrm = float(np.max(np.asarray(f_fn(fine.reshape(-1, d)))))
 
+    check = _DeviceCheck(refine_op, device) if device is not None else None
     queue: List = list(get_all_leaves(root))
     while queue:
         logging.debug("adaptive mesh: queue length %d", len(queue))
@@ -131,16 +170,21 @@ def _generate(root, f_fn: Callable, tol: float, p: int, q: int, restrict_bool: b
         coarse, fine, kid_bounds = clouds(qb)
         f0 = np.asarray(f_fn(coarse), dtype=np.float64)
         f1 = np.asarray(f_fn(fine), dtype=np.float64)
-        diff = f0 @ refine_op.T - f1
-        if l2_norm:
-            w = _cheby_weights_leaf_order(kid_bounds, p).reshape(len(queue), -1)
-            ok = np.sum(w * diff**2, axis=1) / global_nrm < tol
+        assert f1.shape[1] == (1 << d) * n_c
+        w = _cheby_weights_leaf_order(kid_bounds, p).reshape(len(queue), -1) if l2_norm else None
+        if check is not None:
+            err_inf, err_l2, ref_max = check(np.ascontiguousarray(f0), np.ascontiguousarray(f1), w)
         else:
+            diff = f0 @ refine_op.T - f1
+            err_inf = np.max(np.abs(diff), axis=1)
+            err_l2 = np.sum(w * diff**2, axis=1) if l2_norm else None
             ref_max = np.max(np.abs(f1), axis=1)
+        if l2_norm:
+            ok = err_l2 / global_nrm < tol
+        else:
             nrm = np.maximum(global_nrm, ref_max)
-            ok = np.max(np.abs(diff), axis=1) / nrm < tol
+            ok = err_inf / nrm < tol
             global_nrm = float(np.max(nrm))
-        assert diff.shape[1] == (1 << d) * n_c
         nxt: List = []
         for node, good in zip(queue, ok):
             if good:
@@ -165,14 +209,14 @@ def _generate(root, f_fn: Callable, tol: float, p: int, q: int, restrict_bool: b
         queue = nxt
 
 
-def generate_adaptive_mesh_level_restriction_2D(root, f_fn, tol, p, q, restrict_bool=True, l2_norm=False) -> None:
-    """Refine ``root`` in place (`_adaptive_discretization_2D.py:37-199`)."""
-    _generate(root, f_fn, tol, p, q, restrict_bool, l2_norm)
+def generate_adaptive_mesh_level_restriction_2D(root, f_fn, tol, p, q, restrict_bool=True, l2_norm=False, device=None) -> None:
+    """Refine ``root`` in place (`_adaptive_discretization_2D.py:37-199`); ``device``: run the refinement check on a GPU."""
+    _generate(root, f_fn, tol, p, q, restrict_bool, l2_norm, device)
 
 
-def generate_adaptive_mesh_level_restriction_3D(root, f_fn, tol, p, q, restrict_bool=True, l2_norm=False) -> None:
-    """Refine ``root`` in place (`_adaptive_discretization_3D.py:35-205`)."""
-    _generate(root, f_fn, tol, p, q, restrict_bool, l2_norm)
+def generate_adaptive_mesh_level_restriction_3D(root, f_fn, tol, p, q, restrict_bool=True, l2_norm=False, device=None) -> None:
+    """Refine ``root`` in place (`_adaptive_discretization_3D.py:35-205`); ``device``: run the refinement check on a GPU."""
+    _generate(root, f_fn, tol, p, q, restrict_bool, l2_norm, device)
 
 
 generate_adaptive_mesh_level_restriction = generate_adaptive_mesh_level_restriction_3D

@@ -120,12 +120,14 @@ class Domain:
 
     @classmethod
     def from_adaptive_discretization(cls, p: int, q: int, root, f, tol: float, use_level_restriction: bool = True,
-                                     use_l_2_norm: bool = False) -> "Domain":
+                                     use_l_2_norm: bool = False, device=None) -> "Domain":
         """Refine ``root`` until ``f`` (one callable or a list, [..., d] -> [...]) is resolved to ``tol``
-        in the relative L_inf (default) or L_2 sense, then build the Domain (`_domain.py:367-434`)."""
+        in the relative L_inf (default) or L_2 sense, then build the Domain (`_domain.py:367-434`).
+        ``device`` (extension): a CUDA device evaluates the refinement criterion of every round there
+        (``hps_refine_check``); ``None`` keeps the reference's host evaluation."""
         fns = f if isinstance(f, list) else [f]
         gen = (generate_adaptive_mesh_level_restriction_2D if isinstance(root, DiscretizationNode2D)
                else generate_adaptive_mesh_level_restriction_3D)
         for fn in fns:
-            gen(root=root, f_fn=fn, tol=tol, p=p, q=q, restrict_bool=use_level_restriction, l2_norm=use_l_2_norm)
+            gen(root=root, f_fn=fn, tol=tol, p=p, q=q, restrict_bool=use_level_restriction, l2_norm=use_l_2_norm, device=device)
         return cls(p=p, q=q, root=root)

@@ -65,6 +65,8 @@ _SIGNATURES = {
     "hps_lu_dist_run_structured": (_i, [_p, _p, _i, _i, ctypes.POINTER(_p), ctypes.POINTER(_l), ctypes.POINTER(_i), _i, _i,
                                         ctypes.POINTER(_i), _p, _sz, _p]),
     "hps_lu_set_speculative": (_i, [_i]),
+    "hps_refine_check_workspace": (_i, [_i, _i, ctypes.POINTER(_sz)]),
+    "hps_refine_check": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz]),
     "hps_gemv_t_strided_batched": (_i, [_p, _i, _i, _i, _d, _p, _l, _l, _p, _l, _l, _d, _p, _l, _l, _i, _i]),
     "hps_root_cols_structure": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "hps_lu_dist_apply": (_i, [_p, _p, _i, _i, ctypes.POINTER(_p), ctypes.POINTER(_l), ctypes.POINTER(_i), _p, _sz]),

@@ -134,6 +134,46 @@ def solve_jvp(pde_problem, boundary_data, source, d_source=None, d_boundary_data
         return _lib.to_result(u3, host_device), _lib.to_result(du3, host_device)
 
 
+def top_T_jvp(pde_problem, d_coefficients: Dict, chunk: int = 256, compute_device=None, host_device=None):
+    """Directional derivative of the top-level Poincare-Steklov operator (``build_solver(..., return_top_T=True)``: the
+    root DtN map, or the root ItI map ``R`` that the reference converts with ``get_DtN_from_ItI`` and feeds to its
+    boundary-integral coupling, `examples/wave_scattering_utils.py:31-49`) with respect to the coefficient fields.
+
+    Column j of ``T`` is the outgoing data of the homogeneous solution ``u_j`` with boundary data ``e_j``; perturbing the
+    coefficients adds the source ``-sum_k dc_k (D_k u_j)`` with zero boundary data, whose outgoing data is the up pass'
+    ``h_last``.  So ``dT[:, j] = h_last(-sum_k dc_k D_k u_j)``: one multi-source down pass and one multi-source up pass
+    per chunk of boundary unknowns, no re-factorisation."""
+    from .up_pass import up_pass_uniform_2D_DtN, up_pass_uniform_2D_ItI
+
+    _check(pde_problem)
+    dev = _lib.require_cuda(compute_device)
+    dt = _cdt(pde_problem)
+    up = up_pass_uniform_2D_ItI if pde_problem.use_ItI else up_pass_uniform_2D_DtN
+    dom = pde_problem.domain
+    n_b = dom.boundary_points.shape[0]
+    n_leaves, n_c = dom.interior_points.shape[0], dom.p ** 2
+    with torch.cuda.device(dev):
+        dT = torch.empty((n_b, n_b), dtype=dt, device=dev)
+        dcs = {}
+        for key, dc in d_coefficients.items():
+            name = key[: -len("_coefficients")] if key.endswith("_coefficients") else key
+            if name not in _present(pde_problem):
+                raise ValueError(f"{key}: the problem was built without this coefficient field")
+            dcs[name] = _lib.to_device(dc, dev, dtype=dt).unsqueeze(-1)
+        for j0 in range(0, n_b, chunk):
+            j1 = min(n_b, j0 + chunk)
+            E = torch.zeros((n_b, j1 - j0), dtype=dt, device=dev)
+            E[torch.arange(j0, j1, device=dev), torch.arange(j1 - j0, device=dev)] = 1
+            zero = torch.zeros((n_leaves, n_c, j1 - j0), dtype=dt, device=dev)
+            U = _lib.to_device(solve(pde_problem, E, source=zero, compute_device=dev, host_device=dev), dev, dtype=dt)
+            src = torch.zeros_like(U)
+            for name, dc3 in dcs.items():
+                src = src - dc3 * apply_diff_operator(pde_problem, name, U)
+            h_last = up(src.contiguous(), pde_problem, device=dev, host_device=dev, return_h_last=True)[2]
+            dT[:, j0:j1] = _lib.to_device(h_last, dev, dtype=dt).reshape(n_b, j1 - j0)
+        return _lib.to_result(dT, host_device)
+
+
 # ------------------------------------------------------------------------------------------------ plumbing maps
 
 

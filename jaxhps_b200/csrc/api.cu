@@ -487,4 +487,14 @@ int hps_down_adaptive(void* stream, int npp, int n_src, int n_int, int n_ext, co
                        n_tbl, tbl, L_refine, ws);
 }
 
+int hps_refine_check_workspace(int n, int n_f, size_t* bytes) {
+  if (!bytes) return fail_arg(3, "null output pointer");
+  *bytes = refine_check_ws_bytes(n, n_f);
+  return 0;
+}
+int hps_refine_check(void* stream, int n, int n_c, int n_f, const double* f0, const double* f1, const double* LT,
+                     const double* w, double* err_inf, double* err_l2, double* ref_max, void* ws, size_t ws_bytes) {
+  return refine_check(static_cast<cudaStream_t>(stream), n, n_c, n_f, f0, f1, LT, w, err_inf, err_l2, ref_max, ws, ws_bytes);
+}
+
 }  // extern "C"

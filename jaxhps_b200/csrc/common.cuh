@@ -247,4 +247,8 @@ int interp_to_hps(cudaStream_t st, int dim, int n_leaves, int p, int n_x, int n_
                   const double* w_y, const double* w_z, const int* leaf2nat, const double* values, double* out, void* ws,
                   size_t ws_bytes);
 
+size_t refine_check_ws_bytes(int n, int n_f);
+int refine_check(cudaStream_t st, int n, int n_c, int n_f, const double* f0, const double* f1, const double* LT, const double* w,
+                 double* err_inf, double* err_l2, double* ref_max, void* ws, size_t ws_bytes);
+
 }  // namespace hps

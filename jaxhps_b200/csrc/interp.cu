@@ -212,4 +212,60 @@ int interp_to_hps(cudaStream_t st, int dim, int n_leaves, int p, int n_x, int n_
   return 0;
 }
 
+
+// ---- refinement check of the adaptive mesh generator ---------------------------------------------------
+// Reference: src/jaxhps/_adaptive_discretization_3D.py:114-165, 466-503 (vmapped check_current_discretization_global_*),
+// _adaptive_discretization_2D.py:96-140.  Per queued box: interpolate the samples on the box's own Chebyshev cloud to
+// the clouds of its 2^d children (one DMMA GEMM for the whole queue: [n][n_c] x [n_c][n_f]), compare with the samples
+// taken there, and reduce: err_inf = max |interp - fine|, err_l2 = sum w (interp - fine)^2, ref_max = max |fine|.
+namespace {
+__global__ void __launch_bounds__(256) refine_reduce_kernel(int n_f, const double* __restrict__ interp,
+                                                            const double* __restrict__ fine, const double* __restrict__ w,
+                                                            double* __restrict__ err_inf, double* __restrict__ err_l2,
+                                                            double* __restrict__ ref_max) {
+  const int64_t box = blockIdx.x;
+  const double* a = interp + box * n_f;
+  const double* b = fine + box * n_f;
+  const double* ww = w ? w + box * n_f : nullptr;
+  double e_inf = 0.0, e_l2 = 0.0, r_max = 0.0;
+  for (int i = threadIdx.x; i < n_f; i += blockDim.x) {
+    const double f1 = b[i], d = a[i] - f1;
+    e_inf = fmax(e_inf, fabs(d));
+    r_max = fmax(r_max, fabs(f1));
+    if (ww) e_l2 = fma(ww[i] * d, d, e_l2);
+  }
+  __shared__ double s0[8], s1[8], s2[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    e_inf = fmax(e_inf, __shfl_xor_sync(0xffffffffu, e_inf, o));
+    r_max = fmax(r_max, __shfl_xor_sync(0xffffffffu, r_max, o));
+    e_l2 += __shfl_xor_sync(0xffffffffu, e_l2, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s0[warp] = e_inf; s1[warp] = e_l2; s2[warp] = r_max; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) { e_inf = fmax(e_inf, s0[k]); e_l2 += s1[k]; r_max = fmax(r_max, s2[k]); }
+    err_inf[box] = e_inf;
+    err_l2[box] = e_l2;
+    ref_max[box] = r_max;
+  }
+}
+}  // namespace
+
+size_t refine_check_ws_bytes(int n, int n_f) { return align_up((size_t)n * n_f * sizeof(double), 256); }
+
+// f0 [n][n_c], f1 [n][n_f], LT [n_c][n_f] (the transposed refinement operator), w [n][n_f] or NULL
+int refine_check(cudaStream_t st, int n, int n_c, int n_f, const double* f0, const double* f1, const double* LT, const double* w,
+                 double* err_inf, double* err_l2, double* ref_max, void* ws, size_t ws_bytes) {
+  if (n <= 0) return 0;
+  if (n_c <= 0 || n_f <= 0) return fail_arg(3, "non-positive size");
+  if (ws_bytes < refine_check_ws_bytes(n, n_f)) return fail_arg(12, "refine_check: workspace too small");
+  double* interp = static_cast<double*>(ws);
+  HPS_TRY(dgemm(st, n, n_f, n_c, 1.0, f0, n_c, 0, LT, n_f, 0, 0.0, interp, n_f, 0, 1));
+  refine_reduce_kernel<<<n, 256, 0, st>>>(n_f, interp, f1, w, err_inf, err_l2, ref_max);
+  HPS_LAUNCH_CHECK("refine_reduce_kernel");
+  return 0;
+}
+
 }  // namespace hps

@@ -140,3 +140,26 @@ def test_sharded_driver_on_one_gpu_matches_reference(name):
     i = internal_nodes(dom.root).index(dom.root)
     if f"S_{i}" in G:
         assert rel_err(full, G[f"S_{i}"]) < TOL
+
+
+@pytest.mark.parametrize("dim,l2", [(2, False), (2, True), (3, False), (3, True)])
+def test_mesh_generator_refinement_check_on_the_device(dim, l2):
+    """`Domain.from_adaptive_discretization(..., device=cuda)` (criterion through ``hps_refine_check``) builds the same
+    tree, leaf for leaf, as the host generator that `tests/test_adaptive_host.py` pins to the reference."""
+    import jaxhps_b200 as hps
+    from jaxhps_b200._tree import get_all_leaves
+
+    def f(x):
+        r2 = ((x - 0.3) ** 2).sum(-1)
+        return np.exp(-40.0 * r2) + 0.2 * np.sin(3.0 * x[..., 0])
+
+    def root():
+        return hps.DiscretizationNode2D(-1.0, 1.0, -1.0, 1.0) if dim == 2 else hps.DiscretizationNode3D(-1.0, 1.0, -1.0, 1.0, -1.0, 1.0)
+
+    p, q = (8, 6) if dim == 2 else (6, 4)
+    tol = 1e-4 if dim == 2 else 1e-2
+    host = hps.Domain.from_adaptive_discretization(p, q, root(), f, tol, use_l_2_norm=l2)
+    dev = hps.Domain.from_adaptive_discretization(p, q, root(), f, tol, use_l_2_norm=l2, device="cuda:0")
+    lh, ld = get_all_leaves(host.root), get_all_leaves(dev.root)
+    assert len(lh) == len(ld) and len(lh) > 2 ** dim
+    assert np.array_equal(host.interior_points, dev.interior_points)

@@ -62,3 +62,33 @@ def test_adjoint_matches_the_dense_oracle_adjoint():
     assert _rel(np.asarray(bars["source"])[..., 0], f_bar) < 1e-9
     assert _rel(np.asarray(bars["boundary_data"])[..., 0], g_bar) < 1e-9
     assert _rel(bars["I_coefficients"], c_bar["I"]) < 1e-9 and _rel(bars["D_xx_coefficients"], c_bar["D_xx"]) < 1e-9
+
+
+@pytest.mark.parametrize("iti", [False, True])
+def test_top_operator_tangent_matches_finite_differences_of_the_oracle(iti):
+    """d(T_top)/dc (the operator the reference hands to its BIE coupling) against a central difference of the oracle's
+    no-source merge stage."""
+    import copy
+
+    from oracle import hps_oracle as orc
+
+    pb, f, g, df, dg, dco = _problem(iti, 6, 4, 2, 51)
+    d = {"I_coefficients": dco["I_coefficients"], "D_yy_coefficients": dco["D_yy_coefficients"]}
+
+    def top(q):
+        if iti:
+            _, T, _ = orc.nosource_local_solve_stage_uniform_2D_ItI(q)
+            return orc.nosource_merge_stage_uniform_2D_ItI(T, q.domain.L, return_T=True)[3]
+        _, T, _ = orc.nosource_local_solve_stage_uniform_2D_DtN(q)
+        return orc.nosource_merge_stage_uniform_2D_DtN(T, q.domain.L, return_T=True)[3]
+
+    eps, out = 1e-6, []
+    for sgn in (1.0, -1.0):
+        q = copy.copy(pb)
+        for k, v in d.items():
+            setattr(q, k, getattr(pb, k) + sgn * eps * v)
+        out.append(top(q))
+    fd = (out[0] - out[1]) / (2 * eps)
+    hps.build_solver(pb)
+    dT = adjoint.top_T_jvp(pb, d, chunk=17)
+    assert dT.shape == fd.shape and _rel(dT, fd) < 1e-6

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--tol", type=float, nargs="+", default=[1e-2])
     ap.add_argument("--mesh-only", action="store_true")
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--mesh-device", default=None, help="run the refinement check of the mesh generator there (e.g. cuda:0)")
     args = ap.parse_args()
     import jaxhps_b200 as hps
     from jaxhps_b200._tree import get_all_leaves
@@ -44,7 +45,7 @@ def main():
     for tol in args.tol:
         root = hps.DiscretizationNode3D(0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
         t0 = time.perf_counter()
-        dom = hps.Domain.from_adaptive_discretization(p=args.p, q=args.p - 2, root=root, f=source, tol=tol)
+        dom = hps.Domain.from_adaptive_discretization(p=args.p, q=args.p - 2, root=root, f=source, tol=tol, device=args.mesh_device)
         t_mesh = time.perf_counter() - t0
         depths = [leaf.depth for leaf in get_all_leaves(root)]
         rec = dict(config="wavefront adaptive 3D", p=args.p, q=args.p - 2, tol=tol, n_leaves=dom.n_leaves,
