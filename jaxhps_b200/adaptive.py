@@ -24,6 +24,8 @@ only on the root — the children's ``T`` are released as soon as their parent i
 from __future__ import annotations
 
 import ctypes
+import logging
+import os
 from typing import Dict, List
 
 import numpy as np
@@ -38,6 +40,8 @@ from .local_solve import _ORDER_2D, _ORDER_3D, _gather_coeffs, MAX_WORKSPACE_BYT
 #: interface size from which ``T = A + B S`` is formed from the non-zero blocks of B (72 / 16 GEMMs) instead
 #: of one dense product with 4x the flops
 SPARSE_B_MIN_INTERFACE = 1024
+#: replay the adaptive down pass as a CUDA graph from the second solve with the same shapes on (HPS_ADAPTIVE_GRAPH=0: off)
+ADAPTIVE_GRAPH = os.environ.get("HPS_ADAPTIVE_GRAPH", "1") != "0"
 
 __all__ = [
     "local_solve_stage_adaptive_2D_DtN",
@@ -345,52 +349,86 @@ def _down_adaptive(pde_problem, boundary_data, device, host_device, Y_arr=None, 
         f64 = dict(dtype=torch.float64, device=dev)
         n_leaves = len(plan.leaves)
         n_g = plan.n_points(plan.leaves[0])
-        G_leaf = torch.empty((n_leaves, n_g, n_src), **f64)
         first, S1, g1 = st.first
-        G1 = torch.empty((len(first), first[0].n_ext, n_src), **f64) if first else None
-        slot: Dict[int, torch.Tensor] = {id(np_.node): G1[k] for k, np_ in enumerate(first)}
-        for i, leaf in enumerate(plan.leaves):
-            slot[id(leaf)] = G_leaf[i]
-        if id(dom.root) in slot:
-            slot[id(dom.root)].copy_(g_root)
-        else:
-            slot[id(dom.root)] = g_root
-        max_int = max([np_.n_int for np_ in plan.nodes if not np_.all_leaf_children], default=1)
-        ws = torch.empty(max_int * n_src, **f64)
-        for np_ in reversed(plan.nodes):  # shallowest first
-            if np_.all_leaf_children:
-                continue
-            node = np_.node
-            outs: List[torch.Tensor] = []
-            for ch, kid in zip(np_.children, node.children):
-                if id(kid) not in slot:
-                    slot[id(kid)] = torch.empty((ch.n, n_src), **f64)
-                outs.append(slot[id(kid)])
-            g_t = st.g[id(node)]
-            if g_t.shape[-1] != n_src:
-                raise ValueError("boundary data and source term disagree on the number of right-hand sides")
-            rc = lib.hps_down_adaptive(_lib.stream_ptr(), npp, n_src, np_.n_int, np_.n_ext, _lib.ptr(st.S[id(node)]),
-                                       _lib.ptr(slot[id(node)]), _lib.ptr(g_t), len(outs), _ptr_array(outs),
-                                       np_.down_tbl.shape[0], st.tbl(np_, "down"), _lib.ptr(st.L_refine), _lib.ptr(ws))
-            _lib.check(rc, "hps_down_adaptive")
-            del slot[id(node)]
-        if first:
-            down_fn = lib.hps_down_oct_level if dim == 3 else lib.hps_down_quad_level
-            n1, n_int = len(first), first[0].n_int
-            n_child = len(first[0].children)
-            kids = torch.empty((n1 * n_child, n_g, n_src), **f64)
-            ws1 = torch.empty((n1, n_int, n_src), **f64)
-            rc = down_fn(_lib.stream_ptr(), n1, npp, n_src, _lib.ptr(S1), _lib.ptr(G1), _lib.ptr(g1), _lib.ptr(kids), _lib.ptr(ws1))
-            _lib.check(rc, "hps_down_level")
-            idx = torch.tensor([plan.leaf_index[id(k)] for np_ in first for k in np_.node.children], device=dev)
-            G_leaf.index_copy_(0, idx, kids)
         resident = pde_problem.__dict__.get("_adaptive_leaf")  # device copies kept by build_solver
         if Y_arr is None and resident is not None and resident[0].device == dev:
             Y, v = resident
         else:
             Y = _lib.to_device(pde_problem.Y if Y_arr is None else Y_arr, dev)
             v = _lib.to_device(pde_problem.v if v_arr is None else v_arr, dev)
-        u = leaf_apply(Y, G_leaf, v.reshape(n_leaves, -1, n_src), dev)
+        if first and "first_leaf_idx" not in st.__dict__:  # (a host -> device copy: must not happen inside a graph capture)
+            st.first_leaf_idx = torch.tensor([plan.leaf_index[id(k)] for np_ in first for k in np_.node.children], device=dev)
+        for np_ in plan.nodes:
+            if not np_.all_leaf_children and st.g[id(np_.node)].shape[-1] != n_src:
+                raise ValueError("boundary data and source term disagree on the number of right-hand sides")
+
+        def run(g_in: torch.Tensor) -> torch.Tensor:
+            """The whole down pass on the current stream: ~2 launches per planned node, no host synchronisation."""
+            G_leaf = torch.empty((n_leaves, n_g, n_src), **f64)
+            G1 = torch.empty((len(first), first[0].n_ext, n_src), **f64) if first else None
+            slot: Dict[int, torch.Tensor] = {id(np_.node): G1[k] for k, np_ in enumerate(first)}
+            for i, leaf in enumerate(plan.leaves):
+                slot[id(leaf)] = G_leaf[i]
+            if id(dom.root) in slot:
+                slot[id(dom.root)].copy_(g_in)
+            else:
+                slot[id(dom.root)] = g_in
+            max_int = max([np_.n_int for np_ in plan.nodes if not np_.all_leaf_children], default=1)
+            ws = torch.empty(max_int * n_src, **f64)
+            for np_ in reversed(plan.nodes):  # shallowest first
+                if np_.all_leaf_children:
+                    continue
+                node = np_.node
+                outs: List[torch.Tensor] = []
+                for ch, kid in zip(np_.children, node.children):
+                    if id(kid) not in slot:
+                        slot[id(kid)] = torch.empty((ch.n, n_src), **f64)
+                    outs.append(slot[id(kid)])
+                rc = lib.hps_down_adaptive(_lib.stream_ptr(), npp, n_src, np_.n_int, np_.n_ext, _lib.ptr(st.S[id(node)]),
+                                           _lib.ptr(slot[id(node)]), _lib.ptr(st.g[id(node)]), len(outs), _ptr_array(outs),
+                                           np_.down_tbl.shape[0], st.tbl(np_, "down"), _lib.ptr(st.L_refine), _lib.ptr(ws))
+                _lib.check(rc, "hps_down_adaptive")
+                del slot[id(node)]
+            if first:
+                down_fn = lib.hps_down_oct_level if dim == 3 else lib.hps_down_quad_level
+                n1, n_int = len(first), first[0].n_int
+                n_child = len(first[0].children)
+                kids = torch.empty((n1 * n_child, n_g, n_src), **f64)
+                ws1 = torch.empty((n1, n_int, n_src), **f64)
+                rc = down_fn(_lib.stream_ptr(), n1, npp, n_src, _lib.ptr(S1), _lib.ptr(G1), _lib.ptr(g1), _lib.ptr(kids), _lib.ptr(ws1))
+                _lib.check(rc, "hps_down_level")
+                G_leaf.index_copy_(0, st.first_leaf_idx, kids)
+            return leaf_apply(Y, G_leaf, v.reshape(n_leaves, -1, n_src), dev)
+
+        # The pass is launch-bound when issued from Python (config 5: 13.5 ms for ~2 ms of HBM traffic), so from the
+        # second solve with the same shapes on it is replayed as ONE CUDA graph (HPS_ADAPTIVE_GRAPH=0: always eager).
+        graphs = st.__dict__.setdefault("_down_graphs", {})
+        key = (n_src, Y.data_ptr(), v.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        entry = graphs.get(key)
+        if not ADAPTIVE_GRAPH or entry == "eager":
+            u = run(g_root)
+        elif entry is None:
+            u = run(g_root)          # first solve: eager (also the warm-up the capture needs)
+            graphs[key] = "capture"
+        elif entry == "capture":
+            try:
+                g_static = g_root.clone()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    u_static = run(g_static)
+                graph.replay()
+                graphs[key] = (graph, g_static, u_static)
+                u = u_static.clone()
+            except Exception as e:  # capture is an optimisation: fall back to eager launches for this configuration
+                logging.warning("adaptive down pass: CUDA graph capture failed (%s); staying eager", e)
+                torch.cuda.synchronize()
+                graphs[key] = "eager"
+                u = run(g_root)
+        else:
+            graph, g_static, u_static = entry
+            g_static.copy_(g_root)
+            graph.replay()
+            u = u_static.clone()
         return _lib.to_result(u if multi else u[..., 0], host_device)
 
 

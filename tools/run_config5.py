@@ -211,6 +211,16 @@ def main():
             t0 = time.perf_counter()
             u = hps.solve(pb, g)
             t_solve = time.perf_counter() - t0
+        # repeated solves with the same build: the second one captures the down pass as a CUDA graph, later ones replay it
+        t_rep = []
+        for _ in range(5):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            u2 = hps.solve(pb, g, host_device="cuda")
+            torch.cuda.synchronize()
+            t_rep.append(time.perf_counter() - t0)
+        rec["solve_repeat_s"] = [round(t, 5) for t in t_rep]
+        rec["graph_replay_max_diff"] = float((u2.cpu() - torch.as_tensor(u)).abs().max())
         probe_file = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
                                   f"config5_oracle_probe_p{args.p}.npz")
         if os.path.exists(probe_file) and args.load_tree:
