@@ -57,6 +57,12 @@ __all__ = [
 
 
 def _local_solve_adaptive(pde_problem, dim: int, device, host_device):
+    """Leaf solves of an adaptive tree; repeated with full partial pivoting if the threshold-pivoting speculation of the
+    leaf factorisations was rejected (the stage only reads the problem's fields)."""
+    return _lib.with_pivoting_fallback(lambda: _local_solve_adaptive_once(pde_problem, dim, device, host_device))
+
+
+def _local_solve_adaptive_once(pde_problem, dim: int, device, host_device):
     dev = _lib.require_cuda(device)
     lib = _lib.load()
     dom = pde_problem.domain

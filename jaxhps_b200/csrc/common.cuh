@@ -133,7 +133,8 @@ size_t lu_workspace_bytes(int batch, int n);
 // (HPS merge matrices): block columns are then factored without any cross-CTA pivot election and the assumption is
 // verified on the device; info = -2 means it did not hold and the call must be repeated after lu_set_speculative(0).
 constexpr int LU_NO_PIVOT_EXPECTED = 1;
-constexpr int LU_PIVOT_IN_BLOCK = 2;  // with LU_NO_PIVOT_EXPECTED: rows may still be interchanged INSIDE a diagonal block
+constexpr int LU_PIVOT_IN_BLOCK = 2;
+constexpr int LU_THRESHOLD_PIVOTING = 4;  // accept multipliers up to 4 below the diagonal block (threshold pivoting, u = 1/4)  // with LU_NO_PIVOT_EXPECTED: rows may still be interchanged INSIDE a diagonal block
 int lu_solve(cudaStream_t st, int batch, int n, double* A, int64_t lda, int64_t sA, int n_rhs,
              const RhsDesc* rhs, void* ws, size_t ws_bytes, int* info, int flags = 0);
 void lu_set_speculative(int on);

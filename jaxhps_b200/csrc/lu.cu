@@ -1555,7 +1555,7 @@ struct Mat {  // batched row-major matrix view
 // multiplier must satisfy |l| <= 1, otherwise info := -2 (kept if info already reports a zero pivot).
 __global__ void __launch_bounds__(256) spec_commit_kernel(double* __restrict__ A21, int64_t lda, int64_t sA,
                                                           const double* __restrict__ P, int64_t sP, int rows, int jb,
-                                                          int* __restrict__ info) {
+                                                          int* __restrict__ info, double bound) {
   const int mat = blockIdx.y;
   const double* p = P + (int64_t)mat * sP;
   double* a = A21 + (int64_t)mat * sA;
@@ -1564,7 +1564,7 @@ __global__ void __launch_bounds__(256) spec_commit_kernel(double* __restrict__ A
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = e / jb, c = e - r * jb;
     const double v = p[e];
-    bad |= !(fabs(v) <= 1.0 + 1e-8);  // also catches NaN
+    bad |= !(fabs(v) <= bound);  // also catches NaN
     a[r * lda + c] = v;
   }
   if (__syncthreads_or(bad) && threadIdx.x == 0) atomicCAS(&info[mat], 0, -2);
@@ -1583,7 +1583,7 @@ std::atomic<int> g_lu_speculate{[] { const char* e = std::getenv("HPS_LU_SPEC");
 //      partial pivoting over the whole column would have chosen the same pivots.  Otherwise info = -2 and the
 //      caller repeats the operation with hps_lu_set_speculative(0).
 int factor_block_column_spec(cudaStream_t st, int batch, int n, const Mat& A, int j, int jb, LuWorkspace& w, int* info,
-                             bool in_block_pivoting) {
+                             bool in_block_pivoting, double bound) {
   const int nblk = (n + NB - 1) / NB;
   const int64_t sW = (int64_t)nblk * NB * NB;
   static const bool smem_panel = [] { const char* e = std::getenv("HPS_DIAGBLK"); return e && e[0] == 's'; }();  // A/B switch
@@ -1620,7 +1620,7 @@ int factor_block_column_spec(cudaStream_t st, int batch, int n, const Mat& A, in
                   w.P, jb, sP, batch));
     const int64_t total = (int64_t)rows * jb;
     spec_commit_kernel<<<dim3((unsigned)std::min<int64_t>((total + 255) / 256, 1184), batch), 256, 0, st>>>(
-        A.at(j + jb, j), A.ld, A.stride, w.P, sP, rows, jb, info);
+        A.at(j + jb, j), A.ld, A.stride, w.P, sP, rows, jb, info, bound);
     HPS_LAUNCH_CHECK("spec_commit_kernel");
   }
   return 0;
@@ -1630,9 +1630,14 @@ int factor_block_column_spec(cudaStream_t st, int batch, int n, const Mat& A, in
 // its unit-lower diagonal block into Linv[j/NB].  Touches columns [j, j+jb) only.
 // speculate: 0 = pivoted kernels, 1 = speculative with the diagonal taken as pivot, 2 = speculative with partial
 // pivoting inside the diagonal block (matrices that interchange rows locally, e.g. the adaptive interface systems)
+// spec_bound: largest multiplier accepted below the diagonal block.  1 (+ rounding): exactly partial pivoting's
+// choices; 4: THRESHOLD pivoting with u = 1/4 (the block's pivot is kept when it is within a factor 4 of the column
+// maximum — the classical relaxation of sparse direct solvers), used for the leaves' A_ii, which partial pivoting
+// does reshuffle (71 of 1000 rows at p = 12, by at most 100 positions) although the unpivoted multipliers stay <= 1.16.
+constexpr double SPEC_BOUND_EXACT = 1.0 + 1e-8, SPEC_BOUND_THRESHOLD = 4.0;
 int factor_block_column(cudaStream_t st, int batch, int n, const Mat& A, int j, int jb, LuWorkspace& w, int* info,
-                        int speculate = 0) {
-  if (speculate) return factor_block_column_spec(st, batch, n, A, j, jb, w, info, speculate == 2);
+                        int speculate = 0, double spec_bound = SPEC_BOUND_EXACT) {
+  if (speculate) return factor_block_column_spec(st, batch, n, A, j, jb, w, info, speculate == 2, spec_bound);
   bool done = false;
   HPS_TRY(launch_blockcol(st, batch, n, A.p, A.ld, A.stride, j, jb, w, info, done));
   for (int jj = j; !done && jj < j + jb; jj += IB) {
@@ -1766,6 +1771,7 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
   static const bool force_spec = [] { const char* e = std::getenv("HPS_LU_FORCE_SPEC"); return e && e[0] == '1'; }();  // tools/bench_lu.py
   const bool spec_on = ((flags & LU_NO_PIVOT_EXPECTED) || force_spec) && g_lu_speculate.load(std::memory_order_relaxed) != 0;
   const int speculate = spec_on ? ((flags & LU_PIVOT_IN_BLOCK) ? 2 : 1) : 0;
+  const double spec_bound = (flags & LU_THRESHOLD_PIVOTING) ? SPEC_BOUND_THRESHOLD : SPEC_BOUND_EXACT;
   if (batch <= 0 || n <= 0) return 0;
   if (batch > 65535) return fail_arg(2, "lu_solve: batch > 65535");
   Arena ar(ws, ws_bytes);
@@ -1786,7 +1792,7 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
   // to their right (and the interchanges to everything to their left).
   HPS_CUDA(cudaEventRecord(aux->fork, s0));
   HPS_CUDA(cudaStreamWaitEvent(s1, aux->fork, 0));
-  HPS_TRY(factor_block_column(s1, batch, n, A, 0, min(NB, n), w, info, speculate));
+  HPS_TRY(factor_block_column(s1, batch, n, A, 0, min(NB, n), w, info, speculate, spec_bound));
   HPS_CUDA(cudaEventRecord(aux->panel_done[0], s1));
   for (int b = 0; b < nblk; ++b) {
     const int j = b * NB, jb = min(NB, n - j);
@@ -1797,7 +1803,7 @@ int lu_solve(cudaStream_t st, int batch, int n, double* Ap, int64_t lda, int64_t
       // written by s0's update for block b-1, which must have finished.
       if (b > 0) HPS_CUDA(cudaStreamWaitEvent(s1, aux->update_done[(b - 1) & 1], 0));
       HPS_TRY(update_columns(s1, batch, n, A, j, jb, next, nextb, w));
-      HPS_TRY(factor_block_column(s1, batch, n, A, next, nextb, w, info, speculate));
+      HPS_TRY(factor_block_column(s1, batch, n, A, next, nextb, w, info, speculate, spec_bound));
       HPS_CUDA(cudaEventRecord(aux->panel_done[(b + 1) & 1], s1));
     }
     // s0: interchanges on the columns to the left (L in LAPACK form), then the rest of the

@@ -95,16 +95,19 @@ def _local_solve_dtn(pde_problem, dim: int, device, host_device):
         _lib.check(lib.hps_local_solve_dtn_workspace(dim, chunk, p, q, n_src, ctypes.byref(need)), "workspace query")
         ws = _lib.WORKSPACE.get(need.value, dev)
         logging.debug("local_solve: %d leaves in chunks of %d (workspace %.2f GB)", n_leaves, chunk, need.value / 2**30)
-        for s in range(0, n_leaves, chunk):
-            e = min(n_leaves, s + chunk)
-            c_chunk = coeffs[:, s:e].contiguous() if (s, e) != (0, n_leaves) else coeffs
-            rc = lib.hps_local_solve_dtn(
-                _lib.stream_ptr(), dim, e - s, p, q, n_src, which, _lib.ptr(c_chunk), _lib.ptr(D1), _lib.ptr(P),
-                _lib.ptr(Q), _lib.ptr(src[s:e]), _lib.ptr(Y[s:e]), _lib.ptr(T[s:e]), _lib.ptr(v[s:e]),
-                _lib.ptr(h[s:e]), _lib.ptr(ws), ws.numel(), _lib.ptr(info[s:e]),
-            )
-            _lib.check(rc, "hps_local_solve_dtn")
-        _lib.check_info(info, "local solve")
+        def run():
+            for s in range(0, n_leaves, chunk):
+                e = min(n_leaves, s + chunk)
+                c_chunk = coeffs[:, s:e].contiguous() if (s, e) != (0, n_leaves) else coeffs
+                rc = lib.hps_local_solve_dtn(
+                    _lib.stream_ptr(), dim, e - s, p, q, n_src, which, _lib.ptr(c_chunk), _lib.ptr(D1), _lib.ptr(P),
+                    _lib.ptr(Q), _lib.ptr(src[s:e]), _lib.ptr(Y[s:e]), _lib.ptr(T[s:e]), _lib.ptr(v[s:e]),
+                    _lib.ptr(h[s:e]), _lib.ptr(ws), ws.numel(), _lib.ptr(info[s:e]),
+                )
+                _lib.check(rc, "hps_local_solve_dtn")
+            _lib.check_info(info, "local solve")
+
+        _lib.with_pivoting_fallback(run)  # (the stage only reads its inputs: a repeat with full pivoting starts clean)
         if not multi:
             v, h = v[..., 0], h[..., 0]
         return tuple(_lib.to_result(t, host_device) for t in (Y, T, v, h))

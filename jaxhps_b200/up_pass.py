@@ -33,6 +33,10 @@ def _block_perm(order_positions, m: int, dev) -> torch.Tensor:
 
 
 def _nosource_leaves(pde_problem, iti: bool, device, host_device):
+    return _lib.with_pivoting_fallback(lambda: _nosource_leaves_once(pde_problem, iti, device, host_device))
+
+
+def _nosource_leaves_once(pde_problem, iti: bool, device, host_device):
     dev = _lib.require_cuda(device)
     lib = _lib.load()
     dom = pde_problem.domain

@@ -191,3 +191,42 @@ def test_iti_analytic_cases_incl_complex_coefficients(which):
                          I_coefficients=pb.I_coefficients, use_ItI=True, eta=pb.eta)
     hps.build_solver(pb2)
     assert rel_err(hps.solve(pb2, g_in, source=pb.source), u) < 1e-8
+
+
+def test_speculation_failure_falls_back_to_full_pivoting():
+    """A root system that DOES need row interchanges (random interface blocks, unlike any HPS merge matrix): the
+    speculative block columns report info = -2, `_lib.with_pivoting_fallback` repeats the solve with full partial
+    pivoting, and the result equals the dense solve."""
+    import ctypes
+
+    import torch
+
+    from jaxhps_b200 import _dist, _lib
+
+    rng = np.random.default_rng(12)
+    m, n_src = 48, 2  # n_int = 576: several 128-wide block columns
+    Dblk = rng.normal(size=(8, 3 * m, 3 * m))
+    hblk = rng.normal(size=(8, 3 * m, n_src))
+    panels = _dist.balanced_panels(1)[0]
+    Cpan = rng.normal(size=(len(panels), 3 * m, m))
+    ops = _dist.CudaOps("cuda:0")
+    calls = []
+    lib = _lib.load()
+    real = lib.hps_lu_set_speculative
+
+    def spy(on):
+        calls.append(int(on))
+        return real(on)
+
+    lib.hps_lu_set_speculative = spy
+    try:
+        S_r, g = ops.root_solve(ops.tensor(Dblk), ops.tensor(hblk), ops.tensor(Cpan), panels)
+    finally:
+        lib.hps_lu_set_speculative = real
+    assert calls and calls[0] == 0, "the speculative path should have been rejected for a random matrix"
+    # dense reference: assemble D, C, h_int like the oracle-backed test double of the gloo tests
+    from test_dist_gloo import OracleOps
+
+    S_ref, g_ref = OracleOps().root_solve(torch.from_numpy(Dblk), torch.from_numpy(hblk), torch.from_numpy(Cpan), panels)
+    assert np.abs(S_r.cpu().numpy() - S_ref.numpy()).max() / np.abs(S_ref.numpy()).max() < 1e-9
+    assert np.abs(g.cpu().numpy() - g_ref.numpy()).max() / np.abs(g_ref.numpy()).max() < 1e-9
