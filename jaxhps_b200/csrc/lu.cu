@@ -2315,6 +2315,15 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
     static const bool no_struct = [] { const char* e = std::getenv("HPS_LU_STRUCT"); return e && e[0] == '0'; }();
     if (no_struct) structured = false;
   }
+  // The right-hand sides ride along with the factorisation (rank-128 updates, ~28 TF/s) when that fills time the
+  // caller's stream would otherwise spend waiting for the panel chain; when the trailing updates of this rank's own
+  // block columns already outlast the chain (~0.4 ms per block column) — the L=4 root, n = 76 800 — the forward
+  // substitution runs afterwards instead, recursively, at the large-K rate (~35 TF/s).  HPS_DIST_RIDE=0/1 forces it.
+  bool ride_along = 2.0 * n * NB * ((double)n / world) / 30e12 < 1.0e-3;
+  {
+    static const int forced = [] { const char* e = std::getenv("HPS_DIST_RIDE"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+    if (forced >= 0) ride_along = forced != 0;
+  }
   // HPS_DIST_SEND=kernel: SM stores straight into the peers' matrices; default: pack into a staging slot, one
   // contiguous copy-engine transfer per peer, a one-warp kernel raises the flags, the peer unpacks.
   static const bool send_by_kernel = [] { const char* e = std::getenv("HPS_DIST_SEND"); return e && e[0] == 'k'; }();
@@ -2425,7 +2434,7 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
       lo = nb2 + 1;
     }
     HPS_CUDA(cudaEventRecord(aux->update_done[b & 1], s0));
-    HPS_TRY(apply_owned(s0, b, lo, true));
+    HPS_TRY(apply_owned(s0, b, lo, ride_along));
   }
   if (world > 1) {  // the caller's stream also covers the sends still in flight on the communication stream
     HPS_CUDA(cudaEventRecord(aux->sent, s2));
@@ -2439,7 +2448,13 @@ int lu_dist_run(Comm* c, cudaStream_t st, int n, int n_rhs, const RhsDesc* rhs, 
   trtri_upper_kernel<<<dim3(nblk, 1), TRI_THREADS, TRTRI_UPPER_SMEM, s0>>>(A, n, 0, 0, n, w.Uinv, (int64_t)nblk * NB * NB);
   prof_end(PROF_TRTRI, s0);
   HPS_LAUNCH_CHECK("trtri_upper_kernel");
-  for (int k = 0; k < n_rhs; ++k) HPS_TRY(trsm_upper(s0, 1, n, Am, w, rhs[k], 0, n));
+  for (int k = 0; k < n_rhs; ++k) {
+    if (!ride_along) {  // forward substitution after the factorisation: recursive, large-K products
+      HPS_TRY(laswp(s0, 1, rhs[k].ptr, rhs[k].ld, rhs[k].stride, 0, rhs[k].ncols, w.ipiv, n, 0, n));
+      HPS_TRY(trsm_lower(s0, 1, n, Am, w, rhs[k], 0, n, structured));
+    }
+    HPS_TRY(trsm_upper(s0, 1, n, Am, w, rhs[k], 0, n));
+  }
   return 0;
 }
 
