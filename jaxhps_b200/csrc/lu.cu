@@ -14,20 +14,21 @@
 //      level, so the right-hand sides — the bulk of the flops in the HPS merges — run at the
 //      large-K rate of the DMMA kernel and are read/written O(log) times instead of n/128 times.
 //
-// Kernels:
-//   blockcol_kernel  factors a whole NB-wide block column in ONE launch: the rows are split over G
-//                  co-scheduled CTAs (thread-block cluster for G<=8, cooperative launch above) that keep
-//                  their rows x NB chunk in shared memory.  Per column ONE exchange through L2: every
-//                  CTA publishes its pivot candidate (value, row, the row's NB entries) followed by a
-//                  release-stored epoch flag, every CTA acquires all flags and elects the same winner —
-//                  no atomics and no separate barrier.  After each IB-wide inner panel the first CTA
-//                  publishes U12 = L11^-1 A12 and every CTA updates its own rows from shared memory.
-//   panel_kernel   legacy IB-column panel for block columns too tall to be co-resident
-//                  (more than 148 x 196 rows: only the L=4 root); one group barrier per column.
+// Two ways to factor a 128-wide block column:
+//   SPECULATIVE (matrices that partial pivoting leaves alone below the diagonal block: the merges' D, and — with
+//   threshold pivoting — the leaves' A_ii): diagblk_kernel (128 x 128 diagonal block, one CTA, the row panel in
+//   registers) -> trtri_pair_kernel (both triangular inverses) -> ONE DMMA product L21 = A21 U11^-1 ->
+//   spec_commit_kernel (commit + the check that makes it equivalent to (threshold) partial pivoting; info = -2 otherwise).
+//   No cross-CTA exchange at all: 190 us instead of 830 us per block column at n = 19 200.
+//   PIVOTED (everything else, and the fallback): blockcol_kernel (one CTA per matrix, <= 196 rows), blockcol2_kernel
+//   (rows split over G co-scheduled CTAs — cluster for G <= 8, cooperative launch above — that keep their rows x 128
+//   chunk in shared memory and elect each column's pivot through L2 with self-validating 16-byte units), panel_kernel
+//   (IB-column panels for block columns too tall or too many to be co-resident; one group barrier per column).
+// Other kernels:
 //   laswp_kernel   row interchanges on a column range (rows are contiguous: coalesced).
-//   inner_trsm     32x32 unit-lower solve inside the outer panel.
-//   trtri kernels  invert NBxNB triangular diagonal blocks in shared memory so that every
-//                  triangular solve becomes a DMMA GEMM (in place, single tile row).
+//   inner_trsm     32x32 unit-lower solve inside the outer panel (panel_kernel path).
+//   trtri kernels  invert NBxNB triangular diagonal blocks in shared memory (substitutions in registers) so that
+//                  every triangular solve becomes a DMMA GEMM (in place, single tile row).
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -228,22 +229,14 @@ constexpr int BC_THREADS = 512;
 constexpr int BC_UW = NB - IB;   // widest U12 block
 constexpr int BC_MAX_G = 148;
 
-struct alignas(16) BcCand {  // content first; the 16-byte header {val, row, flag} is stored last, as ONE vector store
-  double content[NB];
-  double val;          // |a|, negative when the CTA has no eligible row
-  int row;             // block-column-relative row index
-  unsigned flag;       // epoch of the column this candidate belongs to
-};
-
 struct BcArgs {
   double* A; int64_t lda, sA;
   int n, j, jb, G, rpc;     // rpc: rows per CTA (>= jb when G > 1, so CTA 0 owns every pivot row)
   int* ipiv;                // [batch][n]
   int* info;                // [batch]
-  char* scratch;            // per matrix: BcCand[2][Gcap], diag[2][NB], u12[IB][BC_UW], u12 flag
+  char* scratch;            // per matrix: BcCand2[2][Gcap], BcChunk diag[2][NB], u12[IB][BC_UW], u12 flag
   size_t scratch_stride;
   int Gcap;
-  int rows_cap;             // > 0: only the first rows_cap rows below the diagonal take part (speculative path)
 };
 
 // Tagged exchange (blockcol2_kernel): every 16-byte unit carries its own epoch, so no fence is needed anywhere.
@@ -269,7 +262,6 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;\n" ::: "memory"); }
 // The candidate header travels as one aligned 16-byte access (one L2 sector transaction), so a reader that sees
 // the new epoch in .y's upper half also sees the value and row stored with it.
 template <typename C>
@@ -299,46 +291,36 @@ __device__ __forceinline__ void ld_header(const C* c, double& val, int& row, uns
   flag = (unsigned)(hi >> 32);
 }
 
-// SHARED = false: one CTA per matrix, everything stays in shared memory.
-// SHARED = true : G co-scheduled CTAs per matrix exchange pivot candidates through global memory (L2).
-template <bool SHARED>
+// One CTA per matrix (block columns of at most BC_ROWS rows): everything stays in shared memory.
 __global__ void __launch_bounds__(BC_THREADS, 1) blockcol_kernel(BcArgs a) {
   extern __shared__ __align__(16) double sm[];
   constexpr int LD = BC_LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = blockIdx.x, mat = blockIdx.y;
-  const int G = a.G, jb = a.jb;
-  const int rows = a.rows_cap > 0 ? min(a.rows_cap, a.n - a.j) : a.n - a.j;
-  const int r0 = min(rows, g * a.rpc), r1 = min(rows, r0 + a.rpc), nr = r1 - r0;
+  const int mat = blockIdx.y;
+  const int jb = a.jb;
+  const int rows = a.n - a.j, nr = rows;
   double* A = a.A + (int64_t)mat * a.sA + (int64_t)a.j * a.lda + a.j;
   int* ipiv = a.ipiv + (int64_t)mat * a.n + a.j;
 
-  double* tile = sm;                                   // [rpc][LD]
+  double* tile = sm;                                   // [rows][LD]
   double* U = tile + (((size_t)a.rpc * LD + 1) & ~(size_t)1);  // [IB][BC_UW], 16-byte aligned for the double2 loads
   double* prow = U + IB * BC_UW;                       // [NB]
   double* red_val = prow + NB;                         // [16]
   int* red_idx = reinterpret_cast<int*>(red_val + 16); // [16]
-  __shared__ int s_wg, s_wr;
-
-  char* sc = a.scratch + (size_t)mat * a.scratch_stride;
-  BcCand* cands = reinterpret_cast<BcCand*>(sc);                                       // [2][Gcap]
-  double* diag = reinterpret_cast<double*>(sc + (size_t)2 * a.Gcap * sizeof(BcCand));  // [2][NB]
-  double* u12g = diag + 2 * NB;                                                        // [IB][BC_UW]
-  unsigned* u12_flag = reinterpret_cast<unsigned*>(u12g + IB * BC_UW);
 
   for (int idx = tid; idx < nr * jb; idx += BC_THREADS) {
     const int r = idx / jb, c = idx - r * jb;
-    tile[r * LD + c] = A[(int64_t)(r0 + r) * a.lda + c];
+    tile[r * LD + c] = A[(int64_t)r * a.lda + c];
   }
   __syncthreads();
 
   for (int c = 0; c < jb; ++c) {
     const int c0 = (c / IB) * IB, pe = min(c0 + IB, jb);
-    // ---- local arg-max of |a[r][c]| over rows >= c (lowest row wins ties) ----
+    // ---- arg-max of |a[r][c]| over rows >= c (lowest row wins ties) ----
     double best = -1.0;
     int bidx = 0x7fffffff;
     for (int r = tid; r < nr; r += BC_THREADS) {
-      if (r0 + r >= c) {
+      if (r >= c) {
         const double v = fabs(tile[r * LD + c]);
         if (v > best) { best = v; bidx = r; }
       }
@@ -358,80 +340,22 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol_kernel(BcArgs a) {
       const int oi = red_idx[w];
       if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
     }
-
-    int p;  // block-column-relative pivot row
-    if (!SHARED) {
-      p = (best >= 0.0) ? bidx : c;
-      if (tid < jb) {  // each thread swaps its own column: no cross-thread hazard
-        const double xp = tile[p * LD + tid], xc = tile[c * LD + tid];
-        tile[p * LD + tid] = xc;
-        tile[c * LD + tid] = xp;
-        prow[tid] = xp;
-      }
-      __syncthreads();
-    } else {
-      const unsigned epoch = (unsigned)(a.j + c + 1);
-      BcCand* mine = cands + (size_t)(c & 1) * a.Gcap + g;
-      double* dg = diag + (c & 1) * NB;
-      if (tid < jb) {
-        if (best >= 0.0) mine->content[tid] = tile[bidx * LD + tid];
-      } else if (tid >= NB && tid < NB + jb) {
-        if (c >= r0 && c < r1) dg[tid - NB] = tile[(c - r0) * LD + tid - NB];
-      }
-      __syncthreads();
-      if (tid == 0) {
-        fence_acq_rel_gpu();  // the CTA's content / diag stores (ordered before by the barrier) become visible first
-        st_header(mine, best, (best >= 0.0) ? r0 + bidx : -1, epoch);
-      }
-      if (warp == 0) {
-        // every CTA elects the same winner: largest value, lowest row on ties.  All of a lane's headers are
-        // requested before the first one is examined; lanes spin only on the ones still carrying an old epoch.
-        double wv = -1.0; int wg = 0, wr = 0x7fffffff;
-        constexpr int KMAX = (BC_MAX_G + 31) / 32;
-        double hv[KMAX]; int hr[KMAX]; unsigned hf[KMAX];
-#pragma unroll
-        for (int i = 0; i < KMAX; ++i) {
-          const int k = lane + 32 * i;
-          hf[i] = epoch; hv[i] = -1.0; hr[i] = -1;
-          if (k < G) ld_header(cands + (size_t)(c & 1) * a.Gcap + k, hv[i], hr[i], hf[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < KMAX; ++i) {
-          const int k = lane + 32 * i;
-          if (k < G) {
-            while (hf[i] != epoch) ld_header(cands + (size_t)(c & 1) * a.Gcap + k, hv[i], hr[i], hf[i]);
-            if (hv[i] >= 0.0 && (hv[i] > wv || (hv[i] == wv && hr[i] < wr))) { wv = hv[i]; wg = k; wr = hr[i]; }
-          }
-        }
-        fence_acq_rel_gpu();  // acquire side: the winners' content is read after this (and after the barrier below)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double ov = __shfl_xor_sync(0xffffffffu, wv, o);
-          const int og = __shfl_xor_sync(0xffffffffu, wg, o);
-          const int orr = __shfl_xor_sync(0xffffffffu, wr, o);
-          if (ov > wv || (ov == wv && orr < wr)) { wv = ov; wg = og; wr = orr; }
-        }
-        if (lane == 0) { s_wg = wg; s_wr = (wv >= 0.0) ? wr : c; }
-      }
-      __syncthreads();
-      p = s_wr;
-      if (tid < jb) {
-        const double x = __ldcg(&cands[(size_t)(c & 1) * a.Gcap + s_wg].content[tid]);
-        prow[tid] = x;
-        if (c >= r0 && c < r1) tile[(c - r0) * LD + tid] = x;  // the pivot row moves up to row c ...
-      } else if (tid >= NB && tid < NB + jb) {
-        if (p != c && p >= r0 && p < r1) tile[(p - r0) * LD + tid - NB] = __ldcg(&dg[tid - NB]);  // ... and row c takes its place
-      }
-      __syncthreads();
+    const int p = (best >= 0.0) ? bidx : c;  // block-column-relative pivot row
+    if (tid < jb) {  // each thread swaps its own column: no cross-thread hazard
+      const double xp = tile[p * LD + tid], xc = tile[c * LD + tid];
+      tile[p * LD + tid] = xc;
+      tile[c * LD + tid] = xp;
+      prow[tid] = xp;
     }
-    if (g == 0 && tid == 0) ipiv[c] = a.j + p;
+    __syncthreads();
+    if (tid == 0) ipiv[c] = a.j + p;
     const double piv = prow[c];
     if (piv == 0.0) {
-      if (g == 0 && tid == 0 && a.info[mat] == 0) a.info[mat] = a.j + c + 1;
+      if (tid == 0 && a.info[mat] == 0) a.info[mat] = a.j + c + 1;
     } else {
       // ---- scale the column, rank-1 update of the rest of the inner panel ----
       for (int r = tid; r < nr; r += BC_THREADS) {
-        if (r0 + r > c) {
+        if (r > c) {
           double* row = tile + r * LD;
           const double l = row[c] / piv;
           row[c] = l;
@@ -449,44 +373,30 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol_kernel(BcArgs a) {
     if (c == pe - 1 && pe < jb) {
       // ---- inner panel finished: U12 = L11^-1 A12, then rows >= pe get A22 -= L21 U12 ----
       const int W = jb - pe;  // pe < jb means this panel is IB wide
-      if (g == 0) {
-        if (tid < W) {  // one column of U12 per thread, forward substitution in registers
-          double x[IB];
+      if (tid < W) {  // one column of U12 per thread, forward substitution in registers
+        double x[IB];
 #pragma unroll
-          for (int r = 0; r < IB; ++r) x[r] = tile[(c0 + r) * LD + pe + tid];
+        for (int r = 0; r < IB; ++r) x[r] = tile[(c0 + r) * LD + pe + tid];
 #pragma unroll
-          for (int r = 1; r < IB; ++r) {
-            double s = x[r];
+        for (int r = 1; r < IB; ++r) {
+          double s = x[r];
 #pragma unroll
-            for (int t = 0; t < r; ++t) s = fma(-tile[(c0 + r) * LD + c0 + t], x[t], s);
-            x[r] = s;
-          }
-#pragma unroll
-          for (int r = 0; r < IB; ++r) {
-            tile[(c0 + r) * LD + pe + tid] = x[r];
-            U[r * BC_UW + tid] = x[r];
-            if (SHARED) u12g[r * BC_UW + tid] = x[r];
-          }
+          for (int t = 0; t < r; ++t) s = fma(-tile[(c0 + r) * LD + c0 + t], x[t], s);
+          x[r] = s;
         }
-        __syncthreads();
-        if (SHARED && tid == 0) st_release_u32(u12_flag, (unsigned)(a.j + pe));  // release: fence + store
-      } else {
-        if (tid == 0) {
-          while (ld_acquire_u32(u12_flag) != (unsigned)(a.j + pe)) { }
+#pragma unroll
+        for (int r = 0; r < IB; ++r) {
+          tile[(c0 + r) * LD + pe + tid] = x[r];
+          U[r * BC_UW + tid] = x[r];
         }
-        __syncthreads();
-        for (int idx = tid; idx < IB * W; idx += BC_THREADS) {
-          const int r = idx / W, x = idx - r * W;
-          U[r * BC_UW + x] = __ldcg(&u12g[r * BC_UW + x]);
-        }
-        __syncthreads();
       }
+      __syncthreads();
       // 4x4 register tiles: a warp covers 16 rows x 32 columns per pass
       const int ly = lane >> 3, lx = lane & 7;
       const int nstrips = (nr + 15) >> 4, ncp = (W + 31) >> 5;
       for (int s = warp; s < nstrips; s += BC_THREADS / 32) {
         const int rb = s * 16 + ly * 4;
-        if (r0 + s * 16 + 15 < pe) continue;  // whole strip above the trailing block
+        if (s * 16 + 15 < pe) continue;  // whole strip above the trailing block
         const double* ap[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) ap[i] = tile + min(rb + i, a.rpc - 1) * LD + c0;
@@ -515,7 +425,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol_kernel(BcArgs a) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = rb + i;
-            if (r < nr && r0 + r >= pe) {
+            if (r < nr && r >= pe) {
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj)
                 if (cb + jj < W) tile[r * LD + pe + cb + jj] -= acc[i][jj];
@@ -529,7 +439,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) blockcol_kernel(BcArgs a) {
 
   for (int idx = tid; idx < nr * jb; idx += BC_THREADS) {
     const int r = idx / jb, c = idx - r * jb;
-    A[(int64_t)(r0 + r) * a.lda + c] = tile[r * LD + c];
+    A[(int64_t)r * a.lda + c] = tile[r * LD + c];
   }
 }
 
@@ -807,96 +717,13 @@ __global__ void laswp_kernel(double* A, int64_t lda, int64_t sA, int c0, int nco
   }
 }
 
-// Same interchanges for a SHORT pivot range (k1 - k0 <= NB), in two parallel phases instead of k1 - k0 dependent
-// swaps per thread (which made every call cost ~0.6 us x 128 whatever the column count — on the critical chain
-// of the factorisation):
-//   1. warp 0 composes the swaps into a move list "row dst[e] receives old row src[e]" (at most 2 (k1 - k0) rows
-//      are touched: the range itself and the distinct pivot rows below it);
-//   2. all threads gather the source rows of a 32-column tile into shared memory and scatter them to their
-//      destinations (coalesced row segments, nmov/8 independent loads per thread).
-// A CTA composes once and then walks over column tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-constexpr int LASWP_COLS = 32, LASWP_THREADS = 256;
-constexpr size_t LASWP_SMEM = sizeof(double) * 2 * NB * LASWP_COLS;
-__global__ void __launch_bounds__(LASWP_THREADS) laswp_block_kernel(double* A, int64_t lda, int64_t sA, int c0, int ncols,
-                                                                    const int* ipiv, int n_ipiv, int k0, int k1) {
-  extern __shared__ __align__(16) double sm[];  // [nmov][LASWP_COLS]
-  __shared__ int s_piv[NB], cur_top[NB], out_row[NB], out_cur[NB], dst[2 * NB], src[2 * NB];
-  __shared__ int s_nmov;
-  const int nk = k1 - k0, tid = threadIdx.x;
-  const int* piv = ipiv + (int64_t)blockIdx.y * n_ipiv + k0;
-  for (int i = tid; i < nk; i += LASWP_THREADS) { s_piv[i] = piv[i]; cur_top[i] = k0 + i; }
-  __syncthreads();
-  if (tid < 32) {
-    const int lane = tid;
-    int nout = 0;  // warp-uniform
-    for (int k = 0; k < nk; ++k) {
-      const int p = s_piv[k];
-      if (p == k0 + k) continue;
-      if (p < k1) {
-        if (lane == 0) { const int t = cur_top[k]; cur_top[k] = cur_top[p - k0]; cur_top[p - k0] = t; }
-      } else {
-        int found = -1;
-        for (int base = 0; base < nout; base += 32) {
-          const int i = base + lane;
-          const unsigned m = __ballot_sync(0xffffffffu, i < nout && out_row[i] == p);
-          if (m) { found = base + __ffs(m) - 1; break; }
-        }
-        if (found < 0) {
-          found = nout++;
-          if (lane == 0) { out_row[found] = p; out_cur[found] = p; }
-        }
-        __syncwarp();
-        if (lane == 0) { const int t = cur_top[k]; cur_top[k] = out_cur[found]; out_cur[found] = t; }
-      }
-      __syncwarp();
-    }
-    int cnt = 0;
-    for (int base = 0; base < nk; base += 32) {
-      const int i = base + lane;
-      const bool mv = i < nk && cur_top[i] != k0 + i;
-      const unsigned m = __ballot_sync(0xffffffffu, mv);
-      if (mv) { const int pos = cnt + __popc(m & ((1u << lane) - 1u)); dst[pos] = k0 + i; src[pos] = cur_top[i]; }
-      cnt += __popc(m);
-    }
-    for (int base = 0; base < nout; base += 32) {
-      const int i = base + lane;
-      const bool mv = i < nout && out_cur[i] != out_row[i];
-      const unsigned m = __ballot_sync(0xffffffffu, mv);
-      if (mv) { const int pos = cnt + __popc(m & ((1u << lane) - 1u)); dst[pos] = out_row[i]; src[pos] = out_cur[i]; }
-      cnt += __popc(m);
-    }
-    if (lane == 0) s_nmov = cnt;
-  }
-  __syncthreads();
-  const int nmov = s_nmov;
-  if (nmov == 0) return;
-  const int tx = tid & 31, ty = tid >> 5;
-  const int ntiles = (ncols + LASWP_COLS - 1) / LASWP_COLS;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int col = t * LASWP_COLS + tx;
-    double* a = A + (int64_t)blockIdx.y * sA + c0 + col;
-    if (col < ncols)
-      for (int e = ty; e < nmov; e += LASWP_THREADS / 32) sm[e * LASWP_COLS + tx] = a[(int64_t)src[e] * lda];
-    __syncthreads();
-    if (col < ncols)
-      for (int e = ty; e < nmov; e += LASWP_THREADS / 32) a[(int64_t)dst[e] * lda] = sm[e * LASWP_COLS + tx];
-    __syncthreads();
-  }
-}
-
 // interchanges k0..k1-1 on columns [c0, c0 + ncols) of `batch` matrices sA apart (no profiling, no checks)
 inline void launch_laswp(cudaStream_t st, int batch, double* A, int64_t lda, int64_t sA, int c0, int ncols, const int* ipiv,
                          int n_ipiv, int k0, int k1) {
-  // Measured on B200 (gpurun_out/c18_bench_lu.txt): 87 us per call against 74 us for the serial kernel inside a
-  // factorisation (composition + 64 KB of shared memory next to the GEMM CTAs), so it is opt-in: HPS_LASWP=block.
-  static const bool block = [] { const char* e = std::getenv("HPS_LASWP"); return e && e[0] == 'b'; }();
-  if (k1 - k0 <= NB && block) {
-    const int ntiles = (ncols + LASWP_COLS - 1) / LASWP_COLS;
-    const int gx = std::max(1, std::min(ntiles, 888 / std::max(1, batch)));
-    laswp_block_kernel<<<dim3(gx, batch), LASWP_THREADS, LASWP_SMEM, st>>>(A, lda, sA, c0, ncols, ipiv, n_ipiv, k0, k1);
-  } else {
-    laswp_kernel<<<dim3((ncols + 255) / 256, batch), 256, 0, st>>>(A, lda, sA, c0, ncols, ipiv, n_ipiv, k0, k1);
-  }
+  // (A "composed" variant — the swaps of a block column merged into one move list and applied through shared memory —
+  // measured 87 us per call against 74 us for this kernel inside a factorisation, profiles/r02_laswp_block_vs_serial.txt;
+  // it lives in tools/lu_lab_kernels.cuh.  With unpivoted merge matrices the interchanges are no-ops anyway.)
+  laswp_kernel<<<dim3((ncols + 255) / 256, batch), 256, 0, st>>>(A, lda, sA, c0, ncols, ipiv, n_ipiv, k0, k1);
 }
 
 // X := L^-1 X for the unit-lower ib x ib block at A[jj,jj], X = A[jj:jj+ib, c0:c0+ncols)
@@ -1431,8 +1258,7 @@ int configure_lu_kernels() {
   DeviceState* ds = nullptr;
   HPS_TRY(device_state(ds));
   if (ds->lu_configured.load(std::memory_order_acquire)) return 0;  // idempotent: a race only repeats the calls
-    HPS_CUDA(cudaFuncSetAttribute(blockcol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc_smem_bytes(BC_ROWS)));
-    HPS_CUDA(cudaFuncSetAttribute(blockcol_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc_smem_bytes(BC_ROWS)));
+    HPS_CUDA(cudaFuncSetAttribute(blockcol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc_smem_bytes(BC_ROWS)));
     HPS_CUDA(cudaFuncSetAttribute(blockcol2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bc_smem_bytes(BC_ROWS)));
     HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(panel_kernel<SYNC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
@@ -1442,7 +1268,6 @@ int configure_lu_kernels() {
     HPS_CUDA(cudaFuncSetAttribute(trtri_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_PAIR_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(diagblk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
     HPS_CUDA(cudaFuncSetAttribute(diagblk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
-    HPS_CUDA(cudaFuncSetAttribute(laswp_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LASWP_SMEM));
   ds->lu_configured.store(true, std::memory_order_release);
   return 0;
 }
@@ -1474,19 +1299,16 @@ int launch_blockcol(cudaStream_t st, int batch, int n, double* A, int64_t lda, i
   a.A = A; a.lda = lda; a.sA = sA; a.n = n; a.j = j; a.jb = jb; a.G = G;
   a.rpc = (G == 1) ? rows : std::max(NB, (rows + G - 1) / G);
   a.ipiv = w.ipiv; a.info = info; a.scratch = w.bc_scratch; a.scratch_stride = w.bc_stride; a.Gcap = w.bc_Gcap;
-  a.rows_cap = 0;
   const size_t smem = bc_smem_bytes(a.rpc);
   if (G == 1) {
     prof_begin(PROF_PANEL, st, (double)batch * rows * jb);
-    blockcol_kernel<false><<<dim3(1, batch), BC_THREADS, smem, st>>>(a);
+    blockcol_kernel<<<dim3(1, batch), BC_THREADS, smem, st>>>(a);
     prof_end(PROF_PANEL, st);
     HPS_LAUNCH_CHECK("blockcol_kernel<single>");
     done = true;
     return 0;
   }
-  // HPS_BLOCKCOL=fenced selects the first-generation exchange (fence + header polled by one warp)
-  static const bool fenced = [] { const char* e = std::getenv("HPS_BLOCKCOL"); return e && e[0] == 'f'; }();
-  void (*shared_kernel)(BcArgs) = fenced ? blockcol_kernel<true> : blockcol2_kernel;
+  void (*shared_kernel)(BcArgs) = blockcol2_kernel;
   if (G <= 8) {  // one thread-block cluster per matrix: co-scheduled by the hardware
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G, batch);
@@ -1586,26 +1408,17 @@ int factor_block_column_spec(cudaStream_t st, int batch, int n, const Mat& A, in
                              bool in_block_pivoting, double bound) {
   const int nblk = (n + NB - 1) / NB;
   const int64_t sW = (int64_t)nblk * NB * NB;
-  static const bool smem_panel = [] { const char* e = std::getenv("HPS_DIAGBLK"); return e && e[0] == 's'; }();  // A/B switch
   static const bool force_pivot = [] { const char* e = std::getenv("HPS_DIAGBLK"); return e && e[0] == 'p'; }();
   const bool pivot_in_block = in_block_pivoting || force_pivot;
   prof_begin(PROF_PANEL, st, (double)batch * jb * jb);
-  if (smem_panel) {
-    BcArgs a;
-    a.A = A.p; a.lda = A.ld; a.sA = A.stride; a.n = n; a.j = j; a.jb = jb; a.G = 1; a.rpc = jb;
-    a.ipiv = w.ipiv; a.info = info; a.scratch = w.bc_scratch; a.scratch_stride = w.bc_stride; a.Gcap = w.bc_Gcap;
-    a.rows_cap = jb;
-    blockcol_kernel<false><<<dim3(1, batch), BC_THREADS, bc_smem_bytes(jb), st>>>(a);
-  } else {
-    for (int b0 = 0; b0 < batch; b0 += 65535) {
-      const int nb = std::min(65535, batch - b0);
-      if (pivot_in_block)
-        diagblk_kernel<true><<<nb, DB_THREADS, DB_SMEM, st>>>(A.p + (int64_t)b0 * A.stride, A.ld, A.stride, n, j, jb,
-                                                              w.ipiv + (int64_t)b0 * n, info + b0);
-      else
-        diagblk_kernel<false><<<nb, DB_THREADS, DB_SMEM, st>>>(A.p + (int64_t)b0 * A.stride, A.ld, A.stride, n, j, jb,
-                                                               w.ipiv + (int64_t)b0 * n, info + b0);
-    }
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    const int nb = std::min(65535, batch - b0);
+    if (pivot_in_block)
+      diagblk_kernel<true><<<nb, DB_THREADS, DB_SMEM, st>>>(A.p + (int64_t)b0 * A.stride, A.ld, A.stride, n, j, jb,
+                                                            w.ipiv + (int64_t)b0 * n, info + b0);
+    else
+      diagblk_kernel<false><<<nb, DB_THREADS, DB_SMEM, st>>>(A.p + (int64_t)b0 * A.stride, A.ld, A.stride, n, j, jb,
+                                                             w.ipiv + (int64_t)b0 * n, info + b0);
   }
   prof_end(PROF_PANEL, st);
   HPS_LAUNCH_CHECK("diagonal block LU");
