@@ -355,3 +355,24 @@ def solve_vjp(pde_problem, u, u_bar, compute_device=None, host_device=None) -> D
         for name in _present(pde_problem):
             out[f"{name}_coefficients"] = -(f_bar * apply_diff_operator(pde_problem, name, u3)).sum(dim=-1)
         return {k: _lib.to_result(v, host_device) for k, v in out.items()}
+
+
+def scattering_forward_jvp(pde_problem, R_top, source, d_coefficients: Dict, S, D, source_dirs, k: float, d_source=None,
+                           compute_device=None, host_device=None):
+    """Tangent of the reference's inverse-scattering forward model (`examples/inverse_scattering_utils.py:110-171`):
+    coefficients -> root ItI operator ``R`` -> ``T = get_DtN_from_ItI(R)`` -> incoming impedance data of the scattered
+    field (BIE coupling with the layer potentials ``S``, ``D``) -> ``u = solve(pde_problem, imp, source=source)``.
+    Returns ``(u, du)``.  ``R_top``: what ``build_solver(pde_problem, return_top_T=True)`` returned (no-source build)."""
+    from . import scattering as sc
+
+    _check(pde_problem)
+    if not pde_problem.use_ItI:
+        raise ValueError("the scattering coupling is formulated for ItI problems")
+    dev = _lib.require_cuda(compute_device)
+    eta = pde_problem.eta
+    dR = top_T_jvp(pde_problem, d_coefficients, compute_device=dev, host_device=dev)
+    T, dT = sc.get_DtN_from_ItI_jvp(R_top, dR, eta, device=dev, host_device=dev)
+    imp, dimp = sc.get_scattering_uscat_impedance_jvp(S, D, T, dT, source_dirs, pde_problem.domain.boundary_points, k, eta,
+                                                      device=dev, host_device=dev)
+    return solve_jvp(pde_problem, imp, source, d_source=d_source, d_boundary_data=dimp, d_coefficients=d_coefficients,
+                     compute_device=dev, host_device=host_device)

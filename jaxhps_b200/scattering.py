@@ -117,3 +117,44 @@ def get_scattering_uscat_impedance(S, D, T, source_dirs, bdry_pts, k: float, eta
         uscat = _zsolve(A, b, dev)
         uscat_dn = _zmm(Td, uscat + uin_d, dev) - dn_d
         return _lib.to_result(uscat_dn + 1j * eta * uscat, host_device)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Tangents of the two coupling steps: together with ``adjoint.top_T_jvp`` and ``adjoint.solve_jvp`` they give the
+# directional derivative of the reference's whole inverse-scattering forward model (coefficients -> root ItI operator
+# -> DtN -> incoming impedance data -> solution; `examples/inverse_scattering_utils.py:110-171`), which the reference
+# obtains from ``jax.jvp``.  Same device algebra as above (``hps_zgesv`` / ``hps_zgemm_strided_batched``).
+
+
+def get_DtN_from_ItI_jvp(R, dR, eta: float, device=None, host_device=None):
+    """``(T, dT)`` for ``T = -i eta (R - I)^-1 (R + I)``:  ``dT = -(R - I)^-1 dR (T + i eta I)``."""
+    dev = _lib.require_cuda(device)
+    with torch.cuda.device(dev):
+        Rd, dRd = _dev_c(R, dev), _dev_c(dR, dev)
+        n = Rd.shape[0]
+        eye = torch.eye(n, dtype=_C, device=dev)
+        T = _zsolve(Rd - eye, Rd + eye, dev)
+        T.mul_(-1j * eta)
+        dT = _zsolve(Rd - eye, _zmm(dRd, T + 1j * eta * eye, dev), dev)
+        dT.neg_()
+        return _lib.to_result(T, host_device), _lib.to_result(dT, host_device)
+
+
+def get_scattering_uscat_impedance_jvp(S, D, T, dT, source_dirs, bdry_pts, k: float, eta: float, device=None, host_device=None):
+    """``(imp, d imp)`` of :func:`get_scattering_uscat_impedance` for a tangent ``dT`` of the interior DtN map:
+    with ``A = I/2 - D + S T``, ``u = A^-1 S (dn u_in - T u_in)``:
+    ``du = -A^-1 S dT (u + u_in)``, ``d(du/dn) = dT (u + u_in) + T du``, ``d imp = d(du/dn) + i eta du``."""
+    dev = _lib.require_cuda(device)
+    with torch.cuda.device(dev):
+        Sd, Td, dTd = _dev_c(S, dev), _dev_c(T, dev), _dev_c(dT, dev)
+        A, b = setup_scattering_lin_system(Sd, D, Td, bdry_pts, k, source_dirs, device=dev, host_device=dev)
+        uin, uin_dn = get_uin_and_normals(k, bdry_pts, source_dirs)
+        uin_d, dn_d = _dev_c(uin, dev), _dev_c(uin_dn, dev)
+        uscat = _zsolve(A, b, dev)
+        tot = uscat + uin_d
+        imp = _zmm(Td, tot, dev) - dn_d + 1j * eta * uscat
+        dT_tot = _zmm(dTd, tot, dev)
+        du = _zsolve(A, _zmm(Sd, dT_tot, dev), dev)
+        du.neg_()
+        dimp = dT_tot + _zmm(Td, du, dev) + 1j * eta * du
+        return _lib.to_result(imp, host_device), _lib.to_result(dimp, host_device)

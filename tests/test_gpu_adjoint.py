@@ -92,3 +92,39 @@ def test_top_operator_tangent_matches_finite_differences_of_the_oracle(iti):
     hps.build_solver(pb)
     dT = adjoint.top_T_jvp(pb, d, chunk=17)
     assert dT.shape == fd.shape and _rel(dT, fd) < 1e-6
+
+
+def test_inverse_scattering_forward_model_tangent_matches_finite_differences():
+    """The whole chain of the reference's inverse-scattering example (`examples/inverse_scattering_utils.py:110-171`):
+    q -> (I coefficient, source) -> build (root ItI operator) -> DtN -> BIE coupling -> incoming impedance -> solve.
+    Tangent from `adjoint.scattering_forward_jvp` against a central difference of the same chain run on the GPU."""
+    from jaxhps_b200 import scattering as sc
+
+    rng = np.random.default_rng(61)
+    k = 4.0
+    dom = hps.Domain(8, 6, hps.DiscretizationNode2D(-1.0, 1.0, -1.0, 1.0), 2)
+    pts = dom.interior_points
+    shp = pts[..., 0].shape
+    n_b = dom.boundary_points.shape[0]
+    S = 0.2 * (rng.normal(size=(n_b, n_b)) + 1j * rng.normal(size=(n_b, n_b))) / np.sqrt(n_b)
+    D = 0.2 * (rng.normal(size=(n_b, n_b)) + 1j * rng.normal(size=(n_b, n_b))) / np.sqrt(n_b)
+    dirs = np.array([0.4])
+    uin = sc.get_uin(k, pts.reshape(-1, 2), dirs).reshape(shp)
+    q0 = 0.5 * np.exp(-((pts[..., 0] - 0.2) ** 2 + (pts[..., 1] + 0.1) ** 2) / 0.15**2)
+    dq = rng.normal(size=shp)
+
+    def forward(q):
+        pb = hps.PDEProblem(dom, D_xx_coefficients=np.ones(shp), D_yy_coefficients=np.ones(shp),
+                            I_coefficients=k**2 * (1 + q), use_ItI=True, eta=k)
+        R = hps.build_solver(pb, return_top_T=True)
+        T = sc.get_DtN_from_ItI(R, k)
+        imp = sc.get_scattering_uscat_impedance(S, D, T, dirs, dom.boundary_points, k, k)
+        src = -(k**2) * q * uin
+        return pb, R, src, hps.solve(pb, imp[:, 0], source=src)
+
+    pb, R, src, u = forward(q0)
+    u_j, du = adjoint.scattering_forward_jvp(pb, R, src, {"I_coefficients": k**2 * dq}, S, D, dirs, k, d_source=-(k**2) * dq * uin)
+    assert _rel(u_j, u) < 1e-10
+    eps = 1e-6
+    fd = (forward(q0 + eps * dq)[3] - forward(q0 - eps * dq)[3]) / (2 * eps)
+    assert du.shape == fd.shape and _rel(du, fd) < 1e-6
