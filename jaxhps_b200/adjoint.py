@@ -287,6 +287,58 @@ def _gemv_t(A: torch.Tensor, X: torch.Tensor, sA_shared: bool = False) -> torch.
 # ------------------------------------------------------------------------------------------------ vjp
 
 
+def _up_pass_T(pde_problem, gt_bars, h_top_bar, v_bar_leaf, dev) -> torch.Tensor:
+    """The up pass run backwards (root -> leaves) with transposed operators: cotangents ``gt_bars[level]`` of the
+    particular interface data g~ of every level (or None), ``h_top_bar`` of the root's outgoing data ``h_last``
+    ((n_bdry, n_src) or None) and ``v_bar_leaf`` of the leaves' particular solution v ((n_leaves, p^2, n_src) or None)
+    -> cotangent of the source, (n_leaves, p^2, n_src), zero on the boundary rows."""
+    iti = bool(pde_problem.use_ItI)
+    dt = _cdt(pde_problem)
+    dom = pde_problem.domain
+    p = dom.p
+    n_c, n_i = p * p, (p - 2) ** 2
+    n_b = n_c - n_i
+    up_map, _ = _plumbing(iti, dev)
+    n_levels = len(pde_problem.D_inv_lst)
+    n_src = next(x.shape[-1] for x in ([h_top_bar, v_bar_leaf] + list(gt_bars or [])) if x is not None)
+    h_bar = None if h_top_bar is None else h_top_bar.reshape(1, -1, n_src)
+    for level in range(n_levels - 1, -1, -1):
+        D_inv = _lib.to_device(pde_problem.D_inv_lst[level], dev, dtype=dt)
+        BD_inv = _lib.to_device(pde_problem.BD_inv_lst[level], dev, dtype=dt)
+        n_nodes, n_int, _ = D_inv.shape
+        n_ext = BD_inv.shape[1]
+        m = n_ext // 8
+        h_int_bar = torch.zeros((n_nodes, n_int, n_src), dtype=dt, device=dev)
+        if gt_bars is not None:
+            gi = gt_bars[level]
+            if iti:  # forward: g~ = (-D^-1 h_int)[perm]  ->  the cotangent goes back to the solve order
+                perm = _block_perm(_SOLVE_POS_OF_OUT, m, dev)
+                gs = torch.zeros_like(gi)
+                gs.index_copy_(1, perm, gi)
+                gi = gs
+            h_int_bar = -_gemv_t(D_inv, gi)
+        if h_bar is not None:
+            h_new_bar = torch.roll(h_bar, shifts=m, dims=1).contiguous()   # forward: h = roll(h_new, -m)
+            h_int_bar = h_int_bar - _gemv_t(BD_inv, h_new_bar)
+        else:
+            h_new_bar = torch.zeros((n_nodes, n_ext, n_src), dtype=dt, device=dev)
+        h_bar = up_map.apply_T(torch.cat([h_int_bar, h_new_bar], dim=1), m).reshape(n_nodes * 4, 4 * m, n_src)
+    # ---- leaves: v_bar = (direct) + Q^T h_bar, f_bar = Phi^T v_bar
+    Qm = _lib.to_device(pde_problem.QH if iti else pde_problem.Q, dev, dtype=dt)
+    v_bar = _gemv_t(Qm, h_bar, sA_shared=True)
+    if v_bar_leaf is not None:
+        v_bar = v_bar + v_bar_leaf
+    Phi = _lib.to_device(pde_problem.Phi, dev, dtype=dt)
+    f_bar = torch.zeros_like(v_bar)
+    if iti:
+        f_bar[:, n_b:, :] = _gemv_t(Phi, v_bar)               # Phi (n, n_c, n_i)
+    else:
+        f_bar[:, n_b:, :] = _gemv_t(Phi, v_bar[:, n_b:, :].contiguous())
+    return f_bar
+
+
+
+
 def solve_vjp(pde_problem, u, u_bar, compute_device=None, host_device=None) -> Dict:
     """Cotangents of ``u = solve(pde_problem, g, source=f)``: for any tangents ``(df, dg, dc)``,
     ``sum(u_bar * du) == sum(source_bar * df) + sum(boundary_bar * dg) + sum_k sum(c_k_bar * dc_k)`` (bilinear pairing,
@@ -321,36 +373,7 @@ def solve_vjp(pde_problem, u, u_bar, compute_device=None, host_device=None) -> D
             gt_bars.append(gi)
             g_bar = ge + _gemv_t(S, gi)
         boundary_bar = g_bar[0]                                   # (n_bdry, n_src)
-        # ---- transposed up pass: root -> leaves
-        h_bar = None
-        for level in range(len(S_lst) - 1, -1, -1):
-            D_inv = _lib.to_device(pde_problem.D_inv_lst[level], dev, dtype=dt)
-            BD_inv = _lib.to_device(pde_problem.BD_inv_lst[level], dev, dtype=dt)
-            n_nodes, n_int, _ = D_inv.shape
-            n_ext = BD_inv.shape[1]
-            m = n_ext // 8
-            gi = gt_bars[level]
-            if iti:  # forward: g~ = (-D^-1 h_int)[perm]  ->  the cotangent goes back to the solve order
-                perm = _block_perm(_SOLVE_POS_OF_OUT, m, dev)
-                gs = torch.zeros_like(gi)
-                gs.index_copy_(1, perm, gi)
-                gi = gs
-            h_int_bar = -_gemv_t(D_inv, gi)
-            if h_bar is not None:
-                h_new_bar = torch.roll(h_bar, shifts=m, dims=1).contiguous()   # forward: h = roll(h_new, -m)
-                h_int_bar = h_int_bar - _gemv_t(BD_inv, h_new_bar)
-            else:
-                h_new_bar = torch.zeros((n_nodes, n_ext, n_src), dtype=dt, device=dev)
-            h_bar = up_map.apply_T(torch.cat([h_int_bar, h_new_bar], dim=1), m).reshape(n_nodes * 4, 4 * m, n_src)
-        # ---- leaves: v_bar = w + Q^T h_bar, f_bar = Phi^T v_bar
-        Qm = _lib.to_device(pde_problem.QH if iti else pde_problem.Q, dev, dtype=dt)
-        v_bar = w + _gemv_t(Qm, h_bar, sA_shared=True)
-        Phi = _lib.to_device(pde_problem.Phi, dev, dtype=dt)
-        f_bar = torch.zeros_like(w)
-        if iti:
-            f_bar[:, n_b:, :] = _gemv_t(Phi, v_bar)               # Phi (n, n_c, n_i)
-        else:
-            f_bar[:, n_b:, :] = _gemv_t(Phi, v_bar[:, n_b:, :].contiguous())
+        f_bar = _up_pass_T(pde_problem, gt_bars, None, w, dev)
         out = {"source": f_bar[..., 0] if single else f_bar, "boundary_data": boundary_bar[..., 0] if single else boundary_bar}
         for name in _present(pde_problem):
             out[f"{name}_coefficients"] = -(f_bar * apply_diff_operator(pde_problem, name, u3)).sum(dim=-1)
@@ -376,3 +399,57 @@ def scattering_forward_jvp(pde_problem, R_top, source, d_coefficients: Dict, S, 
                                                       device=dev, host_device=dev)
     return solve_jvp(pde_problem, imp, source, d_source=d_source, d_boundary_data=dimp, d_coefficients=d_coefficients,
                      compute_device=dev, host_device=host_device)
+
+
+def top_T_vjp(pde_problem, T_bar, chunk: int = 256, compute_device=None, host_device=None) -> Dict:
+    """Cotangents of the coefficient fields for a cotangent ``T_bar`` (n_bdry, n_bdry) of the top-level operator:
+    ``sum(T_bar * dT) == sum_k sum(c_k_bar * dc_k)`` with ``dT = top_T_jvp(dc)``.  Column j of ``dT`` is the up pass'
+    ``h_last`` for the source ``-sum_k dc_k D_k u_j``, so ``c_k_bar = -sum_j (H^T T_bar[:, j]) . (D_k u_j)`` with ``H^T`` the
+    transposed up pass (:func:`_up_pass_T`) — per chunk of boundary unknowns one multi-source down pass and one transposed
+    up pass."""
+    _check(pde_problem)
+    dev = _lib.require_cuda(compute_device)
+    dt = _cdt(pde_problem)
+    dom = pde_problem.domain
+    n_b = dom.boundary_points.shape[0]
+    n_leaves, n_c = dom.interior_points.shape[0], dom.p ** 2
+    with torch.cuda.device(dev):
+        Tb = _lib.to_device(T_bar, dev, dtype=dt)
+        names = _present(pde_problem)
+        bars = {name: torch.zeros((n_leaves, n_c), dtype=dt, device=dev) for name in names}
+        for j0 in range(0, n_b, chunk):
+            j1 = min(n_b, j0 + chunk)
+            E = torch.zeros((n_b, j1 - j0), dtype=dt, device=dev)
+            E[torch.arange(j0, j1, device=dev), torch.arange(j1 - j0, device=dev)] = 1
+            zero = torch.zeros((n_leaves, n_c, j1 - j0), dtype=dt, device=dev)
+            U = _lib.to_device(solve(pde_problem, E, source=zero, compute_device=dev, host_device=dev), dev, dtype=dt)
+            lam = _up_pass_T(pde_problem, None, Tb[:, j0:j1].contiguous(), None, dev)
+            for name in names:
+                bars[name] -= (lam * apply_diff_operator(pde_problem, name, U)).sum(dim=-1)
+        return {f"{k}_coefficients": _lib.to_result(v, host_device) for k, v in bars.items()}
+
+
+def scattering_forward_vjp(pde_problem, R_top, source, u, u_bar, S, D, source_dirs, k: float, compute_device=None,
+                           host_device=None) -> Dict:
+    """Cotangents of ``(source, coefficient fields)`` for the reference's inverse-scattering forward model (see
+    :func:`scattering_forward_jvp`): ``sum(u_bar * du) == sum(source_bar * d_source) + sum_k sum(c_k_bar * dc_k)``.
+    The solve's own adjoint gives the direct part and the cotangent of the incoming impedance data; that is pulled back
+    through the BIE coupling (two transposed dense solves), the ItI -> DtN conversion and the top-level operator."""
+    from . import scattering as sc
+
+    _check(pde_problem)
+    dev = _lib.require_cuda(compute_device)
+    eta = pde_problem.eta
+    with torch.cuda.device(dev):
+        bars = solve_vjp(pde_problem, u, u_bar, compute_device=dev, host_device=dev)
+        imp_bar = bars.pop("boundary_data")
+        imp_bar = imp_bar.reshape(imp_bar.shape[0], -1)
+        T_bar = sc.get_scattering_uscat_impedance_vjp(S, D, sc.get_DtN_from_ItI(R_top, eta, device=dev, host_device=dev), imp_bar,
+                                                      source_dirs, pde_problem.domain.boundary_points, k, eta, device=dev,
+                                                      host_device=dev)
+        R_bar = sc.get_DtN_from_ItI_vjp(R_top, T_bar, eta, device=dev, host_device=dev)
+        top = top_T_vjp(pde_problem, R_bar, compute_device=dev, host_device=dev)
+        out = {"source": bars["source"]}
+        for key, v in top.items():
+            out[key] = bars[key] + v
+        return {k2: _lib.to_result(v, host_device) for k2, v in out.items()}

@@ -158,3 +158,39 @@ def get_scattering_uscat_impedance_jvp(S, D, T, dT, source_dirs, bdry_pts, k: fl
         du.neg_()
         dimp = dT_tot + _zmm(Td, du, dev) + 1j * eta * du
         return _lib.to_result(imp, host_device), _lib.to_result(dimp, host_device)
+
+
+def get_DtN_from_ItI_vjp(R, T_bar, eta: float, device=None, host_device=None):
+    """Cotangent of ``R`` for a cotangent ``T_bar`` of ``T = get_DtN_from_ItI(R)`` (plain transposes, no conjugation):
+    ``dT = -(R - I)^-1 dR (T + i eta I)``  =>  ``R_bar = -(R - I)^-T T_bar (T + i eta I)^T``."""
+    dev = _lib.require_cuda(device)
+    with torch.cuda.device(dev):
+        Rd, Tb = _dev_c(R, dev), _dev_c(T_bar, dev)
+        n = Rd.shape[0]
+        eye = torch.eye(n, dtype=_C, device=dev)
+        T = _zsolve(Rd - eye, Rd + eye, dev)
+        T.mul_(-1j * eta)
+        X = _zmm(Tb, (T + 1j * eta * eye).T.contiguous(), dev)
+        R_bar = _zsolve((Rd - eye).T.contiguous(), X, dev)
+        R_bar.neg_()
+        return _lib.to_result(R_bar, host_device)
+
+
+def get_scattering_uscat_impedance_vjp(S, D, T, imp_bar, source_dirs, bdry_pts, k: float, eta: float, device=None,
+                                       host_device=None):
+    """Cotangent of the interior DtN map ``T`` for a cotangent ``imp_bar`` (n, n_src) of
+    :func:`get_scattering_uscat_impedance`: with ``b_bar = A^-T (T^T imp_bar + i eta imp_bar)``,
+    ``T_bar = (imp_bar - S^T b_bar) (u + u_in)^T``."""
+    dev = _lib.require_cuda(device)
+    with torch.cuda.device(dev):
+        Sd, Td, ib = _dev_c(S, dev), _dev_c(T, dev), _dev_c(imp_bar, dev)
+        A, b = setup_scattering_lin_system(Sd, D, Td, bdry_pts, k, source_dirs, device=dev, host_device=dev)
+        uin, _ = get_uin_and_normals(k, bdry_pts, source_dirs)
+        uin_d = _dev_c(uin, dev)
+        uscat = _zsolve(A, b, dev)
+        tot = uscat + uin_d
+        us_bar = _zmm(Td.T.contiguous(), ib, dev) + 1j * eta * ib
+        b_bar = _zsolve(A.T.contiguous(), us_bar, dev)
+        left = ib - _zmm(Sd.T.contiguous(), b_bar, dev)
+        T_bar = _zmm(left, tot.T.contiguous(), dev)
+        return _lib.to_result(T_bar, host_device)

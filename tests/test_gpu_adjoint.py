@@ -128,3 +128,14 @@ def test_inverse_scattering_forward_model_tangent_matches_finite_differences():
     eps = 1e-6
     fd = (forward(q0 + eps * dq)[3] - forward(q0 - eps * dq)[3]) / (2 * eps)
     assert du.shape == fd.shape and _rel(du, fd) < 1e-6
+    # adjoint of the same chain: <u_bar, du> == <source_bar, d_source> + <I_bar, dI>
+    w = rng.normal(size=u.shape) + 1j * rng.normal(size=u.shape)
+    bars = adjoint.scattering_forward_vjp(pb, R, src, u, w, S, D, dirs, k)
+    lhs = np.sum(w * du)
+    rhs = np.sum(bars["source"] * (-(k**2) * dq * uin)) + np.sum(bars["I_coefficients"] * (k**2 * dq))
+    assert abs(lhs - rhs) < 1e-9 * max(1.0, abs(lhs)), (lhs, rhs)
+    # and of the top-level operator alone
+    Rb = rng.normal(size=np.asarray(R).shape) + 1j * rng.normal(size=np.asarray(R).shape)
+    dR = adjoint.top_T_jvp(pb, {"I_coefficients": k**2 * dq}, chunk=19)
+    cb = adjoint.top_T_vjp(pb, Rb, chunk=23)
+    assert abs(np.sum(Rb * dR) - np.sum(cb["I_coefficients"] * (k**2 * dq))) < 1e-9 * max(1.0, abs(np.sum(Rb * dR)))
