@@ -181,7 +181,7 @@ def to_device(x, dev: torch.device, dtype=torch.float64) -> torch.Tensor:
                              "sources and boundary data are supported on the ItI path only")
         t = t.to(dtype)
     if t.device != dev:
-        if t.device.type == "cpu" and t.numel() > 1 << 16:
+        if t.device.type == "cpu" and t.numel() > 1 << 16 and not t.is_pinned():
             t = t.contiguous().pin_memory()
         t = t.to(dev, non_blocking=True)
     return t.contiguous()
@@ -190,7 +190,17 @@ def to_device(x, dev: torch.device, dtype=torch.float64) -> torch.Tensor:
 def to_result(t: torch.Tensor, host_device):
     """Device tensor -> what the caller asked for (NumPy on the host, or the tensor itself)."""
     if is_host(host_device):
-        return t.cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+        if not isinstance(t, torch.Tensor):
+            return np.asarray(t)
+        if t.is_cuda and t.numel() * t.element_size() >= PINNED_RESULT_MIN_BYTES:
+            # large operators (Y, S_lst: GBs) land in page-locked host memory: the copy runs at PCIe speed instead of
+            # the pageable rate, and `to_device` recognises the array as pinned when `solve` brings it back (the blocks
+            # are recycled by torch's pinned-memory cache from one build to the next)
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(t.device).synchronize()
+            return buf.numpy()
+        return t.cpu().numpy()
     dev = torch.device(host_device)
     if dev.type == "cuda" and dev.index is None:
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -198,6 +208,9 @@ def to_result(t: torch.Tensor, host_device):
         return to_device(t, dev)
     return t if t.device == dev else t.to(dev)
 
+
+#: results at least this large are returned to the host through page-locked memory (see `to_result`)
+PINNED_RESULT_MIN_BYTES = 8 << 20
 
 #: most matrices / merges / nodes one C-ABI call accepts (CUDA grid-dimension limit)
 MAX_BATCH = 65535

@@ -106,3 +106,32 @@ def test_lu_reports_exact_singularity():
     b = torch.ones(2, 40, 1, dtype=torch.float64, device=dev)
     info = _lu_solve(A, [b])
     assert info.tolist() == [0, 18]
+
+
+@pytest.mark.parametrize(
+    "M,K,N,batch,alpha,beta,cplx",
+    [
+        (256, 56, 1, 64, 1.0, 0.0, False),     # Y^T w on many leaves
+        (56, 256, 2, 64, 1.0, 0.0, True),      # QH^T h (complex, shared operator is covered by the adjoint tests)
+        (2000, 300, 3, 1, -1.0, 0.0, False),   # few CTAs: the rows are split and summed atomically
+        (2000, 300, 3, 1, 0.5, 2.0, True),     # ... with beta and complex entries
+        (777, 129, 11, 2, 1.0, 1.0, False),    # more than 8 right-hand sides: two column groups
+        (0, 5, 1, 1, 1.0, 0.0, False),         # empty
+    ],
+)
+def test_transposed_matvec_matches_fp64_reference(M, K, N, batch, alpha, beta, cplx):
+    """``hps_gemv_t_strided_batched``: C = alpha A^T X + beta C (plain transpose for complex128), through the raw C ABI."""
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    dt = torch.complex128 if cplx else torch.float64
+    g = torch.Generator().manual_seed(M + 3 * K + 7 * N)
+    A = torch.randn(batch, M, K, dtype=dt, generator=g).to(dev)
+    X = torch.randn(batch, M, N, dtype=dt, generator=g).to(dev)
+    C = torch.randn(batch, K, N, dtype=dt, generator=g).to(dev)
+    ref = alpha * torch.matmul(A.transpose(1, 2), X) + beta * C
+    rc = lib.hps_gemv_t_strided_batched(_lib.stream_ptr(), M, K, N, alpha, A.data_ptr(), K, M * K, X.data_ptr(), N, M * N, beta,
+                                        C.data_ptr(), N, K * N, batch, 1 if cplx else 0)
+    _lib.check(rc, "hps_gemv_t_strided_batched")
+    torch.cuda.synchronize()
+    if M:
+        assert _rel(C, ref) < 1e-13
