@@ -38,7 +38,8 @@ sys.path.insert(0, ROOT)
 
 P, Q = 12, 10
 HBM_FALLBACK_GBPS = 6650.0  # B200_PROFILING.md fallback, used only when MEASURED_PEAKS.json is absent
-PROF_NAMES = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny_matvec", "leaf_assemble", "p2p_send"]
+PROF_NAMES = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny_matvec", "leaf_assemble", "p2p_send",
+              "wait_block", "panel_unsort"]
 
 
 def u_exact(x):
@@ -617,6 +618,7 @@ def run_ours(args, rank, world, local_rank):
                      "hbm_kernels": {"skinny_matvec_GBps": (pw[6] / (pm[6] * 1e-3) * 1e-9) if pm[6] > 0 else None,
                                      "merge_gather_GBps": (pw[5] / (pm[5] * 1e-3) * 1e-9) if pm[5] > 0 else None,
                                      "leaf_assemble_GBps": (pw[7] / (pm[7] * 1e-3) * 1e-9) if pm[7] > 0 else None,
+                                     "panel_unsort_GBps": (pw[10] / (pm[10] * 1e-3) * 1e-9) if pm[10] > 0 else None,
                                      "hbm_peak_GBps": hbm_gbps, "hbm_peak_source": hbm_src}},
         "cpu_baseline": cpu_baseline,
         "wall_s_timed_region": wall,

@@ -42,9 +42,10 @@ const char* hps_last_error_string(void);
  * the library issued since the reset.  Categories: 0 DMMA GEMM (work = flops), 1 LU panel,
  * 2 triangular-block inversion, 3 row interchanges, 4 inner 32x32 solves, 5 merge gather/scatter
  * (work = bytes read + written), 6 narrow-N mat-vec kernel (bytes read), 7 leaf assembly (bytes written),
- * 8 peer-to-peer block-column sends of the distributed factorisation (bytes sent).
- * ms/work/launches: HOST arrays of length HPS_PROF_NCAT = 9. */
-#define HPS_PROF_NCAT 9
+ * 8 peer-to-peer block-column sends of the distributed factorisation (bytes sent), 9 waits for a peer's block column,
+ * 10 in-place return of the S column panels from the solve order to the face order (bytes read + written).
+ * ms/work/launches: HOST arrays of length HPS_PROF_NCAT = 11. */
+#define HPS_PROF_NCAT 11
 int hps_prof_enable(int on);
 int hps_prof_read(void* stream, double* ms, double* work, int64_t* launches, int64_t* all_launches);
 /* per-launch timeline of the recording (ms relative to the first record; stream_id numbers the streams in order of

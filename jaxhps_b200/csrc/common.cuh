@@ -56,7 +56,7 @@ int aux_for_stream(cudaStream_t st, Aux*& out);  // created on first use
 // Optional per-category device timing (CUDA events on the launching stream), used by bench.py
 // for the roofline of the dominant kernels.  Off by default: zero overhead on the product path.
 enum ProfCat { PROF_GEMM = 0, PROF_PANEL = 1, PROF_TRTRI = 2, PROF_LASWP = 3, PROF_INNER = 4, PROF_GATHER = 5,
-               PROF_SKINNY = 6, PROF_ASSEMBLE = 7, PROF_COMM = 8, PROF_WAIT = 9, PROF_NCAT = 10 };
+               PROF_SKINNY = 6, PROF_ASSEMBLE = 7, PROF_COMM = 8, PROF_WAIT = 9, PROF_UNSORT = 10, PROF_NCAT = 11 };
 void prof_begin(int cat, cudaStream_t st, double work);
 void prof_end(int cat, cudaStream_t st);
 void prof_dims(int cat, int a, int b, int c, int d);  // optional shape note on the open record (GEMM: M, N, K, batch)

@@ -512,7 +512,11 @@ int unsort_panels(const Topo& tp, cudaStream_t st, int m, double* S, int64_t ld,
   if (pc.n_cyc == 0 || rows <= 0) return 0;
   const int chunks = (m + CYC_CHUNK - 1) / CYC_CHUNK;
   dim3 grid(pc.n_cyc * chunks, (unsigned)std::min<int64_t>(rows, 65535));
+  int moved = 0;  // panels that change place: each is read once and written once
+  for (int e = 0; e < tp.n_ext; ++e) moved += tp.ext_pos[e] != e;
+  prof_begin(PROF_UNSORT, st, 16.0 * (double)rows * moved * m);
   panel_cycle_kernel<<<grid, 256, 0, st>>>(pc, m, chunks, S, ld, rows);
+  prof_end(PROF_UNSORT, st);
   HPS_LAUNCH_CHECK("panel_cycle_kernel");
   return 0;
 }

@@ -25,7 +25,7 @@ A0 += 4.0 * n**0.5 * torch.eye(n, dtype=torch.float64, device=dev)  # like the m
 B0 = torch.randn(n, ncols, dtype=torch.float64, device=dev)
 comm = _dist.P2PComm.get(_lib, dev, rank, world, None)
 comm.ensure(comm.lu_segment_bytes(n))
-names = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny", "assemble", "p2p_send", "wait_block"]
+names = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny", "assemble", "p2p_send", "wait_block", "panel_unsort"]
 for it in range(reps + 1):
     B = B0.clone()
     _dist._copy_into_segment(comm.matrix_ptr(n), A0)

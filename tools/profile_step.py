@@ -30,7 +30,7 @@ cat, sid, dims = (ctypes.c_int * cap)(), (ctypes.c_int * cap)(), (ctypes.c_int *
 n = ctypes.c_int64()
 lib.hps_prof_timeline(t0, t1, wk, cat, sid, dims, cap, ctypes.byref(n))
 lib.hps_prof_enable(0)
-names = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny", "assemble", "p2p_send", "wait_block"]
+names = ["gemm", "lu_panel", "trtri", "laswp", "inner_trsm", "merge_gather", "skinny", "assemble", "p2p_send", "wait_block", "panel_unsort"]
 N = n.value
 out = []
 span = max(t1[i] for i in range(N)) - min(t0[i] for i in range(N))
