@@ -120,7 +120,7 @@ def _worker(rank, world, port, p, q, L, nsrc, seed, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,p,q,L,nsrc", [(2, 4, 2, 2, 1), (4, 4, 2, 1, 1), (2, 4, 2, 2, 2)])
+@pytest.mark.parametrize("world,p,q,L,nsrc", [(2, 4, 2, 2, 1), (4, 4, 2, 1, 1), (2, 4, 2, 2, 2), (8, 4, 2, 2, 1)])
 def test_sharded_build_and_solve_matches_single_process(tmp_path, world, p, q, L, nsrc):
     seed = 40 + world
     port = _free_port()
