@@ -528,6 +528,19 @@ def run_ours(args, rank, world, local_rank):
                        "resident_leaves_per_s": 8 / (ms_1r / 10 * 1e-3), "e2e_ms_per_step": ms_1 / 10}
         del R1
 
+    # ---- the other BASELINE configs (1, 2, 4, 5) through the public API, single GPU, after everything timed above ----
+    other_configs = None
+    if world == 1 and args.other_configs:
+        try:
+            del R
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import other_configs as oc
+
+            other_configs = oc.run_all(hps)
+        except Exception as e:  # noqa: BLE001
+            other_configs = {"unavailable": repr(e)[:300]}
+
     # ---- BASELINE's target size on 8 GPUs: L=4, 4096 leaves ----
     target_L4 = None
     if world == 8 and args.target_L4 and L != 4:
@@ -602,6 +615,7 @@ def run_ours(args, rank, world, local_rank):
         "factored_root": factored,
         "same_config_sample": same_sample,
         "target_L4": target_L4,
+        "other_configs": other_configs,
         "gpu_launches": launches_timed,
         "roofline": {"kernel": "hps::gemmk::gemm_kernel_hoist (DMMA m8n8k4 FP64)", "bound": "tensor", "achieved": achieved,
                      "peak": fp64_sustained, "unit": "TFLOP/s", "frac": achieved / fp64_sustained,
@@ -637,6 +651,8 @@ def main():
                     help="with 8 ranks: also time BASELINE's target size L=4 (1 warm-up + 2 steps) and embed it")
     ap.add_argument("--factored", type=int, default=1,
                     help="also time the opt-in factored-root (S-free) mode of the sharded driver")
+    ap.add_argument("--other-configs", dest="other_configs", type=int, default=1,
+                    help="single GPU: also run BASELINE configs 1, 2, 4 and 5 once (about 15 s) and embed their numbers")
     ap.add_argument("--host-resident", dest="host_resident", type=int, default=1,
                     help="single GPU: also time one step with the reference-default host_device='cpu'")
     args = ap.parse_args()
