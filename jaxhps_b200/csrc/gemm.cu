@@ -4,6 +4,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include <type_traits>
 #include "gemm_kernel.cuh"
 
 namespace hps {
@@ -130,6 +131,8 @@ __device__ __forceinline__ void e_atomic_add(double* p, double v) { atomicAdd(p,
 __device__ __forceinline__ void e_atomic_add(double2* p, double2 v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
 
 constexpr int GT_NMAX = 8;
+constexpr int GT_UNROLL = 8;
+constexpr int GT_TARGET_CTAS = 148 * 8 * 8;  // 8 CTAs of 128 threads are resident per SM (60 registers): ~8 waves, so the last one costs little
 template <typename E>
 __global__ void __launch_bounds__(128) gemv_t_kernel(int M, int K, int N, double alpha, const E* __restrict__ A, int64_t lda,
                                                      int64_t sA, const E* __restrict__ X, int64_t ldx, int64_t sX, double beta,
@@ -143,7 +146,19 @@ __global__ void __launch_bounds__(128) gemv_t_kernel(int M, int K, int N, double
   E acc[GT_NMAX];
 #pragma unroll
   for (int n = 0; n < GT_NMAX; ++n) acc[n] = e_zero<E>();
-  for (int m = m0; m < m1; ++m) {
+  int m = m0;
+  for (; m + GT_UNROLL <= m1; m += GT_UNROLL) {  // GT_UNROLL independent loads in flight per thread
+    E av[GT_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GT_UNROLL; ++u) av[u] = __ldcs(a + (int64_t)(m + u) * lda);
+#pragma unroll
+    for (int u = 0; u < GT_UNROLL; ++u) {
+#pragma unroll
+      for (int n = 0; n < GT_NMAX; ++n)
+        if (n < N) acc[n] = e_fma(av[u], x[(int64_t)(m + u) * ldx + n], acc[n]);
+    }
+  }
+  for (; m < m1; ++m) {
     const E av = a[(int64_t)m * lda];
 #pragma unroll
     for (int n = 0; n < GT_NMAX; ++n)
@@ -159,6 +174,60 @@ __global__ void __launch_bounds__(128) gemv_t_kernel(int M, int K, int N, double
     for (int n = 0; n < GT_NMAX; ++n)
       if (n < N) e_atomic_add(&c[n], e_scale(alpha, acc[n]));
   }
+}
+// real case with 16-byte aligned rows: two adjacent columns per thread (a CTA row-read is 2 KB contiguous)
+__global__ void __launch_bounds__(128) gemv_t_pair_kernel(int M, int K, int N, double alpha, const double* __restrict__ A,
+                                                          int64_t lda, int64_t sA, const double* __restrict__ X, int64_t ldx,
+                                                          int64_t sX, double beta, double* __restrict__ C, int64_t ldc,
+                                                          int64_t sC, int rows_per_split) {
+  const int k = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int64_t b = blockIdx.y;
+  const int m0 = blockIdx.z * rows_per_split, m1 = min(M, m0 + rows_per_split);
+  if (k >= K) return;  // K is even here
+  const double* a = A + b * sA + k;
+  const double* x = X + b * sX;
+  double acc0[GT_NMAX], acc1[GT_NMAX];
+#pragma unroll
+  for (int n = 0; n < GT_NMAX; ++n) acc0[n] = acc1[n] = 0.0;
+  int m = m0;
+  for (; m + GT_UNROLL <= m1; m += GT_UNROLL) {
+    double2 av[GT_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GT_UNROLL; ++u) av[u] = __ldcs(reinterpret_cast<const double2*>(a + (int64_t)(m + u) * lda));
+#pragma unroll
+    for (int u = 0; u < GT_UNROLL; ++u) {
+#pragma unroll
+      for (int n = 0; n < GT_NMAX; ++n)
+        if (n < N) {
+          const double xv = x[(int64_t)(m + u) * ldx + n];
+          acc0[n] = fma(av[u].x, xv, acc0[n]);
+          acc1[n] = fma(av[u].y, xv, acc1[n]);
+        }
+    }
+  }
+  for (; m < m1; ++m) {
+    const double2 av = *reinterpret_cast<const double2*>(a + (int64_t)m * lda);
+#pragma unroll
+    for (int n = 0; n < GT_NMAX; ++n)
+      if (n < N) {
+        const double xv = x[(int64_t)m * ldx + n];
+        acc0[n] = fma(av.x, xv, acc0[n]);
+        acc1[n] = fma(av.y, xv, acc1[n]);
+      }
+  }
+  double* c0 = C + b * sC + (int64_t)k * ldc;
+  double* c1 = c0 + ldc;
+#pragma unroll
+  for (int n = 0; n < GT_NMAX; ++n)
+    if (n < N) {
+      if (gridDim.z == 1) {
+        c0[n] = (beta != 0.0) ? alpha * acc0[n] + beta * c0[n] : alpha * acc0[n];
+        c1[n] = (beta != 0.0) ? alpha * acc1[n] + beta * c1[n] : alpha * acc1[n];
+      } else {
+        atomicAdd(&c0[n], alpha * acc0[n]);
+        atomicAdd(&c1[n], alpha * acc1[n]);
+      }
+    }
 }
 template <typename E>
 __global__ void gemv_t_scale_kernel(int K, int N, double beta, E* __restrict__ C, int64_t ldc, int64_t sC) {
@@ -270,10 +339,12 @@ static int gemv_t_impl(cudaStream_t st, int M, int K, int N, double alpha, const
     const int nn = std::min(GT_NMAX, N - n0);
     for (int b0 = 0; b0 < batch; b0 += 65535) {
       const int nb = std::min(65535, batch - b0);
-      const int tiles = (K + 127) / 128;
-      // few CTAs (the upper tree levels): split the rows so that every SM has work
+      const bool pair = std::is_same<E, double>::value && K % 2 == 0 && vec_ok(A, lda, sA);
+      const int tiles = pair ? (K / 2 + 127) / 128 : (K + 127) / 128;
+      // few CTAs (the upper tree levels): split the rows (>= 128 per CTA) into ~8 waves of CTAs (profiles/r02_hbm_kernels_summary.txt)
       int splits = 1;
-      if ((int64_t)tiles * nb < 296 && M >= 512) splits = (int)std::min<int64_t>((M + 255) / 256, 296 / ((int64_t)tiles * nb) + 1);
+      if ((int64_t)tiles * nb < GT_TARGET_CTAS && M >= 256)
+        splits = (int)std::min<int64_t>((M + 127) / 128, (GT_TARGET_CTAS + (int64_t)tiles * nb - 1) / ((int64_t)tiles * nb));
       const int rps = (M + splits - 1) / splits;
       const E* Ab = A + (int64_t)b0 * sA;
       const E* Xb = X + (int64_t)b0 * sX + n0;
@@ -281,7 +352,12 @@ static int gemv_t_impl(cudaStream_t st, int M, int K, int N, double alpha, const
       if (splits > 1) {
         gemv_t_scale_kernel<E><<<dim3((unsigned)std::min<int64_t>(((int64_t)K * nn + 255) / 256, 256), nb), 256, 0, st>>>(K, nn, beta, Cb, ldc, sC);
       }
-      gemv_t_kernel<E><<<dim3(tiles, nb, splits), 128, 0, st>>>(M, K, nn, alpha, Ab, lda, sA, Xb, ldx, sX, beta, Cb, ldc, sC, rps);
+      if (pair)
+        gemv_t_pair_kernel<<<dim3(tiles, nb, splits), 128, 0, st>>>(
+            M, K, nn, alpha, reinterpret_cast<const double*>(Ab), lda, sA, reinterpret_cast<const double*>(Xb), ldx, sX, beta,
+            reinterpret_cast<double*>(Cb), ldc, sC, rps);
+      else
+        gemv_t_kernel<E><<<dim3(tiles, nb, splits), 128, 0, st>>>(M, K, nn, alpha, Ab, lda, sA, Xb, ldx, sX, beta, Cb, ldc, sC, rps);
     }
   }
   HPS_LAUNCH_CHECK("gemv_t_kernel");

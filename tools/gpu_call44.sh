@@ -5,5 +5,4 @@ mkdir -p gpurun_out
 cd "$GRAFT_REPO_ROOT"
 timeout 120 python tools/one_gemv_t.py 2>&1 | tail -5
 timeout 300 ncu --set full --clock-control none -k regex:"gemv_t_kernel" -s 2 -c 1 -o gpurun_out/c44_gemv_t python tools/one_gemv_t.py > gpurun_out/c44_ncu_gemv_t.log 2>&1; echo "ncu1 rc=$?"
-timeout 400 ncu --set full --clock-control none -k regex:"panel_cycle_kernel" -s 2 -c 1 -o gpurun_out/c44_panel_cycle python bench.py --steps 1 --warmup 0 --factored 0 --host-resident 0 --other-configs 0 > gpurun_out/c44_ncu_cycle.log 2>&1; echo "ncu2 rc=$?"
 ls -la gpurun_out/*.ncu-rep
