@@ -7,6 +7,7 @@
 //   Y = [P ; Y_int],  v = [0 ; v_int],  T = Q Y,  h = Q v.
 // The solve runs in place inside the caller's Y and v buffers.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -160,6 +161,91 @@ __global__ void __launch_bounds__(256) assemble_kernel(AssembleArgs g) {
       }
       if (b < n_b) out_ie[b] = val; else out_ii[b - n_b] = val;
     }
+  }
+}
+
+// 3D operators without mixed derivatives: a row has only the 3p-2 non-zeros on the three grid lines through its point, and
+// assemble_kernel spends ~40 instructions per ZERO it writes (issue-bound at 0.44 of HBM, profiles/r02_hbm_kernels_summary.txt).
+// Here AL_ROWS rows are zero-filled with 16-byte stores, a barrier orders them before the scatter of the non-zeros, which
+// uses the same fma sequences as assemble_kernel (bit-identical entries).  inv[] maps a natural (i,j,k) to its leaf-ordered column.
+constexpr int AL_ROWS = 4;
+__device__ __forceinline__ void zero_fill(double* ptr, int64_t n) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0) {
+    double2* p2 = reinterpret_cast<double2*>(ptr);
+    const int64_t n2 = n >> 1;
+    for (int64_t e = threadIdx.x; e < n2; e += blockDim.x) p2[e] = make_double2(0.0, 0.0);
+    if ((n & 1) && threadIdx.x == 0) ptr[n - 1] = 0.0;
+  } else {
+    for (int64_t e = threadIdx.x; e < n; e += blockDim.x) ptr[e] = 0.0;
+  }
+}
+__global__ void __launch_bounds__(256) assemble3_lines_kernel(AssembleArgs g) {
+  __shared__ double D[MAX_P * MAX_P];
+  __shared__ double D2[MAX_P * MAX_P];
+  extern __shared__ __align__(4) unsigned char dyn_inv[];
+  unsigned short* inv = reinterpret_cast<unsigned short*>(dyn_inv);  // [p^3]
+  const int p = g.geo.p, n_c = g.geo.n_c, n_i = g.geo.n_i, n_b = g.geo.n_b, q = p - 2;
+  for (int t = threadIdx.x; t < p * p; t += blockDim.x) D[t] = g.D1[t];
+  for (int b = threadIdx.x; b < n_c; b += blockDim.x) {
+    int i, j, k;
+    decode3(b, p, i, j, k);
+    inv[(i * p + j) * p + k] = (unsigned short)b;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < p * p; t += blockDim.x) {
+    const int r = t / p, c = t - r * p;
+    double s = 0.0;
+    for (int u = 0; u < p; ++u) s = fma(D[r * p + u], D[u * p + c], s);
+    D2[t] = s;
+  }
+  __syncthreads();
+  const int leaf = blockIdx.y;
+  const int64_t leaf_row0 = (int64_t)leaf * n_i;
+  const int per_row = 3 * p;
+  for (int a0 = blockIdx.x * AL_ROWS; a0 < n_i; a0 += gridDim.x * AL_ROWS) {
+    const int nr = min(AL_ROWS, n_i - a0);
+    zero_fill(g.Aie + (leaf_row0 + a0) * n_b, (int64_t)nr * n_b);  // the nr rows are contiguous
+    zero_fill(g.Aii + (leaf_row0 + a0) * n_i, (int64_t)nr * n_i);
+    __syncthreads();  // the zeros are ordered before the non-zeros that other threads store into the same rows
+    for (int task = threadIdx.x; task < nr * per_row; task += blockDim.x) {
+      const int r = task / per_row, rem = task - r * per_row, line = rem / p, idx = rem - line * p;
+      const int a = a0 + r, row = n_b + a;
+      const int i = 1 + a / (q * q), ar = a % (q * q), j = 1 + ar / q, k = 1 + ar % q;
+      auto coef = [&](int c) -> double {
+        const int sl = g.slot[c];
+        return sl < 0 ? 0.0 : g.coeffs[((int64_t)sl * g.n_leaves + leaf) * n_c + row];
+      };
+      double val;
+      int col;
+      if (line == 0) {  // x line (and the diagonal entry)
+        if (idx == i) {
+          val = fma(coef(0), D2[i * p + i], 0.0);
+          val = fma(coef(2), D2[j * p + j], val);
+          val = fma(coef(5), D2[k * p + k], val);
+          val = fma(coef(6), D[i * p + i], val);
+          val = fma(coef(7), D[j * p + j], val);
+          val = fma(coef(8), D[k * p + k], val);
+          val += coef(9);
+        } else {
+          val = fma(coef(0), D2[i * p + idx], 0.0);
+          val = fma(coef(6), D[i * p + idx], val);
+        }
+        col = inv[(idx * p + j) * p + k];
+      } else if (line == 1) {  // y line
+        if (idx == j) continue;
+        val = fma(coef(2), D2[j * p + idx], 0.0);
+        val = fma(coef(7), D[j * p + idx], val);
+        col = inv[(i * p + idx) * p + k];
+      } else {  // z line
+        if (idx == k) continue;
+        val = fma(coef(5), D2[k * p + idx], 0.0);
+        val = fma(coef(8), D[k * p + idx], val);
+        col = inv[(i * p + j) * p + idx];
+      }
+      if (col < n_b) g.Aie[(leaf_row0 + a) * n_b + col] = val;
+      else g.Aii[(leaf_row0 + a) * n_i + (col - n_b)] = val;
+    }
+    // no barrier here: the next pass writes other rows
   }
 }
 
@@ -540,8 +626,18 @@ int local_solve_dtn(cudaStream_t st, int dim, int n_leaves, int p, int q, int n_
     const int bx = std::max(1, std::min(geo.n_i, (148 * 16 + n_leaves - 1) / n_leaves));
     const size_t idx_bytes = 4 * (size_t)geo.n_c;
     prof_begin(PROF_ASSEMBLE, st, 8.0 * n_leaves * (double)total);
-    if (dim == 3) assemble_kernel<3><<<dim3(bx, n_leaves), 256, idx_bytes, st>>>(aa);
-    else assemble_kernel<2><<<dim3(bx, n_leaves), 256, idx_bytes, st>>>(aa);
+    const bool mixed = aa.slot[1] >= 0 || aa.slot[3] >= 0 || aa.slot[4] >= 0;
+    static const bool lines_off = std::getenv("HPS_ASSEMBLE_LINES") && std::atoi(std::getenv("HPS_ASSEMBLE_LINES")) == 0;
+    if (dim == 3 && !mixed && 2 * (size_t)geo.n_c <= 30000 && !lines_off) {
+      // ~10 waves of CTAs, each with a few passes of AL_ROWS rows
+      const int passes = (geo.n_i + AL_ROWS - 1) / AL_ROWS;
+      const int bl = std::max(1, std::min(passes, (148 * 8 * 10 + n_leaves - 1) / n_leaves));
+      assemble3_lines_kernel<<<dim3(bl, n_leaves), 256, 2 * (size_t)geo.n_c, st>>>(aa);
+    } else if (dim == 3) {
+      assemble_kernel<3><<<dim3(bx, n_leaves), 256, idx_bytes, st>>>(aa);
+    } else {
+      assemble_kernel<2><<<dim3(bx, n_leaves), 256, idx_bytes, st>>>(aa);
+    }
     prof_end(PROF_ASSEMBLE, st);
     HPS_LAUNCH_CHECK("assemble_kernel");
     const int64_t tot2 = (int64_t)geo.n_b * n_g + (int64_t)geo.n_c * n_src;

@@ -473,36 +473,40 @@ PanelCycles make_cycles(const Topo& tp) {
   pc.start[pc.n_cyc] = (signed char)at;
   return pc;
 }
-constexpr int CYC_CHUNK = 1024;
-__global__ void __launch_bounds__(256) panel_cycle_kernel(PanelCycles pc, int m, int chunks, double* __restrict__ S,
+// A row of a panel is cut into chunks of tpr*E elements: tpr threads (a power of two, <= 256) own E elements each, and a CTA
+// holds 256/tpr rows, so that small panels (m = 100: tpr 128, E 1) do not idle most of the CTA (ncu r02: the m = 100 launch
+// was issue-bound with 100 of 1024 element slots in use).
+template <int E>
+__global__ void __launch_bounds__(256) panel_cycle_kernel(PanelCycles pc, int m, int chunks, int tpr, double* __restrict__ S,
                                                           int64_t ld, int64_t rows) {
   const int cyc = blockIdx.x / chunks, ch = blockIdx.x - cyc * chunks;
   const int b = pc.start[cyc], e = pc.start[cyc + 1];
-  const int t0 = ch * CYC_CHUNK + threadIdx.x;
-  for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+  const int rpc = 256 / tpr, r_in = threadIdx.x / tpr, tt = threadIdx.x - r_in * tpr;
+  const int t0 = ch * tpr * E + tt;
+  for (int64_t row = (int64_t)blockIdx.y * rpc + r_in; row < rows; row += (int64_t)gridDim.y * rpc) {
     double* base = S + row * ld;
-    double tmp[4];
+    double tmp[E];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = t0 + 256 * i;
+    for (int i = 0; i < E; ++i) {
+      const int t = t0 + tpr * i;
       if (t < m) tmp[i] = base[pc.elem[b] * m + t];
     }
     for (int k = b; k + 1 < e; ++k) {
-      double v[4];
+      double v[E];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int t = t0 + 256 * i;
+      for (int i = 0; i < E; ++i) {
+        const int t = t0 + tpr * i;
         if (t < m) v[i] = base[pc.elem[k + 1] * m + t];
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int t = t0 + 256 * i;
+      for (int i = 0; i < E; ++i) {
+        const int t = t0 + tpr * i;
         if (t < m) base[pc.elem[k] * m + t] = v[i];
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = t0 + 256 * i;
+    for (int i = 0; i < E; ++i) {
+      const int t = t0 + tpr * i;
       if (t < m) base[pc.elem[e - 1] * m + t] = tmp[i];
     }
   }
@@ -510,12 +514,21 @@ __global__ void __launch_bounds__(256) panel_cycle_kernel(PanelCycles pc, int m,
 int unsort_panels(const Topo& tp, cudaStream_t st, int m, double* S, int64_t ld, int64_t rows) {
   const PanelCycles pc = make_cycles(tp);
   if (pc.n_cyc == 0 || rows <= 0) return 0;
-  const int chunks = (m + CYC_CHUNK - 1) / CYC_CHUNK;
-  dim3 grid(pc.n_cyc * chunks, (unsigned)std::min<int64_t>(rows, 65535));
   int moved = 0;  // panels that change place: each is read once and written once
   for (int e = 0; e < tp.n_ext; ++e) moved += tp.ext_pos[e] != e;
   prof_begin(PROF_UNSORT, st, 16.0 * (double)rows * moved * m);
-  panel_cycle_kernel<<<grid, 256, 0, st>>>(pc, m, chunks, S, ld, rows);
+  if (m <= 256) {
+    int tpr = 32;
+    while (tpr < m) tpr *= 2;
+    const int rpc = 256 / tpr;
+    dim3 grid(pc.n_cyc, (unsigned)std::min<int64_t>((rows + rpc - 1) / rpc, 65535));
+    panel_cycle_kernel<1><<<grid, 256, 0, st>>>(pc, m, 1, tpr, S, ld, rows);
+  } else {
+    const int tpr = m > 512 ? 256 : 128;
+    const int chunks = (m + 4 * tpr - 1) / (4 * tpr), rpc = 256 / tpr;
+    dim3 grid(pc.n_cyc * chunks, (unsigned)std::min<int64_t>((rows + rpc - 1) / rpc, 65535));
+    panel_cycle_kernel<4><<<grid, 256, 0, st>>>(pc, m, chunks, tpr, S, ld, rows);
+  }
   prof_end(PROF_UNSORT, st);
   HPS_LAUNCH_CHECK("panel_cycle_kernel");
   return 0;
