@@ -116,6 +116,17 @@ class ClockSampler:
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
+            return
+        # nvidia-smi needs a few hundred ms to initialise NVML, during which kernel launches stall: wait for its first
+        # sample here, BEFORE the timed region starts, so that only the steady 200 ms polling runs inside it
+        self.first = ""
+        try:
+            import select
+
+            if select.select([self.proc.stdout], [], [], 3.0)[0]:
+                self.first = self.proc.stdout.readline()
+        except (OSError, ValueError):
+            pass
 
     def stop(self):
         if self.proc is None:
@@ -127,7 +138,7 @@ class ClockSampler:
             self.proc.kill()
             out, _ = self.proc.communicate()
         sm, smax, reasons = [], [], set()
-        for line in out.strip().splitlines():
+        for line in (getattr(self, "first", "") + out).strip().splitlines():
             f = [t.strip() for t in line.split(",")]
             if len(f) < 9:
                 continue
@@ -339,9 +350,9 @@ class Runner:
 
     def timed(self, pb, g, to_host, steps, sampler=None, host_device=None):
         torch = self.torch
-        self.barrier()
         if sampler:
-            sampler.start()
+            sampler.start()  # returns once the sampler is polling; the other ranks wait in the barrier
+        self.barrier()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
