@@ -94,8 +94,9 @@ __device__ __forceinline__ double entry2d(const AssembleArgs& g, const double* D
 
 // blockIdx.y = leaf, blockIdx.x strides over interior rows; the (i,j,k) of every column is decoded
 // once per CTA into shared memory, the row's once per row; structurally-zero entries (all but ~3p per row
-// when no mixed derivative is present) skip the coefficient arithmetic, so the kernel is bound by its
-// 13.8 MB/leaf of writes.
+// when no mixed derivative is present) skip the coefficient arithmetic.  Measured (ncu, round 2): ISSUE-bound, ~40
+// instructions per structural zero, 0.44 of the HBM copy rate - the general path (2D, mixed derivatives);
+// 3D operators without mixed derivatives go through assemble3_lines_kernel below.
 template <int DIM>
 __global__ void __launch_bounds__(256) assemble_kernel(AssembleArgs g) {
   __shared__ double D[MAX_P * MAX_P];
